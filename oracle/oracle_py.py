@@ -1,0 +1,254 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front ends for the two CPU checkers.
+
+  Oracle : oracle/liboracle.so   the from-scratch restatement (rsm_oracle.cpp)
+  Ref    : oracle/_ref/libref.so the reference's own headers compiled in place (ref_driver.cpp);
+           present only where /root/reference was available at build time (it travels to the
+           GPU box as a built file).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Both classes expose the same calls on the same flat numpy inputs so a test
+can swap one for the other.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+c_d = ctypes.c_double
+c_i = ctypes.c_int
+c_l = ctypes.c_long
+c_p = ctypes.c_void_p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ref_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref.so"))
+
+
+def pack_scans(pts_list):
+    n_pts = np.array([len(p) for p in pts_list], dtype=np.int32)
+    if len(pts_list):
+        pts = _f64(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in pts_list], axis=0))
+    else:
+        pts = np.zeros((0, 2), dtype=np.float64)
+    return n_pts, pts
+
+
+class Oracle:
+    """The restatement.  A 'map' here is (float32 grid [size_y, size_x], GridSpec)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/liboracle.so missing: run __graft_entry__.build()")
+        L = ctypes.CDLL(path)
+        L.orc_blur_kernel.restype = c_i
+        L.orc_blur_kernel.argtypes = [c_d, c_d, c_p, c_i]
+        L.orc_grid_build.restype = c_i
+        L.orc_grid_build.argtypes = [c_p, c_i, c_i, ctypes.c_float, c_d, c_d, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_i]
+        L.orc_world_to_map.argtypes = [c_d, c_d, c_d, c_p, c_p]
+        L.orc_map_to_world.argtypes = [c_d, c_d, c_d, c_p, c_p]
+        L.orc_pass_geometry.argtypes = [c_p, c_i, c_d, c_p, c_p, c_p]
+        L.orc_scores.restype = c_i
+        L.orc_scores.argtypes = [c_p, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
+        L.orc_match.restype = c_d
+        L.orc_match.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
+        L.orc_match_chain.restype = c_d
+        L.orc_match_chain.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        self.L = L
+
+    def blur_kernel(self, sigma, res):
+        k = np.zeros(21 * 21, dtype=np.float64)
+        h = self.L.orc_blur_kernel(sigma, res, k.ctypes.data, k.size)
+        if h < 0:
+            return -1, None
+        n = 2 * h + 1
+        return h, k[: n * n].reshape(n, n).copy()
+
+    def build_grid(self, g, base_pts, base_poses):
+        grid = np.empty((g.size_y, g.size_x), dtype=np.float32)
+        n_pts, pts = pack_scans(base_pts)
+        poses = _f64(base_poses)
+        rc = self.L.orc_grid_build(grid.ctypes.data, g.size_x, g.size_y, g.default_prob, g.sigma, g.res,
+                                   g.occu_offset, g.off_x, g.off_y, len(base_pts), n_pts.ctypes.data,
+                                   pts.ctypes.data, poses.ctypes.data, int(g.use_blur))
+        if rc:
+            raise RuntimeError("orc_grid_build rc=%d" % rc)
+        return grid
+
+    def world_to_map(self, g, w):
+        out = np.zeros(3)
+        w = _f64(w)
+        self.L.orc_world_to_map(1.0 / g.res, g.off_x, g.off_y, w.ctypes.data, out.ctypes.data)
+        return out
+
+    def map_to_world(self, g, m):
+        out = np.zeros(3)
+        m = _f64(m)
+        self.L.orc_map_to_world(1.0 / g.res, g.off_x, g.off_y, m.ctypes.data, out.ctypes.data)
+        return out
+
+    def geometry(self, g, param, P, center_map):
+        out = np.zeros(5, dtype=np.int64)
+        dout = np.zeros(4)
+        cell_len = 1 / (1.0 / g.res)
+        param, center_map = _f64(param), _f64(center_map)
+        self.L.orc_pass_geometry(param.ctypes.data, P, cell_len, center_map.ctypes.data, out.ctypes.data, dout.ctypes.data)
+        return dict(n_ang=int(out[0]), n_xy=int(out[1]), step=int(out[2]), divisor=int(out[3]), visited=int(out[4]),
+                    start_x=dout[0], start_y=dout[1], factor=dout[2], start_angle=dout[3])
+
+    def scores(self, grid, g, pts, param, center_map, dump_indices=False):
+        pts, param, center_map = _f64(pts), _f64(param), _f64(center_map)
+        geo = self.geometry(g, param, len(pts), center_map)
+        n = geo["n_ang"] * geo["n_xy"] ** 2
+        score = np.empty(n, dtype=np.float64)
+        gx = gy = None
+        if dump_indices:
+            gx = np.empty((n, geo["visited"]), dtype=np.int32)
+            gy = np.empty((n, geo["visited"]), dtype=np.int32)
+        cell_len = 1 / (1.0 / g.res)
+        self.L.orc_scores(grid.ctypes.data, g.size_x, cell_len, len(pts), pts.ctypes.data, param.ctypes.data,
+                          center_map.ctypes.data, score.ctypes.data, _ptr(gx), _ptr(gy))
+        return (score, gx, gy) if dump_indices else score
+
+    def match(self, grid, g, pts, param, pose_world, cov=None):
+        pts, param = _f64(pts), _f64(param)
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        best = np.zeros(4)
+        navg = c_l(0)
+        sec = c_d(0)
+        r = self.L.orc_match(grid.ctypes.data, g.size_x, g.size_y, 1.0 / g.res, g.off_x, g.off_y, len(pts),
+                             pts.ctypes.data, param.ctypes.data, pose.ctypes.data, cov.ctypes.data,
+                             best.ctypes.data, ctypes.byref(navg), ctypes.byref(sec))
+        return dict(response=r, pose=pose, cov=cov, best_map=best, n_avg=navg.value, seconds=sec.value)
+
+    def match_chain(self, grid, g, pts, params, pose_world, cov=None, use_fine=True):
+        pts = _f64(pts)
+        params = _f64(np.concatenate(params))
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        resp = np.zeros(3)
+        sec = c_d(0)
+        r = self.L.orc_match_chain(grid.ctypes.data, g.size_x, g.size_y, 1.0 / g.res, g.off_x, g.off_y, len(pts),
+                                   pts.ctypes.data, params.ctypes.data, int(use_fine), pose.ctypes.data,
+                                   cov.ctypes.data, resp.ctypes.data, ctypes.byref(sec))
+        return dict(score=r, pose=pose, cov=cov, responses=resp, seconds=sec.value)
+
+
+class Ref:
+    """The reference's own code.  A 'map' here is an opaque handle to a live ScanMatchMap."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libref.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libref.so missing (reference not built here)")
+        L = ctypes.CDLL(path)
+        L.ref_map_create.restype = c_p
+        L.ref_map_create.argtypes = [c_d, c_i, c_i, c_d, c_d, c_d, ctypes.c_float, c_d]
+        L.ref_map_destroy.argtypes = [c_p]
+        L.ref_map_set_offset.argtypes = [c_p, c_d, c_d]
+        L.ref_map_build.restype = c_i
+        L.ref_map_build.argtypes = [c_p, c_i, c_p, c_p, c_p, c_i]
+        L.ref_map_size.argtypes = [c_p, c_p, c_p]
+        L.ref_map_cell_length.restype = c_d
+        L.ref_map_cell_length.argtypes = [c_p]
+        L.ref_map_read.argtypes = [c_p, c_p]
+        L.ref_map_write.argtypes = [c_p, c_p]
+        L.ref_world_to_map.argtypes = [c_p, c_p, c_p]
+        L.ref_map_to_world.argtypes = [c_p, c_p, c_p]
+        L.ref_candidate_count.restype = c_l
+        L.ref_candidate_count.argtypes = [c_p]
+        L.ref_match_candidates.restype = c_d
+        L.ref_match_candidates.argtypes = [c_p, c_i, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
+        L.ref_match.restype = c_d
+        L.ref_match.argtypes = [c_p, c_i, c_p, c_p, c_p, c_p, c_p]
+        L.ref_match_chain.restype = c_d
+        L.ref_match_chain.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        L.ref_blur_kernel.restype = c_i
+        L.ref_blur_kernel.argtypes = [c_d, c_d, c_p, c_i]
+        self.L = L
+
+    def blur_kernel(self, sigma, res):
+        k = np.zeros(21 * 21, dtype=np.float64)
+        h = self.L.ref_blur_kernel(sigma, res, k.ctypes.data, k.size)
+        if h < 0:
+            return -1, None
+        n = 2 * h + 1
+        return h, k[: n * n].reshape(n, n).copy()
+
+    def create_map(self, g):
+        return self.L.ref_map_create(g.res, g.size_x, g.size_y, g.off_x, g.off_y, g.sigma, g.default_prob, g.occu_offset)
+
+    def destroy_map(self, m):
+        self.L.ref_map_destroy(m)
+
+    def build_map(self, m, g, base_pts, base_poses):
+        n_pts, pts = pack_scans(base_pts)
+        poses = _f64(base_poses)
+        rc = self.L.ref_map_build(m, len(base_pts), n_pts.ctypes.data, pts.ctypes.data, poses.ctypes.data, int(g.use_blur))
+        if rc:
+            raise RuntimeError("ref_map_build rc=%d" % rc)
+
+    def read_map(self, m, g):
+        out = np.empty((g.size_y, g.size_x), dtype=np.float32)
+        self.L.ref_map_read(m, out.ctypes.data)
+        return out
+
+    def write_map(self, m, grid):
+        grid = np.ascontiguousarray(grid, dtype=np.float32)
+        self.L.ref_map_write(m, grid.ctypes.data)
+
+    def world_to_map(self, m, w):
+        out = np.zeros(3)
+        w = _f64(w)
+        self.L.ref_world_to_map(m, w.ctypes.data, out.ctypes.data)
+        return out
+
+    def map_to_world(self, m, p):
+        out = np.zeros(3)
+        p = _f64(p)
+        self.L.ref_map_to_world(m, p.ctypes.data, out.ctypes.data)
+        return out
+
+    def candidates(self, m, pts, param, center_map):
+        """Sorted candidate list exactly as the reference leaves it after a pass."""
+        pts, param, center_map = _f64(pts), _f64(param), _f64(center_map)
+        n = self.L.ref_candidate_count(param.ctypes.data)
+        cx, cy, ca, cs = (np.empty(n) for _ in range(4))
+        ci = np.empty(n, dtype=np.int32)
+        nout = c_l(0)
+        best = np.zeros(4)
+        self.L.ref_match_candidates(m, len(pts), pts.ctypes.data, param.ctypes.data, center_map.ctypes.data, n,
+                                    cx.ctypes.data, cy.ctypes.data, ca.ctypes.data, ci.ctypes.data, cs.ctypes.data,
+                                    ctypes.byref(nout), best.ctypes.data)
+        assert nout.value == n, (nout.value, n)
+        return dict(x=cx, y=cy, angle=ca, angle_index=ci, score=cs, best=best)
+
+    def match(self, m, pts, param, pose_world, cov=None):
+        pts, param = _f64(pts), _f64(param)
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        sec = c_d(0)
+        r = self.L.ref_match(m, len(pts), pts.ctypes.data, param.ctypes.data, pose.ctypes.data, cov.ctypes.data, ctypes.byref(sec))
+        return dict(response=r, pose=pose, cov=cov, seconds=sec.value)
+
+    def match_chain(self, m, pts, params, pose_world, cov=None, use_fine=True):
+        pts = _f64(pts)
+        params = _f64(np.concatenate(params))
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        resp = np.zeros(3)
+        sec = c_d(0)
+        r = self.L.ref_match_chain(m, len(pts), pts.ctypes.data, params.ctypes.data, int(use_fine), pose.ctypes.data,
+                                   cov.ctypes.data, resp.ctypes.data, ctypes.byref(sec))
+        return dict(score=r, pose=pose, cov=cov, responses=resp, seconds=sec.value)

@@ -1,0 +1,454 @@
+// TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's correlative scan matcher
+// hot path, written from scratch on flat arrays.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load liboracle.so; nothing under
+// roborts_edu_slam_b200/ may import, link or execute it.
+//
+// Pinning: the reference holds no golden vectors for this path.  The
+// restatement is pinned against the reference's own headers compiled in place
+// (oracle/_ref/libref.so, ref_driver.cpp) by tests/test_oracle_vs_reference.py, and against
+// the fixtures that build wrote to tests/golden/ (used where /root/reference is absent).
+//
+// C++ rather than C for one reason: the reference's winner is defined by libstdc++'s unstable
+// std::sort (correlate_scan_matcher.h:607-608); the same std::sort is used here on
+// (score, index) pairs -- the permutation introsort produces depends only on the comparison
+// outcomes, not on the element type.
+//
+// All citations are file:line under /root/reference/src.  Compiled with -ffp-contract=off:
+// every a*b+c below is two rounded operations, as on the reference's baseline x86-64 build.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const double kMaxVariance = 500.0;      // util/slam_util.h:57
+const double kDoubleTolerance = 1e-06;  // util/slam_util.h:59
+const int kMaxVarianceUse = 20;         // scan_match/correlate_scan_matcher.h:1033
+
+// util/slam_util.h:70-73
+inline bool DoubleEqual(double a, double b, double tol = kDoubleTolerance) {
+  const double delta = a - b;
+  return delta < 0.0 ? delta >= -std::fabs(tol) : delta <= std::fabs(tol);
+}
+// util/slam_util.h:75-77
+inline double Round(double v) { return v >= 0.0 ? std::floor(v + 0.5) : std::ceil(v - 0.5); }
+
+struct Param {
+  double size, sres, aoff, ares, threshold;
+  int use_point_size;
+  bool use_center_penalty;
+  int type;  // 0 coarse, 1 fine, 2 super, 3 fast
+};
+
+Param ReadParam(const double* p) {
+  Param q;
+  q.size = p[0]; q.sres = p[1]; q.aoff = p[2]; q.ares = p[3]; q.threshold = p[4];
+  q.use_point_size = static_cast<int>(p[5]);
+  q.use_center_penalty = p[6] != 0.0;
+  q.type = static_cast<int>(p[7]);
+  return q;
+}
+
+// map/grid_map_base.h:68-93 with Eigen's evaluation order (see oracle/standin/Eigen/Geometry):
+// world_to_map = Scaling(s,s) * Translation(off): linear diag(s,s), translation (s*offx, s*offy);
+// Affine * v = translation + (l00*x + l01*y).
+struct MapTf {
+  double s, tx, ty;          // world -> map
+  double i00, i01, i10, i11, itx, ity;  // map -> world
+};
+
+MapTf MakeTf(double scale, double off_x, double off_y) {
+  MapTf t;
+  t.s = scale;
+  t.tx = scale * off_x;
+  t.ty = scale * off_y;
+  const double l00 = scale, l01 = 0.0, l10 = 0.0, l11 = scale;
+  const double det = l00 * l11 - l10 * l01;
+  const double invdet = 1.0 / det;
+  t.i00 = l11 * invdet;
+  t.i10 = -l10 * invdet;
+  t.i01 = -l01 * invdet;
+  t.i11 = l00 * invdet;
+  t.itx = (-t.i00) * t.tx + (-t.i01) * t.ty;
+  t.ity = (-t.i10) * t.tx + (-t.i11) * t.ty;
+  return t;
+}
+inline void WorldToMap(const MapTf& t, const double* w, double* m) {
+  m[0] = t.tx + (t.s * w[0] + 0.0 * w[1]);
+  m[1] = t.ty + (0.0 * w[0] + t.s * w[1]);
+  m[2] = w[2];
+}
+inline void MapToWorld(const MapTf& t, const double* m, double* w) {
+  w[0] = t.itx + (t.i00 * m[0] + t.i01 * m[1]);
+  w[1] = t.ity + (t.i10 * m[0] + t.i11 * m[1]);
+  w[2] = m[2];
+}
+
+struct Scored {
+  double score;
+  int index;
+};
+
+struct PassGeometry {
+  int n_ang, n_xy, step, divisor;
+  double start_x, start_y, factor, start_angle;
+};
+
+// correlate_scan_matcher.h:154,160-164 (angles), :538,546-548 (translations), :560-566 (beam stride)
+PassGeometry Geometry(const Param& q, int P, double cell_len, const double* center) {
+  PassGeometry g;
+  g.n_ang = static_cast<int>(std::floor(q.aoff * 2 / q.ares) + 1);
+  g.start_angle = center[2] - q.aoff;
+  g.n_xy = static_cast<int>(Round(q.size / q.sres) + 1);
+  g.start_x = center[0] - (q.size / cell_len) * 0.5;
+  g.start_y = center[1] - (q.size / cell_len) * 0.5;
+  g.factor = q.sres / cell_len;
+  int use = q.use_point_size;
+  if (P < 2 * use) { use = P; g.step = 1; } else { g.step = P / (use - 1); }
+  g.divisor = use;
+  return g;
+}
+
+// One brute-force pass: scores in candidate order k = (ia*n_xy + ix)*n_xy + iy, penalised.
+// correlate_scan_matcher.h:552-603, 637-662, 718-745.  serach_angle_size_/2 (== aoff*2/2) is
+// what the angle table receives (:526,536); aoff*2/2 == aoff exactly in binary floating point.
+void ScorePass(const float* grid, int size_x, double cell_len, int P, const double* pts,
+               const Param& q, const double* center, const PassGeometry& g, double* score,
+               int32_t* dump_gx, int32_t* dump_gy) {
+  std::vector<double> lx(P), ly(P);
+  const double half_range = (q.aoff * 2) / 2;
+  const double start_angle = center[2] - half_range;
+  for (int ia = 0; ia < g.n_ang; ++ia) {
+    const double angle = start_angle + ia * q.ares;
+    const double c = std::cos(angle), s = std::sin(angle);
+    for (int p = 0; p < P; ++p) {
+      lx[p] = c * pts[2 * p] - s * pts[2 * p + 1];
+      ly[p] = s * pts[2 * p] + c * pts[2 * p + 1];
+    }
+    for (int ix = 0; ix < g.n_xy; ++ix) {
+      const double x = g.start_x + ix * g.factor;
+      for (int iy = 0; iy < g.n_xy; ++iy) {
+        const double y = g.start_y + iy * g.factor;
+        const size_t k = (static_cast<size_t>(ia) * g.n_xy + ix) * g.n_xy + iy;
+        double sum = 0.0;
+        int v = 0;
+        for (int p = 0; p < P; p += g.step, ++v) {
+          const int gx = static_cast<int>(lx[p] + x + 0.5);
+          const int gy = static_cast<int>(ly[p] + y + 0.5);
+          if (dump_gx) {  // only for the index-parity test on tiny cases
+            const size_t V = (P + g.step - 1) / g.step;
+            dump_gx[k * V + v] = gx;
+            dump_gy[k * V + v] = gy;
+          }
+          sum += static_cast<double>(grid[static_cast<size_t>(gy) * size_x + gx]);
+        }
+        score[k] = sum / g.divisor;
+      }
+    }
+  }
+  if (!q.use_center_penalty) return;
+  const double gain = (q.type == 0) ? 0.4 : 0.2;  // :588-602, :760-761
+  for (int ia = 0; ia < g.n_ang; ++ia) {
+    const double angle = start_angle + ia * q.ares;
+    for (int ix = 0; ix < g.n_xy; ++ix) {
+      const double x = g.start_x + ix * g.factor;
+      for (int iy = 0; iy < g.n_xy; ++iy) {
+        const double y = g.start_y + iy * g.factor;
+        const size_t k = (static_cast<size_t>(ia) * g.n_xy + ix) * g.n_xy + iy;
+        if (DoubleEqual(score[k], 0.0)) continue;
+        const double dx = x - center[0], dy = y - center[1];
+        double d2 = dx * dx + dy * dy;
+        d2 *= (cell_len * cell_len);
+        double dp = 1.0 - (gain * d2 / (q.size / 2));
+        dp = std::max(dp, 0.5);
+        const double da = angle - center[2];
+        const double a2 = da * da;  // pow(x, 2)
+        double ap = 1.0 - (0.25 * a2 / 0.349);
+        ap = std::max(ap, 0.9);
+        score[k] = score[k] * (dp * ap);
+      }
+    }
+  }
+}
+
+struct Best {
+  double x, y, angle, score;
+};
+
+struct PassOut {
+  Best best;
+  double response;
+  long n_avg;
+};
+
+// Everything after the scores exist: sort (:607), FindBestCandidate (:670-710), covariance
+// (:835-858, :887-956, :965-1019), response clamp and pose write-back (:861-869).
+PassOut Finish(std::vector<Scored>& cand, const Param& q, const PassGeometry& g, double cell_len,
+               const double* center, double* cov /*row-major 3x3, in/out*/) {
+  const double start_angle = center[2] - (q.aoff * 2) / 2;
+  auto pose_of = [&](int k, double* x, double* y, double* a) {
+    const int iy = k % g.n_xy;
+    const int ix = (k / g.n_xy) % g.n_xy;
+    const int ia = k / (g.n_xy * g.n_xy);
+    *x = g.start_x + ix * g.factor;
+    *y = g.start_y + iy * g.factor;
+    *a = start_angle + ia * q.ares;
+  };
+  std::sort(cand.begin(), cand.end(), [](const Scored& a, const Scored& b) { return a.score > b.score; });
+
+  PassOut out;
+  Best best;
+  pose_of(cand[0].index, &best.x, &best.y, &best.angle);
+  best.score = cand[0].score;
+  double ax = 0.0, ay = 0.0, tx = 0.0, ty = 0.0, ssum = 0.0;
+  long count = 0;
+  for (const Scored& c : cand) {
+    if (!DoubleEqual(c.score, best.score, 1e-2)) break;
+    double x, y, a;
+    pose_of(c.index, &x, &y, &a);
+    ax += x * c.score;
+    ay += y * c.score;
+    tx += std::cos(a) * c.score;
+    ty += std::sin(a) * c.score;
+    ssum += c.score;
+    ++count;
+  }
+  if (count > 1) {
+    ax /= ssum; ay /= ssum; tx /= ssum; ty /= ssum;
+    best.x = ax; best.y = ay; best.angle = std::atan2(ty, tx);
+  }
+  out.best = best;
+  out.n_avg = count;
+
+  const double max_ang_var = 4 * (q.ares * q.ares);  // :801
+  auto C = [&](int r, int c) -> double& { return cov[3 * r + c]; };
+  auto positional = [&]() {  // :887-956
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C(r, c) = (r == c) ? 1.0 : 0.0;
+    if (best.score < kDoubleTolerance) {
+      C(0, 0) = kMaxVariance; C(1, 1) = kMaxVariance; C(2, 2) = max_ang_var;
+      return;
+    }
+    double vxx = 0.0, vxy = 0.0, vyy = 0.0, norm = 0.0;
+    const double bound = std::min(best.score - 0.1, 0.5);
+    int n = 0;
+    for (const Scored& c : cand) {
+      if (c.score > bound && n < kMaxVarianceUse) {
+        double x, y, a;
+        pose_of(c.index, &x, &y, &a);
+        norm += c.score;
+        vxx += ((x - best.x) * (x - best.x)) * c.score;
+        vxy += ((x - best.x) * (y - best.y) * c.score);
+        vyy += ((y - best.y) * (y - best.y)) * c.score;
+        ++n;
+      } else {
+        break;
+      }
+    }
+    if (norm > kDoubleTolerance) {
+      double xx = vxx / norm, xy = vxy / norm, yy = vyy / norm;
+      const double r = q.sres / cell_len;
+      const double min_var = 0.1 * (r * r);
+      xx = std::max(xx, min_var);
+      yy = std::max(yy, min_var);
+      const double m2 = cell_len * cell_len;
+      C(0, 0) = (xx * m2) / best.score;
+      C(0, 1) = (xy * m2) / best.score;
+      C(1, 0) = (xy * m2) / best.score;
+      C(1, 1) = (yy * m2) / best.score;
+      C(2, 2) = max_ang_var;
+    }
+    if (DoubleEqual(C(0, 0), 0.0)) C(0, 0) = kMaxVariance;
+    if (DoubleEqual(C(1, 1), 0.0)) C(1, 1) = kMaxVariance;
+  };
+  auto angular = [&]() {  // :965-1019
+    if (best.score < kDoubleTolerance) { C(2, 2) = max_ang_var; return; }
+    const double tol = q.sres / cell_len;
+    const double bound = std::min(best.score - 0.1, 0.5);
+    double norm = 0.0, acc = 0.0;
+    int n = 0;
+    for (const Scored& c : cand) {
+      if (c.score >= bound && n < kMaxVarianceUse) {
+        double x, y, a;
+        pose_of(c.index, &x, &y, &a);
+        if (DoubleEqual(x, best.x, tol) && DoubleEqual(y, best.y, tol)) {
+          norm += c.score;
+          acc += ((a - best.angle) * (a - best.angle)) * c.score;
+          ++n;
+        }
+      }
+    }
+    double var = max_ang_var;
+    if (norm > kDoubleTolerance) {
+      var = acc / norm;  // the /4 branch at :1008-1010 is overwritten at :1012
+    } else {
+      var = 200 * max_ang_var;
+    }
+    C(2, 2) = var;
+  };
+  switch (q.type) {
+    case 3:
+    case 0: positional(); angular(); break;
+    case 1: positional(); break;
+    case 2: angular(); break;
+    default: break;
+  }
+  out.response = best.score > 1.0 ? 1.0 : best.score;
+  return out;
+}
+
+double OnePass(const float* grid, int size_x, double scale, double off_x, double off_y, int P,
+               const double* pts, const Param& q, double* pose_world, double* cov,
+               double* best_map_out, long* n_avg_out) {
+  if (P == 0 || grid == nullptr) return 0.0;  // :792-795
+  const MapTf tf = MakeTf(scale, off_x, off_y);
+  const double cell_len = 1 / scale;  // grid_map_base.h:307-309
+  double center[3];
+  WorldToMap(tf, pose_world, center);
+  const PassGeometry g = Geometry(q, P, cell_len, center);
+  const size_t n = static_cast<size_t>(g.n_ang) * g.n_xy * g.n_xy;
+  std::vector<double> score(n);
+  ScorePass(grid, size_x, cell_len, P, pts, q, center, g, score.data(), nullptr, nullptr);
+  std::vector<Scored> cand(n);
+  for (size_t k = 0; k < n; ++k) { cand[k].score = score[k]; cand[k].index = static_cast<int>(k); }
+  PassOut o = Finish(cand, q, g, cell_len, center, cov);
+  if (best_map_out) { best_map_out[0] = o.best.x; best_map_out[1] = o.best.y; best_map_out[2] = o.best.angle; best_map_out[3] = o.best.score; }
+  if (n_avg_out) *n_avg_out = o.n_avg;
+  if (o.response > q.threshold) {
+    const double b[3] = {o.best.x, o.best.y, o.best.angle};
+    MapToWorld(tf, b, pose_world);
+  }
+  return o.response;
+}
+
+}  // namespace
+
+extern "C" {
+
+// occu_grid_map.h:40-59, 83-105
+int orc_blur_kernel(double sigma, double resolution, double* k, int cap) {
+  const double lo = 0.5 * resolution, hi = 10 * resolution;
+  if (!(sigma > lo && sigma < hi && resolution > 0)) return -1;
+  const int half = static_cast<int>((sigma / resolution) * std::sqrt(std::log(2)));
+  const int n = 2 * half + 1;
+  if (k && cap >= n * n) {
+    for (int i = -half; i <= half; ++i)
+      for (int j = -half; j <= half; ++j) {
+        const double d = std::hypot(i * resolution, j * resolution);
+        const double q = d / sigma;
+        k[(i + half) + n * (j + half)] = std::exp(-0.5 * (q * q));
+      }
+  }
+  return half;
+}
+
+// Lookup-grid build in the back-end configuration (just_update_occu, no auto-resize):
+// Reset to default, then per base scan transform / truncate / bounds-skip / stamp.
+// occu_grid_map.h:222-329, 474-497, 531-576; grid_map_cell.h:361-365; grid_map_base.h:339-346.
+// use_blur == 0 is not restated (SET_CELL_OCCUPIED path, out of the hot-path scope) -> returns 2.
+int orc_grid_build(float* grid, int size_x, int size_y, float default_prob, double sigma,
+                   double resolution, double occu_offset, double off_x, double off_y, int n_scans,
+                   const int* n_pts, const double* pts, const double* poses, int use_blur) {
+  std::vector<double> kernel(21 * 21);
+  int half = orc_blur_kernel(sigma, resolution, kernel.data(), 21 * 21);
+  if (!use_blur || half < 0) return 2;
+  const int ks = 2 * half + 1;
+  const size_t ncell = static_cast<size_t>(size_x) * size_y;
+  for (size_t i = 0; i < ncell; ++i) grid[i] = default_prob;
+  const double scale = 1.0 / resolution;
+  const MapTf tf = MakeTf(scale, off_x, off_y);
+  auto set_prob = [&](int x, int y, float prob) {
+    float& c = grid[static_cast<size_t>(y) * size_x + x];
+    if (c < prob && prob <= 1.0f) c = prob;
+  };
+  size_t off = 0;
+  const double tol = half + 1;
+  for (int s = 0; s < n_scans; ++s) {
+    double pm[3];
+    WorldToMap(tf, poses + 3 * s, pm);
+    const double c = std::cos(pm[2]), sn = std::sin(pm[2]);
+    // beam start = transform * origin(0,0) -> translation + (c*0 + (-s)*0)
+    const int sx0 = static_cast<int>((pm[0] + (c * 0.0 + (-sn) * 0.0)) + 0.5);
+    const int sy0 = static_cast<int>((pm[1] + (sn * 0.0 + c * 0.0)) + 0.5);
+    for (int i = 0; i < n_pts[s]; ++i) {
+      const double px = pts[2 * (off + i)], py = pts[2 * (off + i) + 1];
+      const double mx = pm[0] + (c * px + (-sn) * py);
+      const double my = pm[1] + (sn * px + c * py);
+      const int ex = static_cast<int>(mx + 0.5), ey = static_cast<int>(my + 0.5);
+      if (ex == sx0 && ey == sy0) continue;
+      if (!(ex > tol && ex < size_x - tol && ey > tol && ey < size_y - tol)) continue;
+      set_prob(ex, ey, 1.0f);
+      for (int j = -half; j <= half; ++j)
+        for (int ii = -half; ii <= half; ++ii)
+          set_prob(ex + ii, ey + j, static_cast<float>(kernel[(ii + half) + ks * (j + half)] * occu_offset));
+    }
+    off += n_pts[s];
+  }
+  return 0;
+}
+
+void orc_world_to_map(double scale, double off_x, double off_y, const double* w, double* out) {
+  WorldToMap(MakeTf(scale, off_x, off_y), w, out);
+}
+void orc_map_to_world(double scale, double off_x, double off_y, const double* m, double* out) {
+  MapToWorld(MakeTf(scale, off_x, off_y), m, out);
+}
+
+// geometry of a pass: out = {n_ang, n_xy, step, divisor, visited}
+void orc_pass_geometry(const double* param, int P, double cell_len, const double* center_map,
+                       long* out, double* dout /*start_x,start_y,factor,start_angle*/) {
+  const Param q = ReadParam(param);
+  const PassGeometry g = Geometry(q, P, cell_len, center_map);
+  out[0] = g.n_ang; out[1] = g.n_xy; out[2] = g.step; out[3] = g.divisor;
+  out[4] = (P + g.step - 1) / g.step;
+  if (dout) { dout[0] = g.start_x; dout[1] = g.start_y; dout[2] = g.factor; dout[3] = g.start_angle; }
+}
+
+// Penalised scores of every candidate in candidate order; optional (gx,gy) dump
+// [n_cand][visited] for the cell-index parity test.
+int orc_scores(const float* grid, int size_x, double cell_len, int P, const double* pts,
+               const double* param, const double* center_map, double* score, int32_t* gx,
+               int32_t* gy) {
+  const Param q = ReadParam(param);
+  const PassGeometry g = Geometry(q, P, cell_len, center_map);
+  ScorePass(grid, size_x, cell_len, P, pts, q, center_map, g, score, gx, gy);
+  return 0;
+}
+
+// BasedCorrelationScanMatch::ScanMatch restated (correlate_scan_matcher.h:784-875).
+double orc_match(const float* grid, int size_x, int size_y, double scale, double off_x,
+                 double off_y, int P, const double* pts, const double* param, double* pose_world,
+                 double* cov, double* best_map_out, long* n_avg_out, double* seconds) {
+  (void)size_y;
+  auto t0 = std::chrono::steady_clock::now();
+  double r = OnePass(grid, size_x, scale, off_x, off_y, P, pts, ReadParam(param), pose_world, cov,
+                     best_map_out, n_avg_out);
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return r;
+}
+
+// ScanMatchers::ScanMatch with the optimiser off (scan_matchers.h:224-263, 281).
+double orc_match_chain(const float* grid, int size_x, int size_y, double scale, double off_x,
+                       double off_y, int P, const double* pts, const double* params, int use_fine,
+                       double* pose_world, double* cov, double* resp_out, double* seconds) {
+  (void)size_y;
+  auto t0 = std::chrono::steady_clock::now();
+  double score = 0.0, r[3] = {0.0, 0.0, 0.0};
+  int times = 0;
+  r[0] = OnePass(grid, size_x, scale, off_x, off_y, P, pts, ReadParam(params), pose_world, cov, nullptr, nullptr);
+  score += r[0]; ++times;
+  if (use_fine) {
+    r[1] = OnePass(grid, size_x, scale, off_x, off_y, P, pts, ReadParam(params + 8), pose_world, cov, nullptr, nullptr);
+    score += r[1]; ++times;
+    r[2] = OnePass(grid, size_x, scale, off_x, off_y, P, pts, ReadParam(params + 16), pose_world, cov, nullptr, nullptr);
+    score += r[2]; ++times;
+  }
+  score /= times;
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (resp_out) { resp_out[0] = r[0]; resp_out[1] = r[1]; resp_out[2] = r[2]; }
+  return score;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+/* rsm.h -- C ABI of the B200-native correlative scan matcher (librsm.so).
+ *
+ * Drop-in boundary for ONE hot path of KevinLADLee/RoboRTS-Edu-SLAM: the brute-force
+ * correlative scan matcher in src/scan_match/correlate_scan_matcher.h plus the lookup-grid
+ * construction it reads from (src/map/occu_grid_map.h).  The reference has no FFI layer of its
+ * own; each entry point below cites the reference interface it replaces
+ * (file:line under the reference's src/).  INTEGRATION.md shows the C++ adapter a maintainer
+ * would drop into the reference so that scan_matchers.h / slam_processor.cpp compile unchanged.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every call returns an rsm_status (0 = OK) and never throws;
+ *   - all host arrays are caller-owned and only borrowed for the duration of the call;
+ *   - scan points are (x,y) pairs in CELL units in the sensor frame, exactly what
+ *     RangeDataContainer::CreateFrom(scan, 1/resolution) holds (slam/sensor_data_manager.h:99-115);
+ *   - poses are (x, y, theta) in world metres / radians; covariances are row-major 3x3;
+ *   - a context is not re-entrant (the reference serialises callers with scan_match_mutex_,
+ *     scan_matchers.h:298-300); use one context per GPU / per caller thread;
+ *   - there is NO CPU fallback: without a CUDA device rsm_create fails.
+ *
+ * Results are identical to the reference's CPU matcher on the same inputs: bit-exact cell
+ * indices, candidate scores, response and best pose; covariance within 1e-6 relative.
+ */
+#ifndef RSM_H_
+#define RSM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsm_ctx rsm_ctx;   /* opaque: device buffers, streams, scratch */
+typedef struct rsm_grid rsm_grid; /* opaque: one device-resident lookup grid (ScanMatchMap) */
+
+typedef enum rsm_status {
+  RSM_OK = 0,
+  RSM_ERR_NO_DEVICE = 1,       /* no CUDA device / driver: there is no CPU path */
+  RSM_ERR_CUDA = 2,            /* a CUDA runtime call failed; see rsm_last_error */
+  RSM_ERR_INVALID = 3,         /* bad argument */
+  RSM_ERR_WINDOW = 4,          /* search window + scan extent leaves the grid (the reference would
+                                  read out of bounds here; its callers prevent it with MapSizeCheck,
+                                  scan_matchers.h:365-390) */
+  RSM_ERR_UNSUPPORTED = 5,     /* e.g. FAST (branch-and-bound) pass type, non-blur rasterisation */
+  RSM_ERR_NOT_INIT = 6         /* grid has no content yet (reference: !IsMapInit()) */
+} rsm_status;
+
+/* CorrelationScanMatchType, correlate_scan_matcher.h:34-39 */
+enum { RSM_COARSE = 0, RSM_FINE = 1, RSM_SUPER = 2, RSM_FAST = 3 };
+
+/* CorrelationScanMatchParam, correlate_scan_matcher.h:41-86 (max_depth only matters to FAST) */
+typedef struct rsm_pass_param {
+  double search_space_size;       /* full width of the square translation window, metres */
+  double search_space_resolution; /* metres */
+  double search_angle_offset;     /* half range, radians */
+  double search_angle_resolution; /* radians */
+  double response_threshold;
+  int32_t use_point_size;
+  int32_t use_center_penalty;     /* bool */
+  int32_t type;                   /* RSM_COARSE / RSM_FINE / RSM_SUPER */
+  int32_t reserved;
+} rsm_pass_param;
+
+/* Optional per-pass detail (diagnostics and parity tests). */
+typedef struct rsm_pass_detail {
+  double best_score;      /* top candidate score, not clamped */
+  double best_pose_map[3];/* (averaged) best candidate in map cells / rad */
+  int64_t n_candidates;
+  int32_t n_avg;          /* size of the averaging set of FindBestCandidate (:670-710) */
+  int32_t exact_sort_used;/* 1 if exact ties forced the host std::sort path (same result, slower) */
+  int32_t pose_updated;   /* response > threshold */
+  int32_t n_ang, n_xy, visited, divisor;
+  int32_t reserved;
+} rsm_pass_detail;
+
+/* Counters since the context was created or last reset. */
+typedef struct rsm_stats {
+  int64_t kernel_launches;      /* kernels of this library launched */
+  int64_t score_launches;       /* launches of the scoring kernel */
+  int64_t evals;                /* candidate-beam evaluations scored (n_ang*n_xy^2*visited) */
+  int64_t passes;               /* single passes completed */
+  int64_t exact_sort_passes;    /* passes that needed the exact-tie host sort */
+  int64_t h2d_bytes, d2h_bytes; /* bytes copied by this library */
+  double score_kernel_ms;       /* CUDA-event time of scoring kernels (only while profiling is on) */
+  double raster_kernel_ms;      /* CUDA-event time of rasterisation kernels (profiling on) */
+  double select_kernel_ms;      /* CUDA-event time of selection kernels (profiling on) */
+} rsm_stats;
+
+/* ---- context ------------------------------------------------------------------------- */
+int rsm_create(int device, rsm_ctx** out);
+void rsm_destroy(rsm_ctx* ctx);
+const char* rsm_last_error(const rsm_ctx* ctx);
+const char* rsm_version(void);
+int rsm_set_profiling(rsm_ctx* ctx, int on); /* record CUDA events around every kernel class */
+int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out);
+int rsm_reset_stats(rsm_ctx* ctx);
+int rsm_synchronize(rsm_ctx* ctx);
+/* CUDA-event stopwatch on the context's own stream (what bench.py times with). */
+int rsm_timer_start(rsm_ctx* ctx);
+int rsm_timer_stop(rsm_ctx* ctx, double* elapsed_ms);
+/* Overwrite a scratch buffer larger than L2 (126 MB) so the next call starts cold. */
+int rsm_flush_l2(rsm_ctx* ctx);
+
+/* ---- lookup grid ------------------------------------------------------------------------
+ * Replaces the live ScanMatchMap the reference matcher reads through GetGridProbValue
+ * (map/occu_grid_map.h:395-397) and its world<->map transform (map/grid_map_base.h:68-93).
+ * offset is GridMapBase::map_offset_ (metres). */
+int rsm_grid_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, double offset_x,
+                    double offset_y, rsm_grid** out);
+void rsm_grid_destroy(rsm_ctx* ctx, rsm_grid* grid);
+int rsm_grid_set_offset(rsm_ctx* ctx, rsm_grid* grid, double offset_x, double offset_y);
+/* Hand over an existing grid: prob[y*size_x + x] = ProbabilityCell::prob_value_ (map/grid_map_cell.h:301-328). */
+int rsm_grid_upload_f32(rsm_ctx* ctx, rsm_grid* grid, const float* prob);
+/* Device-side construction from base scans; replaces OccuGridMap::InitMapWithRangeVec in the
+ * back-end configuration (just_update_occu, no auto-resize; map/occu_grid_map.h:222-329,
+ * 474-497, 531-576; slam/slam_processor.cpp:448-462).  sigma = map deviation, occu_offset =
+ * gaussian_blur_offset.  pts_xy = concatenated scan points (cells, sensor frame), n_pts[i] points
+ * for scan i, poses_world = n_scans x (x,y,theta) sensor poses. */
+int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double sigma,
+                       double occu_offset, int use_blur, int n_scans, const int32_t* n_pts,
+                       const double* pts_xy, const double* poses_world);
+int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out);
+/* 1 if the grid is held as exact 2^-25 fixed point (integer gather path), 0 if as float32. */
+int rsm_grid_is_fixed_point(const rsm_grid* grid);
+int rsm_world_to_map(const rsm_grid* grid, const double pose_world[3], double pose_map[3]);
+int rsm_map_to_world(const rsm_grid* grid, const double pose_map[3], double pose_world[3]);
+
+/* ---- matching ---------------------------------------------------------------------------
+ * rsm_match: one pass.  Replaces BasedCorrelationScanMatch::ScanMatch(map, range_data, param,
+ * current_pose&, cov_matrix&) -> response (scan_match/correlate_scan_matcher.h:784-875).
+ * pose_world and cov are in/out exactly as there: cov is rewritten according to the pass type,
+ * pose_world only if response > response_threshold.  Invalid input (grid not initialised or
+ * n_pts == 0) returns RSM_OK with *response = 0 and the outputs untouched, like :792-795. */
+int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+              const rsm_pass_param* param, double pose_world[3], double cov[9], double* response,
+              rsm_pass_detail* detail /* nullable */);
+
+/* rsm_match_chain: coarse -> fine -> super-fine on one grid.  Replaces ScanMatchers::ScanMatch
+ * with the optimiser off (scan_match/scan_matchers.h:179-289); params[0..2] = coarse, fine,
+ * super.  *score = mean of the pass responses; responses (nullable) = the individual ones. */
+int rsm_match_chain(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                    const rsm_pass_param params[3], int use_fine, double pose_world[3],
+                    double cov[9], double* score, double responses[3] /* nullable */);
+
+/* rsm_match_batch: n independent chains in batched launches (no reference equivalent; the
+ * reference runs loop-closure candidates one at a time, pose_graph/range_scan_pose_graph.cpp:
+ * 153,312,329).  Pair i uses grids[i], points pts_xy[pts_offset[i] .. pts_offset[i+1]) (offsets
+ * in points), params[3*i .. 3*i+2] (or params[0..2] for every pair when shared_params != 0),
+ * poses_world[3*i..], covs[9*i..]; scores[i] = mean response, responses (nullable) 3 per pair. */
+int rsm_match_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* pts_xy,
+                    const int64_t* pts_offset, const rsm_pass_param* params, int shared_params,
+                    int use_fine, double* poses_world, double* covs, double* scores,
+                    double* responses /* nullable */);
+
+/* rsm_loop_closure_batch: the whole back-end ScanMatchInterface step for n (scan, chain) pairs
+ * (slam/slam_processor.cpp:250-326 without the pub-map penalty): for every pair rasterise a
+ * size x size grid centred on centres_world[2*i..] from its base scans, then run the chain.
+ * Base scans of pair i are scans [scan_offset[i], scan_offset[i+1]) of the base arrays. */
+int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob,
+                           double sigma, double occu_offset, const double* centres_world,
+                           const int64_t* scan_offset, const int32_t* base_n_pts,
+                           const double* base_pts_xy, const double* base_poses_world,
+                           const double* pts_xy, const int64_t* pts_offset,
+                           const rsm_pass_param params[3], int use_fine, double* poses_world,
+                           double* covs, double* scores, double* responses /* nullable */);
+
+/* ---- parity / multi-GPU building blocks --------------------------------------------------
+ * rsm_pass_scores: penalised score of every candidate of one pass in candidate order
+ * k = (angle_index*n_xy + x_index)*n_xy + y_index (the order of correlate_scan_matcher.h:552-584),
+ * restricted to angle indices [angle_begin, angle_end) (pass 0, -1 for all).  scores_out holds
+ * (angle_end-angle_begin)*n_xy^2 doubles.  center given in world coordinates. */
+int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                    const rsm_pass_param* param, const double pose_world[3], int angle_begin,
+                    int angle_end, double* scores_out, int64_t capacity, int64_t* n_written);
+
+/* Angle-sliced single window: each rank scores angle indices
+ * [angle_begin, angle_end) and returns a compact partial (its local maximum, its candidates near
+ * the top and its local top lists) in `partial` (RSM_PARTIAL_BYTES bytes).  After exchanging the
+ * partials (all-gather), rsm_match_finish merges them and finalises exactly like rsm_match. */
+#define RSM_PARTIAL_BYTES (1 << 20)
+int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                      const rsm_pass_param* param, const double pose_world[3], int angle_begin,
+                      int angle_end, void* partial);
+int rsm_match_finish(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                     const rsm_pass_param* param, const void* const* partials, int n_partials,
+                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSM_H_ */

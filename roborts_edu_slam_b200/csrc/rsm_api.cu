@@ -1,0 +1,1072 @@
+// rsm_api.cu -- the C ABI of include/rsm.h: context and grid management, the host side of a pass
+// (geometry, libm angle tables, launch, exact finalisation) and the chain / batch drivers.
+//
+// Host/device split of one pass (reference: BasedCorrelationScanMatch::ScanMatch,
+// scan_match/correlate_scan_matcher.h:784-875):
+//   host    world->map, n_ang / n_xy / stride, cos/sin of every search angle from the HOST libm
+//           (CUDA's sin/cos are not bit-identical to glibc's; n_ang is at most ~10^3 per pass)
+//   device  score_kernel  -> penalised score of every candidate + running maximum
+//           select_kernel -> averaging-set candidates + global top-21
+//           gather_kernel -> scores of the same-(x,y) columns (angular covariance only)
+//   host    FindBestCandidate / covariance on the few dozen candidates that matter, in the
+//           reference's expression order; atan2 from the host libm.
+// If the candidates that are consumed contain exact score ties whose order libstdc++'s unstable
+// sort would decide, the pass falls back to the *exact* path: the score array is copied back and
+// sorted with the same std::sort call the reference makes, which reproduces its order.
+// There is no CPU scoring path anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rsm.h"
+#include "rsm_device.h"
+#include "rsm_host.h"
+#include "rsm_kernels.h"
+
+using namespace rsm;
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct rsm_grid {
+  int size_x = 0, size_y = 0, pitch = 0;
+  double resolution = 0, scale = 0, off_x = 0, off_y = 0;
+  MapTransform tf;
+  bool fixed = true;   // cells are int32 value*2^25 (else float32)
+  bool init = false;   // has content (reference: IsMapInit())
+  bool owned = true;   // d_cells allocated by this grid (false: a slot of a batch pool)
+  void* d_cells = nullptr;
+  double cell_len() const { return 1 / scale; }   // map/grid_map_base.h:307-309
+};
+
+namespace {
+
+struct Buf {
+  char* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Layout {
+  size_t off = 0;
+  size_t take(size_t bytes, size_t align = 256) {
+    off = (off + align - 1) / align * align;
+    size_t o = off;
+    off += bytes;
+    return o;
+  }
+};
+
+enum KernelClass { KC_SCORE = 0, KC_SELECT = 1, KC_RASTER = 2, KC_OTHER = 3, KC_N = 4 };
+
+}  // namespace
+
+struct rsm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  std::string err;
+  rsm_stats stats;
+  bool profiling = false;
+  Buf d_work, d_pts, d_flush, d_pool_grids;
+  Buf h_up, h_down;  // pinned staging
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { cudaEvent_t a, b; int kc; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+};
+
+namespace {
+
+int fail(rsm_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, RSM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int ensure_dev(rsm_ctx* ctx, Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return RSM_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (b.p) CU(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  CU(cudaMalloc(reinterpret_cast<void**>(&b.p), cap));
+  b.cap = cap;
+  return RSM_OK;
+}
+
+int ensure_pinned(rsm_ctx* ctx, Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return RSM_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (b.p) CU(cudaFreeHost(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  CU(cudaMallocHost(reinterpret_cast<void**>(&b.p), cap));
+  b.cap = cap;
+  return RSM_OK;
+}
+
+// CUDA-event bracket around a kernel class while profiling is on
+struct Prof {
+  rsm_ctx* ctx; int kc; cudaEvent_t a = nullptr, b = nullptr;
+  Prof(rsm_ctx* c, int k) : ctx(c), kc(k) {
+    if (!ctx->profiling) return;
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+      cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; ctx->ev_pool.push_back(e);
+    }
+    a = ctx->ev_pool[ctx->ev_used++]; b = ctx->ev_pool[ctx->ev_used++];
+    cudaEventRecord(a, ctx->stream);
+  }
+  ~Prof() {
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->spans.push_back({a, b, kc});
+  }
+};
+
+// call after a stream synchronize
+void harvest_profile(rsm_ctx* ctx) {
+  for (auto& s : ctx->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      if (s.kc == KC_SCORE) ctx->stats.score_kernel_ms += ms;
+      else if (s.kc == KC_SELECT) ctx->stats.select_kernel_ms += ms;
+      else if (s.kc == KC_RASTER) ctx->stats.raster_kernel_ms += ms;
+    }
+  }
+  ctx->spans.clear();
+  ctx->ev_used = 0;
+}
+
+int sync_stream(rsm_ctx* ctx) {
+  CU(cudaStreamSynchronize(ctx->stream));
+  harvest_profile(ctx);
+  return RSM_OK;
+}
+
+inline double key_to_score(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  double d;
+  std::memcpy(&d, &b, 8);
+  return d;
+}
+
+// value representable as an int32 multiple of 2^-25 in [0, 1] ?
+inline bool fix_ok(float v, int* out) {
+  if (!(v >= 0.0f && v <= 1.0f)) return false;
+  const double s = std::ldexp(static_cast<double>(v), kFixShift);
+  const double r = std::floor(s);
+  if (r != s) return false;
+  *out = static_cast<int>(r);
+  return true;
+}
+
+struct TileCfg { int lx, ry, nt; };
+
+// Tile shape of the scoring kernel for a window of n_xy x n_xy translations: lanes along x (lx),
+// ry consecutive y per thread, nt threads.  Minimises padded work plus table-build overhead.
+TileCfg pick_tile(int n_xy) {
+  int lx = 4;
+  while (lx < n_xy && lx < 32) lx <<= 1;
+  TileCfg best{lx, 1, 128};
+  double best_cost = 1e300;
+  const int nts[2] = {128, 256};
+  for (int nt : nts) {
+    const int slots = nt / lx;
+    for (int ry = 1; ry <= 8; ++ry) {
+      const int rows = slots * ry;
+      const int tx = (n_xy + lx - 1) / lx, ty = (n_xy + rows - 1) / rows;
+      const double padded = double(tx) * lx * double(ty) * rows;
+      const double cost = padded * (1.0 + 8.0 * double(lx + rows) / (double(lx) * rows));
+      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && ry > best.ry)) {
+        if (cost < best_cost) best_cost = cost;
+        best = TileCfg{lx, ry, nt};
+      }
+    }
+  }
+  return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one pass over a batch of items
+// ---------------------------------------------------------------------------------------------
+struct PassItem {
+  const rsm_grid* grid = nullptr;
+  const double* d_pts = nullptr;   // device points of this scan
+  int P = 0;
+  rsm_pass_param param;
+  double* pose_world = nullptr;    // in/out
+  double* cov = nullptr;           // in/out
+  double response = 0.0;
+  rsm_pass_detail detail;
+  int ang_begin = 0, ang_end = -1; // angle slice (-1: all)
+  // internal
+  bool active = false;
+  PassGeo geo;
+  int a0 = 0, a1 = 0;              // resolved slice
+  int64_t n_local = 0;             // candidates scored here
+  size_t score_off = 0, trig_off = 0;
+  int sel_cta0 = 0, sel_ncta = 0;
+  bool exact = false;
+  BestPose best;
+  std::vector<Cand> a_list, top, xy;
+  int n_cols = 0;
+  int cols[kMaxCols];
+  size_t gather_off = 0;
+};
+
+enum PassMode { MODE_MATCH = 0, MODE_SCORES = 1 };
+
+struct PassScratch {   // device pointers valid until the next pass
+  double* d_score = nullptr;
+};
+
+// exact path: reproduce the reference's sort on the full score array of one item
+void finish_exact(PassItem& it, const double* score) {
+  const PassGeo& g = it.geo;
+  const int64_t n = it.n_local;
+  const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
+  std::vector<Cand> c(n);
+  for (int64_t k = 0; k < n; ++k) { c[k].score = score[k]; c[k].index = base + k; }
+  std::sort(c.begin(), c.end(), by_score_desc);   // correlate_scan_matcher.h:607-608
+  size_t na = 0;
+  while (na < c.size() && DoubleEqual(c[na].score, c[0].score, kResponseFilterTolerance)) ++na;
+  it.best = find_best(g, c.data(), na);
+  const int type = it.param.type;
+  if (type == RSM_COARSE || type == RSM_FINE || type == RSM_FAST)
+    positional_cov(g, it.param, it.best, c.data(), std::min<size_t>(c.size(), kTopK), it.cov);
+  if (type == RSM_COARSE || type == RSM_SUPER || type == RSM_FAST) {
+    std::vector<Cand> xy;
+    const double bound = cov_score_bound(it.best);
+    for (const Cand& e : c) {
+      if (!(e.score >= bound)) break;   // sorted: nothing further can qualify
+      int ia, ix, iy;
+      g.decode(e.index, &ia, &ix, &iy);
+      if (same_xy(g, it.best, ix, iy)) { xy.push_back(e); if (xy.size() >= size_t(kMaxVarianceUsePointSize)) break; }
+    }
+    angular_cov(g, it.param, it.best, xy.data(), xy.size(), it.cov);
+  }
+}
+
+bool adjacent_tie(const std::vector<Cand>& v, size_t n) {
+  for (size_t i = 1; i < n; ++i) if (v[i].score == v[i - 1].score) return true;
+  return false;
+}
+
+int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* scores_out,
+             int64_t scores_cap, int64_t* scores_written) {
+  const int n_items = int(items.size());
+  // ---- host geometry -------------------------------------------------------------------------
+  std::vector<int> act;
+  for (int i = 0; i < n_items; ++i) {
+    PassItem& it = items[i];
+    it.active = false; it.exact = false; it.response = 0.0;
+    std::memset(&it.detail, 0, sizeof it.detail);
+    if (!it.grid || !it.grid->init || it.P <= 0) continue;   // :792-795 -> response 0, outputs untouched
+    if (it.param.type == RSM_FAST) return fail(ctx, RSM_ERR_UNSUPPORTED, "FAST (branch-and-bound) pass type is not provided");
+    if (!(it.param.search_space_resolution > 0) || !(it.param.search_angle_resolution > 0) ||
+        !(it.param.search_space_size >= 0) || !(it.param.search_angle_offset >= 0) || it.param.use_point_size < 2)
+      return fail(ctx, RSM_ERR_INVALID, "bad pass parameters");
+    double center[3];
+    it.grid->tf.world_to_map(it.pose_world, center);
+    it.geo = make_geo(it.param, it.P, it.grid->cell_len(), center);
+    if (it.geo.n_ang < 1 || it.geo.n_xy < 1 || it.geo.n_cand() > (int64_t(1) << 31) - 1)
+      return fail(ctx, RSM_ERR_INVALID, "search window has %lld candidates", (long long)it.geo.n_cand());
+    it.a0 = std::max(0, it.ang_begin);
+    it.a1 = it.ang_end < 0 ? it.geo.n_ang : std::min(it.ang_end, it.geo.n_ang);
+    if (it.a1 <= it.a0) continue;
+    it.n_local = int64_t(it.a1 - it.a0) * it.geo.n_xy * it.geo.n_xy;
+    it.active = true;
+    act.push_back(i);
+  }
+  if (scores_written) *scores_written = 0;
+  if (act.empty()) return RSM_OK;
+  const int na = int(act.size());
+
+  // ---- layouts -------------------------------------------------------------------------------
+  const TileCfg cfg = pick_tile(items[act[0]].geo.n_xy);
+  const int rows = (cfg.nt / cfg.lx) * cfg.ry;
+  std::vector<ScoreJob> sjobs(na);
+  std::vector<int> s_cta(na + 1, 0);
+  std::vector<SelectJob> ljobs(na);
+  std::vector<int> l_cta(na + 1, 0);
+  Layout dl;   // device work arena
+  const size_t o_sjobs = dl.take(sizeof(ScoreJob) * na);
+  const size_t o_scta = dl.take(sizeof(int) * (na + 1));
+  const size_t o_ljobs = dl.take(sizeof(SelectJob) * na);
+  const size_t o_lcta = dl.take(sizeof(int) * (na + 1));
+  size_t trig_doubles = 0;
+  for (int a = 0; a < na; ++a) { items[act[a]].trig_off = trig_doubles; trig_doubles += size_t(items[act[a]].geo.n_ang) * 3; }
+  const size_t o_trig = dl.take(trig_doubles * 8);
+  const size_t up_bytes = dl.off;          // everything above is uploaded in one copy
+  // zero-initialised block: best keys, err flags, pool counter
+  const size_t o_best = dl.take(size_t(na) * 8);
+  const size_t o_err = dl.take(size_t(na) * 4, 4);
+  const size_t o_poolcnt = dl.take(4, 4);
+  const size_t zero_end = dl.off;
+  int total_sel_cta = 0;
+  int64_t total_cand = 0;
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    int ncta = int(std::min<int64_t>(296, (it.n_local + 16383) / 16384));
+    if (ncta < 1) ncta = 1;
+    it.sel_cta0 = total_sel_cta; it.sel_ncta = ncta;
+    total_sel_cta += ncta;
+    total_cand += it.n_local;
+  }
+  const size_t o_topcnt = dl.take(size_t(total_sel_cta) * 4, 4);
+  const size_t o_top = dl.take(size_t(total_sel_cta) * kTopK * sizeof(Entry), 16);
+  const int pool_cap = int(std::min<int64_t>(std::max<int64_t>(int64_t(na) * 64, 65536), total_cand));
+  const size_t o_pool = dl.take(size_t(pool_cap) * sizeof(PoolEntry), 16);
+  const size_t down_end = dl.off;          // [o_best, down_end) is what the host reads back
+  const size_t o_gjobs = dl.take(sizeof(GatherJob) * na);
+  size_t gather_doubles = 0;
+  for (int a = 0; a < na; ++a) { items[act[a]].gather_off = gather_doubles; gather_doubles += size_t(kMaxCols) * items[act[a]].geo.n_ang; }
+  const size_t o_gout = dl.take(gather_doubles * 8);
+  size_t score_doubles = 0;
+  for (int a = 0; a < na; ++a) { items[act[a]].score_off = score_doubles; score_doubles += size_t(items[act[a]].n_local); }
+  const size_t o_score = dl.take(score_doubles * 8);
+  int rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  char* dw = ctx->d_work.p;
+  rc = ensure_pinned(ctx, ctx->h_up, std::max(up_bytes, sizeof(GatherJob) * size_t(na)));
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_down, std::max(down_end - o_best, gather_doubles * 8));
+  if (rc) return rc;
+
+  // ---- fill jobs, angle tables ---------------------------------------------------------------
+  char* up = ctx->h_up.p;
+  double* h_trig = reinterpret_cast<double*>(up + o_trig);
+  int cta = 0;
+  bool any_fixed = false, any_float = false;
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    const PassGeo& g = it.geo;
+    double* t = h_trig + it.trig_off;
+    for (int ia = 0; ia < g.n_ang; ++ia) {
+      const double angle = g.angle_of(ia);
+      t[3 * ia] = std::cos(angle);      // correlate_scan_matcher.h:171-172
+      t[3 * ia + 1] = std::sin(angle);
+      t[3 * ia + 2] = angle;
+    }
+    ScoreJob& J = sjobs[a];
+    std::memset(&J, 0, sizeof J);
+    J.grid = it.grid->d_cells;
+    J.pts = it.d_pts;
+    J.trig = reinterpret_cast<const double*>(dw + o_trig) + it.trig_off;
+    J.score = reinterpret_cast<double*>(dw + o_score) + it.score_off;
+    J.best_key = reinterpret_cast<unsigned long long*>(dw + o_best) + a;
+    J.err = reinterpret_cast<int*>(dw + o_err) + a;
+    J.pitch = it.grid->pitch; J.size_x = it.grid->size_x; J.size_y = it.grid->size_y;
+    J.P = it.P; J.step = g.step; J.V = g.visited;
+    J.n_xy = g.n_xy; J.ang_begin = it.a0; J.ang_count = it.a1 - it.a0;
+    J.tiles_x = (g.n_xy + cfg.lx - 1) / cfg.lx;
+    J.tiles_y = (g.n_xy + rows - 1) / rows;
+    J.use_penalty = it.param.use_center_penalty ? 1 : 0;
+    J.divisor = double(g.divisor);
+    J.sx = g.start_x; J.sy = g.start_y; J.f = g.factor;
+    J.cx = g.center[0]; J.cy = g.center[1]; J.ca = g.center[2];
+    J.m2 = g.cell_len * g.cell_len;                                   // :733
+    J.half_size = it.param.search_space_size / 2;                     // :734
+    J.gain = (it.param.type == RSM_COARSE) ? 0.4 : 0.2;               // :588-602, :759-761
+    s_cta[a] = cta;
+    cta += J.ang_count * J.tiles_x * J.tiles_y;
+    (it.grid->fixed ? any_fixed : any_float) = true;
+    SelectJob& L = ljobs[a];
+    std::memset(&L, 0, sizeof L);
+    L.score = J.score; L.n = it.n_local; L.best_key = J.best_key;
+    L.top_list = reinterpret_cast<Entry*>(dw + o_top) + size_t(it.sel_cta0) * kTopK;
+    L.top_count = reinterpret_cast<int*>(dw + o_topcnt) + it.sel_cta0;
+    L.err = J.err; L.job_id = a; L.n_cta = it.sel_ncta;
+    L.slice = (it.n_local + it.sel_ncta - 1) / it.sel_ncta;
+    l_cta[a] = it.sel_cta0;
+    ctx->stats.evals += it.n_local * g.visited;
+  }
+  s_cta[na] = cta; l_cta[na] = total_sel_cta;
+  if (any_fixed && any_float) return fail(ctx, RSM_ERR_UNSUPPORTED, "a batch must not mix fixed-point and float32 grids");
+  std::memcpy(up + o_sjobs, sjobs.data(), sizeof(ScoreJob) * na);
+  std::memcpy(up + o_scta, s_cta.data(), sizeof(int) * (na + 1));
+  std::memcpy(up + o_ljobs, ljobs.data(), sizeof(SelectJob) * na);
+  std::memcpy(up + o_lcta, l_cta.data(), sizeof(int) * (na + 1));
+
+  // ---- launch --------------------------------------------------------------------------------
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += up_bytes;
+  CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
+  {
+    Prof p(ctx, KC_SCORE);
+    CU(launch_score(any_fixed, cfg.lx, cfg.ry, cfg.nt, cta, ctx->stream,
+                    reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
+  }
+  ctx->stats.kernel_launches++; ctx->stats.score_launches++;
+
+  if (mode == MODE_SCORES) {
+    // parity/debug: hand the raw score array of item 0 back
+    PassItem& it = items[act[0]];
+    if (it.n_local > scores_cap) return fail(ctx, RSM_ERR_INVALID, "scores_out too small: need %lld", (long long)it.n_local);
+    CU(cudaMemcpyAsync(scores_out, dw + o_score + it.score_off * 8, size_t(it.n_local) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    ctx->stats.d2h_bytes += size_t(it.n_local) * 8;
+    if (scores_written) *scores_written = it.n_local;
+    int e0; std::memcpy(&e0, ctx->h_down.p, 4);
+    if (e0 & kErrWindow) return fail(ctx, RSM_ERR_WINDOW, "search window + scan extent leaves the grid");
+    return RSM_OK;
+  }
+
+  {
+    Prof p(ctx, KC_SELECT);
+    CU(launch_select(total_sel_cta, ctx->stream, reinterpret_cast<const SelectJob*>(dw + o_ljobs),
+                     reinterpret_cast<const int*>(dw + o_lcta), na, reinterpret_cast<PoolEntry*>(dw + o_pool),
+                     pool_cap, reinterpret_cast<int*>(dw + o_poolcnt)));
+  }
+  ctx->stats.kernel_launches++;
+  // read back everything up to the pool, plus a first slice of the pool
+  char* dn = ctx->h_down.p;
+  const size_t head_bytes = o_pool - o_best;
+  const int pool_first = std::min(pool_cap, std::max(4096, na * 8));
+  CU(cudaMemcpyAsync(dn, dw + o_best, head_bytes + size_t(pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.d2h_bytes += head_bytes + size_t(pool_first) * sizeof(PoolEntry);
+  const unsigned long long* h_best = reinterpret_cast<const unsigned long long*>(dn);
+  const int* h_err = reinterpret_cast<const int*>(dn + (o_err - o_best));
+  int pool_count = *reinterpret_cast<const int*>(dn + (o_poolcnt - o_best));
+  const int* h_topcnt = reinterpret_cast<const int*>(dn + (o_topcnt - o_best));
+  const Entry* h_top = reinterpret_cast<const Entry*>(dn + (o_top - o_best));
+  const PoolEntry* h_pool = reinterpret_cast<const PoolEntry*>(dn + (o_pool - o_best));
+  bool pool_overflow = pool_count > pool_cap;
+  if (pool_overflow) pool_count = pool_cap;
+  if (pool_count > pool_first) {
+    CU(cudaMemcpyAsync(dn + head_bytes + size_t(pool_first) * sizeof(PoolEntry),
+                       dw + o_pool + size_t(pool_first) * sizeof(PoolEntry),
+                       size_t(pool_count - pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    ctx->stats.d2h_bytes += size_t(pool_count - pool_first) * sizeof(PoolEntry);
+  }
+
+  // ---- stage 1: best pose, positional covariance ---------------------------------------------
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    if (h_err[a] & kErrWindow) return fail(ctx, RSM_ERR_WINDOW, "search window + scan extent leaves the grid (item %d)", act[a]);
+    it.a_list.clear(); it.top.clear(); it.xy.clear(); it.n_cols = 0;
+    if ((h_err[a] & (kErrPoolFull | kErrSelectFull)) || pool_overflow) it.exact = true;
+  }
+  const int64_t dummy = 0; (void)dummy;
+  for (int e = 0; e < pool_count; ++e) {
+    const PoolEntry& pe = h_pool[e];
+    PassItem& it = items[act[pe.job]];
+    if (it.exact) continue;
+    it.a_list.push_back(Cand{pe.score, int64_t(it.a0) * it.geo.n_xy * it.geo.n_xy + pe.index});
+  }
+  bool need_gather = false;
+  std::vector<GatherJob> gjobs;
+  std::vector<int> gitem;
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    if (it.exact) continue;
+    const PassGeo& g = it.geo;
+    const double top_score = key_to_score(h_best[a]);
+    std::sort(it.a_list.begin(), it.a_list.end(), by_score_desc);
+    if (it.a_list.empty() || it.a_list[0].score != top_score || adjacent_tie(it.a_list, it.a_list.size())) { it.exact = true; continue; }
+    it.best = find_best(g, it.a_list.data(), it.a_list.size());
+    if (size_t(it.best.n_avg) != it.a_list.size()) { it.exact = true; continue; }   // cannot happen; be safe
+    const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
+    for (int c = 0; c < it.sel_ncta; ++c) {
+      const int cnt = h_topcnt[it.sel_cta0 + c];
+      const Entry* e = h_top + size_t(it.sel_cta0 + c) * kTopK;
+      for (int r = 0; r < cnt; ++r) it.top.push_back(Cand{e[r].score, base + e[r].index});
+    }
+    std::sort(it.top.begin(), it.top.end(), by_score_desc);
+    if (it.top.size() > size_t(kTopK)) it.top.resize(kTopK);
+    const int type = it.param.type;
+    const double bound = cov_score_bound(it.best);
+    if (type == RSM_COARSE || type == RSM_FINE) {
+      // the 20-element prefix is unambiguous unless the 20th and 21st scores tie above the bound
+      if (it.top.size() == size_t(kTopK) && it.top[kTopK - 1].score > bound &&
+          it.top[kTopK - 1].score == it.top[kTopK - 2].score) { it.exact = true; continue; }
+      positional_cov(g, it.param, it.best, it.top.data(), it.top.size(), it.cov);
+    }
+    if (type == RSM_COARSE || type == RSM_SUPER) {
+      if (it.best.score < kDoubleTolerance) {
+        angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
+      } else {
+        int xs[8], ys[8], nx = 0, ny = 0;
+        const double tol = g.factor;
+        for (int ix = 0; ix < g.n_xy && nx < 8; ++ix) if (DoubleEqual(g.x_of(ix), it.best.x, tol)) xs[nx++] = ix;
+        for (int iy = 0; iy < g.n_xy && ny < 8; ++iy) if (DoubleEqual(g.y_of(iy), it.best.y, tol)) ys[ny++] = iy;
+        if (nx * ny > kMaxCols) { it.exact = true; continue; }
+        it.n_cols = 0;
+        for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) it.cols[it.n_cols++] = xs[i] * g.n_xy + ys[j];
+        if (it.n_cols == 0) {
+          angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
+        } else {
+          GatherJob G;
+          std::memset(&G, 0, sizeof G);
+          G.score = reinterpret_cast<const double*>(dw + o_score) + it.score_off;
+          G.out = reinterpret_cast<double*>(dw + o_gout) + it.gather_off;
+          G.n_xy = g.n_xy; G.n_ang = it.a1 - it.a0; G.n_cols = it.n_cols;
+          for (int c = 0; c < it.n_cols; ++c) G.cols[c] = it.cols[c];
+          gjobs.push_back(G); gitem.push_back(act[a]);
+          need_gather = true;
+        }
+      }
+    }
+  }
+  // ---- stage 2: angular covariance from the same-(x,y) columns ---------------------------------
+  if (need_gather) {
+    const int ng = int(gjobs.size());
+    std::memcpy(ctx->h_up.p, gjobs.data(), sizeof(GatherJob) * ng);
+    CU(cudaMemcpyAsync(dw + o_gjobs, ctx->h_up.p, sizeof(GatherJob) * ng, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_gather(ng, ctx->stream, reinterpret_cast<const GatherJob*>(dw + o_gjobs)));
+    ctx->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_gout, gather_doubles * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    ctx->stats.h2d_bytes += sizeof(GatherJob) * ng;
+    ctx->stats.d2h_bytes += gather_doubles * 8;
+    const double* h_g = reinterpret_cast<const double*>(ctx->h_down.p);
+    for (int gi = 0; gi < ng; ++gi) {
+      PassItem& it = items[gitem[gi]];
+      const PassGeo& g = it.geo;
+      const double bound = cov_score_bound(it.best);
+      const int nang = it.a1 - it.a0;
+      const double* col = h_g + it.gather_off;
+      it.xy.clear();
+      for (int c = 0; c < it.n_cols; ++c)
+        for (int ia = 0; ia < nang; ++ia) {
+          const double s = col[size_t(c) * nang + ia];
+          if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
+        }
+      std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
+      if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
+          it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) { it.exact = true; continue; }
+      if (it.xy.size() > size_t(kTopK)) it.xy.resize(kTopK);
+      angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
+    }
+  }
+  // ---- exact path for the items that need the reference's own sort order ----------------------
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    if (!it.exact) continue;
+    std::vector<double> sc(it.n_local);
+    CU(cudaMemcpy(sc.data(), dw + o_score + it.score_off * 8, size_t(it.n_local) * 8, cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += size_t(it.n_local) * 8;
+    finish_exact(it, sc.data());
+    ctx->stats.exact_sort_passes++;
+  }
+  // ---- response, pose write-back (:861-869) ----------------------------------------------------
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    const double bs = it.best.score;
+    it.response = bs > 1.0 ? 1.0 : bs;
+    it.detail.best_score = bs;
+    it.detail.best_pose_map[0] = it.best.x; it.detail.best_pose_map[1] = it.best.y; it.detail.best_pose_map[2] = it.best.angle;
+    it.detail.n_candidates = it.geo.n_cand();
+    it.detail.n_avg = it.best.n_avg;
+    it.detail.exact_sort_used = it.exact ? 1 : 0;
+    it.detail.n_ang = it.geo.n_ang; it.detail.n_xy = it.geo.n_xy;
+    it.detail.visited = it.geo.visited; it.detail.divisor = it.geo.divisor;
+    it.detail.pose_updated = 0;
+    if (it.response > it.param.response_threshold) {
+      const double b[3] = {it.best.x, it.best.y, it.best.angle};
+      it.grid->tf.map_to_world(b, it.pose_world);
+      it.detail.pose_updated = 1;
+    }
+    ctx->stats.passes++;
+  }
+  return RSM_OK;
+}
+
+int upload_points(rsm_ctx* ctx, const double* pts_xy, size_t n_points, double** d_out) {
+  const size_t bytes = n_points * 16;
+  int rc = ensure_dev(ctx, ctx->d_pts, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_pts.p, pts_xy, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += bytes;
+  *d_out = reinterpret_cast<double*>(ctx->d_pts.p);
+  return RSM_OK;
+}
+
+// the coarse -> fine -> super-fine chain over a batch (scan_matchers.h:224-263, 281)
+int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* d_pts, const int* n_pts,
+              const rsm_pass_param* params, bool shared_params, bool use_fine, double* poses, double* covs,
+              double* scores, double* responses) {
+  std::vector<PassItem> items(n);
+  std::vector<double> sum(n, 0.0);
+  const int n_pass = use_fine ? 3 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    for (int i = 0; i < n; ++i) {
+      PassItem& it = items[i];
+      it.grid = grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
+      it.param = params[(shared_params ? 0 : 3 * i) + pass];
+      it.pose_world = poses + 3 * i; it.cov = covs + 9 * i;
+      it.ang_begin = 0; it.ang_end = -1;
+    }
+    int rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+      sum[i] += items[i].response;
+      if (responses) responses[3 * i + pass] = items[i].response;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (responses && !use_fine) { responses[3 * i + 1] = 0.0; responses[3 * i + 2] = 0.0; }
+    scores[i] = sum[i] / n_pass;
+  }
+  return RSM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* rsm_version(void) { return "rsm 0.1 (sm_100a)"; }
+
+int rsm_create(int device, rsm_ctx** out) {
+  if (!out) return RSM_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return RSM_ERR_NO_DEVICE;
+  }
+  rsm_ctx* ctx = new rsm_ctx;
+  std::memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->t0) != cudaSuccess || cudaEventCreate(&ctx->t1) != cudaSuccess) {
+    delete ctx;
+    return RSM_ERR_CUDA;
+  }
+  *out = ctx;
+  return RSM_OK;
+}
+
+void rsm_destroy(rsm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  Buf* dev[] = {&ctx->d_work, &ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids};
+  for (Buf* b : dev) if (b->p) cudaFree(b->p);
+  if (ctx->h_up.p) cudaFreeHost(ctx->h_up.p);
+  if (ctx->h_down.p) cudaFreeHost(ctx->h_down.p);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* rsm_last_error(const rsm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rsm_set_profiling(rsm_ctx* ctx, int on) { if (!ctx) return RSM_ERR_INVALID; ctx->profiling = on != 0; return RSM_OK; }
+int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out) { if (!ctx || !out) return RSM_ERR_INVALID; *out = ctx->stats; return RSM_OK; }
+int rsm_reset_stats(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; std::memset(&ctx->stats, 0, sizeof ctx->stats); return RSM_OK; }
+int rsm_synchronize(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; return sync_stream(ctx); }
+
+int rsm_timer_start(rsm_ctx* ctx) {
+  if (!ctx) return RSM_ERR_INVALID;
+  CU(cudaEventRecord(ctx->t0, ctx->stream));
+  return RSM_OK;
+}
+int rsm_timer_stop(rsm_ctx* ctx, double* elapsed_ms) {
+  if (!ctx || !elapsed_ms) return RSM_ERR_INVALID;
+  CU(cudaEventRecord(ctx->t1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->t1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+  *elapsed_ms = ms;
+  return RSM_OK;
+}
+
+int rsm_flush_l2(rsm_ctx* ctx) {
+  if (!ctx) return RSM_ERR_INVALID;
+  const size_t bytes = size_t(256) << 20;
+  int rc = ensure_dev(ctx, ctx->d_flush, bytes);
+  if (rc) return rc;
+  CU(launch_flush(ctx->stream, ctx->d_flush.p, (long long)bytes, 1));
+  return sync_stream(ctx);
+}
+
+// ---- grids -----------------------------------------------------------------------------------
+int rsm_grid_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, double offset_x, double offset_y, rsm_grid** out) {
+  if (!ctx || !out || size_x <= 0 || size_y <= 0 || !(resolution > 0)) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_create: bad arguments");
+  rsm_grid* g = new rsm_grid;
+  g->size_x = size_x; g->size_y = size_y; g->pitch = size_x;
+  g->resolution = resolution;
+  g->scale = 1.0 / resolution;                 // GridMapBase ctor, map/grid_map_base.h:50
+  g->off_x = offset_x; g->off_y = offset_y;
+  g->tf.set(g->scale, offset_x, offset_y);
+  const size_t bytes = (size_t(size_x) * size_y * 4 + 15) / 16 * 16;
+  cudaError_t e = cudaMalloc(&g->d_cells, bytes);
+  if (e != cudaSuccess) { delete g; return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(grid) failed: %s", cudaGetErrorString(e)); }
+  *out = g;
+  return RSM_OK;
+}
+
+void rsm_grid_destroy(rsm_ctx* ctx, rsm_grid* grid) {
+  if (!grid) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (grid->owned && grid->d_cells) cudaFree(grid->d_cells);
+  delete grid;
+}
+
+int rsm_grid_set_offset(rsm_ctx* ctx, rsm_grid* grid, double offset_x, double offset_y) {
+  if (!grid) return fail(ctx, RSM_ERR_INVALID, "null grid");
+  grid->off_x = offset_x; grid->off_y = offset_y;
+  grid->tf.set(grid->scale, offset_x, offset_y);   // set_map_offset -> SetMapTransform (grid_map_base.h:285-289)
+  return RSM_OK;
+}
+
+int rsm_grid_upload_f32(rsm_ctx* ctx, rsm_grid* grid, const float* prob) {
+  if (!ctx || !grid || !prob) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_upload_f32: null argument");
+  const size_t n = size_t(grid->size_x) * grid->size_y;
+  int rc = ensure_pinned(ctx, ctx->h_up, n * 4);
+  if (rc) return rc;
+  int* fx = reinterpret_cast<int*>(ctx->h_up.p);
+  bool ok = true;
+  for (size_t i = 0; i < n; ++i) if (!fix_ok(prob[i], &fx[i])) { ok = false; break; }
+  if (!ok) std::memcpy(ctx->h_up.p, prob, n * 4);
+  grid->fixed = ok;
+  CU(cudaMemcpyAsync(grid->d_cells, ctx->h_up.p, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.h2d_bytes += n * 4;
+  grid->init = true;
+  return RSM_OK;
+}
+
+int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out) {
+  if (!ctx || !grid || !prob_out) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_download_f32: null argument");
+  const size_t n = size_t(grid->size_x) * grid->size_y;
+  int rc = ensure_pinned(ctx, ctx->h_down, n * 4);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_down.p, grid->d_cells, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.d2h_bytes += n * 4;
+  if (grid->fixed) {
+    const int* fx = reinterpret_cast<const int*>(ctx->h_down.p);
+    for (size_t i = 0; i < n; ++i) prob_out[i] = static_cast<float>(std::ldexp(static_cast<double>(fx[i]), -kFixShift));
+  } else {
+    std::memcpy(prob_out, ctx->h_down.p, n * 4);
+  }
+  return RSM_OK;
+}
+
+int rsm_grid_is_fixed_point(const rsm_grid* grid) { return grid && grid->fixed ? 1 : 0; }
+
+int rsm_world_to_map(const rsm_grid* grid, const double pose_world[3], double pose_map[3]) {
+  if (!grid) return RSM_ERR_INVALID;
+  grid->tf.world_to_map(pose_world, pose_map);
+  return RSM_OK;
+}
+int rsm_map_to_world(const rsm_grid* grid, const double pose_map[3], double pose_world[3]) {
+  if (!grid) return RSM_ERR_INVALID;
+  grid->tf.map_to_world(pose_map, pose_world);
+  return RSM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// GaussianBlur (map/occu_grid_map.h:40-59, 83-105): -1 if the parameters are rejected
+int blur_kernel(double sigma, double resolution, std::vector<double>& k) {
+  const double lo = 0.5 * resolution, hi = 10 * resolution;
+  if (!(sigma > lo && sigma < hi && resolution > 0)) return -1;
+  const int half = static_cast<int>((sigma / resolution) * std::sqrt(std::log(2)));
+  const int n = 2 * half + 1;
+  k.assign(size_t(n) * n, 0.0);
+  for (int i = -half; i <= half; ++i)
+    for (int j = -half; j <= half; ++j) {
+      const double d = std::hypot(i * resolution, j * resolution);
+      const double q = d / sigma;
+      k[(i + half) + n * (j + half)] = std::exp(-0.5 * (q * q));
+    }
+  return half;
+}
+
+struct RasterPlan {
+  bool fixed = true;
+  int half = 0, one = 0, fill = 0;
+  std::vector<int> stamp;
+};
+
+// Decide the cell representation for a rasterised grid and build the stamp patterns.
+int plan_raster(rsm_ctx* ctx, float default_prob, double sigma, double resolution, double occu_offset, int use_blur, RasterPlan& pl) {
+  std::vector<double> k;
+  const int half = blur_kernel(sigma, resolution, k);
+  if (!use_blur || half < 0)
+    return fail(ctx, RSM_ERR_UNSUPPORTED, "only the blur (SET_CELL_OCCUPIED_BLUR) construction path is provided");
+  pl.half = half;
+  const int ks = 2 * half + 1;
+  std::vector<float> probs(size_t(ks) * ks);
+  for (size_t i = 0; i < probs.size(); ++i) probs[i] = static_cast<float>(k[i] * occu_offset);   // :567
+  int tmp;
+  bool fixed = fix_ok(default_prob, &tmp);
+  for (float p : probs) if (p <= 1.0f && !(p >= 0.0f && fix_ok(p, &tmp))) fixed = false;
+  if (!(default_prob >= 0.0f)) return fail(ctx, RSM_ERR_INVALID, "default_prob must be >= 0");
+  pl.fixed = fixed;
+  pl.stamp.assign(probs.size(), 0);
+  for (size_t i = 0; i < probs.size(); ++i) {
+    const float p = probs[i];
+    if (!(p <= 1.0f) || !(p > 0.0f)) continue;   // prob > 1 is ignored by SetGridProbability; <= 0 never raises a cell
+    if (fixed) fix_ok(p, &pl.stamp[i]); else std::memcpy(&pl.stamp[i], &p, 4);
+  }
+  const float onef = 1.0f;
+  if (fixed) { pl.one = kFixOne; fix_ok(default_prob, &pl.fill); }
+  else { std::memcpy(&pl.one, &onef, 4); std::memcpy(&pl.fill, &default_prob, 4); }
+  return RSM_OK;
+}
+
+// Fill the RasterScan of one base scan (host libm cos/sin = Eigen::Rotation2Dd, occu_grid_map.h:278-303)
+void make_raster_scan(const rsm_grid* g, const double* pose_world, const double* d_pts, int n_pts, RasterScan& S) {
+  double pm[3];
+  g->tf.world_to_map(pose_world, pm);
+  const double c = std::cos(pm[2]), s = std::sin(pm[2]);
+  S.grid = g->d_cells; S.pts = d_pts; S.n_pts = n_pts;
+  S.pitch = g->pitch; S.size_x = g->size_x; S.size_y = g->size_y;
+  S.c = c; S.s = s; S.tx = pm[0]; S.ty = pm[1];
+  const double ox = pm[0] + (c * 0.0 + (-s) * 0.0), oy = pm[1] + (s * 0.0 + c * 0.0);
+  S.start_x = static_cast<int>(ox + 0.5);
+  S.start_y = static_cast<int>(oy + 0.5);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double sigma, double occu_offset, int use_blur,
+                       int n_scans, const int32_t* n_pts, const double* pts_xy, const double* poses_world) {
+  if (!ctx || !grid || n_scans < 0 || (n_scans > 0 && (!n_pts || !pts_xy || !poses_world)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_grid_rasterize: bad arguments");
+  RasterPlan pl;
+  int rc = plan_raster(ctx, default_prob, sigma, grid->resolution, occu_offset, use_blur, pl);
+  if (rc) return rc;
+  size_t total = 0;
+  for (int s = 0; s < n_scans; ++s) total += size_t(n_pts[s]);
+  Layout dl;
+  const size_t o_fill = dl.take(sizeof(FillJob));
+  const size_t o_scans = dl.take(sizeof(RasterScan) * std::max(1, n_scans));
+  const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t up_bytes = dl.off;
+  rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+  if (rc) return rc;
+  double* d_pts = nullptr;
+  if (total) { rc = upload_points(ctx, pts_xy, total, &d_pts); if (rc) return rc; }
+  char* up = ctx->h_up.p;
+  char* dw = ctx->d_work.p;
+  FillJob F; F.grid = grid->d_cells; F.n_cells = (long long)grid->size_x * grid->size_y; F.value = pl.fill;
+  std::memcpy(up + o_fill, &F, sizeof F);
+  RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
+  size_t off = 0;
+  for (int s = 0; s < n_scans; ++s) {
+    make_raster_scan(grid, poses_world + 3 * s, d_pts + 2 * off, n_pts[s], hs[s]);
+    off += n_pts[s];
+  }
+  std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += up_bytes;
+  {
+    Prof p(ctx, KC_RASTER);
+    CU(launch_fill(1, 148, ctx->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
+    CU(launch_raster(n_scans, ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scans),
+                     reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+  }
+  ctx->stats.kernel_launches += (n_scans > 0) ? 2 : 1;
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  grid->fixed = pl.fixed;
+  if (n_scans > 0) grid->init = true;   // SetUpdated() per UpdateMapByRange (occu_grid_map.h:325)
+  return RSM_OK;
+}
+
+// ---- matching ----------------------------------------------------------------------------------
+int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
+              double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  if (!ctx || !grid || !param || !pose_world || !cov || !response || n_pts < 0 || (n_pts > 0 && !pts_xy))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match: bad arguments");
+  *response = 0.0;
+  if (detail) std::memset(detail, 0, sizeof *detail);
+  if (!grid->init || n_pts == 0) return RSM_OK;   // correlate_scan_matcher.h:792-795
+  double* d_pts = nullptr;
+  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
+  if (rc) return rc;
+  std::vector<PassItem> items(1);
+  items[0].grid = grid; items[0].d_pts = d_pts; items[0].P = n_pts; items[0].param = *param;
+  items[0].pose_world = pose_world; items[0].cov = cov;
+  rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+  if (rc) return rc;
+  *response = items[0].response;
+  if (detail) *detail = items[0].detail;
+  return RSM_OK;
+}
+
+int rsm_match_chain(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param params[3],
+                    int use_fine, double pose_world[3], double cov[9], double* score, double responses[3]) {
+  if (!ctx || !grid || !params || !pose_world || !cov || !score || n_pts < 0 || (n_pts > 0 && !pts_xy))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_chain: bad arguments");
+  double* d_pts = nullptr;
+  if (n_pts > 0) { int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts); if (rc) return rc; }
+  const rsm_grid* grids[1] = {grid};
+  double* dp[1] = {d_pts};
+  int np[1] = {n_pts};
+  return run_chain(ctx, 1, grids, dp, np, params, true, use_fine != 0, pose_world, cov, score, responses);
+}
+
+int rsm_match_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* pts_xy, const int64_t* pts_offset,
+                    const rsm_pass_param* params, int shared_params, int use_fine, double* poses_world, double* covs,
+                    double* scores, double* responses) {
+  if (!ctx || n < 0 || (n > 0 && (!grids || !pts_offset || !params || !poses_world || !covs || !scores)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_batch: bad arguments");
+  if (n == 0) return RSM_OK;
+  const size_t total = size_t(pts_offset[n]);
+  double* d_pts = nullptr;
+  if (total) { int rc = upload_points(ctx, pts_xy, total, &d_pts); if (rc) return rc; }
+  std::vector<double*> dp(n);
+  std::vector<int> np(n);
+  for (int i = 0; i < n; ++i) { dp[i] = d_pts + 2 * pts_offset[i]; np[i] = int(pts_offset[i + 1] - pts_offset[i]); }
+  return run_chain(ctx, n, grids, dp.data(), np.data(), params, shared_params != 0, use_fine != 0, poses_world, covs, scores, responses);
+}
+
+int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob, double sigma,
+                           double occu_offset, const double* centres_world, const int64_t* scan_offset,
+                           const int32_t* base_n_pts, const double* base_pts_xy, const double* base_poses_world,
+                           const double* pts_xy, const int64_t* pts_offset, const rsm_pass_param params[3], int use_fine,
+                           double* poses_world, double* covs, double* scores, double* responses) {
+  if (!ctx || n < 0 || grid_size <= 0 || !(resolution > 0) ||
+      (n > 0 && (!centres_world || !scan_offset || !base_n_pts || !base_pts_xy || !base_poses_world || !pts_xy ||
+                 !pts_offset || !params || !poses_world || !covs || !scores)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_loop_closure_batch: bad arguments");
+  if (n == 0) return RSM_OK;
+  RasterPlan pl;
+  int rc = plan_raster(ctx, default_prob, sigma, resolution, occu_offset, 1, pl);
+  if (rc) return rc;
+  // grids: one pool, one slot per pair
+  const size_t cells = size_t(grid_size) * grid_size;
+  const size_t slot = (cells * 4 + 255) / 256 * 256;
+  rc = ensure_dev(ctx, ctx->d_pool_grids, slot * n);
+  if (rc) return rc;
+  std::vector<rsm_grid> gs(n);
+  std::vector<const rsm_grid*> gp(n);
+  const double scale = 1.0 / resolution;
+  const double cell_len = 1 / scale;
+  for (int i = 0; i < n; ++i) {
+    rsm_grid& g = gs[i];
+    g.size_x = g.size_y = g.pitch = grid_size;
+    g.resolution = resolution; g.scale = scale;
+    // ResetScanMatchMapWithRangeVec: offset = -(pose - 0.5 * size * cell_len)   (slam_processor.cpp:451-455)
+    g.off_x = -(centres_world[2 * i] - 0.5 * grid_size * cell_len);
+    g.off_y = -(centres_world[2 * i + 1] - 0.5 * grid_size * cell_len);
+    g.tf.set(scale, g.off_x, g.off_y);
+    g.fixed = pl.fixed; g.owned = false;
+    g.d_cells = ctx->d_pool_grids.p + slot * i;
+    g.init = scan_offset[i + 1] > scan_offset[i];
+    gp[i] = &g;
+  }
+  // points: [base scans | match scans] in one upload
+  const int64_t n_base_scans = scan_offset[n];
+  size_t base_pts_total = 0;
+  for (int64_t s = 0; s < n_base_scans; ++s) base_pts_total += size_t(base_n_pts[s]);
+  const size_t match_pts_total = size_t(pts_offset[n]);
+  rc = ensure_dev(ctx, ctx->d_pts, (base_pts_total + match_pts_total) * 16);
+  if (rc) return rc;
+  double* d_base = reinterpret_cast<double*>(ctx->d_pts.p);
+  double* d_match = d_base + 2 * base_pts_total;
+  if (base_pts_total) CU(cudaMemcpyAsync(d_base, base_pts_xy, base_pts_total * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (match_pts_total) CU(cudaMemcpyAsync(d_match, pts_xy, match_pts_total * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += (base_pts_total + match_pts_total) * 16;
+  // raster descriptors
+  Layout dl;
+  const size_t o_fill = dl.take(sizeof(FillJob) * n);
+  const size_t o_scans = dl.take(sizeof(RasterScan) * std::max<int64_t>(1, n_base_scans));
+  const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t up_bytes = dl.off;
+  rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+  if (rc) return rc;
+  char* up = ctx->h_up.p;
+  char* dw = ctx->d_work.p;
+  FillJob* hf = reinterpret_cast<FillJob*>(up + o_fill);
+  RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
+  size_t poff = 0;
+  for (int i = 0; i < n; ++i) {
+    hf[i].grid = gs[i].d_cells; hf[i].n_cells = (long long)cells; hf[i].value = pl.fill;
+    for (int64_t s = scan_offset[i]; s < scan_offset[i + 1]; ++s) {
+      make_raster_scan(&gs[i], base_poses_world + 3 * s, d_base + 2 * poff, base_n_pts[s], hs[s]);
+      poff += base_n_pts[s];
+    }
+  }
+  std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += up_bytes;
+  {
+    Prof p(ctx, KC_RASTER);
+    CU(launch_fill(n, 4, ctx->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
+    CU(launch_raster(int(n_base_scans), ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scans),
+                     reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+  }
+  ctx->stats.kernel_launches += 2;
+  // run_pass reuses d_work and the pinned staging: the raster launches above must have consumed them first
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  std::vector<double*> dp(n);
+  std::vector<int> np(n);
+  for (int i = 0; i < n; ++i) { dp[i] = d_match + 2 * pts_offset[i]; np[i] = int(pts_offset[i + 1] - pts_offset[i]); }
+  return run_chain(ctx, n, gp.data(), dp.data(), np.data(), params, true, use_fine != 0, poses_world, covs, scores, responses);
+}
+
+int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
+                    const double pose_world[3], int angle_begin, int angle_end, double* scores_out, int64_t capacity,
+                    int64_t* n_written) {
+  if (!ctx || !grid || !param || !pose_world || !scores_out || n_pts <= 0 || !pts_xy)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_pass_scores: bad arguments");
+  if (!grid->init) return fail(ctx, RSM_ERR_NOT_INIT, "grid has no content");
+  double* d_pts = nullptr;
+  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
+  if (rc) return rc;
+  double pose[3] = {pose_world[0], pose_world[1], pose_world[2]};
+  double cov[9];
+  std::vector<PassItem> items(1);
+  items[0].grid = grid; items[0].d_pts = d_pts; items[0].P = n_pts; items[0].param = *param;
+  items[0].pose_world = pose; items[0].cov = cov;
+  items[0].ang_begin = angle_begin; items[0].ang_end = angle_end;
+  return run_pass(ctx, items, MODE_SCORES, scores_out, capacity, n_written);
+}
+
+int rsm_match_partial(rsm_ctx* ctx, const rsm_grid*, const double*, int, const rsm_pass_param*, const double*, int, int, void*) {
+  return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_match_partial: not built yet");
+}
+int rsm_match_finish(rsm_ctx* ctx, const rsm_grid*, const double*, int, const rsm_pass_param*, const void* const*, int,
+                     double*, double*, double*, rsm_pass_detail*) {
+  return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_match_finish: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// rsm_device.h -- structures shared by the host orchestration (rsm_api.cu) and the kernels
+// (rsm_kernels.cu).  Plain-old-data only; everything a kernel needs about one job is in one
+// struct so that a batched launch is "an array of jobs + a CTA prefix array".
+#ifndef RSM_DEVICE_H_
+#define RSM_DEVICE_H_
+
+#include <stdint.h>
+
+namespace rsm {
+
+// Lookup-grid cells are held either as exact fixed point (value * 2^25 in an int32; every
+// probability the reference writes is a multiple of 2^-25) or as the raw
+// float32 the reference stores (fallback when some value is not representable).
+constexpr int kFixShift = 25;
+constexpr double kFixScale = 1.0 / 33554432.0;  // 2^-25
+constexpr int kFixOne = 1 << kFixShift;
+
+constexpr int kTopK = 21;          // top-20 covariance prefix + 1 to detect a tie at the cut
+constexpr int kChunk = 32;         // beams per shared-memory table chunk of the scoring kernel
+constexpr int kSelectBuf = 2048;   // per-CTA candidate buffer of the selection kernel
+constexpr int kMaxCols = 9;        // same-(x,y) columns gathered for the angular covariance
+
+enum ErrBits {
+  kErrWindow = 1,       // a candidate's endpoint cell fell outside the grid (index was clamped)
+  kErrPoolFull = 2,     // averaging-set pool overflowed its capacity
+  kErrSelectFull = 4    // selection buffer overflowed (massive ties / flat score field)
+};
+
+struct Entry {  // one candidate handed back to the host
+  double score;
+  long long index;
+};
+
+// One scoring job = one pass of one match restricted to an angle slice.
+struct ScoreJob {
+  const void* grid;      // int32 fixed-point or float32 cells, row-major, `pitch` cells per row
+  const double* pts;     // P x 2 scan points, cells, sensor frame
+  const double* trig;    // n_ang x 3 : cos(angle_i), sin(angle_i), angle_i   (host libm values)
+  double* score;         // out: ang_count * n_xy * n_xy penalised scores, candidate order
+  unsigned long long* best_key;  // out: atomicMax of the order-preserving key of the scores
+  int* err;              // out: OR of ErrBits
+  int pitch, size_x, size_y;
+  int P, step, V;        // points, beam stride, beams visited = ceil(P/step)
+  int n_xy, ang_begin, ang_count;
+  int tiles_x, tiles_y;  // candidate tiles per angle
+  int use_penalty;
+  double divisor;        // use_point_size after the reference's adjustment (:561-566)
+  double sx, sy, f;      // search_space_start_x/y and space_step_factor (:546-548), in cells
+  double cx, cy, ca;     // centre pose in map coordinates
+  double m2;             // cell_len * cell_len
+  double half_size;      // search_space_size / 2
+  double gain;           // distance penalty gain (:759-761)
+};
+
+// Averaging-set candidates of all jobs of a launch land in one pool (appended with an atomic
+// counter, so the order is arbitrary; the host buckets by job and sorts).
+struct PoolEntry {
+  double score;
+  int index;   // candidate index within the job's score array
+  int job;
+};
+
+struct SelectJob {
+  const double* score;
+  long long n;                          // candidates in this job
+  const unsigned long long* best_key;   // written by the scoring kernel
+  Entry* top_list; int* top_count;      // per-CTA top-kTopK lists: top_list[cta*kTopK + r], top_count[cta]
+  int* err;
+  int job_id;
+  int n_cta;                            // CTAs working on this job
+  long long slice;                      // candidates per CTA
+};
+
+struct GatherJob {
+  const double* score;
+  double* out;           // out[c * n_ang + ia]
+  int n_xy, n_ang, n_cols;
+  int cols[kMaxCols];    // ix * n_xy + iy
+};
+
+// One base scan to stamp into one grid.
+struct RasterScan {
+  void* grid;
+  const double* pts;     // this scan's points (cells, sensor frame)
+  int n_pts;
+  int pitch, size_x, size_y;
+  int start_x, start_y;  // beam start cell (sensor origin), points landing there are skipped
+  double c, s, tx, ty;   // Translation(tx,ty) * Rotation(theta) with host libm cos/sin
+};
+
+struct FillJob {
+  void* grid;
+  long long n_cells;
+  int value;             // raw 32-bit pattern (fixed-point int or float bits)
+};
+
+}  // namespace rsm
+
+#endif

@@ -1,0 +1,224 @@
+// rsm_host.h -- host-side exact arithmetic of the matcher: map transforms, pass geometry and the
+// finalisation the reference performs on its sorted candidate vector (FindBestCandidate and the
+// two covariance routines).  Header-only, plain C++; compiled for baseline x86-64 with
+// -ffp-contract=off so that every expression is evaluated as the reference's build evaluates it.
+// All citations are file:line under the reference's src/.
+#ifndef RSM_HOST_H_
+#define RSM_HOST_H_
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/rsm.h"
+
+namespace rsm {
+
+constexpr double kMaxVariance = 500.0;          // util/slam_util.h:57
+constexpr double kDoubleTolerance = 1e-06;      // util/slam_util.h:59
+constexpr int kMaxVarianceUsePointSize = 20;    // scan_match/correlate_scan_matcher.h:1033
+constexpr double kResponseFilterTolerance = 1e-2;  // :763
+
+// util/slam_util.h:70-73
+inline bool DoubleEqual(double a, double b, double tolerance = kDoubleTolerance) {
+  const double delta = a - b;
+  return delta < 0.0 ? delta >= -std::fabs(tolerance) : delta <= std::fabs(tolerance);
+}
+// util/slam_util.h:75-77
+inline double Round(double value) { return value >= 0.0 ? std::floor(value + 0.5) : std::ceil(value - 0.5); }
+
+// world <-> map of GridMapBase (map/grid_map_base.h:68-93).  The reference builds
+// world_to_map = AlignedScaling2d(s,s) * Translation2d(offset) and inverts it with Eigen; the
+// member values and the products below follow Eigen 3.3's evaluation order: linear part diag(s,s),
+// translation (s*ox, s*oy); inverse via invdet = 1/(s*s - 0*0); Affine*v = t + (l00*x + l01*y).
+struct MapTransform {
+  double s, tx, ty;
+  double i00, i01, i10, i11, itx, ity;
+  void set(double scale, double off_x, double off_y) {
+    s = scale;
+    tx = scale * off_x;
+    ty = scale * off_y;
+    const double l00 = scale, l01 = 0.0, l10 = 0.0, l11 = scale;
+    const double det = l00 * l11 - l10 * l01;
+    const double invdet = 1.0 / det;
+    i00 = l11 * invdet;
+    i10 = -l10 * invdet;
+    i01 = -l01 * invdet;
+    i11 = l00 * invdet;
+    itx = (-i00) * tx + (-i01) * ty;
+    ity = (-i10) * tx + (-i11) * ty;
+  }
+  void world_to_map(const double* w, double* m) const {
+    m[0] = tx + (s * w[0] + 0.0 * w[1]);
+    m[1] = ty + (0.0 * w[0] + s * w[1]);
+    m[2] = w[2];
+  }
+  void map_to_world(const double* m, double* w) const {
+    w[0] = itx + (i00 * m[0] + i01 * m[1]);
+    w[1] = ity + (i10 * m[0] + i11 * m[1]);
+    w[2] = m[2];
+  }
+};
+
+// Everything about one pass that follows from (param, P, cell_len, centre).
+struct PassGeo {
+  int n_ang, n_xy, step, divisor, visited;
+  double start_x, start_y, factor, start_angle, ares;
+  double cell_len, center[3];
+  int64_t n_cand() const { return int64_t(n_ang) * n_xy * n_xy; }
+  double x_of(int ix) const { return start_x + ix * factor; }      // :569
+  double y_of(int iy) const { return start_y + iy * factor; }      // :572
+  double angle_of(int ia) const { return start_angle + ia * ares; }  // :164
+  void decode(int64_t k, int* ia, int* ix, int* iy) const {
+    *iy = int(k % n_xy);
+    *ix = int((k / n_xy) % n_xy);
+    *ia = int(k / (int64_t(n_xy) * n_xy));
+  }
+};
+
+inline PassGeo make_geo(const rsm_pass_param& q, int P, double cell_len, const double* center) {
+  PassGeo g;
+  const double angle_offset = (q.search_angle_offset * 2) / 2;   // serach_angle_size_ / 2 (:526, :536)
+  g.n_ang = static_cast<int>(std::floor(angle_offset * 2 / q.search_angle_resolution) + 1);  // :154
+  g.start_angle = center[2] - angle_offset;                       // :161
+  g.ares = q.search_angle_resolution;
+  g.n_xy = static_cast<int>(Round(q.search_space_size / q.search_space_resolution) + 1);     // :538
+  g.start_x = center[0] - (q.search_space_size / cell_len) * 0.5;  // :546
+  g.start_y = center[1] - (q.search_space_size / cell_len) * 0.5;  // :547
+  g.factor = q.search_space_resolution / cell_len;                 // :548
+  int use = q.use_point_size;                                      // :561-566
+  if (P < 2 * use) { use = P; g.step = 1; } else { g.step = P / (use - 1); }
+  g.divisor = use;
+  g.visited = (P + g.step - 1) / g.step;
+  g.cell_len = cell_len;
+  g.center[0] = center[0]; g.center[1] = center[1]; g.center[2] = center[2];
+  return g;
+}
+
+struct Cand {
+  double score;
+  int64_t index;
+};
+
+struct BestPose {
+  double x, y, angle, score;
+  int n_avg;
+};
+
+inline bool by_score_desc(const Cand& a, const Cand& b) { return a.score > b.score; }
+
+// FindBestCandidate (:670-710).  `a` = the candidates with DoubleEqual(score, top, 1e-2), sorted
+// by descending score in the reference's order; a[0] is the top candidate.
+inline BestPose find_best(const PassGeo& g, const Cand* a, size_t n) {
+  BestPose b;
+  int ia, ix, iy;
+  g.decode(a[0].index, &ia, &ix, &iy);
+  b.x = g.x_of(ix); b.y = g.y_of(iy); b.angle = g.angle_of(ia); b.score = a[0].score;
+  double ax = 0.0, ay = 0.0, tx = 0.0, ty = 0.0, ssum = 0.0;
+  int count = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (!DoubleEqual(a[i].score, b.score, kResponseFilterTolerance)) break;
+    g.decode(a[i].index, &ia, &ix, &iy);
+    const double s = a[i].score, ang = g.angle_of(ia);
+    ax += g.x_of(ix) * s;
+    ay += g.y_of(iy) * s;
+    tx += std::cos(ang) * s;
+    ty += std::sin(ang) * s;
+    ssum += s;
+    ++count;
+  }
+  if (count > 1) {
+    ax /= ssum; ay /= ssum; tx /= ssum; ty /= ssum;
+    b.x = ax; b.y = ay; b.angle = std::atan2(ty, tx);
+  }
+  b.n_avg = count;
+  return b;
+}
+
+inline double max_angular_variance(const rsm_pass_param& q) {
+  return 4 * (q.search_angle_resolution * q.search_angle_resolution);  // :801
+}
+
+// ComputePositionalCovariance (:887-956).  `top` = the head of the sorted candidate vector
+// (at least min(n_cand, 20) entries).  cov row-major 3x3.
+inline void positional_cov(const PassGeo& g, const rsm_pass_param& q, const BestPose& best,
+                           const Cand* top, size_t n_top, double* cov) {
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cov[3 * r + c] = (r == c) ? 1.0 : 0.0;
+  const double mav = max_angular_variance(q);
+  if (best.score < kDoubleTolerance) {
+    cov[0] = kMaxVariance; cov[4] = kMaxVariance; cov[8] = mav;
+    return;
+  }
+  double vxx = 0.0, vxy = 0.0, vyy = 0.0, norm = 0.0;
+  const double bound = std::min(best.score - 0.1, 0.5);
+  int used = 0;
+  for (size_t i = 0; i < n_top; ++i) {
+    const double s = top[i].score;
+    if (s > bound && used < kMaxVarianceUsePointSize) {
+      int ia, ix, iy;
+      g.decode(top[i].index, &ia, &ix, &iy);
+      const double x = g.x_of(ix), y = g.y_of(iy);
+      norm += s;
+      vxx += ((x - best.x) * (x - best.x)) * s;
+      vxy += ((x - best.x) * (y - best.y) * s);
+      vyy += ((y - best.y) * (y - best.y)) * s;
+      ++used;
+    } else {
+      break;
+    }
+  }
+  if (norm > kDoubleTolerance) {
+    double xx = vxx / norm, xy = vxy / norm, yy = vyy / norm;
+    const double r = q.search_space_resolution / g.cell_len;
+    const double min_variance = 0.1 * (r * r);
+    xx = std::max<double>(xx, min_variance);
+    yy = std::max<double>(yy, min_variance);
+    const double m2 = g.cell_len * g.cell_len;
+    cov[0] = (xx * m2) / best.score;
+    cov[1] = (xy * m2) / best.score;
+    cov[3] = (xy * m2) / best.score;
+    cov[4] = (yy * m2) / best.score;
+    cov[8] = mav;
+  }
+  if (DoubleEqual(cov[0], 0.0)) cov[0] = kMaxVariance;
+  if (DoubleEqual(cov[4], 0.0)) cov[4] = kMaxVariance;
+}
+
+inline double cov_score_bound(const BestPose& best) { return std::min(best.score - 0.1, 0.5); }
+
+inline bool same_xy(const PassGeo& g, const BestPose& best, int ix, int iy) {
+  const double tol = g.factor;  // linear_tolerance = search resolution / map resolution (:840)
+  return DoubleEqual(g.x_of(ix), best.x, tol) && DoubleEqual(g.y_of(iy), best.y, tol);
+}
+
+// ComputeAngularCovariance (:965-1019).  `xy` = the candidates with the "same" (x,y) as the best
+// pose and score >= bound, in sorted order (at least the first 20 of them).
+inline void angular_cov(const PassGeo& g, const rsm_pass_param& q, const BestPose& best,
+                        const Cand* xy, size_t n_xy_list, double* cov) {
+  const double mav = max_angular_variance(q);
+  if (best.score < kDoubleTolerance) { cov[8] = mav; return; }
+  const double bound = cov_score_bound(best);
+  double norm = 0.0, acc = 0.0;
+  int used = 0;
+  for (size_t i = 0; i < n_xy_list; ++i) {
+    const double s = xy[i].score;
+    if (s >= bound && used < kMaxVarianceUsePointSize) {
+      int ia, ix, iy;
+      g.decode(xy[i].index, &ia, &ix, &iy);
+      if (same_xy(g, best, ix, iy)) {
+        const double a = g.angle_of(ia);
+        norm += s;
+        acc += ((a - best.angle) * (a - best.angle)) * s;
+        ++used;
+      }
+    }
+  }
+  double var;
+  if (norm > kDoubleTolerance) var = acc / norm;   // (:1008-1012: the /4 value is overwritten)
+  else var = 200 * mav;
+  cov[8] = var;
+}
+
+}  // namespace rsm
+#endif

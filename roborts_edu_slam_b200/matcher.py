@@ -1,0 +1,404 @@
+"""Host-side mirror of the reference's matcher interface over the C ABI (include/rsm.h).
+
+The reference is C++ (its drop-in adapter is roborts_edu_slam_b200/csrc/scan_matcher_adapter.hpp);
+this module is the same surface for Python callers -- tests, bench.py and torch.distributed
+launchers -- with the reference's names and argument meaning:
+
+  CorrelationScanMatchParam      scan_match/correlate_scan_matcher.h:41-86
+  ScanMatchMap                   map/slam_map.h:32-34 (device-resident lookup grid)
+  BasedCorrelationScanMatch      .ScanMatch(map, scan, param, pose, cov) -> response   (:784-875)
+  ScanMatchers                   .ScanMatch(scan, map, pose, cov, use_fine) -> score   (scan_matchers.h:179-289)
+
+Every compute call goes to librsm.so (CUDA, sm_100a).  There is no CPU path: importing works
+without a GPU (so the ABI can be inspected), creating a Context does not.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsm.so")
+
+COARSE_CORRELATION_SCAN_MATCH = 0
+FINE_CORRELATION_SCAN_MATCH = 1
+SUPER_CORRELATION_SCAN_MATCH = 2
+FAST_CORRELATION_SCAN_MATCH = 3
+
+RSM_OK = 0
+STATUS_NAMES = {0: "RSM_OK", 1: "RSM_ERR_NO_DEVICE", 2: "RSM_ERR_CUDA", 3: "RSM_ERR_INVALID",
+                4: "RSM_ERR_WINDOW", 5: "RSM_ERR_UNSUPPORTED", 6: "RSM_ERR_NOT_INIT"}
+
+c_d, c_i, c_p, c_i64 = ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64
+
+
+class RsmError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+class PassParamStruct(ctypes.Structure):
+    _fields_ = [("search_space_size", c_d), ("search_space_resolution", c_d),
+                ("search_angle_offset", c_d), ("search_angle_resolution", c_d),
+                ("response_threshold", c_d), ("use_point_size", ctypes.c_int32),
+                ("use_center_penalty", ctypes.c_int32), ("type", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+class PassDetail(ctypes.Structure):
+    _fields_ = [("best_score", c_d), ("best_pose_map", c_d * 3), ("n_candidates", c_i64),
+                ("n_avg", ctypes.c_int32), ("exact_sort_used", ctypes.c_int32),
+                ("pose_updated", ctypes.c_int32), ("n_ang", ctypes.c_int32), ("n_xy", ctypes.c_int32),
+                ("visited", ctypes.c_int32), ("divisor", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("kernel_launches", c_i64), ("score_launches", c_i64), ("evals", c_i64), ("passes", c_i64),
+                ("exact_sort_passes", c_i64), ("h2d_bytes", c_i64), ("d2h_bytes", c_i64),
+                ("score_kernel_ms", c_d), ("raster_kernel_ms", c_d), ("select_kernel_ms", c_d)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/rsm.h declares: (restype, argtypes)
+_PPARAM = ctypes.POINTER(PassParamStruct)
+ABI = {
+    "rsm_version": (ctypes.c_char_p, []),
+    "rsm_create": (c_i, [c_i, ctypes.POINTER(c_p)]),
+    "rsm_destroy": (None, [c_p]),
+    "rsm_last_error": (ctypes.c_char_p, [c_p]),
+    "rsm_set_profiling": (c_i, [c_p, c_i]),
+    "rsm_get_stats": (c_i, [c_p, ctypes.POINTER(Stats)]),
+    "rsm_reset_stats": (c_i, [c_p]),
+    "rsm_synchronize": (c_i, [c_p]),
+    "rsm_timer_start": (c_i, [c_p]),
+    "rsm_timer_stop": (c_i, [c_p, ctypes.POINTER(c_d)]),
+    "rsm_flush_l2": (c_i, [c_p]),
+    "rsm_grid_create": (c_i, [c_p, c_i, c_i, c_d, c_d, c_d, ctypes.POINTER(c_p)]),
+    "rsm_grid_destroy": (None, [c_p, c_p]),
+    "rsm_grid_set_offset": (c_i, [c_p, c_p, c_d, c_d]),
+    "rsm_grid_upload_f32": (c_i, [c_p, c_p, c_p]),
+    "rsm_grid_rasterize": (c_i, [c_p, c_p, ctypes.c_float, c_d, c_d, c_i, c_i, c_p, c_p, c_p]),
+    "rsm_grid_download_f32": (c_i, [c_p, c_p, c_p]),
+    "rsm_grid_is_fixed_point": (c_i, [c_p]),
+    "rsm_world_to_map": (c_i, [c_p, c_p, c_p]),
+    "rsm_map_to_world": (c_i, [c_p, c_p, c_p]),
+    "rsm_match": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_match_chain": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_i, c_p, c_p, ctypes.POINTER(c_d), c_p]),
+    "rsm_match_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, _PPARAM, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "rsm_loop_closure_batch": (c_i, [c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                     _PPARAM, c_i, c_p, c_p, c_p, c_p]),
+    "rsm_pass_scores": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p, c_i64, ctypes.POINTER(c_i64)]),
+    "rsm_match_partial": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p]),
+    "rsm_match_finish": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen librsm.so and bind every declared symbol; raises if the extension is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("librsm.so is missing (%s): build it with `python -m roborts_edu_slam_b200.build`; "
+                               "there is no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class CorrelationScanMatchParam:
+    """Same fields and accessors as the reference class (correlate_scan_matcher.h:41-86)."""
+
+    def __init__(self, search_space_size=0.0, search_space_resolution=0.0, search_angle_offset=0.0,
+                 search_angle_resolution=0.0, response_threshold=0.0, use_point_size=0, max_depth=0,
+                 use_center_penalty=True, correlation_scan_match_type=COARSE_CORRELATION_SCAN_MATCH):
+        self._v = dict(search_space_size=search_space_size, search_space_resolution=search_space_resolution,
+                       search_angle_offset=search_angle_offset, search_angle_resolution=search_angle_resolution,
+                       response_threshold=response_threshold, use_point_size=use_point_size, max_depth=max_depth,
+                       use_center_penalty=use_center_penalty, correlation_scan_match_type=correlation_scan_match_type)
+
+    def __getattr__(self, name):
+        v = self.__dict__.get("_v", {})
+        if name.startswith("set_") and name[4:] in v:
+            key = name[4:]
+            return lambda value: v.__setitem__(key, value)
+        if name in v:
+            return lambda: v[name]
+        raise AttributeError(name)
+
+    @classmethod
+    def from_array(cls, p):
+        """p = the 8-double block used by synth.pass_param / the oracle."""
+        return cls(p[0], p[1], p[2], p[3], p[4], int(p[5]), 0, bool(p[6]), int(p[7]))
+
+    def struct(self):
+        v = self._v
+        return PassParamStruct(v["search_space_size"], v["search_space_resolution"], v["search_angle_offset"],
+                               v["search_angle_resolution"], v["response_threshold"], int(v["use_point_size"]),
+                               1 if v["use_center_penalty"] else 0, int(v["correlation_scan_match_type"]), 0)
+
+
+def _as_param(p):
+    return p if isinstance(p, CorrelationScanMatchParam) else CorrelationScanMatchParam.from_array(p)
+
+
+class Context:
+    """One per GPU / caller thread (rsm_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = c_p()
+        rc = self.lib.rsm_create(int(device), ctypes.byref(h))
+        if rc != RSM_OK:
+            raise RsmError(rc, "rsm_create(device=%d) failed; this library has no CPU path" % device)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != RSM_OK:
+            raise RsmError(rc, (self.lib.rsm_last_error(self.h) or b"").decode())
+
+    def set_profiling(self, on):
+        self.check(self.lib.rsm_set_profiling(self.h, int(on)))
+
+    def stats(self):
+        s = Stats()
+        self.check(self.lib.rsm_get_stats(self.h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self.check(self.lib.rsm_reset_stats(self.h))
+
+    def synchronize(self):
+        self.check(self.lib.rsm_synchronize(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.rsm_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = c_d(0)
+        self.check(self.lib.rsm_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self.check(self.lib.rsm_flush_l2(self.h))
+
+
+class ScanMatchMap:
+    """Device-resident lookup grid with the reference map's geometry (OccuGridMap<ProbabilityCell>)."""
+
+    def __init__(self, ctx, resolution, size_x, size_y, offset_x, offset_y):
+        self.ctx = ctx
+        self.resolution, self.size_x, self.size_y = float(resolution), int(size_x), int(size_y)
+        h = c_p()
+        ctx.check(ctx.lib.rsm_grid_create(ctx.h, self.size_x, self.size_y, self.resolution,
+                                          float(offset_x), float(offset_y), ctypes.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_spec(cls, ctx, g):
+        return cls(ctx, g.res, g.size_x, g.size_y, g.off_x, g.off_y)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.rsm_grid_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map_offset(self, off_x, off_y):
+        self.ctx.check(self.ctx.lib.rsm_grid_set_offset(self.ctx.h, self.h, float(off_x), float(off_y)))
+
+    def upload(self, prob):
+        prob = np.ascontiguousarray(prob, dtype=np.float32)
+        assert prob.shape == (self.size_y, self.size_x), prob.shape
+        self.ctx.check(self.ctx.lib.rsm_grid_upload_f32(self.ctx.h, self.h, prob.ctypes.data))
+
+    def InitMapWithRangeVec(self, base_pts, base_poses, default_prob=0.3, sigma=0.15, occu_offset=0.88, use_blur=True):
+        """Device-side construction from base scans (points in cells, sensor frame; poses world)."""
+        n_pts = np.array([len(p) for p in base_pts], dtype=np.int32)
+        pts = _f64(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in base_pts], axis=0)) \
+            if len(base_pts) else np.zeros((0, 2))
+        poses = _f64(base_poses)
+        self.ctx.check(self.ctx.lib.rsm_grid_rasterize(self.ctx.h, self.h, float(default_prob), float(sigma),
+                                                       float(occu_offset), int(use_blur), len(base_pts),
+                                                       n_pts.ctypes.data, pts.ctypes.data, poses.ctypes.data))
+
+    def download(self):
+        out = np.empty((self.size_y, self.size_x), dtype=np.float32)
+        self.ctx.check(self.ctx.lib.rsm_grid_download_f32(self.ctx.h, self.h, out.ctypes.data))
+        return out
+
+    def is_fixed_point(self):
+        return bool(self.ctx.lib.rsm_grid_is_fixed_point(self.h))
+
+    def GetMapCoordsPose(self, pose_world):
+        w, out = _f64(pose_world), np.zeros(3)
+        self.ctx.check(self.ctx.lib.rsm_world_to_map(self.h, w.ctypes.data, out.ctypes.data))
+        return out
+
+    def GetWorldCoordsPose(self, pose_map):
+        m, out = _f64(pose_map), np.zeros(3)
+        self.ctx.check(self.ctx.lib.rsm_map_to_world(self.h, m.ctypes.data, out.ctypes.data))
+        return out
+
+
+class BasedCorrelationScanMatch:
+    """One pass: ScanMatch(map, range_data, param, current_pose, cov_matrix) -> response.
+
+    current_pose (3,) and cov_matrix (3,3) are numpy arrays updated IN PLACE, like the reference's
+    Eigen references (correlate_scan_matcher.h:784-788)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.last_detail = None
+
+    def ScanMatch(self, map_, range_data, scan_match_param, current_pose, cov_matrix):
+        ctx = self.ctx
+        pts = _f64(range_data).reshape(-1, 2)
+        assert current_pose.dtype == np.float64 and cov_matrix.dtype == np.float64
+        assert current_pose.flags.c_contiguous and cov_matrix.flags.c_contiguous
+        ps = _as_param(scan_match_param).struct()
+        resp = c_d(0)
+        det = PassDetail()
+        ctx.check(ctx.lib.rsm_match(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps),
+                                    current_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(resp),
+                                    ctypes.byref(det)))
+        self.last_detail = det
+        return resp.value
+
+    def scores(self, map_, range_data, scan_match_param, pose_world, angle_begin=0, angle_end=-1):
+        """Penalised score of every candidate, candidate order (parity tests)."""
+        ctx = self.ctx
+        pts = _f64(range_data).reshape(-1, 2)
+        p = _as_param(scan_match_param)
+        ps = p.struct()
+        n_ang = int(np.floor(ps.search_angle_offset * 2 / ps.search_angle_resolution) + 1)
+        r = ps.search_space_size / ps.search_space_resolution
+        n_xy = int((np.floor(r + 0.5) if r >= 0 else np.ceil(r - 0.5)) + 1)
+        a1 = n_ang if angle_end < 0 else angle_end
+        cap = max(1, (a1 - angle_begin) * n_xy * n_xy)
+        out = np.empty(cap, dtype=np.float64)
+        w = c_i64(0)
+        pose = _f64(pose_world)
+        ctx.check(ctx.lib.rsm_pass_scores(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps), pose.ctypes.data,
+                                          int(angle_begin), int(angle_end), out.ctypes.data, cap, ctypes.byref(w)))
+        return out[: w.value]
+
+
+class ScanMatchers:
+    """Coarse -> fine -> super-fine chain: ScanMatch(range_data, map, best_pose, cov, use_fine) -> score.
+
+    The reference's signature also carries the coarse-resolution map and scan, which only its
+    optional Gauss-Newton pre-step reads (scan_matchers.h:205-213); all three correlative passes
+    run on the fine map (:238-259), which is what is passed here."""
+
+    def __init__(self, ctx, params):
+        self.ctx = ctx
+        self.SetScanMatchParam(params)
+        self.last_responses = np.zeros(3)
+
+    def SetScanMatchParam(self, params):
+        assert len(params) == 3
+        self.params = [_as_param(p) for p in params]
+        self._arr = (PassParamStruct * 3)(*[p.struct() for p in self.params])
+
+    def ScanMatch(self, range_data, map_, best_pose, cov_matrix, use_fine_scan_match=True):
+        ctx = self.ctx
+        pts = _f64(range_data).reshape(-1, 2)
+        score = c_d(0)
+        self.last_responses = np.zeros(3)
+        ctx.check(ctx.lib.rsm_match_chain(ctx.h, map_.h, pts.ctypes.data, len(pts), self._arr, int(use_fine_scan_match),
+                                          best_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(score),
+                                          self.last_responses.ctypes.data))
+        return score.value
+
+    def ScanMatchBatch(self, maps, scans, poses, covs=None, use_fine_scan_match=True):
+        """n independent chains in batched launches (rsm_match_batch). poses (n,3) in/out."""
+        ctx = self.ctx
+        n = len(maps)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        for i, s in enumerate(scans):
+            offs[i + 1] = offs[i] + len(s)
+        pts = _f64(np.concatenate([np.asarray(s).reshape(-1, 2) for s in scans], axis=0))
+        poses = _f64(poses).copy()
+        covs = np.tile(np.eye(3), (n, 1, 1)) if covs is None else _f64(covs).copy()
+        scores = np.zeros(n)
+        resp = np.zeros((n, 3))
+        handles = (c_p * n)(*[m.h for m in maps])
+        ctx.check(ctx.lib.rsm_match_batch(ctx.h, n, handles, pts.ctypes.data, offs.ctypes.data, self._arr, 1,
+                                          int(use_fine_scan_match), poses.ctypes.data, covs.ctypes.data,
+                                          scores.ctypes.data, resp.ctypes.data))
+        return scores, poses, covs, resp
+
+
+def pack_loop_closure(scenarios):
+    """Flatten a list of synth.Scenario (same grid size / resolution / params) for rsm_loop_closure_batch."""
+    n = len(scenarios)
+    g0 = scenarios[0].grid
+    centres = np.zeros((n, 2))
+    scan_off = np.zeros(n + 1, dtype=np.int64)
+    pts_off = np.zeros(n + 1, dtype=np.int64)
+    base_n, base_pts, base_poses, pts = [], [], [], []
+    for i, sc in enumerate(scenarios):
+        g = sc.grid
+        assert (g.size_x, g.size_y, g.res) == (g0.size_x, g0.size_x, g0.res)
+        assert sc.grid_centre is not None, "loop-closure batches need back-end grids (centred on a pose)"
+        centres[i] = sc.grid_centre
+        scan_off[i + 1] = scan_off[i] + len(sc.base_pts)
+        for bp, pose in zip(sc.base_pts, sc.base_poses):
+            base_n.append(len(bp))
+            base_pts.append(np.asarray(bp).reshape(-1, 2))
+            base_poses.append(pose)
+        pts_off[i + 1] = pts_off[i] + len(sc.scan_pts)
+        pts.append(np.asarray(sc.scan_pts).reshape(-1, 2))
+    return dict(n=n, grid_size=g0.size_x, resolution=g0.res, default_prob=g0.default_prob, sigma=g0.sigma,
+                occu_offset=g0.occu_offset, centres=_f64(centres), scan_off=scan_off,
+                base_n=np.array(base_n, dtype=np.int32), base_pts=_f64(np.concatenate(base_pts, axis=0)),
+                base_poses=_f64(np.array(base_poses)), pts=_f64(np.concatenate(pts, axis=0)), pts_off=pts_off,
+                poses=_f64(np.array([sc.seed_pose for sc in scenarios])))
+
+
+def loop_closure_batch(ctx, packed, params, use_fine=True, centres=None):
+    """rsm_loop_closure_batch on arrays from pack_loop_closure; returns (scores, poses, covs, responses)."""
+    n = packed["n"]
+    arr = (PassParamStruct * 3)(*[_as_param(p).struct() for p in params])
+    poses = packed["poses"].copy()
+    covs = np.tile(np.eye(3), (n, 1, 1))
+    scores = np.zeros(n)
+    resp = np.zeros((n, 3))
+    c = packed["centres"] if centres is None else _f64(centres)
+    ctx.check(ctx.lib.rsm_loop_closure_batch(
+        ctx.h, n, int(packed["grid_size"]), float(packed["resolution"]), float(packed["default_prob"]),
+        float(packed["sigma"]), float(packed["occu_offset"]), c.ctypes.data, packed["scan_off"].ctypes.data,
+        packed["base_n"].ctypes.data, packed["base_pts"].ctypes.data, packed["base_poses"].ctypes.data,
+        packed["pts"].ctypes.data, packed["pts_off"].ctypes.data, arr, int(use_fine), poses.ctypes.data,
+        covs.ctypes.data, scores.ctypes.data, resp.ctypes.data))
+    return scores, poses, covs, resp

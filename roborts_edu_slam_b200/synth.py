@@ -114,6 +114,7 @@ class Scenario:
     seed_pose: np.ndarray           # (3,) world
     truth_pose: np.ndarray          # (3,) world
     passes: List[np.ndarray] = field(default_factory=list)
+    grid_centre: np.ndarray = None  # world (x,y) the back-end grid is centred on (None: explicit grid)
 
 
 def backend_grid(res, sigma, r_max, centre_xy, default_prob=0.3, occu_offset=0.88):
@@ -140,7 +141,8 @@ def make_scenario(name, map_name, truth, beams, fov, r_max, res, sigma, passes,
         base_poses.append(bp)
     g = grid if grid is not None else backend_grid(res, sigma, r_max, truth[:2])
     return Scenario(name, g, base_pts, np.array(base_poses), scan_m * inv,
-                    truth + np.asarray(seed_delta), truth, list(passes))
+                    truth + np.asarray(seed_delta), truth, list(passes),
+                    truth[:2].copy() if grid is None else None)
 
 
 DEG = 0.01745  # the reference writes angles as 0.01745 * degrees (scan_matchers.h:138-153)

@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the correlative scan matcher hot path.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU matcher on the host cores
+
+Metric (BASELINE.json): candidate-beam evaluations per second.  One evaluation = one
+(angle, x, y) candidate x one visited beam (reference: the body of GetResponse's loop,
+scan_match/correlate_scan_matcher.h:645-654).
+
+Workload (BASELINE.json configs[1]): a 720-beam scan ray-cast from rm.pgm
+matched over a +-1 m / +-45 deg window at 0.025 m (81 x 81 x 181 = 1 187 541 candidates x ~707
+beams = 8.4e8 evaluations per step) against a 1120^2 lookup grid rasterised from 8 base scans.
+A "step" is ONE such pass (BasedCorrelationScanMatch::ScanMatch) per GPU.  With N GPUs every rank
+matches its own independent scan/seed (weak scaling, no data-path collective); `value` is the
+whole-job aggregate: N * evals / max-over-ranks device time.
+
+  value   grid and scan resident in HBM; CUDA events on the library's stream around each step;
+          L2 flushed (256 MB streamed through) before every timed step.
+  e2e     same step through the public host-buffer call (rsm_match): scan points come from
+          pinned host memory every step, response/pose/covariance land in host memory.
+  roofline  scoring kernel only: 4 algorithmic bytes per evaluation / its CUDA-event time, against
+          the shared-memory row-gather bandwidth measured by the in-library micro-benchmark.
+  cpu_baseline  the reference's own header (oracle/_ref, else the oracle port) on one host core.
+  loop_closure  extra: batched loop-closure chains (BASELINE configs[3] shape) per second.
+
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidate_beam_evals_per_s"
+UNIT = "evals/s"
+ALGO_BYTES_PER_EVAL = 4  # one float32 prob_value_ per evaluation
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=256, help="loop-closure extra (0 = skip)")
+    ap.add_argument("--cpu-reps", type=int, default=4, help="full config-2 passes timed for cpu_baseline")
+    ap.add_argument("--no-flush", action="store_true")
+    return ap.parse_args()
+
+
+def rank_scenario(rank):
+    """Config 2 with a rank-specific seed so that ranks match independent problems."""
+    from roborts_edu_slam_b200 import synth
+    sc = synth.config2()
+    sc.seed_pose = sc.truth_pose + np.array([0.12 - 0.03 * rank, -0.07 + 0.02 * rank, 0.1 - 0.01 * rank])
+    return sc
+
+
+def workload_config(sc, geo):
+    return {
+        "workload": "BASELINE configs[1]: RPLidar-class 720-beam scan, +-1 m / +-45 deg window at 0.025 m over maps/rm.pgm",
+        "step": "one BasedCorrelationScanMatch::ScanMatch pass per GPU",
+        "candidates": geo["n_ang"] * geo["n_xy"] ** 2, "n_ang": geo["n_ang"], "n_xy": geo["n_xy"],
+        "beams_visited": geo["visited"], "grid": "%dx%d @ %.3f m" % (sc.grid.size_x, sc.grid.size_y, sc.grid.res),
+        "evals_per_step_per_gpu": geo["n_ang"] * geo["n_xy"] ** 2 * geo["visited"],
+        "use_point_size": "all beams", "use_center_penalty": True,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the timed regions run."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.bits, self.max_mhz, self.ok = [], 0, None, False
+        self.active = threading.Event()
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.h = h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            if self.active.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        reasons = [n for b, n in self.REASONS.items() if self.bits & b]
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_handle():
+    """(kind, callable(sc, param, pose) -> seconds for one pass) using the reference build if present."""
+    from oracle.oracle_py import Oracle, Ref, ref_available
+    if ref_available():
+        R = Ref()
+
+        def make(sc):
+            m = R.create_map(sc.grid)
+            R.build_map(m, sc.grid, sc.base_pts, sc.base_poses)
+            return lambda param, pose: R.match(m, sc.scan_pts, param, pose)
+        return "reference", make
+    O = Oracle()
+
+    def make(sc):
+        grid = O.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        return lambda param, pose: O.match(grid, sc.grid, sc.scan_pts, param, pose)
+    return "port", make
+
+
+def run_reference_arm(args):
+    """The reference's CPU matcher on all host cores: one independent match per thread per step.
+    Each step is a bounded sample of the workload: the full 81 x 81 translation window and all
+    beams, but 23 of the 181 search angles (+-5.5 deg), so that K steps finish in minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle_py import Oracle
+    kind, make = cpu_reference_handle()
+    threads = os.cpu_count() or 1
+    scs = [rank_scenario(t % 8) for t in range(threads)]
+    fns = [make(sc) for sc in scs]
+    O = Oracle()
+    params, evals = [], 0
+    for sc in scs:
+        p = sc.passes[0].copy()
+        p[2] = 11 * p[3]          # aoff = 11 * ares -> 23 angles
+        params.append(p)
+        geo = O.geometry(sc.grid, p, len(sc.scan_pts), O.world_to_map(sc.grid, sc.seed_pose))
+        evals += geo["n_ang"] * geo["n_xy"] ** 2 * geo["visited"]
+    full_geo = O.geometry(scs[0].grid, scs[0].passes[0], len(scs[0].scan_pts), O.world_to_map(scs[0].grid, scs[0].seed_pose))
+
+    def one_step():
+        ts = [threading.Thread(target=fns[t], args=(params[t], scs[t].seed_pose)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(min(args.warmup, 2)):
+        one_step()
+    total = sum(one_step() for _ in range(args.steps))
+    value = evals * args.steps / total
+    sample = "per step and thread: config-2 pass restricted to 23 of 181 angles (81x81 translations, all beams), %d threads" % threads
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(scs[0], full_geo),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from roborts_edu_slam_b200 import matcher, synth
+    from roborts_edu_slam_b200.sharding import contiguous_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the matcher has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = matcher.Context(local_rank)
+    sc = rank_scenario(rank)
+    g = sc.grid
+    grid = matcher.ScanMatchMap.from_spec(ctx, g)
+    grid.InitMapWithRangeVec(sc.base_pts, sc.base_poses, g.default_prob, g.sigma, g.occu_offset, g.use_blur)
+    param = sc.passes[0]
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    scan_dev = matcher.RangeDataContainer2d(ctx, sc.scan_pts)
+    pinned = torch.empty((len(sc.scan_pts), 2), dtype=torch.float64).pin_memory()
+    pinned.copy_(torch.from_numpy(np.ascontiguousarray(sc.scan_pts)))
+    scan_host = pinned.numpy()
+
+    # roofline denominators, measured on this GPU
+    smem_row = ctx.microbench_gather(0, 160 * 1024)
+    smem_rand = ctx.microbench_gather(1, 160 * 1024)
+    glob_row = ctx.microbench_gather(2, g.size_x * g.size_y * 4)
+    glob_rand = ctx.microbench_gather(3, g.size_x * g.size_y * 4)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def one_step(scan):
+        pose, cov = sc.seed_pose.copy(), np.eye(3)
+        if not args.no_flush:
+            ctx.flush_l2()
+        ctx.timer_start()
+        m.ScanMatch(grid, scan, param, pose, cov)
+        return ctx.timer_stop(), pose
+
+    for _ in range(args.warmup):
+        one_step(scan_dev)
+    det = m.last_detail
+    evals_step = det.n_candidates * det.visited
+
+    # ---- value: inputs resident ---------------------------------------------------------------
+    ctx.set_profiling(True)
+    barrier()
+    ctx.reset_stats()
+    sampler.active.set()
+    ms_value = 0.0
+    for _ in range(args.steps):
+        ms_value += one_step(scan_dev)[0]
+    sampler.active.clear()
+    barrier()
+    st_value = ctx.stats()
+    t_value = max_over_ranks(ms_value)
+    evals_all = sum_over_ranks(evals_step * args.steps)
+    value = evals_all / (t_value * 1e-3)
+    ctx.set_profiling(False)
+
+    # ---- e2e: host buffers in, host results out -------------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        one_step(scan_host)
+    barrier()
+    ctx.reset_stats()
+    sampler.active.set()
+    ms_e2e = 0.0
+    for _ in range(args.steps):
+        ms_e2e += one_step(scan_host)[0]
+    sampler.active.clear()
+    barrier()
+    st_e2e = ctx.stats()
+    t_e2e = max_over_ranks(ms_e2e)
+    e2e_value = evals_all / (t_e2e * 1e-3)
+
+    # ---- loop-closure extra (config 4 shape): batched chains with device-side grid construction ----
+    loop = None
+    if args.pairs_per_gpu > 0:
+        b, e = contiguous_range(args.pairs_per_gpu * world, rank, world)
+        pairs = synth.config4(e - b, first=b)
+        packed = matcher.pack_loop_closure(pairs)
+        matcher.loop_closure_batch(ctx, packed, pairs[0].passes)   # warm-up
+        barrier()
+        ctx.reset_stats()
+        reps, ms_lc = 3, 0.0
+        sampler.active.set()
+        for _ in range(reps):
+            ctx.timer_start()
+            scores, poses, covs, resp = matcher.loop_closure_batch(ctx, packed, pairs[0].passes)
+            ms_lc += ctx.timer_stop()
+        sampler.active.clear()
+        barrier()
+        st_lc = ctx.stats()
+        t_lc = max_over_ranks(ms_lc)
+        n_matches = sum_over_ranks((e - b) * reps)
+        loop = {
+            "workload": "BASELINE configs[3] shape: 1081-beam scan vs 480^2 grid rasterised from 8 base scans, coarse/fine/super chain (YAML values)",
+            "pairs": int(args.pairs_per_gpu * world), "matches_per_s": n_matches / (t_lc * 1e-3),
+            "ms_per_batch": t_lc / reps, "evals_per_s": sum_over_ranks(st_lc["evals"]) / (t_lc * 1e-3),
+            "exact_sort_passes": int(sum_over_ranks(st_lc["exact_sort_passes"])),
+            "accepted": int(sum_over_ranks(int((scores > 0.6).sum()))),
+        }
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    # ---- cpu baseline (rank 0, N = 1 only) --------------------------------------------------------
+    cpu = None
+    if world == 1 and args.cpu_reps > 0:
+        kind, make = cpu_reference_handle()
+        fn = make(sc)
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_reps):
+            fn(param, sc.seed_pose)
+        dt = time.perf_counter() - t0
+        cpu = {"value": evals_step * args.cpu_reps / dt, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d full config-2 passes (%.3g evaluations each), single thread as in the reference" % (args.cpu_reps, evals_step)}
+
+    if rank == 0:
+        score_launches = max(1, st_value["score_launches"])
+        k_ms = st_value["score_kernel_ms"] / score_launches
+        achieved = ALGO_BYTES_PER_EVAL * evals_step / (k_ms * 1e-3) / 1e9
+        geo = {"n_ang": det.n_ang, "n_xy": det.n_xy, "visited": det.visited}
+        cfg = workload_config(sc, geo)
+        cfg["l2"] = "flushed before every timed step (256 MB streamed)" if not args.no_flush else "not flushed"
+        cfg["parallelism"] = "one independent match per GPU, no data-path collective"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "score_kernel_dram_bytes_per_launch.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic", "config": cfg,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e / args.steps,
+                    "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
+            "gpu_launches": int(st_value["kernel_launches"]),
+            "roofline": {"bound": "smem", "kernel": "score_kernel", "achieved": achieved, "peak": smem_row, "unit": "GB/s",
+                         "frac": achieved / smem_row, "traffic": traffic,
+                         "kernel_ms": k_ms, "evals_per_s_kernel": evals_step / (k_ms * 1e-3),
+                         "peak_source": "rsm_microbench_gather mode 0 (shared-memory row segments) measured in this run",
+                         "other_peaks_gbs": {"smem_random": smem_rand, "global_row_l1l2": glob_row, "global_random_l1l2": glob_rand},
+                         "frac_of_global_row": achieved / glob_row,
+                         "hbm": {"peak": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                                 "achieved": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None}},
+            "kernel_share_of_step": {"score_ms": k_ms, "select_ms": st_value["select_kernel_ms"] / score_launches,
+                                     "step_ms": t_value / args.steps},
+            "exact_sort_passes": int(st_value["exact_sort_passes"]),
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if loop:
+            line["loop_closure"] = loop
+        print(json.dumps(line), flush=True)
+    grid.close()
+    scan_dev.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,15 @@ int rsm_grid_is_fixed_point(const rsm_grid* grid);
 int rsm_world_to_map(const rsm_grid* grid, const double pose_world[3], double pose_map[3]);
 int rsm_map_to_world(const rsm_grid* grid, const double pose_map[3], double pose_world[3]);
 
+/* ---- scans ------------------------------------------------------------------------------
+ * A scan kept resident on the device.  The reference matches the same RangeDataContainer2d
+ * several times (three passes per chain, one chain per loop-closure candidate); uploading it
+ * once replaces the shared_ptr<RangeDataContainer2d> it passes around
+ * (slam/sensor_data_manager.h:88-343).  pts_xy as everywhere: cells, sensor frame. */
+typedef struct rsm_scan rsm_scan;
+int rsm_scan_create(rsm_ctx* ctx, const double* pts_xy, int n_pts, rsm_scan** out);
+void rsm_scan_destroy(rsm_ctx* ctx, rsm_scan* scan);
+
 /* ---- matching ---------------------------------------------------------------------------
  * rsm_match: one pass.  Replaces BasedCorrelationScanMatch::ScanMatch(map, range_data, param,
  * current_pose&, cov_matrix&) -> response (scan_match/correlate_scan_matcher.h:784-875).
@@ -134,6 +143,11 @@ int rsm_map_to_world(const rsm_grid* grid, const double pose_map[3], double pose
 int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
               const rsm_pass_param* param, double pose_world[3], double cov[9], double* response,
               rsm_pass_detail* detail /* nullable */);
+
+/* Same pass on a device-resident scan (no host->device copy of the points). */
+int rsm_match_resident(rsm_ctx* ctx, const rsm_grid* grid, const rsm_scan* scan,
+                       const rsm_pass_param* param, double pose_world[3], double cov[9],
+                       double* response, rsm_pass_detail* detail /* nullable */);
 
 /* rsm_match_chain: coarse -> fine -> super-fine on one grid.  Replaces ScanMatchers::ScanMatch
  * with the optimiser off (scan_match/scan_matchers.h:179-289); params[0..2] = coarse, fine,
@@ -184,6 +198,14 @@ int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, 
 int rsm_match_finish(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
                      const rsm_pass_param* param, const void* const* partials, int n_partials,
                      double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail);
+
+/* ---- measurement support ------------------------------------------------------------------
+ * Gather-bandwidth micro-benchmark used as the roofline denominator of the scoring kernel:
+ * mode 0 = shared-memory row segments (32 consecutive 4-byte words per warp load, the access
+ * shape of the scoring kernel), 1 = shared-memory random words, 2 = global-memory row segments
+ * over an L1/L2-resident footprint, 3 = global-memory random words.  footprint_bytes: tile size
+ * (modes 0/1, <= 200 KB) or buffer size (modes 2/3).  *gbps = bytes gathered / CUDA-event time. */
+int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int iters, double* gbps);
 
 #ifdef __cplusplus
 }

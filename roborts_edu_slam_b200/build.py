@@ -36,12 +36,12 @@ def _nvcc():
 
 def build_rsm(force=False, verbose=False):
     out = os.path.join(HERE, "librsm.so")
-    srcs = [os.path.join(CSRC, f) for f in ("rsm_kernels.cu", "rsm_api.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("rsm_kernels.cu", "rsm_score.cu", "rsm_api.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("rsm_device.h", "rsm_kernels.h", "rsm_host.h")] + \
         [os.path.join(os.path.dirname(HERE), "include", "rsm.h")]
     if not force and not _newer(out, deps):
         return out
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+    cmd = [_nvcc(), "-t", "0"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
     print("[build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return out

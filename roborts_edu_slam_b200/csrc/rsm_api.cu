@@ -45,6 +45,11 @@ struct rsm_grid {
   double cell_len() const { return 1 / scale; }   // map/grid_map_base.h:307-309
 };
 
+struct rsm_scan {
+  double* d_pts = nullptr;
+  int n = 0;
+};
+
 namespace {
 
 struct Buf {
@@ -179,28 +184,23 @@ inline bool fix_ok(float v, int* out) {
   return true;
 }
 
-struct TileCfg { int lx, ry, nt; };
+struct TileCfg { int lx, ry, rows; bool affine; };
 
 // Tile shape of the scoring kernel for a window of n_xy x n_xy translations: lanes along x (lx),
-// ry consecutive y per thread, nt threads.  Minimises padded work plus table-build overhead.
-TileCfg pick_tile(int n_xy) {
+// ry consecutive y per thread.  Minimises padded work, per-beam overhead and table-build overhead.
+TileCfg pick_tile(int n_xy, bool affine_ok) {
   int lx = 4;
   while (lx < n_xy && lx < 32) lx <<= 1;
-  TileCfg best{lx, 1, 128};
+  const bool affine = affine_ok;
+  TileCfg best{lx, 1, score_rows(lx, 1), affine};
   double best_cost = 1e300;
-  const int nts[2] = {128, 256};
-  for (int nt : nts) {
-    const int slots = nt / lx;
-    for (int ry = 1; ry <= 8; ++ry) {
-      const int rows = slots * ry;
-      const int tx = (n_xy + lx - 1) / lx, ty = (n_xy + rows - 1) / rows;
-      const double padded = double(tx) * lx * double(ty) * rows;
-      const double cost = padded * (1.0 + 8.0 * double(lx + rows) / (double(lx) * rows));
-      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && ry > best.ry)) {
-        if (cost < best_cost) best_cost = cost;
-        best = TileCfg{lx, ry, nt};
-      }
-    }
+  const double alpha = affine ? 1.0 : 3.0;   // per-beam cost relative to one row's gather
+  for (int ry = 1; ry <= 8; ++ry) {
+    const int rows = score_rows(lx, ry);
+    const int tx = (n_xy + lx - 1) / lx, ty = (n_xy + rows - 1) / rows;
+    const double padded = double(tx) * lx * double(ty) * rows;
+    const double cost = padded * (1.0 + alpha / ry) * (1.0 + 4.0 * double(lx + rows) / (double(lx) * rows));
+    if (cost < best_cost) { best_cost = cost; best = TileCfg{lx, ry, rows, affine}; }
   }
   return best;
 }
@@ -302,8 +302,23 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   const int na = int(act.size());
 
   // ---- layouts -------------------------------------------------------------------------------
-  const TileCfg cfg = pick_tile(items[act[0]].geo.n_xy);
-  const int rows = (cfg.nt / cfg.lx) * cfg.ry;
+  // the affine variant needs the search step to be the same exact integer number of cells for every job
+  bool affine_ok = true;
+  {
+    const double f0 = items[act[0]].geo.factor;
+    if (!(f0 >= 1.0 && f0 <= 64.0 && f0 == std::floor(f0))) affine_ok = false;
+    for (int a = 0; a < na && affine_ok; ++a) {
+      // same step for every job, and window coordinates small enough for the rounding bound of
+      // the affine index test (rsm_score.cu) to hold
+      const PassGeo& g = items[act[a]].geo;
+      const double lim = 1048576.0;
+      if (g.factor != f0 || !(std::fabs(g.start_x) < lim && std::fabs(g.start_y) < lim &&
+                              std::fabs(g.x_of(g.n_xy + 64)) < lim && std::fabs(g.y_of(g.n_xy + 64)) < lim))
+        affine_ok = false;
+    }
+  }
+  const TileCfg cfg = pick_tile(items[act[0]].geo.n_xy, affine_ok);
+  const int rows = cfg.rows;
   std::vector<ScoreJob> sjobs(na);
   std::vector<int> s_cta(na + 1, 0);
   std::vector<SelectJob> ljobs(na);
@@ -381,6 +396,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.tiles_x = (g.n_xy + cfg.lx - 1) / cfg.lx;
     J.tiles_y = (g.n_xy + rows - 1) / rows;
     J.use_penalty = it.param.use_center_penalty ? 1 : 0;
+    J.f_int = cfg.affine ? int(g.factor) : 0;
+    J.stepoff = J.f_int * it.grid->pitch;
     J.divisor = double(g.divisor);
     J.sx = g.start_x; J.sy = g.start_y; J.f = g.factor;
     J.cx = g.center[0]; J.cy = g.center[1]; J.ca = g.center[2];
@@ -413,7 +430,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
   {
     Prof p(ctx, KC_SCORE);
-    CU(launch_score(any_fixed, cfg.lx, cfg.ry, cfg.nt, cta, ctx->stream,
+    CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, cta, ctx->stream,
                     reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
   }
   ctx->stats.kernel_launches++; ctx->stats.score_launches++;
@@ -925,6 +942,73 @@ int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pt
   if (rc) return rc;
   *response = items[0].response;
   if (detail) *detail = items[0].detail;
+  return RSM_OK;
+}
+
+int rsm_scan_create(rsm_ctx* ctx, const double* pts_xy, int n_pts, rsm_scan** out) {
+  if (!ctx || !out || n_pts < 0 || (n_pts > 0 && !pts_xy)) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_create: bad arguments");
+  rsm_scan* s = new rsm_scan;
+  s->n = n_pts;
+  if (n_pts > 0) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_pts), size_t(n_pts) * 16);
+    if (e != cudaSuccess) { delete s; return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(scan) failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(s->d_pts, pts_xy, size_t(n_pts) * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(s->d_pts); delete s; return fail(ctx, RSM_ERR_CUDA, "scan upload failed: %s", cudaGetErrorString(e)); }
+    ctx->stats.h2d_bytes += size_t(n_pts) * 16;
+  }
+  *out = s;
+  return RSM_OK;
+}
+
+void rsm_scan_destroy(rsm_ctx* ctx, rsm_scan* scan) {
+  if (!scan) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (scan->d_pts) cudaFree(scan->d_pts);
+  delete scan;
+}
+
+int rsm_match_resident(rsm_ctx* ctx, const rsm_grid* grid, const rsm_scan* scan, const rsm_pass_param* param,
+                       double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  if (!ctx || !grid || !scan || !param || !pose_world || !cov || !response)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_resident: bad arguments");
+  *response = 0.0;
+  if (detail) std::memset(detail, 0, sizeof *detail);
+  if (!grid->init || scan->n == 0) return RSM_OK;
+  std::vector<PassItem> items(1);
+  items[0].grid = grid; items[0].d_pts = scan->d_pts; items[0].P = scan->n; items[0].param = *param;
+  items[0].pose_world = pose_world; items[0].cov = cov;
+  int rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+  if (rc) return rc;
+  *response = items[0].response;
+  if (detail) *detail = items[0].detail;
+  return RSM_OK;
+}
+
+int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int iters, double* gbps) {
+  if (!ctx || !gbps || mode < 0 || mode > 3 || footprint_bytes < 1024 || iters < 4)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_microbench_gather: bad arguments");
+  if (mode < 2 && footprint_bytes > 200 * 1024) return fail(ctx, RSM_ERR_INVALID, "shared-memory tile must be <= 200 KB");
+  const unsigned int words = (unsigned int)(footprint_bytes / 4);
+  int rc = ensure_dev(ctx, ctx->d_flush, std::max<size_t>(size_t(footprint_bytes) + 64, size_t(256) << 20));
+  if (rc) return rc;
+  unsigned long long* sink = reinterpret_cast<unsigned long long*>(ctx->d_flush.p);
+  const int* g = reinterpret_cast<const int*>(ctx->d_flush.p + 64);
+  const int n_cta = mode < 2 ? 148 : 148 * 2;
+  iters = iters / 4 * 4;
+  CU(launch_microbench(ctx->stream, mode, g, words, iters, n_cta, sink));   // warm-up (fills L2 / I-cache)
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+  CU(cudaEventRecord(a, ctx->stream));
+  CU(launch_microbench(ctx->stream, mode, g, words, iters, n_cta, sink));
+  CU(cudaEventRecord(b, ctx->stream));
+  CU(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  ctx->stats.kernel_launches += 2;
+  const double bytes = double(n_cta) * 1024.0 * double(iters) * 4.0;
+  *gbps = bytes / (double(ms) * 1e-3) / 1e9;
   return RSM_OK;
 }
 

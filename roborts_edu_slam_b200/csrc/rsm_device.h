@@ -44,6 +44,7 @@ struct ScoreJob {
   int n_xy, ang_begin, ang_count;
   int tiles_x, tiles_y;  // candidate tiles per angle
   int use_penalty;
+  int f_int, stepoff;    // affine variant: search step in cells (exact integer) and f_int * pitch
   double divisor;        // use_point_size after the reference's adjustment (:561-566)
   double sx, sy, f;      // search_space_start_x/y and space_step_factor (:546-548), in cells
   double cx, cy, ca;     // centre pose in map coordinates

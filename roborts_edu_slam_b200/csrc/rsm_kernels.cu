@@ -64,240 +64,6 @@ __device__ __forceinline__ int find_job(const int* __restrict__ cta_begin, int n
 }
 
 // =================================================================================================
-// scoring
-// =================================================================================================
-template <int RYP> struct RowVec;
-template <> struct RowVec<1> { __device__ static void load(const int* p, int* r) { r[0] = p[0]; } };
-template <> struct RowVec<2> { __device__ static void load(const int* p, int* r) { int2 v = *reinterpret_cast<const int2*>(p); r[0] = v.x; r[1] = v.y; } };
-template <> struct RowVec<4> { __device__ static void load(const int* p, int* r) { int4 v = *reinterpret_cast<const int4*>(p); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; } };
-template <> struct RowVec<8> { __device__ static void load(const int* p, int* r) { RowVec<4>::load(p, r); RowVec<4>::load(p + 4, r + 4); } };
-
-template <bool FIXED, int LX, int RY>
-__global__ void __launch_bounds__(256)
-score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
-  constexpr int RYP = (RY <= 1) ? 1 : (RY <= 2) ? 2 : (RY <= 4) ? 4 : 8;
-  constexpr int PC = kChunk;
-  const int NT = blockDim.x;
-  const int tid = threadIdx.x;
-  const int slots = NT / LX;     // y slots per CTA; each owns RY consecutive y translations
-  const int rows = slots * RY;
-  const int tx = tid % LX;       // lane position along x
-  const int ts = tid / LX;       // y slot
-
-  __shared__ ScoreJob J;
-  __shared__ int s_job;
-  __shared__ unsigned long long s_wmax[8];
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  double* sLut = reinterpret_cast<double*>(dyn_smem);   // [2][PC][2] rotated endpoints (x,y)
-  double* sX = sLut + 2 * PC * 2;                        // [LX]   candidate x of this tile
-  double* sY = sX + LX;                                  // [rows] candidate y of this tile
-  int* sGX = reinterpret_cast<int*>(sY + rows);          // [2][PC][LX]          cell x
-  int* sGY = sGX + 2 * PC * LX;                          // [2][PC][slots][RYP]  cell y * pitch
-
-  if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
-  __syncthreads();
-  {
-    const int* src = reinterpret_cast<const int*>(jobs + s_job);
-    int* dst = reinterpret_cast<int*>(&J);
-    for (int i = tid; i < int(sizeof(ScoreJob) / 4); i += NT) dst[i] = __ldg(src + i);
-  }
-  const int first_cta = __ldg(cta_begin + s_job);
-  __syncthreads();
-
-  const int local = blockIdx.x - first_cta;
-  const int tiles = J.tiles_x * J.tiles_y;
-  const int ia_local = local / tiles;
-  const int tile = local - ia_local * tiles;
-  const int tx0 = (tile % J.tiles_x) * LX;
-  const int ty0 = (tile / J.tiles_x) * rows;
-  const int ia = J.ang_begin + ia_local;
-  const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
-  const int V = J.V, n_xy = J.n_xy;
-  const int nchunks = (V + PC - 1) / PC;
-
-  // candidate coordinates of this tile: x = start_x + x_index * factor   (:569, :572)
-  for (int i = tid; i < LX + rows; i += NT) {
-    if (i < LX) sX[i] = dadd(J.sx, dmul((double)(tx0 + i), J.f));
-    else sY[i - LX] = dadd(J.sy, dmul((double)(ty0 + i - LX), J.f));
-  }
-
-  // rotated endpoint of visited beam v: (cos*px - sin*py, sin*px + cos*py)   (:179-180)
-  auto lut_chunk = [&](int c) {
-    if (tid < PC) {
-      const int v = c * PC + tid;
-      if (v < V) {
-        const int p = v * J.step;
-        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
-        double* d = sLut + ((c & 1) * PC + tid) * 2;
-        d[0] = dsub(dmul(cs, px), dmul(sn, py));
-        d[1] = dadd(dmul(sn, px), dmul(cs, py));
-      }
-    }
-  };
-  int err = 0;
-  // cell index tables of chunk c: (int)(lut + candidate + 0.5), truncation toward zero   (:647-648)
-  auto build_chunk = [&](int c) {
-    const int npc = min(PC, V - c * PC);
-    const double* lut = sLut + (c & 1) * PC * 2;
-    int* gxt = sGX + (c & 1) * PC * LX;
-    int* gyt = sGY + (c & 1) * PC * slots * RYP;
-    for (int q = tid; q < npc * LX; q += NT) {
-      const int pc = q / LX, j = q % LX;
-      int g = __double2int_rz(dadd(dadd(lut[pc * 2], sX[j]), 0.5));
-      if (g < 0 || g >= J.size_x) {
-        if (tx0 + j < n_xy) err |= kErrWindow;
-        g = max(0, min(g, J.size_x - 1));
-      }
-      gxt[pc * LX + j] = g;
-    }
-    for (int q = tx; q < npc * RY; q += LX) {
-      const int pc = q / RY, rr = q % RY;
-      int g = __double2int_rz(dadd(dadd(lut[pc * 2 + 1], sY[ts * RY + rr]), 0.5));
-      if (g < 0 || g >= J.size_y) {
-        if (ty0 + ts * RY + rr < n_xy) err |= kErrWindow;
-        g = max(0, min(g, J.size_y - 1));
-      }
-      gyt[(pc * slots + ts) * RYP + rr] = g * J.pitch;
-    }
-  };
-
-  unsigned int a32[RY];
-  unsigned long long a64[RY];
-  double ad[RY];
-#pragma unroll
-  for (int r = 0; r < RY; ++r) { a32[r] = 0u; a64[r] = 0ull; ad[r] = 0.0; }
-
-  const int* gridI = reinterpret_cast<const int*>(J.grid);
-  const float* gridF = reinterpret_cast<const float*>(J.grid);
-
-  lut_chunk(0);
-  __syncthreads();
-  build_chunk(0);
-  if (nchunks > 1) lut_chunk(1);
-  __syncthreads();
-
-  for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) build_chunk(c + 1);
-    if (c + 2 < nchunks) lut_chunk(c + 2);
-
-    const int npc = min(PC, V - c * PC);
-    const int* gxp = sGX + (c & 1) * PC * LX + tx;
-    const int* gyp = sGY + ((c & 1) * PC * slots + ts) * RYP;
-    const int gy_stride = slots * RYP;
-    if (npc == PC) {
-#pragma unroll 8
-      for (int pc = 0; pc < PC; ++pc) {
-        const int gx = gxp[pc * LX];
-        int ro[RYP];
-        RowVec<RYP>::load(gyp + pc * gy_stride, ro);
-#pragma unroll
-        for (int r = 0; r < RY; ++r) {
-          if (FIXED) a32[r] += (unsigned int)__ldg(gridI + (ro[r] + gx));
-          else ad[r] = dadd(ad[r], (double)__ldg(gridF + (ro[r] + gx)));
-        }
-      }
-    } else {
-      for (int pc = 0; pc < npc; ++pc) {
-        const int gx = gxp[pc * LX];
-        int ro[RYP];
-        RowVec<RYP>::load(gyp + pc * gy_stride, ro);
-#pragma unroll
-        for (int r = 0; r < RY; ++r) {
-          if (FIXED) a32[r] += (unsigned int)__ldg(gridI + (ro[r] + gx));
-          else ad[r] = dadd(ad[r], (double)__ldg(gridF + (ro[r] + gx)));
-        }
-      }
-    }
-    if (FIXED) {
-      // <= 32 cells of <= 2^25 each fit a uint32; spill into the 64-bit sum once per chunk
-#pragma unroll
-      for (int r = 0; r < RY; ++r) { a64[r] += a32[r]; a32[r] = 0u; }
-    }
-    __syncthreads();
-  }
-
-  // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
-  const int ix = tx0 + tx;
-  unsigned long long kmax = 0ull;
-  if (ix < n_xy) {
-    const double x = sX[tx];
-    const double dx = dsub(x, J.cx);
-    const double dx2 = dmul(dx, dx);
-    const double da = dsub(ang, J.ca);
-    const double a2 = dmul(da, da);
-    const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, a2), 0.349)), 0.9);
-    double* out = J.score + ((long long)ia_local * n_xy + ix) * n_xy;
-#pragma unroll
-    for (int r = 0; r < RY; ++r) {
-      const int iy = ty0 + ts * RY + r;
-      if (iy < n_xy) {
-        double sum = FIXED ? dmul((double)a64[r], kFixScale) : ad[r];
-        double sc = ddiv(sum, J.divisor);
-        if (J.use_penalty) {
-          // DoubleEqual(score, 0.0) with the default 1e-6 tolerance skips the penalty (:728)
-          const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);
-          if (!zero) {
-            const double dy = dsub(sY[ts * RY + r], J.cy);
-            double d2 = dadd(dx2, dmul(dy, dy));
-            d2 = dmul(d2, J.m2);
-            const double dp = fmax(dsub(1.0, ddiv(dmul(J.gain, d2), J.half_size)), 0.5);
-            sc = dmul(sc, dmul(dp, ap));
-          }
-        }
-        out[iy] = sc;
-        const unsigned long long k = score_key(sc);
-        kmax = k > kmax ? k : kmax;
-      }
-    }
-  }
-  kmax = warp_max_u64(kmax);
-  if ((tid & 31) == 0) s_wmax[tid >> 5] = kmax;
-  if (err) atomicOr(J.err, err);
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long m = 0ull;
-    for (int w = 0; w < (NT >> 5); ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
-    atomicMax(J.best_key, m);
-  }
-}
-
-size_t score_smem_bytes(int lx, int ry, int nt) {
-  const int ryp = (ry <= 1) ? 1 : (ry <= 2) ? 2 : (ry <= 4) ? 4 : 8;
-  const int slots = nt / lx;
-  const int rows = slots * ry;
-  return size_t(2 * kChunk * 2 + lx + rows) * 8 + size_t(2 * kChunk * lx + 2 * kChunk * slots * ryp) * 4;
-}
-
-template <bool FIXED, int LX>
-static cudaError_t launch_score_ry(int ry, int n_cta, int nt, size_t smem, cudaStream_t st,
-                                   const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
-#define RSM_CASE(R)                                                                            \
-  case R:                                                                                      \
-    score_kernel<FIXED, LX, R><<<n_cta, nt, smem, st>>>(jobs, cta_begin, n_jobs);              \
-    break;
-  switch (ry) {
-    RSM_CASE(1) RSM_CASE(2) RSM_CASE(3) RSM_CASE(4) RSM_CASE(5) RSM_CASE(6) RSM_CASE(7) RSM_CASE(8)
-    default: return cudaErrorInvalidValue;
-  }
-#undef RSM_CASE
-  return cudaGetLastError();
-}
-
-cudaError_t launch_score(bool fixed, int lx, int ry, int nt, int n_cta, cudaStream_t st,
-                         const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
-  const size_t smem = score_smem_bytes(lx, ry, nt);
-#define RSM_LX(L)                                                                               \
-  case L:                                                                                       \
-    return fixed ? launch_score_ry<true, L>(ry, n_cta, nt, smem, st, jobs, cta_begin, n_jobs)   \
-                 : launch_score_ry<false, L>(ry, n_cta, nt, smem, st, jobs, cta_begin, n_jobs);
-  switch (lx) {
-    RSM_LX(4) RSM_LX(8) RSM_LX(16) RSM_LX(32)
-    default: return cudaErrorInvalidValue;
-  }
-#undef RSM_LX
-}
-
-// =================================================================================================
 // selection
 // =================================================================================================
 // Block-wide "pop the maximum" over one (key, tag) pair per thread.  Returns the winning key and
@@ -503,6 +269,57 @@ __global__ void __launch_bounds__(256) flush_kernel(int4* buf, long long n4, int
     x.x += v;
     buf[i] = x;
   }
+}
+
+// ---- gather-bandwidth micro-benchmarks (roofline denominators) -------------------
+// Every warp reads `iters` row segments of 32 consecutive 4-byte words (the access shape of
+// score_kernel) or 32 independent random words, from a shared-memory tile or from a global
+// footprint that lives in L1/L2.
+__device__ __forceinline__ unsigned int mix(unsigned int x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(1024)
+microbench_kernel(const int* __restrict__ g, unsigned int words, int iters, int mode, unsigned long long* sink) {
+  extern __shared__ int tile[];
+  const bool use_smem = mode < 2;
+  const bool random = (mode & 1) != 0;
+  if (use_smem) {
+    for (unsigned int i = threadIdx.x; i < words; i += blockDim.x) tile[i] = (int)(i * 2654435761u);
+    __syncthreads();
+  }
+  const unsigned int lane = threadIdx.x & 31;
+  const unsigned int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+  unsigned int st = mix(warp_id * 9781u + 1u);
+  const unsigned int span = random ? words : (words - 32u);
+  for (int it = 0; it < iters; it += 4) {
+    unsigned int b0, b1, b2, b3;
+    if (random) {
+      b0 = mix(st + lane * 4u) % span; b1 = mix(st + lane * 4u + 1u) % span;
+      b2 = mix(st + lane * 4u + 2u) % span; b3 = mix(st + lane * 4u + 3u) % span;
+    } else {
+      b0 = mix(st) % span + lane; b1 = mix(st + 1u) % span + lane;
+      b2 = mix(st + 2u) % span + lane; b3 = mix(st + 3u) % span + lane;
+    }
+    st += 131u;
+    if (use_smem) { acc0 += tile[b0]; acc1 += tile[b1]; acc2 += tile[b2]; acc3 += tile[b3]; }
+    else { acc0 += __ldg(g + b0); acc1 += __ldg(g + b1); acc2 += __ldg(g + b2); acc3 += __ldg(g + b3); }
+  }
+  const unsigned int acc = acc0 + acc1 + acc2 + acc3;
+  if (acc == 0x12345u) atomicAdd(sink, 1ull);   // keeps the loads alive
+}
+
+cudaError_t launch_microbench(cudaStream_t st, int mode, const int* g, unsigned int words, int iters,
+                              int n_cta, unsigned long long* sink) {
+  const size_t smem = mode < 2 ? size_t(words) * 4 : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  microbench_kernel<<<n_cta, 1024, smem, st>>>(g, words, iters, mode, sink);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_flush(cudaStream_t st, void* buf, long long bytes, int v) {

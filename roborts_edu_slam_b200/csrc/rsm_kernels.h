@@ -9,9 +9,14 @@
 
 namespace rsm {
 
-size_t score_smem_bytes(int lx, int ry, int nt);
-// fixed: int32 2^-25 fixed-point cells (else float32).  lx in {4,8,16,32}, ry in 1..8, nt in {128,256}.
-cudaError_t launch_score(bool fixed, int lx, int ry, int nt, int n_cta, cudaStream_t st,
+// Scoring kernel variants (rsm_score.cu).  fixed: int32 2^-25 fixed-point cells (else float32);
+// affine: search step is an exact integer number of cells (lx in {8,16,32}), else lx in {4,8,16,32};
+// ry in 1..8 rows per thread.  A CTA has score_threads(lx) threads and covers lx x score_rows(lx, ry)
+// translations of one angle.
+int score_threads(int lx);
+inline int score_rows(int lx, int ry) { return (score_threads(lx) / lx) * ry; }
+int score_occupancy(bool fixed, bool affine, int lx, int ry);
+cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int n_cta, cudaStream_t st,
                          const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);
@@ -19,6 +24,8 @@ cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);
 cudaError_t launch_fill(int n_jobs, int ctas_per_job, cudaStream_t st, const FillJob* jobs);
 cudaError_t launch_raster(int n_scans, cudaStream_t st, const RasterScan* scans, const int* stamp,
                           int half, int one);
+cudaError_t launch_microbench(cudaStream_t st, int mode, const int* g, unsigned int words, int iters,
+                              int n_cta, unsigned long long* sink);
 cudaError_t launch_flush(cudaStream_t st, void* buf, long long bytes, int v);
 
 }  // namespace rsm

@@ -86,6 +86,10 @@ ABI = {
     "rsm_world_to_map": (c_i, [c_p, c_p, c_p]),
     "rsm_map_to_world": (c_i, [c_p, c_p, c_p]),
     "rsm_match": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_scan_create": (c_i, [c_p, c_p, c_i, ctypes.POINTER(c_p)]),
+    "rsm_scan_destroy": (None, [c_p, c_p]),
+    "rsm_match_resident": (c_i, [c_p, c_p, c_p, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_microbench_gather": (c_i, [c_p, c_i, c_i64, c_i, ctypes.POINTER(c_d)]),
     "rsm_match_chain": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_i, c_p, c_p, ctypes.POINTER(c_d), c_p]),
     "rsm_match_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, _PPARAM, c_i, c_i, c_p, c_p, c_p, c_p]),
     "rsm_loop_closure_batch": (c_i, [c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
@@ -206,6 +210,38 @@ class Context:
     def flush_l2(self):
         self.check(self.lib.rsm_flush_l2(self.h))
 
+    def microbench_gather(self, mode, footprint_bytes, iters=4096):
+        """GB/s of 4-byte gathers: mode 0/1 shared memory (row segments / random), 2/3 global."""
+        g = c_d(0)
+        self.check(self.lib.rsm_microbench_gather(self.h, int(mode), int(footprint_bytes), int(iters), ctypes.byref(g)))
+        return g.value
+
+
+class RangeDataContainer2d:
+    """A scan resident on the device (rsm_scan): points (P,2) in cells, sensor frame."""
+
+    def __init__(self, ctx, pts):
+        self.ctx = ctx
+        pts = _f64(pts).reshape(-1, 2)
+        self.n = len(pts)
+        h = c_p()
+        ctx.check(ctx.lib.rsm_scan_create(ctx.h, pts.ctypes.data, self.n, ctypes.byref(h)))
+        self.h = h
+
+    def GetSize(self):
+        return self.n
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.rsm_scan_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class ScanMatchMap:
     """Device-resident lookup grid with the reference map's geometry (OccuGridMap<ProbabilityCell>)."""
@@ -282,15 +318,20 @@ class BasedCorrelationScanMatch:
 
     def ScanMatch(self, map_, range_data, scan_match_param, current_pose, cov_matrix):
         ctx = self.ctx
-        pts = _f64(range_data).reshape(-1, 2)
         assert current_pose.dtype == np.float64 and cov_matrix.dtype == np.float64
         assert current_pose.flags.c_contiguous and cov_matrix.flags.c_contiguous
         ps = _as_param(scan_match_param).struct()
         resp = c_d(0)
         det = PassDetail()
-        ctx.check(ctx.lib.rsm_match(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps),
-                                    current_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(resp),
-                                    ctypes.byref(det)))
+        if isinstance(range_data, RangeDataContainer2d):
+            ctx.check(ctx.lib.rsm_match_resident(ctx.h, map_.h, range_data.h, ctypes.byref(ps),
+                                                 current_pose.ctypes.data, cov_matrix.ctypes.data,
+                                                 ctypes.byref(resp), ctypes.byref(det)))
+        else:
+            pts = _f64(range_data).reshape(-1, 2)
+            ctx.check(ctx.lib.rsm_match(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps),
+                                        current_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(resp),
+                                        ctypes.byref(det)))
         self.last_detail = det
         return resp.value
 

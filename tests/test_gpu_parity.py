@@ -1,0 +1,291 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on the
+same inputs and against the reference's golden vectors.
+
+Bars (BASELINE.json north_star): bit-exact lookup grid, candidate scores, response and pose;
+covariance within 1e-6 relative (cov_close).  Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+
+from helpers import cov_close, golden_grid, golden_names, load_golden, random_scenario
+from roborts_edu_slam_b200 import matcher, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def device_grid(ctx, sc, rasterize=True, oracle=None):
+    g = sc.grid
+    dg = matcher.ScanMatchMap.from_spec(ctx, g)
+    if rasterize:
+        dg.InitMapWithRangeVec(sc.base_pts, sc.base_poses, g.default_prob, g.sigma, g.occu_offset, g.use_blur)
+    else:
+        dg.upload(oracle.build_grid(g, sc.base_pts, sc.base_poses))
+    return dg
+
+
+def assert_pass_equal(got_resp, got_pose, got_cov, want):
+    assert got_resp == want["response"]
+    assert np.array_equal(got_pose, want["pose"])
+    assert cov_close(got_cov, want["cov"])
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors(ctx, name):
+    """Everything the reference produced for the committed fixtures, through the CUDA path."""
+    sc, z = load_golden(name)
+    g = sc.grid
+    dg = device_grid(ctx, sc)
+    assert np.array_equal(dg.download(), golden_grid(z, g))                 # rasteriser, every cell
+    assert np.array_equal(dg.GetMapCoordsPose(sc.seed_pose), z["centre_map"])
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    scores = m.scores(dg, sc.scan_pts, sc.passes[0], sc.seed_pose)
+    assert np.array_equal(np.sort(scores)[::-1][:64], z["pass0_sorted_head"])
+    import hashlib
+    assert hashlib.sha256(np.sort(scores)[::-1].tobytes()).hexdigest() == str(z["pass0_sorted_scores_sha"])
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    r = m.ScanMatch(dg, sc.scan_pts, sc.passes[0], pose, cov)
+    assert r == float(z["pass0_response"])
+    assert np.array_equal(pose, z["pass0_pose"])
+    assert cov_close(cov, z["pass0_cov"])
+    assert np.array_equal([m.last_detail.best_pose_map[i] for i in range(3)] + [m.last_detail.best_score], z["pass0_best"])
+    if "chain_score" in z.files:
+        sm = matcher.ScanMatchers(ctx, sc.passes)
+        pose, cov = sc.seed_pose.copy(), np.eye(3)
+        s = sm.ScanMatch(sc.scan_pts, dg, pose, cov)
+        assert s == float(z["chain_score"])
+        assert np.array_equal(pose, z["chain_pose"])
+        assert cov_close(cov, z["chain_cov"])
+        assert np.array_equal(sm.last_responses, z["chain_responses"])
+    dg.close()
+
+
+def test_scores_and_indices_small(ctx, oracle, rng):
+    """Every candidate score bit-equal on random small problems: all tile shapes (n_xy 1..40),
+    beam subsampling, penalty on/off, all pass types, f < 1, f = 1, f > 1."""
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    for trial in range(40):
+        sc = random_scenario(rng, n_points=int(rng.integers(3, 400)), size=200)
+        grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        dg = matcher.ScanMatchMap.from_spec(ctx, sc.grid)
+        dg.upload(grid)
+        sres = float(rng.choice([0.05, 0.02, 0.1, 0.025, 0.01, 0.2]))
+        n_steps = int(rng.integers(0, 40))
+        if sres * n_steps > 1.6:
+            n_steps = int(1.6 / sres)
+        p = synth.pass_param(sres * n_steps, sres, float(rng.uniform(0.0, 0.5)), float(rng.uniform(0.004, 0.06)),
+                             0.3, int(rng.choice([10, 37, 100, 100000])), bool(trial % 2), trial % 3)
+        so = oracle.scores(grid, sc.grid, sc.scan_pts, p, oracle.world_to_map(sc.grid, sc.seed_pose))
+        sd = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+        assert so.shape == sd.shape
+        assert np.array_equal(so, sd), "trial %d: %d of %d scores differ" % (trial, int((so != sd).sum()), len(so))
+        want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
+        pose, cov = sc.seed_pose.copy(), np.eye(3)
+        r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+        assert_pass_equal(r, pose, cov, want)
+        assert m.last_detail.n_avg == want["n_avg"]
+        dg.close()
+
+
+def test_rasterizer_matches_oracle(ctx, oracle, rng):
+    for sigma, res in [(0.15, 0.05), (0.03, 0.025), (0.24, 0.08), (0.4, 0.1), (0.03, 0.01)]:
+        sc = random_scenario(rng, n_points=300, size=260, res=res, n_base=5)
+        sc.grid.sigma = sigma
+        want = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        dg = device_grid(ctx, sc)
+        assert dg.is_fixed_point()
+        assert np.array_equal(dg.download(), want)
+        dg.close()
+    # points outside the grid / on the border band are skipped like the reference does
+    sc = random_scenario(rng, n_points=200, size=60, spread=80.0)
+    want = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    dg = device_grid(ctx, sc)
+    assert np.array_equal(dg.download(), want)
+    dg.close()
+    # a kernel value that is not a multiple of 2^-25 switches the grid to float32 cells
+    sc = random_scenario(rng, n_points=200, size=160)
+    sc.grid.occu_offset = 0.2
+    sc.grid.default_prob = 0.1
+    want = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    dg = device_grid(ctx, sc)
+    assert not dg.is_fixed_point()
+    assert np.array_equal(dg.download(), want)
+    dg.close()
+
+
+def test_float32_grid_path(ctx, oracle, rng):
+    """Arbitrary float cells (not 2^-25 multiples): float gather + FP64 accumulate in beam order."""
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    for trial in range(4):
+        sc = random_scenario(rng, n_points=257, size=200)
+        grid = rng.random((sc.grid.size_y, sc.grid.size_x)).astype(np.float32) * np.float32(0.97)
+        dg = matcher.ScanMatchMap.from_spec(ctx, sc.grid)
+        dg.upload(grid)
+        assert not dg.is_fixed_point()
+        assert np.array_equal(dg.download(), grid)
+        p = synth.pass_param(0.6, 0.05, 0.3, 0.02, 0.3, [100000, 50][trial % 2], True, trial % 3)
+        so = oracle.scores(grid, sc.grid, sc.scan_pts, p, oracle.world_to_map(sc.grid, sc.seed_pose))
+        sd = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+        assert np.array_equal(so, sd)
+        want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
+        pose, cov = sc.seed_pose.copy(), np.eye(3)
+        assert_pass_equal(m.ScanMatch(dg, sc.scan_pts, p, pose, cov), pose, cov, want)
+        dg.close()
+
+
+def test_exact_ties_follow_the_reference_sort(ctx, oracle):
+    """Binary grid without the centre penalty: thousands of exact ties, so the averaged pose and the
+    covariance depend on libstdc++'s unstable sort order; the CUDA path must detect that and
+    reproduce it (exact_sort_used) -- still bit-exact."""
+    sc, z = load_golden("ties_icra")
+    dg = device_grid(ctx, sc)
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    used = 0
+    pose_in = sc.seed_pose.copy()
+    for p in sc.passes:
+        want = oracle.match(grid, sc.grid, sc.scan_pts, p, pose_in)
+        pose, cov = pose_in.copy(), np.eye(3)
+        r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+        assert_pass_equal(r, pose, cov, want)
+        assert np.array_equal(cov, want["cov"])
+        used += m.last_detail.exact_sort_used
+        pose_in = want["pose"]
+    assert used >= 1
+    # fully degenerate: scan in unknown space, no penalty -> all candidates tie
+    flat = np.full((sc.grid.size_y, sc.grid.size_x), np.float32(0.3))
+    dg.upload(flat)
+    p = sc.passes[0]
+    want = oracle.match(flat, sc.grid, sc.scan_pts, p, sc.seed_pose)
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+    assert_pass_equal(r, pose, cov, want)
+    assert m.last_detail.n_avg == want["n_avg"] == 3549 and m.last_detail.exact_sort_used == 1
+    dg.close()
+
+
+def test_reference_error_behaviour(ctx, oracle):
+    sc, _ = load_golden("cfg1_icra")
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    dg = matcher.ScanMatchMap.from_spec(ctx, sc.grid)
+    # map not initialised: response 0, outputs untouched (correlate_scan_matcher.h:792-795)
+    pose, cov = sc.seed_pose.copy(), np.arange(9.0).reshape(3, 3)
+    assert m.ScanMatch(dg, sc.scan_pts, sc.passes[0], pose, cov) == 0.0
+    assert np.array_equal(pose, sc.seed_pose) and np.array_equal(cov, np.arange(9.0).reshape(3, 3))
+    dg.InitMapWithRangeVec(sc.base_pts, sc.base_poses)
+    # empty scan: same
+    assert m.ScanMatch(dg, np.zeros((0, 2)), sc.passes[0], pose, cov) == 0.0
+    assert np.array_equal(pose, sc.seed_pose) and np.array_equal(cov, np.arange(9.0).reshape(3, 3))
+    # response below threshold: covariance written, pose untouched
+    p = sc.passes[0].copy()
+    p[4] = 0.99
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+    assert_pass_equal(r, pose, cov, want)
+    assert np.array_equal(pose, sc.seed_pose) and m.last_detail.pose_updated == 0
+    # window leaves the grid: the reference would read out of bounds; the device path reports it
+    far = sc.seed_pose + np.array([11.5, 0.0, 0.0])
+    with pytest.raises(matcher.RsmError) as e:
+        m.ScanMatch(dg, sc.scan_pts, sc.passes[0], far.copy(), np.eye(3))
+    assert e.value.status == 4
+    # FAST (branch and bound) is not provided
+    p = sc.passes[0].copy()
+    p[7] = 3
+    with pytest.raises(matcher.RsmError) as e:
+        m.ScanMatch(dg, sc.scan_pts, p, sc.seed_pose.copy(), np.eye(3))
+    assert e.value.status == 5
+    dg.close()
+
+
+def test_chain_batch_and_loop_closure(ctx, oracle):
+    pairs = synth.config4(12, seed=4321)
+    want = []
+    for sc in pairs:
+        grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        want.append(oracle.match_chain(grid, sc.grid, sc.scan_pts, sc.passes, sc.seed_pose))
+    # (1) one by one through ScanMatchers
+    sm = matcher.ScanMatchers(ctx, pairs[0].passes)
+    grids = [device_grid(ctx, sc) for sc in pairs]
+    for sc, dg, w in zip(pairs, grids, want):
+        pose, cov = sc.seed_pose.copy(), np.eye(3)
+        s = sm.ScanMatch(sc.scan_pts, dg, pose, cov)
+        assert s == w["score"] and np.array_equal(pose, w["pose"]) and cov_close(cov, w["cov"])
+        assert np.array_equal(sm.last_responses, w["responses"])
+    # (2) batched over existing grids
+    scores, poses, covs, resp = sm.ScanMatchBatch(grids, [sc.scan_pts for sc in pairs], [sc.seed_pose for sc in pairs])
+    for i, w in enumerate(want):
+        assert scores[i] == w["score"] and np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"])
+        assert np.array_equal(resp[i], w["responses"])
+    # (3) batched with device-side grid construction
+    packed = matcher.pack_loop_closure(pairs)
+    scores, poses, covs, resp = matcher.loop_closure_batch(ctx, packed, pairs[0].passes)
+    for i, w in enumerate(want):
+        assert scores[i] == w["score"] and np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"])
+        assert np.array_equal(resp[i], w["responses"])
+    # coarse only (use_fine_scan_match = false)
+    sc, dg = pairs[0], grids[0]
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    w = oracle.match_chain(grid, sc.grid, sc.scan_pts, sc.passes, sc.seed_pose, use_fine=False)
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    s = sm.ScanMatch(sc.scan_pts, dg, pose, cov, use_fine_scan_match=False)
+    assert s == w["score"] and np.array_equal(pose, w["pose"]) and cov_close(cov, w["cov"])
+    for dg in grids:
+        dg.close()
+
+
+def test_config2_full_size(ctx, oracle):
+    """BASELINE configs[1] at full size (8.4e8 evaluations): every score, pose, covariance."""
+    sc = synth.config2()
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    dg = device_grid(ctx, sc)
+    assert np.array_equal(dg.download(), grid)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    p = sc.passes[0]
+    so = oracle.scores(grid, sc.grid, sc.scan_pts, p, oracle.world_to_map(sc.grid, sc.seed_pose))
+    sd = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+    assert np.array_equal(so, sd)
+    want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    assert_pass_equal(m.ScanMatch(dg, sc.scan_pts, p, pose, cov), pose, cov, want)
+    dg.close()
+
+
+def test_size_independent_properties_wide_window(ctx):
+    """A window too large for the CPU oracle to finish in seconds (1/4-scale config 5, 1.1e9
+    evaluations): properties that pin the kernel without an oracle."""
+    sc = synth.config5(scale=0.25)
+    dg = device_grid(ctx, sc)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    p = sc.passes[0]
+    full = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+    # (1) angle slices reproduce the full pass bit for bit (what multi-GPU angle slicing relies on)
+    n_ang = int(np.floor(p[2] * 2 / p[3]) + 1)
+    n_xy = int(np.floor(p[0] / p[1] + 0.5) + 1)
+    assert full.size == n_ang * n_xy * n_xy
+    cuts = [0, 1, n_ang // 3, n_ang // 2 + 1, n_ang]
+    parts = [m.scores(dg, sc.scan_pts, p, sc.seed_pose, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts), full)
+    # (2) the float32 kernel and the fixed-point kernel are two independent code paths that must
+    #     agree exactly (float sums of 2^-25 multiples are exact in FP64)
+    cells = dg.download()
+    bumped = cells.copy()
+    bumped[0, 0] = np.float32(0.1)   # one unreachable, non-representable cell forces float32 cells
+    df = matcher.ScanMatchMap.from_spec(ctx, sc.grid)
+    df.upload(bumped)
+    assert dg.is_fixed_point() and not df.is_fixed_point()
+    assert np.array_equal(m.scores(df, sc.scan_pts, p, sc.seed_pose), full)
+    # (3) the matcher's winner is the maximum of the dump, and the unpenalised score is a mean of
+    #     grid values, hence bounded by the grid's range
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+    assert m.last_detail.best_score == full.max() and r == min(full.max(), 1.0)
+    p2 = p.copy()
+    p2[6] = 0.0
+    raw = m.scores(dg, sc.scan_pts, p2, sc.seed_pose, 0, 8)
+    assert raw.min() >= cells.min() - 1e-12 and raw.max() <= cells.max() + 1e-12
+    # (4) idempotence: same call, same bits
+    assert np.array_equal(m.scores(dg, sc.scan_pts, p, sc.seed_pose, 5, 9), full[5 * n_xy * n_xy: 9 * n_xy * n_xy])
+    dg.close()
+    df.close()

@@ -1,0 +1,122 @@
+"""CPU tests (-m "not gpu"): the oracle restatement against the reference's golden vectors and,
+where the reference was compiled here (oracle/_ref), against the reference itself."""
+import numpy as np
+import pytest
+
+from helpers import cov_close, golden_grid, golden_names, load_golden, random_scenario, sha
+from roborts_edu_slam_b200 import synth
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_golden(oracle, name):
+    sc, z = load_golden(name)
+    g = sc.grid
+    grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+    assert sha(grid) == str(z["grid_sha"])
+    assert np.array_equal(grid, golden_grid(z, g))
+    centre = oracle.world_to_map(g, sc.seed_pose)
+    assert np.array_equal(centre, z["centre_map"])
+    scores = oracle.scores(grid, g, sc.scan_pts, sc.passes[0], centre)
+    srt = np.sort(scores)[::-1]
+    assert sha(srt) == str(z["pass0_sorted_scores_sha"])
+    assert np.array_equal(srt[:64], z["pass0_sorted_head"])
+    r = oracle.match(grid, g, sc.scan_pts, sc.passes[0], sc.seed_pose)
+    assert r["response"] == float(z["pass0_response"])
+    assert np.array_equal(r["pose"], z["pass0_pose"])
+    assert np.array_equal(r["cov"], z["pass0_cov"])
+    assert np.array_equal(r["best_map"], z["pass0_best"])
+    if "chain_score" in z.files:
+        rc = oracle.match_chain(grid, g, sc.scan_pts, sc.passes, sc.seed_pose)
+        assert rc["score"] == float(z["chain_score"])
+        assert np.array_equal(rc["pose"], z["chain_pose"])
+        assert np.array_equal(rc["cov"], z["chain_cov"])
+        assert np.array_equal(rc["responses"], z["chain_responses"])
+
+
+def _compare_with_ref(oracle, ref, sc, chain):
+    g = sc.grid
+    grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+    m = ref.create_map(g)
+    try:
+        ref.build_map(m, g, sc.base_pts, sc.base_poses)
+        assert np.array_equal(grid, ref.read_map(m, g))
+        assert np.array_equal(oracle.world_to_map(g, sc.seed_pose), ref.world_to_map(m, sc.seed_pose))
+        assert np.array_equal(oracle.map_to_world(g, [100.25, 77.5, 0.3]), ref.map_to_world(m, [100.25, 77.5, 0.3]))
+        for p in sc.passes:
+            centre = ref.world_to_map(m, sc.seed_pose)
+            geo = oracle.geometry(g, p, len(sc.scan_pts), centre)
+            so = oracle.scores(grid, g, sc.scan_pts, p, centre)
+            cr = ref.candidates(m, sc.scan_pts, p, centre)
+            ix = np.rint((cr["x"] - geo["start_x"]) / geo["factor"]).astype(np.int64)
+            iy = np.rint((cr["y"] - geo["start_y"]) / geo["factor"]).astype(np.int64)
+            k = (cr["angle_index"].astype(np.int64) * geo["n_xy"] + ix) * geo["n_xy"] + iy
+            assert np.array_equal(np.sort(k), np.arange(len(k)))
+            assert np.array_equal(so[k], cr["score"])          # every candidate score, bit for bit
+            ro = oracle.match(grid, g, sc.scan_pts, p, sc.seed_pose)
+            rr = ref.match(m, sc.scan_pts, p, sc.seed_pose)
+            assert ro["response"] == rr["response"]
+            assert np.array_equal(ro["pose"], rr["pose"])
+            assert np.array_equal(ro["cov"], rr["cov"])       # same sort order even under ties
+        if chain:
+            ro = oracle.match_chain(grid, g, sc.scan_pts, sc.passes, sc.seed_pose)
+            rr = ref.match_chain(m, sc.scan_pts, sc.passes, sc.seed_pose)
+            assert ro["score"] == rr["score"]
+            assert np.array_equal(ro["pose"], rr["pose"])
+            assert np.array_equal(ro["cov"], rr["cov"])
+            assert np.array_equal(ro["responses"], rr["responses"])
+    finally:
+        ref.destroy_map(m)
+
+
+def test_oracle_vs_reference_named_configs(oracle, ref):
+    _compare_with_ref(oracle, ref, synth.config1(), False)
+    _compare_with_ref(oracle, ref, synth.config3(True), True)
+    for sc in synth.config4(3, seed=99):
+        _compare_with_ref(oracle, ref, sc, True)
+
+
+def test_oracle_vs_reference_random(oracle, ref, rng):
+    for trial in range(12):
+        sc = random_scenario(rng, n_points=int(rng.integers(5, 300)))
+        kind = [synth.COARSE, synth.FINE, synth.SUPER][trial % 3]
+        ups = int(rng.choice([20, 50, 100000]))
+        pen = bool(trial % 2)
+        sres = float(rng.choice([0.05, 0.02, 0.1, 0.025]))
+        sc.passes = [synth.pass_param(sres * int(rng.integers(2, 9)), sres, float(rng.uniform(0.02, 0.4)),
+                                      float(rng.uniform(0.005, 0.05)), 0.3, ups, pen, kind)]
+        _compare_with_ref(oracle, ref, sc, False)
+
+
+def test_oracle_vs_reference_ties(oracle, ref):
+    # binary grid + no penalty: the winner depends on the unstable sort's tie order
+    sc, _ = load_golden("ties_icra")
+    _compare_with_ref(oracle, ref, sc, True)
+
+
+def test_blur_kernel(oracle, ref):
+    for sigma, res in [(0.15, 0.05), (0.03, 0.025), (0.03, 0.01), (0.24, 0.08), (0.4, 0.1), (0.01, 0.05), (1.0, 0.05)]:
+        ho, ko = oracle.blur_kernel(sigma, res)
+        hr, kr = ref.blur_kernel(sigma, res)
+        assert ho == hr
+        if ho >= 0:
+            assert np.array_equal(ko, kr)
+
+
+def test_oracle_degenerate_inputs(oracle):
+    sc, z = load_golden("cfg1_icra")
+    g = sc.grid
+    grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+    # empty scan: response 0, pose and covariance untouched (correlate_scan_matcher.h:792-795)
+    cov = np.arange(9.0).reshape(3, 3)
+    r = oracle.match(grid, g, np.zeros((0, 2)), sc.passes[0], sc.seed_pose, cov)
+    assert r["response"] == 0.0 and np.array_equal(r["pose"], sc.seed_pose) and np.array_equal(r["cov"], cov)
+    # scan in unknown space: every candidate ties; response below threshold -> pose untouched
+    flat = np.full_like(grid, np.float32(0.3))
+    r = oracle.match(flat, g, sc.scan_pts, sc.passes[0], sc.seed_pose)
+    assert r["response"] < 0.6 and np.array_equal(r["pose"], sc.seed_pose)
+    assert r["n_avg"] > 1
+    nopen = sc.passes[0].copy()
+    nopen[6] = 0.0   # no centre penalty: all 3549 candidates tie exactly
+    r = oracle.match(flat, g, sc.scan_pts, nopen, sc.seed_pose)
+    assert r["n_avg"] == 3549 and np.array_equal(r["pose"], sc.seed_pose)
+    assert cov_close(r["cov"], r["cov"])

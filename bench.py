@@ -238,6 +238,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # the library's host worker pool shares the box's cores with the other ranks
+    os.environ.setdefault("RSM_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
     ctx = matcher.Context(local_rank)
     sc = rank_scenario(rank)
     g = sc.grid
@@ -309,6 +311,10 @@ def main():
         b, e = contiguous_range(args.pairs_per_gpu * world, rank, world)
         pairs = synth.config4(e - b, first=b)
         packed = matcher.pack_loop_closure(pairs)
+        for key in ("base_pts", "pts", "base_poses", "centres", "poses"):   # inputs live in pinned host memory
+            t = torch.from_numpy(packed[key]).pin_memory()
+            packed[key] = t.numpy()
+            packed["_pin_" + key] = t
         matcher.loop_closure_batch(ctx, packed, pairs[0].passes)   # warm-up
         barrier()
         ctx.reset_stats()

@@ -84,6 +84,11 @@ typedef struct rsm_stats {
   double score_kernel_ms;       /* CUDA-event time of scoring kernels (only while profiling is on) */
   double raster_kernel_ms;      /* CUDA-event time of rasterisation kernels (profiling on) */
   double select_kernel_ms;      /* CUDA-event time of selection kernels (profiling on) */
+  /* host wall-clock per phase of a pass, summed (always on): 0 geometry + angle tables + upload,
+   * 1 wait for scoring + selection, 2 host stage 1 (best pose, positional covariance),
+   * 3 same-(x,y) gather round trip, 4 host stage 2 (angular covariance), 5 exact-sort path,
+   * 6 grid rasterisation calls, 7 reserved */
+  double phase_ms[8];
 } rsm_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -17,9 +17,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,8 +78,88 @@ enum KernelClass { KC_SCORE = 0, KC_SELECT = 1, KC_RASTER = 2, KC_OTHER = 3, KC_
 
 }  // namespace
 
+namespace {
+// Small persistent worker pool for the per-item host work of large batches (angle tables,
+// FindBestCandidate, covariances): items are independent, so the range is cut into chunks that
+// the workers and the calling thread pull from an atomic counter.
+class HostPool {
+ public:
+  ~HostPool() { stop(); }
+  void run(int n, int grain, const std::function<void(int, int)>& fn) {
+    if (n <= 0) return;
+    const int chunks = (n + grain - 1) / grain;
+    if (chunks <= 1 || threads_wanted() <= 1) { fn(0, n); return; }
+    start();
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn; n_ = n; grain_ = grain; next_.store(0); pending_ = int(workers_.size()); ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  // RSM_HOST_THREADS caps the pool (one process per GPU shares the host cores with its peers)
+  static int threads_wanted() {
+    static const int n = [] {
+      unsigned hc = std::thread::hardware_concurrency();
+      int t = int(std::min<unsigned>(hc ? hc : 1, 16));
+      if (const char* e = std::getenv("RSM_HOST_THREADS")) { const int v = std::atoi(e); if (v >= 1) t = std::min(v, 64); }
+      return t;
+    }();
+    return n;
+  }
+  void work() {
+    for (;;) {
+      const int c = next_.fetch_add(1);
+      const int b = c * grain_;
+      if (b >= n_) break;
+      (*fn_)(b, std::min(n_, b + grain_));
+    }
+  }
+  void start() {
+    if (!workers_.empty()) return;
+    const int t = threads_wanted() - 1;
+    for (int i = 0; i < t; ++i)
+      workers_.emplace_back([this] {
+        unsigned seen = 0;
+        for (;;) {
+          {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+            if (quit_) return;
+            seen = gen_;
+          }
+          work();
+          {
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) done_cv_.notify_one();
+          }
+        }
+      });
+  }
+  void stop() {
+    { std::lock_guard<std::mutex> lk(m_); quit_ = true; }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+    workers_.clear();
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int, int)>* fn_ = nullptr;
+  int n_ = 0, grain_ = 1, pending_ = 0;
+  unsigned gen_ = 0;
+  bool quit_ = false;
+  std::atomic<int> next_{0};
+};
+}  // namespace
+
 struct rsm_ctx {
   int device = 0;
+  HostPool pool;
   cudaStream_t stream = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::string err;
@@ -87,6 +174,17 @@ struct rsm_ctx {
 };
 
 namespace {
+
+struct PhaseTimer {   // host wall clock, accumulated into rsm_stats::phase_ms
+  rsm_ctx* ctx;
+  std::chrono::steady_clock::time_point t;
+  explicit PhaseTimer(rsm_ctx* c) : ctx(c), t(std::chrono::steady_clock::now()) {}
+  void lap(int phase) {
+    auto n = std::chrono::steady_clock::now();
+    ctx->stats.phase_ms[phase] += std::chrono::duration<double, std::milli>(n - t).count();
+    t = n;
+  }
+};
 
 int fail(rsm_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -274,6 +372,7 @@ bool adjacent_tie(const std::vector<Cand>& v, size_t n) {
 int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* scores_out,
              int64_t scores_cap, int64_t* scores_written) {
   const int n_items = int(items.size());
+  PhaseTimer pt(ctx);
   // ---- host geometry -------------------------------------------------------------------------
   std::vector<int> act;
   for (int i = 0; i < n_items; ++i) {
@@ -341,7 +440,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   int64_t total_cand = 0;
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];
-    int ncta = int(std::min<int64_t>(296, (it.n_local + 16383) / 16384));
+    int ncta = int(std::min<int64_t>(592, (it.n_local + 4095) / 4096));
     if (ncta < 1) ncta = 1;
     it.sel_cta0 = total_sel_cta; it.sel_ncta = ncta;
     total_sel_cta += ncta;
@@ -372,16 +471,22 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   double* h_trig = reinterpret_cast<double*>(up + o_trig);
   int cta = 0;
   bool any_fixed = false, any_float = false;
+  ctx->pool.run(na, 32, [&](int a0, int a1) {
+    for (int a = a0; a < a1; ++a) {
+      const PassItem& it = items[act[a]];
+      const PassGeo& g = it.geo;
+      double* t = h_trig + it.trig_off;
+      for (int ia = 0; ia < g.n_ang; ++ia) {
+        const double angle = g.angle_of(ia);
+        t[3 * ia] = std::cos(angle);      // correlate_scan_matcher.h:171-172
+        t[3 * ia + 1] = std::sin(angle);
+        t[3 * ia + 2] = angle;
+      }
+    }
+  });
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];
     const PassGeo& g = it.geo;
-    double* t = h_trig + it.trig_off;
-    for (int ia = 0; ia < g.n_ang; ++ia) {
-      const double angle = g.angle_of(ia);
-      t[3 * ia] = std::cos(angle);      // correlate_scan_matcher.h:171-172
-      t[3 * ia + 1] = std::sin(angle);
-      t[3 * ia + 2] = angle;
-    }
     ScoreJob& J = sjobs[a];
     std::memset(&J, 0, sizeof J);
     J.grid = it.grid->d_cells;
@@ -457,6 +562,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
                      pool_cap, reinterpret_cast<int*>(dw + o_poolcnt)));
   }
   ctx->stats.kernel_launches++;
+  pt.lap(0);
   // read back everything up to the pool, plus a first slice of the pool
   char* dn = ctx->h_down.p;
   const size_t head_bytes = o_pool - o_best;
@@ -482,6 +588,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     ctx->stats.d2h_bytes += size_t(pool_count - pool_first) * sizeof(PoolEntry);
   }
 
+  pt.lap(1);
   // ---- stage 1: best pose, positional covariance ---------------------------------------------
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];
@@ -496,60 +603,69 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (it.exact) continue;
     it.a_list.push_back(Cand{pe.score, int64_t(it.a0) * it.geo.n_xy * it.geo.n_xy + pe.index});
   }
-  bool need_gather = false;
+  ctx->pool.run(na, 16, [&](int a_begin, int a_end) {
+    for (int a = a_begin; a < a_end; ++a) {
+      PassItem& it = items[act[a]];
+      if (it.exact) continue;
+      const PassGeo& g = it.geo;
+      const double top_score = key_to_score(h_best[a]);
+      std::sort(it.a_list.begin(), it.a_list.end(), by_score_desc);
+      if (it.a_list.empty() || it.a_list[0].score != top_score || adjacent_tie(it.a_list, it.a_list.size())) { it.exact = true; continue; }
+      it.best = find_best(g, it.a_list.data(), it.a_list.size());
+      if (size_t(it.best.n_avg) != it.a_list.size()) { it.exact = true; continue; }   // cannot happen; be safe
+      const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
+      for (int c = 0; c < it.sel_ncta; ++c) {
+        const int cnt = h_topcnt[it.sel_cta0 + c];
+        const Entry* e = h_top + size_t(it.sel_cta0 + c) * kTopK;
+        for (int r = 0; r < cnt; ++r) it.top.push_back(Cand{e[r].score, base + e[r].index});
+      }
+      // only the kTopK best of the merged per-CTA lists matter; their VALUES are unique whatever
+      // the order of equal scores, and equal scores at the cut are detected below
+      if (it.top.size() > size_t(kTopK)) {
+        std::nth_element(it.top.begin(), it.top.begin() + kTopK, it.top.end(), by_score_desc);
+        it.top.resize(kTopK);
+      }
+      std::sort(it.top.begin(), it.top.end(), by_score_desc);
+      const int type = it.param.type;
+      const double bound = cov_score_bound(it.best);
+      if (type == RSM_COARSE || type == RSM_FINE) {
+        // the 20-element prefix is unambiguous unless the 20th and 21st scores tie above the bound
+        if (it.top.size() == size_t(kTopK) && it.top[kTopK - 1].score > bound &&
+            it.top[kTopK - 1].score == it.top[kTopK - 2].score) { it.exact = true; continue; }
+        positional_cov(g, it.param, it.best, it.top.data(), it.top.size(), it.cov);
+      }
+      if (type == RSM_COARSE || type == RSM_SUPER) {
+        if (it.best.score < kDoubleTolerance) {
+          angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
+        } else {
+          int xs[8], ys[8], nx = 0, ny = 0;
+          const double tol = g.factor;
+          for (int ix = 0; ix < g.n_xy && nx < 8; ++ix) if (DoubleEqual(g.x_of(ix), it.best.x, tol)) xs[nx++] = ix;
+          for (int iy = 0; iy < g.n_xy && ny < 8; ++iy) if (DoubleEqual(g.y_of(iy), it.best.y, tol)) ys[ny++] = iy;
+          if (nx * ny > kMaxCols) { it.exact = true; continue; }
+          it.n_cols = 0;
+          for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) it.cols[it.n_cols++] = xs[i] * g.n_xy + ys[j];
+          if (it.n_cols == 0) angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
+        }
+      }
+    }
+  });
   std::vector<GatherJob> gjobs;
   std::vector<int> gitem;
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];
-    if (it.exact) continue;
+    if (it.exact || it.n_cols == 0) continue;
     const PassGeo& g = it.geo;
-    const double top_score = key_to_score(h_best[a]);
-    std::sort(it.a_list.begin(), it.a_list.end(), by_score_desc);
-    if (it.a_list.empty() || it.a_list[0].score != top_score || adjacent_tie(it.a_list, it.a_list.size())) { it.exact = true; continue; }
-    it.best = find_best(g, it.a_list.data(), it.a_list.size());
-    if (size_t(it.best.n_avg) != it.a_list.size()) { it.exact = true; continue; }   // cannot happen; be safe
-    const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
-    for (int c = 0; c < it.sel_ncta; ++c) {
-      const int cnt = h_topcnt[it.sel_cta0 + c];
-      const Entry* e = h_top + size_t(it.sel_cta0 + c) * kTopK;
-      for (int r = 0; r < cnt; ++r) it.top.push_back(Cand{e[r].score, base + e[r].index});
-    }
-    std::sort(it.top.begin(), it.top.end(), by_score_desc);
-    if (it.top.size() > size_t(kTopK)) it.top.resize(kTopK);
-    const int type = it.param.type;
-    const double bound = cov_score_bound(it.best);
-    if (type == RSM_COARSE || type == RSM_FINE) {
-      // the 20-element prefix is unambiguous unless the 20th and 21st scores tie above the bound
-      if (it.top.size() == size_t(kTopK) && it.top[kTopK - 1].score > bound &&
-          it.top[kTopK - 1].score == it.top[kTopK - 2].score) { it.exact = true; continue; }
-      positional_cov(g, it.param, it.best, it.top.data(), it.top.size(), it.cov);
-    }
-    if (type == RSM_COARSE || type == RSM_SUPER) {
-      if (it.best.score < kDoubleTolerance) {
-        angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
-      } else {
-        int xs[8], ys[8], nx = 0, ny = 0;
-        const double tol = g.factor;
-        for (int ix = 0; ix < g.n_xy && nx < 8; ++ix) if (DoubleEqual(g.x_of(ix), it.best.x, tol)) xs[nx++] = ix;
-        for (int iy = 0; iy < g.n_xy && ny < 8; ++iy) if (DoubleEqual(g.y_of(iy), it.best.y, tol)) ys[ny++] = iy;
-        if (nx * ny > kMaxCols) { it.exact = true; continue; }
-        it.n_cols = 0;
-        for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) it.cols[it.n_cols++] = xs[i] * g.n_xy + ys[j];
-        if (it.n_cols == 0) {
-          angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
-        } else {
-          GatherJob G;
-          std::memset(&G, 0, sizeof G);
-          G.score = reinterpret_cast<const double*>(dw + o_score) + it.score_off;
-          G.out = reinterpret_cast<double*>(dw + o_gout) + it.gather_off;
-          G.n_xy = g.n_xy; G.n_ang = it.a1 - it.a0; G.n_cols = it.n_cols;
-          for (int c = 0; c < it.n_cols; ++c) G.cols[c] = it.cols[c];
-          gjobs.push_back(G); gitem.push_back(act[a]);
-          need_gather = true;
-        }
-      }
-    }
+    GatherJob G;
+    std::memset(&G, 0, sizeof G);
+    G.score = reinterpret_cast<const double*>(dw + o_score) + it.score_off;
+    G.out = reinterpret_cast<double*>(dw + o_gout) + it.gather_off;
+    G.n_xy = g.n_xy; G.n_ang = it.a1 - it.a0; G.n_cols = it.n_cols;
+    for (int c = 0; c < it.n_cols; ++c) G.cols[c] = it.cols[c];
+    gjobs.push_back(G); gitem.push_back(act[a]);
   }
+  const bool need_gather = !gjobs.empty();
+  pt.lap(2);
   // ---- stage 2: angular covariance from the same-(x,y) columns ---------------------------------
   if (need_gather) {
     const int ng = int(gjobs.size());
@@ -562,36 +678,59 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (rc) return rc;
     ctx->stats.h2d_bytes += sizeof(GatherJob) * ng;
     ctx->stats.d2h_bytes += gather_doubles * 8;
+    pt.lap(3);
     const double* h_g = reinterpret_cast<const double*>(ctx->h_down.p);
-    for (int gi = 0; gi < ng; ++gi) {
-      PassItem& it = items[gitem[gi]];
-      const PassGeo& g = it.geo;
-      const double bound = cov_score_bound(it.best);
-      const int nang = it.a1 - it.a0;
-      const double* col = h_g + it.gather_off;
-      it.xy.clear();
-      for (int c = 0; c < it.n_cols; ++c)
-        for (int ia = 0; ia < nang; ++ia) {
-          const double s = col[size_t(c) * nang + ia];
-          if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
+    ctx->pool.run(ng, 16, [&](int g_begin, int g_end) {
+      for (int gi = g_begin; gi < g_end; ++gi) {
+        PassItem& it = items[gitem[gi]];
+        const PassGeo& g = it.geo;
+        const double bound = cov_score_bound(it.best);
+        const int nang = it.a1 - it.a0;
+        const double* col = h_g + it.gather_off;
+        it.xy.clear();
+        for (int c = 0; c < it.n_cols; ++c)
+          for (int ia = 0; ia < nang; ++ia) {
+            const double s = col[size_t(c) * nang + ia];
+            if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
+          }
+        if (it.xy.size() > size_t(kTopK)) {
+          std::nth_element(it.xy.begin(), it.xy.begin() + kTopK, it.xy.end(), by_score_desc);
+          it.xy.resize(kTopK);
         }
-      std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
-      if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
-          it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) { it.exact = true; continue; }
-      if (it.xy.size() > size_t(kTopK)) it.xy.resize(kTopK);
-      angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
+        std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
+        if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
+            it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) { it.exact = true; continue; }
+        angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
+      }
+    });
+  }
+  pt.lap(4);
+  // ---- exact path for the items that need the reference's own sort order ----------------------
+  {
+    std::vector<int> ex;
+    std::vector<size_t> ex_off;
+    size_t ex_doubles = 0;
+    for (int a = 0; a < na; ++a)
+      if (items[act[a]].exact) { ex.push_back(act[a]); ex_off.push_back(ex_doubles); ex_doubles += size_t(items[act[a]].n_local); }
+    if (!ex.empty()) {
+      rc = ensure_pinned(ctx, ctx->h_down, ex_doubles * 8);
+      if (rc) return rc;
+      double* h_sc = reinterpret_cast<double*>(ctx->h_down.p);
+      for (size_t i = 0; i < ex.size(); ++i) {
+        const PassItem& it = items[ex[i]];
+        CU(cudaMemcpyAsync(h_sc + ex_off[i], dw + o_score + it.score_off * 8, size_t(it.n_local) * 8,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      rc = sync_stream(ctx);
+      if (rc) return rc;
+      ctx->stats.d2h_bytes += ex_doubles * 8;
+      ctx->pool.run(int(ex.size()), 1, [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) finish_exact(items[ex[i]], h_sc + ex_off[i]);
+      });
+      ctx->stats.exact_sort_passes += int64_t(ex.size());
     }
   }
-  // ---- exact path for the items that need the reference's own sort order ----------------------
-  for (int a = 0; a < na; ++a) {
-    PassItem& it = items[act[a]];
-    if (!it.exact) continue;
-    std::vector<double> sc(it.n_local);
-    CU(cudaMemcpy(sc.data(), dw + o_score + it.score_off * 8, size_t(it.n_local) * 8, cudaMemcpyDeviceToHost));
-    ctx->stats.d2h_bytes += size_t(it.n_local) * 8;
-    finish_exact(it, sc.data());
-    ctx->stats.exact_sort_passes++;
-  }
+  pt.lap(5);
   // ---- response, pose write-back (:861-869) ----------------------------------------------------
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];

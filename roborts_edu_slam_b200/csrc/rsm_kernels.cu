@@ -132,17 +132,31 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
     const unsigned long long key = score_key(s);
     tmax = key > tmax ? key : tmax;
   }
-  // threshold = the kTopK-th largest thread maximum: a lower bound of the slice's kTopK-th largest
-  // element, so everything in the slice's top-kTopK is >= threshold.
+  // threshold: every warp pops its 3 largest thread maxima (warp shuffles only); the minimum of
+  // the 8 third-largest values has at least 24 >= kTopK slice elements at or above it, so it is a
+  // lower bound of the slice's kTopK-th largest element.  Warps with fewer than 3 non-empty
+  // threads report 0, which keeps everything.
   unsigned long long thr = 0ull;
   {
-    unsigned long long mine = tmax;
-    for (int r = 0; r < kTopK; ++r) {
-      KeyTag w = block_argmax(mine, (unsigned int)tid, s_k, s_t);
-      thr = w.key;
-      if (w.key == 0ull) break;  // fewer than kTopK non-empty threads: keep everything
-      if (w.tag == (unsigned int)tid) mine = 0ull;
+    unsigned long long mine = tmax, third = 0ull;
+    const unsigned int lane = tid & 31;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      unsigned long long k = mine;
+      unsigned int t = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        const unsigned int t2 = __shfl_xor_sync(0xffffffffu, t, o);
+        if (k2 > k || (k2 == k && t2 < t)) { k = k2; t = t2; }
+      }
+      third = k;
+      if (t == lane) mine = 0ull;
     }
+    if (lane == 0) s_k[tid >> 5] = third;
+    __syncthreads();
+    thr = s_k[0];
+    for (int w = 1; w < (NT >> 5); ++w) thr = s_k[w] < thr ? s_k[w] : thr;
   }
   __syncthreads();
   // pass 2: everything >= threshold goes to the shared buffer

@@ -56,10 +56,13 @@ class PassDetail(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", c_i64), ("score_launches", c_i64), ("evals", c_i64), ("passes", c_i64),
                 ("exact_sort_passes", c_i64), ("h2d_bytes", c_i64), ("d2h_bytes", c_i64),
-                ("score_kernel_ms", c_d), ("raster_kernel_ms", c_d), ("select_kernel_ms", c_d)]
+                ("score_kernel_ms", c_d), ("raster_kernel_ms", c_d), ("select_kernel_ms", c_d),
+                ("phase_ms", c_d * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_ms"] = [float(v) for v in self.phase_ms]
+        return d
 
 
 # every symbol include/rsm.h declares: (restype, argtypes)

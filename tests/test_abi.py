@@ -35,7 +35,7 @@ def test_library_binds_and_reports_version():
 def test_struct_layouts():
     assert ctypes.sizeof(matcher.PassParamStruct) == 56
     assert ctypes.sizeof(matcher.PassDetail) == 72
-    assert ctypes.sizeof(matcher.Stats) == 80
+    assert ctypes.sizeof(matcher.Stats) == 144
 
 
 def test_no_cpu_fallback():

@@ -112,6 +112,11 @@ int rsm_flush_l2(rsm_ctx* ctx);
  * offset is GridMapBase::map_offset_ (metres). */
 int rsm_grid_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, double offset_x,
                     double offset_y, rsm_grid** out);
+/* Same, from GridMapBase::get_scale_factor() (= 1/resolution as the map computed it) instead of
+ * the resolution, so that an adapter holding a live reference map reproduces its cell length bit
+ * for bit (map/grid_map_base.h:297-309). */
+int rsm_grid_create_from_scale(rsm_ctx* ctx, int size_x, int size_y, double scale_factor,
+                               double offset_x, double offset_y, rsm_grid** out);
 void rsm_grid_destroy(rsm_ctx* ctx, rsm_grid* grid);
 int rsm_grid_set_offset(rsm_ctx* ctx, rsm_grid* grid, double offset_x, double offset_y);
 /* Hand over an existing grid: prob[y*size_x + x] = ProbabilityCell::prob_value_ (map/grid_map_cell.h:301-328). */
@@ -148,6 +153,15 @@ void rsm_scan_destroy(rsm_ctx* ctx, rsm_scan* scan);
 int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
               const rsm_pass_param* param, double pose_world[3], double cov[9], double* response,
               rsm_pass_detail* detail /* nullable */);
+
+/* rsm_match_map: the same pass for a caller that owns the world<->map transform (the C++ adapter
+ * calls the reference map's own GetMapCoordsPose / GetWorldCoordsPose, map/grid_map_base.h:83-93).
+ * center_map = seed pose in map cells / rad; cov in/out as in rsm_match; best_map_out = (averaged)
+ * best candidate in map coordinates, which the caller converts and adopts iff *response exceeds
+ * its threshold (:866-869). */
+int rsm_match_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                  const rsm_pass_param* param, const double center_map[3], double cov[9],
+                  double* response, double best_map_out[3], rsm_pass_detail* detail /* nullable */);
 
 /* Same pass on a device-resident scan (no host->device copy of the points). */
 int rsm_match_resident(rsm_ctx* ctx, const rsm_grid* grid, const rsm_scan* scan,
@@ -209,7 +223,8 @@ int rsm_match_finish(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, i
  * mode 0 = shared-memory row segments (32 consecutive 4-byte words per warp load, the access
  * shape of the scoring kernel), 1 = shared-memory random words, 2 = global-memory row segments
  * over an L1/L2-resident footprint, 3 = global-memory random words.  footprint_bytes: tile size
- * (modes 0/1, <= 200 KB) or buffer size (modes 2/3).  *gbps = bytes gathered / CUDA-event time. */
+ * (modes 0/1, <= 200 KB) or buffer size (modes 2/3), rounded down to a power of two.
+ * *gbps = bytes gathered / CUDA-event time. */
 int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int iters, double* gbps);
 
 #ifdef __cplusplus

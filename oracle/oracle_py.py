@@ -252,3 +252,43 @@ class Ref:
         r = self.L.ref_match_chain(m, len(pts), pts.ctypes.data, params.ctypes.data, int(use_fine), pose.ctypes.data,
                                    cov.ctypes.data, resp.ctypes.data, ctypes.byref(sec))
         return dict(score=r, pose=pose, cov=cov, responses=resp, seconds=sec.value)
+
+
+def dropin_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libdropin.so"))
+
+
+class DropIn:
+    """The product's C++ adapter (scan_matcher_adapter.hpp) running on live reference objects.
+
+    Built only where the reference was available (oracle/_ref/libdropin.so); needs a GPU."""
+
+    def __init__(self, device=0):
+        L = ctypes.CDLL(os.path.join(_HERE, "_ref", "libdropin.so"))
+        L.dropin_create.restype = c_p
+        L.dropin_create.argtypes = [c_i]
+        L.dropin_destroy.argtypes = [c_p]
+        L.dropin_match_chain.restype = c_d
+        L.dropin_match_chain.argtypes = [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        self.L = L
+        self.h = L.dropin_create(device)
+        if not self.h:
+            raise RuntimeError("adapter could not create a CUDA context")
+
+    def close(self):
+        if self.h:
+            self.L.dropin_destroy(self.h)
+            self.h = None
+
+    def match_chain(self, ref_map, pts, params, pose_world, cov=None):
+        """params: list of 1 or 3 pass-parameter blocks; ref_map: handle from Ref.create_map."""
+        pts = _f64(pts)
+        n_pass = len(params)
+        params = _f64(np.concatenate(params))
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        resp = np.zeros(3)
+        used = c_i(0)
+        s = self.L.dropin_match_chain(self.h, ref_map, len(pts), pts.ctypes.data, params.ctypes.data, n_pass,
+                                      pose.ctypes.data, cov.ctypes.data, resp.ctypes.data, ctypes.byref(used))
+        return dict(score=s, pose=pose, cov=cov, responses=resp, exact_used=used.value)

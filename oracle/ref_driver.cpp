@@ -27,13 +27,11 @@
 
 #include "scan_match/correlate_scan_matcher.h"
 
+#include "ref_types.h"
+
 using namespace roborts_slam;
 
 namespace {
-
-struct RefMap {
-  std::shared_ptr<ScanMatchMap> map;
-};
 
 std::shared_ptr<RangeDataContainer2d> MakeScan(int n, const double* xy, const double* pose_world) {
   auto rd = std::make_shared<RangeDataContainer2d>(n > 0 ? n : 1);

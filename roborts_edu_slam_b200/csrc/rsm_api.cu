@@ -316,6 +316,7 @@ struct PassItem {
   double response = 0.0;
   rsm_pass_detail detail;
   int ang_begin = 0, ang_end = -1; // angle slice (-1: all)
+  const double* center_map = nullptr;  // non-null: seed given in map coordinates, pose_world untouched
   // internal
   bool active = false;
   PassGeo geo;
@@ -385,7 +386,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
         !(it.param.search_space_size >= 0) || !(it.param.search_angle_offset >= 0) || it.param.use_point_size < 2)
       return fail(ctx, RSM_ERR_INVALID, "bad pass parameters");
     double center[3];
-    it.grid->tf.world_to_map(it.pose_world, center);
+    if (it.center_map) { center[0] = it.center_map[0]; center[1] = it.center_map[1]; center[2] = it.center_map[2]; }
+    else it.grid->tf.world_to_map(it.pose_world, center);
     it.geo = make_geo(it.param, it.P, it.grid->cell_len(), center);
     if (it.geo.n_ang < 1 || it.geo.n_xy < 1 || it.geo.n_cand() > (int64_t(1) << 31) - 1)
       return fail(ctx, RSM_ERR_INVALID, "search window has %lld candidates", (long long)it.geo.n_cand());
@@ -746,7 +748,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     it.detail.pose_updated = 0;
     if (it.response > it.param.response_threshold) {
       const double b[3] = {it.best.x, it.best.y, it.best.angle};
-      it.grid->tf.map_to_world(b, it.pose_world);
+      if (!it.center_map) it.grid->tf.map_to_world(b, it.pose_world);
       it.detail.pose_updated = 1;
     }
     ctx->stats.passes++;
@@ -869,11 +871,19 @@ int rsm_flush_l2(rsm_ctx* ctx) {
 
 // ---- grids -----------------------------------------------------------------------------------
 int rsm_grid_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, double offset_x, double offset_y, rsm_grid** out) {
-  if (!ctx || !out || size_x <= 0 || size_y <= 0 || !(resolution > 0)) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_create: bad arguments");
+  if (!(resolution > 0)) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_create: bad resolution");
+  int rc = rsm_grid_create_from_scale(ctx, size_x, size_y, 1.0 / resolution, offset_x, offset_y, out);   // map/grid_map_base.h:50
+  if (rc == RSM_OK) (*out)->resolution = resolution;
+  return rc;
+}
+
+int rsm_grid_create_from_scale(rsm_ctx* ctx, int size_x, int size_y, double scale_factor, double offset_x, double offset_y, rsm_grid** out) {
+  if (!ctx || !out || size_x <= 0 || size_y <= 0 || size_x > 32768 || size_y > 32768 || !(scale_factor > 0))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_grid_create: bad arguments");
   rsm_grid* g = new rsm_grid;
   g->size_x = size_x; g->size_y = size_y; g->pitch = size_x;
-  g->resolution = resolution;
-  g->scale = 1.0 / resolution;                 // GridMapBase ctor, map/grid_map_base.h:50
+  g->resolution = 1 / scale_factor;
+  g->scale = scale_factor;
   g->off_x = offset_x; g->off_y = offset_y;
   g->tf.set(g->scale, offset_x, offset_y);
   const size_t bytes = (size_t(size_x) * size_y * 4 + 15) / 16 * 16;
@@ -1084,6 +1094,29 @@ int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pt
   return RSM_OK;
 }
 
+int rsm_match_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
+                  const double center_map[3], double cov[9], double* response, double best_map_out[3],
+                  rsm_pass_detail* detail) {
+  if (!ctx || !grid || !param || !center_map || !cov || !response || !best_map_out || n_pts < 0 || (n_pts > 0 && !pts_xy))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_map: bad arguments");
+  *response = 0.0;
+  if (detail) std::memset(detail, 0, sizeof *detail);
+  if (!grid->init || n_pts == 0) return RSM_OK;   // correlate_scan_matcher.h:792-795
+  double* d_pts = nullptr;
+  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
+  if (rc) return rc;
+  double unused_pose[3] = {0.0, 0.0, 0.0};
+  std::vector<PassItem> items(1);
+  items[0].grid = grid; items[0].d_pts = d_pts; items[0].P = n_pts; items[0].param = *param;
+  items[0].pose_world = unused_pose; items[0].cov = cov; items[0].center_map = center_map;
+  rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+  if (rc) return rc;
+  *response = items[0].response;
+  for (int i = 0; i < 3; ++i) best_map_out[i] = items[0].detail.best_pose_map[i];
+  if (detail) *detail = items[0].detail;
+  return RSM_OK;
+}
+
 int rsm_scan_create(rsm_ctx* ctx, const double* pts_xy, int n_pts, rsm_scan** out) {
   if (!ctx || !out || n_pts < 0 || (n_pts > 0 && !pts_xy)) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_create: bad arguments");
   rsm_scan* s = new rsm_scan;
@@ -1128,13 +1161,14 @@ int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int i
   if (!ctx || !gbps || mode < 0 || mode > 3 || footprint_bytes < 1024 || iters < 4)
     return fail(ctx, RSM_ERR_INVALID, "rsm_microbench_gather: bad arguments");
   if (mode < 2 && footprint_bytes > 200 * 1024) return fail(ctx, RSM_ERR_INVALID, "shared-memory tile must be <= 200 KB");
-  const unsigned int words = (unsigned int)(footprint_bytes / 4);
-  int rc = ensure_dev(ctx, ctx->d_flush, std::max<size_t>(size_t(footprint_bytes) + 64, size_t(256) << 20));
+  unsigned int words = 32768;   // largest power of two not above the requested footprint (>= 128 KB)
+  while (size_t(words) * 2 * 4 <= size_t(footprint_bytes)) words *= 2;
+  int rc = ensure_dev(ctx, ctx->d_flush, std::max<size_t>(size_t(words) * 4 + 256, size_t(256) << 20));
   if (rc) return rc;
   unsigned long long* sink = reinterpret_cast<unsigned long long*>(ctx->d_flush.p);
   const int* g = reinterpret_cast<const int*>(ctx->d_flush.p + 64);
   const int n_cta = mode < 2 ? 148 : 148 * 2;
-  iters = iters / 4 * 4;
+  iters = std::max(8, iters / 8 * 8);
   CU(launch_microbench(ctx->stream, mode, g, words, iters, n_cta, sink));   // warm-up (fills L2 / I-cache)
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));

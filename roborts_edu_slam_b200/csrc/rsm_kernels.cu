@@ -300,26 +300,40 @@ microbench_kernel(const int* __restrict__ g, unsigned int words, int iters, int 
   const bool use_smem = mode < 2;
   const bool random = (mode & 1) != 0;
   if (use_smem) {
-    for (unsigned int i = threadIdx.x; i < words; i += blockDim.x) tile[i] = (int)(i * 2654435761u);
+    for (unsigned int i = threadIdx.x; i < words + 32u; i += blockDim.x) tile[i] = (int)(i * 2654435761u);
     __syncthreads();
   }
+  // `words` is a power of two.  One LCG step yields a base; 8 loads then read 8 row segments (or
+  // 8 scattered words per lane) at fixed strides from it, so address generation costs ~0.4
+  // instructions per load and the load pipe is the limit.  Bases are 4-byte aligned, i.e. row
+  // segments are misaligned with respect to 128-byte lines like the scoring kernel's.
   const unsigned int lane = threadIdx.x & 31;
-  const unsigned int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr unsigned int kStride = 1061u;                 // words between the 8 loads of a step (odd)
+  const unsigned int mask = words / 2 - 1u;               // bases in the lower half; 8 strides stay inside
+  unsigned int st = random ? mix(gtid * 9781u + 7u) : mix((gtid >> 5) * 9781u + 1u);
+  const unsigned int add = random ? 0u : lane;
   unsigned int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-  unsigned int st = mix(warp_id * 9781u + 1u);
-  const unsigned int span = random ? words : (words - 32u);
-  for (int it = 0; it < iters; it += 4) {
-    unsigned int b0, b1, b2, b3;
-    if (random) {
-      b0 = mix(st + lane * 4u) % span; b1 = mix(st + lane * 4u + 1u) % span;
-      b2 = mix(st + lane * 4u + 2u) % span; b3 = mix(st + lane * 4u + 3u) % span;
-    } else {
-      b0 = mix(st) % span + lane; b1 = mix(st + 1u) % span + lane;
-      b2 = mix(st + 2u) % span + lane; b3 = mix(st + 3u) % span + lane;
+  if (use_smem) {
+#pragma unroll 1
+    for (int it = 0; it < iters; it += 8) {
+      st = st * 1664525u + 1013904223u;
+      const int* p = tile + ((st >> 7) & mask) + add;
+      acc0 += p[0] + p[kStride];
+      acc1 += p[2 * kStride] + p[3 * kStride];
+      acc2 += p[4 * kStride] + p[5 * kStride];
+      acc3 += p[6 * kStride] + p[7 * kStride];
     }
-    st += 131u;
-    if (use_smem) { acc0 += tile[b0]; acc1 += tile[b1]; acc2 += tile[b2]; acc3 += tile[b3]; }
-    else { acc0 += __ldg(g + b0); acc1 += __ldg(g + b1); acc2 += __ldg(g + b2); acc3 += __ldg(g + b3); }
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < iters; it += 8) {
+      st = st * 1664525u + 1013904223u;
+      const int* p = g + ((st >> 7) & mask) + add;
+      acc0 += __ldg(p) + __ldg(p + kStride);
+      acc1 += __ldg(p + 2 * kStride) + __ldg(p + 3 * kStride);
+      acc2 += __ldg(p + 4 * kStride) + __ldg(p + 5 * kStride);
+      acc3 += __ldg(p + 6 * kStride) + __ldg(p + 7 * kStride);
+    }
   }
   const unsigned int acc = acc0 + acc1 + acc2 + acc3;
   if (acc == 0x12345u) atomicAdd(sink, 1ull);   // keeps the loads alive
@@ -327,7 +341,7 @@ microbench_kernel(const int* __restrict__ g, unsigned int words, int iters, int 
 
 cudaError_t launch_microbench(cudaStream_t st, int mode, const int* g, unsigned int words, int iters,
                               int n_cta, unsigned long long* sink) {
-  const size_t smem = mode < 2 ? size_t(words) * 4 : 0;
+  const size_t smem = mode < 2 ? size_t(words + 32) * 4 : 0;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

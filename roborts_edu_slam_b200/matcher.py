@@ -80,6 +80,7 @@ ABI = {
     "rsm_timer_stop": (c_i, [c_p, ctypes.POINTER(c_d)]),
     "rsm_flush_l2": (c_i, [c_p]),
     "rsm_grid_create": (c_i, [c_p, c_i, c_i, c_d, c_d, c_d, ctypes.POINTER(c_p)]),
+    "rsm_grid_create_from_scale": (c_i, [c_p, c_i, c_i, c_d, c_d, c_d, ctypes.POINTER(c_p)]),
     "rsm_grid_destroy": (None, [c_p, c_p]),
     "rsm_grid_set_offset": (c_i, [c_p, c_p, c_d, c_d]),
     "rsm_grid_upload_f32": (c_i, [c_p, c_p, c_p]),
@@ -89,6 +90,7 @@ ABI = {
     "rsm_world_to_map": (c_i, [c_p, c_p, c_p]),
     "rsm_map_to_world": (c_i, [c_p, c_p, c_p]),
     "rsm_match": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_match_map": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), c_p, ctypes.POINTER(PassDetail)]),
     "rsm_scan_create": (c_i, [c_p, c_p, c_i, ctypes.POINTER(c_p)]),
     "rsm_scan_destroy": (None, [c_p, c_p]),
     "rsm_match_resident": (c_i, [c_p, c_p, c_p, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),

@@ -1,0 +1,71 @@
+"""GPU test of the drop-in boundary: the C++ adapter class (scan_matcher_adapter.hpp) is handed
+the reference's own live ScanMatchMap / RangeDataContainer2d / CorrelationScanMatchParam objects
+and must return what the reference's BasedCorrelationScanMatch returns for them.  Runs only where
+oracle/_ref was built (the build container had /root/reference; the built files travel)."""
+import numpy as np
+import pytest
+
+from helpers import cov_close, load_golden
+from roborts_edu_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    from oracle.oracle_py import DropIn, dropin_available, ref_available
+    if not (dropin_available() and ref_available()):
+        pytest.skip("oracle/_ref not built")
+    d = DropIn(0)
+    yield d
+    d.close()
+
+
+def _check(ref, dropin, sc, chain):
+    m = ref.create_map(sc.grid)
+    try:
+        ref.build_map(m, sc.grid, sc.base_pts, sc.base_poses)
+        for p in sc.passes:
+            want = ref.match(m, sc.scan_pts, p, sc.seed_pose)
+            got = dropin.match_chain(m, sc.scan_pts, [p], sc.seed_pose)
+            assert got["score"] == want["response"]
+            assert np.array_equal(got["pose"], want["pose"])
+            assert cov_close(got["cov"], want["cov"])
+        if chain:
+            want = ref.match_chain(m, sc.scan_pts, sc.passes, sc.seed_pose)
+            got = dropin.match_chain(m, sc.scan_pts, sc.passes, sc.seed_pose)
+            assert got["score"] == want["score"]
+            assert np.array_equal(got["pose"], want["pose"])
+            assert cov_close(got["cov"], want["cov"])
+            assert np.array_equal(got["responses"], want["responses"])
+    finally:
+        ref.destroy_map(m)
+
+
+def test_adapter_on_live_reference_objects(ref, dropin):
+    _check(ref, dropin, synth.config1(), False)
+    _check(ref, dropin, synth.config3(True), True)
+    for sc in synth.config4(3, seed=7):
+        _check(ref, dropin, sc, True)
+    sc, _ = load_golden("ties_icra")
+    _check(ref, dropin, sc, True)
+
+
+def test_adapter_follows_map_updates(ref, dropin):
+    """The adapter re-uploads the grid when the live map changes (map_update_index)."""
+    a, b = synth.config4(2, seed=11)
+    m = ref.create_map(a.grid)
+    try:
+        ref.build_map(m, a.grid, a.base_pts, a.base_poses)
+        w1 = ref.match(m, a.scan_pts, a.passes[0], a.seed_pose)
+        g1 = dropin.match_chain(m, a.scan_pts, [a.passes[0]], a.seed_pose)
+        assert g1["score"] == w1["response"] and np.array_equal(g1["pose"], w1["pose"])
+        # same map object, new contents and offset (what ResetScanMatchMapWithRangeVec does)
+        ref.L.ref_map_set_offset(m, b.grid.off_x, b.grid.off_y)
+        ref.build_map(m, b.grid, b.base_pts, b.base_poses)
+        w2 = ref.match(m, b.scan_pts, b.passes[0], b.seed_pose)
+        g2 = dropin.match_chain(m, b.scan_pts, [b.passes[0]], b.seed_pose)
+        assert g2["score"] == w2["response"] and np.array_equal(g2["pose"], w2["pose"])
+        assert cov_close(g2["cov"], w2["cov"])
+    finally:
+        ref.destroy_map(m)

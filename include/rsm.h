@@ -206,17 +206,33 @@ int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, in
                     const rsm_pass_param* param, const double pose_world[3], int angle_begin,
                     int angle_end, double* scores_out, int64_t capacity, int64_t* n_written);
 
-/* Angle-sliced single window: each rank scores angle indices
- * [angle_begin, angle_end) and returns a compact partial (its local maximum, its candidates near
- * the top and its local top lists) in `partial` (RSM_PARTIAL_BYTES bytes).  After exchanging the
- * partials (all-gather), rsm_match_finish merges them and finalises exactly like rsm_match. */
-#define RSM_PARTIAL_BYTES (1 << 20)
+/* Angle-sliced single window: one large search window cut along the angle index
+ * over several GPUs (one context per GPU / rank).  The reference's winner is a tolerance-set
+ * average plus two top-20 prefixes, not a single argmax, so the exchange is three calls around
+ * two small all-gathers (e.g. torch.distributed.all_gather over NCCL):
+ *
+ *   rsm_match_partial   every rank scores angle indices [angle_begin, angle_end) and packs its
+ *                       local maximum, its candidates within 1e-2 of it and its local top-21 into
+ *                       `partial` (RSM_PARTIAL_BYTES); the slice's scores stay on the device.
+ *        -- all-gather the partials --
+ *   rsm_match_merge     every rank merges all partials (global maximum, averaging set, best
+ *                       pose, global top-21) and writes its slice's scores of the same-(x,y)
+ *                       columns into `columns` (RSM_COLUMNS_BYTES).
+ *        -- all-gather the columns --
+ *   rsm_match_finish    every rank finalises exactly like rsm_match: pose_world / cov in/out,
+ *                       response, detail.  All ranks obtain identical results.
+ *
+ * If the consumed sets contain exact ties (whose order the reference's unstable sort decides),
+ * rsm_match_finish returns RSM_ERR_UNSUPPORTED: rerun unsliced with rsm_match. */
+#define RSM_PARTIAL_BYTES 65536
+#define RSM_COLUMNS_BYTES 131072
 int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
                       const rsm_pass_param* param, const double pose_world[3], int angle_begin,
                       int angle_end, void* partial);
-int rsm_match_finish(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
-                     const rsm_pass_param* param, const void* const* partials, int n_partials,
-                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail);
+int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, void* columns);
+int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials,
+                     const void* const* columns, double pose_world[3], double cov[9],
+                     double* response, rsm_pass_detail* detail /* nullable */);
 
 /* ---- measurement support ------------------------------------------------------------------
  * Gather-bandwidth micro-benchmark used as the roofline denominator of the scoring kernel:

@@ -157,9 +157,24 @@ class HostPool {
 };
 }  // namespace
 
+struct SliceState {   // what rsm_match_partial leaves behind for merge / finish
+  bool valid = false, merged = false, exact_needed = false;
+  rsm_pass_param param;
+  PassGeo geo;
+  const rsm_grid* grid = nullptr;
+  int a0 = 0, a1 = 0;
+  double* d_score = nullptr;     // slice scores, resident in the work arena
+  char* d_gjob = nullptr; double* d_gout = nullptr;
+  BestPose best;
+  std::vector<Cand> top;
+  int n_cols = 0;
+  int cols[kMaxCols];
+};
+
 struct rsm_ctx {
   int device = 0;
   HostPool pool;
+  SliceState slice;
   cudaStream_t stream = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::string err;
@@ -332,7 +347,17 @@ struct PassItem {
   size_t gather_off = 0;
 };
 
-enum PassMode { MODE_MATCH = 0, MODE_SCORES = 1 };
+enum PassMode { MODE_MATCH = 0, MODE_SCORES = 1, MODE_PARTIAL = 2 };
+
+constexpr uint32_t kPartialMagic = 0x52534d50u;   // 'RSMP'
+struct PartialHeader {
+  uint32_t magic; int32_t a0, a1, n_ang, n_xy, n_pool, n_top, flags;
+  unsigned long long best_key;
+  double reserved[3];
+};
+static_assert(sizeof(PartialHeader) == 64, "PartialHeader layout");
+struct ColumnsHeader { uint32_t magic; int32_t a0, a1, n_cols; int32_t cols[kMaxCols]; int32_t pad[3]; };
+static_assert(sizeof(ColumnsHeader) == 64, "ColumnsHeader layout");
 
 struct PassScratch {   // device pointers valid until the next pass
   double* d_score = nullptr;
@@ -591,6 +616,38 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   }
 
   pt.lap(1);
+  if (mode == MODE_PARTIAL) {
+    // pack item 0's local result; the slice's scores stay where they are (ctx->slice)
+    PassItem& it = items[act[0]];
+    if (h_err[0] & kErrWindow) return fail(ctx, RSM_ERR_WINDOW, "search window + scan extent leaves the grid");
+    const int64_t base = int64_t(it.a0) * it.geo.n_xy * it.geo.n_xy;
+    PartialHeader H;
+    std::memset(&H, 0, sizeof H);
+    H.magic = kPartialMagic; H.a0 = it.a0; H.a1 = it.a1; H.n_ang = it.geo.n_ang; H.n_xy = it.geo.n_xy;
+    H.best_key = h_best[0];
+    const int cap = int((RSM_PARTIAL_BYTES - sizeof(PartialHeader)) / sizeof(Cand)) - kTopK;
+    if ((h_err[0] & (kErrPoolFull | kErrSelectFull)) || pool_overflow || pool_count > cap) H.flags |= 1;
+    Cand* out = reinterpret_cast<Cand*>(reinterpret_cast<char*>(scores_out) + sizeof(PartialHeader));
+    if (!(H.flags & 1)) {
+      for (int e = 0; e < pool_count; ++e) out[H.n_pool++] = Cand{h_pool[e].score, base + h_pool[e].index};
+    }
+    std::vector<Cand> top;
+    for (int c = 0; c < it.sel_ncta; ++c) {
+      const int cnt = h_topcnt[it.sel_cta0 + c];
+      const Entry* e = h_top + size_t(it.sel_cta0 + c) * kTopK;
+      for (int r = 0; r < cnt; ++r) top.push_back(Cand{e[r].score, base + e[r].index});
+    }
+    if (top.size() > size_t(kTopK)) { std::nth_element(top.begin(), top.begin() + kTopK, top.end(), by_score_desc); top.resize(kTopK); }
+    std::sort(top.begin(), top.end(), by_score_desc);
+    for (const Cand& c : top) out[H.n_pool + H.n_top++] = c;
+    std::memcpy(scores_out, &H, sizeof H);
+    SliceState& S = ctx->slice;
+    S.valid = true; S.merged = false; S.exact_needed = false;
+    S.param = it.param; S.geo = it.geo; S.grid = it.grid; S.a0 = it.a0; S.a1 = it.a1;
+    S.d_score = reinterpret_cast<double*>(dw + o_score) + it.score_off;
+    S.d_gjob = dw + o_gjobs; S.d_gout = reinterpret_cast<double*>(dw + o_gout) + it.gather_off;
+    return RSM_OK;
+  }
   // ---- stage 1: best pose, positional covariance ---------------------------------------------
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];
@@ -1318,12 +1375,173 @@ int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, in
   return run_pass(ctx, items, MODE_SCORES, scores_out, capacity, n_written);
 }
 
-int rsm_match_partial(rsm_ctx* ctx, const rsm_grid*, const double*, int, const rsm_pass_param*, const double*, int, int, void*) {
-  return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_match_partial: not built yet");
+int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
+                      const double pose_world[3], int angle_begin, int angle_end, void* partial) {
+  if (!ctx || !grid || !param || !pose_world || !partial || n_pts <= 0 || !pts_xy)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_partial: bad arguments");
+  if (!grid->init) return fail(ctx, RSM_ERR_NOT_INIT, "grid has no content");
+  ctx->slice.valid = false;
+  std::memset(partial, 0, sizeof(PartialHeader));
+  double* d_pts = nullptr;
+  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
+  if (rc) return rc;
+  double pose[3] = {pose_world[0], pose_world[1], pose_world[2]};
+  double cov[9];
+  std::vector<PassItem> items(1);
+  items[0].grid = grid; items[0].d_pts = d_pts; items[0].P = n_pts; items[0].param = *param;
+  items[0].pose_world = pose; items[0].cov = cov;
+  items[0].ang_begin = angle_begin; items[0].ang_end = angle_end;
+  rc = run_pass(ctx, items, MODE_PARTIAL, reinterpret_cast<double*>(partial), 0, nullptr);
+  if (rc) return rc;
+  if (!ctx->slice.valid) {   // empty slice: still hand over a well-formed (empty) partial
+    PartialHeader H;
+    std::memset(&H, 0, sizeof H);
+    H.magic = kPartialMagic; H.a0 = H.a1 = std::max(0, angle_begin);
+    std::memcpy(partial, &H, sizeof H);
+    double center[3];
+    grid->tf.world_to_map(pose_world, center);
+    SliceState& S = ctx->slice;
+    S.valid = true; S.merged = false; S.exact_needed = false; S.param = *param; S.grid = grid;
+    S.geo = make_geo(*param, n_pts, grid->cell_len(), center);
+    S.a0 = S.a1 = H.a0; S.d_score = nullptr; S.d_gjob = nullptr; S.d_gout = nullptr;
+  }
+  return RSM_OK;
 }
-int rsm_match_finish(rsm_ctx* ctx, const rsm_grid*, const double*, int, const rsm_pass_param*, const void* const*, int,
-                     double*, double*, double*, rsm_pass_detail*) {
-  return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_match_finish: not built yet");
+
+int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, void* columns) {
+  if (!ctx || !partials || n_partials < 1 || !columns) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: bad arguments");
+  SliceState& S = ctx->slice;
+  if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: no rsm_match_partial pending on this context");
+  const PassGeo& g = S.geo;
+  unsigned long long best_key = 0ull;
+  bool exact = false;
+  for (int r = 0; r < n_partials; ++r) {
+    PartialHeader H;
+    std::memcpy(&H, partials[r], sizeof H);
+    if (H.magic != kPartialMagic) return fail(ctx, RSM_ERR_INVALID, "partial %d is not an rsm partial", r);
+    if (H.a1 > H.a0 && (H.n_ang != g.n_ang || H.n_xy != g.n_xy)) return fail(ctx, RSM_ERR_INVALID, "partial %d comes from another window", r);
+    if (H.flags & 1) exact = true;
+    best_key = std::max(best_key, H.best_key);
+  }
+  const double top_score = key_to_score(best_key);
+  std::vector<Cand> a_list;
+  S.top.clear();
+  for (int r = 0; r < n_partials && !exact; ++r) {
+    PartialHeader H;
+    std::memcpy(&H, partials[r], sizeof H);
+    const Cand* e = reinterpret_cast<const Cand*>(static_cast<const char*>(partials[r]) + sizeof(PartialHeader));
+    for (int i = 0; i < H.n_pool; ++i)
+      if (DoubleEqual(e[i].score, top_score, kResponseFilterTolerance)) a_list.push_back(e[i]);
+    for (int i = 0; i < H.n_top; ++i) S.top.push_back(e[H.n_pool + i]);
+  }
+  S.n_cols = 0;
+  if (!exact) {
+    std::sort(a_list.begin(), a_list.end(), by_score_desc);
+    if (a_list.empty() || a_list[0].score != top_score || adjacent_tie(a_list, a_list.size())) exact = true;
+  }
+  if (!exact) {
+    S.best = find_best(g, a_list.data(), a_list.size());
+    if (S.top.size() > size_t(kTopK)) { std::nth_element(S.top.begin(), S.top.begin() + kTopK, S.top.end(), by_score_desc); S.top.resize(kTopK); }
+    std::sort(S.top.begin(), S.top.end(), by_score_desc);
+    const int type = S.param.type;
+    if ((type == RSM_COARSE || type == RSM_SUPER) && !(S.best.score < kDoubleTolerance)) {
+      int xs[8], ys[8], nx = 0, ny = 0;
+      const double tol = g.factor;
+      for (int ix = 0; ix < g.n_xy && nx < 8; ++ix) if (DoubleEqual(g.x_of(ix), S.best.x, tol)) xs[nx++] = ix;
+      for (int iy = 0; iy < g.n_xy && ny < 8; ++iy) if (DoubleEqual(g.y_of(iy), S.best.y, tol)) ys[ny++] = iy;
+      if (nx * ny > kMaxCols) exact = true;
+      else for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) S.cols[S.n_cols++] = xs[i] * g.n_xy + ys[j];
+    }
+  }
+  S.exact_needed = exact;
+  S.merged = true;
+  // this rank's column scores
+  ColumnsHeader CH;
+  std::memset(&CH, 0, sizeof CH);
+  CH.magic = kPartialMagic; CH.a0 = S.a0; CH.a1 = S.a1; CH.n_cols = exact ? 0 : S.n_cols;
+  for (int c = 0; c < CH.n_cols; ++c) CH.cols[c] = S.cols[c];
+  const int nang = S.a1 - S.a0;
+  const size_t need = sizeof(ColumnsHeader) + size_t(CH.n_cols) * nang * 8;
+  if (need > RSM_COLUMNS_BYTES) return fail(ctx, RSM_ERR_UNSUPPORTED, "angle slice too long for RSM_COLUMNS_BYTES (%d angles)", nang);
+  std::memcpy(columns, &CH, sizeof CH);
+  if (CH.n_cols > 0 && nang > 0) {
+    GatherJob G;
+    std::memset(&G, 0, sizeof G);
+    G.score = S.d_score; G.out = S.d_gout; G.n_xy = g.n_xy; G.n_ang = nang; G.n_cols = CH.n_cols;
+    for (int c = 0; c < CH.n_cols; ++c) G.cols[c] = CH.cols[c];
+    int rc = ensure_pinned(ctx, ctx->h_up, sizeof G);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, ctx->h_down, size_t(CH.n_cols) * nang * 8);
+    if (rc) return rc;
+    std::memcpy(ctx->h_up.p, &G, sizeof G);
+    CU(cudaMemcpyAsync(S.d_gjob, ctx->h_up.p, sizeof G, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_gather(1, ctx->stream, reinterpret_cast<const GatherJob*>(S.d_gjob)));
+    ctx->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_down.p, S.d_gout, size_t(CH.n_cols) * nang * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    std::memcpy(static_cast<char*>(columns) + sizeof(ColumnsHeader), ctx->h_down.p, size_t(CH.n_cols) * nang * 8);
+  }
+  return RSM_OK;
+}
+
+int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, const void* const* columns,
+                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  if (!ctx || !partials || !columns || n_partials < 1 || !pose_world || !cov || !response)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: bad arguments");
+  SliceState& S = ctx->slice;
+  if (!S.valid || !S.merged) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: call rsm_match_partial and rsm_match_merge first");
+  S.valid = false;
+  *response = 0.0;
+  if (detail) std::memset(detail, 0, sizeof *detail);
+  if (S.exact_needed)
+    return fail(ctx, RSM_ERR_UNSUPPORTED, "exact score ties in the consumed candidate sets: rerun this match unsliced (rsm_match)");
+  const PassGeo& g = S.geo;
+  const int type = S.param.type;
+  const double bound = cov_score_bound(S.best);
+  if (type == RSM_COARSE || type == RSM_FINE) {
+    if (S.top.size() == size_t(kTopK) && S.top[kTopK - 1].score > bound && S.top[kTopK - 1].score == S.top[kTopK - 2].score)
+      return fail(ctx, RSM_ERR_UNSUPPORTED, "exact score tie at the covariance cut: rerun this match unsliced (rsm_match)");
+    positional_cov(g, S.param, S.best, S.top.data(), S.top.size(), cov);
+  }
+  if (type == RSM_COARSE || type == RSM_SUPER) {
+    std::vector<Cand> xy;
+    if (!(S.best.score < kDoubleTolerance)) {
+      for (int r = 0; r < n_partials; ++r) {
+        ColumnsHeader CH;
+        std::memcpy(&CH, columns[r], sizeof CH);
+        if (CH.magic != kPartialMagic) return fail(ctx, RSM_ERR_INVALID, "columns %d is not an rsm column block", r);
+        const double* col = reinterpret_cast<const double*>(static_cast<const char*>(columns[r]) + sizeof(ColumnsHeader));
+        const int nang = CH.a1 - CH.a0;
+        for (int c = 0; c < CH.n_cols; ++c)
+          for (int ia = 0; ia < nang; ++ia) {
+            const double s = col[size_t(c) * nang + ia];
+            if (s >= bound) xy.push_back(Cand{s, int64_t(CH.a0 + ia) * g.n_xy * g.n_xy + CH.cols[c]});
+          }
+      }
+      if (xy.size() > size_t(kTopK)) { std::nth_element(xy.begin(), xy.begin() + kTopK, xy.end(), by_score_desc); xy.resize(kTopK); }
+      std::sort(xy.begin(), xy.end(), by_score_desc);
+      if (xy.size() > size_t(kMaxVarianceUsePointSize) && xy[kMaxVarianceUsePointSize].score == xy[kMaxVarianceUsePointSize - 1].score)
+        return fail(ctx, RSM_ERR_UNSUPPORTED, "exact score tie at the angular covariance cut: rerun this match unsliced (rsm_match)");
+    }
+    angular_cov(g, S.param, S.best, xy.data(), xy.size(), cov);
+  }
+  const double bs = S.best.score;
+  *response = bs > 1.0 ? 1.0 : bs;
+  rsm_pass_detail d;
+  std::memset(&d, 0, sizeof d);
+  d.best_score = bs;
+  d.best_pose_map[0] = S.best.x; d.best_pose_map[1] = S.best.y; d.best_pose_map[2] = S.best.angle;
+  d.n_candidates = g.n_cand(); d.n_avg = S.best.n_avg;
+  d.n_ang = g.n_ang; d.n_xy = g.n_xy; d.visited = g.visited; d.divisor = g.divisor;
+  if (*response > S.param.response_threshold) {
+    const double b[3] = {S.best.x, S.best.y, S.best.angle};
+    S.grid->tf.map_to_world(b, pose_world);
+    d.pose_updated = 1;
+  }
+  if (detail) *detail = d;
+  ctx->stats.passes++;
+  return RSM_OK;
 }
 
 }  // extern "C"

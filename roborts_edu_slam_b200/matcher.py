@@ -101,7 +101,8 @@ ABI = {
                                      _PPARAM, c_i, c_p, c_p, c_p, c_p]),
     "rsm_pass_scores": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p, c_i64, ctypes.POINTER(c_i64)]),
     "rsm_match_partial": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p]),
-    "rsm_match_finish": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_match_merge": (c_i, [c_p, c_p, c_i, c_p]),
+    "rsm_match_finish": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
 }
 
 _lib = None
@@ -357,6 +358,46 @@ class BasedCorrelationScanMatch:
         ctx.check(ctx.lib.rsm_pass_scores(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps), pose.ctypes.data,
                                           int(angle_begin), int(angle_end), out.ctypes.data, cap, ctypes.byref(w)))
         return out[: w.value]
+
+
+RSM_PARTIAL_BYTES = 65536
+RSM_COLUMNS_BYTES = 131072
+
+
+class SlicedScanMatch:
+    """One large search window cut along the angle index over several GPUs.
+
+    Every rank owns a Context and a copy of the grid.  `all_gather(buf)` must return the list of
+    every rank's uint8 buffer in rank order (torch.distributed.all_gather over NCCL in bench.py,
+    a plain list in the single-process tests).  All ranks return identical results."""
+
+    def __init__(self, ctx, rank, world_size, all_gather):
+        self.ctx, self.rank, self.world, self.all_gather = ctx, rank, world_size, all_gather
+        self.last_detail = None
+
+    def ScanMatch(self, map_, range_data, scan_match_param, current_pose, cov_matrix):
+        from .sharding import contiguous_range
+        ctx = self.ctx
+        pts = _f64(range_data).reshape(-1, 2)
+        ps = _as_param(scan_match_param).struct()
+        n_ang = int(np.floor(ps.search_angle_offset * 2 / ps.search_angle_resolution) + 1)
+        a0, a1 = contiguous_range(n_ang, self.rank, self.world)
+        partial = np.zeros(RSM_PARTIAL_BYTES, dtype=np.uint8)
+        pose = _f64(current_pose)
+        ctx.check(ctx.lib.rsm_match_partial(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps),
+                                            pose.ctypes.data, a0, a1, partial.ctypes.data))
+        partials = [np.ascontiguousarray(p, dtype=np.uint8) for p in self.all_gather(partial)]
+        pp = (c_p * len(partials))(*[p.ctypes.data for p in partials])
+        columns = np.zeros(RSM_COLUMNS_BYTES, dtype=np.uint8)
+        ctx.check(ctx.lib.rsm_match_merge(ctx.h, pp, len(partials), columns.ctypes.data))
+        cols = [np.ascontiguousarray(c, dtype=np.uint8) for c in self.all_gather(columns)]
+        cp = (c_p * len(cols))(*[c.ctypes.data for c in cols])
+        resp = c_d(0)
+        det = PassDetail()
+        ctx.check(ctx.lib.rsm_match_finish(ctx.h, pp, len(partials), cp, current_pose.ctypes.data,
+                                           cov_matrix.ctypes.data, ctypes.byref(resp), ctypes.byref(det)))
+        self.last_detail = det
+        return resp.value
 
 
 class ScanMatchers:

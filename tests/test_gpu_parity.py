@@ -289,3 +289,83 @@ def test_size_independent_properties_wide_window(ctx):
     assert np.array_equal(m.scores(dg, sc.scan_pts, p, sc.seed_pose, 5, 9), full[5 * n_xy * n_xy: 9 * n_xy * n_xy])
     dg.close()
     df.close()
+
+
+def test_angle_sliced_match_equals_unsliced(oracle):
+    """one window cut along the angle index over N ranks, merged through the partial /
+    merge / finish calls, must equal the unsliced match (and hence the reference).  The ranks are
+    emulated by N contexts on this GPU, run in lock step; the all-gather is a list."""
+    import threading
+    from roborts_edu_slam_b200.sharding import contiguous_range
+
+    def run_sliced(sc, p, pose_in, world):
+        ctxs = [matcher.Context(0) for _ in range(world)]
+        grids = []
+        for c in ctxs:
+            dg = matcher.ScanMatchMap.from_spec(c, sc.grid)
+            dg.InitMapWithRangeVec(sc.base_pts, sc.base_poses, sc.grid.default_prob, sc.grid.sigma, sc.grid.occu_offset)
+            grids.append(dg)
+        # a barrier-style all-gather between threads
+        slots, barrier, out = [None] * world, threading.Barrier(world), [None] * world
+
+        def make_gather(rank):
+            def gather(buf):
+                slots[rank] = buf.copy()
+                barrier.wait()
+                res = [b.copy() for b in slots]
+                barrier.wait()
+                return res
+            return gather
+
+        def worker(rank):
+            sm = matcher.SlicedScanMatch(ctxs[rank], rank, world, make_gather(rank))
+            pose, cov = pose_in.copy(), np.eye(3)
+            try:
+                r = sm.ScanMatch(grids[rank], sc.scan_pts, p, pose, cov)
+                out[rank] = (r, pose, cov, sm.last_detail.n_avg)
+            except matcher.RsmError as e:   # exact ties: the sliced path declines, by contract
+                assert e.status == 5
+                out[rank] = "ties"
+
+        ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for dg in grids:
+            dg.close()
+        for c in ctxs:
+            c.close()
+        return out
+
+    cases = [(synth.config1(), 3), (synth.config3(True), 2), (synth.config4(1, seed=5)[0], 4)]
+    for sc, world in cases:
+        grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        pose_in = sc.seed_pose.copy()
+        for p in sc.passes:
+            want = oracle.match(grid, sc.grid, sc.scan_pts, p, pose_in)
+            res = run_sliced(sc, p, pose_in, world)
+            assert all(r is not None for r in res)
+            if any(isinstance(r, str) for r in res):
+                # every rank must decline together, and the unsliced match must report the exact path
+                assert all(r == "ties" for r in res)
+                c0 = matcher.Context(0)
+                dg = device_grid(c0, sc)
+                m0 = matcher.BasedCorrelationScanMatch(c0)
+                pose, cov = pose_in.copy(), np.eye(3)
+                assert_pass_equal(m0.ScanMatch(dg, sc.scan_pts, p, pose, cov), pose, cov, want)
+                assert m0.last_detail.exact_sort_used == 1
+                dg.close()
+                c0.close()
+            else:
+                for r, pose, cov, navg in res:     # every rank holds the same, reference-identical result
+                    assert r == want["response"] and np.array_equal(pose, want["pose"]) and cov_close(cov, want["cov"])
+                    assert navg == want["n_avg"]
+            pose_in = want["pose"]
+    # more ranks than angles: empty slices are fine
+    sc = synth.config1()
+    p = synth.pass_param(0.2, 0.05, 0.03, 0.0349, 0.3, 100000, True, 0)   # n_ang = 2
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
+    for r, pose, cov, navg in run_sliced(sc, p, sc.seed_pose, 4):
+        assert r == want["response"] and np.array_equal(pose, want["pose"]) and cov_close(cov, want["cov"])

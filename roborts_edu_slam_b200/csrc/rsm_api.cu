@@ -337,7 +337,7 @@ struct PassItem {
   PassGeo geo;
   int a0 = 0, a1 = 0;              // resolved slice
   int64_t n_local = 0;             // candidates scored here
-  size_t score_off = 0, trig_off = 0;
+  size_t score_off = 0, trig_off = 0, spec_off = 0;
   int sel_cta0 = 0, sel_ncta = 0;
   bool exact = false;
   BestPose best;
@@ -462,6 +462,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   const size_t o_best = dl.take(size_t(na) * 8);
   const size_t o_err = dl.take(size_t(na) * 4, 4);
   const size_t o_poolcnt = dl.take(4, 4);
+  const size_t o_done = dl.take(size_t(na) * 4, 4);
   const size_t zero_end = dl.off;
   int total_sel_cta = 0;
   int64_t total_cand = 0;
@@ -473,11 +474,21 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     total_sel_cta += ncta;
     total_cand += it.n_local;
   }
-  const size_t o_topcnt = dl.take(size_t(total_sel_cta) * 4, 4);
-  const size_t o_top = dl.take(size_t(total_sel_cta) * kTopK * sizeof(Entry), 16);
+  const size_t o_fcnt = dl.take(size_t(na) * 4, 4);
+  const size_t o_speccols = dl.take(size_t(na) * (kMaxCols + 1) * 4, 4);
+  const size_t o_ftop = dl.take(size_t(na) * kTopK * sizeof(Entry), 16);
+  size_t spec_doubles = 0;
+  for (int a = 0; a < na; ++a) {
+    PassItem& it = items[act[a]];
+    it.spec_off = spec_doubles;
+    if (it.param.type == RSM_COARSE || it.param.type == RSM_SUPER) spec_doubles += size_t(kMaxCols) * (it.a1 - it.a0);
+  }
+  const size_t o_spec = dl.take(spec_doubles * 8, 16);
   const int pool_cap = int(std::min<int64_t>(std::max<int64_t>(int64_t(na) * 64, 65536), total_cand));
   const size_t o_pool = dl.take(size_t(pool_cap) * sizeof(PoolEntry), 16);
   const size_t down_end = dl.off;          // [o_best, down_end) is what the host reads back
+  const size_t o_topcnt = dl.take(size_t(total_sel_cta) * 4, 4);   // per-CTA lists stay on the device
+  const size_t o_top = dl.take(size_t(total_sel_cta) * kTopK * sizeof(Entry), 16);
   const size_t o_gjobs = dl.take(sizeof(GatherJob) * na);
   size_t gather_doubles = 0;
   for (int a = 0; a < na; ++a) { items[act[a]].gather_off = gather_doubles; gather_doubles += size_t(kMaxCols) * items[act[a]].geo.n_ang; }
@@ -544,6 +555,13 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     L.score = J.score; L.n = it.n_local; L.best_key = J.best_key;
     L.top_list = reinterpret_cast<Entry*>(dw + o_top) + size_t(it.sel_cta0) * kTopK;
     L.top_count = reinterpret_cast<int*>(dw + o_topcnt) + it.sel_cta0;
+    L.final_top = reinterpret_cast<Entry*>(dw + o_ftop) + size_t(a) * kTopK;
+    L.final_count = reinterpret_cast<int*>(dw + o_fcnt) + a;
+    const bool wants_angular = it.param.type == RSM_COARSE || it.param.type == RSM_SUPER;
+    L.spec_cols = reinterpret_cast<int*>(dw + o_speccols) + size_t(a) * (kMaxCols + 1);
+    L.spec_out = wants_angular ? reinterpret_cast<double*>(dw + o_spec) + it.spec_off : nullptr;
+    L.done = reinterpret_cast<int*>(dw + o_done) + a;
+    L.n_xy = g.n_xy; L.n_ang = it.a1 - it.a0;
     L.err = J.err; L.job_id = a; L.n_cta = it.sel_ncta;
     L.slice = (it.n_local + it.sel_ncta - 1) / it.sel_ncta;
     l_cta[a] = it.sel_cta0;
@@ -601,8 +619,10 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   const unsigned long long* h_best = reinterpret_cast<const unsigned long long*>(dn);
   const int* h_err = reinterpret_cast<const int*>(dn + (o_err - o_best));
   int pool_count = *reinterpret_cast<const int*>(dn + (o_poolcnt - o_best));
-  const int* h_topcnt = reinterpret_cast<const int*>(dn + (o_topcnt - o_best));
-  const Entry* h_top = reinterpret_cast<const Entry*>(dn + (o_top - o_best));
+  const int* h_fcnt = reinterpret_cast<const int*>(dn + (o_fcnt - o_best));
+  const Entry* h_ftop = reinterpret_cast<const Entry*>(dn + (o_ftop - o_best));
+  const int* h_speccols = reinterpret_cast<const int*>(dn + (o_speccols - o_best));
+  const double* h_spec = reinterpret_cast<const double*>(dn + (o_spec - o_best));
   const PoolEntry* h_pool = reinterpret_cast<const PoolEntry*>(dn + (o_pool - o_best));
   bool pool_overflow = pool_count > pool_cap;
   if (pool_overflow) pool_count = pool_cap;
@@ -631,15 +651,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (!(H.flags & 1)) {
       for (int e = 0; e < pool_count; ++e) out[H.n_pool++] = Cand{h_pool[e].score, base + h_pool[e].index};
     }
-    std::vector<Cand> top;
-    for (int c = 0; c < it.sel_ncta; ++c) {
-      const int cnt = h_topcnt[it.sel_cta0 + c];
-      const Entry* e = h_top + size_t(it.sel_cta0 + c) * kTopK;
-      for (int r = 0; r < cnt; ++r) top.push_back(Cand{e[r].score, base + e[r].index});
-    }
-    if (top.size() > size_t(kTopK)) { std::nth_element(top.begin(), top.begin() + kTopK, top.end(), by_score_desc); top.resize(kTopK); }
-    std::sort(top.begin(), top.end(), by_score_desc);
-    for (const Cand& c : top) out[H.n_pool + H.n_top++] = c;
+    for (int r = 0; r < h_fcnt[0]; ++r) out[H.n_pool + H.n_top++] = Cand{h_ftop[r].score, base + h_ftop[r].index};
     std::memcpy(scores_out, &H, sizeof H);
     SliceState& S = ctx->slice;
     S.valid = true; S.merged = false; S.exact_needed = false;
@@ -673,18 +685,10 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       it.best = find_best(g, it.a_list.data(), it.a_list.size());
       if (size_t(it.best.n_avg) != it.a_list.size()) { it.exact = true; continue; }   // cannot happen; be safe
       const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
-      for (int c = 0; c < it.sel_ncta; ++c) {
-        const int cnt = h_topcnt[it.sel_cta0 + c];
-        const Entry* e = h_top + size_t(it.sel_cta0 + c) * kTopK;
-        for (int r = 0; r < cnt; ++r) it.top.push_back(Cand{e[r].score, base + e[r].index});
-      }
-      // only the kTopK best of the merged per-CTA lists matter; their VALUES are unique whatever
+      // the job's top-kTopK as merged on the device (descending); their VALUES are unique whatever
       // the order of equal scores, and equal scores at the cut are detected below
-      if (it.top.size() > size_t(kTopK)) {
-        std::nth_element(it.top.begin(), it.top.begin() + kTopK, it.top.end(), by_score_desc);
-        it.top.resize(kTopK);
-      }
-      std::sort(it.top.begin(), it.top.end(), by_score_desc);
+      const Entry* ft = h_ftop + size_t(a) * kTopK;
+      for (int r = 0; r < h_fcnt[a]; ++r) it.top.push_back(Cand{ft[r].score, base + ft[r].index});
       const int type = it.param.type;
       const double bound = cov_score_bound(it.best);
       if (type == RSM_COARSE || type == RSM_FINE) {
@@ -704,7 +708,36 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
           if (nx * ny > kMaxCols) { it.exact = true; continue; }
           it.n_cols = 0;
           for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) it.cols[it.n_cols++] = xs[i] * g.n_xy + ys[j];
-          if (it.n_cols == 0) angular_cov(g, it.param, it.best, nullptr, 0, it.cov);
+          if (it.n_cols == 0) { angular_cov(g, it.param, it.best, nullptr, 0, it.cov); continue; }
+          // the device already gathered the 3x3 neighbourhood of the top candidate: use it when it
+          // covers every same-(x,y) column, else leave n_cols set for the gather round trip
+          const int* sc_cols = h_speccols + size_t(a) * (kMaxCols + 1);
+          const int nspec = sc_cols[0];
+          const int nang = it.a1 - it.a0;
+          int where[kMaxCols];
+          bool covered = nspec > 0;
+          for (int c = 0; c < it.n_cols && covered; ++c) {
+            where[c] = -1;
+            for (int q = 0; q < nspec; ++q) if (sc_cols[1 + q] == it.cols[c]) where[c] = q;
+            if (where[c] < 0) covered = false;
+          }
+          if (!covered) continue;
+          const double* vals = h_spec + it.spec_off;
+          it.xy.clear();
+          for (int c = 0; c < it.n_cols; ++c)
+            for (int ia = 0; ia < nang; ++ia) {
+              const double s = vals[size_t(where[c]) * nang + ia];
+              if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
+            }
+          it.n_cols = 0;   // no round trip needed
+          if (it.xy.size() > size_t(kTopK)) {
+            std::nth_element(it.xy.begin(), it.xy.begin() + kTopK, it.xy.end(), by_score_desc);
+            it.xy.resize(kTopK);
+          }
+          std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
+          if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
+              it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) { it.exact = true; continue; }
+          angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
         }
       }
     }

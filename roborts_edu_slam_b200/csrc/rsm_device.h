@@ -63,12 +63,17 @@ struct PoolEntry {
 
 struct SelectJob {
   const double* score;
-  long long n;                          // candidates in this job
+  long long n;                          // candidates in this job (angle slice x n_xy^2)
   const unsigned long long* best_key;   // written by the scoring kernel
   Entry* top_list; int* top_count;      // per-CTA top-kTopK lists: top_list[cta*kTopK + r], top_count[cta]
+  Entry* final_top; int* final_count;   // merged by the job's last CTA: the job's top-kTopK, descending
+  int* spec_cols;                       // [0] = number of speculative columns, [1..9] = ix*n_xy+iy
+  double* spec_out;                     // spec_out[c * n_ang + ia]  (nullptr: no speculative gather)
+  int* done;                            // arrival counter of the job's CTAs (zeroed before launch)
   int* err;
   int job_id;
   int n_cta;                            // CTAs working on this job
+  int n_xy, n_ang;                      // window width and number of (local) angles
   long long slice;                      // candidates per CTA
 };
 

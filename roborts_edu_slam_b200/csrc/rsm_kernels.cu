@@ -66,76 +66,33 @@ __device__ __forceinline__ int find_job(const int* __restrict__ cta_begin, int n
 // =================================================================================================
 // selection
 // =================================================================================================
-// Block-wide "pop the maximum" over one (key, tag) pair per thread.  Returns the winning key and
-// tag to every thread; among equal keys the smallest tag wins.  tag must be unique per live item.
-struct KeyTag { unsigned long long key; unsigned int tag; };
-
-__device__ __forceinline__ KeyTag block_argmax(unsigned long long key, unsigned int tag,
-                                               unsigned long long* s_k, unsigned int* s_t) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
-    unsigned int t2 = __shfl_xor_sync(0xffffffffu, tag, o);
-    if (k2 > key || (k2 == key && t2 < tag)) { key = k2; tag = t2; }
-  }
-  __syncthreads();  // protect s_k/s_t from the previous round's readers
-  if (lane == 0) { s_k[warp] = key; s_t[warp] = tag; }
-  __syncthreads();
-  KeyTag r;
-  r.key = s_k[0]; r.tag = s_t[0];
-  for (int w = 1; w < nw; ++w) {
-    const unsigned long long k2 = s_k[w];
-    const unsigned int t2 = s_t[w];
-    if (k2 > r.key || (k2 == r.key && t2 < r.tag)) { r.key = k2; r.tag = t2; }
-  }
-  return r;
-}
-
-__global__ void __launch_bounds__(256)
-select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs,
-              PoolEntry* __restrict__ pool, int pool_cap, int* __restrict__ pool_count) {
-  __shared__ SelectJob J;
-  __shared__ int s_job;
-  __shared__ unsigned long long s_k[8];
-  __shared__ unsigned int s_t[8];
-  __shared__ unsigned long long s_bkey[kSelectBuf];
-  __shared__ unsigned int s_bidx[kSelectBuf];   // index relative to the slice start
-  __shared__ int s_count;
+// Block-wide top-kTopK of n keys given by key_at(i), i in [0, n): emit(r, key, i) is called for
+// r = 0.. in descending key order (smallest i first among equal keys), each rank by one thread.
+// Two streaming passes over the keys (visit(i, key) is called once per element during the
+// first), then a rank computation over the few keys that reached the threshold.  Returns the
+// number emitted; *overflow is set when more than kSelectBuf keys reach the threshold (massive ties).
+template <typename KeyAt, typename Visit, typename Emit>
+__device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit, unsigned long long* s_k,
+                           unsigned long long* s_bkey, unsigned int* s_bidx, int* s_count, bool* overflow) {
   const int tid = threadIdx.x, NT = blockDim.x;
-
-  if (tid == 0) { s_job = find_job(cta_begin, n_jobs, blockIdx.x); s_count = 0; }
-  __syncthreads();
-  {
-    const int* src = reinterpret_cast<const int*>(jobs + s_job);
-    int* dst = reinterpret_cast<int*>(&J);
-    for (int i = tid; i < int(sizeof(SelectJob) / 4); i += NT) dst[i] = __ldg(src + i);
-  }
-  const int cta = blockIdx.x - __ldg(cta_begin + s_job);
-  __syncthreads();
-
-  const long long lo = (long long)cta * J.slice;
-  const long long hi = min(J.n, lo + J.slice);
-  const double best = key_score(*J.best_key);
-
-  // pass 1: averaging-set candidates (DoubleEqual(score, best, 1e-2), :685) and thread maxima
   unsigned long long tmax = 0ull;
-  for (long long k = lo + tid; k < hi; k += NT) {
-    const double s = J.score[k];
-    const double delta = dsub(s, best);
-    const bool near_best = delta < 0.0 ? (delta >= -1e-2) : (delta <= 1e-2);
-    if (near_best) {
-      const int pos = atomicAdd(pool_count, 1);
-      if (pos < pool_cap) { PoolEntry e; e.score = s; e.index = (int)k; e.job = J.job_id; pool[pos] = e; }
-      else atomicOr(J.err, kErrPoolFull);
+  // four independent loads in flight per thread: these passes are pure L2 latency otherwise
+  for (unsigned int i0 = tid; i0 < n; i0 += 4 * NT) {
+    unsigned long long k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) k[u] = (i0 + u * NT < n) ? key_at(i0 + u * NT) : 0ull;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * NT < n) {
+        visit(i0 + u * NT, k[u]);
+        tmax = k[u] > tmax ? k[u] : tmax;
+      }
     }
-    const unsigned long long key = score_key(s);
-    tmax = key > tmax ? key : tmax;
   }
   // threshold: every warp pops its 3 largest thread maxima (warp shuffles only); the minimum of
-  // the 8 third-largest values has at least 24 >= kTopK slice elements at or above it, so it is a
-  // lower bound of the slice's kTopK-th largest element.  Warps with fewer than 3 non-empty
-  // threads report 0, which keeps everything.
+  // the warps' third-largest values has at least 24 >= kTopK keys at or above it, so it is a
+  // lower bound of the kTopK-th largest key.  Warps with fewer than 3 non-empty threads report 0,
+  // which keeps everything (then n < 256 <= kSelectBuf).
   unsigned long long thr = 0ull;
   {
     unsigned long long mine = tmax, third = 0ull;
@@ -153,46 +110,166 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
       third = k;
       if (t == lane) mine = 0ull;
     }
+    __syncthreads();   // previous users of s_k / s_count / the buffer are done
     if (lane == 0) s_k[tid >> 5] = third;
+    if (tid == 0) { s_count[0] = 0; s_count[1] = 0; }
     __syncthreads();
     thr = s_k[0];
     for (int w = 1; w < (NT >> 5); ++w) thr = s_k[w] < thr ? s_k[w] : thr;
   }
-  __syncthreads();
-  // pass 2: everything >= threshold goes to the shared buffer
-  for (long long k = lo + tid; k < hi; k += NT) {
-    const unsigned long long key = score_key(J.score[k]);
-    if (key >= thr) {
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < kSelectBuf) { s_bkey[pos] = key; s_bidx[pos] = (unsigned int)(k - lo); }
+  for (unsigned int i0 = tid; i0 < n; i0 += 4 * NT) {
+    unsigned long long k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) k[u] = (i0 + u * NT < n) ? key_at(i0 + u * NT) : 0ull;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k[u] > thr) {
+        const int pos = atomicAdd(s_count, 1);
+        if (pos < kSelectBuf - kTopK) { s_bkey[pos] = k[u]; s_bidx[pos] = i0 + u * NT; }
+      } else if (k[u] == thr && k[u] != 0ull) {
+        // keys tied with the threshold: kTopK of them are enough (score fields on maps with few
+        // distinct cell values tie massively), kept in the tail of the buffer
+        const int pos = atomicAdd(s_count + 1, 1);
+        if (pos < kTopK) { s_bkey[kSelectBuf - kTopK + pos] = k[u]; s_bidx[kSelectBuf - kTopK + pos] = i0 + u * NT; }
+      }
     }
   }
   __syncthreads();
-  int count = s_count;
-  if (count > kSelectBuf) {
-    if (tid == 0) atomicOr(J.err, kErrSelectFull);
-    count = kSelectBuf;
-  }
-  // pop the kTopK largest of the buffer
-  const int emit = min(count, kTopK);
-  for (int r = 0; r < emit; ++r) {
-    unsigned long long key = 0ull;
-    unsigned int tag = 0xffffffffu;
-    for (int i = tid; i < count; i += NT) {
-      const unsigned long long k2 = s_bkey[i];
-      if (k2 > key || (k2 == key && (unsigned int)i < tag)) { key = k2; tag = (unsigned int)i; }
+  int count = s_count[0];
+  const int n_eq = min(s_count[1], kTopK);
+  if (count > kSelectBuf - kTopK) { *overflow = true; count = kSelectBuf - kTopK; }
+  __syncthreads();
+  // compact: move the tied keys right behind the others
+  unsigned long long kk = 0ull;
+  unsigned int ii = 0u;
+  if (tid < n_eq) { kk = s_bkey[kSelectBuf - kTopK + tid]; ii = s_bidx[kSelectBuf - kTopK + tid]; }
+  __syncthreads();
+  if (tid < n_eq) { s_bkey[count + tid] = kk; s_bidx[count + tid] = ii; }
+  __syncthreads();
+  count += n_eq;
+  // rank of every buffered key among the buffered keys; ranks < kTopK are the answer
+  for (int i = tid; i < count; i += NT) {
+    const unsigned long long ki = s_bkey[i];
+    const unsigned int ei = s_bidx[i];
+    int rank = 0;
+    for (int j = 0; j < count; j += 8) {      // 8 independent shared-memory loads in flight
+      unsigned long long kj[8];
+      unsigned int ej[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool in = j + u < count;
+        kj[u] = in ? s_bkey[j + u] : 0ull;
+        ej[u] = in ? s_bidx[j + u] : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) rank += (kj[u] > ki || (kj[u] == ki && ej[u] < ei)) ? 1 : 0;
+      if (rank >= kTopK) break;               // already out of the top list
     }
-    KeyTag w = block_argmax(key, tag, s_k, s_t);
-    if (tid == 0) {
-      Entry e;
-      e.score = key_score(w.key);
-      e.index = lo + s_bidx[w.tag];
-      J.top_list[cta * kTopK + r] = e;
-      s_bkey[w.tag] = 0ull;
-    }
-    __syncthreads();
+    if (rank < kTopK) emit(rank, ki, ei);
   }
-  if (tid == 0) J.top_count[cta] = emit;
+  __syncthreads();
+  return min(count, kTopK);
+}
+
+// One CTA per slice of a job's score array; the last CTA of a job to finish merges the per-CTA
+// lists into the job's final top-kTopK and gathers, speculatively, the scores of the 3x3
+// translation neighbourhood of the best candidate over all angles: those are the same-(x,y)
+// columns the angular covariance needs whenever the averaged best pose stays in that
+// neighbourhood (always when the averaging set has one member).
+__global__ void __launch_bounds__(256)
+select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs,
+              PoolEntry* __restrict__ pool, int pool_cap, int* __restrict__ pool_count) {
+  __shared__ SelectJob J;
+  __shared__ int s_job;
+  __shared__ unsigned long long s_k[8];
+  __shared__ unsigned long long s_bkey[kSelectBuf];
+  __shared__ unsigned int s_bidx[kSelectBuf];
+  __shared__ int s_count[2];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, NT = blockDim.x;
+
+  if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + s_job);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < int(sizeof(SelectJob) / 4); i += NT) dst[i] = __ldg(src + i);
+  }
+  const int cta = blockIdx.x - __ldg(cta_begin + s_job);
+  __syncthreads();
+
+  const long long lo = (long long)cta * J.slice;
+  const long long hi = min(J.n, lo + J.slice);
+  const unsigned int n_slice = hi > lo ? (unsigned int)(hi - lo) : 0u;
+  const double best = key_score(*J.best_key);
+  const double* __restrict__ sc = J.score + lo;
+
+  bool overflow = false;
+  Entry* my_list = J.top_list + (size_t)cta * kTopK;
+  const int emitted = block_top_k(
+      n_slice, [&](unsigned int i) { return score_key(sc[i]); },
+      [&](unsigned int i, unsigned long long key) {
+        // averaging-set candidates: DoubleEqual(score, best, 1e-2)   (:685)
+        const double s = key_score(key);
+        const double delta = dsub(s, best);
+        const bool near_best = delta < 0.0 ? (delta >= -1e-2) : (delta <= 1e-2);
+        if (near_best) {
+          const int pos = atomicAdd(pool_count, 1);
+          if (pos < pool_cap) { PoolEntry e; e.score = s; e.index = (int)(lo + i); e.job = J.job_id; pool[pos] = e; }
+          else atomicOr(J.err, kErrPoolFull);
+        }
+      },
+      [&](int r, unsigned long long key, unsigned int i) { Entry e; e.score = key_score(key); e.index = lo + i; my_list[r] = e; },
+      s_k, s_bkey, s_bidx, s_count, &overflow);
+  // unused slots get a score whose key is 0 so that the merge needs no per-list count
+  for (int r = emitted + tid; r < kTopK; r += NT) { Entry e; e.score = __longlong_as_double(-1ll); e.index = -1; my_list[r] = e; }
+  __threadfence();     // every thread's list entries are visible device-wide before the ticket
+  __syncthreads();
+  if (tid == 0) {
+    J.top_count[cta] = emitted;
+    if (overflow) atomicOr(J.err, kErrSelectFull);
+    __threadfence();
+    s_last = (atomicAdd(J.done, 1) == J.n_cta - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- last CTA of the job: merge the per-CTA lists ------------------------------------------
+  const unsigned int n_ent = (unsigned int)J.n_cta * kTopK;
+  const Entry* ent = J.top_list;
+  overflow = false;
+  const int n_final = block_top_k(
+      n_ent,
+      [&](unsigned int i) -> unsigned long long { return score_key(ent[i].score); },
+      [](unsigned int, unsigned long long) {},
+      [&](int r, unsigned long long, unsigned int i) { J.final_top[r] = ent[i]; },
+      s_k, s_bkey, s_bidx, s_count, &overflow);
+  if (tid == 0) {
+    *J.final_count = n_final;
+    if (overflow) atomicOr(J.err, kErrSelectFull);
+  }
+  __syncthreads();
+  // ---- speculative gather of the best candidate's 3x3 translation neighbourhood -------------------
+  if (n_final > 0 && J.spec_out != nullptr) {
+    const long long kbest = J.final_top[0].index;       // written by thread 0 above, visible after the barrier
+    const int n_xy = J.n_xy;
+    const long long plane = (long long)n_xy * n_xy;
+    const int rem = (int)(kbest % plane);
+    const int bx = rem / n_xy, by = rem % n_xy;
+    const int x0 = max(bx - 1, 0), x1 = min(bx + 1, n_xy - 1), y0 = max(by - 1, 0), y1 = min(by + 1, n_xy - 1);
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncol = nx * ny;
+    if (tid == 0) J.spec_cols[0] = ncol;
+    if (tid < ncol) J.spec_cols[1 + tid] = (x0 + tid / ny) * n_xy + (y0 + tid % ny);
+    const int nang = J.n_ang;
+    for (int i = tid; i < ncol * nang; i += NT) {
+      const int c = i / nang, ia = i - c * nang;
+      const int col = (x0 + c / ny) * n_xy + (y0 + c % ny);
+      J.spec_out[i] = J.score[(long long)ia * plane + col];
+    }
+  } else if (tid == 0 && J.spec_cols != nullptr) {
+    J.spec_cols[0] = 0;
+  }
 }
 
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,

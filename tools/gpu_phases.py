@@ -19,19 +19,20 @@ g = sc.grid
 grid = matcher.ScanMatchMap.from_spec(ctx, g)
 grid.InitMapWithRangeVec(sc.base_pts, sc.base_poses, g.default_prob, g.sigma, g.occu_offset, g.use_blur)
 scan = matcher.RangeDataContainer2d(ctx, sc.scan_pts)
-for prof in (False, True):
+for prof in ((True,) if "--quick" in sys.argv else (False, True)):
     ctx.set_profiling(prof)
     for _ in range(3):
         m.ScanMatch(grid, scan, sc.passes[0], sc.seed_pose.copy(), np.eye(3))
     ctx.reset_stats()
-    n = 20
+    n = 3 if "--quick" in sys.argv else 20
     t0 = time.perf_counter()
     for _ in range(n):
         m.ScanMatch(grid, scan, sc.passes[0], sc.seed_pose.copy(), np.eye(3))
     wall = (time.perf_counter() - t0) / n
     show("cfg2 profiling=%s wall %.1f us" % (prof, wall * 1e6), ctx.stats(), n)
 
-for npairs in (64, 256):
+QUICK = "--quick" in sys.argv
+for npairs in ((64,) if QUICK else (64, 256)):
     pairs = synth.config4(npairs)
     packed = matcher.pack_loop_closure(pairs)
     import torch

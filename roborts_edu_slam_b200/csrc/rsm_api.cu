@@ -444,6 +444,13 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     }
   }
   const TileCfg cfg = pick_tile(items[act[0]].geo.n_xy, affine_ok);
+  // immediate-offset variant: unit search step and the same padded pitch for every job
+  int const_pitch = 0;
+  if (cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
+    const_pitch = items[act[0]].grid->pitch;
+    if (const_pitch != kPitchSmall && const_pitch != kPitchLarge) const_pitch = 0;
+    for (int a = 1; a < na && const_pitch; ++a) if (items[act[a]].grid->pitch != const_pitch) const_pitch = 0;
+  }
   const int rows = cfg.rows;
   std::vector<ScoreJob> sjobs(na);
   std::vector<int> s_cta(na + 1, 0);
@@ -580,7 +587,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
   {
     Prof p(ctx, KC_SCORE);
-    CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, cta, ctx->stream,
+    CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
                     reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
   }
   ctx->stats.kernel_launches++; ctx->stats.score_launches++;
@@ -971,13 +978,14 @@ int rsm_grid_create_from_scale(rsm_ctx* ctx, int size_x, int size_y, double scal
   if (!ctx || !out || size_x <= 0 || size_y <= 0 || size_x > 32768 || size_y > 32768 || !(scale_factor > 0))
     return fail(ctx, RSM_ERR_INVALID, "rsm_grid_create: bad arguments");
   rsm_grid* g = new rsm_grid;
-  g->size_x = size_x; g->size_y = size_y; g->pitch = size_x;
+  g->size_x = size_x; g->size_y = size_y; g->pitch = grid_pitch_for(size_x);
   g->resolution = 1 / scale_factor;
   g->scale = scale_factor;
   g->off_x = offset_x; g->off_y = offset_y;
   g->tf.set(g->scale, offset_x, offset_y);
-  const size_t bytes = (size_t(size_x) * size_y * 4 + 15) / 16 * 16;
+  const size_t bytes = size_t(g->pitch) * size_y * 4;   // pitch is a multiple of 32 cells
   cudaError_t e = cudaMalloc(&g->d_cells, bytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_cells, 0, bytes, ctx->stream);   // padding columns are never read, keep them defined
   if (e != cudaSuccess) { delete g; return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(grid) failed: %s", cudaGetErrorString(e)); }
   *out = g;
   return RSM_OK;
@@ -1007,7 +1015,8 @@ int rsm_grid_upload_f32(rsm_ctx* ctx, rsm_grid* grid, const float* prob) {
   for (size_t i = 0; i < n; ++i) if (!fix_ok(prob[i], &fx[i])) { ok = false; break; }
   if (!ok) std::memcpy(ctx->h_up.p, prob, n * 4);
   grid->fixed = ok;
-  CU(cudaMemcpyAsync(grid->d_cells, ctx->h_up.p, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpy2DAsync(grid->d_cells, size_t(grid->pitch) * 4, ctx->h_up.p, size_t(grid->size_x) * 4,
+                       size_t(grid->size_x) * 4, size_t(grid->size_y), cudaMemcpyHostToDevice, ctx->stream));
   rc = sync_stream(ctx);
   if (rc) return rc;
   ctx->stats.h2d_bytes += n * 4;
@@ -1020,7 +1029,8 @@ int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out) {
   const size_t n = size_t(grid->size_x) * grid->size_y;
   int rc = ensure_pinned(ctx, ctx->h_down, n * 4);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->h_down.p, grid->d_cells, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpy2DAsync(ctx->h_down.p, size_t(grid->size_x) * 4, grid->d_cells, size_t(grid->pitch) * 4,
+                       size_t(grid->size_x) * 4, size_t(grid->size_y), cudaMemcpyDeviceToHost, ctx->stream));
   rc = sync_stream(ctx);
   if (rc) return rc;
   ctx->stats.d2h_bytes += n * 4;
@@ -1138,7 +1148,7 @@ int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double 
   if (total) { rc = upload_points(ctx, pts_xy, total, &d_pts); if (rc) return rc; }
   char* up = ctx->h_up.p;
   char* dw = ctx->d_work.p;
-  FillJob F; F.grid = grid->d_cells; F.n_cells = (long long)grid->size_x * grid->size_y; F.value = pl.fill;
+  FillJob F; F.grid = grid->d_cells; F.n_cells = (long long)grid->pitch * grid->size_y; F.value = pl.fill;
   std::memcpy(up + o_fill, &F, sizeof F);
   RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
   size_t off = 0;
@@ -1316,7 +1326,8 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
   int rc = plan_raster(ctx, default_prob, sigma, resolution, occu_offset, 1, pl);
   if (rc) return rc;
   // grids: one pool, one slot per pair
-  const size_t cells = size_t(grid_size) * grid_size;
+  const int pool_pitch = grid_pitch_for(grid_size);
+  const size_t cells = size_t(pool_pitch) * grid_size;
   const size_t slot = (cells * 4 + 255) / 256 * 256;
   rc = ensure_dev(ctx, ctx->d_pool_grids, slot * n);
   if (rc) return rc;
@@ -1326,7 +1337,7 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
   const double cell_len = 1 / scale;
   for (int i = 0; i < n; ++i) {
     rsm_grid& g = gs[i];
-    g.size_x = g.size_y = g.pitch = grid_size;
+    g.size_x = g.size_y = grid_size; g.pitch = pool_pitch;
     g.resolution = resolution; g.scale = scale;
     // ResetScanMatchMapWithRangeVec: offset = -(pose - 0.5 * size * cell_len)   (slam_processor.cpp:451-455)
     g.off_x = -(centres_world[2 * i] - 0.5 * grid_size * cell_len);

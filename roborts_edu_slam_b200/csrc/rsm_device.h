@@ -15,6 +15,16 @@ constexpr int kFixShift = 25;
 constexpr double kFixScale = 1.0 / 33554432.0;  // 2^-25
 constexpr int kFixOne = 1 << kFixShift;
 
+// Device grids are padded to one of two row pitches (cells) so that the scoring kernel reaches the
+// rows of a tile with immediate offsets (no address arithmetic per gather); wider grids keep
+// pitch = size_x rounded up to 32 and use the run-time stride variant.  129 and 17 cache lines
+// per row: consecutive rows fall into different L1 sets.
+constexpr int kPitchSmall = 544;
+constexpr int kPitchLarge = 4128;
+inline int grid_pitch_for(int size_x) {
+  return size_x <= kPitchSmall ? kPitchSmall : size_x <= kPitchLarge ? kPitchLarge : (size_x + 31) / 32 * 32;
+}
+
 constexpr int kTopK = 21;          // top-20 covariance prefix + 1 to detect a tie at the cut
 constexpr int kChunk = 32;         // beams per shared-memory table chunk of the scoring kernel
 constexpr int kSelectBuf = 2048;   // per-CTA candidate buffer of the selection kernel

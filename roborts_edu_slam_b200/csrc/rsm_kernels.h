@@ -15,8 +15,9 @@ namespace rsm {
 // translations of one angle.
 int score_threads(int lx);
 inline int score_rows(int lx, int ry) { return (score_threads(lx) / lx) * ry; }
-int score_occupancy(bool fixed, bool affine, int lx, int ry);
-cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int n_cta, cudaStream_t st,
+// const_pitch: kPitchSmall / kPitchLarge if every job has that row pitch and a unit search step, else 0
+int score_occupancy(bool fixed, bool affine, int lx, int ry, int const_pitch);
+cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitch, int n_cta, cudaStream_t st,
                          const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);

@@ -80,7 +80,9 @@ __device__ __forceinline__ int cell_index(double lut, double cand) {
   return __double2int_rz(dadd(dadd(lut, cand), 0.5));
 }
 
-template <bool FIXED, bool AFFINE, int LX, int RY>
+// PITCH > 0: AFFINE with a unit search step on a grid of that compile-time row pitch -- the RY rows
+// of a thread are then reached with immediate offsets.
+template <bool FIXED, bool AFFINE, int LX, int RY, int PITCH>
 __global__ void __launch_bounds__(threads_of(LX), min_blocks_of(RY, threads_of(LX)))
 score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
   constexpr int RYP = ryp_of(RY);
@@ -125,7 +127,7 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
   const int ia = J.ang_begin + ia_local;
   const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
   const int V = J.V, n_xy = J.n_xy, pitch = J.pitch, size_x = J.size_x, size_y = J.size_y;
-  const int stepoff = J.stepoff;   // affine: (search step in cells) * pitch
+  const int stepoff = PITCH > 0 ? PITCH : J.stepoff;   // affine: (search step in cells) * pitch
   const int nchunks = (V + PC - 1) / PC;
 
   if (AFFINE && tid < SLOTS) { sAff[0][tid] = 1; sAff[1][tid] = 1; sAff[2][tid] = 1; }
@@ -325,59 +327,75 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
 // ---- variant table ----------------------------------------------------------------------------
 typedef void (*ScoreFn)(const ScoreJob*, const int*, int);
 
-template <bool FIXED, bool AFFINE, int LX>
+template <bool FIXED, bool AFFINE, int LX, int PITCH>
 static ScoreFn pick_ry(int ry) {
   switch (ry) {
-    case 1: return score_kernel<FIXED, AFFINE, LX, 1>;
-    case 2: return score_kernel<FIXED, AFFINE, LX, 2>;
-    case 3: return score_kernel<FIXED, AFFINE, LX, 3>;
-    case 4: return score_kernel<FIXED, AFFINE, LX, 4>;
-    case 5: return score_kernel<FIXED, AFFINE, LX, 5>;
-    case 6: return score_kernel<FIXED, AFFINE, LX, 6>;
-    case 7: return score_kernel<FIXED, AFFINE, LX, 7>;
-    case 8: return score_kernel<FIXED, AFFINE, LX, 8>;
+    case 1: return score_kernel<FIXED, AFFINE, LX, 1, PITCH>;
+    case 2: return score_kernel<FIXED, AFFINE, LX, 2, PITCH>;
+    case 3: return score_kernel<FIXED, AFFINE, LX, 3, PITCH>;
+    case 4: return score_kernel<FIXED, AFFINE, LX, 4, PITCH>;
+    case 5: return score_kernel<FIXED, AFFINE, LX, 5, PITCH>;
+    case 6: return score_kernel<FIXED, AFFINE, LX, 6, PITCH>;
+    case 7: return score_kernel<FIXED, AFFINE, LX, 7, PITCH>;
+    case 8: return score_kernel<FIXED, AFFINE, LX, 8, PITCH>;
     default: return nullptr;
   }
 }
 
 template <bool FIXED>
-static ScoreFn pick_lx(bool affine, int lx, int ry) {
+static ScoreFn pick_lx(bool affine, int lx, int ry, int pitch) {
   if (affine) {
+    if (FIXED && pitch == kPitchSmall) {
+      switch (lx) {
+        case 16: return pick_ry<FIXED, true, 16, kPitchSmall>(ry);
+        case 32: return pick_ry<FIXED, true, 32, kPitchSmall>(ry);
+        default: break;
+      }
+    }
+    if (FIXED && pitch == kPitchLarge) {
+      switch (lx) {
+        case 16: return pick_ry<FIXED, true, 16, kPitchLarge>(ry);
+        case 32: return pick_ry<FIXED, true, 32, kPitchLarge>(ry);
+        default: break;
+      }
+    }
     switch (lx) {
-      case 4: return pick_ry<FIXED, true, 4>(ry);
-      case 8: return pick_ry<FIXED, true, 8>(ry);
-      case 16: return pick_ry<FIXED, true, 16>(ry);
-      case 32: return pick_ry<FIXED, true, 32>(ry);
+      case 4: return pick_ry<FIXED, true, 4, 0>(ry);
+      case 8: return pick_ry<FIXED, true, 8, 0>(ry);
+      case 16: return pick_ry<FIXED, true, 16, 0>(ry);
+      case 32: return pick_ry<FIXED, true, 32, 0>(ry);
       default: return nullptr;
     }
   }
   switch (lx) {
-    case 4: return pick_ry<FIXED, false, 4>(ry);
-    case 8: return pick_ry<FIXED, false, 8>(ry);
-    case 16: return pick_ry<FIXED, false, 16>(ry);
-    case 32: return pick_ry<FIXED, false, 32>(ry);
+    case 4: return pick_ry<FIXED, false, 4, 0>(ry);
+    case 8: return pick_ry<FIXED, false, 8, 0>(ry);
+    case 16: return pick_ry<FIXED, false, 16, 0>(ry);
+    case 32: return pick_ry<FIXED, false, 32, 0>(ry);
     default: return nullptr;
   }
 }
 
-static ScoreFn score_fn(bool fixed, bool affine, int lx, int ry) {
-  return fixed ? pick_lx<true>(affine, lx, ry) : pick_lx<false>(affine, lx, ry);
+// const_pitch: kPitchSmall / kPitchLarge when every job of the launch has that row pitch AND a unit
+// search step (immediate-offset variant), else 0
+static ScoreFn score_fn(bool fixed, bool affine, int lx, int ry, int const_pitch) {
+  return fixed ? pick_lx<true>(affine, lx, ry, const_pitch) : pick_lx<false>(affine, lx, ry, 0);
 }
 
 int score_threads(int lx) { return threads_of(lx); }
 
 // resident CTAs per SM of a variant (0 if the variant does not exist)
-int score_occupancy(bool fixed, bool affine, int lx, int ry) {
-  ScoreFn fn = score_fn(fixed, affine, lx, ry);
+int score_occupancy(bool fixed, bool affine, int lx, int ry, int const_pitch) {
+  ScoreFn fn = score_fn(fixed, affine, lx, ry, const_pitch);
   if (!fn) return 0;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads_of(lx), 0) != cudaSuccess) { cudaGetLastError(); return 0; }
   return nb;
 }
 
-cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int n_cta, cudaStream_t st,
+cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitch, int n_cta, cudaStream_t st,
                          const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
-  ScoreFn fn = score_fn(fixed, affine, lx, ry);
+  ScoreFn fn = score_fn(fixed, affine, lx, ry, const_pitch);
   if (!fn) return cudaErrorInvalidValue;
   fn<<<n_cta, threads_of(lx), 0, st>>>(jobs, cta_begin, n_jobs);
   return cudaGetLastError();

@@ -443,10 +443,22 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
         affine_ok = false;
     }
   }
-  const TileCfg cfg = pick_tile(items[act[0]].geo.n_xy, affine_ok);
+  TileCfg cfg = pick_tile(items[act[0]].geo.n_xy, affine_ok);
+  // staged variant (shared-memory window + TMA): big windows, unit step, fixed-point grids
+  // (measured on B200: the L1 path reaches its load-issue floor, 5.1e12 evaluations/s on the wide
+  //  window, against 3.7e12 for this first staged version, so the staged variant is opt-in)
+  bool use_staged = affine_ok && items[act[0]].geo.factor == 1.0 && items[act[0]].geo.n_xy >= 48 &&
+                    std::getenv("RSM_STAGED") != nullptr;
+  int max_V = 0;
+  for (int a = 0; a < na && use_staged; ++a) {
+    const PassItem& it = items[act[a]];
+    if (!it.grid->fixed || it.geo.visited > 2048 || (it.grid->pitch & 3)) use_staged = false;
+    max_V = std::max(max_V, it.geo.visited);
+  }
+  if (use_staged) { int tx, ty; score_staged_tile(&tx, &ty); cfg.lx = tx; cfg.rows = ty; cfg.ry = 0; cfg.affine = true; }
   // immediate-offset variant: unit search step and the same padded pitch for every job
   int const_pitch = 0;
-  if (cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
+  if (!use_staged && cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
     const_pitch = items[act[0]].grid->pitch;
     if (const_pitch != kPitchSmall && const_pitch != kPitchLarge) const_pitch = 0;
     for (int a = 1; a < na && const_pitch; ++a) if (items[act[a]].grid->pitch != const_pitch) const_pitch = 0;
@@ -587,8 +599,12 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
   {
     Prof p(ctx, KC_SCORE);
-    CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
-                    reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
+    if (use_staged)
+      CU(launch_score_staged(cta, max_V, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+                             reinterpret_cast<const int*>(dw + o_scta), na));
+    else
+      CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
+                      reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
   }
   ctx->stats.kernel_launches++; ctx->stats.score_launches++;
 

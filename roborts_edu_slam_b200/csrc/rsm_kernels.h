@@ -19,6 +19,11 @@ inline int score_rows(int lx, int ry) { return (score_threads(lx) / lx) * ry; }
 int score_occupancy(bool fixed, bool affine, int lx, int ry, int const_pitch);
 cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitch, int n_cta, cudaStream_t st,
                          const ScoreJob* jobs, const int* cta_begin, int n_jobs);
+// Staged variant (shared-memory window filled by TMA bulk copies): fixed-point grid, unit search step.
+// A CTA covers score_staged_tile() translations of one angle; max_V = largest visited-beam count.
+void score_staged_tile(int* tile_x, int* tile_y);
+size_t score_staged_smem(int V);
+cudaError_t launch_score_staged(int n_cta, int max_V, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);
 cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);

@@ -401,4 +401,274 @@ cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitc
   return cudaGetLastError();
 }
 
+
+// =================================================================================================
+// staged variant: the grid window of a beam group lives in shared memory, filled by TMA bulk copies
+// =================================================================================================
+// For windows of >= ~48 translations per axis on a fixed-point grid with a unit search step.
+// The L1 path above is bound by L1 data-pipe wavefronts: a warp's 32 consecutive cells start at an
+// arbitrary cell, so every gather touches two 128-byte lines.  Shared memory has no such penalty
+// (32 consecutive words are conflict-free at any offset), so here a CTA of 256 threads owns one
+// angle and a tile of (32*RX) x (8*RY) translations, walks the beams in ROUNDS of up to 32
+// consecutive beams whose endpoint boxes fit a SW x HMAX-cell shared-memory tile, and
+//   * warp 0 plans the next round (prefix min/max of the beams' tile-origin cells with warp
+//     shuffles), arms an mbarrier with the byte count and issues one cp.async.bulk (TMA, UBLKCP)
+//     per tile row into the other buffer,
+//   * all 8 warps gather the current round from shared memory: per beam one broadcast load of the
+//     tile-relative base, then RX*RY loads at compile-time offsets and RX*RY/2 three-input adds.
+// Per-beam tile origins use the same provable affine index test as the L1 path (tile-wide);
+// beams that fail it or whose tile leaves the grid (a handful per million) are added afterwards
+// with exact per-thread indices read from global memory -- integer sums are order-independent.
+namespace staged {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kSW = 160;                    // shared tile row pitch, cells
+constexpr int kBufCells = 12288;            // 48 KB per buffer
+constexpr int kHMax = kBufCells / kSW;      // 76 rows
+constexpr int kRound = 32;                  // beams per round at most
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_row(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+
+template <int RX, int RY>
+__global__ void __launch_bounds__(kThreads, 2)
+score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
+  constexpr int TILE_X = 32 * RX, TILE_Y = kWarps * RY, NC = RX * RY;
+  static_assert(TILE_X + 4 <= kSW && TILE_Y <= kHMax, "a single beam must fit the shared tile");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  __shared__ ScoreJob J;
+  __shared__ int s_job;
+  __shared__ unsigned long long s_wmax[kWarps];
+  __shared__ double sX[TILE_X], sY[TILE_Y];
+  __shared__ int sBase[2][kRound];          // tile-relative cell offset of each beam of the round, -1 = skip
+  __shared__ int sCount[2];                 // beams in the round
+  __shared__ __align__(8) uint64_t sBar[2];
+  __shared__ int sUnsafeCount;
+  __shared__ int sUnsafe[64];              // beams that need exact per-thread indices
+  extern __shared__ __align__(128) unsigned char dyn[];
+  int* buf0 = reinterpret_cast<int*>(dyn);
+  int* buf1 = buf0 + kBufCells;
+  int2* sBeam = reinterpret_cast<int2*>(buf1 + kBufCells);   // [V] tile-origin cell of every visited beam
+
+  if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + s_job);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < int(sizeof(ScoreJob) / 4); i += kThreads) dst[i] = __ldg(src + i);
+  }
+  const int first_cta = __ldg(cta_begin + s_job);
+  if (tid == 0) { mbar_init(&sBar[0], 1); mbar_init(&sBar[1], 1); sUnsafeCount = 0; }
+  __syncthreads();
+
+  const int local = blockIdx.x - first_cta;
+  const int tiles = J.tiles_x * J.tiles_y;
+  const int ia_local = local / tiles;
+  const int tile = local - ia_local * tiles;
+  const int tx0 = (tile % J.tiles_x) * TILE_X;
+  const int ty0 = (tile / J.tiles_x) * TILE_Y;
+  const int ia = J.ang_begin + ia_local;
+  const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
+  const int V = J.V, n_xy = J.n_xy, pitch = J.pitch, size_x = J.size_x, size_y = J.size_y;
+  const int* __restrict__ grid = reinterpret_cast<const int*>(J.grid);
+
+  for (int i = tid; i < TILE_X + TILE_Y; i += kThreads) {
+    if (i < TILE_X) sX[i] = dadd(J.sx, dmul((double)(tx0 + i), J.f));
+    else sY[i - TILE_X] = dadd(J.sy, dmul((double)(ty0 + i - TILE_X), J.f));
+  }
+  __syncthreads();
+  // tile-origin cell of every beam + the affine safety test for the whole tile (see header)
+  for (int v = tid; v < V; v += kThreads) {
+    const int p = v * J.step;
+    const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+    const double lx = dsub(dmul(cs, px), dmul(sn, py));
+    const double ly = dadd(dmul(sn, px), dmul(cs, py));
+    const double tx_ = dadd(dadd(lx, sX[0]), 0.5), ty_ = dadd(dadd(ly, sY[0]), 0.5);
+    const int gx0 = __double2int_rz(tx_), gy0 = __double2int_rz(ty_);
+    const double fx = tx_ - (double)gx0, fy = ty_ - (double)gy0;
+    const bool ok = fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 &&
+                    gx0 >= 0 && gx0 + TILE_X - 1 < size_x && gy0 >= 0 && gy0 + TILE_Y - 1 < size_y;
+    sBeam[v] = ok ? make_int2(gx0, gy0) : make_int2(-1, -1);
+    if (!ok) { const int pos = atomicAdd(&sUnsafeCount, 1); if (pos < 64) sUnsafe[pos] = v; }
+  }
+  __syncthreads();
+
+  // ---- round planner (warp 0): beams [b, b + n) into buffer `which` ----------------------------
+  auto plan_round = [&](int b, int which) {
+    const int v = b + lane;
+    int2 e = make_int2(-1, -1);
+    if (v < V) e = sBeam[v];
+    const bool live = v < V, safe = live && e.x >= 0;
+    int xmin = safe ? e.x : 0x7fffffff, xmax = safe ? e.x : -1, ymin = safe ? e.y : 0x7fffffff, ymax = safe ? e.y : -1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {      // inclusive prefix min / max over lanes 0..lane
+      const int a = __shfl_up_sync(0xffffffffu, xmin, o), c = __shfl_up_sync(0xffffffffu, xmax, o);
+      const int d = __shfl_up_sync(0xffffffffu, ymin, o), f = __shfl_up_sync(0xffffffffu, ymax, o);
+      if (lane >= o) { xmin = min(xmin, a); xmax = max(xmax, c); ymin = min(ymin, d); ymax = max(ymax, f); }
+    }
+    const bool any = xmax >= 0;
+    const int xl = xmin & ~3;
+    const int w = any ? ((xmax - xl + TILE_X + 3) & ~3) : 0, h = any ? (ymax - ymin + TILE_Y) : 0;
+    const bool fits = live && w <= kSW && h <= kHMax;
+    const unsigned int vote = __ballot_sync(0xffffffffu, fits);
+    const int n = (vote == 0xffffffffu) ? 32 : (__ffs(~vote) - 1);   // length of the leading run of ones
+    // extents of the chosen prefix live in lane n-1
+    const int src = max(n - 1, 0);
+    const int rxl = __shfl_sync(0xffffffffu, xl, src), ryl = __shfl_sync(0xffffffffu, ymin, src);
+    const int rw = __shfl_sync(0xffffffffu, w, src), rh = __shfl_sync(0xffffffffu, h, src);
+    if (lane < n) sBase[which][lane] = safe ? (e.y - ryl) * kSW + (e.x - rxl) : -1;
+    if (lane == 0) sCount[which] = n;
+    if (n > 0 && rh > 0) {
+      int* dst = which ? buf1 : buf0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) mbar_expect_tx(&sBar[which], (uint32_t)(rh * rw * 4));
+      __syncwarp();
+      for (int r = lane; r < rh; r += 32)
+        tma_row(dst + r * kSW, grid + ((size_t)(ryl + r) * pitch + rxl), (uint32_t)(rw * 4), &sBar[which]);
+    } else if (lane == 0) {
+      mbar_expect_tx(&sBar[which], 0u);     // nothing to copy: complete the phase right away
+    }
+  };
+
+  unsigned int a32[NC];
+  unsigned long long a64[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { a32[c] = 0u; a64[c] = 0ull; }
+  const int thread_off = (warp * RY) * kSW + lane;
+
+  if (warp == 0 && V > 0) plan_round(0, 0);
+  __syncthreads();
+  int b = 0;
+  for (int r = 0; b < V; ++r) {
+    const int which = r & 1;
+    const int n = sCount[which];
+    if (warp == 0 && b + n < V) plan_round(b + n, which ^ 1);
+    mbar_wait(&sBar[which], (uint32_t)((r >> 1) & 1));
+    const int* tile_buf = (which ? buf1 : buf0) + thread_off;
+#pragma unroll 2
+    for (int j = 0; j < n; ++j) {
+      const int base = sBase[which][j];
+      if (base >= 0) {
+        const int* q = tile_buf + base;
+#pragma unroll
+        for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+          for (int rx = 0; rx < RX; ++rx) a32[ry * RX + rx] += (unsigned int)q[ry * kSW + rx * 32];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { a64[c] += a32[c]; a32[c] = 0u; }
+    __syncthreads();
+    b += n;
+  }
+
+  // beams that failed the tile-wide test: exact indices, straight from global memory
+  int err = 0;
+  const int n_unsafe = sUnsafeCount;
+  const int n_slow = n_unsafe <= 64 ? n_unsafe : V;      // more than the list holds: scan every beam
+  for (int u = 0; u < n_slow; ++u) {
+    const int v = n_unsafe <= 64 ? sUnsafe[u] : u;
+    if (sBeam[v].x >= 0) continue;
+    const int p = v * J.step;
+    const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+    const double lx = dsub(dmul(cs, px), dmul(sn, py));
+    const double ly = dadd(dmul(sn, px), dmul(cs, py));
+    int gy[RY];
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry) {
+      int g = cell_index(ly, sY[warp * RY + ry]);
+      if (g < 0 || g >= size_y) { if (ty0 + warp * RY + ry < n_xy) err |= kErrWindow; g = max(0, min(g, size_y - 1)); }
+      gy[ry] = g * pitch;
+    }
+#pragma unroll
+    for (int rx = 0; rx < RX; ++rx) {
+      int g = cell_index(lx, sX[lane + 32 * rx]);
+      if (g < 0 || g >= size_x) { if (tx0 + lane + 32 * rx < n_xy) err |= kErrWindow; g = max(0, min(g, size_x - 1)); }
+#pragma unroll
+      for (int ry = 0; ry < RY; ++ry) a64[ry * RX + rx] += (unsigned int)__ldg(grid + (gy[ry] + g));
+    }
+  }
+
+  // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
+  unsigned long long kmax = 0ull;
+  const double da = dsub(ang, J.ca);
+  const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, dmul(da, da)), 0.349)), 0.9);
+#pragma unroll
+  for (int rx = 0; rx < RX; ++rx) {
+    const int ix = tx0 + lane + 32 * rx;
+    if (ix >= n_xy) continue;
+    const double dx = dsub(sX[lane + 32 * rx], J.cx);
+    const double dx2 = dmul(dx, dx);
+    double* out = J.score + ((long long)ia_local * n_xy + ix) * n_xy;
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry) {
+      const int iy = ty0 + warp * RY + ry;
+      if (iy >= n_xy) continue;
+      double sc = ddiv(dmul((double)a64[ry * RX + rx], kFixScale), J.divisor);
+      if (J.use_penalty) {
+        const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);
+        if (!zero) {
+          const double dy = dsub(sY[warp * RY + ry], J.cy);
+          double d2 = dadd(dx2, dmul(dy, dy));
+          d2 = dmul(d2, J.m2);
+          const double dp = fmax(dsub(1.0, ddiv(dmul(J.gain, d2), J.half_size)), 0.5);
+          sc = dmul(sc, dmul(dp, ap));
+        }
+      }
+      out[iy] = sc;
+      const unsigned long long k = score_key(sc);
+      kmax = k > kmax ? k : kmax;
+    }
+  }
+  kmax = warp_max_u64(kmax);
+  if (lane == 0) s_wmax[warp] = kmax;
+  if (err) atomicOr(J.err, err);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = 0ull;
+    for (int w = 0; w < kWarps; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
+    atomicMax(J.best_key, m);
+  }
+}
+
+}  // namespace staged
+
+void score_staged_tile(int* tile_x, int* tile_y) { *tile_x = 96; *tile_y = 32; }
+
+size_t score_staged_smem(int V) { return size_t(2 * staged::kBufCells) * 4 + size_t(V) * 8; }
+
+cudaError_t launch_score_staged(int n_cta, int max_V, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
+  auto fn = staged::score_staged_kernel<3, 4>;
+  const size_t smem = score_staged_smem(max_V);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  fn<<<n_cta, staged::kThreads, smem, st>>>(jobs, cta_begin, n_jobs);
+  return cudaGetLastError();
+}
+
 }  // namespace rsm

@@ -456,6 +456,16 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     max_V = std::max(max_V, it.geo.visited);
   }
   if (use_staged) { int tx, ty; score_staged_tile(&tx, &ty); cfg.lx = tx; cfg.rows = ty; cfg.ry = 0; cfg.affine = true; }
+  // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
+  bool use_flat = !use_staged && !cfg.affine && std::getenv("RSM_NO_FLAT") == nullptr;
+  for (int a = 0; a < na && use_flat; ++a) {
+    const PassGeo& g = items[act[a]].geo;
+    // 16.16 fixed-point coordinates: window coordinates must stay well inside +-2^14 cells
+    // (measured: the tiled kernel wins from about 8 translations per axis on)
+    if (g.n_xy < 3 || g.n_xy > 6 || !(std::fabs(g.start_x) < 8192.0 && std::fabs(g.start_y) < 8192.0 &&
+                                       std::fabs(g.x_of(g.n_xy)) < 8192.0 && std::fabs(g.y_of(g.n_xy)) < 8192.0))
+      use_flat = false;
+  }
   // immediate-offset variant: unit search step and the same padded pitch for every job
   int const_pitch = 0;
   if (!use_staged && cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
@@ -567,7 +577,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.half_size = it.param.search_space_size / 2;                     // :734
     J.gain = (it.param.type == RSM_COARSE) ? 0.4 : 0.2;               // :588-602, :759-761
     s_cta[a] = cta;
-    cta += J.ang_count * J.tiles_x * J.tiles_y;
+    cta += use_flat ? score_flat_ctas(int(it.n_local)) : J.ang_count * J.tiles_x * J.tiles_y;
     (it.grid->fixed ? any_fixed : any_float) = true;
     SelectJob& L = ljobs[a];
     std::memset(&L, 0, sizeof L);
@@ -599,7 +609,10 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
   {
     Prof p(ctx, KC_SCORE);
-    if (use_staged)
+    if (use_flat)
+      CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+                             reinterpret_cast<const int*>(dw + o_scta), na));
+    else if (use_staged)
       CU(launch_score_staged(cta, max_V, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                              reinterpret_cast<const int*>(dw + o_scta), na));
     else

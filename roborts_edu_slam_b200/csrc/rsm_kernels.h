@@ -19,6 +19,9 @@ inline int score_rows(int lx, int ry) { return (score_threads(lx) / lx) * ry; }
 int score_occupancy(bool fixed, bool affine, int lx, int ry, int const_pitch);
 cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitch, int n_cta, cudaStream_t st,
                          const ScoreJob* jobs, const int* cta_begin, int n_jobs);
+// Flat variant (small windows, non-integer step): one thread per candidate, 256 candidates per CTA.
+int score_flat_ctas(int n_local);
+cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 // Staged variant (shared-memory window filled by TMA bulk copies): fixed-point grid, unit search step.
 // A CTA covers score_staged_tile() translations of one angle; max_V = largest visited-beam count.
 void score_staged_tile(int* tile_x, int* tile_y);

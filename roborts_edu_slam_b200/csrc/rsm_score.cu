@@ -403,6 +403,166 @@ cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitc
 
 
 // =================================================================================================
+// flat variant: small windows with a non-integer search step (the fine / super-fine passes)
+// =================================================================================================
+// A fine pass is 11 x 11 translations x 11 angles, a super-fine pass 3 x 3 x 21: tiles of such
+// windows leave most lanes of the tiled kernel idle, and their index tables are as large as the
+// work itself.  B200 issues only ~17 FP64 operations per clock per SM (measured), so computing
+// (int)(lut + x + 0.5) in FP64 per evaluation is out of the question too.  Instead:
+//   * a CTA of 256 threads takes 256 consecutive candidates of the job in (angle, y, x) order
+//     (spanning up to 30 angles); every thread owns ONE candidate;
+//   * coordinates are carried as 32-bit fixed point with 16 fractional bits: lutq = rn(lut * 2^16)
+//     per (angle, beam) (built per 32-beam chunk from the FP64 endpoint), xq = rn(x * 2^16) + 2^15
+//     per thread.  t = lutq + xq is an integer add; it differs from the reference's FP64 value
+//     T = (lut + x) + 0.5 by at most 2^-16 + 1e-11 cells, so whenever frac(t) lies in
+//     [2, 65533] / 65536 and t >= 0, trunc(T) is PROVABLY t >> 16;
+//   * the ~1.2e-4 of evaluations that fail the test (or leave the grid) recompute the index with
+//     the exact FP64 expression.
+namespace flat {
+
+constexpr int kThreads = 256;
+constexpr int kPC = 32;          // beams per chunk
+constexpr int kMaxAngles = 32;   // angles a CTA may span (n_xy >= 3 -> at most 30)
+constexpr double kQ = 65536.0;
+
+__device__ __forceinline__ int to_q(double v) {   // rn(v * 2^16), saturated so that sums cannot overflow
+  return __double2int_rn(fmin(fmax(dmul(v, kQ), -1073741824.0), 1073741824.0));
+}
+
+template <bool FIXED>
+__global__ void __launch_bounds__(kThreads, 4)
+score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
+  const int tid = threadIdx.x;
+  __shared__ ScoreJob J;
+  __shared__ int s_job;
+  __shared__ unsigned long long s_wmax[kThreads / 32];
+  __shared__ int2 sLutQ[2][kMaxAngles][kPC];
+
+  if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + s_job);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < int(sizeof(ScoreJob) / 4); i += kThreads) dst[i] = __ldg(src + i);
+  }
+  const int first_cta = __ldg(cta_begin + s_job);
+  __syncthreads();
+
+  const int n_xy = J.n_xy, plane = n_xy * n_xy;
+  const int n_local = J.ang_count * plane;
+  const int k0 = (blockIdx.x - first_cta) * kThreads;          // first candidate of this CTA, (angle, y, x) order
+  const int kk = k0 + tid;
+  const bool live = kk < n_local;
+  const int kc = live ? kk : n_local - 1;
+  const int ia_l = kc / plane, rem = kc - ia_l * plane;
+  const int iy = rem / n_xy, ix = rem - iy * n_xy;
+  const int a_first = k0 / plane;
+  const int a_last = min(k0 + kThreads - 1, n_local - 1) / plane;
+  const int n_a = a_last - a_first + 1;
+  const int a_rel = ia_l - a_first;
+  const int ia = J.ang_begin + ia_l;
+  const double x = dadd(J.sx, dmul((double)ix, J.f));          // :569
+  const double y = dadd(J.sy, dmul((double)iy, J.f));          // :572
+  const int xq = to_q(x) + 32768, yq = to_q(y) + 32768;
+  const int V = J.V, pitch = J.pitch;
+  const unsigned int size_x = (unsigned int)J.size_x, size_y = (unsigned int)J.size_y;
+  const int nchunks = (V + kPC - 1) / kPC;
+  const int* gridI = reinterpret_cast<const int*>(J.grid);
+  const float* gridF = reinterpret_cast<const float*>(J.grid);
+
+  // fixed-point rotated endpoints of chunk c for the CTA's angles   (:179-180)
+  auto lut_chunk = [&](int c) {
+    const int npc = min(kPC, V - c * kPC);
+    for (int q = tid; q < n_a * kPC; q += kThreads) {
+      const int a = q / kPC, pc = q % kPC;
+      if (pc < npc) {
+        const int ja = J.ang_begin + a_first + a;
+        const double cs = __ldg(J.trig + 3 * ja), sn = __ldg(J.trig + 3 * ja + 1);
+        const int p = (c * kPC + pc) * J.step;
+        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+        sLutQ[c & 1][a][pc] = make_int2(to_q(dsub(dmul(cs, px), dmul(sn, py))), to_q(dadd(dmul(sn, px), dmul(cs, py))));
+      }
+    }
+  };
+
+  unsigned int a32 = 0u;
+  unsigned long long a64 = 0ull;
+  double ad = 0.0;
+  int err = 0;
+  lut_chunk(0);
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) lut_chunk(c + 1);
+    const int npc = min(kPC, V - c * kPC);
+    const int2* l = sLutQ[c & 1][a_rel];
+#pragma unroll 4
+    for (int pc = 0; pc < npc; ++pc) {
+      const int2 e = l[pc];
+      const int tx = e.x + xq, ty = e.y + yq;
+      int gx = tx >> 16, gy = ty >> 16;
+      const bool ok = (((unsigned int)(tx - 2) & 0xffffu) <= 65531u) && (((unsigned int)(ty - 2) & 0xffffu) <= 65531u) &&
+                      (unsigned int)gx < size_x && (unsigned int)gy < size_y;
+      if (!ok) {
+        // exact FP64 index: the fixed-point value is within 2^-15 of a cell boundary, or off the grid
+        const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1);
+        const int p = (c * kPC + pc) * J.step;
+        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+        gx = cell_index(dsub(dmul(cs, px), dmul(sn, py)), x);      // :647-648
+        gy = cell_index(dadd(dmul(sn, px), dmul(cs, py)), y);
+        if ((unsigned int)gx >= size_x || (unsigned int)gy >= size_y) {
+          if (live) err = kErrWindow;
+          gx = max(0, min(gx, (int)size_x - 1));
+          gy = max(0, min(gy, (int)size_y - 1));
+        }
+      }
+      if (FIXED) a32 += (unsigned int)__ldg(gridI + (gy * pitch + gx));
+      else ad = dadd(ad, (double)__ldg(gridF + (gy * pitch + gx)));
+    }
+    if (FIXED) { a64 += a32; a32 = 0u; }
+    __syncthreads();
+  }
+
+  unsigned long long key = 0ull;
+  if (live) {
+    double sc = ddiv(FIXED ? dmul((double)a64, kFixScale) : ad, J.divisor);    // :659
+    if (J.use_penalty) {
+      const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);             // :728
+      if (!zero) {
+        const double ang = __ldg(J.trig + 3 * ia + 2);
+        const double dx = dsub(x, J.cx), dy = dsub(y, J.cy);
+        double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+        d2 = dmul(d2, J.m2);
+        const double dp = fmax(dsub(1.0, ddiv(dmul(J.gain, d2), J.half_size)), 0.5);
+        const double da = dsub(ang, J.ca);
+        const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, dmul(da, da)), 0.349)), 0.9);
+        sc = dmul(sc, dmul(dp, ap));
+      }
+    }
+    J.score[((long long)ia_l * n_xy + ix) * n_xy + iy] = sc;
+    key = score_key(sc);
+  }
+  key = warp_max_u64(key);
+  if ((tid & 31) == 0) s_wmax[tid >> 5] = key;
+  if (err) atomicOr(J.err, err);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = 0ull;
+    for (int w = 0; w < kThreads / 32; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
+    atomicMax(J.best_key, m);
+  }
+}
+
+}  // namespace flat
+
+int score_flat_ctas(int n_local) { return (n_local + flat::kThreads - 1) / flat::kThreads; }
+
+cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
+  if (fixed) flat::score_flat_kernel<true><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  else flat::score_flat_kernel<false><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
 // staged variant: the grid window of a beam group lives in shared memory, filled by TMA bulk copies
 // =================================================================================================
 // For windows of >= ~48 translations per axis on a fixed-point grid with a unit search step.

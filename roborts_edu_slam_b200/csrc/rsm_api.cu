@@ -315,6 +315,10 @@ TileCfg pick_tile(int n_xy, bool affine_ok) {
     const double cost = padded * (1.0 + alpha / ry) * (1.0 + 4.0 * double(lx + rows) / (double(lx) * rows));
     if (cost < best_cost) { best_cost = cost; best = TileCfg{lx, ry, rows, affine}; }
   }
+  if (const char* e = std::getenv("RSM_RY")) {   // tuning aid: force the rows-per-thread choice
+    const int ry = std::atoi(e);
+    if (ry >= 1 && ry <= 8) best = TileCfg{lx, ry, score_rows(lx, ry), affine};
+  }
   return best;
 }
 

@@ -369,3 +369,52 @@ def test_angle_sliced_match_equals_unsliced(oracle):
     want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
     for r, pose, cov, navg in run_sliced(sc, p, sc.seed_pose, 4):
         assert r == want["response"] and np.array_equal(pose, want["pose"]) and cov_close(cov, want["cov"])
+
+
+def test_staged_shared_memory_variant(ctx, monkeypatch):
+    """The opt-in TMA-staged variant (RSM_STAGED=1) must reproduce the default path bit for bit."""
+    sc = synth.config5(scale=0.25)
+    dg = device_grid(ctx, sc)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    p = sc.passes[0]
+    ref = m.scores(dg, sc.scan_pts, p, sc.seed_pose, 3, 40)
+    monkeypatch.setenv("RSM_STAGED", "1")
+    got = m.scores(dg, sc.scan_pts, p, sc.seed_pose, 3, 40)
+    assert np.array_equal(got, ref)
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    r1 = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+    monkeypatch.delenv("RSM_STAGED")
+    pose2, cov2 = sc.seed_pose.copy(), np.eye(3)
+    r2 = m.ScanMatch(dg, sc.scan_pts, p, pose2, cov2)
+    assert r1 == r2 and np.array_equal(pose, pose2) and np.array_equal(cov, cov2)
+    # a window that touches the grid border: tiles fall back to exact per-thread indices
+    edge = sc.seed_pose.copy()
+    g = sc.grid
+    edge[:2] = [-(g.off_x) + 12.5, -(g.off_y) + 12.5]       # 12.5 m from the grid corner
+    ref = m.scores(dg, sc.scan_pts[:50] * 0.2, p, edge, 0, 6)
+    monkeypatch.setenv("RSM_STAGED", "1")
+    got = m.scores(dg, sc.scan_pts[:50] * 0.2, p, edge, 0, 6)
+    assert np.array_equal(got, ref)
+    dg.close()
+
+
+def test_wide_grid_runtime_pitch(ctx, oracle, rng):
+    """Grids wider than the largest padded pitch (4128 cells) use the run-time stride variants."""
+    g = synth.GridSpec(0.05, 0.15, 4300, 300, 1.0, 1.0)
+    grid = synth.random_grid(rng, g.size_x, g.size_y)
+    dg = matcher.ScanMatchMap.from_spec(ctx, g)
+    dg.upload(grid)
+    assert np.array_equal(dg.download(), grid)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    ang = np.sort(rng.uniform(-np.pi, np.pi, 300))
+    pts = np.stack([np.cos(ang) * rng.uniform(20, 100, 300), np.sin(ang) * rng.uniform(20, 100, 300)], axis=1)
+    pose = np.array([4300 * 0.05 - 12.0, 6.5, 0.4])       # near the right edge, past column 4128
+    for p in (synth.pass_param(1.0, 0.05, 0.2, 0.02, 0.3, 100000, True, 0),
+              synth.pass_param(0.4, 0.02, 0.1, 0.02, 0.3, 100000, True, 1)):
+        so = oracle.scores(grid, g, pts, p, oracle.world_to_map(g, pose))
+        sd = m.scores(dg, pts, p, pose)
+        assert np.array_equal(so, sd)
+        want = oracle.match(grid, g, pts, p, pose)
+        pz, cz = pose.copy(), np.eye(3)
+        assert_pass_equal(m.ScanMatch(dg, pts, p, pz, cz), pz, cz, want)
+    dg.close()

@@ -14,9 +14,12 @@
 // sort would decide, the pass falls back to the *exact* path: the score array is copied back and
 // sorted with the same std::sort call the reference makes, which reproduces its order.
 // There is no CPU scoring path anywhere in this file.
+#include <cuda.h>           // CUtensorMap types only; the encoder is fetched through the runtime
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -182,6 +185,10 @@ struct rsm_ctx {
   bool profiling = false;
   Buf d_work, d_pts, d_flush, d_pool_grids;
   Buf h_up, h_down;  // pinned staging
+  // staged scoring variant: tensor maps of the grids seen so far, keyed by (cells, size, pitch)
+  struct alignas(64) TmapPair { CUtensorMap box[2]; };
+  std::map<std::tuple<const void*, int, int, int>, TmapPair> tmaps;
+  void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<cudaEvent_t> ev_pool;
   struct Span { cudaEvent_t a, b; int kc; };
   std::vector<Span> spans;
@@ -211,6 +218,42 @@ int fail(rsm_ctx* ctx, int code, const char* fmt, ...) {
     ctx->err = buf;
   }
   return code;
+}
+
+// Tensor maps (wide box, tall box) over a fixed-point grid, for the TMA box copies of the staged
+// scoring variant.  Out-of-grid parts of a box are filled with zeros.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, const rsm_ctx::TmapPair** out) {
+  const auto key = std::make_tuple((const void*)g->d_cells, g->size_x, g->size_y, g->pitch);
+  auto it = ctx->tmaps.find(key);
+  if (it != ctx->tmaps.end()) { *out = &it->second; return RSM_OK; }
+  if (!ctx->encode_tiled) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+      return fail(ctx, RSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    ctx->encode_tiled = fn;
+  }
+  if (ctx->tmaps.size() > 8192) ctx->tmaps.clear();
+  rsm_ctx::TmapPair pair;
+  int bw[2], bh[2];
+  score_staged_boxes(bw, bh);
+  for (int b = 0; b < 2; ++b) {
+    const cuuint64_t dims[2] = {cuuint64_t(g->size_x), cuuint64_t(g->size_y)};
+    const cuuint64_t strides[1] = {cuuint64_t(g->pitch) * 4};
+    const cuuint32_t box[2] = {cuuint32_t(bw[b]), cuuint32_t(bh[b])};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        &pair.box[b], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, g->d_cells, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, RSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  }
+  *out = &ctx->tmaps.emplace(key, pair).first->second;
+  return RSM_OK;
 }
 
 #define CU(call)                                                                              \
@@ -448,18 +491,47 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     }
   }
   TileCfg cfg = pick_tile(items[act[0]].geo.n_xy, affine_ok);
-  // staged variant (shared-memory window + TMA): big windows, unit step, fixed-point grids
-  // (measured on B200: the L1 path reaches its load-issue floor, 5.1e12 evaluations/s on the wide
-  //  window, against 3.7e12 for this first staged version, so the staged variant is opt-in)
+  // staged variant (TMA boxes of the grid in shared memory, rsm_score.cu): windows of 48 and more
+  // translations per axis at unit step on fixed-point grids.  Measured on B200 against the L1 path:
+  // 0.224 vs 0.265 ms on config 2, 11.3 vs 13.6 ms on the wide window.  RSM_NO_STAGED=1 turns it off.
   bool use_staged = affine_ok && items[act[0]].geo.factor == 1.0 && items[act[0]].geo.n_xy >= 48 &&
-                    std::getenv("RSM_STAGED") != nullptr;
+                    std::getenv("RSM_NO_STAGED") == nullptr;
   int max_V = 0;
   for (int a = 0; a < na && use_staged; ++a) {
     const PassItem& it = items[act[a]];
     if (!it.grid->fixed || it.geo.visited > 2048 || (it.grid->pitch & 3)) use_staged = false;
     max_V = std::max(max_V, it.geo.visited);
   }
-  if (use_staged) { int tx, ty; score_staged_tile(&tx, &ty); cfg.lx = tx; cfg.rows = ty; cfg.ry = 0; cfg.affine = true; }
+  int n_split = 1, staged_variant = 0;
+  if (use_staged) {
+    int tx, ty;
+    int max_nxy = 0;
+    for (int a = 0; a < na; ++a) max_nxy = std::max(max_nxy, items[act[a]].geo.n_xy);
+    staged_variant = score_staged_variant(max_nxy);
+    score_staged_tile(staged_variant, &tx, &ty);
+    cfg.lx = tx; cfg.rows = ty; cfg.ry = 0; cfg.affine = true;
+    // beams are split over the CTAs of a cluster so that the last wave of CTAs is not mostly empty:
+    // a CTA costs its share of the beams plus a fixed part (job fetch, beam table, pipeline fill)
+    // worth about 25 beams plus its share of the epilogue; pick the split with the smallest
+    // waves x cost, a wave being the CTAs resident at once for that cluster size
+    long long work_items = 0;
+    int min_V = 1 << 30;
+    for (int a = 0; a < na; ++a) {
+      const PassItem& it = items[act[a]];
+      const int t1 = (it.geo.n_xy + tx - 1) / tx, t2 = (it.geo.n_xy + ty - 1) / ty;
+      work_items += (long long)(it.a1 - it.a0) * t1 * t2;
+      min_V = std::min(min_V, it.geo.visited);
+    }
+    const int s_max = std::max(1, std::min(8, min_V / 64));
+    double best_cost = 0.0;
+    for (int sp = 1; sp <= s_max; ++sp) {
+      const int resident = score_staged_resident_ctas(staged_variant, sp, max_V);
+      if (resident <= 0) continue;
+      const long long waves = (work_items * sp + resident - 1) / resident;
+      const double cost = double(waves) * (double(max_V) / sp + 25.0 + 60.0 / sp + (sp > 1 ? 4.0 : 0.0));
+      if (best_cost == 0.0 || cost < best_cost) { best_cost = cost; n_split = sp; }
+    }
+  }
   // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
   bool use_flat = !use_staged && !cfg.affine && std::getenv("RSM_NO_FLAT") == nullptr;
   for (int a = 0; a < na && use_flat; ++a) {
@@ -490,6 +562,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   size_t trig_doubles = 0;
   for (int a = 0; a < na; ++a) { items[act[a]].trig_off = trig_doubles; trig_doubles += size_t(items[act[a]].geo.n_ang) * 3; }
   const size_t o_trig = dl.take(trig_doubles * 8);
+  const size_t o_tmaps = dl.take(use_staged ? size_t(na) * 256 : 0, 128);
   const size_t up_bytes = dl.off;          // everything above is uploaded in one copy
   // zero-initialised block: best keys, err flags, pool counter
   const size_t o_best = dl.take(size_t(na) * 8);
@@ -574,6 +647,14 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.use_penalty = it.param.use_center_penalty ? 1 : 0;
     J.f_int = cfg.affine ? int(g.factor) : 0;
     J.stepoff = J.f_int * it.grid->pitch;
+    J.n_split = n_split;
+    if (use_staged) {
+      const rsm_ctx::TmapPair* tp = nullptr;
+      rc = grid_tmaps(ctx, it.grid, &tp);
+      if (rc) return rc;
+      std::memcpy(up + o_tmaps + size_t(a) * 256, tp, 256);
+      J.tmap = dw + o_tmaps + size_t(a) * 256;
+    }
     J.divisor = double(g.divisor);
     J.sx = g.start_x; J.sy = g.start_y; J.f = g.factor;
     J.cx = g.center[0]; J.cy = g.center[1]; J.ca = g.center[2];
@@ -581,7 +662,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.half_size = it.param.search_space_size / 2;                     // :734
     J.gain = (it.param.type == RSM_COARSE) ? 0.4 : 0.2;               // :588-602, :759-761
     s_cta[a] = cta;
-    cta += use_flat ? score_flat_ctas(int(it.n_local)) : J.ang_count * J.tiles_x * J.tiles_y;
+    cta += use_flat ? score_flat_ctas(int(it.n_local)) : J.ang_count * J.tiles_x * J.tiles_y * (use_staged ? n_split : 1);
     (it.grid->fixed ? any_fixed : any_float) = true;
     SelectJob& L = ljobs[a];
     std::memset(&L, 0, sizeof L);
@@ -617,7 +698,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                              reinterpret_cast<const int*>(dw + o_scta), na));
     else if (use_staged)
-      CU(launch_score_staged(cta, max_V, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+      CU(launch_score_staged(staged_variant, n_split, cta, (max_V + n_split - 1) / n_split, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                              reinterpret_cast<const int*>(dw + o_scta), na));
     else
       CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,

@@ -23,10 +23,16 @@ cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitc
 int score_flat_ctas(int n_local);
 cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 // Staged variant (shared-memory window filled by TMA bulk copies): fixed-point grid, unit search step.
-// A CTA covers score_staged_tile() translations of one angle; max_V = largest visited-beam count.
-void score_staged_tile(int* tile_x, int* tile_y);
-size_t score_staged_smem(int V);
-cudaError_t launch_score_staged(int n_cta, int max_V, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
+// A CTA covers score_staged_tile(variant) translations of one angle and 1/n_split of the beams; the
+// n_split CTAs of a tile are launched as one thread-block cluster and combine their sums through
+// distributed shared memory.  score_staged_variant picks the tile shape for a window size.
+int score_staged_variant(int n_xy);
+void score_staged_tile(int variant, int* tile_x, int* tile_y);
+void score_staged_boxes(int box_w[2], int box_h[2]);   // the two TMA box shapes (cells)
+size_t score_staged_smem(int beams_per_split);
+int score_staged_resident_ctas(int variant, int n_split, int max_beams_per_split);
+cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_beams_per_split, cudaStream_t st,
+                                const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);
 cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);

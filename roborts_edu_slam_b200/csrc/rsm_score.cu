@@ -563,30 +563,44 @@ cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const Scor
 }
 
 // =================================================================================================
-// staged variant: the grid window of a beam group lives in shared memory, filled by TMA bulk copies
+// staged variant: the grid window of a beam round lives in shared memory, filled by TMA bulk copies
 // =================================================================================================
 // For windows of >= ~48 translations per axis on a fixed-point grid with a unit search step.
-// The L1 path above is bound by L1 data-pipe wavefronts: a warp's 32 consecutive cells start at an
-// arbitrary cell, so every gather touches two 128-byte lines.  Shared memory has no such penalty
-// (32 consecutive words are conflict-free at any offset), so here a CTA of 256 threads owns one
-// angle and a tile of (32*RX) x (8*RY) translations, walks the beams in ROUNDS of up to 32
-// consecutive beams whose endpoint boxes fit a SW x HMAX-cell shared-memory tile, and
-//   * warp 0 plans the next round (prefix min/max of the beams' tile-origin cells with warp
-//     shuffles), arms an mbarrier with the byte count and issues one cp.async.bulk (TMA, UBLKCP)
-//     per tile row into the other buffer,
-//   * all 8 warps gather the current round from shared memory: per beam one broadcast load of the
-//     tile-relative base, then RX*RY loads at compile-time offsets and RX*RY/2 three-input adds.
+// The L1 path above is bound by L1 load issue: a warp's 32 consecutive cells start at an arbitrary
+// cell, so every gather touches two 128-byte lines (~1.8 cycles per warp load).  Shared memory has
+// no such penalty (32 consecutive words are conflict-free at any offset: 1 cycle).  Staging only
+// pays if each staged cell is gathered several times, which needs BIG candidate tiles:
+//   * a CTA owns one angle, one 96 x 96 tile of translations (18 candidates per thread in
+//     registers) and one contiguous slice of the beams; 16 compute warps + 1 producer warp;
+//   * the producer walks the slice in ROUNDS of up to 32 consecutive beams whose tile-origin
+//     boxes fit a 20 480-cell buffer (prefix min/max with warp shuffles), publishes the round's
+//     tile-relative bases, arms the buffer's FULL mbarrier with the byte count and issues one
+//     cp.async.bulk (TMA, SASS UBLKCP) per tile row; it runs one round ahead (two buffers) and
+//     re-uses a buffer when the 16 compute warps have arrived on its EMPTY mbarrier;
+//   * compute warps wait on FULL, gather with per-row strides and immediate column offsets
+//     (1 LDS + 0.5 IADD3 per evaluation), arrive on EMPTY -- no block-wide barrier in the loop;
+//   * beams are split over CTAs to fill the machine when a job has few (angle, tile) pairs;
+//     partial sums are integers, so they are combined with 64-bit atomic adds and the last CTA of
+//     an (angle, tile) (atomic ticket) finalises the scores.
 // Per-beam tile origins use the same provable affine index test as the L1 path (tile-wide);
-// beams that fail it or whose tile leaves the grid (a handful per million) are added afterwards
-// with exact per-thread indices read from global memory -- integer sums are order-independent.
+// beams that fail it or whose tile leaves the grid are added afterwards with exact per-thread
+// indices read from global memory -- integer sums are order-independent.
 namespace staged {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = 8;
-constexpr int kSW = 160;                    // shared tile row pitch, cells
-constexpr int kBufCells = 12288;            // 48 KB per buffer
-constexpr int kHMax = kBufCells / kSW;      // 76 rows
+constexpr int kComputeWarps = 16;
+constexpr int kThreads = (kComputeWarps + 1) * 32;   // + 1 producer warp
+constexpr int kBufCells = 20480;            // 80 KB per buffer
+constexpr int kBoxW0 = 160, kBoxH0 = 128;   // the two TMA box shapes (both kBufCells cells): wide and tall
+constexpr int kBoxW1 = 128, kBoxH1 = 160;
 constexpr int kRound = 32;                  // beams per round at most
+#ifdef RSM_STAGED_DEBUG
+__device__ unsigned long long g_dbg[16];
+#define DBG_T() clock64()
+#define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
+#else
+#define DBG_T() 0ll
+#define DBG_ADD(i, v) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -595,41 +609,92 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void tma_row(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(b))
-               : "memory");
+// Polling wait with a sleep between polls: a waiting warp must not take issue slots from the compute
+// warps of its scheduler (measured: a producer spinning on try_wait slowed its four neighbours by 15%).
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, unsigned int sleep_ns) {
+  const uint32_t a = smem_u32(b);
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(sleep_ns);
+  }
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long ld_dsmem_u64(const void* local, int cta_rank) {
+  uint32_t remote;
+  unsigned long long v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(cta_rank));
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(remote) : "memory");
+  return v;
+}
+// One box of the grid (a CUtensorMap built by the host, held in global memory) into shared memory.
+__device__ __forceinline__ void tma_box(void* dst, const void* tmap, int x, int y, uint64_t* b) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(b))
+      : "memory");
+}
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+
+// One round of one compute warp: every beam of the round adds its NX x RY cells to the accumulators.
+// FULL: all RY rows of the warp are inside the window (no row predicate).
+template <int RX, int RY, int NX, bool FULL>
+__device__ __forceinline__ void accumulate_round(unsigned int (&lo)[RX * RY], const int* tile_buf, const int* bases, int n,
+                                                 int sw, int rows) {
+#pragma unroll 2
+  for (int j = 0; j < n; ++j) {
+    const int* q = tile_buf + bases[j];
+    int v[RY][NX];
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry) {
+      const int* qr = q + ry * sw;
+#pragma unroll
+      for (int rx = 0; rx < NX; ++rx) v[ry][rx] = (FULL || ry < rows) ? qr[rx * 32] : 0;
+    }
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < NX; ++rx) lo[ry * RX + rx] += (unsigned int)v[ry][rx];
+  }
 }
 
 template <int RX, int RY>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
-  constexpr int TILE_X = 32 * RX, TILE_Y = kWarps * RY, NC = RX * RY;
-  static_assert(TILE_X + 4 <= kSW && TILE_Y <= kHMax, "a single beam must fit the shared tile");
+  constexpr int TILE_X = 32 * RX, TILE_Y = kComputeWarps * RY, NC = RX * RY;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == kComputeWarps;
+  const long long k0 = DBG_T();
 
   __shared__ ScoreJob J;
   __shared__ int s_job;
-  __shared__ unsigned long long s_wmax[kWarps];
+  __shared__ int s_last;
+  __shared__ unsigned long long s_wmax[kComputeWarps];
   __shared__ double sX[TILE_X], sY[TILE_Y];
   __shared__ int sBase[2][kRound];          // tile-relative cell offset of each beam of the round, -1 = skip
-  __shared__ int sCount[2];                 // beams in the round
-  __shared__ __align__(8) uint64_t sBar[2];
+  __shared__ int sMeta[2][4];               // beams in the round, row pitch, last-round flag
+  __shared__ __align__(8) uint64_t sFull[2], sEmpty[2];
   __shared__ int sUnsafeCount;
-  __shared__ int sUnsafe[64];              // beams that need exact per-thread indices
+  __shared__ int sUnsafe[64];               // beams that need exact per-thread indices
   extern __shared__ __align__(128) unsigned char dyn[];
   int* buf0 = reinterpret_cast<int*>(dyn);
   int* buf1 = buf0 + kBufCells;
-  int2* sBeam = reinterpret_cast<int2*>(buf1 + kBufCells);   // [V] tile-origin cell of every visited beam
+  int2* sBeam = reinterpret_cast<int2*>(buf1 + kBufCells);   // tile-origin cell of every beam of the slice
 
   if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
   __syncthreads();
@@ -639,28 +704,42 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
     for (int i = tid; i < int(sizeof(ScoreJob) / 4); i += kThreads) dst[i] = __ldg(src + i);
   }
   const int first_cta = __ldg(cta_begin + s_job);
-  if (tid == 0) { mbar_init(&sBar[0], 1); mbar_init(&sBar[1], 1); sUnsafeCount = 0; }
+  if (tid == 0) {
+    mbar_init(&sFull[0], 1); mbar_init(&sFull[1], 1);
+    mbar_init(&sEmpty[0], kComputeWarps); mbar_init(&sEmpty[1], kComputeWarps);
+    sUnsafeCount = 0;
+  }
   __syncthreads();
 
+  const int S = J.n_split;
   const int local = blockIdx.x - first_cta;
   const int tiles = J.tiles_x * J.tiles_y;
-  const int ia_local = local / tiles;
-  const int tile = local - ia_local * tiles;
+  const int per_angle = tiles * S;
+  const int ia_local = local / per_angle;
+  const int rem = local - ia_local * per_angle;
+  const int tile = rem / S, split = rem - tile * S;
   const int tx0 = (tile % J.tiles_x) * TILE_X;
   const int ty0 = (tile / J.tiles_x) * TILE_Y;
   const int ia = J.ang_begin + ia_local;
   const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
   const int V = J.V, n_xy = J.n_xy, pitch = J.pitch, size_x = J.size_x, size_y = J.size_y;
+  const int vb = (V + S - 1) / S;
+  const int v_begin = min(V, split * vb), v_end = min(V, v_begin + vb);
+  const int nv = v_end - v_begin;
   const int* __restrict__ grid = reinterpret_cast<const int*>(J.grid);
+  // the part of the tile that is inside the window: whole 32-lane groups in x, single rows in y
+  const int nx_act = min(RX, (n_xy - tx0 + 31) >> 5);
+  const int ext_x = 32 * nx_act, ext_y = min(TILE_Y, n_xy - ty0);
+  const int rows = max(0, min(RY, n_xy - (ty0 + warp * RY)));      // rows of this warp inside the window
 
   for (int i = tid; i < TILE_X + TILE_Y; i += kThreads) {
     if (i < TILE_X) sX[i] = dadd(J.sx, dmul((double)(tx0 + i), J.f));
     else sY[i - TILE_X] = dadd(J.sy, dmul((double)(ty0 + i - TILE_X), J.f));
   }
   __syncthreads();
-  // tile-origin cell of every beam + the affine safety test for the whole tile (see header)
-  for (int v = tid; v < V; v += kThreads) {
-    const int p = v * J.step;
+  // tile-origin cell of every beam of the slice + the affine safety test for the whole tile
+  for (int j = tid; j < nv; j += kThreads) {
+    const int p = (v_begin + j) * J.step;
     const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
     const double lx = dsub(dmul(cs, px), dmul(sn, py));
     const double ly = dadd(dmul(sn, px), dmul(cs, py));
@@ -668,167 +747,304 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
     const int gx0 = __double2int_rz(tx_), gy0 = __double2int_rz(ty_);
     const double fx = tx_ - (double)gx0, fy = ty_ - (double)gy0;
     const bool ok = fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 &&
-                    gx0 >= 0 && gx0 + TILE_X - 1 < size_x && gy0 >= 0 && gy0 + TILE_Y - 1 < size_y;
-    sBeam[v] = ok ? make_int2(gx0, gy0) : make_int2(-1, -1);
-    if (!ok) { const int pos = atomicAdd(&sUnsafeCount, 1); if (pos < 64) sUnsafe[pos] = v; }
+                    gx0 >= 0 && gx0 + ext_x - 1 < size_x && gy0 >= 0 && gy0 + ext_y - 1 < size_y;
+    sBeam[j] = ok ? make_int2(gx0, gy0) : make_int2(-1, -1);
+    if (!ok) { const int pos = atomicAdd(&sUnsafeCount, 1); if (pos < 64) sUnsafe[pos] = j; }
   }
   __syncthreads();
 
-  // ---- round planner (warp 0): beams [b, b + n) into buffer `which` ----------------------------
-  auto plan_round = [&](int b, int which) {
-    const int v = b + lane;
-    int2 e = make_int2(-1, -1);
-    if (v < V) e = sBeam[v];
-    const bool live = v < V, safe = live && e.x >= 0;
-    int xmin = safe ? e.x : 0x7fffffff, xmax = safe ? e.x : -1, ymin = safe ? e.y : 0x7fffffff, ymax = safe ? e.y : -1;
+  // Accumulators: 32-bit sums kept below 2^31 between rounds (a round adds at most 32 * 2^25 = 2^30),
+  // the overflow counted in units of 2^31, four 8-bit counters per register (total < 2^36 for
+  // V <= 2048, so a counter stays below 32).  64-bit accumulators here would cost 36 registers and
+  // leave ptxas no room to keep the 18 shared-memory loads of a beam in flight.
+  unsigned int lo[NC];
+  unsigned int hi[(NC + 3) / 4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {      // inclusive prefix min / max over lanes 0..lane
-      const int a = __shfl_up_sync(0xffffffffu, xmin, o), c = __shfl_up_sync(0xffffffffu, xmax, o);
-      const int d = __shfl_up_sync(0xffffffffu, ymin, o), f = __shfl_up_sync(0xffffffffu, ymax, o);
-      if (lane >= o) { xmin = min(xmin, a); xmax = max(xmax, c); ymin = min(ymin, d); ymax = max(ymax, f); }
-    }
-    const bool any = xmax >= 0;
-    const int xl = xmin & ~3;
-    const int w = any ? ((xmax - xl + TILE_X + 3) & ~3) : 0, h = any ? (ymax - ymin + TILE_Y) : 0;
-    const bool fits = live && w <= kSW && h <= kHMax;
-    const unsigned int vote = __ballot_sync(0xffffffffu, fits);
-    const int n = (vote == 0xffffffffu) ? 32 : (__ffs(~vote) - 1);   // length of the leading run of ones
-    // extents of the chosen prefix live in lane n-1
-    const int src = max(n - 1, 0);
-    const int rxl = __shfl_sync(0xffffffffu, xl, src), ryl = __shfl_sync(0xffffffffu, ymin, src);
-    const int rw = __shfl_sync(0xffffffffu, w, src), rh = __shfl_sync(0xffffffffu, h, src);
-    if (lane < n) sBase[which][lane] = safe ? (e.y - ryl) * kSW + (e.x - rxl) : -1;
-    if (lane == 0) sCount[which] = n;
-    if (n > 0 && rh > 0) {
-      int* dst = which ? buf1 : buf0;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (lane == 0) mbar_expect_tx(&sBar[which], (uint32_t)(rh * rw * 4));
-      __syncwarp();
-      for (int r = lane; r < rh; r += 32)
-        tma_row(dst + r * kSW, grid + ((size_t)(ryl + r) * pitch + rxl), (uint32_t)(rw * 4), &sBar[which]);
-    } else if (lane == 0) {
-      mbar_expect_tx(&sBar[which], 0u);     // nothing to copy: complete the phase right away
-    }
-  };
+  for (int c = 0; c < NC; ++c) lo[c] = 0u;
+#pragma unroll
+  for (int c = 0; c < (NC + 3) / 4; ++c) hi[c] = 0u;
 
-  unsigned int a32[NC];
+  const long long k1 = DBG_T();
+  if (nv > 0) {
+    if (producer) {
+      // ---- producer warp: plan rounds, publish bases, arm FULL, issue one TMA box copy per round ----
+      const char* tmaps = reinterpret_cast<const char*>(J.tmap);
+      if (lane == 0) { tmap_acquire(tmaps); tmap_acquire(tmaps + 128); }
+      __syncwarp();
+      int b = 0;
+      for (int r = 0; b < nv; ++r) {
+        const int which = r & 1;
+        const long long t0 = DBG_T();
+        if (r >= 2) mbar_wait(&sEmpty[which], (uint32_t)(((r >> 1) - 1) & 1), 200);
+        const long long t1 = DBG_T();
+        const int j = b + lane;
+        int2 e = make_int2(-1, -1);
+        if (j < nv) e = sBeam[j];
+        const bool live = j < nv, safe = live && e.x >= 0;
+        int xmin = safe ? e.x : 0x7fffffff, xmax = safe ? e.x : -1, ymin = safe ? e.y : 0x7fffffff, ymax = safe ? e.y : -1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {      // inclusive prefix min / max over lanes 0..lane
+          const int a0 = __shfl_up_sync(0xffffffffu, xmin, o), a1 = __shfl_up_sync(0xffffffffu, xmax, o);
+          const int a2 = __shfl_up_sync(0xffffffffu, ymin, o), a3 = __shfl_up_sync(0xffffffffu, ymax, o);
+          if (lane >= o) { xmin = min(xmin, a0); xmax = max(xmax, a1); ymin = min(ymin, a2); ymax = max(ymax, a3); }
+        }
+        // the longest run of beams whose tile footprints share one box, wide or tall
+        const bool any = xmax >= 0;
+        const int xl = xmin & ~3;   // the inner box coordinate must be a multiple of 16 bytes
+        const int dx = xmax - xl + ext_x, dy = ymax - ymin + ext_y;
+        const bool fit0 = live && (!any || (dx <= kBoxW0 && dy <= kBoxH0));
+        const bool fit1 = live && (!any || (dx <= kBoxW1 && dy <= kBoxH1));
+        const unsigned int vote0 = __ballot_sync(0xffffffffu, fit0), vote1 = __ballot_sync(0xffffffffu, fit1);
+        const int n0 = (vote0 == 0xffffffffu) ? 32 : (__ffs(~vote0) - 1);   // leading run of ones (>= 1: one beam always fits)
+        const int n1 = (vote1 == 0xffffffffu) ? 32 : (__ffs(~vote1) - 1);
+        const bool tall = n1 > n0;
+        const int n = tall ? n1 : n0, rw = tall ? kBoxW1 : kBoxW0;
+        const int srcl = n - 1;
+        const bool rany = __shfl_sync(0xffffffffu, (int)any, srcl) != 0;
+        int rxl = __shfl_sync(0xffffffffu, xl, srcl), ryl = __shfl_sync(0xffffffffu, ymin, srcl);
+        if (!rany) { rxl = 0; ryl = 0; }
+        if (lane < n) sBase[which][lane] = safe ? (e.y - ryl) * rw + (e.x - rxl) : -1;
+        const unsigned int unsafe = __ballot_sync(0xffffffffu, lane < n && !safe);
+        if (lane == 0) { sMeta[which][0] = n; sMeta[which][1] = rw; sMeta[which][2] = (b + n >= nv) ? 1 : 0; sMeta[which][3] = unsafe == 0u; }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        const long long t2 = DBG_T();
+        if (lane == 0) {
+          mbar_expect_tx(&sFull[which], (uint32_t)(kBufCells * 4));
+          tma_box(which ? buf1 : buf0, tmaps + (tall ? 128 : 0), rxl, ryl, &sFull[which]);
+        }
+        b += n;
+#ifdef RSM_STAGED_DEBUG
+        const long long t3 = DBG_T();
+        if (lane == 0) { DBG_ADD(0, 1); DBG_ADD(1, t1 - t0); DBG_ADD(2, t2 - t1); DBG_ADD(3, t3 - t2); DBG_ADD(5, n); DBG_ADD(6, tall); }
+#endif
+      }
+    } else {
+      // ---- compute warps -----------------------------------------------------------------------------
+      for (int r = 0;; ++r) {
+        const int which = r & 1;
+        const long long c0 = DBG_T();
+        mbar_wait(&sFull[which], (uint32_t)((r >> 1) & 1), 40);
+        const long long c1 = DBG_T();
+        const int n = sMeta[which][0], sw = sMeta[which][1], last = sMeta[which][2], all_safe = sMeta[which][3];
+        const int* tile_buf = (which ? buf1 : buf0) + (warp * RY) * sw + lane;
+        const int* bases = sBase[which];
+        if (rows > 0) {
+          if (all_safe && rows == RY) {
+            if (nx_act == RX) accumulate_round<RX, RY, RX, true>(lo, tile_buf, bases, n, sw, rows);
+            else if (RX > 2 && nx_act == 2) accumulate_round<RX, RY, (RX > 2 ? 2 : 1), true>(lo, tile_buf, bases, n, sw, rows);
+            else accumulate_round<RX, RY, 1, true>(lo, tile_buf, bases, n, sw, rows);
+          } else if (all_safe) {
+            // the warp that straddles the window edge in y: same loop, loads predicated per row
+            if (nx_act == RX) accumulate_round<RX, RY, RX, false>(lo, tile_buf, bases, n, sw, rows);
+            else if (RX > 2 && nx_act == 2) accumulate_round<RX, RY, (RX > 2 ? 2 : 1), false>(lo, tile_buf, bases, n, sw, rows);
+            else accumulate_round<RX, RY, 1, false>(lo, tile_buf, bases, n, sw, rows);
+          } else {
+            // a round with a beam that failed the tile-wide index test (rare)
+            for (int j = 0; j < n; ++j) {
+              const int base = bases[j];
+              if (base < 0) continue;
+              const int* q = tile_buf + base;
+#pragma unroll
+              for (int ry = 0; ry < RY; ++ry) {
+                if (ry >= rows) continue;
+                const int* qr = q + ry * sw;
+#pragma unroll
+                for (int rx = 0; rx < RX; ++rx)
+                  if (rx < nx_act) lo[ry * RX + rx] += (unsigned int)qr[rx * 32];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { hi[c >> 2] += (lo[c] >> 31) << (8 * (c & 3)); lo[c] &= 0x7fffffffu; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sEmpty[which]);
+#ifdef RSM_STAGED_DEBUG
+        if (lane == 0 && warp == 0) { DBG_ADD(8, c1 - c0); DBG_ADD(9, DBG_T() - c1); }
+        if (lane == 0 && warp == 15) { DBG_ADD(10, c1 - c0); DBG_ADD(11, DBG_T() - c1); }
+#endif
+        if (last) break;
+      }
+    }
+  }
+  __syncthreads();
+  const long long k2 = DBG_T();
+
   unsigned long long a64[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) { a32[c] = 0u; a64[c] = 0ull; }
-  const int thread_off = (warp * RY) * kSW + lane;
+  for (int c = 0; c < NC; ++c) a64[c] = ((unsigned long long)((hi[c >> 2] >> (8 * (c & 3))) & 0xffu) << 31) + lo[c];
 
-  if (warp == 0 && V > 0) plan_round(0, 0);
-  __syncthreads();
-  int b = 0;
-  for (int r = 0; b < V; ++r) {
-    const int which = r & 1;
-    const int n = sCount[which];
-    if (warp == 0 && b + n < V) plan_round(b + n, which ^ 1);
-    mbar_wait(&sBar[which], (uint32_t)((r >> 1) & 1));
-    const int* tile_buf = (which ? buf1 : buf0) + thread_off;
-#pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-      const int base = sBase[which][j];
-      if (base >= 0) {
-        const int* q = tile_buf + base;
+  int err = 0;
+  if (!producer) {
+    // beams that failed the tile-wide test: exact indices, straight from global memory
+    const int n_unsafe = sUnsafeCount;
+    const int n_slow = n_unsafe <= 64 ? n_unsafe : nv;      // more than the list holds: scan every beam
+    for (int u = 0; u < n_slow; ++u) {
+      const int j = n_unsafe <= 64 ? sUnsafe[u] : u;
+      if (sBeam[j].x >= 0) continue;
+      const int p = (v_begin + j) * J.step;
+      const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+      const double lx = dsub(dmul(cs, px), dmul(sn, py));
+      const double ly = dadd(dmul(sn, px), dmul(cs, py));
+      int gy[RY];
 #pragma unroll
-        for (int ry = 0; ry < RY; ++ry)
+      for (int ry = 0; ry < RY; ++ry) {
+        int g = cell_index(ly, sY[warp * RY + ry]);
+        if (g < 0 || g >= size_y) { if (ty0 + warp * RY + ry < n_xy) err |= kErrWindow; g = max(0, min(g, size_y - 1)); }
+        gy[ry] = g * pitch;
+      }
 #pragma unroll
-          for (int rx = 0; rx < RX; ++rx) a32[ry * RX + rx] += (unsigned int)q[ry * kSW + rx * 32];
+      for (int rx = 0; rx < RX; ++rx) {
+        int g = cell_index(lx, sX[lane + 32 * rx]);
+        if (g < 0 || g >= size_x) { if (tx0 + lane + 32 * rx < n_xy) err |= kErrWindow; g = max(0, min(g, size_x - 1)); }
+#pragma unroll
+        for (int ry = 0; ry < RY; ++ry) a64[ry * RX + rx] += (unsigned int)__ldg(grid + (gy[ry] + g));
       }
     }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) { a64[c] += a32[c]; a32[c] = 0u; }
-    __syncthreads();
-    b += n;
   }
 
-  // beams that failed the tile-wide test: exact indices, straight from global memory
-  int err = 0;
-  const int n_unsafe = sUnsafeCount;
-  const int n_slow = n_unsafe <= 64 ? n_unsafe : V;      // more than the list holds: scan every beam
-  for (int u = 0; u < n_slow; ++u) {
-    const int v = n_unsafe <= 64 ? sUnsafe[u] : u;
-    if (sBeam[v].x >= 0) continue;
-    const int p = v * J.step;
-    const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
-    const double lx = dsub(dmul(cs, px), dmul(sn, py));
-    const double ly = dadd(dmul(sn, px), dmul(cs, py));
-    int gy[RY];
+  // ---- beam splits: the S CTAs of an (angle, tile) form a thread-block cluster.  Every CTA parks its
+  // integer partial sums in its own shared memory; after a cluster barrier CTA k sums accumulator
+  // slots c = k, k + S, ... over all peers through distributed shared memory and finishes those.
+  const long long k_angle = (long long)ia_local * n_xy * n_xy;
+  if (S > 1) {
+    unsigned long long* part = reinterpret_cast<unsigned long long*>(dyn);   // [NC][compute threads], stage buffers are free now
+    if (!producer) {
 #pragma unroll
-    for (int ry = 0; ry < RY; ++ry) {
-      int g = cell_index(ly, sY[warp * RY + ry]);
-      if (g < 0 || g >= size_y) { if (ty0 + warp * RY + ry < n_xy) err |= kErrWindow; g = max(0, min(g, size_y - 1)); }
-      gy[ry] = g * pitch;
+      for (int c = 0; c < NC; ++c) part[c * (kComputeWarps * 32) + tid] = a64[c];
     }
+    cluster_sync();
+    if (!producer) {
 #pragma unroll
-    for (int rx = 0; rx < RX; ++rx) {
-      int g = cell_index(lx, sX[lane + 32 * rx]);
-      if (g < 0 || g >= size_x) { if (tx0 + lane + 32 * rx < n_xy) err |= kErrWindow; g = max(0, min(g, size_x - 1)); }
-#pragma unroll
-      for (int ry = 0; ry < RY; ++ry) a64[ry * RX + rx] += (unsigned int)__ldg(grid + (gy[ry] + g));
+      for (int c = 0; c < NC; ++c) {
+        if (c % S != split) continue;
+        unsigned long long sum = 0ull;
+        for (int peer = 0; peer < S; ++peer) sum += ld_dsmem_u64(&part[c * (kComputeWarps * 32) + tid], peer);
+        a64[c] = sum;
+      }
     }
   }
-
   // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
   unsigned long long kmax = 0ull;
-  const double da = dsub(ang, J.ca);
-  const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, dmul(da, da)), 0.349)), 0.9);
+  if (!producer) {
+    const double da = dsub(ang, J.ca);
+    const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, dmul(da, da)), 0.349)), 0.9);
 #pragma unroll
-  for (int rx = 0; rx < RX; ++rx) {
-    const int ix = tx0 + lane + 32 * rx;
-    if (ix >= n_xy) continue;
-    const double dx = dsub(sX[lane + 32 * rx], J.cx);
-    const double dx2 = dmul(dx, dx);
-    double* out = J.score + ((long long)ia_local * n_xy + ix) * n_xy;
+    for (int rx = 0; rx < RX; ++rx) {
+      const int ix = tx0 + lane + 32 * rx;
+      if (ix >= n_xy) continue;
+      const double dx = dsub(sX[lane + 32 * rx], J.cx);
+      const double dx2 = dmul(dx, dx);
+      double* out = J.score + k_angle + (long long)ix * n_xy;
 #pragma unroll
-    for (int ry = 0; ry < RY; ++ry) {
-      const int iy = ty0 + warp * RY + ry;
-      if (iy >= n_xy) continue;
-      double sc = ddiv(dmul((double)a64[ry * RX + rx], kFixScale), J.divisor);
-      if (J.use_penalty) {
-        const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);
-        if (!zero) {
-          const double dy = dsub(sY[warp * RY + ry], J.cy);
-          double d2 = dadd(dx2, dmul(dy, dy));
-          d2 = dmul(d2, J.m2);
-          const double dp = fmax(dsub(1.0, ddiv(dmul(J.gain, d2), J.half_size)), 0.5);
-          sc = dmul(sc, dmul(dp, ap));
+      for (int ry = 0; ry < RY; ++ry) {
+        const int iy = ty0 + warp * RY + ry;
+        if (iy >= n_xy || (S > 1 && (ry * RX + rx) % S != split)) continue;
+        double sc = ddiv(dmul((double)a64[ry * RX + rx], kFixScale), J.divisor);
+        if (J.use_penalty) {
+          const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);
+          if (!zero) {
+            const double dy = dsub(sY[warp * RY + ry], J.cy);
+            double d2 = dadd(dx2, dmul(dy, dy));
+            d2 = dmul(d2, J.m2);
+            const double dp = fmax(dsub(1.0, ddiv(dmul(J.gain, d2), J.half_size)), 0.5);
+            sc = dmul(sc, dmul(dp, ap));
+          }
         }
+        out[iy] = sc;
+        const unsigned long long k = score_key(sc);
+        kmax = k > kmax ? k : kmax;
       }
-      out[iy] = sc;
-      const unsigned long long k = score_key(sc);
-      kmax = k > kmax ? k : kmax;
     }
+    kmax = warp_max_u64(kmax);
+    if (lane == 0) s_wmax[warp] = kmax;
   }
-  kmax = warp_max_u64(kmax);
-  if (lane == 0) s_wmax[warp] = kmax;
   if (err) atomicOr(J.err, err);
   __syncthreads();
   if (tid == 0) {
     unsigned long long m = 0ull;
-    for (int w = 0; w < kWarps; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
+    for (int w = 0; w < kComputeWarps; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
     atomicMax(J.best_key, m);
+#ifdef RSM_STAGED_DEBUG
+    DBG_ADD(12, 1); DBG_ADD(13, k1 - k0); DBG_ADD(14, k2 - k1); DBG_ADD(15, DBG_T() - k2);
+#endif
   }
+  if (S > 1) cluster_sync();   // peers may still be reading this CTA's partial sums
 }
 
 }  // namespace staged
 
-void score_staged_tile(int* tile_x, int* tile_y) { *tile_x = 96; *tile_y = 32; }
+// Tile shapes of the staged variant: 0 = 96 x 96 candidates per CTA, 1 = 64 x 64.
+int score_staged_variant(int n_xy) { return n_xy > 64 ? 0 : 1; }
 
-size_t score_staged_smem(int V) { return size_t(2 * staged::kBufCells) * 4 + size_t(V) * 8; }
-
-cudaError_t launch_score_staged(int n_cta, int max_V, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
-  auto fn = staged::score_staged_kernel<3, 4>;
-  const size_t smem = score_staged_smem(max_V);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  fn<<<n_cta, staged::kThreads, smem, st>>>(jobs, cta_begin, n_jobs);
-  return cudaGetLastError();
+void score_staged_tile(int variant, int* tile_x, int* tile_y) {
+  *tile_x = variant == 0 ? 96 : 64;
+  *tile_y = staged::kComputeWarps * (variant == 0 ? 6 : 4);
 }
+
+void score_staged_boxes(int box_w[2], int box_h[2]) {
+  box_w[0] = staged::kBoxW0; box_h[0] = staged::kBoxH0;
+  box_w[1] = staged::kBoxW1; box_h[1] = staged::kBoxH1;
+}
+
+size_t score_staged_smem(int beams_per_split) { return size_t(2 * staged::kBufCells) * 4 + size_t(beams_per_split) * 8; }
+
+static void (*staged_fn(int variant))(const ScoreJob*, const int*, int) {
+  return variant == 0 ? staged::score_staged_kernel<3, 6> : staged::score_staged_kernel<2, 4>;
+}
+
+static cudaError_t staged_configure(int variant, size_t smem) {
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[variant]) {
+    cudaError_t e = cudaFuncSetAttribute(staged_fn(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[variant] = smem;
+  }
+  return cudaSuccess;
+}
+
+// CTAs of the staged variant that can be resident at once when launched as clusters of n_split
+// (a cluster lives inside one GPC, so sizes that do not divide the GPC's SM count leave SMs idle).
+int score_staged_resident_ctas(int variant, int n_split, int max_beams_per_split) {
+  static int cache[2][9] = {{0}};
+  if (n_split < 1 || n_split > 8) return 0;
+  if (cache[variant][n_split]) return cache[variant][n_split];
+  const size_t smem = score_staged_smem(max_beams_per_split > 2048 ? max_beams_per_split : 2048);
+  if (staged_configure(variant, smem) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_split * 64); cfg.blockDim = dim3(staged::kThreads); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = n_split; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, staged_fn(variant), &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cache[variant][n_split] = n * n_split;
+  return cache[variant][n_split];
+}
+
+cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_beams_per_split, cudaStream_t st,
+                                const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
+  const size_t smem = score_staged_smem(max_beams_per_split);
+  cudaError_t e = staged_configure(variant, smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_cta); cfg.blockDim = dim3(staged::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = n_split; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, staged_fn(variant), jobs, cta_begin, n_jobs);
+}
+
+#ifdef RSM_STAGED_DEBUG
+extern "C" int rsm_debug_staged(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, staged::g_dbg, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(staged::g_dbg, z, sizeof z); }
+  return 0;
+}
+#endif
 
 }  // namespace rsm

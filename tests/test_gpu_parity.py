@@ -372,29 +372,53 @@ def test_angle_sliced_match_equals_unsliced(oracle):
 
 
 def test_staged_shared_memory_variant(ctx, monkeypatch):
-    """The opt-in TMA-staged variant (RSM_STAGED=1) must reproduce the default path bit for bit."""
+    """The TMA-staged variant (default for wide unit-step windows) and the L1 variant
+    (RSM_NO_STAGED=1) must agree bit for bit."""
     sc = synth.config5(scale=0.25)
     dg = device_grid(ctx, sc)
     m = matcher.BasedCorrelationScanMatch(ctx)
     p = sc.passes[0]
-    ref = m.scores(dg, sc.scan_pts, p, sc.seed_pose, 3, 40)
-    monkeypatch.setenv("RSM_STAGED", "1")
     got = m.scores(dg, sc.scan_pts, p, sc.seed_pose, 3, 40)
-    assert np.array_equal(got, ref)
     pose, cov = sc.seed_pose.copy(), np.eye(3)
     r1 = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
-    monkeypatch.delenv("RSM_STAGED")
+    monkeypatch.setenv("RSM_NO_STAGED", "1")
+    ref = m.scores(dg, sc.scan_pts, p, sc.seed_pose, 3, 40)
+    assert np.array_equal(got, ref)
     pose2, cov2 = sc.seed_pose.copy(), np.eye(3)
     r2 = m.ScanMatch(dg, sc.scan_pts, p, pose2, cov2)
     assert r1 == r2 and np.array_equal(pose, pose2) and np.array_equal(cov, cov2)
-    # a window that touches the grid border: tiles fall back to exact per-thread indices
+    # a window that touches the grid border: beams fall back to exact per-thread indices
     edge = sc.seed_pose.copy()
     g = sc.grid
     edge[:2] = [-(g.off_x) + 12.5, -(g.off_y) + 12.5]       # 12.5 m from the grid corner
     ref = m.scores(dg, sc.scan_pts[:50] * 0.2, p, edge, 0, 6)
-    monkeypatch.setenv("RSM_STAGED", "1")
+    monkeypatch.delenv("RSM_NO_STAGED")
     got = m.scores(dg, sc.scan_pts[:50] * 0.2, p, edge, 0, 6)
     assert np.array_equal(got, ref)
+    dg.close()
+
+
+@pytest.mark.parametrize("n_xy,beams", [(49, 90), (61, 700), (64, 300), (65, 130), (81, 1000), (96, 64), (97, 520), (131, 260)])
+def test_staged_tiles_and_clusters(ctx, oracle, rng, n_xy, beams):
+    """Staged variant against the oracle over window sizes that hit both tile shapes, partial
+    tiles / rows, and beam counts that give cluster sizes from 1 to 8."""
+    g = synth.GridSpec(0.05, 0.15, 700, 600, 3.0, 2.0)
+    grid = synth.random_grid(rng, g.size_x, g.size_y)
+    dg = matcher.ScanMatchMap.from_spec(ctx, g)
+    dg.upload(grid)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    ang = np.sort(rng.uniform(-np.pi, np.pi, beams))
+    rad = rng.uniform(1.0, 7.0, beams)
+    pts = np.stack([np.cos(ang) * rad, np.sin(ang) * rad], axis=1)
+    pose = np.array([700 * 0.05 / 2 - 3.0 + 0.013, 600 * 0.05 / 2 - 2.0 - 0.021, 0.3])
+    p = synth.pass_param((n_xy - 1) * 0.05, 0.05, 0.06, 0.02, 0.3, 100000, True, 0)      # 6 or 7 angles
+    so = oracle.scores(grid, g, pts, p, oracle.world_to_map(g, pose))
+    assert so.size % (n_xy * n_xy) == 0 and so.size // (n_xy * n_xy) in (6, 7)
+    sd = m.scores(dg, pts, p, pose)
+    assert np.array_equal(so, sd)
+    want = oracle.match(grid, g, pts, p, pose)
+    pz, cz = pose.copy(), np.eye(3)
+    assert_pass_equal(m.ScanMatch(dg, pts, p, pz, cz), pz, cz, want)
     dg.close()
 
 

@@ -502,7 +502,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (!it.grid->fixed || it.geo.visited > 2048 || (it.grid->pitch & 3)) use_staged = false;
     max_V = std::max(max_V, it.geo.visited);
   }
-  int n_split = 1, staged_variant = 0;
+  int n_split = 1, staged_variant = 0, split_b = 0;   // split_b: split of the second launch, 0 = one launch
+  long long items_a = 0;                             // (angle, tile) items of the first launch
   if (use_staged) {
     int tx, ty;
     int max_nxy = 0;
@@ -510,10 +511,12 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     staged_variant = score_staged_variant(max_nxy);
     score_staged_tile(staged_variant, &tx, &ty);
     cfg.lx = tx; cfg.rows = ty; cfg.ry = 0; cfg.affine = true;
-    // beams are split over the CTAs of a cluster so that the last wave of CTAs is not mostly empty:
-    // a CTA costs its share of the beams plus a fixed part (job fetch, beam table, pipeline fill)
-    // worth about 25 beams plus its share of the epilogue; pick the split with the smallest
-    // waves x cost, a wave being the CTAs resident at once for that cluster size
+    // Beams are split over the CTAs of a cluster (n_split) so that waves of CTAs are full.  A CTA
+    // costs, in beams: its share of the beams, a fixed part (job fetch, beam table, pipeline fill)
+    // worth about 19, its share of the epilogue (55 / split) and the cluster exchange (10).  A wave
+    // is the CTAs resident at once for that cluster size.  With few waves one split size leaves
+    // the last wave mostly empty, so the angles may be cut in two launches: whole waves at split
+    // A, the remaining angles at a larger split B that fills one more, shorter wave.
     long long work_items = 0;
     int min_V = 1 << 30;
     for (int a = 0; a < na; ++a) {
@@ -523,14 +526,33 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       min_V = std::min(min_V, it.geo.visited);
     }
     const int s_max = std::max(1, std::min(8, min_V / 64));
-    double best_cost = 0.0;
+    int resident[9] = {0};
+    double unit[9] = {0};
     for (int sp = 1; sp <= s_max; ++sp) {
-      const int resident = score_staged_resident_ctas(staged_variant, sp, max_V);
-      if (resident <= 0) continue;
-      const long long waves = (work_items * sp + resident - 1) / resident;
-      const double cost = double(waves) * (double(max_V) / sp + 25.0 + 60.0 / sp + (sp > 1 ? 4.0 : 0.0));
-      if (best_cost == 0.0 || cost < best_cost) { best_cost = cost; n_split = sp; }
+      resident[sp] = score_staged_resident_ctas(staged_variant, sp, max_V);
+      unit[sp] = double(max_V) / sp + 19.0 + 55.0 / sp + (sp > 1 ? 10.0 : 0.0);
     }
+    const bool two_phase_ok = std::getenv("RSM_ONE_PHASE") == nullptr;
+    double best_cost = 0.0;
+    for (int sa = 1; sa <= s_max; ++sa) {
+      if (resident[sa] <= 0) continue;
+      const long long per_wave = resident[sa] / sa;                       // work items per full wave at split sa
+      const long long full = (work_items + per_wave - 1) / per_wave;      // waves if everything runs at split sa
+      const double one = double(full) * unit[sa];
+      if (best_cost == 0.0 || one < best_cost) { best_cost = one; n_split = sa; split_b = 0; items_a = work_items; }
+      if (!two_phase_ok || full < 2 || full > 16) continue;
+      const long long in_a = (full - 1) * per_wave;                        // whole waves at split sa
+      for (int sb = sa + 1; sb <= s_max; ++sb) {
+        if (resident[sb] <= 0) continue;
+        const long long rest = work_items - in_a;
+        const long long waves_b = (rest * sb + resident[sb] - 1) / resident[sb];
+        const double two = double(full - 1) * unit[sa] + double(waves_b) * unit[sb] + 12.0;   // + a launch boundary
+        if (two < best_cost) { best_cost = two; n_split = sa; split_b = sb; items_a = in_a; }
+      }
+    }
+    if (std::getenv("RSM_DEBUG_SPLIT"))
+      std::fprintf(stderr, "[rsm] staged plan: %lld items, split %d for the first %lld, split %d for the rest, cost %.0f\n",
+                   work_items, n_split, items_a, split_b, best_cost);
   }
   // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
   bool use_flat = !use_staged && !cfg.affine && std::getenv("RSM_NO_FLAT") == nullptr;
@@ -555,8 +577,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   std::vector<SelectJob> ljobs(na);
   std::vector<int> l_cta(na + 1, 0);
   Layout dl;   // device work arena
-  const size_t o_sjobs = dl.take(sizeof(ScoreJob) * na);
-  const size_t o_scta = dl.take(sizeof(int) * (na + 1));
+  const size_t o_sjobs = dl.take(sizeof(ScoreJob) * (use_staged ? 2 * size_t(na) : size_t(na)));   // staged: up to two launches
+  const size_t o_scta = dl.take(sizeof(int) * (use_staged ? 2 * (size_t(na) + 1) : size_t(na) + 1));
   const size_t o_ljobs = dl.take(sizeof(SelectJob) * na);
   const size_t o_lcta = dl.take(sizeof(int) * (na + 1));
   size_t trig_doubles = 0;
@@ -683,8 +705,51 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   }
   s_cta[na] = cta; l_cta[na] = total_sel_cta;
   if (any_fixed && any_float) return fail(ctx, RSM_ERR_UNSUPPORTED, "a batch must not mix fixed-point and float32 grids");
-  std::memcpy(up + o_sjobs, sjobs.data(), sizeof(ScoreJob) * na);
-  std::memcpy(up + o_scta, s_cta.data(), sizeof(int) * (na + 1));
+  // staged variant: cut the (job, angle) sequence into the launches of the plan
+  struct StagedLaunch { int split = 1, n_jobs = 0, n_cta = 0, beams = 0; size_t jobs_off = 0, cta_off = 0; };
+  StagedLaunch launches[2];
+  int n_launches = 0;
+  if (use_staged) {
+    std::vector<ScoreJob> pj[2];
+    std::vector<int> pc[2];
+    long long left_a = split_b ? items_a : (long long)1 << 60;
+    for (int a = 0; a < na; ++a) {
+      const ScoreJob& J = sjobs[a];
+      const long long tiles = (long long)J.tiles_x * J.tiles_y;
+      const int ang_a = int(std::min<long long>(J.ang_count, left_a / tiles));
+      left_a -= (long long)ang_a * tiles;
+      if (ang_a < J.ang_count) left_a = 0;             // the cut is one point of the sequence
+      for (int ph = 0; ph < 2; ++ph) {
+        const int first = ph == 0 ? 0 : ang_a, count = ph == 0 ? ang_a : J.ang_count - ang_a;
+        if (count <= 0) continue;
+        ScoreJob K = J;
+        K.ang_begin = J.ang_begin + first; K.ang_count = count;
+        K.score = J.score + (long long)first * J.n_xy * J.n_xy;
+        K.n_split = ph == 0 ? n_split : split_b;
+        pc[ph].push_back(launches[ph].n_cta);
+        launches[ph].n_cta += int(count * tiles) * K.n_split;
+        pj[ph].push_back(K);
+      }
+    }
+    size_t jobs_off = o_sjobs, cta_off = o_scta;
+    for (int ph = 0; ph < 2; ++ph) {
+      if (pj[ph].empty()) continue;
+      StagedLaunch& L = launches[n_launches++];
+      L = launches[ph];
+      L.split = ph == 0 ? n_split : split_b;
+      L.n_jobs = int(pj[ph].size());
+      L.beams = (max_V + L.split - 1) / L.split;
+      pc[ph].push_back(L.n_cta);
+      L.jobs_off = jobs_off; L.cta_off = cta_off;
+      std::memcpy(up + jobs_off, pj[ph].data(), sizeof(ScoreJob) * pj[ph].size());
+      std::memcpy(up + cta_off, pc[ph].data(), sizeof(int) * pc[ph].size());
+      jobs_off += sizeof(ScoreJob) * pj[ph].size();
+      cta_off += sizeof(int) * pc[ph].size();
+    }
+  } else {
+    std::memcpy(up + o_sjobs, sjobs.data(), sizeof(ScoreJob) * na);
+    std::memcpy(up + o_scta, s_cta.data(), sizeof(int) * (na + 1));
+  }
   std::memcpy(up + o_ljobs, ljobs.data(), sizeof(SelectJob) * na);
   std::memcpy(up + o_lcta, l_cta.data(), sizeof(int) * (na + 1));
 
@@ -698,8 +763,12 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                              reinterpret_cast<const int*>(dw + o_scta), na));
     else if (use_staged)
-      CU(launch_score_staged(staged_variant, n_split, cta, (max_V + n_split - 1) / n_split, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
-                             reinterpret_cast<const int*>(dw + o_scta), na));
+      for (int l = 0; l < n_launches; ++l) {
+        const StagedLaunch& L = launches[l];
+        CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, ctx->stream,
+                               reinterpret_cast<const ScoreJob*>(dw + L.jobs_off), reinterpret_cast<const int*>(dw + L.cta_off), L.n_jobs));
+        if (l > 0) ctx->stats.kernel_launches++;
+      }
     else
       CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
                       reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));

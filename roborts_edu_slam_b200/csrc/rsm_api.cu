@@ -596,7 +596,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   int64_t total_cand = 0;
   for (int a = 0; a < na; ++a) {
     PassItem& it = items[act[a]];
-    int ncta = int(std::min<int64_t>(592, (it.n_local + 4095) / 4096));
+    int ncta = int(std::min<int64_t>(592, (it.n_local + kSelectSlice - 1) / kSelectSlice));
     if (ncta < 1) ncta = 1;
     it.sel_cta0 = total_sel_cta; it.sel_ncta = ncta;
     total_sel_cta += ncta;

@@ -71,58 +71,74 @@ __device__ __forceinline__ int find_job(const int* __restrict__ cta_begin, int n
 // Two streaming passes over the keys (visit(i, key) is called once per element during the
 // first), then a rank computation over the few keys that reached the threshold.  Returns the
 // number emitted; *overflow is set when more than kSelectBuf keys reach the threshold (massive ties).
+#ifdef RSM_SELECT_DEBUG
+__device__ unsigned long long g_sel_dbg[16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define SDBG(i) do { if (threadIdx.x == 0) g_sel_dbg[i] = gtime(); } while (0)
+#define SDBG_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_sel_dbg[i], gtime()); } while (0)
+#define SDBG_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_sel_dbg[i], gtime()); } while (0)
+#define SDBG_DUR(i, t0) do { if (threadIdx.x == 0) atomicMax(&g_sel_dbg[i], gtime() - (t0)); } while (0)
+#define SDBG_T() gtime()
+#else
+#define SDBG(i) do {} while (0)
+#define SDBG_MIN(i) do {} while (0)
+#define SDBG_MAX(i) do {} while (0)
+#define SDBG_DUR(i, t0) do {} while (0)
+#define SDBG_T() 0ull
+#endif
 template <typename KeyAt, typename Visit, typename Emit>
 __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit, unsigned long long* s_k,
-                           unsigned long long* s_bkey, unsigned int* s_bidx, int* s_count, bool* overflow) {
+                           unsigned long long* s_bkey, unsigned int* s_bidx, int* s_count, bool* overflow,
+                           unsigned long long* s_cache, unsigned int cache_n) {
   const int tid = threadIdx.x, NT = blockDim.x;
+  constexpr int U = 8;   // independent loads in flight per thread: these passes are pure L2 latency otherwise
   unsigned long long tmax = 0ull;
-  // four independent loads in flight per thread: these passes are pure L2 latency otherwise
-  for (unsigned int i0 = tid; i0 < n; i0 += 4 * NT) {
-    unsigned long long k[4];
+  const unsigned long long d0 = SDBG_T();
+  for (unsigned int i0 = tid; i0 < n; i0 += U * NT) {
+    unsigned long long k[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) k[u] = (i0 + u * NT < n) ? key_at(i0 + u * NT) : 0ull;
+    for (int u = 0; u < U; ++u) k[u] = (i0 + u * NT < n) ? key_at(i0 + u * NT) : 0ull;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (i0 + u * NT < n) {
+        if (i0 + u * NT < cache_n) s_cache[i0 + u * NT] = k[u];   // read back by this same thread in the second pass
         visit(i0 + u * NT, k[u]);
         tmax = k[u] > tmax ? k[u] : tmax;
       }
     }
   }
-  // threshold: every warp pops its 3 largest thread maxima (warp shuffles only); the minimum of
-  // the warps' third-largest values has at least 24 >= kTopK keys at or above it, so it is a
-  // lower bound of the kTopK-th largest key.  Warps with fewer than 3 non-empty threads report 0,
-  // which keeps everything (then n < 256 <= kSelectBuf).
+  // threshold: every warp ranks the high words of its lanes' maxima with shuffles and reports the
+  // kTopK-th largest; the largest report is the threshold.  The lanes' maxima are distinct
+  // elements, so at least kTopK keys are at or above any warp's report (low words cleared): a
+  // lower bound of the kTopK-th largest key, tight enough that only a few dozen keys pass.  Warps
+  // with fewer than kTopK non-empty lanes report 0; if all do, everything is kept (n is small).
   unsigned long long thr = 0ull;
+  __syncthreads();
+  SDBG_DUR(8, d0);
   {
-    unsigned long long mine = tmax, third = 0ull;
     const unsigned int lane = tid & 31;
+    const unsigned int h = (unsigned int)(tmax >> 32);
+    int rank = 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      unsigned long long k = mine;
-      unsigned int t = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, k, o);
-        const unsigned int t2 = __shfl_xor_sync(0xffffffffu, t, o);
-        if (k2 > k || (k2 == k && t2 < t)) { k = k2; t = t2; }
-      }
-      third = k;
-      if (t == lane) mine = 0ull;
+    for (int j = 0; j < 32; ++j) {
+      const unsigned int hj = __shfl_sync(0xffffffffu, h, j);
+      rank += (hj > h || (hj == h && j < (int)lane)) ? 1 : 0;
     }
     __syncthreads();   // previous users of s_k / s_count / the buffer are done
-    if (lane == 0) s_k[tid >> 5] = third;
+    if (rank == kTopK - 1) s_k[tid >> 5] = (unsigned long long)h << 32;
     if (tid == 0) { s_count[0] = 0; s_count[1] = 0; }
     __syncthreads();
-    thr = s_k[0];
-    for (int w = 1; w < (NT >> 5); ++w) thr = s_k[w] < thr ? s_k[w] : thr;
+    for (int w = 0; w < (NT >> 5); ++w) thr = s_k[w] > thr ? s_k[w] : thr;
   }
-  for (unsigned int i0 = tid; i0 < n; i0 += 4 * NT) {
-    unsigned long long k[4];
+  for (unsigned int i0 = tid; i0 < n; i0 += U * NT) {
+    unsigned long long k[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) k[u] = (i0 + u * NT < n) ? key_at(i0 + u * NT) : 0ull;
+    for (int u = 0; u < U; ++u) {
+      const unsigned int i = i0 + u * NT;
+      k[u] = i < n ? (i < cache_n ? s_cache[i] : key_at(i)) : 0ull;
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (k[u] > thr) {
         const int pos = atomicAdd(s_count, 1);
         if (pos < kSelectBuf - kTopK) { s_bkey[pos] = k[u]; s_bidx[pos] = i0 + u * NT; }
@@ -135,6 +151,7 @@ __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit,
     }
   }
   __syncthreads();
+  SDBG_DUR(9, d0);
   int count = s_count[0];
   const int n_eq = min(s_count[1], kTopK);
   if (count > kSelectBuf - kTopK) { *overflow = true; count = kSelectBuf - kTopK; }
@@ -147,7 +164,39 @@ __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit,
   if (tid < n_eq) { s_bkey[count + tid] = kk; s_bidx[count + tid] = ii; }
   __syncthreads();
   count += n_eq;
-  // rank of every buffered key among the buffered keys; ranks < kTopK are the answer
+  if (count <= NT) {
+    // bitonic sort of the buffered (key, index) pairs, one per thread in registers: descending key,
+    // ascending index among equal keys; the first kTopK are the answer.  Exchanges at distances
+    // below 32 are warp shuffles, the others go through shared memory.
+    int N = 32;
+    while (N < count) N <<= 1;
+    unsigned long long k = tid < count ? s_bkey[tid] : 0ull;
+    unsigned int idx = tid < count ? s_bidx[tid] : 0xffffffffu;
+    __syncthreads();
+    for (int kk = 2; kk <= N; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        unsigned long long ok;
+        unsigned int oi;
+        if (j >= 32) {
+          s_bkey[tid] = k; s_bidx[tid] = idx;
+          __syncthreads();
+          ok = s_bkey[tid ^ j]; oi = s_bidx[tid ^ j];
+          __syncthreads();
+        } else {
+          ok = __shfl_xor_sync(0xffffffffu, k, j);
+          oi = __shfl_xor_sync(0xffffffffu, idx, j);
+        }
+        const bool other_first = ok > k || (ok == k && oi < idx);   // the partner's pair sorts before this one
+        const bool lower = (tid & j) == 0, descending_run = (tid & kk) == 0;
+        if ((lower == descending_run) ? other_first : !other_first) { k = ok; idx = oi; }
+      }
+    }
+    if (tid < min(count, kTopK)) emit(tid, k, idx);
+    __syncthreads();
+    SDBG_DUR(10, d0);
+    return min(count, kTopK);
+  }
+  // (massive ties only) rank of every buffered key among the buffered keys; ranks < kTopK are the answer
   for (int i = tid; i < count; i += NT) {
     const unsigned long long ki = s_bkey[i];
     const unsigned int ei = s_bidx[i];
@@ -168,6 +217,10 @@ __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit,
     if (rank < kTopK) emit(rank, ki, ei);
   }
   __syncthreads();
+  SDBG_DUR(10, d0);
+#ifdef RSM_SELECT_DEBUG
+  if (threadIdx.x == 0) atomicMax(&g_sel_dbg[11], (unsigned long long)count);
+#endif
   return min(count, kTopK);
 }
 
@@ -176,16 +229,17 @@ __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit,
 // translation neighbourhood of the best candidate over all angles: those are the same-(x,y)
 // columns the angular covariance needs whenever the averaged best pose stays in that
 // neighbourhood (always when the averaging set has one member).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSelectThreads)
 select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs,
               PoolEntry* __restrict__ pool, int pool_cap, int* __restrict__ pool_count) {
   __shared__ SelectJob J;
   __shared__ int s_job;
-  __shared__ unsigned long long s_k[8];
+  __shared__ unsigned long long s_k[kSelectThreads / 32];
   __shared__ unsigned long long s_bkey[kSelectBuf];
   __shared__ unsigned int s_bidx[kSelectBuf];
   __shared__ int s_count[2];
   __shared__ int s_last;
+  extern __shared__ unsigned long long s_cache[];   // kSelectSlice keys of the first pass, for the second
   const int tid = threadIdx.x, NT = blockDim.x;
 
   if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
@@ -197,11 +251,14 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
   }
   const int cta = blockIdx.x - __ldg(cta_begin + s_job);
   __syncthreads();
+  SDBG_MIN(0); SDBG_MAX(1);
 
   const long long lo = (long long)cta * J.slice;
   const long long hi = min(J.n, lo + J.slice);
   const unsigned int n_slice = hi > lo ? (unsigned int)(hi - lo) : 0u;
   const double best = key_score(*J.best_key);
+  // keys below this cannot be within 1e-2 of the best score: skips the FP64 test for almost all
+  const unsigned long long near_floor = score_key(dsub(best, 0.0101));
   const double* __restrict__ sc = J.score + lo;
 
   bool overflow = false;
@@ -210,6 +267,7 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
       n_slice, [&](unsigned int i) { return score_key(sc[i]); },
       [&](unsigned int i, unsigned long long key) {
         // averaging-set candidates: DoubleEqual(score, best, 1e-2)   (:685)
+        if (key < near_floor) return;
         const double s = key_score(key);
         const double delta = dsub(s, best);
         const bool near_best = delta < 0.0 ? (delta >= -1e-2) : (delta <= 1e-2);
@@ -220,11 +278,12 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
         }
       },
       [&](int r, unsigned long long key, unsigned int i) { Entry e; e.score = key_score(key); e.index = lo + i; my_list[r] = e; },
-      s_k, s_bkey, s_bidx, s_count, &overflow);
+      s_k, s_bkey, s_bidx, s_count, &overflow, s_cache, kSelectSlice);
   // unused slots get a score whose key is 0 so that the merge needs no per-list count
   for (int r = emitted + tid; r < kTopK; r += NT) { Entry e; e.score = __longlong_as_double(-1ll); e.index = -1; my_list[r] = e; }
   __threadfence();     // every thread's list entries are visible device-wide before the ticket
   __syncthreads();
+  SDBG_MIN(2); SDBG_MAX(3);
   if (tid == 0) {
     J.top_count[cta] = emitted;
     if (overflow) atomicOr(J.err, kErrSelectFull);
@@ -234,6 +293,7 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  SDBG(4);
 
   // ---- last CTA of the job: merge the per-CTA lists ------------------------------------------
   const unsigned int n_ent = (unsigned int)J.n_cta * kTopK;
@@ -244,12 +304,13 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
       [&](unsigned int i) -> unsigned long long { return score_key(ent[i].score); },
       [](unsigned int, unsigned long long) {},
       [&](int r, unsigned long long, unsigned int i) { J.final_top[r] = ent[i]; },
-      s_k, s_bkey, s_bidx, s_count, &overflow);
+      s_k, s_bkey, s_bidx, s_count, &overflow, s_cache, kSelectSlice);
   if (tid == 0) {
     *J.final_count = n_final;
     if (overflow) atomicOr(J.err, kErrSelectFull);
   }
   __syncthreads();
+  SDBG(5);
   // ---- speculative gather of the best candidate's 3x3 translation neighbourhood -------------------
   if (n_final > 0 && J.spec_out != nullptr) {
     const long long kbest = J.final_top[0].index;       // written by thread 0 above, visible after the barrier
@@ -262,19 +323,47 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
     if (tid == 0) J.spec_cols[0] = ncol;
     if (tid < ncol) J.spec_cols[1 + tid] = (x0 + tid / ny) * n_xy + (y0 + tid % ny);
     const int nang = J.n_ang;
-    for (int i = tid; i < ncol * nang; i += NT) {
-      const int c = i / nang, ia = i - c * nang;
-      const int col = (x0 + c / ny) * n_xy + (y0 + c % ny);
-      J.spec_out[i] = J.score[(long long)ia * plane + col];
+    for (int i0 = tid; i0 < ncol * nang; i0 += 4 * NT) {      // 4 independent loads in flight
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NT;
+        if (i < ncol * nang) {
+          const int c = i / nang, ia = i - c * nang;
+          const int col = (x0 + c / ny) * n_xy + (y0 + c % ny);
+          v[u] = J.score[(long long)ia * plane + col];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * NT < ncol * nang) J.spec_out[i0 + u * NT] = v[u];
     }
   } else if (tid == 0 && J.spec_cols != nullptr) {
     J.spec_cols[0] = 0;
   }
+  __syncthreads();
+  SDBG(6);
 }
+#ifdef RSM_SELECT_DEBUG
+extern "C" int rsm_debug_select(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_sel_dbg, sizeof(unsigned long long) * 16);
+  unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = (i == 0 || i == 2) ? ~0ull : 0ull;
+  cudaMemcpyToSymbol(g_sel_dbg, z, sizeof z);
+  return 0;
+}
+#endif
 
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count) {
-  select_kernel<<<n_cta, 256, 0, st>>>(jobs, cta_begin, n_jobs, pool, pool_cap, pool_count);
+  const size_t smem = size_t(kSelectSlice) * 8;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  select_kernel<<<n_cta, kSelectThreads, smem, st>>>(jobs, cta_begin, n_jobs, pool, pool_cap, pool_count);
   return cudaGetLastError();
 }
 

@@ -594,7 +594,7 @@ constexpr int kBoxW0 = 160, kBoxH0 = 128;   // the two TMA box shapes (both kBuf
 constexpr int kBoxW1 = 128, kBoxH1 = 160;
 constexpr int kRound = 32;                  // beams per round at most
 #ifdef RSM_STAGED_DEBUG
-__device__ unsigned long long g_dbg[16];
+__device__ unsigned long long g_dbg[32];
 #define DBG_T() clock64()
 #define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
 #else
@@ -925,6 +925,7 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
       }
     }
   }
+  const long long k3 = DBG_T();
   // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
   unsigned long long kmax = 0ull;
   if (!producer) {
@@ -962,12 +963,13 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
   }
   if (err) atomicOr(J.err, err);
   __syncthreads();
+  const long long k4 = DBG_T();
   if (tid == 0) {
     unsigned long long m = 0ull;
     for (int w = 0; w < kComputeWarps; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
     atomicMax(J.best_key, m);
 #ifdef RSM_STAGED_DEBUG
-    DBG_ADD(12, 1); DBG_ADD(13, k1 - k0); DBG_ADD(14, k2 - k1); DBG_ADD(15, DBG_T() - k2);
+    { const int o = S > 1 ? 24 : 12; DBG_ADD(o, 1); DBG_ADD(o + 1, k1 - k0); DBG_ADD(o + 2, k2 - k1); DBG_ADD(o + 3, k3 - k2); DBG_ADD(o + 4, k4 - k3); DBG_ADD(o + 5, DBG_T() - k4); }
 #endif
   }
   if (S > 1) cluster_sync();   // peers may still be reading this CTA's partial sums
@@ -1041,8 +1043,8 @@ cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_bea
 #ifdef RSM_STAGED_DEBUG
 extern "C" int rsm_debug_staged(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, staged::g_dbg, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(staged::g_dbg, z, sizeof z); }
+  cudaMemcpyFromSymbol(out, staged::g_dbg, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(staged::g_dbg, z, sizeof z); }
   return 0;
 }
 #endif

@@ -6,7 +6,7 @@ from roborts_edu_slam_b200 import synth, matcher
 ctx = matcher.Context(0)
 m = matcher.BasedCorrelationScanMatch(ctx)
 lib = ctypes.CDLL(matcher.LIB_PATH)
-out = (ctypes.c_ulonglong * 16)()
+out = (ctypes.c_ulonglong * 32)()
 for name, sc in (("cfg5/4", synth.config5(scale=0.25)), ("cfg2", synth.config2()), ("cfg5", synth.config5())):
     g = sc.grid
     grid = matcher.ScanMatchMap.from_spec(ctx, g)
@@ -18,7 +18,9 @@ for name, sc in (("cfg5/4", synth.config5(scale=0.25)), ("cfg2", synth.config2()
     lib.rsm_debug_staged(out, 1)
     v = list(out)
     r = max(v[0], 1)
-    c = max(v[12], 1)
-    print(name, "rounds", v[0], "per round: empty-wait %.0f plan %.0f issue %.0f beams %.1f tall %.2f | w0 full-wait %.0f compute %.0f | w15 full-wait %.0f compute %.0f | finishing CTAs %d: prologue %.0f loop %.0f epilogue %.0f" % (
-        v[1]/r, v[2]/r, v[3]/r, v[5]/r, v[6]/r, v[8]/r, v[9]/r, v[10]/r, v[11]/r, v[12], v[13]/c, v[14]/c, v[15]/c), flush=True)
+    print(name, "rounds", v[0], "per round: empty-wait %.0f plan %.0f issue %.0f beams %.1f tall %.2f | w0 full-wait %.0f compute %.0f | w15 full-wait %.0f compute %.0f" % (
+        v[1]/r, v[2]/r, v[3]/r, v[5]/r, v[6]/r, v[8]/r, v[9]/r, v[10]/r, v[11]/r), flush=True)
+    for o, what in ((12, "unsplit"), (24, "cluster")):
+        c = max(v[o], 1)
+        print("   %s CTAs %d: prologue %.0f loop %.0f combine %.0f epilogue %.0f tail %.0f" % (what, v[o], v[o+1]/c, v[o+2]/c, v[o+3]/c, v[o+4]/c, v[o+5]/c), flush=True)
     grid.close(); scan.close()

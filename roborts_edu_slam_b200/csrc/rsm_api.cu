@@ -179,6 +179,8 @@ struct rsm_ctx {
   HostPool pool;
   SliceState slice;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                 // second staged scoring launch, concurrent with the first
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::string err;
   rsm_stats stats;
@@ -762,14 +764,25 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (use_flat)
       CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                              reinterpret_cast<const int*>(dw + o_scta), na));
-    else if (use_staged)
+    else if (use_staged) {
+      // the launches cover disjoint angles: the second one goes to a side stream so that its
+      // clusters take SMs as soon as CTAs of the first retire (no kernel-boundary drain between them)
+      const bool fork = n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
+      if (fork) {
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+      }
       for (int l = 0; l < n_launches; ++l) {
         const StagedLaunch& L = launches[l];
-        CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, ctx->stream,
+        CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, (fork && l == 1) ? ctx->stream2 : ctx->stream,
                                reinterpret_cast<const ScoreJob*>(dw + L.jobs_off), reinterpret_cast<const int*>(dw + L.cta_off), L.n_jobs));
         if (l > 0) ctx->stats.kernel_launches++;
       }
-    else
+      if (fork) {
+        CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      }
+    } else
       CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
                       reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
   }
@@ -1096,6 +1109,9 @@ int rsm_create(int device, rsm_ctx** out) {
   std::memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->t0) != cudaSuccess || cudaEventCreate(&ctx->t1) != cudaSuccess) {
     delete ctx;
     return RSM_ERR_CUDA;
@@ -1114,6 +1130,8 @@ void rsm_destroy(rsm_ctx* ctx) {
   if (ctx->h_down.p) cudaFreeHost(ctx->h_down.p);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
+  cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+  cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -29,7 +29,8 @@ constexpr int kTopK = 21;          // top-20 covariance prefix + 1 to detect a t
 constexpr int kChunk = 32;         // beams per shared-memory table chunk of the scoring kernel
 constexpr int kSelectBuf = 2048;
 constexpr int kSelectThreads = 512;   // select_kernel CTA size
-constexpr int kSelectSlice = 8192;    // candidates per select CTA (at least)   // per-CTA candidate buffer of the selection kernel
+constexpr int kSelectSlice = 8192;    // candidates per select CTA (at least); a multiple of 8 * kSelectThreads
+static_assert(kSelectSlice % (8 * kSelectThreads) == 0, "block_top_k caches whole iterations");   // per-CTA candidate buffer of the selection kernel
 constexpr int kMaxCols = 9;        // same-(x,y) columns gathered for the angular covariance
 
 enum ErrBits {

@@ -101,7 +101,7 @@ __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit,
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i0 + u * NT < n) {
-        if (i0 + u * NT < cache_n) s_cache[i0 + u * NT] = k[u];   // read back by this same thread in the second pass
+        if (i0 < cache_n) s_cache[i0 + u * NT] = k[u];   // read back by this same thread in the second pass
         visit(i0 + u * NT, k[u]);
         tmax = k[u] > tmax ? k[u] : tmax;
       }
@@ -132,10 +132,12 @@ __device__ int block_top_k(unsigned int n, KeyAt key_at, Visit visit, Emit emit,
   }
   for (unsigned int i0 = tid; i0 < n; i0 += U * NT) {
     unsigned long long k[U];
+    if (i0 < cache_n) {      // cache_n is a multiple of U * NT: an iteration is cached as a whole or not at all
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned int i = i0 + u * NT;
-      k[u] = i < n ? (i < cache_n ? s_cache[i] : key_at(i)) : 0ull;
+      for (int u = 0; u < U; ++u) k[u] = (i0 + u * NT < n) ? s_cache[i0 + u * NT] : 0ull;
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) k[u] = (i0 + u * NT < n) ? key_at(i0 + u * NT) : 0ull;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

@@ -191,6 +191,10 @@ struct rsm_ctx {
   struct alignas(64) TmapPair { CUtensorMap box[2]; };
   std::map<std::tuple<const void*, int, int, int>, TmapPair> tmaps;
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
+  // CUDA graphs of whole passes (upload, zeroing, score launches, select, read-back), keyed by
+  // everything that shapes the launch sequence; the per-call data travels in the pinned buffer
+  struct PassGraph { int seen = 0; cudaGraphExec_t exec = nullptr; };
+  std::map<std::vector<long long>, PassGraph> graphs;
   std::vector<cudaEvent_t> ev_pool;
   struct Span { cudaEvent_t a, b; int kc; };
   std::vector<Span> spans;
@@ -756,40 +760,59 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   std::memcpy(up + o_lcta, l_cta.data(), sizeof(int) * (na + 1));
 
   // ---- launch --------------------------------------------------------------------------------
-  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  char* dn = ctx->h_down.p;
+  const size_t head_bytes = o_pool - o_best;
+  const int pool_first = std::min(pool_cap, std::max(4096, na * 8));
+  const bool fork = use_staged && n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
+  auto enqueue_score = [&]() -> int {
+    CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
+    {
+      Prof p(ctx, KC_SCORE);
+      if (use_flat)
+        CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+                               reinterpret_cast<const int*>(dw + o_scta), na));
+      else if (use_staged) {
+        // the launches cover disjoint angles: the second one goes to a side stream so that its
+        // clusters take SMs as soon as CTAs of the first retire (no kernel-boundary drain between them)
+              if (fork) {
+          CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+          CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        }
+        for (int l = 0; l < n_launches; ++l) {
+          const StagedLaunch& L = launches[l];
+          CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, (fork && l == 1) ? ctx->stream2 : ctx->stream,
+                                 reinterpret_cast<const ScoreJob*>(dw + L.jobs_off), reinterpret_cast<const int*>(dw + L.cta_off), L.n_jobs));
+        }
+        if (fork) {
+          CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+          CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        }
+      } else
+        CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
+                        reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
+    }
+    return RSM_OK;
+  };
+  auto enqueue_tail = [&]() -> int {
+    {
+      Prof p(ctx, KC_SELECT);
+      CU(launch_select(total_sel_cta, ctx->stream, reinterpret_cast<const SelectJob*>(dw + o_ljobs),
+                       reinterpret_cast<const int*>(dw + o_lcta), na, reinterpret_cast<PoolEntry*>(dw + o_pool),
+                       pool_cap, reinterpret_cast<int*>(dw + o_poolcnt)));
+    }
+    // read back everything up to the pool, plus a first slice of the pool
+    CU(cudaMemcpyAsync(dn, dw + o_best, head_bytes + size_t(pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, ctx->stream));
+    return RSM_OK;
+  };
   ctx->stats.h2d_bytes += up_bytes;
-  CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
-  {
-    Prof p(ctx, KC_SCORE);
-    if (use_flat)
-      CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
-                             reinterpret_cast<const int*>(dw + o_scta), na));
-    else if (use_staged) {
-      // the launches cover disjoint angles: the second one goes to a side stream so that its
-      // clusters take SMs as soon as CTAs of the first retire (no kernel-boundary drain between them)
-      const bool fork = n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
-      if (fork) {
-        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-      }
-      for (int l = 0; l < n_launches; ++l) {
-        const StagedLaunch& L = launches[l];
-        CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, (fork && l == 1) ? ctx->stream2 : ctx->stream,
-                               reinterpret_cast<const ScoreJob*>(dw + L.jobs_off), reinterpret_cast<const int*>(dw + L.cta_off), L.n_jobs));
-        if (l > 0) ctx->stats.kernel_launches++;
-      }
-      if (fork) {
-        CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-      }
-    } else
-      CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
-                      reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
-  }
-  ctx->stats.kernel_launches++; ctx->stats.score_launches++;
+  ctx->stats.kernel_launches += use_staged ? n_launches : 1;
+  ctx->stats.score_launches++;
 
   if (mode == MODE_SCORES) {
     // parity/debug: hand the raw score array of item 0 back
+    rc = enqueue_score();
+    if (rc) return rc;
     PassItem& it = items[act[0]];
     if (it.n_local > scores_cap) return fail(ctx, RSM_ERR_INVALID, "scores_out too small: need %lld", (long long)it.n_local);
     CU(cudaMemcpyAsync(scores_out, dw + o_score + it.score_off * 8, size_t(it.n_local) * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -803,19 +826,50 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     return RSM_OK;
   }
 
-  {
-    Prof p(ctx, KC_SELECT);
-    CU(launch_select(total_sel_cta, ctx->stream, reinterpret_cast<const SelectJob*>(dw + o_ljobs),
-                     reinterpret_cast<const int*>(dw + o_lcta), na, reinterpret_cast<PoolEntry*>(dw + o_pool),
-                     pool_cap, reinterpret_cast<int*>(dw + o_poolcnt)));
+  // A whole pass replayed as one CUDA graph once its shape has been seen twice: one launch call
+  // instead of a copy, a memset, up to three kernels, two event pairs and a read-back.
+  bool launched = false;
+  // (single matches only: that is where the launch sequence is a visible share of the call; a
+  //  batch enqueues its few long kernels well ahead of the GPU anyway)
+  if (!ctx->profiling && na <= 8 && std::getenv("RSM_NO_GRAPH") == nullptr) {
+    std::vector<long long> key = {(long long)(intptr_t)dw, (long long)(intptr_t)up, (long long)(intptr_t)dn, (long long)up_bytes,
+                                  (long long)o_best, (long long)zero_end, use_flat, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
+                                  const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
+                                  total_sel_cta, (long long)o_ljobs, (long long)o_lcta, (long long)o_pool, pool_cap,
+                                  (long long)o_poolcnt, (long long)head_bytes, pool_first};
+    for (int l = 0; l < n_launches; ++l) {
+      const StagedLaunch& L = launches[l];
+      key.insert(key.end(), {L.split, L.n_cta, L.beams, (long long)L.jobs_off, (long long)L.cta_off, L.n_jobs});
+    }
+    if (ctx->graphs.size() > 64) {
+      for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+      ctx->graphs.clear();
+    }
+    rsm_ctx::PassGraph& G = ctx->graphs[key];
+    if (!G.exec && ++G.seen == 2 && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int r = enqueue_score();
+      if (r == RSM_OK) r = enqueue_tail();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (r != RSM_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
+        G.exec = nullptr;
+        cudaGetLastError();
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (G.exec) {
+      CU(cudaGraphLaunch(G.exec, ctx->stream));
+      launched = true;
+    }
+  }
+  if (!launched) {
+    rc = enqueue_score();
+    if (rc) return rc;
+    rc = enqueue_tail();
+    if (rc) return rc;
   }
   ctx->stats.kernel_launches++;
   pt.lap(0);
-  // read back everything up to the pool, plus a first slice of the pool
-  char* dn = ctx->h_down.p;
-  const size_t head_bytes = o_pool - o_best;
-  const int pool_first = std::min(pool_cap, std::max(4096, na * 8));
-  CU(cudaMemcpyAsync(dn, dw + o_best, head_bytes + size_t(pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, ctx->stream));
   rc = sync_stream(ctx);
   if (rc) return rc;
   ctx->stats.d2h_bytes += head_bytes + size_t(pool_first) * sizeof(PoolEntry);
@@ -1128,6 +1182,7 @@ void rsm_destroy(rsm_ctx* ctx) {
   for (Buf* b : dev) if (b->p) cudaFree(b->p);
   if (ctx->h_up.p) cudaFreeHost(ctx->h_up.p);
   if (ctx->h_down.p) cudaFreeHost(ctx->h_down.p);
+  for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
   cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);

@@ -456,7 +456,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_value["kernel_launches"]),
-            "roofline": {"bound": "smem", "kernel": "score_kernel", "achieved": achieved, "peak": smem_row, "unit": "GB/s",
+            "roofline": {"bound": "smem", "kernel": "staged::score_staged_kernel<3,6> (all score launches of a step: 148 unsplit CTAs + 132 CTAs as clusters of 4)",
+                         "achieved": achieved, "peak": smem_row, "unit": "GB/s",
                          "frac": achieved / smem_row, "traffic": traffic,
                          "kernel_ms": k_ms, "evals_per_s_kernel": evals_step / (k_ms * 1e-3),
                          "peak_source": "rsm_microbench_gather mode 0 (shared-memory row segments) measured in this run",

@@ -226,6 +226,18 @@ int fail(rsm_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+// Every entry point makes the context's device current for the calling thread (a new host thread
+// starts on device 0) and puts the caller's device back on return.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const rsm_ctx* ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != ctx->device) cudaSetDevice(ctx->device); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // Tensor maps (wide box, tall box) over a fixed-point grid, for the TMA box copies of the staged
 // scoring variant.  Out-of-grid parts of a box are filled with zeros.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1196,14 +1208,16 @@ const char* rsm_last_error(const rsm_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int rsm_set_profiling(rsm_ctx* ctx, int on) { if (!ctx) return RSM_ERR_INVALID; ctx->profiling = on != 0; return RSM_OK; }
 int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out) { if (!ctx || !out) return RSM_ERR_INVALID; *out = ctx->stats; return RSM_OK; }
 int rsm_reset_stats(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; std::memset(&ctx->stats, 0, sizeof ctx->stats); return RSM_OK; }
-int rsm_synchronize(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; return sync_stream(ctx); }
+int rsm_synchronize(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; DeviceGuard device_guard(ctx); return sync_stream(ctx); }
 
 int rsm_timer_start(rsm_ctx* ctx) {
+  DeviceGuard device_guard(ctx);
   if (!ctx) return RSM_ERR_INVALID;
   CU(cudaEventRecord(ctx->t0, ctx->stream));
   return RSM_OK;
 }
 int rsm_timer_stop(rsm_ctx* ctx, double* elapsed_ms) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !elapsed_ms) return RSM_ERR_INVALID;
   CU(cudaEventRecord(ctx->t1, ctx->stream));
   CU(cudaEventSynchronize(ctx->t1));
@@ -1214,6 +1228,7 @@ int rsm_timer_stop(rsm_ctx* ctx, double* elapsed_ms) {
 }
 
 int rsm_flush_l2(rsm_ctx* ctx) {
+  DeviceGuard device_guard(ctx);
   if (!ctx) return RSM_ERR_INVALID;
   const size_t bytes = size_t(256) << 20;
   int rc = ensure_dev(ctx, ctx->d_flush, bytes);
@@ -1231,6 +1246,7 @@ int rsm_grid_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, dou
 }
 
 int rsm_grid_create_from_scale(rsm_ctx* ctx, int size_x, int size_y, double scale_factor, double offset_x, double offset_y, rsm_grid** out) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !out || size_x <= 0 || size_y <= 0 || size_x > 32768 || size_y > 32768 || !(scale_factor > 0))
     return fail(ctx, RSM_ERR_INVALID, "rsm_grid_create: bad arguments");
   rsm_grid* g = new rsm_grid;
@@ -1248,6 +1264,7 @@ int rsm_grid_create_from_scale(rsm_ctx* ctx, int size_x, int size_y, double scal
 }
 
 void rsm_grid_destroy(rsm_ctx* ctx, rsm_grid* grid) {
+  DeviceGuard device_guard(ctx);
   if (!grid) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   if (grid->owned && grid->d_cells) cudaFree(grid->d_cells);
@@ -1262,6 +1279,7 @@ int rsm_grid_set_offset(rsm_ctx* ctx, rsm_grid* grid, double offset_x, double of
 }
 
 int rsm_grid_upload_f32(rsm_ctx* ctx, rsm_grid* grid, const float* prob) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !prob) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_upload_f32: null argument");
   const size_t n = size_t(grid->size_x) * grid->size_y;
   int rc = ensure_pinned(ctx, ctx->h_up, n * 4);
@@ -1281,6 +1299,7 @@ int rsm_grid_upload_f32(rsm_ctx* ctx, rsm_grid* grid, const float* prob) {
 }
 
 int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !prob_out) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_download_f32: null argument");
   const size_t n = size_t(grid->size_x) * grid->size_y;
   int rc = ensure_pinned(ctx, ctx->h_down, n * 4);
@@ -1384,6 +1403,7 @@ extern "C" {
 
 int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double sigma, double occu_offset, int use_blur,
                        int n_scans, const int32_t* n_pts, const double* pts_xy, const double* poses_world) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || n_scans < 0 || (n_scans > 0 && (!n_pts || !pts_xy || !poses_world)))
     return fail(ctx, RSM_ERR_INVALID, "rsm_grid_rasterize: bad arguments");
   RasterPlan pl;
@@ -1432,6 +1452,7 @@ int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double 
 // ---- matching ----------------------------------------------------------------------------------
 int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
               double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !param || !pose_world || !cov || !response || n_pts < 0 || (n_pts > 0 && !pts_xy))
     return fail(ctx, RSM_ERR_INVALID, "rsm_match: bad arguments");
   *response = 0.0;
@@ -1453,6 +1474,7 @@ int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pt
 int rsm_match_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
                   const double center_map[3], double cov[9], double* response, double best_map_out[3],
                   rsm_pass_detail* detail) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !param || !center_map || !cov || !response || !best_map_out || n_pts < 0 || (n_pts > 0 && !pts_xy))
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_map: bad arguments");
   *response = 0.0;
@@ -1474,6 +1496,7 @@ int rsm_match_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int 
 }
 
 int rsm_scan_create(rsm_ctx* ctx, const double* pts_xy, int n_pts, rsm_scan** out) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !out || n_pts < 0 || (n_pts > 0 && !pts_xy)) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_create: bad arguments");
   rsm_scan* s = new rsm_scan;
   s->n = n_pts;
@@ -1490,6 +1513,7 @@ int rsm_scan_create(rsm_ctx* ctx, const double* pts_xy, int n_pts, rsm_scan** ou
 }
 
 void rsm_scan_destroy(rsm_ctx* ctx, rsm_scan* scan) {
+  DeviceGuard device_guard(ctx);
   if (!scan) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   if (scan->d_pts) cudaFree(scan->d_pts);
@@ -1498,6 +1522,7 @@ void rsm_scan_destroy(rsm_ctx* ctx, rsm_scan* scan) {
 
 int rsm_match_resident(rsm_ctx* ctx, const rsm_grid* grid, const rsm_scan* scan, const rsm_pass_param* param,
                        double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !scan || !param || !pose_world || !cov || !response)
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_resident: bad arguments");
   *response = 0.0;
@@ -1514,6 +1539,7 @@ int rsm_match_resident(rsm_ctx* ctx, const rsm_grid* grid, const rsm_scan* scan,
 }
 
 int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int iters, double* gbps) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !gbps || mode < 0 || mode > 3 || footprint_bytes < 1024 || iters < 4)
     return fail(ctx, RSM_ERR_INVALID, "rsm_microbench_gather: bad arguments");
   if (mode < 2 && footprint_bytes > 200 * 1024) return fail(ctx, RSM_ERR_INVALID, "shared-memory tile must be <= 200 KB");
@@ -1543,6 +1569,7 @@ int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int i
 
 int rsm_match_chain(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param params[3],
                     int use_fine, double pose_world[3], double cov[9], double* score, double responses[3]) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !params || !pose_world || !cov || !score || n_pts < 0 || (n_pts > 0 && !pts_xy))
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_chain: bad arguments");
   double* d_pts = nullptr;
@@ -1556,6 +1583,7 @@ int rsm_match_chain(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, in
 int rsm_match_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* pts_xy, const int64_t* pts_offset,
                     const rsm_pass_param* params, int shared_params, int use_fine, double* poses_world, double* covs,
                     double* scores, double* responses) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || n < 0 || (n > 0 && (!grids || !pts_offset || !params || !poses_world || !covs || !scores)))
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_batch: bad arguments");
   if (n == 0) return RSM_OK;
@@ -1573,6 +1601,7 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
                            const int32_t* base_n_pts, const double* base_pts_xy, const double* base_poses_world,
                            const double* pts_xy, const int64_t* pts_offset, const rsm_pass_param params[3], int use_fine,
                            double* poses_world, double* covs, double* scores, double* responses) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || n < 0 || grid_size <= 0 || !(resolution > 0) ||
       (n > 0 && (!centres_world || !scan_offset || !base_n_pts || !base_pts_xy || !base_poses_world || !pts_xy ||
                  !pts_offset || !params || !poses_world || !covs || !scores)))
@@ -1660,6 +1689,7 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
 int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
                     const double pose_world[3], int angle_begin, int angle_end, double* scores_out, int64_t capacity,
                     int64_t* n_written) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !param || !pose_world || !scores_out || n_pts <= 0 || !pts_xy)
     return fail(ctx, RSM_ERR_INVALID, "rsm_pass_scores: bad arguments");
   if (!grid->init) return fail(ctx, RSM_ERR_NOT_INIT, "grid has no content");
@@ -1677,6 +1707,7 @@ int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, in
 
 int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
                       const double pose_world[3], int angle_begin, int angle_end, void* partial) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !grid || !param || !pose_world || !partial || n_pts <= 0 || !pts_xy)
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_partial: bad arguments");
   if (!grid->init) return fail(ctx, RSM_ERR_NOT_INIT, "grid has no content");
@@ -1709,6 +1740,7 @@ int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, 
 }
 
 int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, void* columns) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !partials || n_partials < 1 || !columns) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: bad arguments");
   SliceState& S = ctx->slice;
   if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: no rsm_match_partial pending on this context");
@@ -1787,6 +1819,7 @@ int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, v
 
 int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, const void* const* columns,
                      double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !partials || !columns || n_partials < 1 || !pose_world || !cov || !response)
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: bad arguments");
   SliceState& S = ctx->slice;

@@ -27,6 +27,7 @@ inline int grid_pitch_for(int size_x) {
 
 constexpr int kTopK = 21;          // top-20 covariance prefix + 1 to detect a tie at the cut
 constexpr int kChunk = 32;         // beams per shared-memory table chunk of the scoring kernel
+constexpr int kMaxDevices = 64;   // per-device launch configuration caches
 constexpr int kSelectBuf = 2048;
 constexpr int kSelectThreads = 512;   // select_kernel CTA size
 constexpr int kSelectSlice = 8192;    // candidates per select CTA (at least); a multiple of 8 * kSelectThreads

@@ -359,11 +359,14 @@ extern "C" int rsm_debug_select(unsigned long long* out) {
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count) {
   const size_t smem = size_t(kSelectSlice) * 8;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};   // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   select_kernel<<<n_cta, kSelectThreads, smem, st>>>(jobs, cta_begin, n_jobs, pool, pool_cap, pool_count);
   return cudaGetLastError();

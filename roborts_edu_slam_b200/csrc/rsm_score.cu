@@ -997,11 +997,14 @@ static void (*staged_fn(int variant))(const ScoreJob*, const int*, int) {
 }
 
 static cudaError_t staged_configure(int variant, size_t smem) {
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[variant]) {
+  static size_t configured[kMaxDevices][2] = {{0, 0}};   // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (smem > configured[dev][variant]) {
     cudaError_t e = cudaFuncSetAttribute(staged_fn(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[variant] = smem;
+    configured[dev][variant] = smem;
   }
   return cudaSuccess;
 }

@@ -442,3 +442,32 @@ def test_wide_grid_runtime_pitch(ctx, oracle, rng):
         pz, cz = pose.copy(), np.eye(3)
         assert_pass_equal(m.ScanMatch(dg, pts, p, pz, cz), pz, cz, want)
     dg.close()
+
+
+def test_second_device_from_a_fresh_thread(oracle):
+    """A context on device 1 used from a new host thread (whose current device is 0): every
+    entry point has to select the context's device itself.  Needs two GPUs."""
+    import threading
+    try:
+        c1 = matcher.Context(1)
+    except matcher.RsmError:
+        pytest.skip("one GPU only")
+    sc = synth.config1()
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    want = oracle.match(grid, sc.grid, sc.scan_pts, sc.passes[0], sc.seed_pose)
+    out = {}
+
+    def work():
+        dg = matcher.ScanMatchMap.from_spec(c1, sc.grid)
+        dg.upload(grid)
+        m = matcher.BasedCorrelationScanMatch(c1)
+        pose, cov = sc.seed_pose.copy(), np.eye(3)
+        out["r"] = m.ScanMatch(dg, sc.scan_pts, sc.passes[0], pose, cov)
+        out["pose"] = pose
+        dg.close()
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    c1.close()
+    assert out["r"] == want["response"] and np.array_equal(out["pose"], want["pose"])

@@ -121,6 +121,24 @@ void rsm_grid_destroy(rsm_ctx* ctx, rsm_grid* grid);
 int rsm_grid_set_offset(rsm_ctx* ctx, rsm_grid* grid, double offset_x, double offset_y);
 /* Hand over an existing grid: prob[y*size_x + x] = ProbabilityCell::prob_value_ (map/grid_map_cell.h:301-328). */
 int rsm_grid_upload_f32(rsm_ctx* ctx, rsm_grid* grid, const float* prob);
+/* Occupancy of a publishing map (PubMap = OccuGridMap<CountCell>, map/slam_map.h:35) for the map
+ * check below: occupied[y*size_x + x] != 0 where CheckOccuLineVisitorCallback would count the cell
+ * (map/occu_grid_map.h:447-471): CountCellFunctions::GetGridStates(cell) == GridStates_Occupied
+ * (pass_count >= 2 and value >= 0.5, map/grid_map_cell.h:125-136) without blur, value >
+ * cell_occu_prob_offset with blur.  The grid object only lends its size and world<->map transform. */
+int rsm_grid_upload_occupancy(rsm_ctx* ctx, rsm_grid* grid, const uint8_t* occupied);
+/* OccuGridMap::MapFeedbackResponsePenalty (map/occu_grid_map.h:331-392) through
+ * SlamProcessor::MapCheckPenalize (slam/slam_processor.cpp:573-595), for n candidate poses in one
+ * launch: coeff_out[i] = max(1 + 2*gain - gain * (rays of scan i blocked by an occupied cell farther
+ * than bound_tolerance from the ray's end), 0.1), 0.0 for a pose outside the map, and through
+ * 1/(1+exp(-10*(coeff-0.4))) when use_logistic (the loop-closure call, slam_processor.cpp:313-317).
+ * Scan i = pts_xy[2*pts_begin[i] .. 2*(pts_begin[i]+pts_count[i])) in cells of the publishing map,
+ * sensor frame (ranges may overlap or coincide); sensor_origin_xy = RangeDataContainer::sensor_origin()
+ * (NULL = (0,0)).  check_point_num / bound_tolerance / penalty_gain = map_check_* parameters. */
+int rsm_map_check_penalize(rsm_ctx* ctx, const rsm_grid* pub_map, int n, const double* poses_world,
+                           const double* pts_xy, const int64_t* pts_begin, const int32_t* pts_count,
+                           const double* sensor_origin_xy, int check_point_num, double bound_tolerance,
+                           double penalty_gain, int use_logistic, double* coeff_out);
 /* Device-side construction from base scans; replaces OccuGridMap::InitMapWithRangeVec in the
  * back-end configuration (just_update_occu, no auto-resize; map/occu_grid_map.h:222-329,
  * 474-497, 531-576; slam/slam_processor.cpp:448-462).  sigma = map deviation, occu_offset =

@@ -64,7 +64,20 @@ class Oracle:
         L.orc_match.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
         L.orc_match_chain.restype = c_d
         L.orc_match_chain.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        L.orc_map_check_penalize.restype = c_d
+        L.orc_map_check_penalize.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_i, c_d, c_d, c_i]
         self.L = L
+
+    def map_check_penalize(self, occupied, g, pts_cells, pose_world, check_point_num, bound_tolerance, penalty_gain,
+                           use_logistic=False, origin=(0.0, 0.0)):
+        """MapFeedbackResponsePenalty (+ the loop-closure logistic) over an occupancy mask [size_y, size_x]."""
+        occ = np.ascontiguousarray(occupied, dtype=np.uint8)
+        pts = np.ascontiguousarray(pts_cells, dtype=np.float64)
+        pose = np.ascontiguousarray(pose_world, dtype=np.float64)
+        org = np.ascontiguousarray(origin, dtype=np.float64)
+        return self.L.orc_map_check_penalize(occ.ctypes.data, g.size_x, g.size_y, 1.0 / g.res, g.off_x, g.off_y, len(pts),
+                                             pts.ctypes.data, pose.ctypes.data, org.ctypes.data, int(check_point_num),
+                                             float(bound_tolerance), float(penalty_gain), 1 if use_logistic else 0)
 
     def blur_kernel(self, sigma, res):
         k = np.zeros(21 * 21, dtype=np.float64)
@@ -176,7 +189,44 @@ class Ref:
         L.ref_match_chain.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
         L.ref_blur_kernel.restype = c_i
         L.ref_blur_kernel.argtypes = [c_d, c_d, c_p, c_i]
+        L.ref_pubmap_create.restype = c_p
+        L.ref_pubmap_create.argtypes = [c_d, c_i, c_i, c_d, c_d, ctypes.c_float]
+        L.ref_pubmap_destroy.argtypes = [c_p]
+        L.ref_pubmap_update.restype = c_i
+        L.ref_pubmap_update.argtypes = [c_p, c_i, c_p, c_p]
+        L.ref_pubmap_read.argtypes = [c_p, c_p, c_p, c_p]
+        L.ref_pubmap_penalty.restype = c_d
+        L.ref_pubmap_penalty.argtypes = [c_p, c_i, c_p, c_p, c_p, c_i, c_d, c_d, c_i, c_i]
         self.L = L
+
+    # ---- publishing map (CountCell) and MapFeedbackResponsePenalty -------------------------------
+    def pubmap_create(self, g, default_prob=0.5):
+        return self.L.ref_pubmap_create(g.res, g.size_x, g.size_y, g.off_x, g.off_y, default_prob)
+
+    def pubmap_destroy(self, m):
+        self.L.ref_pubmap_destroy(m)
+
+    def pubmap_update(self, m, pts_cells, pose_world):
+        pts = np.ascontiguousarray(pts_cells, dtype=np.float64)
+        pose = np.ascontiguousarray(pose_world, dtype=np.float64)
+        return self.L.ref_pubmap_update(m, len(pts), pts.ctypes.data, pose.ctypes.data)
+
+    def pubmap_read(self, m, g):
+        n = g.size_x * g.size_y
+        val = np.zeros(n, dtype=np.float32); cnt = np.zeros(n, dtype=np.float32); occ = np.zeros(n, dtype=np.uint8)
+        self.L.ref_pubmap_read(m, val.ctypes.data, cnt.ctypes.data, occ.ctypes.data)
+        shape = (g.size_y, g.size_x)
+        return val.reshape(shape), cnt.reshape(shape), occ.reshape(shape)
+
+    def pubmap_penalty(self, m, pts_cells, pose_world, check_point_num, bound_tolerance, penalty_gain, use_blur=False,
+                       use_logistic=False, origin=None):
+        pts = np.ascontiguousarray(pts_cells, dtype=np.float64)
+        pose = np.ascontiguousarray(pose_world, dtype=np.float64)
+        org = np.ascontiguousarray(origin, dtype=np.float64) if origin is not None else None
+        return self.L.ref_pubmap_penalty(m, len(pts), pts.ctypes.data, pose.ctypes.data,
+                                         org.ctypes.data if org is not None else None, int(check_point_num),
+                                         float(bound_tolerance), float(penalty_gain), 1 if use_blur else 0,
+                                         1 if use_logistic else 0)
 
     def blur_kernel(self, sigma, res):
         k = np.zeros(21 * 21, dtype=np.float64)

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "scan_match/correlate_scan_matcher.h"
+#include "map/slam_map.h"
 
 #include "ref_types.h"
 
@@ -225,6 +226,55 @@ int ref_blur_kernel(double sigma, double resolution, double* k, int cap) {
   int n = g.GetKernelGridSize();
   if (k && cap >= n * n) std::memcpy(k, g.GetKernelValuePointer(), sizeof(double) * n * n);
   return g.GetKernelGridHalfSize();
+}
+
+
+// ---- publishing map + MapFeedbackResponsePenalty (occu_grid_map.h:331-392, 447-471) --------------
+// A front-end style PubMap (CountCell): no blur, free space ray-traced, auto-resize off.
+void* ref_pubmap_create(double resolution, int size_x, int size_y, double off_x, double off_y, float default_prob) {
+  auto* m = new std::shared_ptr<PubMap>(std::make_shared<PubMap>(resolution, Eigen::Vector2i(size_x, size_y),
+                                                                 Eigen::Vector2d(off_x, off_y), 0.0, default_prob));
+  (*m)->set_use_auto_map_resize(false);
+  (*m)->set_just_update_occu(false);
+  std::vector<std::shared_ptr<RangeDataContainer2d>> none;
+  (*m)->InitMapWithRangeVec(none, false, false);
+  return m;
+}
+
+void ref_pubmap_destroy(void* m) { delete static_cast<std::shared_ptr<PubMap>*>(m); }
+
+// UpdateMapByRange(scan, use_blur=false): pts in CELL units of this map, sensor frame; pose world metres.
+int ref_pubmap_update(void* m, int n_pts, const double* pts, const double* pose_world) {
+  auto& map = *static_cast<std::shared_ptr<PubMap>*>(m);
+  return map->UpdateMapByRange(MakeScan(n_pts, pts, pose_world), false) ? 0 : 1;
+}
+
+// Per cell: prob_value_, pass_count_ and the occupancy the no-blur check uses
+// (CountCellFunctions::GetGridStates == GridStates_Occupied, grid_map_cell.h:125-136).
+void ref_pubmap_read(void* m, float* value, float* pass_count, unsigned char* occupied) {
+  auto& map = *static_cast<std::shared_ptr<PubMap>*>(m);
+  CountCellFunctions f;
+  const int n = map->GetGridCellNum();
+  for (int i = 0; i < n; ++i) {
+    auto& c = map->GetCell(i);
+    if (value) value[i] = c.GetValue();
+    if (pass_count) pass_count[i] = c.pass_count();
+    if (occupied) occupied[i] = f.GetGridStates(c) == GridStates_Occupied ? 1 : 0;
+  }
+}
+
+// origin: RangeDataContainer::sensor_origin() (NULL = (0,0)).  use_logistic re-states the one line of
+// SlamProcessor::MapCheckPenalize (slam/slam_processor.cpp:589-591; that file needs ROS and cannot be
+// compiled here) on top of the reference's own MapFeedbackResponsePenalty.
+double ref_pubmap_penalty(void* m, int n_pts, const double* pts, const double* pose_world, const double* origin,
+                          int check_point_num, double bound_tolerance, double penalty_gain, int use_blur, int use_logistic) {
+  auto& map = *static_cast<std::shared_ptr<PubMap>*>(m);
+  auto scan = MakeScan(n_pts, pts, nullptr);
+  if (origin) scan->set_sensor_origin(Eigen::Vector2d(origin[0], origin[1]));
+  double penalty = map->MapFeedbackResponsePenalty(scan, Eigen::Vector3d(pose_world[0], pose_world[1], pose_world[2]),
+                                                   check_point_num, bound_tolerance, penalty_gain, use_blur != 0);
+  if (use_logistic) penalty = (1 / (1 + exp(-10 * (penalty - 0.4))));
+  return penalty;
 }
 
 }  // extern "C"

@@ -451,4 +451,70 @@ double orc_match_chain(const float* grid, int size_x, int size_y, double scale, 
   return score;
 }
 
+
+// OccuGridMap::MapFeedbackResponsePenalty (map/occu_grid_map.h:331-392): rays from the sensor to
+// every check point, walked with LineVisitor::ErgodLineBresenhami (:125-187); the callback
+// (CheckOccuLineVisitorCallback, :447-471) adds 1 to the ray's result, while that result is still
+// below 1, for a cell that counts as occupied and lies farther than bound_tolerance from the ray's
+// end point.  `occupied[y*size_x+x]` is that per-cell test (GetGridStates == Occupied without
+// blur, value > cell_occu_prob_offset with blur), evaluated by the caller.
+// pts: raw scan points in cells of this map, sensor frame; origin: RangeDataContainer::sensor_origin().
+double orc_map_feedback_penalty(const unsigned char* occupied, int size_x, int size_y, double scale, double off_x,
+                                double off_y, int n_pts, const double* pts, const double* pose_world,
+                                const double* origin, int check_point_num, double bound_tolerance, double penalty_gain) {
+  if (bound_tolerance < 0 || check_point_num <= 0 || penalty_gain <= 0.0 || penalty_gain >= 1.0) return 1.0;   // :337-341
+  const MapTf tf = MakeTf(scale, off_x, off_y);
+  double pm[3];
+  WorldToMap(tf, pose_world, pm);
+  if (!(pm[0] > 0.0 && pm[0] < size_x && pm[1] > 0.0 && pm[1] < size_y)) return 0.0;                            // :351-353
+  const double c = std::cos(pm[2]), sn = std::sin(pm[2]);
+  const int sx0 = static_cast<int>((pm[0] + (c * origin[0] + (-sn) * origin[1])) + 0.5);                        // :357-359
+  const int sy0 = static_cast<int>((pm[1] + (sn * origin[0] + c * origin[1])) + 0.5);
+  if (check_point_num == 1 && n_pts >= 2) return std::nan("");   // the reference divides by zero here (:367)
+  int step = 1;
+  if (n_pts < 2 * check_point_num) { check_point_num = n_pts; step = 1; }                                       // :361-368
+  else step = n_pts / (check_point_num - 1);
+  double penalty = 0;
+  for (int p = 0; p < n_pts; p += step) {
+    const double px = pts[2 * p], py = pts[2 * p + 1];
+    const int ex = static_cast<int>((pm[0] + (c * px + (-sn) * py)) + 0.5);
+    const int ey = static_cast<int>((pm[1] + (sn * px + c * py)) + 0.5);
+    if ((sx0 == ex && sy0 == ey) || !(double(ex) > 0.0 && double(ex) < size_x && double(ey) > 0.0 && double(ey) < size_y)) continue;
+    // ErgodLineBresenhami(start, end)
+    double res = 0.0;
+    int x0 = sx0, y0 = sy0, x1 = ex, y1 = ey;
+    const bool steep = std::abs(y1 - y0) > std::abs(x1 - x0);
+    if (steep) { std::swap(x0, y0); std::swap(x1, y1); }
+    if (x0 > x1) { std::swap(x0, x1); std::swap(y0, y1); }
+    const int delta_x = x1 - x0, delta_y = std::abs(y1 - y0);
+    int error = 0, y = y0;
+    const int y_step = y0 < y1 ? 1 : -1;
+    for (int x = x0; x <= x1; ++x) {
+      const int qx = steep ? y : x, qy = steep ? x : y;
+      error += delta_y;
+      if (2 * error >= delta_x) { y += y_step; error -= delta_x; }
+      double penalty_sum = 0.0;
+      // (a sensor cell outside the map makes the reference read out of bounds; such cells count as free here)
+      if (qx >= 0 && qx < size_x && qy >= 0 && qy < size_y && occupied[static_cast<size_t>(qy) * size_x + qx]) {
+        const double ddx = double(ex) - double(qx), ddy = double(ey) - double(qy);
+        if (std::sqrt(ddx * ddx + ddy * ddy) > bound_tolerance) penalty_sum += 1.0;                              // slam_util.h:94-96
+      }
+      if (res < 1.0) res += penalty_sum;
+    }
+    penalty += res;
+  }
+  penalty *= penalty_gain;
+  return std::max((1.0 + 2 * penalty_gain - penalty), 0.1);                                                      // :389-390
+}
+
+// SlamProcessor::MapCheckPenalize (slam/slam_processor.cpp:573-595), use_map_check_feedback on.
+double orc_map_check_penalize(const unsigned char* occupied, int size_x, int size_y, double scale, double off_x,
+                              double off_y, int n_pts, const double* pts, const double* pose_world, const double* origin,
+                              int check_point_num, double bound_tolerance, double penalty_gain, int use_logistic) {
+  double penalty = orc_map_feedback_penalty(occupied, size_x, size_y, scale, off_x, off_y, n_pts, pts, pose_world, origin,
+                                            check_point_num, bound_tolerance, penalty_gain);
+  if (use_logistic) penalty = (1 / (1 + exp(-10 * (penalty - 0.4))));
+  return penalty;
+}
+
 }  // extern "C"

@@ -52,6 +52,7 @@ struct rsm_grid {
   bool init = false;   // has content (reference: IsMapInit())
   bool owned = true;   // d_cells allocated by this grid (false: a slot of a batch pool)
   void* d_cells = nullptr;
+  unsigned char* d_occ = nullptr;   // publishing-map occupancy mask (rsm_grid_upload_occupancy), size_x bytes per row
   double cell_len() const { return 1 / scale; }   // map/grid_map_base.h:307-309
 };
 
@@ -1268,6 +1269,7 @@ void rsm_grid_destroy(rsm_ctx* ctx, rsm_grid* grid) {
   if (!grid) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   if (grid->owned && grid->d_cells) cudaFree(grid->d_cells);
+  if (grid->d_occ) cudaFree(grid->d_occ);
   delete grid;
 }
 
@@ -1314,6 +1316,107 @@ int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out) {
     for (size_t i = 0; i < n; ++i) prob_out[i] = static_cast<float>(std::ldexp(static_cast<double>(fx[i]), -kFixShift));
   } else {
     std::memcpy(prob_out, ctx->h_down.p, n * 4);
+  }
+  return RSM_OK;
+}
+
+int rsm_grid_upload_occupancy(rsm_ctx* ctx, rsm_grid* grid, const uint8_t* occupied) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || !occupied) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_upload_occupancy: null argument");
+  const size_t n = size_t(grid->size_x) * grid->size_y;
+  if (!grid->d_occ) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&grid->d_occ), n);
+    if (e != cudaSuccess) return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(occupancy) failed: %s", cudaGetErrorString(e));
+  }
+  int rc = ensure_pinned(ctx, ctx->h_up, n);
+  if (rc) return rc;
+  std::memcpy(ctx->h_up.p, occupied, n);
+  CU(cudaMemcpyAsync(grid->d_occ, ctx->h_up.p, n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = sync_stream(ctx);           // the staging buffer is reused by the next call
+  if (rc) return rc;
+  ctx->stats.h2d_bytes += n;
+  return RSM_OK;
+}
+
+// MapFeedbackResponsePenalty + MapCheckPenalize for n poses in one launch.
+int rsm_map_check_penalize(rsm_ctx* ctx, const rsm_grid* pub_map, int n, const double* poses_world, const double* pts_xy,
+                           const int64_t* pts_begin, const int32_t* pts_count, const double* sensor_origin_xy,
+                           int check_point_num, double bound_tolerance, double penalty_gain, int use_logistic,
+                           double* coeff_out) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pub_map || n < 0 || (n > 0 && (!poses_world || !pts_begin || !pts_count || !coeff_out)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: bad arguments");
+  if (n == 0) return RSM_OK;
+  if (!pub_map->d_occ) return fail(ctx, RSM_ERR_NOT_INIT, "rsm_map_check_penalize: no occupancy uploaded for this map");
+  // occu_grid_map.h:337-341: out-of-range knobs switch the check off
+  if (bound_tolerance < 0 || check_point_num <= 0 || penalty_gain <= 0.0 || penalty_gain >= 1.0) {
+    for (int i = 0; i < n; ++i) coeff_out[i] = use_logistic ? (1 / (1 + std::exp(-10 * (1.0 - 0.4)))) : 1.0;
+    return RSM_OK;
+  }
+  const double ox = sensor_origin_xy ? sensor_origin_xy[0] : 0.0, oy = sensor_origin_xy ? sensor_origin_xy[1] : 0.0;
+  int64_t lo = INT64_MAX, hi = 0;
+  for (int i = 0; i < n; ++i) {
+    if (pts_count[i] < 0 || pts_begin[i] < 0) return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: bad point range");
+    if (check_point_num == 1 && pts_count[i] >= 2)   // the reference divides by zero (occu_grid_map.h:367)
+      return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: check_point_num = 1 with 2 or more points");
+    if (pts_count[i] == 0) continue;
+    lo = std::min(lo, pts_begin[i]);
+    hi = std::max(hi, pts_begin[i] + pts_count[i]);
+  }
+  if (hi <= lo) { lo = 0; hi = 0; }
+  if (hi > lo && !pts_xy) return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: pts_xy is null");
+  const size_t pts_bytes = size_t(hi - lo) * 16;
+  Layout dl;
+  const size_t o_jobs = dl.take(sizeof(PenaltyJob) * size_t(n));
+  const size_t o_pts = dl.take(pts_bytes, 16);
+  const size_t up_bytes = dl.off;
+  const size_t o_out = dl.take(size_t(n) * 4, 16);
+  int rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_down, size_t(n) * 4);
+  if (rc) return rc;
+  char* dw = ctx->d_work.p;
+  char* up = ctx->h_up.p;
+  if (pts_bytes) std::memcpy(up + o_pts, pts_xy + 2 * lo, pts_bytes);
+  PenaltyJob* jobs = reinterpret_cast<PenaltyJob*>(up + o_jobs);
+  std::vector<char> outside(n, 0);
+  for (int i = 0; i < n; ++i) {
+    PenaltyJob& J = jobs[i];
+    std::memset(&J, 0, sizeof J);
+    double pm[3];
+    pub_map->tf.world_to_map(poses_world + 3 * i, pm);                                   // :349
+    // PointInMap(x, y) is strict on both sides (grid_map_base.h:339-346); outside -> 0.0 (:351-353)
+    outside[i] = !(pm[0] > 0.0 && pm[0] < pub_map->size_x && pm[1] > 0.0 && pm[1] < pub_map->size_y);
+    const double c = std::cos(pm[2]), sn = std::sin(pm[2]);                              // Rotation2Dd, host libm
+    J.c = c; J.s = sn; J.tx = pm[0]; J.ty = pm[1];
+    J.sx0 = static_cast<int>((pm[0] + (c * ox + (-sn) * oy)) + 0.5);                      // :357-359
+    J.sy0 = static_cast<int>((pm[1] + (sn * ox + c * oy)) + 0.5);
+    const int all = pts_count[i];
+    J.n_pts = outside[i] ? 0 : all;
+    J.step = (all < 2 * check_point_num) ? 1 : all / (check_point_num - 1);                // :361-368
+    J.pts = reinterpret_cast<const double*>(dw + o_pts) + 2 * (pts_begin[i] - lo);
+    J.blocked = reinterpret_cast<int*>(dw + o_out) + i;
+  }
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_penalty(n, ctx->stream, reinterpret_cast<const PenaltyJob*>(dw + o_jobs), pub_map->d_occ, pub_map->size_x,
+                    pub_map->size_y, bound_tolerance));
+  CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_out, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.h2d_bytes += up_bytes; ctx->stats.d2h_bytes += size_t(n) * 4; ctx->stats.kernel_launches++;
+  const int* blocked = reinterpret_cast<const int*>(ctx->h_down.p);
+  for (int i = 0; i < n; ++i) {
+    double coeff;
+    if (outside[i]) coeff = 0.0;
+    else {
+      double penalty = double(blocked[i]);            // the reference adds 1.0 per blocked ray
+      penalty *= penalty_gain;
+      coeff = std::max((1.0 + 2 * penalty_gain - penalty), 0.1);                           // :389-390
+    }
+    if (use_logistic) coeff = (1 / (1 + std::exp(-10 * (coeff - 0.4))));                   // slam_processor.cpp:589-591
+    coeff_out[i] = coeff;
   }
   return RSM_OK;
 }

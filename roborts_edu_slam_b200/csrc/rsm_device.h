@@ -117,6 +117,17 @@ struct FillJob {
   int value;             // raw 32-bit pattern (fixed-point int or float bits)
 };
 
+// One pose of a map-check batch (MapFeedbackResponsePenalty): the rays of one scan through the
+// publishing map's occupancy mask.
+struct PenaltyJob {
+  const double* pts;     // scan points, cells of the publishing map, sensor frame
+  int n_pts, step;       // points and check stride (:361-368)
+  int sx0, sy0;          // beam start cell (host: pose transform of the sensor origin, :357-359)
+  double c, s, tx, ty;   // cos / sin (host libm) and translation of the pose in map cells
+  int* blocked;          // out: rays that met an occupied cell beyond the tolerance
+  int pad0, pad1;
+};
+
 }  // namespace rsm
 
 #endif

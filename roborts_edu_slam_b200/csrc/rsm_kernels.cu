@@ -526,4 +526,55 @@ cudaError_t launch_flush(cudaStream_t st, void* buf, long long bytes, int v) {
   return cudaGetLastError();
 }
 
+
+// =================================================================================================
+// map check: rays of a scan through the publishing map (MapFeedbackResponsePenalty)
+// =================================================================================================
+// One CTA per pose, one thread per checked ray.  A ray is LineVisitor::ErgodLineBresenhami from the
+// sensor cell to the beam's end cell (map/occu_grid_map.h:125-187); it counts once if any visited
+// cell is occupied and farther than the tolerance from the end cell (:447-471 -- the callback only
+// adds while the ray's result is below 1, so the walk stops at the first such cell).
+__global__ void __launch_bounds__(128)
+penalty_kernel(const PenaltyJob* __restrict__ jobs, const unsigned char* __restrict__ occ, int size_x, int size_y,
+               double bound_tolerance) {
+  const PenaltyJob J = jobs[blockIdx.x];
+  int blocked = 0;
+  for (int r = threadIdx.x; r * (long long)J.step < J.n_pts; r += blockDim.x) {
+    const int p = r * J.step;
+    const double px = J.pts[2 * p], py = J.pts[2 * p + 1];
+    // pose_transform * point, + 0.5, truncate (:372-375); Affine * v = translation + (l00 x + l01 y)
+    const int ex = __double2int_rz(dadd(dadd(J.tx, dadd(dmul(J.c, px), dmul(-J.s, py))), 0.5));
+    const int ey = __double2int_rz(dadd(dadd(J.ty, dadd(dmul(J.s, px), dmul(J.c, py))), 0.5));
+    if ((ex == J.sx0 && ey == J.sy0) || !(ex > 0 && ex < size_x && ey > 0 && ey < size_y)) continue;   // :377 (PointInMap is strict)
+    int x0 = J.sx0, y0 = J.sy0, x1 = ex, y1 = ey;
+    const bool steep = abs(y1 - y0) > abs(x1 - x0);
+    if (steep) { int t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
+    if (x0 > x1) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+    const int delta_x = x1 - x0, delta_y = abs(y1 - y0), y_step = y0 < y1 ? 1 : -1;
+    int error = 0, y = y0;
+    for (int x = x0; x <= x1; ++x) {
+      const int qx = steep ? y : x, qy = steep ? x : y;
+      error += delta_y;
+      if (2 * error >= delta_x) { y += y_step; error -= delta_x; }
+      // (only a sensor cell outside the map can put a visited cell outside it; the reference reads
+      //  out of bounds there, here such cells count as free)
+      if (qx >= 0 && qx < size_x && qy >= 0 && qy < size_y && occ[(size_t)qy * size_x + qx]) {
+        const int ddx = ex - qx, ddy = ey - qy;
+        if (__dsqrt_rn((double)((long long)ddx * ddx + (long long)ddy * ddy)) > bound_tolerance) { ++blocked; break; }       // slam_util.h:94-96
+      }
+    }
+  }
+  blocked = __reduce_add_sync(0xffffffffu, blocked);
+  __shared__ int s_sum[4];
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = blocked;
+  __syncthreads();
+  if (threadIdx.x == 0) *J.blocked = s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3];
+}
+
+cudaError_t launch_penalty(int n_jobs, cudaStream_t st, const PenaltyJob* jobs, const unsigned char* occ, int size_x,
+                           int size_y, double bound_tolerance) {
+  penalty_kernel<<<n_jobs, 128, 0, st>>>(jobs, occ, size_x, size_y, bound_tolerance);
+  return cudaGetLastError();
+}
+
 }  // namespace rsm

@@ -37,6 +37,8 @@ cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, con
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);
 cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);
 cudaError_t launch_fill(int n_jobs, int ctas_per_job, cudaStream_t st, const FillJob* jobs);
+cudaError_t launch_penalty(int n_jobs, cudaStream_t st, const PenaltyJob* jobs, const unsigned char* occ, int size_x,
+                           int size_y, double bound_tolerance);
 cudaError_t launch_raster(int n_scans, cudaStream_t st, const RasterScan* scans, const int* stamp,
                           int half, int one);
 cudaError_t launch_microbench(cudaStream_t st, int mode, const int* g, unsigned int words, int iters,

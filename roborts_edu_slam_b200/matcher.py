@@ -86,6 +86,8 @@ ABI = {
     "rsm_grid_upload_f32": (c_i, [c_p, c_p, c_p]),
     "rsm_grid_rasterize": (c_i, [c_p, c_p, ctypes.c_float, c_d, c_d, c_i, c_i, c_p, c_p, c_p]),
     "rsm_grid_download_f32": (c_i, [c_p, c_p, c_p]),
+    "rsm_grid_upload_occupancy": (c_i, [c_p, c_p, c_p]),
+    "rsm_map_check_penalize": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_i, c_p]),
     "rsm_grid_is_fixed_point": (c_i, [c_p]),
     "rsm_world_to_map": (c_i, [c_p, c_p, c_p]),
     "rsm_map_to_world": (c_i, [c_p, c_p, c_p]),
@@ -292,6 +294,38 @@ class ScanMatchMap:
         self.ctx.check(self.ctx.lib.rsm_grid_rasterize(self.ctx.h, self.h, float(default_prob), float(sigma),
                                                        float(occu_offset), int(use_blur), len(base_pts),
                                                        n_pts.ctypes.data, pts.ctypes.data, poses.ctypes.data))
+
+    def upload_occupancy(self, occupied):
+        """Occupancy mask of a publishing map (PubMap) for MapCheckPenalize: nonzero where the
+        reference's CheckOccuLineVisitorCallback counts the cell (occu_grid_map.h:447-471)."""
+        occ = np.ascontiguousarray(occupied, dtype=np.uint8)
+        assert occ.shape == (self.size_y, self.size_x), occ.shape
+        self.ctx.check(self.ctx.lib.rsm_grid_upload_occupancy(self.ctx.h, self.h, occ.ctypes.data))
+
+    def MapCheckPenalize(self, scans, poses_world, check_point_num=100, bound_tolerance=2.5, penalty_gain=0.015,
+                         use_logistic=False, sensor_origin=None):
+        """SlamProcessor::MapCheckPenalize (slam_processor.cpp:573-595) for many candidate poses at
+        once.  scans: one array of points (cells of this map, sensor frame) shared by every pose, or
+        a list with one array per pose.  Returns the response coefficients."""
+        poses = _f64(np.asarray(poses_world, dtype=np.float64).reshape(-1, 3))
+        n = len(poses)
+        if isinstance(scans, (list, tuple)):
+            assert len(scans) == n
+            arrs = [np.asarray(a, dtype=np.float64).reshape(-1, 2) for a in scans]
+            count = np.array([len(a) for a in arrs], dtype=np.int32)
+            begin = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64) if n else np.zeros(0, dtype=np.int64)
+            pts = _f64(np.concatenate(arrs, axis=0)) if n else np.zeros((0, 2))
+        else:
+            pts = _f64(np.asarray(scans, dtype=np.float64).reshape(-1, 2))
+            count = np.full(n, len(pts), dtype=np.int32)
+            begin = np.zeros(n, dtype=np.int64)
+        org = _f64(sensor_origin) if sensor_origin is not None else None
+        out = np.zeros(n, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.rsm_map_check_penalize(
+            self.ctx.h, self.h, n, poses.ctypes.data, pts.ctypes.data if len(pts) else None, begin.ctypes.data,
+            count.ctypes.data, org.ctypes.data if org is not None else None, int(check_point_num),
+            float(bound_tolerance), float(penalty_gain), 1 if use_logistic else 0, out.ctypes.data))
+        return out
 
     def download(self):
         out = np.empty((self.size_y, self.size_x), dtype=np.float32)

@@ -16,7 +16,21 @@ def sha(a):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("maps_"))
+                  if not os.path.basename(p).startswith(("maps_", "mapcheck_")))
+
+
+def mapcheck_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "mapcheck_*.npz")))
+
+
+def load_mapcheck(name):
+    """-> (GridSpec of the publishing map, occupancy [size_y, size_x] uint8, npz with scan, poses, parameter sets and
+    the reference's coefficients)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    gs = z["grid_spec"]
+    g = synth.GridSpec(float(gs[0]), 0.0, int(gs[1]), int(gs[2]), float(gs[3]), float(gs[4]), 0.5, 0.88, False)
+    occ = np.unpackbits(z["occ_packed"])[: g.size_x * g.size_y].reshape(g.size_y, g.size_x)
+    return g, occ, z
 
 
 def load_golden(name):

@@ -471,3 +471,43 @@ def test_second_device_from_a_fresh_thread(oracle):
     t.join()
     c1.close()
     assert out["r"] == want["response"] and np.array_equal(out["pose"], want["pose"])
+
+
+# ---- map check ---------------------------------------------------------------
+def test_mapcheck_golden_and_oracle(ctx, oracle, rng):
+    """rsm_map_check_penalize against the reference's coefficients (fixtures) and, on fresh random
+    poses / knobs / per-pose scans, against the oracle: bit-equal."""
+    from helpers import load_mapcheck, mapcheck_names
+    for name in mapcheck_names():
+        g, occ, z = load_mapcheck(name)
+        pm = matcher.ScanMatchMap.from_spec(ctx, g)
+        pm.upload_occupancy(occ)
+        for k, ps in enumerate(z["param_sets"]):
+            got = pm.MapCheckPenalize(z["scan_pts"], z["poses"], int(ps[0]), ps[1], ps[2], bool(ps[3]), ps[4:6])
+            assert np.array_equal(got, z["coeff"][k]), (name, k, got, z["coeff"][k])
+        # one scan per pose (different lengths, one empty), random knobs
+        poses = z["poses"][:24] + rng.uniform(-0.2, 0.2, (24, 3))
+        scans = [z["scan_pts"][: int(rng.integers(0, len(z["scan_pts"]) + 1))] for _ in range(24)]
+        scans[5] = z["scan_pts"][:0]
+        for cp, tol, gain, logistic in ((100, 2.5, 0.015, True), (13, 0.5, 0.2, False)):
+            got = pm.MapCheckPenalize(scans, poses, cp, tol, gain, logistic)
+            want = np.array([oracle.map_check_penalize(occ, g, s, p, cp, tol, gain, logistic) for s, p in zip(scans, poses)])
+            assert np.array_equal(got, want)
+        pm.close()
+
+
+def test_mapcheck_errors(ctx):
+    g = synth.GridSpec(0.05, 0.0, 64, 48, 1.0, 1.0, 0.5, 0.88, False)
+    pm = matcher.ScanMatchMap.from_spec(ctx, g)
+    with pytest.raises(matcher.RsmError) as e:
+        pm.MapCheckPenalize(np.zeros((4, 2)), np.zeros((1, 3)))
+    assert "RSM_ERR_NOT_INIT" in str(e.value)
+    pm.upload_occupancy(np.zeros((48, 64), dtype=np.uint8))
+    assert pm.MapCheckPenalize(np.ones((4, 2)), np.zeros((0, 3))).shape == (0,)
+    with pytest.raises(matcher.RsmError) as e:     # the reference divides by zero for check_point_num = 1
+        pm.MapCheckPenalize(np.ones((4, 2)), np.zeros((1, 3)), 1, 2.5, 0.015)
+    assert "RSM_ERR_INVALID" in str(e.value)
+    # an empty map blocks nothing: 1 + 2 * gain
+    assert np.array_equal(pm.MapCheckPenalize(np.array([[5.0, 1.0], [0.0, 7.0]]), np.array([[0.5, 0.4, 0.1]]), 100, 2.5, 0.015),
+                          np.array([1.0 + 2 * 0.015]))
+    pm.close()

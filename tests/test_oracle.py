@@ -120,3 +120,44 @@ def test_oracle_degenerate_inputs(oracle):
     r = oracle.match(flat, g, sc.scan_pts, nopen, sc.seed_pose)
     assert r["n_avg"] == 3549 and np.array_equal(r["pose"], sc.seed_pose)
     assert cov_close(r["cov"], r["cov"])
+
+
+# ---- map check: MapFeedbackResponsePenalty / MapCheckPenalize ---------------------
+def test_mapcheck_oracle_matches_golden(oracle):
+    """The restatement against the coefficients the reference returned (committed fixtures)."""
+    from helpers import load_mapcheck, mapcheck_names
+    names = mapcheck_names()
+    assert names
+    for name in names:
+        g, occ, z = load_mapcheck(name)
+        for k, ps in enumerate(z["param_sets"]):
+            for i, pose in enumerate(z["poses"]):
+                got = oracle.map_check_penalize(occ, g, z["scan_pts"], pose, int(ps[0]), ps[1], ps[2], bool(ps[3]), ps[4:6])
+                assert got == z["coeff"][k, i], (name, k, i, got, z["coeff"][k, i])
+
+
+def test_mapcheck_oracle_matches_reference(oracle, ref, rng):
+    """Live reference (its own UpdateMapByRange builds the publishing map) vs the restatement on random
+    poses, scan subsets and knobs, with and without the loop-closure logistic."""
+    sc = synth.config1()
+    g = sc.grid
+    m = ref.pubmap_create(g)
+    for pts, pose in zip(sc.base_pts, sc.base_poses):
+        assert ref.pubmap_update(m, pts, pose) == 0
+    _, _, occ = ref.pubmap_read(m, g)
+    assert occ.sum() > 100
+    seen = set()
+    for k in range(400):
+        pose = sc.truth_pose + np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)]) * rng.choice([0.05, 0.3, 1.0])
+        n = int(rng.choice([len(sc.scan_pts), 150, 250, 30, 0]))
+        cp = int(rng.choice([100, 20, 7, 2]))       # 1 makes the reference divide by zero (occu_grid_map.h:367)
+        tol = float(rng.choice([2.5, 0.0, 1.0]))
+        gain = float(rng.choice([0.015, 0.1]))
+        logistic = bool(k & 1)
+        org = (0.0, 0.0) if k % 3 else (float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)))
+        a = ref.pubmap_penalty(m, sc.scan_pts[:n], pose, cp, tol, gain, False, logistic, org)
+        b = oracle.map_check_penalize(occ, g, sc.scan_pts[:n], pose, cp, tol, gain, logistic, org)
+        assert a == b, (k, a, b)
+        seen.add(a)
+    assert len(seen) > 20
+    ref.pubmap_destroy(m)

@@ -325,44 +325,76 @@ def main():
                 packed[key] = tt.numpy()
                 packed["_pin_" + key] = tt
             parts.append((ctx if t == 0 else matcher.Context(local_rank), packed))
+        # the same pairs with every scan already in a device-resident scan store (the back end adds each accepted
+        # scan once; loop-closure candidates then name chains by id: rsm_scan_match_interface_batch)
+        stores = []
+        for t in range(nctx):
+            pb, pe = contiguous_range(e - b, t, nctx)
+            c = parts[t][0]
+            st = matcher.ScanStore(c)
+            chains, mids = [], []
+            for sc in pairs[pb:pe]:
+                chains.append([st.AddRangeData(p_, q_) for p_, q_ in zip(sc.base_pts, sc.base_poses)])
+                mids.append(st.AddRangeData(sc.scan_pts, sc.seed_pose))
+            stores.append((st, chains, mids, [sc.grid_centre for sc in pairs[pb:pe]], [sc.seed_pose for sc in pairs[pb:pe]]))
         results = [None] * nctx
 
-        def lc_worker(t):
+        def lc_worker_host(t):
             c, packed = parts[t]
             results[t] = matcher.loop_closure_batch(c, packed, pairs[0].passes)
 
-        def lc_run():
-            ts = [threading.Thread(target=lc_worker, args=(t,)) for t in range(nctx)]
-            t0 = time.perf_counter()
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-            torch.cuda.synchronize()
-            return (time.perf_counter() - t0) * 1e3
+        def lc_worker_store(t):
+            st, chains, mids, centres, seeds = stores[t]
+            results[t] = matcher.scan_match_interface_batch(parts[t][0], st, pairs[0].grid, centres, chains, mids, seeds,
+                                                            pairs[0].passes)
 
-        lc_run()   # warm-up
-        barrier()
-        for c, _ in parts:
-            c.reset_stats()
-        reps, ms_lc = 3, 0.0
-        sampler.active.set()
-        for _ in range(reps):
-            ms_lc += lc_run()
-        sampler.active.clear()
-        barrier()
-        st_lc = {k: sum(c.stats()[k] for c, _ in parts) for k in ("evals", "exact_sort_passes")}
-        t_lc = max_over_ranks(ms_lc)
-        n_matches = sum_over_ranks((e - b) * reps)
-        accepted = sum(int((r[0] > 0.6).sum()) for r in results)
+        def lc_measure(worker):
+            def lc_run():
+                ts = [threading.Thread(target=worker, args=(t,)) for t in range(nctx)]
+                t0 = time.perf_counter()
+                for t in ts:
+                    t.start()
+                for t in ts:
+                    t.join()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) * 1e3
+
+            lc_run()   # warm-up
+            barrier()
+            for c, _ in parts:
+                c.reset_stats()
+            reps, ms_lc = 3, 0.0
+            sampler.active.set()
+            for _ in range(reps):
+                ms_lc += lc_run()
+            sampler.active.clear()
+            barrier()
+            st_lc = {k: sum(c.stats()[k] for c, _ in parts) for k in ("evals", "exact_sort_passes", "h2d_bytes", "d2h_bytes")}
+            t_lc = max_over_ranks(ms_lc)
+            n_matches = sum_over_ranks((e - b) * reps)
+            accepted = sum(int((r[0] > 0.6).sum()) for r in results)
+            return {
+                "matches_per_s": n_matches / (t_lc * 1e-3), "ms_per_batch": t_lc / reps,
+                "evals_per_s": sum_over_ranks(st_lc["evals"]) / (t_lc * 1e-3),
+                "exact_sort_passes": int(sum_over_ranks(st_lc["exact_sort_passes"])),
+                "accepted": int(sum_over_ranks(accepted)),
+                "h2d_bytes_per_batch": st_lc["h2d_bytes"] / reps, "d2h_bytes_per_batch": st_lc["d2h_bytes"] / reps,
+            }, [(r[0].copy(), r[1].copy()) for r in results]
+
+        lc_host, res_host = lc_measure(lc_worker_host)
+        lc_store, res_store = lc_measure(lc_worker_store)
+        same = all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(res_host, res_store))
         loop = {
             "workload": "BASELINE configs[3] shape: 1081-beam scan vs 480^2 grid rasterised from 8 base scans, coarse/fine/super chain (YAML values)",
-            "pairs": int(args.pairs_per_gpu * world), "matches_per_s": n_matches / (t_lc * 1e-3),
-            "ms_per_batch": t_lc / reps, "evals_per_s": sum_over_ranks(st_lc["evals"]) / (t_lc * 1e-3),
-            "exact_sort_passes": int(sum_over_ranks(st_lc["exact_sort_passes"])),
-            "accepted": int(sum_over_ranks(accepted)), "contexts_per_gpu": nctx,
-            "timing": "host wall clock around the batched calls (pinned host inputs -> host results), max over ranks",
+            "pairs": int(args.pairs_per_gpu * world), "contexts_per_gpu": nctx,
+            "scans": "resident in a device scan store, chains named by id (rsm_scan_match_interface_batch)",
+            **lc_store,
+            "host_scans": dict(lc_host, scans="every base scan shipped from pinned host memory per call (rsm_loop_closure_batch)"),
+            "store_equals_host_scans": bool(same),
+            "timing": "host wall clock around the batched calls (host inputs -> host results), max over ranks",
         }
+        for st, *_ in stores:
+            st.close()
         for c, _ in parts[1:]:
             c.close()
     # ---- wide relocalisation extra (config 5): ONE window angle-sliced over the ranks -----------

@@ -215,6 +215,53 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
                            const rsm_pass_param params[3], int use_fine, double* poses_world,
                            double* covs, double* scores, double* responses /* nullable */);
 
+/* ---- scan store and the batched back-end step -------------------------
+ * A scan store is the device-resident counterpart of one resolution of
+ * SensorDataManager::multiresolution_range_data_[name] (slam/sensor_data_manager.h:514-525): every
+ * accepted scan is added once (points in cells of that resolution, sensor frame -- what
+ * RangeDataContainer::CreateFrom(scan, 1/resolution) holds, :99-115 -- plus its sensor pose) and is
+ * addressed by the id the reference uses for it.  Poses change when the pose graph is optimised
+ * (SlamProcessor::UpdateRangeData, slam/slam_processor.cpp:597-603): rsm_scan_store_set_poses. */
+typedef struct rsm_scan_store rsm_scan_store;
+int rsm_scan_store_create(rsm_ctx* ctx, rsm_scan_store** out);
+void rsm_scan_store_destroy(rsm_ctx* ctx, rsm_scan_store* store);
+int rsm_scan_store_add(rsm_ctx* ctx, rsm_scan_store* store, const double* pts_xy, int n_pts,
+                       const double pose_world[3], int32_t* id_out /* nullable */);
+int rsm_scan_store_set_poses(rsm_ctx* ctx, rsm_scan_store* store, int n, const int32_t* ids,
+                             const double* poses_world);
+int rsm_scan_store_get_pose(const rsm_scan_store* store, int32_t id, double pose_world[3]);
+int rsm_scan_store_size(const rsm_scan_store* store);
+
+/* map_check_* parameters of SlamProcessor::MapCheckPenalize (slam/slam_processor.cpp:573-595) */
+typedef struct rsm_map_check_param {
+  double bound_tolerance;
+  double penalty_gain;
+  int32_t check_point_num;
+  int32_t use_logistic;
+} rsm_map_check_param;
+
+/* rsm_scan_match_interface_batch: SlamProcessor::ScanMatchInterface (slam/slam_processor.cpp:250-326)
+ * for n loop-closure candidates in batched launches, with scans named by id the way the pose graph
+ * names them (ScanMatchFunc(range_data, closest_id, range_id, pose&, cov&, ...),
+ * pose_graph/range_scan_pose_graph.h:30-35; called once per candidate chain at
+ * pose_graph/range_scan_pose_graph.cpp:153,312,329).  Candidate i matches scan match_ids[i] against
+ * the chain chain_ids[chain_offset[i] .. chain_offset[i+1]): a grid_size^2 grid centred on
+ * centres_world[2i..] is reset from the chain's scans at their stored poses (:448-462), then the
+ * coarse/fine/super chain runs from poses_world[3i..] (in/out; covs in/out as in rsm_match_batch).
+ * Only ids travel host->device: the points are already resident.
+ * With pub_map != NULL the step ends like the reference's: scores[i] *= MapCheckPenalize(scan
+ * match_ids[i] of pub_store -- the same scan in cells of the publishing map --, matched pose,
+ * use_logistic), clamped to 1 (:313-317).  responses (nullable) = the three pass responses. */
+int rsm_scan_match_interface_batch(rsm_ctx* ctx, const rsm_scan_store* store, int n, int grid_size,
+                                   double resolution, float default_prob, double sigma, double occu_offset,
+                                   const double* centres_world, const int64_t* chain_offset,
+                                   const int32_t* chain_ids, const int32_t* match_ids,
+                                   const rsm_pass_param params[3], int use_fine, double* poses_world,
+                                   double* covs, double* scores, double* responses /* nullable */,
+                                   const rsm_grid* pub_map /* nullable */,
+                                   const rsm_scan_store* pub_store /* nullable */,
+                                   const rsm_map_check_param* check /* nullable */);
+
 /* ---- parity / multi-GPU building blocks --------------------------------------------------
  * rsm_pass_scores: penalised score of every candidate of one pass in candidate order
  * k = (angle_index*n_xy + x_index)*n_xy + y_index (the order of correlate_scan_matcher.h:552-584),

@@ -61,6 +61,15 @@ struct rsm_scan {
   int n = 0;
 };
 
+// Device-resident counterpart of SensorDataManager::multiresolution_range_data_[name]
+// (slam/sensor_data_manager.h:514-525): scans addressed by id, each with its current sensor pose.
+struct rsm_scan_store {
+  struct Entry { double* d_pts; int n; double pose[3]; };
+  std::vector<Entry> scans;
+  std::vector<void*> chunks;          // device allocations; scans never move once stored
+  size_t chunk_used = 0, chunk_cap = 0;
+};
+
 namespace {
 
 struct Buf {
@@ -1155,6 +1164,78 @@ int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* 
   return RSM_OK;
 }
 
+// MapFeedbackResponsePenalty (map/occu_grid_map.h:331-392) + MapCheckPenalize (slam/slam_processor.cpp:573-595) for n
+// poses in one launch.  Points of pose i: host range pts_xy[2*pts_begin[i]..] (uploaded here, [lo, hi) = the hull of the
+// ranges) or, when dev_pts is given, the device-resident scan dev_pts[i].
+int map_check_core(rsm_ctx* ctx, const rsm_grid* pub_map, int n, const double* poses_world, const double* pts_xy,
+                   int64_t lo, int64_t hi, const int64_t* pts_begin, const double* const* dev_pts, const int32_t* pts_count,
+                   const double* sensor_origin_xy, int check_point_num, double bound_tolerance, double penalty_gain,
+                   int use_logistic, double* coeff_out) {
+  // occu_grid_map.h:337-341: out-of-range knobs switch the check off
+  if (bound_tolerance < 0 || check_point_num <= 0 || penalty_gain <= 0.0 || penalty_gain >= 1.0) {
+    for (int i = 0; i < n; ++i) coeff_out[i] = use_logistic ? (1 / (1 + std::exp(-10 * (1.0 - 0.4)))) : 1.0;
+    return RSM_OK;
+  }
+  for (int i = 0; i < n; ++i)
+    if (check_point_num == 1 && pts_count[i] >= 2)   // the reference divides by zero (occu_grid_map.h:367)
+      return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: check_point_num = 1 with 2 or more points");
+  const double ox = sensor_origin_xy ? sensor_origin_xy[0] : 0.0, oy = sensor_origin_xy ? sensor_origin_xy[1] : 0.0;
+  const size_t pts_bytes = dev_pts ? 0 : size_t(hi - lo) * 16;
+  Layout dl;
+  const size_t o_jobs = dl.take(sizeof(PenaltyJob) * size_t(n));
+  const size_t o_pts = dl.take(pts_bytes, 16);
+  const size_t up_bytes = dl.off;
+  const size_t o_out = dl.take(size_t(n) * 4, 16);
+  int rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_down, size_t(n) * 4);
+  if (rc) return rc;
+  char* dw = ctx->d_work.p;
+  char* up = ctx->h_up.p;
+  if (pts_bytes) std::memcpy(up + o_pts, pts_xy + 2 * lo, pts_bytes);
+  PenaltyJob* jobs = reinterpret_cast<PenaltyJob*>(up + o_jobs);
+  std::vector<char> outside(n, 0);
+  for (int i = 0; i < n; ++i) {
+    PenaltyJob& J = jobs[i];
+    std::memset(&J, 0, sizeof J);
+    double pm[3];
+    pub_map->tf.world_to_map(poses_world + 3 * i, pm);                                   // :349
+    // PointInMap(x, y) is strict on both sides (grid_map_base.h:339-346); outside -> 0.0 (:351-353)
+    outside[i] = !(pm[0] > 0.0 && pm[0] < pub_map->size_x && pm[1] > 0.0 && pm[1] < pub_map->size_y);
+    const double c = std::cos(pm[2]), sn = std::sin(pm[2]);                              // Rotation2Dd, host libm
+    J.c = c; J.s = sn; J.tx = pm[0]; J.ty = pm[1];
+    J.sx0 = static_cast<int>((pm[0] + (c * ox + (-sn) * oy)) + 0.5);                      // :357-359
+    J.sy0 = static_cast<int>((pm[1] + (sn * ox + c * oy)) + 0.5);
+    const int all = pts_count[i];
+    J.n_pts = outside[i] ? 0 : all;
+    J.step = (all < 2 * check_point_num) ? 1 : all / (check_point_num - 1);                // :361-368
+    J.pts = dev_pts ? dev_pts[i] : reinterpret_cast<const double*>(dw + o_pts) + 2 * (pts_begin[i] - lo);
+    J.blocked = reinterpret_cast<int*>(dw + o_out) + i;
+  }
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_penalty(n, ctx->stream, reinterpret_cast<const PenaltyJob*>(dw + o_jobs), pub_map->d_occ, pub_map->size_x,
+                    pub_map->size_y, bound_tolerance));
+  CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_out, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.h2d_bytes += up_bytes; ctx->stats.d2h_bytes += size_t(n) * 4; ctx->stats.kernel_launches++;
+  const int* blocked = reinterpret_cast<const int*>(ctx->h_down.p);
+  for (int i = 0; i < n; ++i) {
+    double coeff;
+    if (outside[i]) coeff = 0.0;
+    else {
+      double penalty = double(blocked[i]);            // the reference adds 1.0 per blocked ray
+      penalty *= penalty_gain;
+      coeff = std::max((1.0 + 2 * penalty_gain - penalty), 0.1);                           // :389-390
+    }
+    if (use_logistic) coeff = (1 / (1 + std::exp(-10 * (coeff - 0.4))));                   // slam_processor.cpp:589-591
+    coeff_out[i] = coeff;
+  }
+  return RSM_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1348,77 +1429,17 @@ int rsm_map_check_penalize(rsm_ctx* ctx, const rsm_grid* pub_map, int n, const d
     return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: bad arguments");
   if (n == 0) return RSM_OK;
   if (!pub_map->d_occ) return fail(ctx, RSM_ERR_NOT_INIT, "rsm_map_check_penalize: no occupancy uploaded for this map");
-  // occu_grid_map.h:337-341: out-of-range knobs switch the check off
-  if (bound_tolerance < 0 || check_point_num <= 0 || penalty_gain <= 0.0 || penalty_gain >= 1.0) {
-    for (int i = 0; i < n; ++i) coeff_out[i] = use_logistic ? (1 / (1 + std::exp(-10 * (1.0 - 0.4)))) : 1.0;
-    return RSM_OK;
-  }
-  const double ox = sensor_origin_xy ? sensor_origin_xy[0] : 0.0, oy = sensor_origin_xy ? sensor_origin_xy[1] : 0.0;
   int64_t lo = INT64_MAX, hi = 0;
   for (int i = 0; i < n; ++i) {
     if (pts_count[i] < 0 || pts_begin[i] < 0) return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: bad point range");
-    if (check_point_num == 1 && pts_count[i] >= 2)   // the reference divides by zero (occu_grid_map.h:367)
-      return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: check_point_num = 1 with 2 or more points");
     if (pts_count[i] == 0) continue;
     lo = std::min(lo, pts_begin[i]);
     hi = std::max(hi, pts_begin[i] + pts_count[i]);
   }
   if (hi <= lo) { lo = 0; hi = 0; }
   if (hi > lo && !pts_xy) return fail(ctx, RSM_ERR_INVALID, "rsm_map_check_penalize: pts_xy is null");
-  const size_t pts_bytes = size_t(hi - lo) * 16;
-  Layout dl;
-  const size_t o_jobs = dl.take(sizeof(PenaltyJob) * size_t(n));
-  const size_t o_pts = dl.take(pts_bytes, 16);
-  const size_t up_bytes = dl.off;
-  const size_t o_out = dl.take(size_t(n) * 4, 16);
-  int rc = ensure_dev(ctx, ctx->d_work, dl.off);
-  if (rc) return rc;
-  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
-  if (rc) return rc;
-  rc = ensure_pinned(ctx, ctx->h_down, size_t(n) * 4);
-  if (rc) return rc;
-  char* dw = ctx->d_work.p;
-  char* up = ctx->h_up.p;
-  if (pts_bytes) std::memcpy(up + o_pts, pts_xy + 2 * lo, pts_bytes);
-  PenaltyJob* jobs = reinterpret_cast<PenaltyJob*>(up + o_jobs);
-  std::vector<char> outside(n, 0);
-  for (int i = 0; i < n; ++i) {
-    PenaltyJob& J = jobs[i];
-    std::memset(&J, 0, sizeof J);
-    double pm[3];
-    pub_map->tf.world_to_map(poses_world + 3 * i, pm);                                   // :349
-    // PointInMap(x, y) is strict on both sides (grid_map_base.h:339-346); outside -> 0.0 (:351-353)
-    outside[i] = !(pm[0] > 0.0 && pm[0] < pub_map->size_x && pm[1] > 0.0 && pm[1] < pub_map->size_y);
-    const double c = std::cos(pm[2]), sn = std::sin(pm[2]);                              // Rotation2Dd, host libm
-    J.c = c; J.s = sn; J.tx = pm[0]; J.ty = pm[1];
-    J.sx0 = static_cast<int>((pm[0] + (c * ox + (-sn) * oy)) + 0.5);                      // :357-359
-    J.sy0 = static_cast<int>((pm[1] + (sn * ox + c * oy)) + 0.5);
-    const int all = pts_count[i];
-    J.n_pts = outside[i] ? 0 : all;
-    J.step = (all < 2 * check_point_num) ? 1 : all / (check_point_num - 1);                // :361-368
-    J.pts = reinterpret_cast<const double*>(dw + o_pts) + 2 * (pts_begin[i] - lo);
-    J.blocked = reinterpret_cast<int*>(dw + o_out) + i;
-  }
-  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(launch_penalty(n, ctx->stream, reinterpret_cast<const PenaltyJob*>(dw + o_jobs), pub_map->d_occ, pub_map->size_x,
-                    pub_map->size_y, bound_tolerance));
-  CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_out, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  rc = sync_stream(ctx);
-  if (rc) return rc;
-  ctx->stats.h2d_bytes += up_bytes; ctx->stats.d2h_bytes += size_t(n) * 4; ctx->stats.kernel_launches++;
-  const int* blocked = reinterpret_cast<const int*>(ctx->h_down.p);
-  for (int i = 0; i < n; ++i) {
-    double coeff;
-    if (outside[i]) coeff = 0.0;
-    else {
-      double penalty = double(blocked[i]);            // the reference adds 1.0 per blocked ray
-      penalty *= penalty_gain;
-      coeff = std::max((1.0 + 2 * penalty_gain - penalty), 0.1);                           // :389-390
-    }
-    if (use_logistic) coeff = (1 / (1 + std::exp(-10 * (coeff - 0.4))));                   // slam_processor.cpp:589-591
-    coeff_out[i] = coeff;
-  }
-  return RSM_OK;
+  return map_check_core(ctx, pub_map, n, poses_world, pts_xy, lo, hi, pts_begin, nullptr, pts_count, sensor_origin_xy,
+                        check_point_num, bound_tolerance, penalty_gain, use_logistic, coeff_out);
 }
 
 int rsm_grid_is_fixed_point(const rsm_grid* grid) { return grid && grid->fixed ? 1 : 0; }
@@ -1699,17 +1720,22 @@ int rsm_match_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const dou
   return run_chain(ctx, n, grids, dp.data(), np.data(), params, shared_params != 0, use_fine != 0, poses_world, covs, scores, responses);
 }
 
-int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob, double sigma,
-                           double occu_offset, const double* centres_world, const int64_t* scan_offset,
-                           const int32_t* base_n_pts, const double* base_pts_xy, const double* base_poses_world,
-                           const double* pts_xy, const int64_t* pts_offset, const rsm_pass_param params[3], int use_fine,
-                           double* poses_world, double* covs, double* scores, double* responses) {
-  DeviceGuard device_guard(ctx);
-  if (!ctx || n < 0 || grid_size <= 0 || !(resolution > 0) ||
-      (n > 0 && (!centres_world || !scan_offset || !base_n_pts || !base_pts_xy || !base_poses_world || !pts_xy ||
-                 !pts_offset || !params || !poses_world || !covs || !scores)))
-    return fail(ctx, RSM_ERR_INVALID, "rsm_loop_closure_batch: bad arguments");
-  if (n == 0) return RSM_OK;
+}  // extern "C"
+
+namespace {
+
+struct BaseRef { const double* d_pts; int n; const double* pose_world; };   // one base scan of a chain
+
+// ScanMatchInterface for n (scan, chain) pairs (slam/slam_processor.cpp:250-326): per pair reset a
+// grid_size^2 grid centred on centres_world[2i..] from the pair's base scans (:448-462), run the chain, and --
+// when a publishing map is given -- scale the score by the map check and clamp it to 1 (:313-317).
+// base[scan_offset[i] .. scan_offset[i+1]) = base scans of pair i, all points already on the device.
+int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob, double sigma,
+                      double occu_offset, const double* centres_world, const int64_t* scan_offset,
+                      const std::vector<BaseRef>& base, double* const* dp, const int* np, const rsm_pass_param* params,
+                      bool use_fine, double* poses_world, double* covs, double* scores, double* responses,
+                      const rsm_grid* pub_map, const double* const* pub_pts, const int32_t* pub_counts,
+                      const rsm_map_check_param* check) {
   RasterPlan pl;
   int rc = plan_raster(ctx, default_prob, sigma, resolution, occu_offset, 1, pl);
   if (rc) return rc;
@@ -1736,18 +1762,7 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
     g.init = scan_offset[i + 1] > scan_offset[i];
     gp[i] = &g;
   }
-  // points: [base scans | match scans] in one upload
   const int64_t n_base_scans = scan_offset[n];
-  size_t base_pts_total = 0;
-  for (int64_t s = 0; s < n_base_scans; ++s) base_pts_total += size_t(base_n_pts[s]);
-  const size_t match_pts_total = size_t(pts_offset[n]);
-  rc = ensure_dev(ctx, ctx->d_pts, (base_pts_total + match_pts_total) * 16);
-  if (rc) return rc;
-  double* d_base = reinterpret_cast<double*>(ctx->d_pts.p);
-  double* d_match = d_base + 2 * base_pts_total;
-  if (base_pts_total) CU(cudaMemcpyAsync(d_base, base_pts_xy, base_pts_total * 16, cudaMemcpyHostToDevice, ctx->stream));
-  if (match_pts_total) CU(cudaMemcpyAsync(d_match, pts_xy, match_pts_total * 16, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->stats.h2d_bytes += (base_pts_total + match_pts_total) * 16;
   // raster descriptors
   Layout dl;
   const size_t o_fill = dl.take(sizeof(FillJob) * n);
@@ -1762,13 +1777,10 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
   char* dw = ctx->d_work.p;
   FillJob* hf = reinterpret_cast<FillJob*>(up + o_fill);
   RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
-  size_t poff = 0;
   for (int i = 0; i < n; ++i) {
     hf[i].grid = gs[i].d_cells; hf[i].n_cells = (long long)cells; hf[i].value = pl.fill;
-    for (int64_t s = scan_offset[i]; s < scan_offset[i + 1]; ++s) {
-      make_raster_scan(&gs[i], base_poses_world + 3 * s, d_base + 2 * poff, base_n_pts[s], hs[s]);
-      poff += base_n_pts[s];
-    }
+    for (int64_t s = scan_offset[i]; s < scan_offset[i + 1]; ++s)
+      make_raster_scan(&gs[i], base[s].pose_world, base[s].d_pts, base[s].n, hs[s]);
   }
   std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
   CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1783,10 +1795,160 @@ int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution
   // run_pass reuses d_work and the pinned staging: the raster launches above must have consumed them first
   rc = sync_stream(ctx);
   if (rc) return rc;
+  rc = run_chain(ctx, n, gp.data(), dp, np, params, true, use_fine, poses_world, covs, scores, responses);
+  if (rc || !pub_map) return rc;
+  // MapCheckPenalize(pub_map_range_data, best_pose, true) on the matched poses (slam_processor.cpp:313-317)
+  std::vector<double> coeff(n);
+  rc = map_check_core(ctx, pub_map, n, poses_world, nullptr, 0, 0, nullptr, pub_pts, pub_counts, nullptr,
+                      check->check_point_num, check->bound_tolerance, check->penalty_gain, check->use_logistic, coeff.data());
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    scores[i] *= coeff[i];
+    scores[i] = (scores[i] > 1.0) ? (1.0) : (scores[i]);
+  }
+  return RSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsm_loop_closure_batch(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob, double sigma,
+                           double occu_offset, const double* centres_world, const int64_t* scan_offset,
+                           const int32_t* base_n_pts, const double* base_pts_xy, const double* base_poses_world,
+                           const double* pts_xy, const int64_t* pts_offset, const rsm_pass_param params[3], int use_fine,
+                           double* poses_world, double* covs, double* scores, double* responses) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || n < 0 || grid_size <= 0 || !(resolution > 0) ||
+      (n > 0 && (!centres_world || !scan_offset || !base_n_pts || !base_pts_xy || !base_poses_world || !pts_xy ||
+                 !pts_offset || !params || !poses_world || !covs || !scores)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_loop_closure_batch: bad arguments");
+  if (n == 0) return RSM_OK;
+  // points: [base scans | match scans] in one device buffer
+  const int64_t n_base_scans = scan_offset[n];
+  size_t base_pts_total = 0;
+  for (int64_t s = 0; s < n_base_scans; ++s) base_pts_total += size_t(base_n_pts[s]);
+  const size_t match_pts_total = size_t(pts_offset[n]);
+  int rc = ensure_dev(ctx, ctx->d_pts, (base_pts_total + match_pts_total) * 16);
+  if (rc) return rc;
+  double* d_base = reinterpret_cast<double*>(ctx->d_pts.p);
+  double* d_match = d_base + 2 * base_pts_total;
+  if (base_pts_total) CU(cudaMemcpyAsync(d_base, base_pts_xy, base_pts_total * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (match_pts_total) CU(cudaMemcpyAsync(d_match, pts_xy, match_pts_total * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += (base_pts_total + match_pts_total) * 16;
+  std::vector<BaseRef> base(n_base_scans);
+  size_t poff = 0;
+  for (int64_t s = 0; s < n_base_scans; ++s) {
+    base[s] = BaseRef{d_base + 2 * poff, base_n_pts[s], base_poses_world + 3 * s};
+    poff += base_n_pts[s];
+  }
   std::vector<double*> dp(n);
   std::vector<int> np(n);
   for (int i = 0; i < n; ++i) { dp[i] = d_match + 2 * pts_offset[i]; np[i] = int(pts_offset[i + 1] - pts_offset[i]); }
-  return run_chain(ctx, n, gp.data(), dp.data(), np.data(), params, true, use_fine != 0, poses_world, covs, scores, responses);
+  return loop_closure_core(ctx, n, grid_size, resolution, default_prob, sigma, occu_offset, centres_world, scan_offset,
+                           base, dp.data(), np.data(), params, use_fine != 0, poses_world, covs, scores, responses,
+                           nullptr, nullptr, nullptr, nullptr);
+}
+
+// ---- scan store ----------------------------------------------------------------------------------
+int rsm_scan_store_create(rsm_ctx* ctx, rsm_scan_store** out) {
+  if (!ctx || !out) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_store_create: null argument");
+  *out = new rsm_scan_store;
+  return RSM_OK;
+}
+
+void rsm_scan_store_destroy(rsm_ctx* ctx, rsm_scan_store* store) {
+  DeviceGuard device_guard(ctx);
+  if (!store) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (void* c : store->chunks) cudaFree(c);
+  delete store;
+}
+
+int rsm_scan_store_size(const rsm_scan_store* store) { return store ? int(store->scans.size()) : 0; }
+
+int rsm_scan_store_add(rsm_ctx* ctx, rsm_scan_store* store, const double* pts_xy, int n_pts, const double pose_world[3],
+                       int32_t* id_out) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !store || n_pts < 0 || (n_pts > 0 && !pts_xy) || !pose_world)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_scan_store_add: bad arguments");
+  const size_t bytes = (size_t(n_pts) * 16 + 255) / 256 * 256;
+  if (store->chunks.empty() || store->chunk_used + bytes > store->chunk_cap) {
+    const size_t cap = std::max<size_t>(bytes, size_t(16) << 20);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(scan store) failed: %s", cudaGetErrorString(e));
+    store->chunks.push_back(p); store->chunk_used = 0; store->chunk_cap = cap;
+  }
+  rsm_scan_store::Entry E;
+  E.d_pts = reinterpret_cast<double*>(static_cast<char*>(store->chunks.back()) + store->chunk_used);
+  E.n = n_pts;
+  for (int k = 0; k < 3; ++k) E.pose[k] = pose_world[k];
+  if (n_pts > 0) {
+    CU(cudaMemcpyAsync(E.d_pts, pts_xy, size_t(n_pts) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sync_stream(ctx);   // the caller's array is only borrowed for the call
+    if (rc) return rc;
+    ctx->stats.h2d_bytes += size_t(n_pts) * 16;
+  }
+  store->chunk_used += bytes;
+  store->scans.push_back(E);
+  if (id_out) *id_out = int32_t(store->scans.size() - 1);
+  return RSM_OK;
+}
+
+int rsm_scan_store_set_poses(rsm_ctx* ctx, rsm_scan_store* store, int n, const int32_t* ids, const double* poses_world) {
+  if (!ctx || !store || n < 0 || (n > 0 && (!ids || !poses_world)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_scan_store_set_poses: bad arguments");
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || size_t(ids[i]) >= store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_store_set_poses: unknown scan id %d", ids[i]);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) store->scans[ids[i]].pose[k] = poses_world[3 * i + k];
+  return RSM_OK;
+}
+
+int rsm_scan_store_get_pose(const rsm_scan_store* store, int32_t id, double pose_world[3]) {
+  if (!store || !pose_world || id < 0 || size_t(id) >= store->scans.size()) return RSM_ERR_INVALID;
+  for (int k = 0; k < 3; ++k) pose_world[k] = store->scans[id].pose[k];
+  return RSM_OK;
+}
+
+int rsm_scan_match_interface_batch(rsm_ctx* ctx, const rsm_scan_store* store, int n, int grid_size, double resolution,
+                                   float default_prob, double sigma, double occu_offset, const double* centres_world,
+                                   const int64_t* chain_offset, const int32_t* chain_ids, const int32_t* match_ids,
+                                   const rsm_pass_param params[3], int use_fine, double* poses_world, double* covs,
+                                   double* scores, double* responses, const rsm_grid* pub_map,
+                                   const rsm_scan_store* pub_store, const rsm_map_check_param* check) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !store || n < 0 || grid_size <= 0 || !(resolution > 0) ||
+      (n > 0 && (!centres_world || !chain_offset || !match_ids || !params || !poses_world || !covs || !scores)) ||
+      (pub_map && (!pub_store || !check)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: bad arguments");
+  if (n == 0) return RSM_OK;
+  if (pub_map && !pub_map->d_occ) return fail(ctx, RSM_ERR_NOT_INIT, "rsm_scan_match_interface_batch: no occupancy uploaded for the publishing map");
+  const int64_t n_entries = chain_offset[n];
+  if (n_entries < 0 || (n_entries > 0 && !chain_ids)) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: bad chain list");
+  const size_t have = store->scans.size();
+  std::vector<BaseRef> base(n_entries);
+  for (int64_t s = 0; s < n_entries; ++s) {
+    if (chain_ids[s] < 0 || size_t(chain_ids[s]) >= have) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: unknown scan id %d", chain_ids[s]);
+    const rsm_scan_store::Entry& E = store->scans[chain_ids[s]];
+    base[s] = BaseRef{E.d_pts, E.n, E.pose};
+  }
+  std::vector<double*> dp(n);
+  std::vector<int> np(n);
+  std::vector<const double*> pub_pts(pub_map ? n : 0);
+  std::vector<int32_t> pub_counts(pub_map ? n : 0);
+  for (int i = 0; i < n; ++i) {
+    if (match_ids[i] < 0 || size_t(match_ids[i]) >= have) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: unknown scan id %d", match_ids[i]);
+    dp[i] = store->scans[match_ids[i]].d_pts; np[i] = store->scans[match_ids[i]].n;
+    if (pub_map) {
+      if (size_t(match_ids[i]) >= pub_store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: scan id %d is not in the publishing-map store", match_ids[i]);
+      pub_pts[i] = pub_store->scans[match_ids[i]].d_pts; pub_counts[i] = pub_store->scans[match_ids[i]].n;
+    }
+  }
+  return loop_closure_core(ctx, n, grid_size, resolution, default_prob, sigma, occu_offset, centres_world, chain_offset,
+                           base, dp.data(), np.data(), params, use_fine != 0, poses_world, covs, scores, responses,
+                           pub_map, pub_map ? pub_pts.data() : nullptr, pub_map ? pub_counts.data() : nullptr, check);
 }
 
 int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,

@@ -65,6 +65,12 @@ class Stats(ctypes.Structure):
         return d
 
 
+class MapCheckParamStruct(ctypes.Structure):
+    """rsm_map_check_param"""
+    _fields_ = [("bound_tolerance", c_d), ("penalty_gain", c_d), ("check_point_num", ctypes.c_int32),
+                ("use_logistic", ctypes.c_int32)]
+
+
 # every symbol include/rsm.h declares: (restype, argtypes)
 _PPARAM = ctypes.POINTER(PassParamStruct)
 ABI = {
@@ -101,6 +107,14 @@ ABI = {
     "rsm_match_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, _PPARAM, c_i, c_i, c_p, c_p, c_p, c_p]),
     "rsm_loop_closure_batch": (c_i, [c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                      _PPARAM, c_i, c_p, c_p, c_p, c_p]),
+    "rsm_scan_store_create": (c_i, [c_p, ctypes.POINTER(c_p)]),
+    "rsm_scan_store_destroy": (None, [c_p, c_p]),
+    "rsm_scan_store_add": (c_i, [c_p, c_p, c_p, c_i, c_p, ctypes.POINTER(ctypes.c_int32)]),
+    "rsm_scan_store_set_poses": (c_i, [c_p, c_p, c_i, c_p, c_p]),
+    "rsm_scan_store_get_pose": (c_i, [c_p, ctypes.c_int32, c_p]),
+    "rsm_scan_store_size": (c_i, [c_p]),
+    "rsm_scan_match_interface_batch": (c_i, [c_p, c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p,
+                                             _PPARAM, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "rsm_pass_scores": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p, c_i64, ctypes.POINTER(c_i64)]),
     "rsm_match_partial": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p]),
     "rsm_match_merge": (c_i, [c_p, c_p, c_i, c_p]),
@@ -522,4 +536,76 @@ def loop_closure_batch(ctx, packed, params, use_fine=True, centres=None):
         packed["base_n"].ctypes.data, packed["base_pts"].ctypes.data, packed["base_poses"].ctypes.data,
         packed["pts"].ctypes.data, packed["pts_off"].ctypes.data, arr, int(use_fine), poses.ctypes.data,
         covs.ctypes.data, scores.ctypes.data, resp.ctypes.data))
+    return scores, poses, covs, resp
+
+
+class ScanStore:
+    """Device-resident scans addressed by id: one resolution of the reference's
+    SensorDataManager::multiresolution_range_data_[name] (sensor_data_manager.h:514-525)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = c_p()
+        ctx.check(ctx.lib.rsm_scan_store_create(ctx.h, ctypes.byref(h)))
+        self.h = h
+
+    def AddRangeData(self, pts_cells, sensor_pose):
+        pts = _f64(np.asarray(pts_cells).reshape(-1, 2))
+        pose = _f64(sensor_pose)
+        out = ctypes.c_int32(-1)
+        self.ctx.check(self.ctx.lib.rsm_scan_store_add(self.ctx.h, self.h, pts.ctypes.data, len(pts), pose.ctypes.data,
+                                                       ctypes.byref(out)))
+        return out.value
+
+    def UpdateRangeData(self, ids, sensor_poses):
+        """SlamProcessor::UpdateRangeData (slam_processor.cpp:597-603) for a list of ids."""
+        ids = np.ascontiguousarray(np.atleast_1d(ids), dtype=np.int32)
+        poses = _f64(np.asarray(sensor_poses).reshape(-1, 3))
+        assert len(ids) == len(poses)
+        self.ctx.check(self.ctx.lib.rsm_scan_store_set_poses(self.ctx.h, self.h, len(ids), ids.ctypes.data, poses.ctypes.data))
+
+    def sensor_pose(self, scan_id):
+        out = np.zeros(3)
+        if self.ctx.lib.rsm_scan_store_get_pose(self.h, int(scan_id), out.ctypes.data) != 0:
+            raise RsmError(3, "unknown scan id %d" % scan_id)
+        return out
+
+    def __len__(self):
+        return int(self.ctx.lib.rsm_scan_store_size(self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.rsm_scan_store_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+def scan_match_interface_batch(ctx, store, grid_spec, centres, chains, match_ids, seed_poses, params, use_fine=True,
+                               pub_map=None, pub_store=None, check=None):
+    """SlamProcessor::ScanMatchInterface (slam_processor.cpp:250-326) for many loop-closure candidates:
+    candidate i matches scan match_ids[i] of `store` against the chain `chains[i]` (list of scan ids) on a
+    back-end grid of grid_spec's size / resolution / blur centred on centres[i].  With pub_map / pub_store /
+    check = (check_point_num, bound_tolerance, penalty_gain, use_logistic) the scores end with the map check.
+    Returns (scores, poses, covs, responses)."""
+    n = len(chains)
+    off = np.zeros(n + 1, dtype=np.int64)
+    for i, ch in enumerate(chains):
+        off[i + 1] = off[i] + len(ch)
+    ids = np.ascontiguousarray(np.concatenate([np.asarray(ch, dtype=np.int32) for ch in chains]) if n else np.zeros(0), dtype=np.int32)
+    mids = np.ascontiguousarray(match_ids, dtype=np.int32)
+    arr = (PassParamStruct * 3)(*[_as_param(p).struct() for p in params])
+    poses = _f64(np.asarray(seed_poses).reshape(-1, 3)).copy()
+    covs = np.tile(np.eye(3), (n, 1, 1))
+    scores = np.zeros(n)
+    resp = np.zeros((n, 3))
+    c = _f64(np.asarray(centres).reshape(-1, 2))
+    g = grid_spec
+    chk = None
+    if pub_map is not None:
+        chk = MapCheckParamStruct(float(check[1]), float(check[2]), int(check[0]), int(bool(check[3])))
+    ctx.check(ctx.lib.rsm_scan_match_interface_batch(
+        ctx.h, store.h, n, int(g.size_x), float(g.res), float(g.default_prob), float(g.sigma), float(g.occu_offset),
+        c.ctypes.data, off.ctypes.data, ids.ctypes.data, mids.ctypes.data, arr, int(use_fine), poses.ctypes.data,
+        covs.ctypes.data, scores.ctypes.data, resp.ctypes.data,
+        pub_map.h if pub_map is not None else None, pub_store.h if pub_store is not None else None,
+        ctypes.byref(chk) if chk is not None else None))
     return scores, poses, covs, resp

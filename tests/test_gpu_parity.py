@@ -511,3 +511,89 @@ def test_mapcheck_errors(ctx):
     assert np.array_equal(pm.MapCheckPenalize(np.array([[5.0, 1.0], [0.0, 7.0]]), np.array([[0.5, 0.4, 0.1]]), 100, 2.5, 0.015),
                           np.array([1.0 + 2 * 0.015]))
     pm.close()
+
+
+# ---- scan store + batched ScanMatchInterface ---------------------------------
+def test_scan_store_interface_batch(ctx, oracle):
+    """rsm_scan_match_interface_batch: chains and match scans named by id in a device-resident store,
+    back-end grid reset + chain + map check per candidate, against the oracle run candidate by candidate
+    (slam_processor.cpp:250-326); pose updates of stored scans (UpdateRangeData) are followed."""
+    from helpers import load_mapcheck
+    pairs = synth.config4(4)                       # pair 0 = the scenario the mapcheck_pair0 fixture was built on
+    store, pub_store = matcher.ScanStore(ctx), matcher.ScanStore(ctx)
+    chains, match_ids = [], []
+    for sc in pairs:
+        ids = [store.AddRangeData(p, pose) for p, pose in zip(sc.base_pts, sc.base_poses)]
+        mid = store.AddRangeData(sc.scan_pts, sc.seed_pose)
+        for p, pose in zip(sc.base_pts, sc.base_poses):
+            pub_store.AddRangeData(p, pose)
+        assert pub_store.AddRangeData(sc.scan_pts, sc.seed_pose) == mid
+        chains.append(ids)
+        match_ids.append(mid)
+    assert len(store) == len(pub_store) == 4 * 9 and np.array_equal(store.sensor_pose(chains[1][2]), pairs[1].base_poses[2])
+    # candidates: every pair against its own chain, pair 0's scan against a sub-chain and against a chain
+    # mixing scans of two pairs, one candidate with an empty chain (grid not initialised -> 0, pose untouched)
+    cands = [(i, chains[i], pairs[i].grid_centre, pairs[i].seed_pose) for i in range(4)]
+    cands.append((0, chains[0][2:6], pairs[0].grid_centre, pairs[0].seed_pose + np.array([0.03, 0.02, -0.04])))
+    cands.append((0, chains[0][:4] + chains[1][:2], pairs[0].grid_centre, pairs[0].seed_pose))
+    cands.append((1, [], pairs[1].grid_centre, pairs[1].seed_pose))
+    g0 = pairs[0].grid
+    gpub, occ, _ = load_mapcheck("mapcheck_pair0")
+    pm = matcher.ScanMatchMap.from_spec(ctx, gpub)
+    pm.upload_occupancy(occ)
+    check = (100, 2.5, 0.015, True)
+
+    def flat(ids):
+        out_pts, out_poses = [], []
+        for i in ids:
+            p, k = divmod(i, 9)
+            out_pts.append(pairs[p].base_pts[k])
+            out_poses.append(store.sensor_pose(i))
+        return out_pts, np.array(out_poses).reshape(-1, 3)
+
+    def expected(with_check):
+        want = []
+        for who, ids, centre, seed in cands:
+            sc = pairs[who]
+            g = synth.backend_grid(g0.res, g0.sigma, 10.0, centre)
+            assert (g.size_x, g.off_x) == (g0.size_x, sc.grid.off_x)
+            if not ids:
+                want.append(dict(score=0.0, pose=np.asarray(seed, dtype=np.float64), responses=np.zeros(3), cov=np.eye(3)))
+                continue
+            bpts, bposes = flat(ids)
+            grid = oracle.build_grid(g, bpts, bposes)
+            w = oracle.match_chain(grid, g, sc.scan_pts, sc.passes, seed)
+            if with_check:
+                c = oracle.map_check_penalize(occ, gpub, sc.scan_pts, w["pose"], *check)
+                s = w["score"] * c
+                w = dict(w, score=1.0 if s > 1.0 else s)
+            want.append(w)
+        return want
+
+    def run(with_check):
+        return matcher.scan_match_interface_batch(
+            ctx, store, g0, [c[2] for c in cands], [c[1] for c in cands], [match_ids[c[0]] for c in cands],
+            [c[3] for c in cands], pairs[0].passes, True,
+            pm if with_check else None, pub_store if with_check else None, check if with_check else None)
+
+    for with_check in (False, True):
+        scores, poses, covs, resp = run(with_check)
+        for i, w in enumerate(expected(with_check)):
+            assert scores[i] == w["score"], (with_check, i, scores[i], w["score"])
+            assert np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"])
+            assert np.array_equal(resp[i], w["responses"])
+    assert expected(True)[1]["score"] == 0.0 or expected(True)[1]["score"] < expected(False)[1]["score"]
+    # the pose graph moves two stored scans: the next batch rasterises them at their new poses
+    store.UpdateRangeData([chains[0][1], chains[0][5]],
+                          [pairs[0].base_poses[1] + np.array([0.07, -0.03, 0.02]), pairs[0].base_poses[5] + np.array([-0.05, 0.04, -0.03])])
+    scores, poses, covs, resp = run(False)
+    for i, w in enumerate(expected(False)):
+        assert scores[i] == w["score"] and np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"])
+    # errors: unknown ids
+    with pytest.raises(matcher.RsmError) as e:
+        matcher.scan_match_interface_batch(ctx, store, g0, [pairs[0].grid_centre], [[0, 999]], [match_ids[0]],
+                                           [pairs[0].seed_pose], pairs[0].passes)
+    assert "RSM_ERR_INVALID" in str(e.value)
+    pm.close()
+    store.close()
+    pub_store.close()

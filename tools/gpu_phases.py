@@ -51,3 +51,23 @@ for npairs in ((64,) if QUICK else (64, 256)):
         wall = (time.perf_counter() - t0) / n
         st = ctx.stats()
         show("loop_closure %d pairs profiling=%s wall %.2f ms (%.0f matches/s, %.3g evals/s)" % (npairs, prof, wall * 1e3, npairs / wall, st["evals"] / n / wall), st, n)
+    # the same pairs from a device-resident scan store (ids only travel)
+    st_ = matcher.ScanStore(ctx)
+    chains, mids = [], []
+    for sc_ in pairs:
+        chains.append([st_.AddRangeData(p, q) for p, q in zip(sc_.base_pts, sc_.base_poses)])
+        mids.append(st_.AddRangeData(sc_.scan_pts, sc_.seed_pose))
+    centres = [sc_.grid_centre for sc_ in pairs]
+    seeds = [sc_.seed_pose for sc_ in pairs]
+    for prof in (False, True):
+        ctx.set_profiling(prof)
+        matcher.scan_match_interface_batch(ctx, st_, pairs[0].grid, centres, chains, mids, seeds, pairs[0].passes)
+        ctx.reset_stats()
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            matcher.scan_match_interface_batch(ctx, st_, pairs[0].grid, centres, chains, mids, seeds, pairs[0].passes)
+        wall = (time.perf_counter() - t0) / n
+        st = ctx.stats()
+        show("store loop_closure %d pairs profiling=%s wall %.2f ms (%.0f matches/s, %.3g evals/s) raster_k %.1f us" % (npairs, prof, wall * 1e3, npairs / wall, st["evals"] / n / wall, st["raster_kernel_ms"] * 1e3 / n), st, n)
+    st_.close()

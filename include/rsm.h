@@ -262,6 +262,42 @@ int rsm_scan_match_interface_batch(rsm_ctx* ctx, const rsm_scan_store* store, in
                                    const rsm_scan_store* pub_store /* nullable */,
                                    const rsm_map_check_param* check /* nullable */);
 
+/* ---- Gauss-Newton matcher ----------------------------------------------
+ * OptimizeScanMatchParam, scan_match/optimize_scan_matcher.h:33-58 */
+typedef struct rsm_optimize_param {
+  double cost_decrease_threshold;
+  double cost_min_threshold;
+  double max_update_distance;   /* metres */
+  double max_update_angle;      /* radians */
+  int32_t iterate_max_times;    /* >= 1 */
+  int32_t reserved;
+} rsm_optimize_param;
+
+/* rsm_optimize: replaces BasedOptimizeScanMatch::ScanMatch(map, range_data, param, best_pose&) -> cost
+ * (scan_match/optimize_scan_matcher.h:68-131): Gauss-Newton on the bilinearly interpolated lookup grid.
+ * pose_world in/out; *cost = the reference's return value (1000 = kMaxCost for an uninitialised grid, an
+ * empty scan or a NaN step, with pose_world untouched); iterations (nullable) = cost evaluations made.
+ * Per-point terms are evaluated on the device and added in point order, so H, b and the cost carry
+ * the reference's bits; the 3x3 solve follows Eigen 3.3's LDLT on the host. */
+int rsm_optimize(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                 const rsm_optimize_param* param, double pose_world[3], double* cost,
+                 int32_t* iterations /* nullable */);
+/* n independent problems, one launch per iteration over those still iterating.  Problem i uses
+ * grids[i] and points pts_xy[pts_offset[i] .. pts_offset[i+1]). */
+int rsm_optimize_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* pts_xy,
+                       const int64_t* pts_offset, const rsm_optimize_param* param, double* poses_world,
+                       double* costs, int32_t* iterations /* nullable */);
+/* rsm_match_chain_opt: ScanMatchers::ScanMatch with use_optimize_scan_match on
+ * (scan_match/scan_matchers.h:179-289): the optimiser on the coarse map with the scan in coarse-map
+ * cells; if it fails (cost > optimize_failed_cost) or use_fine is 0, its result is dropped and the
+ * coarse correlative pass runs from the seed; then fine and super-fine on the fine map.
+ * responses (nullable) = {optimiser cost, coarse, fine, super responses}, 0 for a step not run. */
+int rsm_match_chain_opt(rsm_ctx* ctx, const rsm_grid* coarse_grid, const double* pts_coarse, int n_coarse,
+                        const rsm_grid* fine_grid, const double* pts_fine, int n_fine,
+                        const rsm_pass_param params[3], const rsm_optimize_param* opt,
+                        double optimize_failed_cost, int use_fine, double pose_world[3], double cov[9],
+                        double* score, double responses[4] /* nullable */);
+
 /* ---- parity / multi-GPU building blocks --------------------------------------------------
  * rsm_pass_scores: penalised score of every candidate of one pass in candidate order
  * k = (angle_index*n_xy + x_index)*n_xy + y_index (the order of correlate_scan_matcher.h:552-584),

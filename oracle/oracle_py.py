@@ -64,6 +64,13 @@ class Oracle:
         L.orc_match.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
         L.orc_match_chain.restype = c_d
         L.orc_match_chain.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        L.orc_optimize.restype = c_d
+        L.orc_optimize.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p]
+        L.orc_optimize_cost.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
+        L.orc_ldlt3_solve.argtypes = [c_p, c_p, c_p]
+        L.orc_match_chain_opt.restype = c_d
+        L.orc_match_chain_opt.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p,
+                                          c_p, c_p, c_d, c_i, c_p, c_p, c_p]
         L.orc_map_check_penalize.restype = c_d
         L.orc_map_check_penalize.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_i, c_d, c_d, c_i]
         self.L = L
@@ -158,6 +165,49 @@ class Oracle:
         return dict(score=r, pose=pose, cov=cov, responses=resp, seconds=sec.value)
 
 
+    # ---- BasedOptimizeScanMatch (optimize_scan_matcher.h) ------------------------------------------
+    # op = (iterate_max_times, cost_decrease_threshold, cost_min_threshold, max_update_distance, max_update_angle)
+    def optimize(self, grid, g, pts, op, pose_world):
+        pts, op = _f64(pts), _f64(op)
+        pose = _f64(pose_world).copy()
+        grid = np.ascontiguousarray(grid, dtype=np.float32)
+        iters, oob = c_i(0), c_l(0)
+        cost = self.L.orc_optimize(grid.ctypes.data, g.size_x, g.size_y, 1.0 / g.res, g.off_x, g.off_y, len(pts),
+                                   pts.ctypes.data, op.ctypes.data, pose.ctypes.data, ctypes.byref(iters), ctypes.byref(oob))
+        return dict(cost=cost, pose=pose, iterations=iters.value, oob_reads=oob.value)
+
+    def optimize_cost(self, grid, g, pts, pose_map):
+        pts, pm = _f64(pts), _f64(pose_map)
+        grid = np.ascontiguousarray(grid, dtype=np.float32)
+        H, b, cost = np.zeros((3, 3)), np.zeros(3), c_d(0)
+        self.L.orc_optimize_cost(grid.ctypes.data, g.size_x, g.size_y, len(pts), pts.ctypes.data, pm.ctypes.data,
+                                 H.ctypes.data, b.ctypes.data, ctypes.byref(cost))
+        return H, b, cost.value
+
+    def ldlt3_solve(self, H, b):
+        Hc = _f64(np.asarray(H).T)      # column-major
+        b = _f64(b)
+        x = np.zeros(3)
+        self.L.orc_ldlt3_solve(Hc.ctypes.data, b.ctypes.data, x.ctypes.data)
+        return x
+
+    def match_chain_opt(self, grid_c, g_c, pts_c, grid_f, g_f, pts_f, params, op, failed_cost, pose_world, cov=None,
+                        use_fine=True):
+        pts_c, pts_f, op = _f64(pts_c), _f64(pts_f), _f64(op)
+        params = _f64(np.concatenate(params))
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        grid_c = np.ascontiguousarray(grid_c, dtype=np.float32)
+        grid_f = np.ascontiguousarray(grid_f, dtype=np.float32)
+        resp = np.zeros(4)
+        r = self.L.orc_match_chain_opt(grid_c.ctypes.data, g_c.size_x, g_c.size_y, 1.0 / g_c.res, g_c.off_x, g_c.off_y,
+                                       len(pts_c), pts_c.ctypes.data, grid_f.ctypes.data, g_f.size_x, g_f.size_y,
+                                       1.0 / g_f.res, g_f.off_x, g_f.off_y, len(pts_f), pts_f.ctypes.data,
+                                       params.ctypes.data, op.ctypes.data, float(failed_cost), int(use_fine),
+                                       pose.ctypes.data, cov.ctypes.data, resp.ctypes.data)
+        return dict(score=r, pose=pose, cov=cov, optimize_cost=resp[0], responses=resp[1:].copy())
+
+
 class Ref:
     """The reference's own code.  A 'map' here is an opaque handle to a live ScanMatchMap."""
 
@@ -189,6 +239,10 @@ class Ref:
         L.ref_match_chain.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
         L.ref_blur_kernel.restype = c_i
         L.ref_blur_kernel.argtypes = [c_d, c_d, c_p, c_i]
+        L.ref_optimize.restype = c_d
+        L.ref_optimize.argtypes = [c_p, c_i, c_p, c_p, c_p]
+        L.ref_match_chain_opt.restype = c_d
+        L.ref_match_chain_opt.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_d, c_i, c_p, c_p, c_p]
         L.ref_pubmap_create.restype = c_p
         L.ref_pubmap_create.argtypes = [c_d, c_i, c_i, c_d, c_d, ctypes.c_float]
         L.ref_pubmap_destroy.argtypes = [c_p]
@@ -227,6 +281,24 @@ class Ref:
                                          org.ctypes.data if org is not None else None, int(check_point_num),
                                          float(bound_tolerance), float(penalty_gain), 1 if use_blur else 0,
                                          1 if use_logistic else 0)
+
+    def optimize(self, m, pts, op, pose_world):
+        """The reference's BasedOptimizeScanMatch::ScanMatch (LDLT solve = the stand-in's restatement of Eigen's)."""
+        pts, op = _f64(pts), _f64(op)
+        pose = _f64(pose_world).copy()
+        cost = self.L.ref_optimize(m, len(pts), pts.ctypes.data, op.ctypes.data, pose.ctypes.data)
+        return dict(cost=cost, pose=pose)
+
+    def match_chain_opt(self, m_c, pts_c, m_f, pts_f, params, op, failed_cost, pose_world, cov=None, use_fine=True):
+        pts_c, pts_f, op = _f64(pts_c), _f64(pts_f), _f64(op)
+        params = _f64(np.concatenate(params))
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        resp = np.zeros(4)
+        r = self.L.ref_match_chain_opt(m_c, len(pts_c), pts_c.ctypes.data, m_f, len(pts_f), pts_f.ctypes.data,
+                                       params.ctypes.data, op.ctypes.data, float(failed_cost), int(use_fine),
+                                       pose.ctypes.data, cov.ctypes.data, resp.ctypes.data)
+        return dict(score=r, pose=pose, cov=cov, optimize_cost=resp[0], responses=resp[1:].copy())
 
     def blur_kernel(self, sigma, res):
         k = np.zeros(21 * 21, dtype=np.float64)

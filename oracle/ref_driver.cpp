@@ -10,10 +10,12 @@
 //   * OccuGridMap<ProbabilityCell>::InitMapWithRangeVec   (occu_grid_map.h:222-329)
 //   * MultiResolutionCorrelateScanMatcher::ScanMatch      (correlate_scan_matcher.h:516-614)
 //   * BasedCorrelationScanMatch::ScanMatch                (correlate_scan_matcher.h:784-875)
-// on arbitrary inputs.  scan_matchers.h itself cannot be compiled without real Eigen
-// (it pulls in optimize_scan_matcher.h -> LDLT); its 3-pass chain
-// (scan_matchers.h:224-263, optimiser off) is driven here by calling the reference's
-// BasedCorrelationScanMatch three times exactly as those lines do.
+//   * BasedOptimizeScanMatch::ScanMatch                   (optimize_scan_matcher.h:68-131; its
+//     H.ldlt().solve(b) resolves to the stand-in's restatement of Eigen 3.3's LDLT, the one piece
+//     of that function that is therefore NOT the reference's own arithmetic)
+// on arbitrary inputs.  scan_matchers.h itself is not compiled (sensor_data_manager / ROS
+// plumbing); its chain (scan_matchers.h:179-289, optimiser off and on) is driven here by calling
+// the reference's BasedOptimizeScanMatch / BasedCorrelationScanMatch exactly as those lines do.
 //
 // Output: oracle/_ref/libref.so (git-ignored).  Built by oracle/Makefile.
 #include <algorithm>
@@ -26,6 +28,7 @@
 #include <vector>
 
 #include "scan_match/correlate_scan_matcher.h"
+#include "scan_match/optimize_scan_matcher.h"
 #include "map/slam_map.h"
 
 #include "ref_types.h"
@@ -216,6 +219,73 @@ double ref_match_chain(void* m, int n, const double* xy, const double* params, i
   for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) cov[3 * r + k] = c(r, k);
   pose_world[0] = process_pose[0]; pose_world[1] = process_pose[1]; pose_world[2] = process_pose[2];
   return score;
+}
+
+// BasedOptimizeScanMatch::ScanMatch (optimize_scan_matcher.h:68-131) on one map.
+// op = {iterate_max_times, cost_decrease_threshold, cost_min_threshold, max_update_distance, max_update_angle}
+static std::shared_ptr<OptimizeScanMatchParam> MakeOptParam(const double* op) {
+  auto q = std::make_shared<OptimizeScanMatchParam>();
+  q->set_iterate_max_times(static_cast<int>(op[0]));
+  q->set_cost_decrease_threshold(op[1]);
+  q->set_cost_min_threshold(op[2]);
+  q->set_max_update_distance(op[3]);
+  q->set_max_update_angle_(op[4]);
+  return q;
+}
+
+double ref_optimize(void* m, int n, const double* xy, const double* op, double* pose_world) {
+  auto* h = static_cast<RefMap*>(m);
+  auto rd = MakeScan(n, xy, nullptr);
+  BasedOptimizeScanMatch opt;
+  Eigen::Vector3d pose(pose_world[0], pose_world[1], pose_world[2]);
+  double cost = opt.ScanMatch(h->map, rd, MakeOptParam(op), pose);
+  pose_world[0] = pose[0]; pose_world[1] = pose[1]; pose_world[2] = pose[2];
+  return cost;
+}
+
+// ScanMatchers::ScanMatch with use_optimize_scan_match = true (scan_matchers.h:179-289; MapSizeCheck left to
+// the caller): the optimiser runs on the coarse map with the coarse-resolution scan, the correlative passes on
+// the fine map.  resp_out (optional) = {optimiser cost, coarse, fine, super responses} (0 where a step is skipped).
+double ref_match_chain_opt(void* m_coarse, int n_c, const double* xy_c, void* m_fine, int n_f, const double* xy_f,
+                           const double* params, const double* op, double optimize_failed_cost, int use_fine,
+                           double* pose_world, double* cov, double* resp_out) {
+  auto* hc = static_cast<RefMap*>(m_coarse);
+  auto* hf = static_cast<RefMap*>(m_fine);
+  auto rd_c = MakeScan(n_c, xy_c, nullptr);
+  auto rd_f = MakeScan(n_f, xy_f, nullptr);
+  BasedOptimizeScanMatch optimizer;
+  BasedCorrelationScanMatch matcher;
+  Eigen::Vector3d best_pose(pose_world[0], pose_world[1], pose_world[2]);
+  Eigen::Matrix3d c;
+  for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) c(r, k) = cov[3 * r + k];
+  double scan_match_score = 0.0;
+  int scan_match_times = 0;
+  Eigen::Vector3d process_pose(best_pose);
+  double optimize_cost = optimizer.ScanMatch(hc->map, rd_c, MakeOptParam(op), process_pose);
+  scan_match_score = optimize_failed_cost / (optimize_cost + optimize_failed_cost);
+  scan_match_times++;
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  if (!use_fine || optimize_cost > optimize_failed_cost) {
+    scan_match_score = 0.0;
+    scan_match_times--;
+    process_pose = best_pose;
+    r0 = matcher.ScanMatch(hf->map, rd_f, MakeParam(params), process_pose, c);
+    scan_match_score += r0;
+    scan_match_times++;
+  }
+  best_pose = process_pose;
+  if (use_fine) {
+    r1 = matcher.ScanMatch(hf->map, rd_f, MakeParam(params + 8), process_pose, c);
+    scan_match_score += r1; scan_match_times++;
+    r2 = matcher.ScanMatch(hf->map, rd_f, MakeParam(params + 16), process_pose, c);
+    scan_match_score += r2; scan_match_times++;
+  }
+  best_pose = process_pose;
+  scan_match_score /= scan_match_times;
+  if (resp_out) { resp_out[0] = optimize_cost; resp_out[1] = r0; resp_out[2] = r1; resp_out[3] = r2; }
+  for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) cov[3 * r + k] = c(r, k);
+  pose_world[0] = best_pose[0]; pose_world[1] = best_pose[1]; pose_world[2] = best_pose[2];
+  return scan_match_score;
 }
 
 // GaussianBlur kernel as the reference builds it (occu_grid_map.h:83-105): returns half size,

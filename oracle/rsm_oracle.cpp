@@ -16,6 +16,7 @@
 // All citations are file:line under /root/reference/src.  Compiled with -ffp-contract=off:
 // every a*b+c below is two rounded operations, as on the reference's baseline x86-64 build.
 #include <algorithm>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -449,6 +450,220 @@ double orc_match_chain(const float* grid, int size_x, int size_y, double scale, 
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (resp_out) { resp_out[0] = r[0]; resp_out[1] = r[1]; resp_out[2] = r[2]; }
   return score;
+}
+
+}  // extern "C"
+
+namespace {
+
+// ---- BasedOptimizeScanMatch (scan_match/optimize_scan_matcher.h:60-237) ---------------------------
+// Gauss-Newton on the bilinearly interpolated lookup grid.  Pinning: every line below is checked
+// bit for bit against the reference's own header compiled in place (oracle/_ref), EXCEPT the 3x3
+// solve: the reference calls Eigen's H.ldlt().solve(b); real Eigen is not in this image, so both
+// this file and the stand-in header restate Eigen 3.3's LDLT (Cholesky/LDLT.h) -- that one step
+// is "parity unpinned" (it is association-free for 3x3 apart from d22 - (l20*t0 + l21*t1) and the
+// two-term sums of the triangular solves).
+
+// Eigen 3.3 LDLT<Matrix3d>::compute (ldlt_inplace<Lower>::unblocked) + _solve_impl, column-major 3x3.
+void Ldlt3Solve(const double* H /* column-major */, const double* b, double* x) {
+  double m[9];
+  for (int i = 0; i < 9; ++i) m[i] = H[i];
+  auto M = [&](int r, int c) -> double& { return m[c * 3 + r]; };
+  int tr[3];
+  double temp[3];
+  const int n = 3;
+  for (int k = 0; k < n; ++k) {
+    int big = k;
+    double best = std::fabs(M(k, k));
+    for (int i = k + 1; i < n; ++i) if (std::fabs(M(i, i)) > best) { best = std::fabs(M(i, i)); big = i; }
+    tr[k] = big;
+    if (k != big) {
+      const int sz = n - big - 1;
+      for (int j = 0; j < k; ++j) std::swap(M(k, j), M(big, j));
+      for (int i = 0; i < sz; ++i) std::swap(M(big + 1 + i, k), M(big + 1 + i, big));
+      std::swap(M(k, k), M(big, big));
+      for (int i = k + 1; i < big; ++i) { const double t = M(i, k); M(i, k) = M(big, i); M(big, i) = t; }
+    }
+    const int rs = n - k - 1;
+    if (k > 0) {
+      for (int j = 0; j < k; ++j) temp[j] = M(j, j) * M(k, j);
+      double dot = M(k, 0) * temp[0];
+      for (int j = 1; j < k; ++j) dot = dot + M(k, j) * temp[j];
+      M(k, k) -= dot;
+      for (int i = 0; i < rs; ++i)
+        for (int j = 0; j < k; ++j) M(k + 1 + i, k) = M(k + 1 + i, k) + M(k + 1 + i, j) * (-1.0 * temp[j]);
+    }
+    const double akk = M(k, k);
+    const bool pivot_ok = std::fabs(akk) > 0.0;
+    if (k == 0 && !pivot_ok) { for (int j = 0; j < n; ++j) tr[j] = j; break; }
+    if (rs > 0 && pivot_ok) for (int i = 0; i < rs; ++i) M(k + 1 + i, k) /= akk;
+  }
+  for (int i = 0; i < n; ++i) x[i] = b[i];
+  for (int k = 0; k < n; ++k) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
+  for (int i = 1; i < n; ++i) {
+    double sum = M(i, 0) * x[0];
+    for (int j = 1; j < i; ++j) sum = sum + M(i, j) * x[j];
+    x[i] -= sum;
+  }
+  for (int i = 0; i < n; ++i) { if (std::fabs(M(i, i)) > DBL_MIN) x[i] /= M(i, i); else x[i] = 0.0; }
+  for (int i = n - 2; i >= 0; --i) {
+    double sum = M(i + 1, i) * x[i + 1];
+    for (int j = i + 2; j < n; ++j) sum = sum + M(j, i) * x[j];
+    x[i] -= sum;
+  }
+  for (int k = n - 1; k >= 0; --k) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
+}
+
+// util/slam_util.h:79-87
+inline double MaxAbxLimit(double value, double limit) {
+  if (value > std::fabs(limit)) value = std::fabs(limit);
+  else if (value < -std::fabs(limit)) value = -std::fabs(limit);
+  return value;
+}
+// util/slam_util.h:103-111
+inline double NormalizeAngle(double angle) {
+  double a = std::fmod(std::fmod(angle, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI);
+  if (a > M_PI) a -= 2.0 * M_PI;
+  return a;
+}
+
+// UpdateCost (optimize_scan_matcher.h:154-220): H (column-major, symmetric by construction), b, cost
+// for one pose estimate in map cells.  A cell index past the end of the cell array (x1 == size_x in the
+// last row: the reference reads out of bounds there) reads 0.
+void OptimizeCost(const float* grid, int size_x, int size_y, int P, const double* pts, const double* est,
+                  double* H, double* b, double* cost_out, long* oob_reads = nullptr) {
+  const double c = std::cos(est[2]), sn = std::sin(est[2]);        // :95-97, :197-198
+  for (int i = 0; i < 9; ++i) H[i] = 0.0;
+  b[0] = b[1] = b[2] = 0.0;
+  double cost = 0.0;
+  int valid_point = 1;                                             // :160
+  const long n_cells = static_cast<long>(size_x) * size_y;
+  auto cell = [&](int x, int y) -> double {
+    const long idx = static_cast<long>(y) * size_x + x;            // grid_map_base.h:352-354
+    if (idx >= 0 && idx < n_cells) return static_cast<double>(grid[idx]);
+    if (oob_reads) ++*oob_reads;                                   // undefined behaviour in the reference
+    return 0.0;
+  };
+  for (int p = 0; p < P; ++p) {
+    const double lx = pts[2 * p], ly = pts[2 * p + 1];
+    const double x = (c * lx + (-sn) * ly) + est[0];               // rotation * local_point + translation (:167)
+    const double y = (sn * lx + c * ly) + est[1];
+    if (!(x > 0 && x < size_x && y > 0 && y < size_y)) continue;   // PointInMap, grid_map_base.h:330-337
+    const double x0 = std::floor(x), y0 = std::floor(y), x1 = std::ceil(x), y1 = std::ceil(y);
+    const double m00 = cell(static_cast<int>(x0), static_cast<int>(y0));
+    const double m01 = cell(static_cast<int>(x0), static_cast<int>(y1));
+    const double m10 = cell(static_cast<int>(x1), static_cast<int>(y0));
+    const double m11 = cell(static_cast<int>(x1), static_cast<int>(y1));
+    double r = ((y - y0) * (m11 * (x - x0) + m01 * (x1 - x)) + (y1 - y) * (m10 * (x - x0) + m00 * (x1 - x)));   // :186-187
+    r = (r >= 0) ? ((r <= 1) ? r : 1) : 0;                         // :190-191
+    const double error = 1 - r;
+    cost += (error * error);
+    const double ds0 = (-sn * lx - c * ly);                        // :197
+    const double ds1 = (c * lx - sn * ly);                         // :198
+    const double dm0 = ((y - y0) * (m11 - m01) + (y1 - y) * (m10 - m00));   // :200
+    const double dm1 = ((x - x0) * (m11 - m10) + (x1 - x) * (m01 - m00));   // :201
+    double J[3];                                                   // J = -de_m * de_s (:204), lazy 1x2 * 2x3 product
+    J[0] = (-dm0) * 1.0 + (-dm1) * 0.0;
+    J[1] = (-dm0) * 0.0 + (-dm1) * 1.0;
+    J[2] = (-dm0) * ds0 + (-dm1) * ds1;
+    for (int cc = 0; cc < 3; ++cc)
+      for (int rr = 0; rr < 3; ++rr) H[cc * 3 + rr] = H[cc * 3 + rr] + J[rr] * J[cc];   // :206
+    for (int rr = 0; rr < 3; ++rr) b[rr] = b[rr] + (-J[rr]) * error;                     // :207
+    ++valid_point;
+  }
+  cost *= (1000.0 / valid_point);                                  // :218, kCostPointSize = 1000
+  *cost_out = cost;
+}
+
+// BasedOptimizeScanMatch::ScanMatch (:68-131).  op = {iterate_max_times, cost_decrease_threshold,
+// cost_min_threshold, max_update_distance, max_update_angle}.  iterate_max_times < 1 would return the
+// previous call's cost in the reference (a stale member); here it returns NaN.
+double Optimize(const float* grid, int size_x, int size_y, double scale, double off_x, double off_y, int P,
+                const double* pts, const double* op, double* pose_world, int* iters_out, long* oob_reads = nullptr) {
+  const double kMaxCost = 1.0 * 1000;
+  if (iters_out) *iters_out = 0;
+  if (P == 0) return kMaxCost;                                     // :73-76 (map initialised by the caller)
+  const MapTf tf = MakeTf(scale, off_x, off_y);
+  double est[3];
+  WorldToMap(tf, pose_world, est);
+  const double map_resolution = 1 / scale;                         // GetCellLength(), grid_map_base.h:307-309
+  const int iterate_max_times = static_cast<int>(op[0]);
+  double cost = std::nan(""), last_cost = 0.0;
+  int iter = 0;
+  for (; iter < iterate_max_times; ++iter) {
+    last_cost = cost;
+    double H[9], b[3], det[3];
+    OptimizeCost(grid, size_x, size_y, P, pts, est, H, b, &cost, oob_reads);
+    Ldlt3Solve(H, b, det);                                         // :135-141
+    if (std::isnan(det[0]) || std::isnan(det[1]) || std::isnan(det[2])) { if (iters_out) *iters_out = iter; return kMaxCost; }   // :103-106
+    if (iter > 0 && (last_cost - cost < op[1] || cost < op[2])) break;   // :112-118
+    est[0] += MaxAbxLimit(det[0], op[3] / map_resolution);         // :143-152
+    est[1] += MaxAbxLimit(det[1], op[3] / map_resolution);
+    est[2] += MaxAbxLimit(det[2], op[4]);
+  }
+  if (iters_out) *iters_out = iter;
+  est[2] = NormalizeAngle(est[2]);                                 // :125
+  MapToWorld(tf, est, pose_world);                                 // :127
+  return cost;
+}
+
+}  // namespace
+
+extern "C" {
+
+// oob_out (optional): reads past the end of the cell array (a point in the last row's strip size_y-1 < y < size_y:
+// undefined behaviour in the reference, 0.0 here and in the CUDA path)
+double orc_optimize(const float* grid, int size_x, int size_y, double scale, double off_x, double off_y, int P,
+                    const double* pts, const double* op, double* pose_world, int* iters_out, long* oob_out) {
+  long oob = 0;
+  const double c = Optimize(grid, size_x, size_y, scale, off_x, off_y, P, pts, op, pose_world, iters_out, &oob);
+  if (oob_out) *oob_out = oob;
+  return c;
+}
+
+// H (row-major 3x3 = column-major, it is symmetric), b, cost of one UpdateCost evaluation at a map pose
+void orc_optimize_cost(const float* grid, int size_x, int size_y, int P, const double* pts, const double* pose_map,
+                       double* H, double* b, double* cost) {
+  OptimizeCost(grid, size_x, size_y, P, pts, pose_map, H, b, cost);
+}
+
+void orc_ldlt3_solve(const double* H_colmajor, const double* b, double* x) { Ldlt3Solve(H_colmajor, b, x); }
+
+// ScanMatchers::ScanMatch with use_optimize_scan_match = true (scan_matchers.h:179-289): optimiser on the
+// coarse map / coarse-resolution scan, correlative passes on the fine map.
+// resp_out (optional) = {optimiser cost, coarse, fine, super responses}.
+double orc_match_chain_opt(const float* grid_c, int size_xc, int size_yc, double scale_c, double off_xc, double off_yc,
+                           int Pc, const double* pts_c, const float* grid_f, int size_xf, int size_yf, double scale_f,
+                           double off_xf, double off_yf, int Pf, const double* pts_f, const double* params,
+                           const double* op, double optimize_failed_cost, int use_fine, double* pose_world,
+                           double* cov, double* resp_out) {
+  (void)size_yf;
+  double best_pose[3] = {pose_world[0], pose_world[1], pose_world[2]};
+  double process_pose[3] = {best_pose[0], best_pose[1], best_pose[2]};
+  double scan_match_score = 0.0;
+  int scan_match_times = 0;
+  const double optimize_cost = Optimize(grid_c, size_xc, size_yc, scale_c, off_xc, off_yc, Pc, pts_c, op, process_pose, nullptr);   // :207
+  scan_match_score = optimize_failed_cost / (optimize_cost + optimize_failed_cost);          // :211
+  scan_match_times++;
+  double r[3] = {0.0, 0.0, 0.0};
+  if (!use_fine || optimize_cost > optimize_failed_cost) {                                   // :224-226
+    scan_match_score = 0.0;
+    scan_match_times--;
+    for (int k = 0; k < 3; ++k) process_pose[k] = best_pose[k];                              // :232
+    r[0] = OnePass(grid_f, size_xf, scale_f, off_xf, off_yf, Pf, pts_f, ReadParam(params), process_pose, cov, nullptr, nullptr);
+    scan_match_score += r[0];
+    scan_match_times++;
+  }
+  if (use_fine) {                                                                            // :247-263
+    r[1] = OnePass(grid_f, size_xf, scale_f, off_xf, off_yf, Pf, pts_f, ReadParam(params + 8), process_pose, cov, nullptr, nullptr);
+    scan_match_score += r[1]; scan_match_times++;
+    r[2] = OnePass(grid_f, size_xf, scale_f, off_xf, off_yf, Pf, pts_f, ReadParam(params + 16), process_pose, cov, nullptr, nullptr);
+    scan_match_score += r[2]; scan_match_times++;
+  }
+  scan_match_score /= scan_match_times;                                                      // :281
+  if (resp_out) { resp_out[0] = optimize_cost; resp_out[1] = r[0]; resp_out[2] = r[1]; resp_out[3] = r[2]; }
+  for (int k = 0; k < 3; ++k) pose_world[k] = process_pose[k];
+  return scan_match_score;
 }
 
 

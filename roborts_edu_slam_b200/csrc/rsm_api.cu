@@ -1809,6 +1809,93 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
   return RSM_OK;
 }
 
+
+// BasedOptimizeScanMatch::ScanMatch (scan_match/optimize_scan_matcher.h:68-131) for n independent problems.
+// Every iteration is one launch over the still-active problems (UpdateCost on the device, sums in point
+// order); the 3x3 solve, the stopping rule and the clamped update run here with the host libm, as do the
+// cos / sin of the next estimate.  poses_world in/out; costs out; iterations (nullable) = UpdateCost calls.
+int optimize_core(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* const* d_pts, const int* n_pts,
+                  const rsm_optimize_param* op, double* poses_world, double* costs, int32_t* iterations) {
+  const double kMaxCost = 1.0 * 1000;                         // :231-232
+  if (op->iterate_max_times < 1)   // the reference would return the previous call's cost_ (a stale member)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_optimize: iterate_max_times must be >= 1");
+  struct Prob { int i; double est[3]; double cost, last_cost; };
+  std::vector<Prob> act;
+  act.reserve(n);
+  for (int i = 0; i < n; ++i) {
+    if (iterations) iterations[i] = 0;
+    if (!grids[i]->init || n_pts[i] == 0) { costs[i] = kMaxCost; continue; }    // :73-76, pose untouched
+    Prob P; P.i = i; P.cost = 0.0; P.last_cost = 0.0;
+    grids[i]->tf.world_to_map(poses_world + 3 * i, P.est);                      // :80-81
+    act.push_back(P);
+  }
+  const size_t out_stride = kOptSums + 1;
+  auto finish = [&](const Prob& P) {
+    double est[3] = {P.est[0], P.est[1], normalize_angle(P.est[2])};            // :125
+    grids[P.i]->tf.map_to_world(est, poses_world + 3 * P.i);                     // :127
+    costs[P.i] = P.cost;
+  };
+  for (int iter = 0; iter < op->iterate_max_times && !act.empty(); ++iter) {
+    const int m = int(act.size());
+    Layout dl;
+    const size_t o_jobs = dl.take(sizeof(OptimizeJob) * size_t(m));
+    const size_t up_bytes = dl.off;
+    const size_t o_out = dl.take(size_t(m) * out_stride * 8, 16);
+    int rc = ensure_dev(ctx, ctx->d_work, dl.off);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, ctx->h_down, size_t(m) * out_stride * 8);
+    if (rc) return rc;
+    char* dw = ctx->d_work.p;
+    OptimizeJob* jobs = reinterpret_cast<OptimizeJob*>(ctx->h_up.p + o_jobs);
+    for (int a = 0; a < m; ++a) {
+      const Prob& P = act[a];
+      const rsm_grid* g = grids[P.i];
+      OptimizeJob& J = jobs[a];
+      std::memset(&J, 0, sizeof J);
+      J.grid = g->d_cells; J.pts = d_pts[P.i]; J.n_pts = n_pts[P.i];
+      J.size_x = g->size_x; J.size_y = g->size_y; J.pitch = g->pitch; J.fixed = g->fixed ? 1 : 0;
+      J.c = std::cos(P.est[2]); J.s = std::sin(P.est[2]);                        // :95-97
+      J.tx = P.est[0]; J.ty = P.est[1];
+      J.out = reinterpret_cast<double*>(dw + o_out) + size_t(a) * out_stride;
+    }
+    CU(cudaMemcpyAsync(dw + o_jobs, ctx->h_up.p + o_jobs, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_optimize(m, ctx->stream, reinterpret_cast<const OptimizeJob*>(dw + o_jobs)));
+    CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_out, size_t(m) * out_stride * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    ctx->stats.h2d_bytes += up_bytes; ctx->stats.d2h_bytes += size_t(m) * out_stride * 8; ctx->stats.kernel_launches++;
+    const double* out = reinterpret_cast<const double*>(ctx->h_down.p);
+    std::vector<Prob> next;
+    next.reserve(m);
+    for (int a = 0; a < m; ++a) {
+      Prob P = act[a];
+      const double* S = out + size_t(a) * out_stride;
+      if (iterations) iterations[P.i] = iter + 1;
+      const int valid_point = 1 + int(S[kOptSums]);                              // :160, :211
+      P.last_cost = P.cost;                                                      // :87
+      P.cost = S[9] * (1000.0 / valid_point);                                    // :218
+      const double H[3][3] = {{S[0], S[1], S[2]}, {S[1], S[3], S[4]}, {S[2], S[4], S[5]}};
+      const double b[3] = {S[6], S[7], S[8]};
+      double det[3];
+      ldlt3_solve(H, b, det);                                                    // :135-141
+      if (std::isnan(det[0]) || std::isnan(det[1]) || std::isnan(det[2])) { costs[P.i] = kMaxCost; continue; }   // :103-106
+      if (iter > 0 && (P.last_cost - P.cost < op->cost_decrease_threshold || P.cost < op->cost_min_threshold)) {  // :112-118
+        finish(P);
+        continue;
+      }
+      const double map_resolution = grids[P.i]->cell_len();                      // :83
+      P.est[0] += max_abs_limit(det[0], op->max_update_distance / map_resolution);   // :143-152
+      P.est[1] += max_abs_limit(det[1], op->max_update_distance / map_resolution);
+      P.est[2] += max_abs_limit(det[2], op->max_update_angle);
+      next.push_back(P);
+    }
+    act.swap(next);
+  }
+  for (const Prob& P : act) finish(P);     // ran out of iterations
+  return RSM_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1949,6 +2036,85 @@ int rsm_scan_match_interface_batch(rsm_ctx* ctx, const rsm_scan_store* store, in
   return loop_closure_core(ctx, n, grid_size, resolution, default_prob, sigma, occu_offset, centres_world, chain_offset,
                            base, dp.data(), np.data(), params, use_fine != 0, poses_world, covs, scores, responses,
                            pub_map, pub_map ? pub_pts.data() : nullptr, pub_map ? pub_counts.data() : nullptr, check);
+}
+
+// ---- Gauss-Newton matcher -----------------------------------------------------------------------
+int rsm_optimize_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* pts_xy, const int64_t* pts_offset,
+                       const rsm_optimize_param* param, double* poses_world, double* costs, int32_t* iterations) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || n < 0 || !param || (n > 0 && (!grids || !pts_offset || !poses_world || !costs)))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_optimize_batch: bad arguments");
+  if (n == 0) return RSM_OK;
+  for (int i = 0; i < n; ++i) if (!grids[i]) return fail(ctx, RSM_ERR_INVALID, "rsm_optimize_batch: null grid");
+  const size_t total = size_t(pts_offset[n]);
+  if (total && !pts_xy) return fail(ctx, RSM_ERR_INVALID, "rsm_optimize_batch: pts_xy is null");
+  double* d_pts = nullptr;
+  if (total) { int rc = upload_points(ctx, pts_xy, total, &d_pts); if (rc) return rc; }
+  std::vector<const double*> dp(n);
+  std::vector<int> np(n);
+  for (int i = 0; i < n; ++i) { dp[i] = d_pts + 2 * pts_offset[i]; np[i] = int(pts_offset[i + 1] - pts_offset[i]); }
+  return optimize_core(ctx, n, grids, dp.data(), np.data(), param, poses_world, costs, iterations);
+}
+
+int rsm_optimize(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_optimize_param* param,
+                 double pose_world[3], double* cost, int32_t* iterations) {
+  if (!grid || n_pts < 0) return fail(ctx, RSM_ERR_INVALID, "rsm_optimize: bad arguments");
+  const int64_t off[2] = {0, n_pts};
+  const rsm_grid* gs[1] = {grid};
+  return rsm_optimize_batch(ctx, 1, gs, pts_xy, off, param, pose_world, cost, iterations);
+}
+
+int rsm_match_chain_opt(rsm_ctx* ctx, const rsm_grid* coarse_grid, const double* pts_coarse, int n_coarse,
+                        const rsm_grid* fine_grid, const double* pts_fine, int n_fine, const rsm_pass_param params[3],
+                        const rsm_optimize_param* opt, double optimize_failed_cost, int use_fine, double pose_world[3],
+                        double cov[9], double* score, double responses[4]) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !coarse_grid || !fine_grid || !params || !opt || !pose_world || !cov || !score || n_coarse < 0 || n_fine < 0 ||
+      (n_coarse > 0 && !pts_coarse) || (n_fine > 0 && !pts_fine))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_chain_opt: bad arguments");
+  // scan_matchers.h:179-289 with use_optimize_scan_match_ = true
+  const double best_pose[3] = {pose_world[0], pose_world[1], pose_world[2]};
+  double process_pose[3] = {best_pose[0], best_pose[1], best_pose[2]};
+  double optimize_cost = 0.0;
+  int rc = rsm_optimize(ctx, coarse_grid, pts_coarse, n_coarse, opt, process_pose, &optimize_cost, nullptr);   // :207
+  if (rc) return rc;
+  double scan_match_score = optimize_failed_cost / (optimize_cost + optimize_failed_cost);   // :211
+  int scan_match_times = 1;
+  double r[3] = {0.0, 0.0, 0.0};
+  double* d_pts = nullptr;
+  if (n_fine > 0) { rc = upload_points(ctx, pts_fine, size_t(n_fine), &d_pts); if (rc) return rc; }
+  auto one_pass = [&](int k) -> int {
+    std::vector<PassItem> items(1);
+    items[0].grid = fine_grid; items[0].d_pts = d_pts; items[0].P = n_fine; items[0].param = params[k];
+    items[0].pose_world = process_pose; items[0].cov = cov;
+    if (!fine_grid->init || n_fine == 0) { r[k] = 0.0; return RSM_OK; }          // correlate_scan_matcher.h:792-795
+    int e = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+    if (e) return e;
+    r[k] = items[0].response;
+    return RSM_OK;
+  };
+  if (!use_fine || optimize_cost > optimize_failed_cost) {                                     // :224-226
+    scan_match_score = 0.0;                                                                    // :230-232
+    scan_match_times--;
+    for (int k = 0; k < 3; ++k) process_pose[k] = best_pose[k];
+    rc = one_pass(0);                                                                          // :237-239
+    if (rc) return rc;
+    scan_match_score += r[0];
+    scan_match_times++;
+  }
+  if (use_fine) {                                                                              // :247-263
+    rc = one_pass(1);
+    if (rc) return rc;
+    scan_match_score += r[1]; scan_match_times++;
+    rc = one_pass(2);
+    if (rc) return rc;
+    scan_match_score += r[2]; scan_match_times++;
+  }
+  scan_match_score /= scan_match_times;                                                        // :281
+  for (int k = 0; k < 3; ++k) pose_world[k] = process_pose[k];
+  *score = scan_match_score;
+  if (responses) { responses[0] = optimize_cost; responses[1] = r[0]; responses[2] = r[1]; responses[3] = r[2]; }
+  return RSM_OK;
 }
 
 int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,

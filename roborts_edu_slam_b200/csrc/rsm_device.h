@@ -128,6 +128,18 @@ struct PenaltyJob {
   int pad0, pad1;
 };
 
+// One Gauss-Newton evaluation (BasedOptimizeScanMatch::UpdateCost) of one (grid, scan, pose estimate).
+constexpr int kOptSums = 10;   // H00 H10 H20 H11 H21 H22 b0 b1 b2 cost
+struct OptimizeJob {
+  const void* grid;      // lookup grid cells (fixed-point int32 or float32)
+  const double* pts;     // scan points, cells of this grid, sensor frame
+  int n_pts;
+  int size_x, size_y, pitch;
+  int fixed, pad0;
+  double c, s, tx, ty;   // cos / sin of the estimate's heading (host libm) and its translation in map cells
+  double* out;           // kOptSums sums in point order + the number of points inside the map
+};
+
 }  // namespace rsm
 
 #endif

@@ -7,6 +7,7 @@
 #define RSM_HOST_H_
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -218,6 +219,63 @@ inline void angular_cov(const PassGeo& g, const rsm_pass_param& q, const BestPos
   if (norm > kDoubleTolerance) var = acc / norm;   // (:1008-1012: the /4 value is overwritten)
   else var = 200 * mav;
   cov[8] = var;
+}
+
+// ---- host side of the Gauss-Newton matcher (scan_match/optimize_scan_matcher.h) --------------------
+// util/slam_util.h:79-87
+inline double max_abs_limit(double value, double limit) {
+  const double lim = std::fabs(limit);
+  if (value > lim) return lim;
+  if (value < -lim) return -lim;
+  return value;
+}
+// util/slam_util.h:103-111
+inline double normalize_angle(double angle) {
+  const double two_pi = 2.0 * M_PI;
+  double a = std::fmod(std::fmod(angle, two_pi) + two_pi, two_pi);
+  if (a > M_PI) a -= two_pi;
+  return a;
+}
+
+// det = H.ldlt().solve(b) for a symmetric 3x3 H (optimize_scan_matcher.h:135-141).  Follows Eigen 3.3's
+// LDLT (Cholesky/LDLT.h): in-place lower factorisation with the largest remaining diagonal entry as pivot,
+// then x = P^T L^-T D^+ L^-1 P b with pivots of magnitude <= DBL_MIN treated as zero.  a[r][c] is the
+// working copy; only its lower triangle is read after the swaps.
+inline void ldlt3_solve(const double H[3][3], const double b[3], double x[3]) {
+  double a[3][3];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = H[r][c];
+  int perm[3] = {0, 1, 2};
+  double w[3];
+  for (int k = 0; k < 3; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < 3; ++i) if (std::fabs(a[i][i]) > std::fabs(a[piv][piv])) piv = i;
+    perm[k] = piv;
+    if (piv != k) {
+      for (int c = 0; c < k; ++c) std::swap(a[k][c], a[piv][c]);               // row heads
+      for (int r = piv + 1; r < 3; ++r) std::swap(a[r][k], a[r][piv]);          // column tails
+      std::swap(a[k][k], a[piv][piv]);
+      for (int i = k + 1; i < piv; ++i) std::swap(a[i][k], a[piv][i]);          // the strip between them
+    }
+    if (k > 0) {
+      for (int c = 0; c < k; ++c) w[c] = a[c][c] * a[k][c];
+      double dot = a[k][0] * w[0];
+      for (int c = 1; c < k; ++c) dot = dot + a[k][c] * w[c];
+      a[k][k] -= dot;
+      for (int r = k + 1; r < 3; ++r)
+        for (int c = 0; c < k; ++c) a[r][k] = a[r][k] + a[r][c] * (-1.0 * w[c]);
+    }
+    const double d = a[k][k];
+    if (k == 0 && !(std::fabs(d) > 0.0)) { perm[0] = 0; perm[1] = 1; perm[2] = 2; break; }   // zero diagonal: nothing to eliminate
+    if (std::fabs(d) > 0.0) for (int r = k + 1; r < 3; ++r) a[r][k] /= d;
+  }
+  for (int i = 0; i < 3; ++i) x[i] = b[i];
+  for (int k = 0; k < 3; ++k) if (perm[k] != k) std::swap(x[k], x[perm[k]]);
+  x[1] -= a[1][0] * x[0];
+  x[2] -= (a[2][0] * x[0] + a[2][1] * x[1]);
+  for (int i = 0; i < 3; ++i) { if (std::fabs(a[i][i]) > DBL_MIN) x[i] /= a[i][i]; else x[i] = 0.0; }
+  x[1] -= a[2][1] * x[2];
+  x[0] -= (a[1][0] * x[1] + a[2][0] * x[2]);
+  for (int k = 2; k >= 0; --k) if (perm[k] != k) std::swap(x[k], x[perm[k]]);
 }
 
 }  // namespace rsm

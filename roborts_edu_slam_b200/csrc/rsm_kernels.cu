@@ -21,6 +21,7 @@
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 #include "rsm_device.h"
@@ -417,33 +418,51 @@ cudaError_t launch_fill(int n_jobs, int ctas_per_job, cudaStream_t st, const Fil
 // and the result does not depend on the order the reference visits points and scans in.
 // stamp[(2h+1)^2]: pattern of float(kernel[i,j] * occu_offset), 0 where that exceeds 1.0f
 // (SetGridProbability ignores prob > 1, map/grid_map_cell.h:361-365); one = pattern of 1.0f.
-__global__ void __launch_bounds__(128)
+// Two phases per chunk of points: (1) one thread per point computes the end cell in FP64 (the reference's
+// association) and parks it in shared memory; (2) one thread per (point, stamp row) composites 2h+1 consecutive
+// cells.  A cell is read first (L2) and the atomic is only issued when it would raise the value: the maximum is
+// monotone, so a stale read can only cause a redundant atomic, never a missed one.  Neighbouring scan points
+// and the scans of one chain overlap heavily, which removes most of the atomics.
+constexpr int kRasterChunk = 1024;
+__global__ void __launch_bounds__(256)
 raster_kernel(const RasterScan* __restrict__ scans, const int* __restrict__ stamp, int half, int one) {
+  __shared__ int2 s_cell[kRasterChunk];
   const RasterScan S = scans[blockIdx.x];
   int* grid = reinterpret_cast<int*>(S.grid);
   const int ks = 2 * half + 1;
   const int tol = half + 1;
-  for (int i = threadIdx.x; i < S.n_pts; i += blockDim.x) {
-    const double px = S.pts[2 * i], py = S.pts[2 * i + 1];
-    // Affine * v = translation + (l00*x + l01*y), l = (c, -s; s, c)   (occu_grid_map.h:279-283)
-    const double mx = dadd(S.tx, dadd(dmul(S.c, px), dmul(-S.s, py)));
-    const double my = dadd(S.ty, dadd(dmul(S.s, px), dmul(S.c, py)));
-    const int ex = __double2int_rz(dadd(mx, 0.5));
-    const int ey = __double2int_rz(dadd(my, 0.5));
-    if (ex == S.start_x && ey == S.start_y) continue;                    // :312
-    if (!(ex > tol && ex < S.size_x - tol && ey > tol && ey < S.size_y - tol)) continue;  // :476
-    atomicMax(grid + (long long)ey * S.pitch + ex, one);                  // :544
-    for (int j = -half; j <= half; ++j)
+  for (int base = 0; base < S.n_pts; base += kRasterChunk) {
+    const int cnt = min(kRasterChunk, S.n_pts - base);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const double px = S.pts[2 * (base + i)], py = S.pts[2 * (base + i) + 1];
+      // Affine * v = translation + (l00*x + l01*y), l = (c, -s; s, c)   (occu_grid_map.h:279-283)
+      const double mx = dadd(S.tx, dadd(dmul(S.c, px), dmul(-S.s, py)));
+      const double my = dadd(S.ty, dadd(dmul(S.s, px), dmul(S.c, py)));
+      int ex = __double2int_rz(dadd(mx, 0.5));
+      const int ey = __double2int_rz(dadd(my, 0.5));
+      if (ex == S.start_x && ey == S.start_y) ex = INT_MIN;                                   // :312
+      else if (!(ex > tol && ex < S.size_x - tol && ey > tol && ey < S.size_y - tol)) ex = INT_MIN;  // :476
+      s_cell[i] = make_int2(ex, ey);
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < cnt * ks; w += blockDim.x) {
+      const int i = w / ks, j = w - i * ks - half;
+      const int2 c = s_cell[i];
+      if (c.x == INT_MIN) continue;
+      int* row = grid + (long long)(c.y + j) * S.pitch + c.x;
       for (int ii = -half; ii <= half; ++ii) {
-        const int v = __ldg(stamp + (ii + half) + ks * (j + half));
-        if (v) atomicMax(grid + (long long)(ey + j) * S.pitch + (ex + ii), v);   // :560-573
+        int v = __ldg(stamp + (ii + half) + ks * (j + half));                                   // :560-573
+        if (j == 0 && ii == 0) v = max(v, one);                                                  // :544
+        if (v && __ldcg(row + ii) < v) atomicMax(row + ii, v);
       }
+    }
+    __syncthreads();
   }
 }
 
 cudaError_t launch_raster(int n_scans, cudaStream_t st, const RasterScan* scans, const int* stamp, int half, int one) {
   if (n_scans == 0) return cudaSuccess;
-  raster_kernel<<<n_scans, 128, 0, st>>>(scans, stamp, half, one);
+  raster_kernel<<<n_scans, 256, 0, st>>>(scans, stamp, half, one);
   return cudaGetLastError();
 }
 
@@ -574,6 +593,90 @@ penalty_kernel(const PenaltyJob* __restrict__ jobs, const unsigned char* __restr
 cudaError_t launch_penalty(int n_jobs, cudaStream_t st, const PenaltyJob* jobs, const unsigned char* occ, int size_x,
                            int size_y, double bound_tolerance) {
   penalty_kernel<<<n_jobs, 128, 0, st>>>(jobs, occ, size_x, size_y, bound_tolerance);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// Gauss-Newton cost evaluation (BasedOptimizeScanMatch::UpdateCost, scan_match/optimize_scan_matcher.h:154-220)
+// =================================================================================================
+// One CTA per (grid, scan, pose estimate).  The reference adds the per-point terms of H = sum J^T J,
+// b = sum -J^T e and cost = sum e^2 in point order, in FP64; a tree reduction would round differently.
+// So the work is split by what can run in parallel without changing a bit: all threads compute the
+// terms of a chunk of points (bilinear read of four cells, Jacobian, products -- every operation the
+// reference's, none fused) into shared memory, then ten threads -- one per distinct sum; H is symmetric
+// term by term because J_r*J_c is commutative -- add the chunk's terms in point order.  A point
+// outside the map contributes +0.0 terms, which leaves every sum unchanged (the sums start at +0 and can
+// never become -0).  The chain of ~P dependent adds is the latency floor of the kernel; the ten chains
+// and all jobs of a batch run side by side.
+constexpr int kOptChunk = 256;
+__device__ __forceinline__ double opt_cell(const OptimizeJob& J, int x, int y) {
+  // flat cell index y*size_x + x as the reference computes it (grid_map_base.h:352-354): x == size_x wraps into
+  // the next row; past the last cell the reference reads out of bounds, here that reads 0
+  if (x >= J.size_x) { x -= J.size_x; y += 1; }
+  if (y >= J.size_y) return 0.0;
+  const size_t at = (size_t)y * J.pitch + x;
+  if (J.fixed) return dmul((double)(reinterpret_cast<const int*>(J.grid)[at]), 1.0 / 33554432.0);
+  return (double)(reinterpret_cast<const float*>(J.grid)[at]);
+}
+
+__global__ void __launch_bounds__(128)
+optimize_kernel(const OptimizeJob* __restrict__ jobs) {
+  __shared__ double s_term[kOptSums][kOptChunk + 1];
+  __shared__ int s_valid[4];
+  const OptimizeJob J = jobs[blockIdx.x];
+  double acc = 0.0;
+  int valid = 0;
+  for (int base = 0; base < J.n_pts; base += kOptChunk) {
+    const int cnt = min(kOptChunk, J.n_pts - base);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const double lx = J.pts[2 * (base + i)], ly = J.pts[2 * (base + i) + 1];
+      const double x = dadd(dadd(dmul(J.c, lx), dmul(-J.s, ly)), J.tx);     // rotation * local_point + translation (:167)
+      const double y = dadd(dadd(dmul(J.s, lx), dmul(J.c, ly)), J.ty);
+      double t[kOptSums];
+#pragma unroll
+      for (int k = 0; k < kOptSums; ++k) t[k] = 0.0;
+      if (x > 0 && x < J.size_x && y > 0 && y < J.size_y) {                  // PointInMap (grid_map_base.h:330-337)
+        ++valid;
+        const double x0 = floor(x), y0 = floor(y), x1 = ceil(x), y1 = ceil(y);
+        const double m00 = opt_cell(J, (int)x0, (int)y0), m01 = opt_cell(J, (int)x0, (int)y1);
+        const double m10 = opt_cell(J, (int)x1, (int)y0), m11 = opt_cell(J, (int)x1, (int)y1);
+        const double fx = dsub(x, x0), gx = dsub(x1, x), fy = dsub(y, y0), gy = dsub(y1, y);
+        double r = dadd(dmul(fy, dadd(dmul(m11, fx), dmul(m01, gx))), dmul(gy, dadd(dmul(m10, fx), dmul(m00, gx))));   // :186-187
+        r = (r >= 0) ? ((r <= 1) ? r : 1) : 0;                               // :190-191
+        const double e = dsub(1.0, r);
+        const double ds0 = dsub(dmul(-J.s, lx), dmul(J.c, ly));              // :197
+        const double ds1 = dsub(dmul(J.c, lx), dmul(J.s, ly));               // :198
+        const double dm0 = dadd(dmul(fy, dsub(m11, m01)), dmul(gy, dsub(m10, m00)));   // :200
+        const double dm1 = dadd(dmul(fx, dsub(m11, m10)), dmul(gx, dsub(m01, m00)));   // :201
+        const double j0 = dadd(dmul(-dm0, 1.0), dmul(-dm1, 0.0));            // J = -de_m * de_s (:204)
+        const double j1 = dadd(dmul(-dm0, 0.0), dmul(-dm1, 1.0));
+        const double j2 = dadd(dmul(-dm0, ds0), dmul(-dm1, ds1));
+        t[0] = dmul(j0, j0); t[1] = dmul(j1, j0); t[2] = dmul(j2, j0);       // :206
+        t[3] = dmul(j1, j1); t[4] = dmul(j2, j1); t[5] = dmul(j2, j2);
+        t[6] = dmul(-j0, e); t[7] = dmul(-j1, e); t[8] = dmul(-j2, e);       // :207
+        t[9] = dmul(e, e);                                                   // :193
+      }
+#pragma unroll
+      for (int k = 0; k < kOptSums; ++k) s_term[k][i] = t[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < kOptSums) {
+      const double* row = s_term[threadIdx.x];
+#pragma unroll 8
+      for (int i = 0; i < cnt; ++i) acc = dadd(acc, row[i]);
+    }
+    __syncthreads();
+  }
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0) s_valid[threadIdx.x >> 5] = valid;
+  __syncthreads();
+  if (threadIdx.x < kOptSums) J.out[threadIdx.x] = acc;
+  if (threadIdx.x == 0) J.out[kOptSums] = (double)(s_valid[0] + s_valid[1] + s_valid[2] + s_valid[3]);
+}
+
+cudaError_t launch_optimize(int n_jobs, cudaStream_t st, const OptimizeJob* jobs) {
+  if (n_jobs == 0) return cudaSuccess;
+  optimize_kernel<<<n_jobs, 128, 0, st>>>(jobs);
   return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);
 cudaError_t launch_fill(int n_jobs, int ctas_per_job, cudaStream_t st, const FillJob* jobs);
 cudaError_t launch_penalty(int n_jobs, cudaStream_t st, const PenaltyJob* jobs, const unsigned char* occ, int size_x,
                            int size_y, double bound_tolerance);
+cudaError_t launch_optimize(int n_jobs, cudaStream_t st, const OptimizeJob* jobs);
 cudaError_t launch_raster(int n_scans, cudaStream_t st, const RasterScan* scans, const int* stamp,
                           int half, int one);
 cudaError_t launch_microbench(cudaStream_t st, int mode, const int* g, unsigned int words, int iters,

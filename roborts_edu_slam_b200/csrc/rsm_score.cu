@@ -99,7 +99,9 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
   __shared__ ScoreJob J;
   __shared__ int s_job;
   __shared__ unsigned long long s_wmax[NT / 32];
-  __shared__ double sLut[2][PC][2];     // rotated endpoints (x, y) of the chunk's beams
+  __shared__ double sLut[3][PC][2];     // rotated endpoints (x, y) of the chunk's beams, indexed chunk % 3: while chunk c
+                                        // is gathered (its exact-recompute path reads them), chunk c+1's tables are built
+                                        // from theirs and chunk c+2's are written
   __shared__ double sX[LX];             // candidate x of this tile
   __shared__ double sY[ROWS];           // candidate y of this tile
   __shared__ __align__(16) int sGX[2][PC][GXW];  // general: cell x per (beam, lane)
@@ -144,8 +146,8 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
       if (v < V) {
         const int p = v * J.step;
         const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
-        sLut[c & 1][tid][0] = dsub(dmul(cs, px), dmul(sn, py));
-        sLut[c & 1][tid][1] = dadd(dmul(sn, px), dmul(cs, py));
+        sLut[c % 3][tid][0] = dsub(dmul(cs, px), dmul(sn, py));
+        sLut[c % 3][tid][1] = dadd(dmul(sn, px), dmul(cs, py));
       }
     }
   };
@@ -158,8 +160,8 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
       const int F = J.f_int;
       for (int q = tid; q < npc * SLOTS; q += NT) {
         const int pc = q / SLOTS, sl = q % SLOTS;
-        const double tx_ = dadd(dadd(sLut[b][pc][0], sX[0]), 0.5);
-        const double ty_ = dadd(dadd(sLut[b][pc][1], sY[sl * RY]), 0.5);
+        const double tx_ = dadd(dadd(sLut[c % 3][pc][0], sX[0]), 0.5);
+        const double ty_ = dadd(dadd(sLut[c % 3][pc][1], sY[sl * RY]), 0.5);
         const int gx0 = __double2int_rz(tx_), gy0 = __double2int_rz(ty_);
         const double fx = tx_ - (double)gx0, fy = ty_ - (double)gy0;
         const bool ok = fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 &&
@@ -170,7 +172,7 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
     } else {
       for (int q = tid; q < npc * LX; q += NT) {
         const int pc = q / LX, j = q % LX;
-        int g = cell_index(sLut[b][pc][0], sX[j]);
+        int g = cell_index(sLut[c % 3][pc][0], sX[j]);
         if (g < 0 || g >= size_x) {
           if (tx0 + j < n_xy) e = kErrWindow;
           g = max(0, min(g, size_x - 1));
@@ -179,7 +181,7 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
       }
       for (int q = tx; q < npc * RY; q += LX) {
         const int pc = q / RY, rr = q % RY;
-        int g = cell_index(sLut[b][pc][1], sY[ts * RY + rr]);
+        int g = cell_index(sLut[c % 3][pc][1], sY[ts * RY + rr]);
         if (g < 0 || g >= size_y) {
           if (ty0 + ts * RY + rr < n_xy) e = kErrWindow;
           g = max(0, min(g, size_y - 1));
@@ -239,12 +241,12 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
           } else {
             // exact recomputation for this (beam, slot): frac(t0) too close to a cell boundary,
             // or the tile touches the grid border
-            int gx = cell_index(sLut[b][pc][0], sX[tx]);
+            int gx = cell_index(sLut[c % 3][pc][0], sX[tx]);
             if (gx < 0 || gx >= size_x) {
               if (tx0 + tx < n_xy) err |= kErrWindow;
               gx = max(0, min(gx, size_x - 1));
             }
-            const double ly = sLut[b][pc][1];
+            const double ly = sLut[c % 3][pc][1];
 #pragma unroll
             for (int r = 0; r < RY; ++r) {
               int g = cell_index(ly, sY[ts * RY + r]);

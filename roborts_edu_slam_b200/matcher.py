@@ -71,6 +71,12 @@ class MapCheckParamStruct(ctypes.Structure):
                 ("use_logistic", ctypes.c_int32)]
 
 
+class OptimizeParamStruct(ctypes.Structure):
+    """rsm_optimize_param (OptimizeScanMatchParam, optimize_scan_matcher.h:33-58)"""
+    _fields_ = [("cost_decrease_threshold", c_d), ("cost_min_threshold", c_d), ("max_update_distance", c_d),
+                ("max_update_angle", c_d), ("iterate_max_times", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 # every symbol include/rsm.h declares: (restype, argtypes)
 _PPARAM = ctypes.POINTER(PassParamStruct)
 ABI = {
@@ -115,6 +121,11 @@ ABI = {
     "rsm_scan_store_size": (c_i, [c_p]),
     "rsm_scan_match_interface_batch": (c_i, [c_p, c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p,
                                              _PPARAM, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "rsm_optimize": (c_i, [c_p, c_p, c_p, c_i, ctypes.POINTER(OptimizeParamStruct), c_p, ctypes.POINTER(c_d),
+                           ctypes.POINTER(ctypes.c_int32)]),
+    "rsm_optimize_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, ctypes.POINTER(OptimizeParamStruct), c_p, c_p, c_p]),
+    "rsm_match_chain_opt": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_i, _PPARAM, ctypes.POINTER(OptimizeParamStruct), c_d, c_i,
+                                  c_p, c_p, ctypes.POINTER(c_d), c_p]),
     "rsm_pass_scores": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p, c_i64, ctypes.POINTER(c_i64)]),
     "rsm_match_partial": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p]),
     "rsm_match_merge": (c_i, [c_p, c_p, c_i, c_p]),
@@ -412,6 +423,62 @@ RSM_PARTIAL_BYTES = 65536
 RSM_COLUMNS_BYTES = 131072
 
 
+class OptimizeScanMatchParam:
+    """Same fields as the reference class (optimize_scan_matcher.h:33-58)."""
+
+    def __init__(self, iterate_max_times=10, cost_decrease_threshold=1.0, cost_min_threshold=2.0,
+                 max_update_distance=0.5, max_update_angle=0.2):
+        self.iterate_max_times = int(iterate_max_times)
+        self.cost_decrease_threshold = float(cost_decrease_threshold)
+        self.cost_min_threshold = float(cost_min_threshold)
+        self.max_update_distance = float(max_update_distance)
+        self.max_update_angle = float(max_update_angle)
+
+    def struct(self):
+        return OptimizeParamStruct(self.cost_decrease_threshold, self.cost_min_threshold, self.max_update_distance,
+                                   self.max_update_angle, self.iterate_max_times, 0)
+
+
+def _as_opt(p):
+    return p if isinstance(p, OptimizeScanMatchParam) else OptimizeScanMatchParam(*p)
+
+
+class BasedOptimizeScanMatch:
+    """ScanMatch(map, range_data, optimize_scan_match_param, best_pose) -> cost; best_pose (numpy, world) is
+    updated in place like the reference's Eigen::Vector3d& (optimize_scan_matcher.h:68-131)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.last_iterations = 0
+
+    def ScanMatch(self, map_, range_data, optimize_scan_match_param, best_pose):
+        ctx = self.ctx
+        pts = _f64(range_data).reshape(-1, 2)
+        st = _as_opt(optimize_scan_match_param).struct()
+        cost, it = c_d(0), ctypes.c_int32(0)
+        ctx.check(ctx.lib.rsm_optimize(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(st), best_pose.ctypes.data,
+                                       ctypes.byref(cost), ctypes.byref(it)))
+        self.last_iterations = it.value
+        return cost.value
+
+    def ScanMatchBatch(self, maps, scans, optimize_scan_match_param, poses):
+        """n independent problems (rsm_optimize_batch) -> (costs, poses, iterations)."""
+        ctx = self.ctx
+        n = len(maps)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        for i, s_ in enumerate(scans):
+            offs[i + 1] = offs[i] + len(s_)
+        pts = _f64(np.concatenate([np.asarray(s_).reshape(-1, 2) for s_ in scans], axis=0)) if n else np.zeros((0, 2))
+        poses = _f64(poses).copy()
+        costs = np.zeros(n)
+        iters = np.zeros(n, dtype=np.int32)
+        st = _as_opt(optimize_scan_match_param).struct()
+        handles = (c_p * n)(*[m.h for m in maps])
+        ctx.check(ctx.lib.rsm_optimize_batch(ctx.h, n, handles, pts.ctypes.data, offs.ctypes.data, ctypes.byref(st),
+                                             poses.ctypes.data, costs.ctypes.data, iters.ctypes.data))
+        return costs, poses, iters
+
+
 class SlicedScanMatch:
     """One large search window cut along the angle index over several GPUs.
 
@@ -473,6 +540,25 @@ class ScanMatchers:
         ctx.check(ctx.lib.rsm_match_chain(ctx.h, map_.h, pts.ctypes.data, len(pts), self._arr, int(use_fine_scan_match),
                                           best_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(score),
                                           self.last_responses.ctypes.data))
+        return score.value
+
+    def ScanMatchWithOptimize(self, coarse_map_range_data, fine_map_range_data, coarse_map, fine_map, best_pose, cov_matrix,
+                              optimize_scan_match_param, optimize_failed_cost, use_fine_scan_match=True):
+        """The reference's full signature with use_optimize_scan_match on (scan_matchers.h:179-289):
+        Gauss-Newton on the coarse map first, the correlative passes on the fine map.  -> score;
+        self.last_optimize_cost / self.last_responses hold the step results."""
+        ctx = self.ctx
+        pc = _f64(coarse_map_range_data).reshape(-1, 2)
+        pf = _f64(fine_map_range_data).reshape(-1, 2)
+        st = _as_opt(optimize_scan_match_param).struct()
+        score = c_d(0)
+        resp = np.zeros(4)
+        ctx.check(ctx.lib.rsm_match_chain_opt(ctx.h, coarse_map.h, pc.ctypes.data, len(pc), fine_map.h, pf.ctypes.data, len(pf),
+                                              self._arr, ctypes.byref(st), float(optimize_failed_cost), int(use_fine_scan_match),
+                                              best_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(score),
+                                              resp.ctypes.data))
+        self.last_optimize_cost = resp[0]
+        self.last_responses = resp[1:].copy()
         return score.value
 
     def ScanMatchBatch(self, maps, scans, poses, covs=None, use_fine_scan_match=True):

@@ -16,7 +16,7 @@ def sha(a):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("maps_", "mapcheck_")))
+                  if not os.path.basename(p).startswith(("maps_", "mapcheck_", "optimize_")))
 
 
 def mapcheck_names():
@@ -82,3 +82,21 @@ def random_scenario(rng, n_points=200, size=160, res=0.05, n_base=3, spread=60.0
     seed = truth + np.array([0.08, -0.05, 0.06])
     return synth.Scenario("random", g, base_pts, np.array(base_poses), seen_from(truth), seed, truth, [],
                           truth[:2].copy())
+
+
+def optimize_cases():
+    """-> (npz of the reference's Gauss-Newton outputs, [(tag, fine scenario, coarse GridSpec, coarse base scans,
+    coarse scan)]) -- inputs re-synthesised, checked against the fixture's checksum."""
+    import hashlib
+    z = np.load(os.path.join(GOLDEN_DIR, "optimize_cases.npz"), allow_pickle=False)
+    out = []
+    for sc in (synth.config1(), synth.config4(1)[0]):
+        tag = sc.name.split("_")[-1]
+        h = hashlib.sha256()
+        for a in [sc.scan_pts, sc.base_poses] + list(sc.base_pts):
+            h.update(np.ascontiguousarray(a).tobytes())
+        assert h.hexdigest() == str(z[tag + "_checksum"]), "synthetic inputs changed since the fixture was made"
+        g = sc.grid
+        gc = synth.backend_grid(g.res * 2, g.sigma * 2, 10.0, sc.grid_centre)
+        out.append((tag, sc, gc, [p * 0.5 for p in sc.base_pts], sc.scan_pts * 0.5))
+    return z, out

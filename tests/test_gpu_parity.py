@@ -597,3 +597,111 @@ def test_scan_store_interface_batch(ctx, oracle):
     pm.close()
     store.close()
     pub_store.close()
+
+
+# ---- Gauss-Newton matcher ----------------------------------------------------
+def test_optimize_golden(ctx):
+    """rsm_optimize / rsm_optimize_batch / rsm_match_chain_opt against the outputs of the reference's own
+    optimize_scan_matcher.h (committed fixture): cost, pose, chain score and responses bit for bit."""
+    from helpers import optimize_cases
+    z, cases = optimize_cases()
+    opt = matcher.BasedOptimizeScanMatch(ctx)
+    for tag, sc, gc, base_c, scan_c in cases:
+        gf = sc.grid
+        dev_f = device_grid(ctx, sc)
+        dev_c = matcher.ScanMatchMap.from_spec(ctx, gc)
+        dev_c.InitMapWithRangeVec(base_c, sc.base_poses, gc.default_prob, gc.sigma, gc.occu_offset, gc.use_blur)
+        seeds = sc.truth_pose + z["seed_deltas"]
+        for mi, (dev, pts) in enumerate(((dev_f, sc.scan_pts), (dev_c, scan_c))):
+            for oi, op in enumerate(z["opt_sets"]):
+                costs, poses, iters = opt.ScanMatchBatch([dev] * len(seeds), [pts] * len(seeds), op, seeds)
+                assert np.array_equal(costs, z[tag + "_cost"][mi, oi]), (tag, mi, oi, costs, z[tag + "_cost"][mi, oi])
+                assert np.array_equal(poses, z[tag + "_pose"][mi, oi])
+                assert iters.min() >= 1 and iters.max() <= int(op[0])
+                pose = seeds[0].copy()                                   # one problem through rsm_optimize
+                assert opt.ScanMatch(dev, pts, op, pose) == z[tag + "_cost"][mi, oi, 0]
+                assert np.array_equal(pose, z[tag + "_pose"][mi, oi, 0]) and opt.last_iterations == iters[0]
+        sm = matcher.ScanMatchers(ctx, synth.chain_yaml())
+        for fi, fc in enumerate(z["failed_costs"]):
+            for ui, use_fine in enumerate((True, False)):
+                for si in range(4):
+                    pose, cov = seeds[si].copy(), np.eye(3)
+                    s = sm.ScanMatchWithOptimize(scan_c, sc.scan_pts, dev_c, dev_f, pose, cov, z["opt_sets"][0], fc, use_fine)
+                    assert s == z[tag + "_chain_score"][fi, ui, si], (tag, fi, ui, si)
+                    assert np.array_equal(pose, z[tag + "_chain_pose"][fi, ui, si])
+                    assert cov_close(cov, z[tag + "_chain_cov"][fi, ui, si])
+                    assert sm.last_optimize_cost == z[tag + "_chain_resp"][fi, ui, si, 0]
+                    assert np.array_equal(sm.last_responses, z[tag + "_chain_resp"][fi, ui, si, 1:])
+        dev_f.close()
+        dev_c.close()
+
+
+def test_optimize_random_and_errors(ctx, oracle, rng):
+    """Random problems against the oracle (blur-level and arbitrary float cells, scans that partly leave the
+    map, random knobs), a mixed batch, and the reference's error behaviour."""
+    opt = matcher.BasedOptimizeScanMatch(ctx)
+    devs, scans, seeds, want = [], [], [], []
+    op = (10, 0.1, 0.5, 0.5, 0.5)
+    for k in range(24):
+        sc = random_scenario(rng, n_points=int(rng.integers(1, 700)), size=int(rng.choice([96, 160, 333])))
+        g = sc.grid
+        grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+        if k % 3 == 2:
+            grid = rng.random(grid.shape).astype(np.float32)
+        dg = matcher.ScanMatchMap.from_spec(ctx, g)
+        dg.upload(grid)
+        assert dg.is_fixed_point() == (k % 3 != 2)
+        scale = rng.choice([0.02, 0.2, 1.0, 4.0])
+        seed = sc.truth_pose + np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)]) * scale
+        knobs = (int(rng.integers(1, 12)), float(rng.choice([0.1, 1.0, 1e-6])), float(rng.choice([0.5, 2.0, 0.0])),
+                 float(rng.choice([0.5, 0.05])), float(rng.choice([0.5, 0.2, 0.02])))
+        w = oracle.optimize(grid, g, sc.scan_pts, knobs, seed)
+        pose = seed.copy()
+        assert opt.ScanMatch(dg, sc.scan_pts, knobs, pose) == w["cost"], k
+        assert np.array_equal(pose, w["pose"]) and opt.last_iterations == min(knobs[0], w["iterations"] + 1)
+        devs.append(dg); scans.append(sc.scan_pts); seeds.append(seed)
+        want.append(oracle.optimize(grid, g, sc.scan_pts, op, seed))
+    costs, poses, iters = opt.ScanMatchBatch(devs, scans, op, np.array(seeds))
+    assert np.array_equal(costs, [w["cost"] for w in want]) and np.array_equal(poses, [w["pose"] for w in want])
+    # errors: empty scan / uninitialised grid -> kMaxCost, pose untouched (optimize_scan_matcher.h:73-76)
+    pose = seeds[0].copy()
+    assert opt.ScanMatch(devs[0], np.zeros((0, 2)), op, pose) == 1000.0 and np.array_equal(pose, seeds[0])
+    fresh = matcher.ScanMatchMap.from_spec(ctx, synth.GridSpec(0.05, 0.15, 64, 64, 0.0, 0.0))
+    assert opt.ScanMatch(fresh, scans[0], op, pose) == 1000.0 and np.array_equal(pose, seeds[0])
+    with pytest.raises(matcher.RsmError) as e:
+        opt.ScanMatch(devs[0], scans[0], (0, 0.1, 0.5, 0.5, 0.5), pose)
+    assert "RSM_ERR_INVALID" in str(e.value)
+    fresh.close()
+    for dg in devs:
+        dg.close()
+
+
+def test_cell_boundary_fallback_paths(ctx, oracle, rng):
+    """Beams whose rotated end point sits exactly on a cell boundary for a whole tile fail the kernels'
+    provable index test and take the exact per-thread path.  Regression: the tiled kernel used to read
+    those beams' end points from a buffer that the prefetch of a later chunk had already overwritten.
+    Axis-aligned search angle (index 0 is exactly 0 rad), an integer-aligned centre and end points on a
+    half-cell lattice put every beam of angle 0 on that path; other angles run the fast path."""
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    for n_pts, half_lattice, window, size in ((200, 1.0, 0.6, 200), (333, 0.2, 0.6, 200), (97, 1.0, 0.25, 200),
+                                              (150, 1.0, 2.4, 320), (700, 0.05, 2.4, 320), (260, 1.0, 3.2, 400)):
+        g = synth.GridSpec(0.05, 0.15, size, size, 0.0, 0.0)
+        levels = np.array([0.3, 0.5642, 0.6666, 0.7046, 0.7875, 0.8324, 1.0], dtype=np.float32)
+        grid = levels[rng.integers(0, len(levels), (size, size))]
+        pts = rng.uniform(-60, 60, (n_pts, 2))
+        snap = rng.random(n_pts) < half_lattice
+        pts[snap] = np.round(pts[snap] * 2) / 2            # multiples of half a cell
+        seed = np.array([size // 2 * 0.05, size // 2 * 0.05, 0.3])
+        p = synth.pass_param(window, 0.05, 0.3, 0.1, 0.3, 100000, True, 0)     # angle index 0: 0.3 - 0.3 = 0 rad exactly
+        dg = matcher.ScanMatchMap.from_spec(ctx, g)
+        dg.upload(grid)
+        assert dg.is_fixed_point()
+        centre = oracle.world_to_map(g, seed)
+        assert centre[0] == size // 2 and centre[2] - 0.3 == 0.0
+        so = oracle.scores(grid, g, pts, p, centre)
+        sd = m.scores(dg, pts, p, seed)
+        assert np.array_equal(so, sd), (n_pts, window, int((so != sd).sum()))
+        want = oracle.match(grid, g, pts, p, seed)
+        pose, cov = seed.copy(), np.eye(3)
+        assert_pass_equal(m.ScanMatch(dg, pts, p, pose, cov), pose, cov, want)
+        dg.close()

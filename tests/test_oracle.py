@@ -161,3 +161,76 @@ def test_mapcheck_oracle_matches_reference(oracle, ref, rng):
         seen.add(a)
     assert len(seen) > 20
     ref.pubmap_destroy(m)
+
+
+# ---- Gauss-Newton matcher: BasedOptimizeScanMatch ---------------------------------
+def test_ldlt3_solve_properties(oracle, rng):
+    """The restated 3x3 LDLT (the one step that cannot be pinned against real Eigen here): solves SPD and
+    indefinite symmetric systems to rounding accuracy whatever the pivot order, returns the pseudo-inverse
+    solution for a singular diagonal block and zeros for H = 0."""
+    for k in range(300):
+        A = rng.normal(size=(3, 3))
+        H = A @ A.T if k % 2 else (A + A.T)
+        H = H[np.ix_(*[rng.permutation(3)] * 2)] * 10.0 ** rng.integers(-3, 4)
+        b = rng.normal(size=3)
+        x = oracle.ldlt3_solve(H, b)
+        assert np.allclose(H @ x, b, rtol=0, atol=1e-9 * np.linalg.cond(H) * max(1.0, np.abs(b).max()))
+    assert np.array_equal(oracle.ldlt3_solve(np.zeros((3, 3)), [1.0, 2.0, 3.0]), np.zeros(3))
+    x = oracle.ldlt3_solve(np.diag([4.0, 0.0, 2.0]), [8.0, 5.0, 1.0])
+    assert np.array_equal(x, [2.0, 0.0, 0.5])
+
+
+def test_optimize_oracle_matches_golden(oracle):
+    """Restatement vs the outputs of the reference's own optimize_scan_matcher.h (committed fixture):
+    cost and pose bit for bit, on the fine and the coarse map, plus the chain that starts with the optimiser."""
+    from helpers import optimize_cases
+    z, cases = optimize_cases()
+    for tag, sc, gc, base_c, scan_c in cases:
+        gf = sc.grid
+        grid_f = oracle.build_grid(gf, sc.base_pts, sc.base_poses)
+        grid_c = oracle.build_grid(gc, base_c, sc.base_poses)
+        for mi, (grid, g, pts) in enumerate(((grid_f, gf, sc.scan_pts), (grid_c, gc, scan_c))):
+            for oi, op in enumerate(z["opt_sets"]):
+                for si, d in enumerate(z["seed_deltas"]):
+                    r = oracle.optimize(grid, g, pts, op, sc.truth_pose + d)
+                    assert r["cost"] == z[tag + "_cost"][mi, oi, si], (tag, mi, oi, si)
+                    assert np.array_equal(r["pose"], z[tag + "_pose"][mi, oi, si])
+        for fi, fc in enumerate(z["failed_costs"]):
+            for ui, use_fine in enumerate((True, False)):
+                for si, d in enumerate(z["seed_deltas"][:4]):
+                    r = oracle.match_chain_opt(grid_c, gc, scan_c, grid_f, gf, sc.scan_pts, synth.chain_yaml(), z["opt_sets"][0],
+                                               fc, sc.truth_pose + d, use_fine=use_fine)
+                    assert r["score"] == z[tag + "_chain_score"][fi, ui, si], (tag, fi, ui, si)
+                    assert np.array_equal(r["pose"], z[tag + "_chain_pose"][fi, ui, si])
+                    assert np.array_equal(r["cov"], z[tag + "_chain_cov"][fi, ui, si])
+                    assert r["optimize_cost"] == z[tag + "_chain_resp"][fi, ui, si, 0]
+                    assert np.array_equal(r["responses"], z[tag + "_chain_resp"][fi, ui, si, 1:])
+    # both branches of scan_matchers.h:224-226 are exercised by the fixture
+    resp = z["pair0_chain_resp"]
+    assert (resp[:, 0, :, 1] == 0).any() and (resp[:, 0, :, 1] != 0).any()
+
+
+def test_optimize_oracle_matches_reference(oracle, ref, rng):
+    """Live reference header vs the restatement on random problems (random grids, float-valued cells,
+    scans that partly leave the map, random knobs)."""
+    compared = 0
+    for k in range(60):
+        sc = random_scenario(rng, n_points=int(rng.integers(5, 300)), size=int(rng.choice([96, 160])))
+        g = sc.grid
+        grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+        if k % 4 == 3:   # arbitrary float cells instead of the few blur levels
+            grid = rng.random(grid.shape).astype(np.float32)
+        m = ref.create_map(g)
+        ref.write_map(m, grid)
+        op = (int(rng.integers(1, 12)), float(rng.choice([0.1, 1.0, 1e-6])), float(rng.choice([0.5, 2.0, 0.0])),
+              float(rng.choice([0.5, 0.05])), float(rng.choice([0.5, 0.2, 0.02])))
+        scale = rng.choice([0.02, 0.2, 1.0, 4.0])
+        seed = sc.truth_pose + np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)]) * scale
+        a = oracle.optimize(grid, g, sc.scan_pts, op, seed)
+        b = ref.optimize(m, sc.scan_pts, op, seed)
+        ref.destroy_map(m)
+        if a["oob_reads"]:     # a point in the strip size_y-1 < y < size_y: the reference reads past its cell array
+            continue
+        compared += 1
+        assert a["cost"] == b["cost"] and np.array_equal(a["pose"], b["pose"]), (k, a, b)
+    assert compared >= 40

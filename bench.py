@@ -54,7 +54,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=256, help="loop-closure extra (0 = skip)")
     ap.add_argument("--cpu-reps", type=int, default=4, help="full config-2 passes timed for cpu_baseline")
-    ap.add_argument("--lc-contexts", type=int, default=3, help="host threads / contexts per GPU for the loop-closure extra")
+    ap.add_argument("--lc-contexts", type=int, default=0,
+                    help="host threads / contexts per GPU for the loop-closure extra (0 = min(4, host cores / ranks))")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-wide", action="store_true", help="skip the angle-sliced wide-window extra (BASELINE configs[4])")
     return ap.parse_args()
@@ -241,6 +242,8 @@ def main():
         return float(t.item())
 
     # the library's host worker pool shares the box's cores with the other ranks
+    if args.lc_contexts <= 0:
+        args.lc_contexts = max(1, min(4, (os.cpu_count() or 1) // max(1, world)))
     os.environ.setdefault("RSM_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world) // max(1, args.lc_contexts))))
     ctx = matcher.Context(local_rank)
     sc = rank_scenario(rank)

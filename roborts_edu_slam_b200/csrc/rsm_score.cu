@@ -777,8 +777,7 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
       for (int r = 0; b < nv; ++r) {
         const int which = r & 1;
         const long long t0 = DBG_T();
-        if (r >= 2) mbar_wait(&sEmpty[which], (uint32_t)(((r >> 1) - 1) & 1), 200);
-        const long long t1 = DBG_T();
+        const long long t1 = t0;
         const int j = b + lane;
         int2 e = make_int2(-1, -1);
         if (j < nv) e = sBeam[j];
@@ -805,6 +804,9 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
         const bool rany = __shfl_sync(0xffffffffu, (int)any, srcl) != 0;
         int rxl = __shfl_sync(0xffffffffu, xl, srcl), ryl = __shfl_sync(0xffffffffu, ymin, srcl);
         if (!rany) { rxl = 0; ryl = 0; }
+        // the round is planned in registers while the compute warps still read this buffer's bases; only
+        // publishing them and the copy itself wait for the buffer
+        if (r >= 2) mbar_wait(&sEmpty[which], (uint32_t)(((r >> 1) - 1) & 1), 100);
         if (lane < n) sBase[which][lane] = safe ? (e.y - ryl) * rw + (e.x - rxl) : -1;
         const unsigned int unsafe = __ballot_sync(0xffffffffu, lane < n && !safe);
         if (lane == 0) { sMeta[which][0] = n; sMeta[which][1] = rw; sMeta[which][2] = (b + n >= nv) ? 1 : 0; sMeta[which][3] = unsafe == 0u; }

@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsm.so")
+LIB_PATH = os.environ.get("RSM_LIB_PATH") or os.path.join(_HERE, "librsm.so")   # override: debug builds only
 
 COARSE_CORRELATION_SCAN_MATCH = 0
 FINE_CORRELATION_SCAN_MATCH = 1

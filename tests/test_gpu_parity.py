@@ -705,3 +705,59 @@ def test_cell_boundary_fallback_paths(ctx, oracle, rng):
         pose, cov = seed.copy(), np.eye(3)
         assert_pass_equal(m.ScanMatch(dg, pts, p, pose, cov), pose, cov, want)
         dg.close()
+
+
+def test_fuzz_every_scoring_variant(ctx, oracle):
+    """Seeded fuzz over what selects a scoring kernel and its slow paths: window width (flat / tiled /
+    staged, one or several tiles, cluster splits), search step (unit, integer, fractional), grid width
+    (both padded pitches and the run-time pitch), fixed-point vs float cells, beam subsampling, end points
+    snapped to cell boundaries, integer-aligned centres.  Every candidate score bit-equal, then the pass."""
+    rng = np.random.default_rng(987654321)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    levels = np.array([0.3, 0.5642, 0.6666, 0.7046, 0.7875, 0.8324, 1.0], dtype=np.float32)
+    n_done = 0
+    for trial in range(90):
+        size = int(rng.choice([160, 300, 544, 700, 1200]))
+        res = 0.05
+        n_xy = int(rng.choice([3, 5, 7, 11, 13, 25, 33, 49, 65, 81, 97]))
+        step_cells = float(rng.choice([1.0, 1.0, 1.0, 2.0, 0.4, 0.2, 0.5]))
+        if n_xy >= 49 and rng.random() < 0.7:
+            step_cells = 1.0                      # mostly the staged kernel for wide windows
+        sres = res * step_cells
+        window = sres * (n_xy - 1)
+        n_ang = int(rng.integers(1, 8))
+        ares = float(rng.choice([0.0349, 0.1, 0.01]))
+        aoff = ares * (n_ang - 1) / 2 + 1e-9
+        P = int(rng.choice([1, 7, 33, 100, 257, 640, 900]))
+        if n_xy * n_xy * n_ang * P > 6e7:
+            P = max(1, int(6e7 / (n_xy * n_xy * n_ang)))
+        half_window_cells = window / res / 2
+        reach = size / 2 - half_window_cells - 6
+        if reach < 8:
+            continue
+        pts = rng.uniform(-1, 1, (P, 2))
+        pts = pts / np.maximum(1.0, np.linalg.norm(pts, axis=1, keepdims=True)) * reach
+        snap = rng.random(P) < rng.choice([0.0, 0.1, 1.0])
+        pts[snap] = np.round(pts[snap] * 2) / 2
+        g = synth.GridSpec(res, 0.15, size, size, float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)))
+        fixed = rng.random() < 0.75
+        grid = levels[rng.integers(0, len(levels), (size, size))] if fixed else rng.random((size, size)).astype(np.float32)
+        centre_cells = np.array([size / 2, size / 2]) + (rng.integers(-3, 4, 2) if rng.random() < 0.5 else rng.uniform(-3, 3, 2))
+        theta = float(rng.choice([0.0, aoff, rng.uniform(-3, 3)]))
+        seed = np.array([centre_cells[0] * res - g.off_x, centre_cells[1] * res - g.off_y, theta])
+        use_pts = int(rng.choice([100000, 100000, 50, 7]))
+        p = synth.pass_param(window, sres, aoff, ares, 0.3, use_pts, bool(rng.integers(0, 2)), int(rng.integers(0, 3)))
+        dg = matcher.ScanMatchMap.from_spec(ctx, g)
+        dg.upload(grid)
+        centre = oracle.world_to_map(g, seed)
+        geo = oracle.geometry(g, p, P, centre)
+        so = oracle.scores(grid, g, pts, p, centre)
+        sd = m.scores(dg, pts, p, seed)
+        assert np.array_equal(so, sd), (trial, size, n_xy, step_cells, n_ang, P, fixed, use_pts, int((so != sd).sum()))
+        want = oracle.match(grid, g, pts, p, seed)
+        pose, cov = seed.copy(), np.eye(3)
+        assert_pass_equal(m.ScanMatch(dg, pts, p, pose, cov), pose, cov, want)
+        assert (geo["n_xy"], geo["n_ang"]) == (m.last_detail.n_xy, m.last_detail.n_ang)
+        dg.close()
+        n_done += 1
+    assert n_done >= 70

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=256, help="loop-closure extra (0 = skip)")
     ap.add_argument("--cpu-reps", type=int, default=4, help="full config-2 passes timed for cpu_baseline")
+    ap.add_argument("--no-widened", action="store_true", help="skip the map-check / Gauss-Newton extras (N = 1 only)")
     ap.add_argument("--lc-contexts", type=int, default=0,
                     help="host threads / contexts per GPU for the loop-closure extra (0 = min(4, host cores / ranks))")
     ap.add_argument("--no-flush", action="store_true")
@@ -400,6 +401,74 @@ def main():
             st.close()
         for c, _ in parts[1:]:
             c.close()
+    # ---- widened rows, N = 1 only: map check and Gauss-Newton matcher ------
+    widened = None
+    if world == 1 and not args.no_widened:
+        widened = {}
+        orc = None
+        if args.cpu_reps > 0:
+            from oracle.oracle_py import Oracle      # CPU baseline leg only (the checker, never the product path)
+            orc = Oracle()
+        # (1) MapCheckPenalize for a batch of candidate poses: 1081-beam scan, 100 check rays per pose
+        zc = np.load(os.path.join(ROOT, "tests", "golden", "mapcheck_pair0.npz"), allow_pickle=False)
+        gsp = zc["grid_spec"]
+        gpub = synth.GridSpec(float(gsp[0]), 0.0, int(gsp[1]), int(gsp[2]), float(gsp[3]), float(gsp[4]), 0.5, 0.88, False)
+        occ = np.unpackbits(zc["occ_packed"])[: gpub.size_x * gpub.size_y].reshape(gpub.size_y, gpub.size_x)
+        pm = matcher.ScanMatchMap.from_spec(ctx, gpub)
+        pm.upload_occupancy(occ)
+        rng = np.random.default_rng(7)
+        n_poses = 4096
+        poses_mc = zc["poses"][0] + rng.uniform(-1.0, 1.0, (n_poses, 3)) * np.array([1.5, 1.5, 0.5])
+        scan_mc = zc["scan_pts"]
+        pm.MapCheckPenalize(scan_mc, poses_mc, 100, 2.5, 0.015, True)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            coeff = pm.MapCheckPenalize(scan_mc, poses_mc, 100, 2.5, 0.015, True)
+        dt = (time.perf_counter() - t0) / 5
+        entry = {"workload": "MapCheckPenalize, %d candidate poses x one %d-point scan, check_point_num 100, logistic (loop-closure form)" % (n_poses, len(scan_mc)),
+                 "poses_per_s": n_poses / dt, "ms_per_batch": dt * 1e3, "timing": "host wall clock, host poses in -> host coefficients out"}
+        if args.cpu_reps > 0:
+            n_cpu = 256
+            t0 = time.perf_counter()
+            want = np.array([orc.map_check_penalize(occ, gpub, scan_mc, p_, 100, 2.5, 0.015, True) for p_ in poses_mc[:n_cpu]])
+            dtc = time.perf_counter() - t0
+            entry["cpu_baseline"] = {"value": n_cpu / dtc, "unit": "poses/s", "cores": 1, "kind": "port", "sample": "%d of the poses" % n_cpu}
+            entry["equals_cpu"] = bool(np.array_equal(want, coeff[:n_cpu]))
+        widened["map_check"] = entry
+        pm.close()
+        # (2) BasedOptimizeScanMatch for a batch of problems (config 4 pairs, yaml knobs)
+        n_opt = 128
+        pairs_o = synth.config4(n_opt)
+        grids_o = []
+        for sc_ in pairs_o:
+            dg_ = matcher.ScanMatchMap.from_spec(ctx, sc_.grid)
+            dg_.InitMapWithRangeVec(sc_.base_pts, sc_.base_poses, sc_.grid.default_prob, sc_.grid.sigma, sc_.grid.occu_offset, True)
+            grids_o.append(dg_)
+        opt = matcher.BasedOptimizeScanMatch(ctx)
+        knobs = (10, 0.1, 0.5, 0.5, 0.5)
+        scans_o = [sc_.scan_pts for sc_ in pairs_o]
+        seeds_o = np.array([sc_.seed_pose for sc_ in pairs_o])
+        opt.ScanMatchBatch(grids_o, scans_o, knobs, seeds_o)
+        ctx.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            costs_o, poses_o, iters_o = opt.ScanMatchBatch(grids_o, scans_o, knobs, seeds_o)
+        dt = (time.perf_counter() - t0) / 3
+        entry = {"workload": "BasedOptimizeScanMatch, %d problems (config-4 pairs, 1081-beam scans, 480^2 grids), yaml knobs" % n_opt,
+                 "problems_per_s": n_opt / dt, "ms_per_batch": dt * 1e3, "mean_iterations": float(iters_o.mean()),
+                 "launches_per_batch": ctx.stats()["kernel_launches"] / 3,
+                 "timing": "host wall clock, host scans + seeds in -> host poses + costs out"}
+        if args.cpu_reps > 0:
+            n_cpu = 16
+            cpu_grids = [orc.build_grid(sc_.grid, sc_.base_pts, sc_.base_poses) for sc_ in pairs_o[:n_cpu]]
+            t0 = time.perf_counter()
+            want = [orc.optimize(cpu_grids[i], pairs_o[i].grid, scans_o[i], knobs, seeds_o[i]) for i in range(n_cpu)]
+            dtc = time.perf_counter() - t0
+            entry["cpu_baseline"] = {"value": n_cpu / dtc, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "%d of the problems" % n_cpu}
+            entry["equals_cpu"] = bool(all(want[i]["cost"] == costs_o[i] and np.array_equal(want[i]["pose"], poses_o[i]) for i in range(n_cpu)))
+        widened["optimize"] = entry
+        for dg_ in grids_o:
+            dg_.close()
     # ---- wide relocalisation extra (config 5): ONE window angle-sliced over the ranks -----------
     wide = None
     if not args.no_wide:
@@ -508,6 +577,8 @@ def main():
             line["cpu_baseline"] = cpu
         if loop:
             line["loop_closure"] = loop
+        if widened is not None:
+            line["widened"] = widened
         if wide:
             line["wide_window"] = wide
         print(json.dumps(line), flush=True)

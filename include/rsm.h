@@ -147,6 +147,30 @@ int rsm_map_check_penalize(rsm_ctx* ctx, const rsm_grid* pub_map, int n, const d
 int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double sigma,
                        double occu_offset, int use_blur, int n_scans, const int32_t* n_pts,
                        const double* pts_xy, const double* poses_world);
+/* ---- front-end map maintenance ----------------------------------------
+ * The front-end scan-match maps are constructed once and then only stamped (just_update_occu,
+ * slam/slam_processor.cpp:466-512) by one UpdateMapByRange per accepted scan (:529-571); keeping them
+ * on the device replaces the whole-map upload an adapter would otherwise make after every scan.
+ * The resize POLICY (bound box bookkeeping, GridMapBase::UpdateBound / ExtendSize,
+ * map/grid_map_base.h:188-274) stays with the caller -- the reference's own map object or a restatement
+ * -- which tells the device map what happened:
+ *   rsm_grid_fill             a constructed map: new CellType[n]{default_prob} gives cell 0 the map's
+ *                             default_prob and every other cell kDefaultCellProb = 0.5
+ *                             (map/grid_map_base.h:150-163, map/grid_map_cell.h:30); not yet IsMapInit().
+ *   rsm_grid_update_by_range  UpdateMapByRange(range_data, use_blur) returned true: stamp that scan
+ *                             (map/occu_grid_map.h:258-329, 531-576); no reset.
+ *   rsm_grid_extend           UpdateMapByRange / MapSizeCheck extended the map (and dropped the scan,
+ *                             :296-300): new size, where the old cell (0,0) went
+ *                             (pre_grid_offset = -GetFloorMin()), the new map_offset_.  New cells get
+ *                             fill_prob, cell 0 first_cell_prob, then the old rows are copied in
+ *                             (grid_map_base.h:222-238).  Drops an uploaded occupancy mask. */
+int rsm_grid_fill(rsm_ctx* ctx, rsm_grid* grid, float fill_prob, float first_cell_prob);
+int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
+                             const double* pts_xy, int n_pts, const double pose_world[3]);
+int rsm_grid_extend(rsm_ctx* ctx, rsm_grid* grid, int new_size_x, int new_size_y, int pre_grid_offset_x,
+                    int pre_grid_offset_y, double new_offset_x, double new_offset_y, float fill_prob,
+                    float first_cell_prob);
+int rsm_grid_geometry(const rsm_grid* grid, int* size_x, int* size_y, double* offset_x, double* offset_y);
 int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out);
 /* 1 if the grid is held as exact 2^-25 fixed point (integer gather path), 0 if as float32. */
 int rsm_grid_is_fixed_point(const rsm_grid* grid);

@@ -239,6 +239,12 @@ class Ref:
         L.ref_match_chain.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
         L.ref_blur_kernel.restype = c_i
         L.ref_blur_kernel.argtypes = [c_d, c_d, c_p, c_i]
+        L.ref_frontend_map_create.restype = c_p
+        L.ref_frontend_map_create.argtypes = [c_d, c_i, c_i, c_d, c_d, c_d, ctypes.c_float, c_d, c_d]
+        L.ref_frontend_map_update.restype = c_i
+        L.ref_frontend_map_update.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p]
+        L.ref_frontend_map_size_check.restype = c_i
+        L.ref_frontend_map_size_check.argtypes = [c_p, c_p, c_d, c_d, c_p]
         L.ref_optimize.restype = c_d
         L.ref_optimize.argtypes = [c_p, c_i, c_p, c_p, c_p]
         L.ref_match_chain_opt.restype = c_d
@@ -281,6 +287,29 @@ class Ref:
                                          org.ctypes.data if org is not None else None, int(check_point_num),
                                          float(bound_tolerance), float(penalty_gain), 1 if use_blur else 0,
                                          1 if use_logistic else 0)
+
+    # ---- front-end scan-match map (auto-resize, incremental UpdateMapByRange) ---------------------
+    def frontend_map_create(self, g, extend_factor=0.2):
+        return self.L.ref_frontend_map_create(g.res, g.size_x, g.size_y, g.off_x, g.off_y, g.sigma, g.default_prob,
+                                              g.occu_offset, float(extend_factor))
+
+    def frontend_map_update(self, m, pts_cells, pose_world, use_blur=True):
+        """-> (stamped?, (size_x, size_y, off_x, off_y) afterwards)"""
+        pts, pose = _f64(pts_cells), _f64(pose_world)
+        geom = np.zeros(4)
+        ok = self.L.ref_frontend_map_update(m, len(pts), pts.ctypes.data, pose.ctypes.data, int(use_blur), geom.ctypes.data)
+        return bool(ok), (int(geom[0]), int(geom[1]), float(geom[2]), float(geom[3]))
+
+    def frontend_map_size_check(self, m, pose_world, range_max, offset):
+        pose = _f64(pose_world)
+        geom = np.zeros(4)
+        ok = self.L.ref_frontend_map_size_check(m, pose.ctypes.data, float(range_max), float(offset), geom.ctypes.data)
+        return bool(ok), (int(geom[0]), int(geom[1]), float(geom[2]), float(geom[3]))
+
+    def read_map_sized(self, m, size_x, size_y):
+        out = np.empty((size_y, size_x), dtype=np.float32)
+        self.L.ref_map_read(m, out.ctypes.data)
+        return out
 
     def optimize(self, m, pts, op, pose_world):
         """The reference's BasedOptimizeScanMatch::ScanMatch (LDLT solve = the stand-in's restatement of Eigen's)."""

@@ -27,9 +27,25 @@
 #include <mutex>
 #include <vector>
 
+#include <cfloat>
+#include <cmath>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <condition_variable>
+
+// The front-end map tests need GridMapBase::map_offset_ (no getter) after a resize: open the reference's
+// classes for this translation unit only (test infrastructure; layout is unaffected, nothing is modified).
+#define private public
+#define protected public
 #include "scan_match/correlate_scan_matcher.h"
 #include "scan_match/optimize_scan_matcher.h"
 #include "map/slam_map.h"
+
+#undef private
+#undef protected
 
 #include "ref_types.h"
 
@@ -286,6 +302,49 @@ double ref_match_chain_opt(void* m_coarse, int n_c, const double* xy_c, void* m_
   for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) cov[3 * r + k] = c(r, k);
   pose_world[0] = best_pose[0]; pose_world[1] = best_pose[1]; pose_world[2] = best_pose[2];
   return scan_match_score;
+}
+
+// ---- front-end scan-match map: incremental UpdateMapByRange with auto-resize (slam_processor.cpp:466-512, 529-571) ----
+// Constructed like CreateAllMap does (no Reset: cell 0 = default_prob, every other cell kDefaultCellProb = 0.5,
+// grid_map_base.h:150-163), auto-resize on, just_update_occu on.
+void* ref_frontend_map_create(double resolution, int size_x, int size_y, double off_x, double off_y, double deviation,
+                              float default_prob, double occu_offset, double extend_factor) {
+  auto* h = new RefMap;
+  h->map = std::make_shared<ScanMatchMap>(resolution, Eigen::Vector2i(size_x, size_y), Eigen::Vector2d(off_x, off_y),
+                                          deviation, default_prob);
+  h->map->set_extend_factor(extend_factor);
+  h->map->set_cell_occu_prob_offset(occu_offset);
+  h->map->set_use_auto_map_resize(true);
+  h->map->set_just_update_occu(true);
+  return h;
+}
+
+// UpdateMapByRange(range_data, use_blur): 1 = the scan was stamped, 0 = the map was extended instead (the scan is
+// dropped, occu_grid_map.h:296-300).  geom_out = {size_x, size_y, map_offset_x, map_offset_y}.
+int ref_frontend_map_update(void* m, int n, const double* xy, const double* pose_world, int use_blur, double* geom_out) {
+  auto* h = static_cast<RefMap*>(m);
+  auto rd = MakeScan(n, xy, pose_world);
+  const bool ok = h->map->UpdateMapByRange(rd, use_blur != 0);
+  if (geom_out) {
+    geom_out[0] = h->map->GetSizeX(); geom_out[1] = h->map->GetSizeY();
+    geom_out[2] = h->map->map_offset_[0]; geom_out[3] = h->map->map_offset_[1];
+  }
+  return ok ? 1 : 0;
+}
+
+// MapSizeCheck's bound update (scan_matchers.h:365-390): 1 = inside, 0 = the map was extended.
+int ref_frontend_map_size_check(void* m, const double* pose_world, double range_max, double offset, double* geom_out) {
+  auto* h = static_cast<RefMap*>(m);
+  Eigen::Vector3d center_pose = h->map->GetMapCoordsPose(Eigen::Vector3d(pose_world[0], pose_world[1], pose_world[2]));
+  const double max_size = (range_max + offset) / h->map->GetCellLength();
+  BoundBox2d box(Eigen::Vector2d((center_pose.x() - max_size), (center_pose.y() - max_size)),
+                 Eigen::Vector2d((center_pose.x() + max_size), (center_pose.y() + max_size)));
+  const bool ok = h->map->UpdateBound(box);
+  if (geom_out) {
+    geom_out[0] = h->map->GetSizeX(); geom_out[1] = h->map->GetSizeY();
+    geom_out[2] = h->map->map_offset_[0]; geom_out[3] = h->map->map_offset_[1];
+  }
+  return ok ? 1 : 0;
 }
 
 // GaussianBlur kernel as the reference builds it (occu_grid_map.h:83-105): returns half size,

@@ -1573,6 +1573,131 @@ int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double 
   return RSM_OK;
 }
 
+// ---- front-end map maintenance: the scan-match maps stay on the device between scans ----
+int rsm_grid_fill(rsm_ctx* ctx, rsm_grid* grid, float fill_prob, float first_cell_prob) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || !(fill_prob >= 0.0f) || !(first_cell_prob >= 0.0f)) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_fill: bad arguments");
+  int vf = 0, v0 = 0;
+  const bool fixed = fix_ok(fill_prob, &vf) && fix_ok(first_cell_prob, &v0);
+  if (!fixed) { std::memcpy(&vf, &fill_prob, 4); std::memcpy(&v0, &first_cell_prob, 4); }
+  int rc = ensure_dev(ctx, ctx->d_work, sizeof(FillJob) * 2);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, sizeof(FillJob) * 2);
+  if (rc) return rc;
+  FillJob* F = reinterpret_cast<FillJob*>(ctx->h_up.p);
+  F[0].grid = grid->d_cells; F[0].n_cells = (long long)grid->pitch * grid->size_y; F[0].value = vf;
+  F[1].grid = grid->d_cells; F[1].n_cells = 1; F[1].value = v0;      // new CellType[n]{default}: only cell 0 gets it
+  CU(cudaMemcpyAsync(ctx->d_work.p, F, sizeof(FillJob) * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_fill(1, 148, ctx->stream, reinterpret_cast<const FillJob*>(ctx->d_work.p)));
+  CU(launch_fill(1, 1, ctx->stream, reinterpret_cast<const FillJob*>(ctx->d_work.p) + 1));
+  ctx->stats.kernel_launches += 2; ctx->stats.h2d_bytes += sizeof(FillJob) * 2;
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  grid->fixed = fixed;
+  grid->init = false;       // a constructed map is not IsMapInit() until its first update (grid_map_base.h:311-317)
+  return RSM_OK;
+}
+
+int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
+                             const double* pts_xy, int n_pts, const double pose_world[3]) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || n_pts < 0 || (n_pts > 0 && !pts_xy) || !pose_world)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_grid_update_by_range: bad arguments");
+  RasterPlan pl;
+  // the stamp patterns depend on the map's cell representation, which the fill / upload decided
+  int rc = plan_raster(ctx, 0.5f, sigma, grid->resolution, occu_offset, use_blur, pl);
+  if (rc) return rc;
+  if (grid->fixed && !pl.fixed) return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_grid_update_by_range: the blur levels are not 2^-25 multiples but the map is held in fixed point");
+  if (!grid->fixed && pl.fixed) {     // float map: stamp float patterns
+    std::vector<double> k;
+    const int half = blur_kernel(sigma, grid->resolution, k);
+    for (size_t i = 0; i < pl.stamp.size(); ++i) {
+      const float p = static_cast<float>(k[i] * occu_offset);
+      pl.stamp[i] = 0;
+      if (p <= 1.0f && p > 0.0f) std::memcpy(&pl.stamp[i], &p, 4);
+    }
+    (void)half;
+    const float onef = 1.0f;
+    std::memcpy(&pl.one, &onef, 4);
+    pl.fixed = false;
+  }
+  Layout dl;
+  const size_t o_scan = dl.take(sizeof(RasterScan));
+  const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t up_bytes = dl.off;
+  rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+  if (rc) return rc;
+  double* d_pts = nullptr;
+  if (n_pts) { rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts); if (rc) return rc; }
+  char* up = ctx->h_up.p;
+  char* dw = ctx->d_work.p;
+  make_raster_scan(grid, pose_world, d_pts, n_pts, *reinterpret_cast<RasterScan*>(up + o_scan));
+  std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += up_bytes;
+  {
+    Prof p(ctx, KC_RASTER);
+    CU(launch_raster(1, ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scan), reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+  }
+  ctx->stats.kernel_launches++;
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  grid->init = true;      // SetUpdated() (occu_grid_map.h:325)
+  return RSM_OK;
+}
+
+int rsm_grid_extend(rsm_ctx* ctx, rsm_grid* grid, int new_size_x, int new_size_y, int pre_grid_offset_x, int pre_grid_offset_y,
+                    double new_offset_x, double new_offset_y, float fill_prob, float first_cell_prob) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || !grid->owned || new_size_x <= 0 || new_size_y <= 0 || new_size_x > 32768 || new_size_y > 32768 ||
+      pre_grid_offset_x < 0 || pre_grid_offset_y < 0 || pre_grid_offset_x + grid->size_x > new_size_x ||
+      pre_grid_offset_y + grid->size_y > new_size_y)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_grid_extend: the old map must fit inside the new one");
+  int vf = 0, v0 = 0;
+  const bool fill_fixed = fix_ok(fill_prob, &vf) && fix_ok(first_cell_prob, &v0);
+  if (grid->fixed && !fill_fixed) return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_grid_extend: fill value is not a 2^-25 multiple but the map is held in fixed point");
+  if (!grid->fixed) { std::memcpy(&vf, &fill_prob, 4); std::memcpy(&v0, &first_cell_prob, 4); }
+  const int new_pitch = grid_pitch_for(new_size_x);
+  void* d_new = nullptr;
+  cudaError_t e = cudaMalloc(&d_new, size_t(new_pitch) * new_size_y * 4);
+  if (e != cudaSuccess) return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(extended grid) failed: %s", cudaGetErrorString(e));
+  int rc = ensure_dev(ctx, ctx->d_work, sizeof(FillJob) * 2);
+  if (rc == RSM_OK) rc = ensure_pinned(ctx, ctx->h_up, sizeof(FillJob) * 2);
+  if (rc) { cudaFree(d_new); return rc; }
+  FillJob* F = reinterpret_cast<FillJob*>(ctx->h_up.p);
+  F[0].grid = d_new; F[0].n_cells = (long long)new_pitch * new_size_y; F[0].value = vf;
+  F[1].grid = d_new; F[1].n_cells = 1; F[1].value = v0;
+  // grid_map_base.h:226-238: new CellType[n]{default_cell_prob_}, then the old rows are copied in at pre_grid_offset
+  cudaError_t err = cudaMemcpyAsync(ctx->d_work.p, F, sizeof(FillJob) * 2, cudaMemcpyHostToDevice, ctx->stream);
+  if (err == cudaSuccess) err = launch_fill(1, 148, ctx->stream, reinterpret_cast<const FillJob*>(ctx->d_work.p));
+  if (err == cudaSuccess) err = launch_fill(1, 1, ctx->stream, reinterpret_cast<const FillJob*>(ctx->d_work.p) + 1);
+  if (err == cudaSuccess)
+    err = cudaMemcpy2DAsync(static_cast<char*>(d_new) + (size_t(pre_grid_offset_y) * new_pitch + pre_grid_offset_x) * 4, size_t(new_pitch) * 4,
+                            grid->d_cells, size_t(grid->pitch) * 4, size_t(grid->size_x) * 4, size_t(grid->size_y),
+                            cudaMemcpyDeviceToDevice, ctx->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+  if (err != cudaSuccess) { cudaFree(d_new); return fail(ctx, RSM_ERR_CUDA, "rsm_grid_extend failed: %s", cudaGetErrorString(err)); }
+  ctx->stats.kernel_launches += 2;
+  cudaFree(grid->d_cells);
+  if (grid->d_occ) { cudaFree(grid->d_occ); grid->d_occ = nullptr; }
+  grid->d_cells = d_new;
+  grid->size_x = new_size_x; grid->size_y = new_size_y; grid->pitch = new_pitch;
+  grid->off_x = new_offset_x; grid->off_y = new_offset_y;
+  grid->tf.set(grid->scale, new_offset_x, new_offset_y);      // SetMapTransform (grid_map_base.h:253)
+  return RSM_OK;
+}
+
+int rsm_grid_geometry(const rsm_grid* grid, int* size_x, int* size_y, double* offset_x, double* offset_y) {
+  if (!grid) return RSM_ERR_INVALID;
+  if (size_x) *size_x = grid->size_x;
+  if (size_y) *size_y = grid->size_y;
+  if (offset_x) *offset_x = grid->off_x;
+  if (offset_y) *offset_y = grid->off_y;
+  return RSM_OK;
+}
+
 // ---- matching ----------------------------------------------------------------------------------
 int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
               double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {

@@ -98,6 +98,10 @@ ABI = {
     "rsm_grid_upload_f32": (c_i, [c_p, c_p, c_p]),
     "rsm_grid_rasterize": (c_i, [c_p, c_p, ctypes.c_float, c_d, c_d, c_i, c_i, c_p, c_p, c_p]),
     "rsm_grid_download_f32": (c_i, [c_p, c_p, c_p]),
+    "rsm_grid_fill": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
+    "rsm_grid_update_by_range": (c_i, [c_p, c_p, c_d, c_d, c_i, c_p, c_i, c_p]),
+    "rsm_grid_extend": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, ctypes.c_float, ctypes.c_float]),
+    "rsm_grid_geometry": (c_i, [c_p, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_d), ctypes.POINTER(c_d)]),
     "rsm_grid_upload_occupancy": (c_i, [c_p, c_p, c_p]),
     "rsm_map_check_penalize": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_i, c_p]),
     "rsm_grid_is_fixed_point": (c_i, [c_p]),
@@ -319,6 +323,30 @@ class ScanMatchMap:
         self.ctx.check(self.ctx.lib.rsm_grid_rasterize(self.ctx.h, self.h, float(default_prob), float(sigma),
                                                        float(occu_offset), int(use_blur), len(base_pts),
                                                        n_pts.ctypes.data, pts.ctypes.data, poses.ctypes.data))
+
+    # ---- front-end maintenance: the map stays on the device between scans ----------------------------
+    def fill(self, fill_prob=0.5, first_cell_prob=0.3):
+        """A freshly constructed map: cell 0 = default_prob, the others kDefaultCellProb (grid_map_base.h:150-163)."""
+        self.ctx.check(self.ctx.lib.rsm_grid_fill(self.ctx.h, self.h, float(fill_prob), float(first_cell_prob)))
+
+    def UpdateMapByRange(self, pts_cells, sensor_pose, sigma=0.15, occu_offset=0.88, use_blur=True):
+        """Stamp one scan (the reference's UpdateMapByRange returned true for it); no reset."""
+        pts = _f64(np.asarray(pts_cells).reshape(-1, 2))
+        pose = _f64(sensor_pose)
+        self.ctx.check(self.ctx.lib.rsm_grid_update_by_range(self.ctx.h, self.h, float(sigma), float(occu_offset), int(use_blur),
+                                                             pts.ctypes.data, len(pts), pose.ctypes.data))
+
+    def ExtendSize(self, new_size_x, new_size_y, pre_grid_offset, new_map_offset, fill_prob=0.5, first_cell_prob=0.3):
+        """Mirror of GridMapBase::ExtendSize (grid_map_base.h:188-254) once the caller's policy decided it."""
+        self.ctx.check(self.ctx.lib.rsm_grid_extend(self.ctx.h, self.h, int(new_size_x), int(new_size_y), int(pre_grid_offset[0]),
+                                                    int(pre_grid_offset[1]), float(new_map_offset[0]), float(new_map_offset[1]),
+                                                    float(fill_prob), float(first_cell_prob)))
+        self.size_x, self.size_y = int(new_size_x), int(new_size_y)
+
+    def geometry(self):
+        sx, sy, ox, oy = c_i(0), c_i(0), c_d(0), c_d(0)
+        self.ctx.check(self.ctx.lib.rsm_grid_geometry(self.h, ctypes.byref(sx), ctypes.byref(sy), ctypes.byref(ox), ctypes.byref(oy)))
+        return sx.value, sy.value, ox.value, oy.value
 
     def upload_occupancy(self, occupied):
         """Occupancy mask of a publishing map (PubMap) for MapCheckPenalize: nonzero where the

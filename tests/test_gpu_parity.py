@@ -761,3 +761,51 @@ def test_fuzz_every_scoring_variant(ctx, oracle):
         dg.close()
         n_done += 1
     assert n_done >= 70
+
+
+# ---- front-end map maintenance -----------------------------------------------
+def test_frontend_map_stays_on_device(ctx):
+    """A scan-match map kept on the device across 44 scans of a trajectory that leaves the initial extent on
+    every side: rsm_grid_fill / rsm_grid_update_by_range / rsm_grid_extend against the cells the reference's own
+    UpdateMapByRange + ExtendSize produced after every step (fixture), then a match on the grown map."""
+    import hashlib
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_frontend", os.path.join(os.path.dirname(__file__), "golden", "make_frontend.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)              # only its pure helpers are used (trajectory, scans, spec); Ref is not touched
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend_willow.npz"), allow_pickle=False)
+    g = mf.spec()
+    poses, pts = mf.trajectory(), mf.scans()
+    h = hashlib.sha256()
+    for a in pts:
+        h.update(np.ascontiguousarray(a).tobytes())
+    assert h.hexdigest() == str(z["inputs_sha"])
+    dg = matcher.ScanMatchMap.from_spec(ctx, g)
+    dg.fill(0.5, g.default_prob)
+    fresh = dg.download()
+    assert fresh[0, 0] == np.float32(0.3) and (fresh.ravel()[1:] == np.float32(0.5)).all()
+    scale = 1.0 / g.res
+    n_ext = 0
+    for k, (p, s) in enumerate(zip(poses, pts)):
+        sx, sy, ox, oy = (int(z["geom"][k][0]), int(z["geom"][k][1]), float(z["geom"][k][2]), float(z["geom"][k][3]))
+        if bool(z["stamped"][k]):
+            dg.UpdateMapByRange(s, p, g.sigma, g.occu_offset, True)
+        else:
+            osx, osy, oox, ooy = dg.geometry()
+            pre = (int(round((ox - oox) * scale)), int(round((oy - ooy) * scale)))
+            dg.ExtendSize(sx, sy, pre, (ox, oy), 0.5, g.default_prob)
+            n_ext += 1
+        assert dg.geometry() == (sx, sy, ox, oy)
+        cells = dg.download()
+        assert hashlib.sha256(cells.tobytes()).hexdigest() == str(z["shas"][k]), "step %d" % k
+    assert n_ext == 5 and dg.is_fixed_point()
+    final = np.full(cells.size, np.float32(0.5), dtype=np.float32)
+    final[z["final_nz_index"]] = z["final_nz_value"]
+    assert np.array_equal(cells.ravel(), final)
+    # the grown map is a normal lookup grid: match the last scan against it
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    pose, cov = poses[-1] + np.array([0.08, -0.05, 0.04]), np.eye(3)
+    r = m.ScanMatch(dg, pts[-1], synth.chain_yaml()[0], pose, cov)
+    assert r > 0.6 and np.hypot(*(pose[:2] - poses[-1][:2])) < 0.06
+    dg.close()

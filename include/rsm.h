@@ -172,6 +172,29 @@ int rsm_grid_extend(rsm_ctx* ctx, rsm_grid* grid, int new_size_x, int new_size_y
                     float first_cell_prob);
 int rsm_grid_geometry(const rsm_grid* grid, int* size_x, int* size_y, double* offset_x, double* offset_y);
 int rsm_grid_download_f32(rsm_ctx* ctx, rsm_grid* grid, float* prob_out);
+
+/* Publishing map on the device: PubMap = OccuGridMap<CountCell> (map/slam_map.h:35) as hit / pass / value
+ * planes.  rsm_pubmap_update_by_range is UpdateMapByRange(range_data) with ray-traced free space
+ * (map/occu_grid_map.h:258-329, 125-187, 474-530; map/grid_map_cell.h:92-108) for a scan the reference's
+ * resize policy accepted; update_free_factor / update_occu_factor are the CountCellFunctions knobs
+ * SlamProcessor::UpdateMap sets before every update (slam/slam_processor.cpp:538-551).  rsm_pubmap_extend
+ * mirrors ExtendSize like rsm_grid_extend.  rsm_pubmap_refresh_occupancy evaluates
+ * GetGridStates == Occupied (pass_count >= min_pass_through and value >= occu_threshold,
+ * map/grid_map_cell.h:125-136) into the mask rsm_map_check_penalize reads: pass
+ * rsm_pubmap_check_grid(pm) as its pub_map -- no occupancy upload. */
+typedef struct rsm_pubmap rsm_pubmap;
+int rsm_pubmap_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, double offset_x, double offset_y,
+                      float default_prob, rsm_pubmap** out);
+void rsm_pubmap_destroy(rsm_ctx* ctx, rsm_pubmap* pm);
+int rsm_pubmap_update_by_range(rsm_ctx* ctx, rsm_pubmap* pm, const double* pts_xy, int n_pts,
+                               const double pose_world[3], float update_free_factor, float update_occu_factor);
+int rsm_pubmap_extend(rsm_ctx* ctx, rsm_pubmap* pm, int new_size_x, int new_size_y, int pre_grid_offset_x,
+                      int pre_grid_offset_y, double new_offset_x, double new_offset_y);
+int rsm_pubmap_refresh_occupancy(rsm_ctx* ctx, rsm_pubmap* pm, float occu_threshold, float min_pass_through);
+const rsm_grid* rsm_pubmap_check_grid(const rsm_pubmap* pm);
+int rsm_pubmap_download(rsm_ctx* ctx, const rsm_pubmap* pm, float* prob_out /* nullable */,
+                        float* pass_out /* nullable */, float* hit_out /* nullable */,
+                        uint8_t* occupied_out /* nullable */);
 /* 1 if the grid is held as exact 2^-25 fixed point (integer gather path), 0 if as float32. */
 int rsm_grid_is_fixed_point(const rsm_grid* grid);
 int rsm_world_to_map(const rsm_grid* grid, const double pose_world[3], double pose_map[3]);

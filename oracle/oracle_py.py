@@ -239,6 +239,12 @@ class Ref:
         L.ref_match_chain.argtypes = [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
         L.ref_blur_kernel.restype = c_i
         L.ref_blur_kernel.argtypes = [c_d, c_d, c_p, c_i]
+        L.ref_pubmap_create_frontend.restype = c_p
+        L.ref_pubmap_create_frontend.argtypes = [c_d, c_i, c_i, c_d, c_d, c_d]
+        L.ref_pubmap_set_factors.argtypes = [c_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+        L.ref_pubmap_update_geom.restype = c_i
+        L.ref_pubmap_update_geom.argtypes = [c_p, c_i, c_p, c_p, c_p]
+        L.ref_pubmap_read_all.argtypes = [c_p, c_p, c_p, c_p, c_p]
         L.ref_frontend_map_create.restype = c_p
         L.ref_frontend_map_create.argtypes = [c_d, c_i, c_i, c_d, c_d, c_d, ctypes.c_float, c_d, c_d]
         L.ref_frontend_map_update.restype = c_i
@@ -287,6 +293,27 @@ class Ref:
                                          org.ctypes.data if org is not None else None, int(check_point_num),
                                          float(bound_tolerance), float(penalty_gain), 1 if use_blur else 0,
                                          1 if use_logistic else 0)
+
+    # ---- publishing map as the front end keeps it -----------------------------------------------------
+    def pubmap_create_frontend(self, g, extend_factor=0.2):
+        return self.L.ref_pubmap_create_frontend(g.res, g.size_x, g.size_y, g.off_x, g.off_y, float(extend_factor))
+
+    def pubmap_set_factors(self, m, free_factor, occu_factor, occu_threshold, min_pass_through):
+        self.L.ref_pubmap_set_factors(m, free_factor, occu_factor, occu_threshold, min_pass_through)
+
+    def pubmap_update_geom(self, m, pts_cells, pose_world):
+        pts, pose = _f64(pts_cells), _f64(pose_world)
+        geom = np.zeros(4)
+        ok = self.L.ref_pubmap_update_geom(m, len(pts), pts.ctypes.data, pose.ctypes.data, geom.ctypes.data)
+        return bool(ok), (int(geom[0]), int(geom[1]), float(geom[2]), float(geom[3]))
+
+    def pubmap_read_all(self, m, size_x, size_y):
+        n = size_x * size_y
+        val, cnt, hit = (np.zeros(n, dtype=np.float32) for _ in range(3))
+        occ = np.zeros(n, dtype=np.uint8)
+        self.L.ref_pubmap_read_all(m, val.ctypes.data, cnt.ctypes.data, hit.ctypes.data, occ.ctypes.data)
+        shape = (size_y, size_x)
+        return val.reshape(shape), cnt.reshape(shape), hit.reshape(shape), occ.reshape(shape)
 
     # ---- front-end scan-match map (auto-resize, incremental UpdateMapByRange) ---------------------
     def frontend_map_create(self, g, extend_factor=0.2):

@@ -392,6 +392,48 @@ void ref_pubmap_read(void* m, float* value, float* pass_count, unsigned char* oc
   }
 }
 
+// The publishing map as the front end keeps it (slam_processor.cpp:477-483, 538-553): constructed, never Reset,
+// auto-resize on, ray-traced free space, CountCellFunctions knobs set before every update.
+void* ref_pubmap_create_frontend(double resolution, int size_x, int size_y, double off_x, double off_y, double extend_factor) {
+  auto* m = new std::shared_ptr<PubMap>(std::make_shared<PubMap>(resolution, Eigen::Vector2i(size_x, size_y),
+                                                                 Eigen::Vector2d(off_x, off_y)));
+  (*m)->set_extend_factor(extend_factor);
+  (*m)->set_use_auto_map_resize(true);
+  return m;
+}
+
+void ref_pubmap_set_factors(void* m, float free_factor, float occu_factor, float occu_threshold, float min_pass_through) {
+  auto& map = *static_cast<std::shared_ptr<PubMap>*>(m);
+  map->SetOccuThreshold(occu_threshold);
+  map->SetMinPassThrough(min_pass_through);
+  map->SetUpdateFreeFactor(free_factor);
+  map->SetUpdateOccupiedFactor(occu_factor);
+}
+
+// 1 = updated, 0 = extended instead (scan dropped).  geom_out = {size_x, size_y, map_offset_x, map_offset_y}.
+int ref_pubmap_update_geom(void* m, int n_pts, const double* pts, const double* pose_world, double* geom_out) {
+  auto& map = *static_cast<std::shared_ptr<PubMap>*>(m);
+  const bool ok = map->UpdateMapByRange(MakeScan(n_pts, pts, pose_world), false);
+  if (geom_out) {
+    geom_out[0] = map->GetSizeX(); geom_out[1] = map->GetSizeY();
+    geom_out[2] = map->map_offset_[0]; geom_out[3] = map->map_offset_[1];
+  }
+  return ok ? 1 : 0;
+}
+
+// Per cell: value, pass count, hit count and the map's own GetGridStates == Occupied (with the knobs set above).
+void ref_pubmap_read_all(void* m, float* value, float* pass_count, float* hit_count, unsigned char* occupied) {
+  auto& map = *static_cast<std::shared_ptr<PubMap>*>(m);
+  const int n = map->GetGridCellNum();
+  for (int i = 0; i < n; ++i) {
+    auto& c = map->GetCell(i);
+    if (value) value[i] = c.GetValue();
+    if (pass_count) pass_count[i] = c.pass_count_;
+    if (hit_count) hit_count[i] = c.hit_count_;
+    if (occupied) occupied[i] = map->GetGridStates(i) == GridStates_Occupied ? 1 : 0;
+  }
+}
+
 // origin: RangeDataContainer::sensor_origin() (NULL = (0,0)).  use_logistic re-states the one line of
 // SlamProcessor::MapCheckPenalize (slam/slam_processor.cpp:589-591; that file needs ROS and cannot be
 // compiled here) on top of the reference's own MapFeedbackResponsePenalty.

@@ -70,6 +70,17 @@ struct rsm_scan_store {
   size_t chunk_used = 0, chunk_cap = 0;
 };
 
+// Device-resident publishing map: OccuGridMap<CountCell> (map/slam_map.h:35) as three float planes + the update index.
+struct rsm_pubmap {
+  rsm_grid g;                      // geometry + the occupancy mask the map check reads (g.d_occ); no lookup cells
+  float* d_hit = nullptr;
+  float* d_pass = nullptr;
+  float* d_prob = nullptr;
+  int* d_mark = nullptr;
+  float default_prob = 0.5f;
+  int cur_update_index = 0;        // occu_grid_map.h:207, advanced by 3 per update
+};
+
 namespace {
 
 struct Buf {
@@ -1696,6 +1707,166 @@ int rsm_grid_geometry(const rsm_grid* grid, int* size_x, int* size_y, double* of
   if (offset_x) *offset_x = grid->off_x;
   if (offset_y) *offset_y = grid->off_y;
   return RSM_OK;
+}
+
+// ---- publishing map on the device (second half) -------------------------------------
+}  // extern "C"
+namespace {
+int pubmap_alloc(rsm_ctx* ctx, int sx, int sy, float default_prob, float** hit, float** pass, float** prob, int** mark) {
+  const size_t n = size_t(sx) * sy;
+  *hit = *pass = *prob = nullptr; *mark = nullptr;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(hit), n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(pass), n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(prob), n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(mark), n * 4);
+  // CountCell::ResetGridCell: prob = val, pass = hit = 0, update_index = -1 (grid_map_cell.h:64-69)
+  if (e == cudaSuccess) e = cudaMemsetAsync(*hit, 0, n * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(*pass, 0, n * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(*mark, 0xff, n * 4, ctx->stream);
+  if (e == cudaSuccess) e = launch_fill_f32(ctx->stream, *prob, (long long)n, default_prob);
+  if (e != cudaSuccess) {
+    cudaFree(*hit); cudaFree(*pass); cudaFree(*prob); cudaFree(*mark);
+    return fail(ctx, RSM_ERR_CUDA, "publishing map allocation failed: %s", cudaGetErrorString(e));
+  }
+  return RSM_OK;
+}
+}  // namespace
+extern "C" {
+
+int rsm_pubmap_create(rsm_ctx* ctx, int size_x, int size_y, double resolution, double offset_x, double offset_y,
+                      float default_prob, rsm_pubmap** out) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !out || size_x <= 0 || size_y <= 0 || size_x > 32768 || size_y > 32768 || !(resolution > 0))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_create: bad arguments");
+  rsm_pubmap* pm = new rsm_pubmap;
+  pm->default_prob = default_prob;
+  rsm_grid& g = pm->g;
+  g.size_x = size_x; g.size_y = size_y; g.pitch = size_x;
+  g.resolution = resolution; g.scale = 1.0 / resolution;      // map/grid_map_base.h:50
+  g.off_x = offset_x; g.off_y = offset_y;
+  g.tf.set(g.scale, offset_x, offset_y);
+  g.owned = false; g.d_cells = nullptr; g.init = false;
+  int rc = pubmap_alloc(ctx, size_x, size_y, default_prob, &pm->d_hit, &pm->d_pass, &pm->d_prob, &pm->d_mark);
+  if (rc == RSM_OK && cudaMalloc(reinterpret_cast<void**>(&g.d_occ), size_t(size_x) * size_y) != cudaSuccess)
+    rc = fail(ctx, RSM_ERR_CUDA, "cudaMalloc(occupancy) failed");
+  if (rc == RSM_OK && cudaMemsetAsync(g.d_occ, 0, size_t(size_x) * size_y, ctx->stream) != cudaSuccess) rc = RSM_ERR_CUDA;
+  if (rc == RSM_OK) rc = sync_stream(ctx);
+  if (rc) { delete pm; return rc; }
+  *out = pm;
+  return RSM_OK;
+}
+
+void rsm_pubmap_destroy(rsm_ctx* ctx, rsm_pubmap* pm) {
+  DeviceGuard device_guard(ctx);
+  if (!pm) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  cudaFree(pm->d_hit); cudaFree(pm->d_pass); cudaFree(pm->d_prob); cudaFree(pm->d_mark);
+  if (pm->g.d_occ) cudaFree(pm->g.d_occ);
+  delete pm;
+}
+
+const rsm_grid* rsm_pubmap_check_grid(const rsm_pubmap* pm) { return pm ? &pm->g : nullptr; }
+
+int rsm_pubmap_update_by_range(rsm_ctx* ctx, rsm_pubmap* pm, const double* pts_xy, int n_pts, const double pose_world[3],
+                               float update_free_factor, float update_occu_factor) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pm || n_pts < 0 || (n_pts > 0 && !pts_xy) || !pose_world)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_update_by_range: bad arguments");
+  rsm_grid& g = pm->g;
+  PubScan S;
+  std::memset(&S, 0, sizeof S);
+  double pmap[3];
+  g.tf.world_to_map(pose_world, pmap);                                       // occu_grid_map.h:278
+  const double c = std::cos(pmap[2]), s = std::sin(pmap[2]);                 // Rotation2Dd, host libm
+  S.c = c; S.s = s; S.tx = pmap[0]; S.ty = pmap[1];
+  S.start_x = static_cast<int>((pmap[0] + (c * 0.0 + (-s) * 0.0)) + 0.5);    // :303-305, sensor_origin = (0, 0)
+  S.start_y = static_cast<int>((pmap[1] + (s * 0.0 + c * 0.0)) + 0.5);
+  S.hit = pm->d_hit; S.pass = pm->d_pass; S.prob = pm->d_prob; S.mark = pm->d_mark;
+  S.n_pts = n_pts; S.size_x = g.size_x; S.size_y = g.size_y;
+  S.free_tag = pm->cur_update_index + 1; S.occ_tag = pm->cur_update_index + 2;   // :272-273
+  S.add_pass = 1.0f + update_free_factor; S.add_hit = 1.0f + update_occu_factor; // grid_map_cell.h:93-94
+  // cells the rays can touch: the hull of the start cell and the end cells (same arithmetic as the kernel)
+  int bx0 = S.start_x, bx1 = S.start_x, by0 = S.start_y, by1 = S.start_y;
+  for (int i = 0; i < n_pts; ++i) {
+    const double px = pts_xy[2 * i], py = pts_xy[2 * i + 1];
+    const int ex = static_cast<int>((S.tx + (c * px + (-s) * py)) + 0.5);
+    const int ey = static_cast<int>((S.ty + (s * px + c * py)) + 0.5);
+    bx0 = std::min(bx0, ex); bx1 = std::max(bx1, ex); by0 = std::min(by0, ey); by1 = std::max(by1, ey);
+  }
+  S.bx0 = std::max(bx0, 0); S.by0 = std::max(by0, 0); S.bx1 = std::min(bx1, g.size_x - 1); S.by1 = std::min(by1, g.size_y - 1);
+  pm->cur_update_index += 3;                                                 // :326
+  g.init = true;                                                             // SetUpdated()
+  if (n_pts == 0 || S.bx1 < S.bx0 || S.by1 < S.by0) return RSM_OK;
+  double* d_pts = nullptr;
+  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
+  if (rc) return rc;
+  S.pts = d_pts;
+  rc = ensure_dev(ctx, ctx->d_work, sizeof S);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, sizeof S);
+  if (rc) return rc;
+  std::memcpy(ctx->h_up.p, &S, sizeof S);
+  CU(cudaMemcpyAsync(ctx->d_work.p, ctx->h_up.p, sizeof S, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pub_update(ctx->stream, reinterpret_cast<const PubScan*>(ctx->d_work.p)));
+  ctx->stats.kernel_launches += 2; ctx->stats.h2d_bytes += sizeof S;
+  return sync_stream(ctx);
+}
+
+int rsm_pubmap_extend(rsm_ctx* ctx, rsm_pubmap* pm, int new_size_x, int new_size_y, int pre_grid_offset_x, int pre_grid_offset_y,
+                      double new_offset_x, double new_offset_y) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pm) return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_extend: null argument");
+  rsm_grid& g = pm->g;
+  if (new_size_x <= 0 || new_size_y <= 0 || new_size_x > 32768 || new_size_y > 32768 || pre_grid_offset_x < 0 || pre_grid_offset_y < 0 ||
+      pre_grid_offset_x + g.size_x > new_size_x || pre_grid_offset_y + g.size_y > new_size_y)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_extend: the old map must fit inside the new one");
+  float *hit, *pass, *prob; int* mark;
+  int rc = pubmap_alloc(ctx, new_size_x, new_size_y, pm->default_prob, &hit, &pass, &prob, &mark);   // grid_map_base.h:226
+  if (rc) return rc;
+  unsigned char* occ = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&occ), size_t(new_size_x) * new_size_y) != cudaSuccess) {
+    cudaFree(hit); cudaFree(pass); cudaFree(prob); cudaFree(mark);
+    return fail(ctx, RSM_ERR_CUDA, "cudaMalloc(occupancy) failed");
+  }
+  const size_t at = size_t(pre_grid_offset_y) * new_size_x + pre_grid_offset_x;
+  const size_t np = size_t(new_size_x) * 4, op = size_t(g.size_x) * 4;
+  cudaError_t e = cudaMemcpy2DAsync(hit + at, np, pm->d_hit, op, op, g.size_y, cudaMemcpyDeviceToDevice, ctx->stream);   // :228-232
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(pass + at, np, pm->d_pass, op, op, g.size_y, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(prob + at, np, pm->d_prob, op, op, g.size_y, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(mark + at, np, pm->d_mark, op, op, g.size_y, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(occ, 0, size_t(new_size_x) * new_size_y, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(hit); cudaFree(pass); cudaFree(prob); cudaFree(mark); cudaFree(occ);
+    return fail(ctx, RSM_ERR_CUDA, "rsm_pubmap_extend failed: %s", cudaGetErrorString(e));
+  }
+  cudaFree(pm->d_hit); cudaFree(pm->d_pass); cudaFree(pm->d_prob); cudaFree(pm->d_mark); cudaFree(g.d_occ);
+  pm->d_hit = hit; pm->d_pass = pass; pm->d_prob = prob; pm->d_mark = mark; g.d_occ = occ;
+  g.size_x = new_size_x; g.size_y = new_size_y; g.pitch = new_size_x;
+  g.off_x = new_offset_x; g.off_y = new_offset_y;
+  g.tf.set(g.scale, new_offset_x, new_offset_y);
+  pm->cur_update_index += 3;                                                 // occu_grid_map.h:296-299
+  return RSM_OK;
+}
+
+int rsm_pubmap_refresh_occupancy(rsm_ctx* ctx, rsm_pubmap* pm, float occu_threshold, float min_pass_through) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pm) return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_refresh_occupancy: null argument");
+  CU(launch_pub_occupancy(ctx->stream, pm->d_pass, pm->d_prob, (long long)pm->g.size_x * pm->g.size_y, occu_threshold,
+                          min_pass_through, pm->g.d_occ));
+  ctx->stats.kernel_launches++;
+  return sync_stream(ctx);
+}
+
+int rsm_pubmap_download(rsm_ctx* ctx, const rsm_pubmap* pm, float* prob_out, float* pass_out, float* hit_out, uint8_t* occupied_out) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pm) return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_download: null argument");
+  const size_t n = size_t(pm->g.size_x) * pm->g.size_y;
+  if (prob_out) CU(cudaMemcpyAsync(prob_out, pm->d_prob, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pass_out) CU(cudaMemcpyAsync(pass_out, pm->d_pass, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hit_out) CU(cudaMemcpyAsync(hit_out, pm->d_hit, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (occupied_out) CU(cudaMemcpyAsync(occupied_out, pm->g.d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_stream(ctx);
 }
 
 // ---- matching ----------------------------------------------------------------------------------

@@ -140,6 +140,20 @@ struct OptimizeJob {
   double* out;           // kOptSums sums in point order + the number of points inside the map
 };
 
+// One UpdateMapByRange of a publishing map (OccuGridMap<CountCell>): ray-traced free space + occupied end cells.
+struct PubScan {
+  float* hit; float* pass; float* prob;   // CountCell::hit_count_, pass_count_, prob_value_ planes (dense, size_x per row)
+  int* mark;                              // CountCell::update_index_
+  const double* pts;                      // scan points, cells of this map, sensor frame
+  int n_pts;
+  int size_x, size_y;
+  int start_x, start_y;                   // beam start cell
+  int free_tag, occ_tag;                  // cur_mark_free_index / cur_mark_occu_index of this update
+  int bx0, by0, bx1, by1;                 // cells the update can touch (inclusive), for the apply pass
+  float add_pass, add_hit;                // 1.0f + update_free_factor_, 1.0f + update_occu_factor_
+  double c, s, tx, ty;                    // pose in map cells: cos / sin from the host libm
+};
+
 }  // namespace rsm
 
 #endif

@@ -680,4 +680,92 @@ cudaError_t launch_optimize(int n_jobs, cudaStream_t st, const OptimizeJob* jobs
   return cudaGetLastError();
 }
 
+// =================================================================================================
+// publishing map (OccuGridMap<CountCell>::UpdateMapByRange, map/occu_grid_map.h:258-329, 474-530)
+// =================================================================================================
+// Within one update every cell changes at most once per kind: SetCellFree acts only while update_index_ <
+// cur_mark_free_index, SetCellOccu only while update_index_ < cur_mark_occu_index, and an occupied cell's own ray
+// has marked it free first (the Bresenham walk ends on the end cell).  So a cell's fate depends only on whether
+// any ray passed it (free) and whether any ray ended on it (occupied), not on the beam order: pass 1 records
+// that with atomicMax on the update index exactly as the reference stores it; pass 2 applies the float updates
+// the reference would have made, in its order: free; or free, un-free, occupied.
+__global__ void __launch_bounds__(128) pub_mark_kernel(const PubScan* __restrict__ scan) {
+  const PubScan S = *scan;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n_pts; i += gridDim.x * blockDim.x) {
+  const double px = S.pts[2 * i], py = S.pts[2 * i + 1];
+  const int ex = __double2int_rz(dadd(dadd(S.tx, dadd(dmul(S.c, px), dmul(-S.s, py))), 0.5));   // :301-310
+  const int ey = __double2int_rz(dadd(dadd(S.ty, dadd(dmul(S.s, px), dmul(S.c, py))), 0.5));
+  if (ex == S.start_x && ey == S.start_y) continue;                                                // :312
+  // LineVisitor::ErgodLineBresenhami (:125-187)
+  int x0 = S.start_x, y0 = S.start_y, x1 = ex, y1 = ey;
+  const bool steep = abs(y1 - y0) > abs(x1 - x0);
+  if (steep) { int t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
+  if (x0 > x1) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+  const int delta_x = x1 - x0, delta_y = abs(y1 - y0), y_step = y0 < y1 ? 1 : -1;
+  int error = 0, y = y0;
+  for (int x = x0; x <= x1; ++x) {
+    const int qx = steep ? y : x, qy = steep ? x : y;
+    error += delta_y;
+    if (2 * error >= delta_x) { y += y_step; error -= delta_x; }
+    // CellUpdate: PointInMap(x, y, half_kernel_size_ + 1) with half_kernel_size_ = 0 (:476, grid_map_base.h:339-346)
+    if (qx > 1 && qx < S.size_x - 1 && qy > 1 && qy < S.size_y - 1) atomicMax(S.mark + (size_t)qy * S.size_x + qx, S.free_tag);
+  }
+  if (ex > 1 && ex < S.size_x - 1 && ey > 1 && ey < S.size_y - 1) atomicMax(S.mark + (size_t)ey * S.size_x + ex, S.occ_tag);
+  }
+}
+
+__global__ void __launch_bounds__(256) pub_apply_kernel(const PubScan* __restrict__ scan) {
+  const PubScan S = *scan;
+  const int w = S.bx1 - S.bx0 + 1, h = S.by1 - S.by0 + 1;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (long long)w * h; k += (long long)gridDim.x * blockDim.x) {
+    const int x = S.bx0 + (int)(k % w), y = S.by0 + (int)(k / w);
+    const size_t c = (size_t)y * S.size_x + x;
+    const int m = S.mark[c];
+    if (m == S.free_tag) {                              // CountCellFunctions::UpdateSetFree (grid_map_cell.h:100-103)
+      const float pass = __fadd_rn(S.pass[c], S.add_pass);
+      S.pass[c] = pass;
+      S.prob[c] = __fdiv_rn(S.hit[c], pass);
+    } else if (m == S.occ_tag) {                        // UpdateSetFree, UpdateUnsetFree, UpdateSetOccupied (:92-108)
+      float pass = __fadd_rn(S.pass[c], S.add_pass);
+      pass = __fsub_rn(pass, S.add_pass);
+      const float hit = __fadd_rn(S.hit[c], S.add_hit);
+      pass = __fadd_rn(pass, S.add_pass);
+      float prob = __fdiv_rn(hit, pass);
+      if (prob > 1.0f) prob = 1.0f;
+      S.hit[c] = hit; S.pass[c] = pass; S.prob[c] = prob;
+    }
+  }
+}
+
+cudaError_t launch_pub_update(cudaStream_t st, const PubScan* scan_dev_and_host_copy) {
+  // the caller passes the device copy; grid sizes are fixed upper bounds (the kernels read n_pts / the box themselves)
+  pub_mark_kernel<<<64, 128, 0, st>>>(scan_dev_and_host_copy);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  pub_apply_kernel<<<296, 256, 0, st>>>(scan_dev_and_host_copy);
+  return cudaGetLastError();
+}
+
+// CountCellFunctions::GetGridStates == GridStates_Occupied (grid_map_cell.h:125-136): what the map check reads
+__global__ void __launch_bounds__(256)
+pub_occupancy_kernel(const float* __restrict__ pass, const float* __restrict__ prob, long long n, float thr, float min_pass,
+                     unsigned char* __restrict__ occ) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    occ[i] = (pass[i] >= min_pass && !(prob[i] < thr)) ? 1 : 0;
+}
+
+cudaError_t launch_pub_occupancy(cudaStream_t st, const float* pass, const float* prob, long long n_cells, float occu_threshold,
+                                 float min_pass_through, unsigned char* occ) {
+  pub_occupancy_kernel<<<296, 256, 0, st>>>(pass, prob, n_cells, occu_threshold, min_pass_through, occ);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_f32(cudaStream_t st, float* p, long long n, float v) {
+  fill_f32_kernel<<<296, 256, 0, st>>>(p, n, v);
+  return cudaGetLastError();
+}
+
 }  // namespace rsm

@@ -98,6 +98,13 @@ ABI = {
     "rsm_grid_upload_f32": (c_i, [c_p, c_p, c_p]),
     "rsm_grid_rasterize": (c_i, [c_p, c_p, ctypes.c_float, c_d, c_d, c_i, c_i, c_p, c_p, c_p]),
     "rsm_grid_download_f32": (c_i, [c_p, c_p, c_p]),
+    "rsm_pubmap_create": (c_i, [c_p, c_i, c_i, c_d, c_d, c_d, ctypes.c_float, ctypes.POINTER(c_p)]),
+    "rsm_pubmap_destroy": (None, [c_p, c_p]),
+    "rsm_pubmap_update_by_range": (c_i, [c_p, c_p, c_p, c_i, c_p, ctypes.c_float, ctypes.c_float]),
+    "rsm_pubmap_extend": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d]),
+    "rsm_pubmap_refresh_occupancy": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
+    "rsm_pubmap_check_grid": (c_p, [c_p]),
+    "rsm_pubmap_download": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "rsm_grid_fill": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
     "rsm_grid_update_by_range": (c_i, [c_p, c_p, c_d, c_d, c_i, c_p, c_i, c_p]),
     "rsm_grid_extend": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, ctypes.c_float, ctypes.c_float]),
@@ -397,6 +404,49 @@ class ScanMatchMap:
         m, out = _f64(pose_map), np.zeros(3)
         self.ctx.check(self.ctx.lib.rsm_map_to_world(self.h, m.ctypes.data, out.ctypes.data))
         return out
+
+
+class PubMap(ScanMatchMap):
+    """Device-resident publishing map (OccuGridMap<CountCell>, slam_map.h:35).  Inherits the map-check call:
+    self.h is the map's check grid, whose occupancy mask refresh_occupancy() computes on the device."""
+
+    def __init__(self, ctx, resolution, size_x, size_y, offset_x, offset_y, default_prob=0.5):
+        self.ctx = ctx
+        self.resolution, self.size_x, self.size_y = float(resolution), int(size_x), int(size_y)
+        pm = c_p()
+        ctx.check(ctx.lib.rsm_pubmap_create(ctx.h, self.size_x, self.size_y, self.resolution, float(offset_x), float(offset_y),
+                                            float(default_prob), ctypes.byref(pm)))
+        self.pm = pm
+        self.h = c_p(ctx.lib.rsm_pubmap_check_grid(pm))
+
+    def close(self):
+        if getattr(self, "pm", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.rsm_pubmap_destroy(self.ctx.h, self.pm)
+        self.pm = None
+        self.h = None
+
+    def UpdateMapByRange(self, pts_cells, sensor_pose, update_free_factor=0.0, update_occu_factor=0.0):
+        pts = _f64(np.asarray(pts_cells).reshape(-1, 2))
+        pose = _f64(sensor_pose)
+        self.ctx.check(self.ctx.lib.rsm_pubmap_update_by_range(self.ctx.h, self.pm, pts.ctypes.data, len(pts), pose.ctypes.data,
+                                                               float(update_free_factor), float(update_occu_factor)))
+
+    def ExtendSize(self, new_size_x, new_size_y, pre_grid_offset, new_map_offset):
+        self.ctx.check(self.ctx.lib.rsm_pubmap_extend(self.ctx.h, self.pm, int(new_size_x), int(new_size_y), int(pre_grid_offset[0]),
+                                                      int(pre_grid_offset[1]), float(new_map_offset[0]), float(new_map_offset[1])))
+        self.size_x, self.size_y = int(new_size_x), int(new_size_y)
+        self.h = c_p(self.ctx.lib.rsm_pubmap_check_grid(self.pm))
+
+    def refresh_occupancy(self, occu_threshold=0.5, min_pass_through=2.0):
+        self.ctx.check(self.ctx.lib.rsm_pubmap_refresh_occupancy(self.ctx.h, self.pm, float(occu_threshold), float(min_pass_through)))
+
+    def download_all(self):
+        shape = (self.size_y, self.size_x)
+        prob, cnt, hit = (np.zeros(shape, dtype=np.float32) for _ in range(3))
+        occ = np.zeros(shape, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.rsm_pubmap_download(self.ctx.h, self.pm, prob.ctypes.data, cnt.ctypes.data, hit.ctypes.data,
+                                                        occ.ctypes.data))
+        return prob, cnt, hit, occ
 
 
 class BasedCorrelationScanMatch:

@@ -16,7 +16,7 @@ def sha(a):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("maps_", "mapcheck_", "optimize_", "frontend_")))
+                  if not os.path.basename(p).startswith(("maps_", "mapcheck_", "optimize_", "frontend_", "pubmap_")))
 
 
 def mapcheck_names():

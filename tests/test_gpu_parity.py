@@ -809,3 +809,51 @@ def test_frontend_map_stays_on_device(ctx):
     r = m.ScanMatch(dg, pts[-1], synth.chain_yaml()[0], pose, cov)
     assert r > 0.6 and np.hypot(*(pose[:2] - poses[-1][:2])) < 0.06
     dg.close()
+
+
+def test_publishing_map_on_device(ctx):
+    """PubMap (CountCell: hit / pass / value per cell) updated on the device with ray-traced free space across
+    the 44-scan trajectory, with the knobs SlamProcessor::UpdateMap sets, against the reference's own cells after
+    every step (fixture); then the occupancy it yields feeds the map check without any upload and reproduces
+    the reference's MapCheckPenalize coefficients."""
+    import hashlib
+    import importlib.util
+    import os
+    here = os.path.dirname(__file__)
+    mods = {}
+    import sys
+    sys.path.insert(0, os.path.join(here, "golden"))
+    try:
+        for name in ("make_frontend", "make_pubmap"):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(here, "golden", name + ".py"))
+            mods[name] = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mods[name])          # pure helpers only (trajectory, scans, spec, factors)
+    finally:
+        sys.path.pop(0)
+    mf, mp = mods["make_frontend"], mods["make_pubmap"]
+    z = np.load(os.path.join(here, "golden", "pubmap_willow.npz"), allow_pickle=False)
+    g = mf.spec()
+    poses, pts = mf.trajectory(), mf.scans()
+    pm = matcher.PubMap(ctx, g.res, g.size_x, g.size_y, g.off_x, g.off_y)
+    scale = 1.0 / g.res
+    for k, (p, s) in enumerate(zip(poses, pts)):
+        sx, sy, ox, oy = (int(z["geom"][k][0]), int(z["geom"][k][1]), float(z["geom"][k][2]), float(z["geom"][k][3]))
+        f = mp.factors(k)
+        if bool(z["stamped"][k]):
+            pm.UpdateMapByRange(s, p, f[0], f[1])
+        else:
+            _, _, oox, ooy = pm.geometry()
+            pm.ExtendSize(sx, sy, (int(round((ox - oox) * scale)), int(round((oy - ooy) * scale))), (ox, oy))
+        assert pm.geometry() == (sx, sy, ox, oy)
+        val, cnt, hit, _ = pm.download_all()
+        h = hashlib.sha256()
+        for a in (val, cnt, hit):
+            h.update(a.tobytes())
+        assert h.hexdigest() == str(z["shas"][k]), "step %d" % k
+    pm.refresh_occupancy(float(z["knobs"][0]), float(z["knobs"][1]))
+    occ = pm.download_all()[3]
+    want_occ = np.unpackbits(z["occ_packed"])[: occ.size].reshape(occ.shape)
+    assert np.array_equal(occ, want_occ) and occ.sum() > 1000
+    got = pm.MapCheckPenalize(pts[-1], z["check_poses"], 100, 2.5, 0.015, True)
+    assert np.array_equal(got, z["coeff"]) and len(np.unique(got)) >= 10
+    pm.close()

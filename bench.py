@@ -469,6 +469,64 @@ def main():
         widened["optimize"] = entry
         for dg_ in grids_o:
             dg_.close()
+        # (3) front-end map maintenance: one accepted scan into the fine scan-match map (0.01 m, 2400^2, 5x5 stamps)
+        #     and into the publishing map (0.05 m, ray-traced free space), maps resident on the device
+        occ_w = synth.load_map("willow")
+        tr = [np.array([14.375 + 0.05 * k, 28.625 + 0.02 * k, 0.3 + 0.01 * k]) for k in range(24)]
+        scans_m = [synth.raycast(occ_w, p_[0], p_[1], p_[2], 1081, np.deg2rad(270.25), 10.0) for p_ in tr]
+        gfine = synth.backend_grid(0.01, 0.03, 10.0, tr[0][:2])
+        gpubm = synth.backend_grid(0.05, 0.15, 10.0, tr[0][:2])
+        fine = matcher.ScanMatchMap.from_spec(ctx, gfine)
+        fine.fill(0.5, 0.3)
+        pubm = matcher.PubMap(ctx, gpubm.res, gpubm.size_x, gpubm.size_y, gpubm.off_x, gpubm.off_y)
+        fine_pts = [s_ * (1 / 0.01) for s_ in scans_m]
+        pub_pts = [s_ * (1 / 0.05) for s_ in scans_m]
+        for k in range(4):
+            fine.UpdateMapByRange(fine_pts[k], tr[k], gfine.sigma, gfine.occu_offset, True)
+            pubm.UpdateMapByRange(pub_pts[k], tr[k], 0.0, 0.0)
+        t0 = time.perf_counter()
+        for k in range(4, 24):
+            fine.UpdateMapByRange(fine_pts[k], tr[k], gfine.sigma, gfine.occu_offset, True)
+            pubm.UpdateMapByRange(pub_pts[k], tr[k], 0.0, 0.0)
+        pubm.refresh_occupancy(0.2, 4.0)
+        dt = (time.perf_counter() - t0) / 20
+        host_copy = fine.download()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fine.upload(host_copy)
+        dtu = (time.perf_counter() - t0) / 3
+        entry = {"workload": "per accepted scan (1081 beams): UpdateMapByRange on the fine scan-match map (0.01 m, 2400^2, blur) "
+                             "and on the publishing map (0.05 m, 480^2, ray-traced free space), both resident on the device",
+                 "scans_per_s": 1.0 / dt, "ms_per_scan": dt * 1e3,
+                 "whole_map_upload_ms": dtu * 1e3,
+                 "note": "whole_map_upload_ms is what an adapter that keeps the maps on the host pays per scan instead (rsm_grid_upload_f32 of the fine map)",
+                 "timing": "host wall clock, host scan in"}
+        if args.cpu_reps > 0:
+            from oracle.oracle_py import Ref, ref_available
+            if ref_available():
+                R_ = Ref()
+                mfine = R_.frontend_map_create(gfine, 0.2)
+                mpub = R_.pubmap_create_frontend(gpubm, 0.2)
+                R_.pubmap_set_factors(mpub, 0.0, 0.0, 0.2, 4.0)
+                for k in range(4):
+                    R_.frontend_map_update(mfine, fine_pts[k], tr[k], True)
+                    R_.pubmap_update_geom(mpub, pub_pts[k], tr[k])
+                t0 = time.perf_counter()
+                for k in range(4, 24):
+                    R_.frontend_map_update(mfine, fine_pts[k], tr[k], True)
+                    R_.pubmap_update_geom(mpub, pub_pts[k], tr[k])
+                dtc = (time.perf_counter() - t0) / 20
+                same_fine = bool(np.array_equal(R_.read_map_sized(mfine, gfine.size_x, gfine.size_y), host_copy))
+                val_r = R_.pubmap_read_all(mpub, gpubm.size_x, gpubm.size_y)[0]
+                same_pub = bool(np.array_equal(val_r, pubm.download_all()[0]))
+                entry["cpu_baseline"] = {"value": 1.0 / dtc, "unit": "scans/s", "cores": 1, "kind": "reference",
+                                         "sample": "the same 20 scans through the reference's own OccuGridMap::UpdateMapByRange (both maps)"}
+                entry["equals_cpu"] = same_fine and same_pub
+                R_.destroy_map(mfine)
+                R_.pubmap_destroy(mpub)
+        widened["frontend_update"] = entry
+        fine.close()
+        pubm.close()
     # ---- wide relocalisation extra (config 5): ONE window angle-sliced over the ranks -----------
     wide = None
     if not args.no_wide:

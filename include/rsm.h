@@ -345,6 +345,17 @@ int rsm_match_chain_opt(rsm_ctx* ctx, const rsm_grid* coarse_grid, const double*
                         double optimize_failed_cost, int use_fine, double pose_world[3], double cov[9],
                         double* score, double responses[4] /* nullable */);
 
+/* ---- map rebuilds from the scan store ---------------------------------------------------------
+ * SlamProcessor::CorrectPoseAndMap (slam/slam_processor.cpp:329-371) rebuilds all three maps from every
+ * stored scan at its corrected pose after a loop closure: InitMapWithRangeVec = Reset + one
+ * UpdateMapByRange per scan (map/occu_grid_map.h:222-255).  With the scans in a store these are one call
+ * each, ids in the reference's order (the publishing map's list ends with map_min_passthrough extra copies
+ * of id 0, :351-354; its float counters accumulate in list order).  Map extents stay the caller's policy. */
+int rsm_grid_rebuild(rsm_ctx* ctx, rsm_grid* grid, const rsm_scan_store* store, int n, const int32_t* ids,
+                     float default_prob, double sigma, double occu_offset, int use_blur);
+int rsm_pubmap_rebuild(rsm_ctx* ctx, rsm_pubmap* pm, const rsm_scan_store* store, int n, const int32_t* ids,
+                       float update_free_factor, float update_occu_factor);
+
 /* ---- parity / multi-GPU building blocks --------------------------------------------------
  * rsm_pass_scores: penalised score of every candidate of one pass in candidate order
  * k = (angle_index*n_xy + x_index)*n_xy + y_index (the order of correlate_scan_matcher.h:552-584),

@@ -37,6 +37,8 @@
 #include "../../include/rsm.h"
 #include "rsm_device.h"
 #include "rsm_host.h"
+#include <climits>
+
 #include "rsm_kernels.h"
 
 using namespace rsm;
@@ -1767,13 +1769,12 @@ void rsm_pubmap_destroy(rsm_ctx* ctx, rsm_pubmap* pm) {
 
 const rsm_grid* rsm_pubmap_check_grid(const rsm_pubmap* pm) { return pm ? &pm->g : nullptr; }
 
-int rsm_pubmap_update_by_range(rsm_ctx* ctx, rsm_pubmap* pm, const double* pts_xy, int n_pts, const double pose_world[3],
-                               float update_free_factor, float update_occu_factor) {
-  DeviceGuard device_guard(ctx);
-  if (!ctx || !pm || n_pts < 0 || (n_pts > 0 && !pts_xy) || !pose_world)
-    return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_update_by_range: bad arguments");
+}  // extern "C"
+namespace {
+// descriptor of one UpdateMapByRange of a publishing map; advances the map's update index
+void make_pub_scan(rsm_pubmap* pm, const double* d_pts, int n_pts, const double* pose_world, float update_free_factor,
+                   float update_occu_factor, PubScan& S) {
   rsm_grid& g = pm->g;
-  PubScan S;
   std::memset(&S, 0, sizeof S);
   double pmap[3];
   g.tf.world_to_map(pose_world, pmap);                                       // occu_grid_map.h:278
@@ -1782,34 +1783,116 @@ int rsm_pubmap_update_by_range(rsm_ctx* ctx, rsm_pubmap* pm, const double* pts_x
   S.start_x = static_cast<int>((pmap[0] + (c * 0.0 + (-s) * 0.0)) + 0.5);    // :303-305, sensor_origin = (0, 0)
   S.start_y = static_cast<int>((pmap[1] + (s * 0.0 + c * 0.0)) + 0.5);
   S.hit = pm->d_hit; S.pass = pm->d_pass; S.prob = pm->d_prob; S.mark = pm->d_mark;
-  S.n_pts = n_pts; S.size_x = g.size_x; S.size_y = g.size_y;
+  S.pts = d_pts; S.n_pts = n_pts; S.size_x = g.size_x; S.size_y = g.size_y;
   S.free_tag = pm->cur_update_index + 1; S.occ_tag = pm->cur_update_index + 2;   // :272-273
   S.add_pass = 1.0f + update_free_factor; S.add_hit = 1.0f + update_occu_factor; // grid_map_cell.h:93-94
-  // cells the rays can touch: the hull of the start cell and the end cells (same arithmetic as the kernel)
-  int bx0 = S.start_x, bx1 = S.start_x, by0 = S.start_y, by1 = S.start_y;
-  for (int i = 0; i < n_pts; ++i) {
-    const double px = pts_xy[2 * i], py = pts_xy[2 * i + 1];
-    const int ex = static_cast<int>((S.tx + (c * px + (-s) * py)) + 0.5);
-    const int ey = static_cast<int>((S.ty + (s * px + c * py)) + 0.5);
-    bx0 = std::min(bx0, ex); bx1 = std::max(bx1, ex); by0 = std::min(by0, ey); by1 = std::max(by1, ey);
-  }
-  S.bx0 = std::max(bx0, 0); S.by0 = std::max(by0, 0); S.bx1 = std::min(bx1, g.size_x - 1); S.by1 = std::min(by1, g.size_y - 1);
+  S.bx0 = INT_MAX; S.by0 = INT_MAX; S.bx1 = -1; S.by1 = -1;                  // filled by the mark pass
   pm->cur_update_index += 3;                                                 // :326
   g.init = true;                                                             // SetUpdated()
-  if (n_pts == 0 || S.bx1 < S.bx0 || S.by1 < S.by0) return RSM_OK;
+}
+}  // namespace
+extern "C" {
+
+int rsm_pubmap_update_by_range(rsm_ctx* ctx, rsm_pubmap* pm, const double* pts_xy, int n_pts, const double pose_world[3],
+                               float update_free_factor, float update_occu_factor) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pm || n_pts < 0 || (n_pts > 0 && !pts_xy) || !pose_world)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_update_by_range: bad arguments");
   double* d_pts = nullptr;
-  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
-  if (rc) return rc;
-  S.pts = d_pts;
+  int rc = RSM_OK;
+  if (n_pts > 0) { rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts); if (rc) return rc; }
+  PubScan S;
+  make_pub_scan(pm, d_pts, n_pts, pose_world, update_free_factor, update_occu_factor, S);
+  if (n_pts == 0) return RSM_OK;
   rc = ensure_dev(ctx, ctx->d_work, sizeof S);
   if (rc) return rc;
   rc = ensure_pinned(ctx, ctx->h_up, sizeof S);
   if (rc) return rc;
   std::memcpy(ctx->h_up.p, &S, sizeof S);
   CU(cudaMemcpyAsync(ctx->d_work.p, ctx->h_up.p, sizeof S, cudaMemcpyHostToDevice, ctx->stream));
-  CU(launch_pub_update(ctx->stream, reinterpret_cast<const PubScan*>(ctx->d_work.p)));
+  CU(launch_pub_update(ctx->stream, reinterpret_cast<PubScan*>(ctx->d_work.p)));
   ctx->stats.kernel_launches += 2; ctx->stats.h2d_bytes += sizeof S;
   return sync_stream(ctx);
+}
+
+// ---- rebuilds from the scan store (SlamProcessor::CorrectPoseAndMap, slam/slam_processor.cpp:329-371) -------------
+int rsm_pubmap_rebuild(rsm_ctx* ctx, rsm_pubmap* pm, const rsm_scan_store* store, int n, const int32_t* ids,
+                       float update_free_factor, float update_occu_factor) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !pm || !store || n < 0 || (n > 0 && !ids)) return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_rebuild: bad arguments");
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || size_t(ids[i]) >= store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "rsm_pubmap_rebuild: unknown scan id %d", ids[i]);
+  rsm_grid& g = pm->g;
+  const size_t cells = size_t(g.size_x) * g.size_y;
+  // InitMapWithRangeVec: Reset() (every cell ResetGridCell(default)), indices restart (occu_grid_map.h:222-237)
+  CU(cudaMemsetAsync(pm->d_hit, 0, cells * 4, ctx->stream));
+  CU(cudaMemsetAsync(pm->d_pass, 0, cells * 4, ctx->stream));
+  CU(cudaMemsetAsync(pm->d_mark, 0xff, cells * 4, ctx->stream));
+  CU(launch_fill_f32(ctx->stream, pm->d_prob, (long long)cells, pm->default_prob));
+  pm->cur_update_index = 0;
+  g.init = false;
+  if (n == 0) return sync_stream(ctx);
+  int rc = ensure_dev(ctx, ctx->d_work, sizeof(PubScan) * size_t(n));
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, sizeof(PubScan) * size_t(n));
+  if (rc) return rc;
+  PubScan* hs = reinterpret_cast<PubScan*>(ctx->h_up.p);
+  for (int i = 0; i < n; ++i) {
+    const rsm_scan_store::Entry& E = store->scans[ids[i]];
+    make_pub_scan(pm, E.d_pts, E.n, E.pose, update_free_factor, update_occu_factor, hs[i]);
+  }
+  CU(cudaMemcpyAsync(ctx->d_work.p, hs, sizeof(PubScan) * size_t(n), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += sizeof(PubScan) * size_t(n);
+  // one update after the other on the stream: the float counters of a cell accumulate in scan order
+  for (int i = 0; i < n; ++i) {
+    if (hs[i].n_pts == 0) continue;
+    CU(launch_pub_update(ctx->stream, reinterpret_cast<PubScan*>(ctx->d_work.p) + i));
+    ctx->stats.kernel_launches += 2;
+  }
+  return sync_stream(ctx);
+}
+
+int rsm_grid_rebuild(rsm_ctx* ctx, rsm_grid* grid, const rsm_scan_store* store, int n, const int32_t* ids, float default_prob,
+                     double sigma, double occu_offset, int use_blur) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || !store || n < 0 || (n > 0 && !ids)) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_rebuild: bad arguments");
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || size_t(ids[i]) >= store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "rsm_grid_rebuild: unknown scan id %d", ids[i]);
+  RasterPlan pl;
+  int rc = plan_raster(ctx, default_prob, sigma, grid->resolution, occu_offset, use_blur, pl);
+  if (rc) return rc;
+  Layout dl;
+  const size_t o_fill = dl.take(sizeof(FillJob));
+  const size_t o_scans = dl.take(sizeof(RasterScan) * std::max(1, n));
+  const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t up_bytes = dl.off;
+  rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
+  if (rc) return rc;
+  char* up = ctx->h_up.p;
+  char* dw = ctx->d_work.p;
+  FillJob F; F.grid = grid->d_cells; F.n_cells = (long long)grid->pitch * grid->size_y; F.value = pl.fill;
+  std::memcpy(up + o_fill, &F, sizeof F);
+  RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
+  for (int i = 0; i < n; ++i) {
+    const rsm_scan_store::Entry& E = store->scans[ids[i]];
+    make_raster_scan(grid, E.pose, E.d_pts, E.n, hs[i]);
+  }
+  std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += up_bytes;
+  {
+    Prof p(ctx, KC_RASTER);
+    CU(launch_fill(1, 148, ctx->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
+    CU(launch_raster(n, ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scans), reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+  }
+  ctx->stats.kernel_launches += (n > 0) ? 2 : 1;
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  grid->fixed = pl.fixed;
+  if (n > 0) grid->init = true;
+  return RSM_OK;
 }
 
 int rsm_pubmap_extend(rsm_ctx* ctx, rsm_pubmap* pm, int new_size_x, int new_size_y, int pre_grid_offset_x, int pre_grid_offset_y,

@@ -149,7 +149,7 @@ struct PubScan {
   int size_x, size_y;
   int start_x, start_y;                   // beam start cell
   int free_tag, occ_tag;                  // cur_mark_free_index / cur_mark_occu_index of this update
-  int bx0, by0, bx1, by1;                 // cells the update can touch (inclusive), for the apply pass
+  int bx0, by0, bx1, by1;                 // cells the update can touch (inclusive): written by the mark pass, read by the apply pass
   float add_pass, add_hit;                // 1.0f + update_free_factor_, 1.0f + update_occu_factor_
   double c, s, tx, ty;                    // pose in map cells: cos / sin from the host libm
 };

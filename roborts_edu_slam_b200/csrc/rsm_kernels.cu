@@ -689,13 +689,15 @@ cudaError_t launch_optimize(int n_jobs, cudaStream_t st, const OptimizeJob* jobs
 // any ray passed it (free) and whether any ray ended on it (occupied), not on the beam order: pass 1 records
 // that with atomicMax on the update index exactly as the reference stores it; pass 2 applies the float updates
 // the reference would have made, in its order: free; or free, un-free, occupied.
-__global__ void __launch_bounds__(128) pub_mark_kernel(const PubScan* __restrict__ scan) {
+__global__ void __launch_bounds__(128) pub_mark_kernel(PubScan* __restrict__ scan) {
   const PubScan S = *scan;
+  int bx0 = S.start_x, bx1 = S.start_x, by0 = S.start_y, by1 = S.start_y;   // hull of the start cell and the end cells
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n_pts; i += gridDim.x * blockDim.x) {
   const double px = S.pts[2 * i], py = S.pts[2 * i + 1];
   const int ex = __double2int_rz(dadd(dadd(S.tx, dadd(dmul(S.c, px), dmul(-S.s, py))), 0.5));   // :301-310
   const int ey = __double2int_rz(dadd(dadd(S.ty, dadd(dmul(S.s, px), dmul(S.c, py))), 0.5));
   if (ex == S.start_x && ey == S.start_y) continue;                                                // :312
+  bx0 = min(bx0, ex); bx1 = max(bx1, ex); by0 = min(by0, ey); by1 = max(by1, ey);
   // LineVisitor::ErgodLineBresenhami (:125-187)
   int x0 = S.start_x, y0 = S.start_y, x1 = ex, y1 = ey;
   const bool steep = abs(y1 - y0) > abs(x1 - x0);
@@ -712,11 +714,19 @@ __global__ void __launch_bounds__(128) pub_mark_kernel(const PubScan* __restrict
   }
   if (ex > 1 && ex < S.size_x - 1 && ey > 1 && ey < S.size_y - 1) atomicMax(S.mark + (size_t)ey * S.size_x + ex, S.occ_tag);
   }
+  // the cells this update can have touched, for the apply pass (every ray stays inside the hull of its two ends)
+  bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
+  by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&scan->bx0, max(bx0, 0)); atomicMax(&scan->bx1, min(bx1, S.size_x - 1));
+    atomicMin(&scan->by0, max(by0, 0)); atomicMax(&scan->by1, min(by1, S.size_y - 1));
+  }
 }
 
 __global__ void __launch_bounds__(256) pub_apply_kernel(const PubScan* __restrict__ scan) {
   const PubScan S = *scan;
   const int w = S.bx1 - S.bx0 + 1, h = S.by1 - S.by0 + 1;
+  if (w <= 0 || h <= 0) return;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (long long)w * h; k += (long long)gridDim.x * blockDim.x) {
     const int x = S.bx0 + (int)(k % w), y = S.by0 + (int)(k / w);
     const size_t c = (size_t)y * S.size_x + x;
@@ -737,12 +747,13 @@ __global__ void __launch_bounds__(256) pub_apply_kernel(const PubScan* __restric
   }
 }
 
-cudaError_t launch_pub_update(cudaStream_t st, const PubScan* scan_dev_and_host_copy) {
-  // the caller passes the device copy; grid sizes are fixed upper bounds (the kernels read n_pts / the box themselves)
-  pub_mark_kernel<<<64, 128, 0, st>>>(scan_dev_and_host_copy);
+cudaError_t launch_pub_update(cudaStream_t st, PubScan* scan) {
+  // `scan` is the device copy, its box initialised empty (bx0 = by0 = INT_MAX, bx1 = by1 = -1); the launch shapes
+  // are fixed upper bounds, the kernels stride over n_pts / the box themselves
+  pub_mark_kernel<<<16, 128, 0, st>>>(scan);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  pub_apply_kernel<<<296, 256, 0, st>>>(scan_dev_and_host_copy);
+  pub_apply_kernel<<<296, 256, 0, st>>>(scan);
   return cudaGetLastError();
 }
 

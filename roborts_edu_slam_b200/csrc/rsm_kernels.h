@@ -39,7 +39,7 @@ cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);
 cudaError_t launch_fill(int n_jobs, int ctas_per_job, cudaStream_t st, const FillJob* jobs);
 cudaError_t launch_penalty(int n_jobs, cudaStream_t st, const PenaltyJob* jobs, const unsigned char* occ, int size_x,
                            int size_y, double bound_tolerance);
-cudaError_t launch_pub_update(cudaStream_t st, const PubScan* scan);
+cudaError_t launch_pub_update(cudaStream_t st, PubScan* scan);
 cudaError_t launch_pub_occupancy(cudaStream_t st, const float* pass, const float* prob, long long n_cells, float occu_threshold,
                                  float min_pass_through, unsigned char* occ);
 cudaError_t launch_fill_f32(cudaStream_t st, float* p, long long n, float v);

@@ -105,6 +105,8 @@ ABI = {
     "rsm_pubmap_refresh_occupancy": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
     "rsm_pubmap_check_grid": (c_p, [c_p]),
     "rsm_pubmap_download": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p]),
+    "rsm_grid_rebuild": (c_i, [c_p, c_p, c_p, c_i, c_p, ctypes.c_float, c_d, c_d, c_i]),
+    "rsm_pubmap_rebuild": (c_i, [c_p, c_p, c_p, c_i, c_p, ctypes.c_float, ctypes.c_float]),
     "rsm_grid_fill": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
     "rsm_grid_update_by_range": (c_i, [c_p, c_p, c_d, c_d, c_i, c_p, c_i, c_p]),
     "rsm_grid_extend": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, ctypes.c_float, ctypes.c_float]),
@@ -331,6 +333,12 @@ class ScanMatchMap:
                                                        float(occu_offset), int(use_blur), len(base_pts),
                                                        n_pts.ctypes.data, pts.ctypes.data, poses.ctypes.data))
 
+    def InitMapWithStore(self, store, ids, default_prob=0.3, sigma=0.15, occu_offset=0.88, use_blur=True):
+        """InitMapWithRangeVec over scans of a device scan store (CorrectPoseAndMap's rebuild of a scan-match map)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rsm_grid_rebuild(self.ctx.h, self.h, store.h, len(ids), ids.ctypes.data, float(default_prob),
+                                                     float(sigma), float(occu_offset), int(use_blur)))
+
     # ---- front-end maintenance: the map stays on the device between scans ----------------------------
     def fill(self, fill_prob=0.5, first_cell_prob=0.3):
         """A freshly constructed map: cell 0 = default_prob, the others kDefaultCellProb (grid_map_base.h:150-163)."""
@@ -436,6 +444,12 @@ class PubMap(ScanMatchMap):
                                                       int(pre_grid_offset[1]), float(new_map_offset[0]), float(new_map_offset[1])))
         self.size_x, self.size_y = int(new_size_x), int(new_size_y)
         self.h = c_p(self.ctx.lib.rsm_pubmap_check_grid(self.pm))
+
+    def InitMapWithRangeVec(self, store, ids, update_free_factor=0.0, update_occu_factor=0.0):
+        """Reset + one update per stored scan, in list order (CorrectPoseAndMap's rebuild)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rsm_pubmap_rebuild(self.ctx.h, self.pm, store.h, len(ids), ids.ctypes.data,
+                                                       float(update_free_factor), float(update_occu_factor)))
 
     def refresh_occupancy(self, occu_threshold=0.5, min_pass_through=2.0):
         self.ctx.check(self.ctx.lib.rsm_pubmap_refresh_occupancy(self.ctx.h, self.pm, float(occu_threshold), float(min_pass_through)))

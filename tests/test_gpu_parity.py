@@ -857,3 +857,34 @@ def test_publishing_map_on_device(ctx):
     got = pm.MapCheckPenalize(pts[-1], z["check_poses"], 100, 2.5, 0.015, True)
     assert np.array_equal(got, z["coeff"]) and len(np.unique(got)) >= 10
     pm.close()
+
+
+def test_map_rebuilds_from_the_scan_store(ctx, oracle, rng):
+    """CorrectPoseAndMap's rebuilds (slam_processor.cpp:329-371) from a device scan store: the scan-match map
+    against the oracle's InitMapWithRangeVec, the publishing map against the scan-by-scan device path (itself
+    pinned to the reference by test_publishing_map_on_device), after the pose graph moved every scan."""
+    sc = synth.config4(1)[0]
+    g = sc.grid
+    store = matcher.ScanStore(ctx)
+    ids = [store.AddRangeData(p, pose) for p, pose in zip(sc.base_pts, sc.base_poses)]
+    new_poses = sc.base_poses + rng.uniform(-0.05, 0.05, sc.base_poses.shape)
+    store.UpdateRangeData(ids, new_poses)
+    order = ids[::-1] + [ids[0]] * 3          # any order, repeats allowed (the reference appends id 0 min_passthrough times)
+    dg = matcher.ScanMatchMap.from_spec(ctx, g)
+    dg.InitMapWithStore(store, order, g.default_prob, g.sigma, g.occu_offset, True)
+    want = oracle.build_grid(g, [sc.base_pts[i] for i in order], new_poses[order])
+    assert np.array_equal(dg.download(), want)
+    dg.InitMapWithStore(store, [], g.default_prob, g.sigma, g.occu_offset, True)      # Reset only
+    assert (dg.download() == np.float32(g.default_prob)).all()
+    a = matcher.PubMap(ctx, g.res, g.size_x, g.size_y, g.off_x, g.off_y)
+    b = matcher.PubMap(ctx, g.res, g.size_x, g.size_y, g.off_x, g.off_y)
+    b.UpdateMapByRange(sc.scan_pts, sc.seed_pose, 4.0, 8.0)                            # stale content the rebuild must wipe
+    b.InitMapWithRangeVec(store, order, 0.3, 0.7)
+    for i in order:
+        a.UpdateMapByRange(sc.base_pts[i], new_poses[i], 0.3, 0.7)
+    for x, y in zip(a.download_all()[:3], b.download_all()[:3]):
+        assert np.array_equal(x, y)
+    assert a.download_all()[1].max() >= len(order) - 1
+    for m_ in (a, b, dg):
+        m_.close()
+    store.close()

@@ -397,6 +397,27 @@ def main():
             "store_equals_host_scans": bool(same),
             "timing": "host wall clock around the batched calls (host inputs -> host results), max over ranks",
         }
+        if world == 1 and args.cpu_reps > 0:
+            # the reference's own ScanMatchInterface step on one core: grid rebuild from the chain + coarse/fine/super chain
+            from oracle.oracle_py import Oracle, Ref, ref_available
+            n_cpu = 6
+            if ref_available():
+                R_ = Ref()
+                t0 = time.perf_counter()
+                for sc_ in pairs[:n_cpu]:
+                    m_ = R_.create_map(sc_.grid)
+                    R_.build_map(m_, sc_.grid, sc_.base_pts, sc_.base_poses)
+                    R_.match_chain(m_, sc_.scan_pts, sc_.passes, sc_.seed_pose)
+                    R_.destroy_map(m_)
+                dtc, kind_ = time.perf_counter() - t0, "reference"
+            else:
+                O_ = Oracle()
+                t0 = time.perf_counter()
+                for sc_ in pairs[:n_cpu]:
+                    O_.match_chain(O_.build_grid(sc_.grid, sc_.base_pts, sc_.base_poses), sc_.grid, sc_.scan_pts, sc_.passes, sc_.seed_pose)
+                dtc, kind_ = time.perf_counter() - t0, "port"
+            loop["cpu_baseline"] = {"value": n_cpu / dtc, "unit": "matches/s", "cores": 1, "kind": kind_,
+                                    "sample": "%d of the pairs: grid rebuild from the 8 base scans + coarse/fine/super chain each" % n_cpu}
         for st, *_ in stores:
             st.close()
         for c, _ in parts[1:]:

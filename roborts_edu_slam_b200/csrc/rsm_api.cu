@@ -605,9 +605,22 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
                                        std::fabs(g.x_of(g.n_xy)) < 8192.0 && std::fabs(g.y_of(g.n_xy)) < 8192.0))
       use_flat = false;
   }
+  // patch variant: batches of small unit-step windows on fixed-point grids (the back-end chain's coarse pass).
+  // Its CTAs are 8 angles x the whole window x every beam, four resident per SM: below one full wave of them
+  // (592) the tiled kernel's many small CTAs balance better (measured: 64-pair sub-batches lose 4 %, 256-pair
+  // batches gain 18 % of the coarse pass).  RSM_NO_PATCH=1 / RSM_FORCE_PATCH=1 override.
+  bool use_patch = !use_staged && !use_flat && cfg.affine && items[act[0]].geo.factor == 1.0 && std::getenv("RSM_NO_PATCH") == nullptr;
+  int patch_nxy = 0, patch_ctas = 0;
+  for (int a = 0; a < na && use_patch; ++a) {
+    const PassItem& it = items[act[a]];
+    if (!it.grid->fixed || (it.grid->pitch & 3) || it.geo.n_xy < 3 || it.geo.n_xy > 16) use_patch = false;
+    patch_nxy = std::max(patch_nxy, it.geo.n_xy);
+    patch_ctas += (it.a1 - it.a0 + score_patch_angles() - 1) / score_patch_angles();
+  }
+  if (use_patch && patch_ctas < 592 && std::getenv("RSM_FORCE_PATCH") == nullptr) use_patch = false;
   // immediate-offset variant: unit search step and the same padded pitch for every job
   int const_pitch = 0;
-  if (!use_staged && cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
+  if (!use_staged && !use_patch && cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
     const_pitch = items[act[0]].grid->pitch;
     if (const_pitch != kPitchSmall && const_pitch != kPitchLarge) const_pitch = 0;
     for (int a = 1; a < na && const_pitch; ++a) if (items[act[a]].grid->pitch != const_pitch) const_pitch = 0;
@@ -725,7 +738,9 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.half_size = it.param.search_space_size / 2;                     // :734
     J.gain = (it.param.type == RSM_COARSE) ? 0.4 : 0.2;               // :588-602, :759-761
     s_cta[a] = cta;
-    cta += use_flat ? score_flat_ctas(int(it.n_local)) : J.ang_count * J.tiles_x * J.tiles_y * (use_staged ? n_split : 1);
+    cta += use_flat ? score_flat_ctas(int(it.n_local))
+                    : use_patch ? (J.ang_count + score_patch_angles() - 1) / score_patch_angles()
+                                : J.ang_count * J.tiles_x * J.tiles_y * (use_staged ? n_split : 1);
     (it.grid->fixed ? any_fixed : any_float) = true;
     SelectJob& L = ljobs[a];
     std::memset(&L, 0, sizeof L);
@@ -807,6 +822,9 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       if (use_flat)
         CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                                reinterpret_cast<const int*>(dw + o_scta), na));
+      else if (use_patch)
+        CU(launch_score_patch(patch_nxy, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+                              reinterpret_cast<const int*>(dw + o_scta), na));
       else if (use_staged) {
         // the launches cover disjoint angles: the second one goes to a side stream so that its
         // clusters take SMs as soon as CTAs of the first retire (no kernel-boundary drain between them)
@@ -868,7 +886,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   //  batch enqueues its few long kernels well ahead of the GPU anyway)
   if (!ctx->profiling && na <= 8 && std::getenv("RSM_NO_GRAPH") == nullptr) {
     std::vector<long long> key = {(long long)(intptr_t)dw, (long long)(intptr_t)up, (long long)(intptr_t)dn, (long long)up_bytes,
-                                  (long long)o_best, (long long)zero_end, use_flat, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
+                                  (long long)o_best, (long long)zero_end, use_flat + 2 * (use_patch ? patch_nxy : 0), use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
                                   total_sel_cta, (long long)o_ljobs, (long long)o_lcta, (long long)o_pool, pool_cap,
                                   (long long)o_poolcnt, (long long)head_bytes, pool_first};

@@ -22,6 +22,10 @@ cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitc
 // Flat variant (small windows, non-integer step): one thread per candidate, 256 candidates per CTA.
 int score_flat_ctas(int n_local);
 cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
+// Patch variant (batches of small unit-step windows, fixed point): one CTA = score_patch_angles() consecutive search
+// angles of one job, the whole window (n_xy <= 16) per angle; grid cells reach shared memory as one box per 32 beams.
+int score_patch_angles();
+cudaError_t launch_score_patch(int n_xy, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 // Staged variant (shared-memory window filled by TMA bulk copies): fixed-point grid, unit search step.
 // A CTA covers score_staged_tile(variant) translations of one angle and 1/n_split of the beams; the
 // n_split CTAs of a tile are launched as one thread-block cluster and combine their sums through

@@ -326,6 +326,210 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
   }
 }
 
+// =================================================================================================
+// Patch kernel: small unit-step windows (<= 16 translations per axis) of a BATCH of matches, fixed point.
+// =================================================================================================
+// The back-end chain's coarse pass is 13 x 13 translations: in the tiled kernel a warp load covers two
+// 16-cell row segments (13 useful) that straddle L1 lines, ~9 evaluations per L1 cycle.  Here a CTA owns
+// kAngles consecutive search angles of one match, one warp per angle.  Per chunk of 32 beams lane b of warp a
+// computes the patch origin of (angle a, beam b) in FP64 (reference association, same provable index test as
+// above); the CTA takes the hull of the 256 origins, and if hull + patch fits the 112 x 96-cell tile the CTA copies
+// that rectangle from the grid into shared memory (16-byte loads), each cell then serving up to 256 patches.
+// A warp gathers its angle's window with NR shared-memory loads per beam: lanes 0-15 read row r, lanes 16-31
+// row r+1; the tile pitch of 112 = 16 (mod 32) puts the two half-warps into disjoint banks.  The origin of beam j
+// reaches the warp by shuffle.  Chunks whose hull does not fit (far beams, where eight angles fan out) gather
+// straight from global memory with the same origins; beams that fail the index test take exact per-thread indices.
+namespace patch {
+#ifdef RSM_STAGED_DEBUG
+__device__ unsigned long long g_pdbg[8];
+#define PDBG_ADD(i, v) atomicAdd(&g_pdbg[i], (unsigned long long)(v))
+#else
+#define PDBG_ADD(i, v)
+#endif
+constexpr int kAngles = 8;
+constexpr int kThreads = kAngles * 32;
+constexpr int kBoxW = 112, kBoxH = 96;   // capacity; only the hull of a chunk is copied
+constexpr int kPC = 32;
+
+template <int NR>
+__global__ void __launch_bounds__(kThreads, 4)
+score_patch_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ ScoreJob J;
+  __shared__ int s_job;
+  __shared__ __align__(16) int tile[kBoxW * kBoxH];
+  __shared__ int s_box[kAngles][4];
+  __shared__ unsigned long long s_wmax[kAngles];
+
+  if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + s_job);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < int(sizeof(ScoreJob) / 4); i += kThreads) dst[i] = __ldg(src + i);
+  }
+  const int first_cta = __ldg(cta_begin + s_job);
+  __syncthreads();
+
+  const int ia_local = (blockIdx.x - first_cta) * kAngles + warp;
+  const bool active = ia_local < J.ang_count;
+  const int ia = J.ang_begin + (active ? ia_local : J.ang_count - 1);
+  const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
+  const int V = J.V, n_xy = J.n_xy, pitch = J.pitch, size_x = J.size_x, size_y = J.size_y;
+  const int ixl = lane & 15, hp = lane >> 4;
+  const double x0 = dadd(J.sx, dmul(0.0, J.f)), y0 = dadd(J.sy, dmul(0.0, J.f));   // candidate (0, 0)   (:569, :572)
+  const double xc = dadd(J.sx, dmul((double)ixl, J.f));
+  const int* grid = reinterpret_cast<const int*>(J.grid);
+  const int nchunks = (V + kPC - 1) / kPC;
+
+  unsigned int a32[NR];
+  unsigned long long a64[NR];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) { a32[k] = 0u; a64[k] = 0ull; }
+  int err = 0;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int v = c * kPC + lane;
+    const bool vb = v < V;
+    double lx = 0.0, ly = 0.0;
+    int gx0 = 0, gy0 = 0;
+    bool ok = false;
+    if (vb) {
+      const int p = v * J.step;
+      const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+      lx = dsub(dmul(cs, px), dmul(sn, py));                      // :179-180
+      ly = dadd(dmul(sn, px), dmul(cs, py));
+      const double tx_ = dadd(dadd(lx, x0), 0.5), ty_ = dadd(dadd(ly, y0), 0.5);
+      gx0 = __double2int_rz(tx_); gy0 = __double2int_rz(ty_);
+      const double fx = tx_ - (double)gx0, fy = ty_ - (double)gy0;
+      ok = active && fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 &&
+           gx0 >= 0 && gx0 + 15 < size_x && gy0 >= 0 && gy0 + 2 * NR - 1 < size_y;
+    }
+    const int npc = min(kPC, V - c * kPC);
+    // One segment of the chunk's beams [j0, j1): hull of the origins, copy it if it fits the tile, gather.
+    auto segment = [&](int j0, int j1) {
+      const bool mine = ok && lane >= j0 && lane < j1;
+      {
+        const int xmin = __reduce_min_sync(0xffffffffu, mine ? gx0 : 0x7fffffff), xmax = __reduce_max_sync(0xffffffffu, mine ? gx0 : -1);
+        const int ymin = __reduce_min_sync(0xffffffffu, mine ? gy0 : 0x7fffffff), ymax = __reduce_max_sync(0xffffffffu, mine ? gy0 : -1);
+        if (lane == 0) { s_box[warp][0] = xmin; s_box[warp][1] = xmax; s_box[warp][2] = ymin; s_box[warp][3] = ymax; }
+      }
+      __syncthreads();
+      int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
+#pragma unroll
+      for (int w = 0; w < kAngles; ++w) {
+        bx0 = min(bx0, s_box[w][0]); bx1 = max(bx1, s_box[w][1]); by0 = min(by0, s_box[w][2]); by1 = max(by1, s_box[w][3]);
+      }
+      const int xl = bx0 & ~3;                                       // 16-byte aligned rows
+      const bool fits = bx1 >= 0 && (bx1 - xl + 16 <= kBoxW) && (by1 - by0 + 2 * NR <= kBoxH);
+      if (tid == 0) { PDBG_ADD(0, 1); PDBG_ADD(1, fits ? 1 : 0); PDBG_ADD(2, bx1 >= 0 ? bx1 - xl + 16 : 0); PDBG_ADD(3, bx1 >= 0 ? by1 - by0 + 2 * NR : 0); }
+      if (fits) {
+        const int w4 = (bx1 - xl + 16 + 3) >> 2, hh = by1 - by0 + 2 * NR;       // the hull, in int4 columns x rows
+        for (int q = tid; q < w4 * hh; q += kThreads) {
+          const int r = q / w4, c4 = q - r * w4;
+          const int gy = by0 + r, gx = xl + 4 * c4;
+          int4 val = make_int4(0, 0, 0, 0);
+          if (gy < size_y && gx + 3 < pitch) val = __ldg(reinterpret_cast<const int4*>(grid + (size_t)gy * pitch + gx));
+          *reinterpret_cast<int4*>(tile + r * kBoxW + 4 * c4) = val;
+        }
+        __syncthreads();
+      }
+      if (active) {
+        const int my_base = ok ? (fits ? (gy0 - by0) * kBoxW + (gx0 - xl) : gy0 * pitch + gx0) : -1;
+        for (int j = j0; j < min(j1, npc); ++j) {
+          const int b = __shfl_sync(0xffffffffu, my_base, j);
+          if (b >= 0) {
+            if (fits) {
+              const int* q = tile + b + hp * kBoxW + ixl;
+#pragma unroll
+              for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)q[k * 2 * kBoxW];
+            } else {
+              const int* q = grid + b + hp * pitch + ixl;
+#pragma unroll
+              for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)__ldg(q + k * 2 * pitch);
+            }
+          } else {
+            // exact indices for this beam: frac(t0) too close to a cell boundary, or the patch touches the grid border
+            const double lxj = __shfl_sync(0xffffffffu, lx, j), lyj = __shfl_sync(0xffffffffu, ly, j);
+            int gx = cell_index(lxj, xc);
+            if (gx < 0 || gx >= size_x) { if (ixl < n_xy) err |= kErrWindow; gx = max(0, min(gx, size_x - 1)); }
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+              const int iy = 2 * k + hp;
+              int gy = cell_index(lyj, dadd(J.sy, dmul((double)iy, J.f)));
+              if (gy < 0 || gy >= size_y) { if (iy < n_xy) err |= kErrWindow; gy = max(0, min(gy, size_y - 1)); }
+              a32[k] += (unsigned int)__ldg(grid + (size_t)gy * pitch + gx);
+            }
+          }
+        }
+      }
+      __syncthreads();     // the tile and s_box are reused by the next segment
+    };
+    // (measured: retrying the two halves of a chunk whose hull does not fit made half of them fit but bought no time)
+    segment(0, kPC);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { a64[k] += a32[k]; a32[k] = 0u; }   // <= 32 cells of <= 2^25 per chunk
+  }
+
+  // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
+  unsigned long long kmax = 0ull;
+  if (active && ixl < n_xy) {
+    const double dx = dsub(xc, J.cx);
+    const double dx2 = dmul(dx, dx);
+    const double da = dsub(ang, J.ca);
+    const double a2 = dmul(da, da);
+    const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, a2), 0.349)), 0.9);
+    double* out = J.score + ((long long)ia_local * n_xy + ixl) * n_xy;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int iy = 2 * k + hp;
+      if (iy < n_xy) {
+        double sc = ddiv(dmul((double)a64[k], kFixScale), J.divisor);
+        if (J.use_penalty) {
+          const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);     // :728
+          if (!zero) {
+            const double dy = dsub(dadd(J.sy, dmul((double)iy, J.f)), J.cy);
+            double d2 = dadd(dx2, dmul(dy, dy));
+            d2 = dmul(d2, J.m2);
+            const double dp = fmax(dsub(1.0, ddiv(dmul(J.gain, d2), J.half_size)), 0.5);
+            sc = dmul(sc, dmul(dp, ap));
+          }
+        }
+        out[iy] = sc;
+        const unsigned long long key = score_key(sc);
+        kmax = key > kmax ? key : kmax;
+      }
+    }
+  }
+  kmax = warp_max_u64(kmax);
+  if (lane == 0) s_wmax[warp] = kmax;
+  if (err) atomicOr(J.err, err);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = 0ull;
+    for (int w = 0; w < kAngles; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;
+    atomicMax(J.best_key, m);
+  }
+}
+}  // namespace patch
+
+int score_patch_angles() { return patch::kAngles; }
+#ifdef RSM_STAGED_DEBUG
+extern "C" void rsm_debug_patch(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, patch::g_pdbg, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(patch::g_pdbg, z, sizeof z); }
+}
+#endif
+
+cudaError_t launch_score_patch(int n_xy, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
+  if (n_cta <= 0) return cudaSuccess;
+  if (n_xy <= 8) patch::score_patch_kernel<4><<<n_cta, patch::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  else if (n_xy <= 14) patch::score_patch_kernel<7><<<n_cta, patch::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  else patch::score_patch_kernel<8><<<n_cta, patch::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  return cudaGetLastError();
+}
+
 // ---- variant table ----------------------------------------------------------------------------
 typedef void (*ScoreFn)(const ScoreJob*, const int*, int);
 

@@ -888,3 +888,65 @@ def test_map_rebuilds_from_the_scan_store(ctx, oracle, rng):
     for m_ in (a, b, dg):
         m_.close()
     store.close()
+
+
+def test_patch_kernel_variant(ctx, oracle, monkeypatch):
+    """The shared-memory patch kernel (batches of small unit-step windows): forced on single matches so that every
+    window width 3..16, boxes that fit and that do not (far beams, wide angle fans), beams on cell boundaries and
+    patches at the grid border are compared score by score; then a batch large enough to select it by itself."""
+    rng = np.random.default_rng(13579)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    levels = np.array([0.3, 0.5642, 0.6666, 0.7046, 0.7875, 0.8324, 1.0], dtype=np.float32)
+    monkeypatch.setenv("RSM_FORCE_PATCH", "1")
+    for trial in range(60):
+        size = int(rng.choice([120, 300, 544, 700]))
+        res = 0.05
+        n_xy = int(rng.choice([3, 5, 7, 8, 9, 12, 13, 14, 15, 16]))
+        window = res * (n_xy - 1)
+        n_ang = int(rng.choice([1, 5, 8, 9, 21, 30]))
+        ares = float(rng.choice([0.0349, 0.1, 0.005]))
+        aoff = ares * (n_ang - 1) / 2 + 1e-9
+        P = int(rng.choice([1, 31, 32, 33, 100, 360, 940]))
+        reach = size / 2 - n_xy / 2 - (1 if trial % 5 == 0 else 6)      # every fifth problem brushes the grid border
+        radius = rng.uniform(0.05, 1.0, P) ** float(rng.choice([0.3, 1.0, 3.0])) * reach
+        ang = np.sort(rng.uniform(-np.pi, np.pi, P)) if trial % 2 else rng.uniform(-np.pi, np.pi, P)
+        pts = np.stack([np.cos(ang) * radius, np.sin(ang) * radius], axis=1)
+        snap = rng.random(P) < rng.choice([0.0, 0.2, 1.0])
+        pts[snap] = np.round(pts[snap] * 2) / 2
+        g = synth.GridSpec(res, 0.15, size, size, float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)))
+        grid = levels[rng.integers(0, len(levels), (size, size))]
+        centre_cells = np.array([size / 2, size / 2]) + (rng.integers(-1, 2, 2) if rng.random() < 0.5 else rng.uniform(-1, 1, 2))
+        theta = float(rng.choice([0.0, aoff, rng.uniform(-3, 3)]))
+        seed = np.array([centre_cells[0] * res - g.off_x, centre_cells[1] * res - g.off_y, theta])
+        p = synth.pass_param(window, res, aoff, ares, 0.3, int(rng.choice([100000, 50])), bool(rng.integers(0, 2)), int(rng.integers(0, 3)))
+        dg = matcher.ScanMatchMap.from_spec(ctx, g)
+        dg.upload(grid)
+        centre = oracle.world_to_map(g, seed)
+        try:
+            sd = m.scores(dg, pts, p, seed)
+        except matcher.RsmError as e:            # a patch really left the grid: the reference would read out of bounds
+            assert "RSM_ERR_WINDOW" in str(e) and trial % 5 == 0
+            dg.close()
+            continue
+        so = oracle.scores(grid, g, pts, p, centre)
+        assert np.array_equal(so, sd), (trial, size, n_xy, n_ang, P, int((so != sd).sum()))
+        want = oracle.match(grid, g, pts, p, seed)
+        pose, cov = seed.copy(), np.eye(3)
+        assert_pass_equal(m.ScanMatch(dg, pts, p, pose, cov), pose, cov, want)
+        dg.close()
+    monkeypatch.delenv("RSM_FORCE_PATCH")
+    # a batch that selects the patch kernel by itself (150 chains x 4 angle groups >= 592 CTAs), against the oracle
+    pairs = synth.config4(150, seed=2468)
+    packed = matcher.pack_loop_closure(pairs)
+    st0 = ctx.stats()["score_launches"]
+    scores, poses, covs, resp = matcher.loop_closure_batch(ctx, packed, pairs[0].passes)
+    for i, sc in enumerate(pairs):
+        if i % 3:
+            continue                      # the oracle chain costs 20 ms per pair: check every third
+        w = oracle.match_chain(oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses), sc.grid, sc.scan_pts, sc.passes, sc.seed_pose)
+        assert scores[i] == w["score"] and np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"])
+        assert np.array_equal(resp[i], w["responses"])
+    monkeypatch.setenv("RSM_NO_PATCH", "1")     # and the whole batch against the tiled kernel
+    scores2, poses2, covs2, resp2 = matcher.loop_closure_batch(ctx, packed, pairs[0].passes)
+    assert np.array_equal(scores, scores2) and np.array_equal(poses, poses2) and np.array_equal(covs, covs2) and np.array_equal(resp, resp2)
+    assert ctx.stats()["score_launches"] >= st0

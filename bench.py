@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--cpu-reps", type=int, default=4, help="full config-2 passes timed for cpu_baseline")
     ap.add_argument("--no-widened", action="store_true", help="skip the map-check / Gauss-Newton extras (N = 1 only)")
     ap.add_argument("--lc-contexts", type=int, default=0,
-                    help="host threads / contexts per GPU for the loop-closure extra (0 = min(4, host cores / ranks))")
+                    help="host threads / contexts per GPU for the loop-closure extra (0 = min(4, host cores / ranks - 1))")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-wide", action="store_true", help="skip the angle-sliced wide-window extra (BASELINE configs[4])")
     return ap.parse_args()
@@ -244,7 +244,9 @@ def main():
 
     # the library's host worker pool shares the box's cores with the other ranks
     if args.lc_contexts <= 0:
-        args.lc_contexts = max(1, min(4, (os.cpu_count() or 1) // max(1, world)))
+        # one host thread per context spins in the stream synchronisations: leave a core per rank for the rest
+        # (measured at N = 8 on 32 cores: 2 / 3 / 4 / 6 contexts -> 690 k / 729 k / 611 k / 419 k matches/s)
+        args.lc_contexts = max(1, min(4, (os.cpu_count() or 1) // max(1, world) - 1))
     os.environ.setdefault("RSM_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world) // max(1, args.lc_contexts))))
     ctx = matcher.Context(local_rank)
     sc = rank_scenario(rank)

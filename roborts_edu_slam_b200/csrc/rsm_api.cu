@@ -1639,15 +1639,14 @@ int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double 
   int rc = plan_raster(ctx, 0.5f, sigma, grid->resolution, occu_offset, use_blur, pl);
   if (rc) return rc;
   if (grid->fixed && !pl.fixed) return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_grid_update_by_range: the blur levels are not 2^-25 multiples but the map is held in fixed point");
-  if (!grid->fixed && pl.fixed) {     // float map: stamp float patterns
+  if (!grid->fixed && pl.fixed) {     // float map: the same stamps as float patterns
     std::vector<double> k;
-    const int half = blur_kernel(sigma, grid->resolution, k);
+    blur_kernel(sigma, grid->resolution, k);
     for (size_t i = 0; i < pl.stamp.size(); ++i) {
       const float p = static_cast<float>(k[i] * occu_offset);
       pl.stamp[i] = 0;
       if (p <= 1.0f && p > 0.0f) std::memcpy(&pl.stamp[i], &p, 4);
     }
-    (void)half;
     const float onef = 1.0f;
     std::memcpy(&pl.one, &onef, 4);
     pl.fixed = false;

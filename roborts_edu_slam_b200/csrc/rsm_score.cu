@@ -885,11 +885,10 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
   constexpr int TILE_X = 32 * RX, TILE_Y = kComputeWarps * RY, NC = RX * RY;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = warp == kComputeWarps;
-  const long long k0 = DBG_T();
+  const long long k0 = DBG_T(); (void)k0;
 
   __shared__ ScoreJob J;
   __shared__ int s_job;
-  __shared__ int s_last;
   __shared__ unsigned long long s_wmax[kComputeWarps];
   __shared__ double sX[TILE_X], sY[TILE_Y];
   __shared__ int sBase[2][kRound];          // tile-relative cell offset of each beam of the round, -1 = skip
@@ -970,7 +969,7 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
 #pragma unroll
   for (int c = 0; c < (NC + 3) / 4; ++c) hi[c] = 0u;
 
-  const long long k1 = DBG_T();
+  const long long k1 = DBG_T(); (void)k1;
   if (nv > 0) {
     if (producer) {
       // ---- producer warp: plan rounds, publish bases, arm FULL, issue one TMA box copy per round ----
@@ -1077,7 +1076,7 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
     }
   }
   __syncthreads();
-  const long long k2 = DBG_T();
+  const long long k2 = DBG_T(); (void)k2;
 
   unsigned long long a64[NC];
 #pragma unroll
@@ -1133,7 +1132,7 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
       }
     }
   }
-  const long long k3 = DBG_T();
+  const long long k3 = DBG_T(); (void)k3;
   // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
   unsigned long long kmax = 0ull;
   if (!producer) {
@@ -1171,7 +1170,7 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
   }
   if (err) atomicOr(J.err, err);
   __syncthreads();
-  const long long k4 = DBG_T();
+  const long long k4 = DBG_T(); (void)k4;
   if (tid == 0) {
     unsigned long long m = 0ull;
     for (int w = 0; w < kComputeWarps; ++w) m = s_wmax[w] > m ? s_wmax[w] : m;

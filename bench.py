@@ -550,6 +550,63 @@ def main():
         widened["frontend_update"] = entry
         fine.close()
         pubm.close()
+    # ---- the other single-match configurations of BASELINE.json (N = 1 only): latency of one call, host in -> host out --
+    small = None
+    if world == 1 and not args.no_widened:
+        small = {}
+        ref_ok = False
+        if args.cpu_reps > 0:
+            from oracle.oracle_py import Oracle, Ref, ref_available
+            ref_ok = ref_available()
+            cpu_ = Ref() if ref_ok else Oracle()
+        for tag, scx, label in (("configs0", synth.config1(), "BASELINE configs[0]: 360-beam scan vs icra submap, +-0.3 m / +-20 deg, 0.05 m, one coarse pass"),
+                                ("configs2", synth.config3(), "BASELINE configs[2]: Hokuyo 1081-beam, coarse 0.1 m + fine + super chain with covariance on the 0.01 m map (2400^2), all beams"),
+                                ("configs2_shipped", synth.config3(shipped_points=True), "the same chain with the shipped use_point_size 100/100/200")):
+            gx = scx.grid
+            dgx = matcher.ScanMatchMap.from_spec(ctx, gx)
+            dgx.InitMapWithRangeVec(scx.base_pts, scx.base_poses, gx.default_prob, gx.sigma, gx.occu_offset, gx.use_blur)
+            chain = len(scx.passes) == 3
+            smx = matcher.ScanMatchers(ctx, scx.passes) if chain else None
+
+            def call():
+                pose_, cov_ = scx.seed_pose.copy(), np.eye(3)
+                r_ = smx.ScanMatch(scx.scan_pts, dgx, pose_, cov_) if chain else m.ScanMatch(dgx, scx.scan_pts, scx.passes[0], pose_, cov_)
+                return r_, pose_, cov_
+            for _ in range(5):
+                call()
+            ctx.reset_stats()
+            n_rep = 50
+            t0 = time.perf_counter()
+            for _ in range(n_rep):
+                got = call()
+            dt = (time.perf_counter() - t0) / n_rep
+            stx = ctx.stats()
+            entry = {"workload": label, "ms_per_match": dt * 1e3, "evals_per_match": stx["evals"] / n_rep,
+                     "evals_per_s": stx["evals"] / n_rep / dt, "kernel_launches_per_match": stx["kernel_launches"] / n_rep,
+                     "timing": "host wall clock per call, host scan in -> host pose / covariance out, grid resident"}
+            if args.cpu_reps > 0:
+                if ref_ok:
+                    mref = cpu_.create_map(gx)
+                    cpu_.build_map(mref, gx, scx.base_pts, scx.base_poses)
+                    fn_ = (lambda: cpu_.match_chain(mref, scx.scan_pts, scx.passes, scx.seed_pose)) if chain else \
+                          (lambda: cpu_.match(mref, scx.scan_pts, scx.passes[0], scx.seed_pose))
+                else:
+                    gcpu = cpu_.build_grid(gx, scx.base_pts, scx.base_poses)
+                    fn_ = (lambda: cpu_.match_chain(gcpu, gx, scx.scan_pts, scx.passes, scx.seed_pose)) if chain else \
+                          (lambda: cpu_.match(gcpu, gx, scx.scan_pts, scx.passes[0], scx.seed_pose))
+                fn_()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    w_ = fn_()
+                dtc = (time.perf_counter() - t0) / 3
+                entry["cpu_baseline"] = {"value": 1e3 * dtc, "unit": "ms per match", "cores": 1, "kind": "reference" if ref_ok else "port",
+                                         "sample": "3 matches, grid built beforehand"}
+                entry["equals_cpu"] = bool((got[0] == (w_["score"] if chain else w_["response"])) and np.array_equal(got[1], w_["pose"])
+                                           and np.allclose(got[2], w_["cov"], rtol=1e-6, atol=0.0))
+                if ref_ok:
+                    cpu_.destroy_map(mref)
+            small[tag] = entry
+            dgx.close()
     # ---- wide relocalisation extra (config 5): ONE window angle-sliced over the ranks -----------
     wide = None
     if not args.no_wide:
@@ -660,6 +717,8 @@ def main():
             line["loop_closure"] = loop
         if widened is not None:
             line["widened"] = widened
+        if small is not None:
+            line["other_configs"] = small
         if wide:
             line["wide_window"] = wide
         print(json.dumps(line), flush=True)

@@ -425,7 +425,7 @@ struct PassItem {
   PassGeo geo;
   int a0 = 0, a1 = 0;              // resolved slice
   int64_t n_local = 0;             // candidates scored here
-  size_t score_off = 0, trig_off = 0, spec_off = 0;
+  size_t score_off = 0, trig_off = 0, spec_off = 0, acc_off = 0, ticket_off = 0;
   int sel_cta0 = 0, sel_ncta = 0;
   bool exact = false;
   BestPose best;
@@ -626,6 +626,28 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     for (int a = 1; a < na && const_pitch; ++a) if (items[act[a]].grid->pitch != const_pitch) const_pitch = 0;
   }
   const int rows = cfg.rows;
+  // small launches of the tiled / flat kernels on fixed-point grids: split the beams of every (angle, tile) over
+  // `beam_split` CTAs that add integer partial sums into per-candidate accumulators; the last one to arrive
+  // finishes.  A single front-end match is 1 .. 81 CTAs that would each walk ~1000 beams alone.
+  int beam_split = 1;
+  if (!use_staged && !use_patch && std::getenv("RSM_NO_BEAM_SPLIT") == nullptr) {
+    bool all_fixed = true;
+    long long base_ctas = 0, cands = 0;
+    int min_chunks = 1 << 30;
+    for (int a = 0; a < na; ++a) {
+      const PassItem& it = items[act[a]];
+      const PassGeo& g = it.geo;
+      if (!it.grid->fixed) all_fixed = false;
+      base_ctas += use_flat ? score_flat_ctas(int(it.n_local))
+                            : (long long)(it.a1 - it.a0) * ((g.n_xy + cfg.lx - 1) / cfg.lx) * ((g.n_xy + rows - 1) / rows);
+      cands += it.n_local;
+      min_chunks = std::min(min_chunks, (g.visited + 31) / 32);
+    }
+    long long target = 6 * 148;     // CTAs wanted: these are 128 .. 256-thread CTAs, several resident per SM
+    if (const char* e = std::getenv("RSM_SPLIT_TARGET")) target = std::max(1, std::atoi(e));
+    if (all_fixed && base_ctas > 0 && 2 * base_ctas <= target && cands <= (1 << 20))
+      beam_split = int(std::max<long long>(1, std::min<long long>({(long long)min_chunks, 32, (target + base_ctas - 1) / base_ctas})));
+  }
   std::vector<ScoreJob> sjobs(na);
   std::vector<int> s_cta(na + 1, 0);
   std::vector<SelectJob> ljobs(na);
@@ -640,8 +662,21 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   const size_t o_trig = dl.take(trig_doubles * 8);
   const size_t o_tmaps = dl.take(use_staged ? size_t(na) * 256 : 0, 128);
   const size_t up_bytes = dl.off;          // everything above is uploaded in one copy
-  // zero-initialised block: best keys, err flags, pool counter
-  const size_t o_best = dl.take(size_t(na) * 8);
+  // zero-initialised block: [beam-split accumulators and tickets (not read back),] best keys, err flags, pool counter
+  size_t acc_total = 0, ticket_total = 0;
+  if (beam_split > 1)
+    for (int a = 0; a < na; ++a) {
+      PassItem& it = items[act[a]];
+      const PassGeo& g = it.geo;
+      it.acc_off = acc_total; it.ticket_off = ticket_total;
+      acc_total += size_t(it.n_local);
+      ticket_total += use_flat ? size_t(score_flat_ctas(int(it.n_local)))
+                               : size_t(it.a1 - it.a0) * ((g.n_xy + cfg.lx - 1) / cfg.lx) * ((g.n_xy + rows - 1) / rows);
+    }
+  const size_t o_acc = dl.take(acc_total * 8, 256);
+  const size_t o_tickets = dl.take(ticket_total * 4, 4);
+  const size_t zero_begin = beam_split > 1 ? o_acc : dl.off;
+  const size_t o_best = dl.take(size_t(na) * 8, beam_split > 1 ? 8 : 256);
   const size_t o_err = dl.take(size_t(na) * 4, 4);
   const size_t o_poolcnt = dl.take(4, 4);
   const size_t o_done = dl.take(size_t(na) * 4, 4);
@@ -723,7 +758,11 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.use_penalty = it.param.use_center_penalty ? 1 : 0;
     J.f_int = cfg.affine ? int(g.factor) : 0;
     J.stepoff = J.f_int * it.grid->pitch;
-    J.n_split = n_split;
+    J.n_split = use_staged ? n_split : beam_split;
+    if (beam_split > 1) {
+      J.acc = reinterpret_cast<unsigned long long*>(dw + o_acc) + it.acc_off;
+      J.tickets = reinterpret_cast<int*>(dw + o_tickets) + it.ticket_off;
+    }
     if (use_staged) {
       const rsm_ctx::TmapPair* tp = nullptr;
       rc = grid_tmaps(ctx, it.grid, &tp);
@@ -738,9 +777,9 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.half_size = it.param.search_space_size / 2;                     // :734
     J.gain = (it.param.type == RSM_COARSE) ? 0.4 : 0.2;               // :588-602, :759-761
     s_cta[a] = cta;
-    cta += use_flat ? score_flat_ctas(int(it.n_local))
+    cta += use_flat ? score_flat_ctas(int(it.n_local)) * beam_split
                     : use_patch ? (J.ang_count + score_patch_angles() - 1) / score_patch_angles()
-                                : J.ang_count * J.tiles_x * J.tiles_y * (use_staged ? n_split : 1);
+                                : J.ang_count * J.tiles_x * J.tiles_y * (use_staged ? n_split : beam_split);
     (it.grid->fixed ? any_fixed : any_float) = true;
     SelectJob& L = ljobs[a];
     std::memset(&L, 0, sizeof L);
@@ -816,7 +855,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   const bool fork = use_staged && n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
   auto enqueue_score = [&]() -> int {
     CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(dw + o_best, 0, zero_end - o_best, ctx->stream));
+    CU(cudaMemsetAsync(dw + (beam_split > 1 ? zero_begin : o_best), 0, zero_end - (beam_split > 1 ? zero_begin : o_best), ctx->stream));
     {
       Prof p(ctx, KC_SCORE);
       if (use_flat)
@@ -886,7 +925,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   //  batch enqueues its few long kernels well ahead of the GPU anyway)
   if (!ctx->profiling && na <= 8 && std::getenv("RSM_NO_GRAPH") == nullptr) {
     std::vector<long long> key = {(long long)(intptr_t)dw, (long long)(intptr_t)up, (long long)(intptr_t)dn, (long long)up_bytes,
-                                  (long long)o_best, (long long)zero_end, use_flat + 2 * (use_patch ? patch_nxy : 0), use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
+                                  (long long)o_best, (long long)zero_end, use_flat + 2 * (use_patch ? patch_nxy : 0) + 64 * beam_split, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
                                   total_sel_cta, (long long)o_ljobs, (long long)o_lcta, (long long)o_pool, pool_cap,
                                   (long long)o_poolcnt, (long long)head_bytes, pool_first};

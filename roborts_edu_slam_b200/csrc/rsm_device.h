@@ -59,8 +59,11 @@ struct ScoreJob {
   int tiles_x, tiles_y;  // candidate tiles per angle
   int use_penalty;
   int f_int, stepoff;    // affine variant: search step in cells (exact integer) and f_int * pitch
-  int n_split;           // staged variant: CTAs (one cluster) sharing the beams of one (angle, tile)
+  int n_split;           // staged variant: CTAs (one cluster) sharing the beams of one (angle, tile);
+                         // tiled / flat variants: CTAs sharing them through `acc` (small fixed-point launches)
   int pad0;
+  unsigned long long* acc;  // n_split > 1 (tiled / flat): integer partial sums per candidate, zeroed before the launch
+  int* tickets;             // n_split > 1 (tiled / flat): arrival counter per group of CTAs sharing candidates
   const void* tmap;      // staged variant: two CUtensorMaps over the grid (wide box, tall box), 128 B each
   double divisor;        // use_point_size after the reference's adjustment (:561-566)
   double sx, sy, f;      // search_space_start_x/y and space_step_factor (:546-548), in cells

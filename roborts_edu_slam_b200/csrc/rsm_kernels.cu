@@ -302,12 +302,19 @@ select_kernel(const SelectJob* __restrict__ jobs, const int* __restrict__ cta_be
   const unsigned int n_ent = (unsigned int)J.n_cta * kTopK;
   const Entry* ent = J.top_list;
   overflow = false;
-  const int n_final = block_top_k(
-      n_ent,
-      [&](unsigned int i) -> unsigned long long { return score_key(ent[i].score); },
-      [](unsigned int, unsigned long long) {},
-      [&](int r, unsigned long long, unsigned int i) { J.final_top[r] = ent[i]; },
-      s_k, s_bkey, s_bidx, s_count, &overflow, s_cache, kSelectSlice);
+  int n_final;
+  if (J.n_cta == 1) {
+    // a single slice (every small pass): its list already is the job's top-kTopK
+    n_final = emitted;
+    for (int r = tid; r < emitted; r += NT) J.final_top[r] = ent[r];
+  } else {
+    n_final = block_top_k(
+        n_ent,
+        [&](unsigned int i) -> unsigned long long { return score_key(ent[i].score); },
+        [](unsigned int, unsigned long long) {},
+        [&](int r, unsigned long long, unsigned int i) { J.final_top[r] = ent[i]; },
+        s_k, s_bkey, s_bidx, s_count, &overflow, s_cache, kSelectSlice);
+  }
   if (tid == 0) {
     *J.final_count = n_final;
     if (overflow) atomicOr(J.err, kErrSelectFull);

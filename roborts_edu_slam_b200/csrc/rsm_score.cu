@@ -120,7 +120,10 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
   const int first_cta = __ldg(cta_begin + s_job);
   __syncthreads();
 
-  const int local = blockIdx.x - first_cta;
+  // small launches: S CTAs share the beams of one (angle, tile) -- integer partial sums, so the order is free
+  const int S = (FIXED && J.n_split > 1) ? J.n_split : 1;
+  const int local = (blockIdx.x - first_cta) / S;
+  const int split = (blockIdx.x - first_cta) - local * S;
   const int tiles = J.tiles_x * J.tiles_y;
   const int ia_local = local / tiles;
   const int tile = local - ia_local * tiles;
@@ -130,7 +133,10 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
   const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
   const int V = J.V, n_xy = J.n_xy, pitch = J.pitch, size_x = J.size_x, size_y = J.size_y;
   const int stepoff = PITCH > 0 ? PITCH : J.stepoff;   // affine: (search step in cells) * pitch
-  const int nchunks = (V + PC - 1) / PC;
+  const int nchunks_all = (V + PC - 1) / PC;
+  const int per_split = (nchunks_all + S - 1) / S;
+  const int c_begin = min(split * per_split, nchunks_all);
+  const int nchunks = min(nchunks_all, c_begin + per_split);      // this CTA gathers chunks [c_begin, nchunks)
 
   if (AFFINE && tid < SLOTS) { sAff[0][tid] = 1; sAff[1][tid] = 1; sAff[2][tid] = 1; }
   // candidate coordinates of this tile: x = start_x + x_index * factor   (:569, :572)
@@ -202,13 +208,13 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
   const float* gridF = reinterpret_cast<const float*>(J.grid);
   int err = 0;
 
-  lut_chunk(0);
+  if (c_begin < nchunks) lut_chunk(c_begin);
   __syncthreads();
-  err |= build_chunk(0);
-  if (nchunks > 1) lut_chunk(1);
+  if (c_begin < nchunks) err |= build_chunk(c_begin);
+  if (c_begin + 1 < nchunks) lut_chunk(c_begin + 1);
   __syncthreads();
 
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_begin; c < nchunks; ++c) {
     if (c + 1 < nchunks) err |= build_chunk(c + 1);
     if (c + 2 < nchunks) lut_chunk(c + 2);
 
@@ -281,8 +287,36 @@ score_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begi
     __syncthreads();
   }
 
-  // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
   const int ix = tx0 + tx;
+  if (FIXED && S > 1) {
+    // add this CTA's partial sums; the last CTA of the (angle, tile) to arrive reads the totals and finishes
+    __shared__ int s_ticket;
+    if (ix < n_xy) {
+      unsigned long long* acc = J.acc + ((long long)ia_local * n_xy + ix) * n_xy;
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        const int iy = ty0 + ts * RY + r;
+        if (iy < n_xy && a64[r]) atomicAdd(acc + iy, a64[r]);
+      }
+    }
+    if (err) atomicOr(J.err, err);
+    err = 0;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(J.tickets + local, 1);
+    __syncthreads();
+    if (s_ticket != S - 1) return;
+    __threadfence();
+    if (ix < n_xy) {
+      const unsigned long long* acc = J.acc + ((long long)ia_local * n_xy + ix) * n_xy;
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        const int iy = ty0 + ts * RY + r;
+        if (iy < n_xy) a64[r] = __ldcg(acc + iy);
+      }
+    }
+  }
+  // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum
   unsigned long long kmax = 0ull;
   if (ix < n_xy) {
     const double x = sX[tx];
@@ -656,7 +690,9 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
 
   const int n_xy = J.n_xy, plane = n_xy * n_xy;
   const int n_local = J.ang_count * plane;
-  const int k0 = (blockIdx.x - first_cta) * kThreads;          // first candidate of this CTA, (angle, y, x) order
+  const int S = (FIXED && J.n_split > 1) ? J.n_split : 1;      // CTAs sharing the beams of one block of candidates
+  const int group = (blockIdx.x - first_cta) / S, split = (blockIdx.x - first_cta) - group * S;
+  const int k0 = group * kThreads;                             // first candidate of this CTA, (angle, y, x) order
   const int kk = k0 + tid;
   const bool live = kk < n_local;
   const int kc = live ? kk : n_local - 1;
@@ -672,7 +708,10 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
   const int xq = to_q(x) + 32768, yq = to_q(y) + 32768;
   const int V = J.V, pitch = J.pitch;
   const unsigned int size_x = (unsigned int)J.size_x, size_y = (unsigned int)J.size_y;
-  const int nchunks = (V + kPC - 1) / kPC;
+  const int nchunks_all = (V + kPC - 1) / kPC;
+  const int per_split = (nchunks_all + S - 1) / S;
+  const int c_begin = min(split * per_split, nchunks_all);
+  const int nchunks = min(nchunks_all, c_begin + per_split);   // this CTA gathers chunks [c_begin, nchunks)
   const int* gridI = reinterpret_cast<const int*>(J.grid);
   const float* gridF = reinterpret_cast<const float*>(J.grid);
 
@@ -695,9 +734,9 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
   unsigned long long a64 = 0ull;
   double ad = 0.0;
   int err = 0;
-  lut_chunk(0);
+  if (c_begin < nchunks) lut_chunk(c_begin);
   __syncthreads();
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_begin; c < nchunks; ++c) {
     if (c + 1 < nchunks) lut_chunk(c + 1);
     const int npc = min(kPC, V - c * kPC);
     const int2* l = sLutQ[c & 1][a_rel];
@@ -728,6 +767,19 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
     __syncthreads();
   }
 
+  if (FIXED && S > 1) {
+    __shared__ int s_ticket;
+    if (live && a64) atomicAdd(J.acc + kk, a64);
+    if (err) atomicOr(J.err, err);
+    err = 0;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(J.tickets + group, 1);
+    __syncthreads();
+    if (s_ticket != S - 1) return;
+    __threadfence();
+    if (live) a64 = __ldcg(J.acc + kk);
+  }
   unsigned long long key = 0ull;
   if (live) {
     double sc = ddiv(FIXED ? dmul((double)a64, kFixScale) : ad, J.divisor);    // :659

@@ -1,0 +1,65 @@
+// TEST SHIM (CPU): exposes the product's host-side arithmetic (roborts_edu_slam_b200/csrc/rsm_host.h -- the code that
+// runs on the host between kernels) so that tests/test_host_logic.py can check it against the oracle without a GPU.
+// hs_finalize glues the header's functions together the way run_pass's exact path (finish_exact, rsm_api.cu) does.
+#include <algorithm>
+#include <vector>
+
+#include "rsm_host.h"
+
+using namespace rsm;
+
+extern "C" {
+
+void hs_ldlt3(const double* H_rowmajor, const double* b, double* x) {
+  double H[3][3];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[r][c] = H_rowmajor[3 * r + c];
+  ldlt3_solve(H, b, x);
+}
+double hs_normalize_angle(double a) { return normalize_angle(a); }
+double hs_max_abs_limit(double v, double lim) { return max_abs_limit(v, lim); }
+
+void hs_world_to_map(double scale, double off_x, double off_y, const double* w, double* m) {
+  MapTransform t; t.set(scale, off_x, off_y); t.world_to_map(w, m);
+}
+void hs_map_to_world(double scale, double off_x, double off_y, const double* m, double* w) {
+  MapTransform t; t.set(scale, off_x, off_y); t.map_to_world(m, w);
+}
+
+// out_i = {n_ang, n_xy, step, divisor, visited}; out_d = {start_x, start_y, factor, start_angle}
+void hs_geometry(const rsm_pass_param* q, int P, double cell_len, const double* center, long* out_i, double* out_d) {
+  const PassGeo g = make_geo(*q, P, cell_len, center);
+  out_i[0] = g.n_ang; out_i[1] = g.n_xy; out_i[2] = g.step; out_i[3] = g.divisor; out_i[4] = g.visited;
+  out_d[0] = g.start_x; out_d[1] = g.start_y; out_d[2] = g.factor; out_d[3] = g.start_angle;
+}
+
+// Everything after the scores exist, on the full score array (candidate order): returns the response;
+// best = {x, y, angle, score} in map coordinates; cov row-major 3x3 in/out; n_avg = size of the averaging set.
+double hs_finalize(const rsm_pass_param* q, int P, double cell_len, const double* center, const double* score, long n,
+                   double* best_out, double* cov, int* n_avg) {
+  const PassGeo g = make_geo(*q, P, cell_len, center);
+  std::vector<Cand> c(n);
+  for (long k = 0; k < n; ++k) { c[k].score = score[k]; c[k].index = k; }
+  std::sort(c.begin(), c.end(), by_score_desc);
+  size_t na = 0;
+  while (na < c.size() && DoubleEqual(c[na].score, c[0].score, kResponseFilterTolerance)) ++na;
+  const BestPose best = find_best(g, c.data(), na);
+  const int type = q->type;
+  if (type == RSM_COARSE || type == RSM_FINE)
+    positional_cov(g, *q, best, c.data(), std::min<size_t>(c.size(), 21), cov);
+  if (type == RSM_COARSE || type == RSM_SUPER) {
+    std::vector<Cand> xy;
+    const double bound = cov_score_bound(best);
+    for (const Cand& e : c) {
+      if (!(e.score >= bound)) break;
+      int ia, ix, iy;
+      g.decode(e.index, &ia, &ix, &iy);
+      if (same_xy(g, best, ix, iy)) { xy.push_back(e); if (xy.size() >= size_t(kMaxVarianceUsePointSize)) break; }
+    }
+    angular_cov(g, *q, best, xy.data(), xy.size(), cov);
+  }
+  best_out[0] = best.x; best_out[1] = best.y; best_out[2] = best.angle; best_out[3] = best.score;
+  *n_avg = best.n_avg;
+  return std::min(best.score, 1.0);
+}
+
+}  // extern "C"

@@ -329,6 +329,12 @@ typedef struct rsm_optimize_param {
 int rsm_optimize(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
                  const rsm_optimize_param* param, double pose_world[3], double* cost,
                  int32_t* iterations /* nullable */);
+/* The same for a caller that owns the world<->map transform (the C++ adapter uses the live reference map's
+ * GetMapCoordsPose / GetWorldCoordsPose): pose_map = the estimate in map cells / rad in, the optimised
+ * estimate with its angle normalised (:125) out -- untouched when *cost comes back as kMaxCost. */
+int rsm_optimize_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
+                     const rsm_optimize_param* param, double pose_map[3], double* cost,
+                     int32_t* iterations /* nullable */);
 /* n independent problems, one launch per iteration over those still iterating.  Problem i uses
  * grids[i] and points pts_xy[pts_offset[i] .. pts_offset[i+1]). */
 int rsm_optimize_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* pts_xy,

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "scan_match/correlate_scan_matcher.h"
+#include "scan_match/optimize_scan_matcher.h"
 #include "ref_types.h"
 #include "scan_matcher_adapter.hpp"
 
@@ -71,6 +72,28 @@ double dropin_match_chain(void* h, void* ref_map, int n, const double* xy, const
   pose_world[0] = pose[0]; pose_world[1] = pose[1]; pose_world[2] = pose[2];
   if (exact_used) *exact_used = used;
   return score;
+}
+
+// the adapter's Gauss-Newton class on a live reference map: op = {iterate_max_times, cost_decrease_threshold,
+// cost_min_threshold, max_update_distance, max_update_angle}; returns the cost, pose_world in/out
+void* dropin_opt_create(int device) {
+  try { return new rsm_adapter::BasedOptimizeScanMatch(device); } catch (...) { return nullptr; }
+}
+void dropin_opt_destroy(void* h) { delete static_cast<rsm_adapter::BasedOptimizeScanMatch*>(h); }
+double dropin_optimize(void* h, void* ref_map, int n, const double* xy, const double* op, double* pose_world) {
+  auto* m = static_cast<rsm_adapter::BasedOptimizeScanMatch*>(h);
+  auto* rm = static_cast<RefMap*>(ref_map);
+  auto rd = MakeScan(n, xy);
+  auto q = std::make_shared<OptimizeScanMatchParam>();
+  q->set_iterate_max_times(static_cast<int>(op[0]));
+  q->set_cost_decrease_threshold(op[1]);
+  q->set_cost_min_threshold(op[2]);
+  q->set_max_update_distance(op[3]);
+  q->set_max_update_angle_(op[4]);
+  Eigen::Vector3d pose(pose_world[0], pose_world[1], pose_world[2]);
+  const double cost = m->ScanMatch(rm->map, rd, q, pose);
+  pose_world[0] = pose[0]; pose_world[1] = pose[1]; pose_world[2] = pose[2];
+  return cost;
 }
 
 }  // extern "C"

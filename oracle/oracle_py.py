@@ -448,15 +448,31 @@ class DropIn:
         L.dropin_destroy.argtypes = [c_p]
         L.dropin_match_chain.restype = c_d
         L.dropin_match_chain.argtypes = [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        L.dropin_opt_create.restype = c_p
+        L.dropin_opt_create.argtypes = [c_i]
+        L.dropin_opt_destroy.argtypes = [c_p]
+        L.dropin_optimize.restype = c_d
+        L.dropin_optimize.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p]
         self.L = L
         self.h = L.dropin_create(device)
-        if not self.h:
+        self.opt = L.dropin_opt_create(device)
+        if not self.h or not self.opt:
             raise RuntimeError("adapter could not create a CUDA context")
 
     def close(self):
         if self.h:
             self.L.dropin_destroy(self.h)
             self.h = None
+        if self.opt:
+            self.L.dropin_opt_destroy(self.opt)
+            self.opt = None
+
+    def optimize(self, ref_map, pts, op, pose_world):
+        """rsm_adapter::BasedOptimizeScanMatch::ScanMatch on a live reference map."""
+        pts, op = _f64(pts), _f64(op)
+        pose = _f64(pose_world).copy()
+        cost = self.L.dropin_optimize(self.opt, ref_map, len(pts), pts.ctypes.data, op.ctypes.data, pose.ctypes.data)
+        return dict(cost=cost, pose=pose)
 
     def match_chain(self, ref_map, pts, params, pose_world, cov=None):
         """params: list of 1 or 3 pass-parameter blocks; ref_map: handle from Ref.create_map."""

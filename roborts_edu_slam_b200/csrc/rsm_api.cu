@@ -2250,7 +2250,8 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
 // order); the 3x3 solve, the stopping rule and the clamped update run here with the host libm, as do the
 // cos / sin of the next estimate.  poses_world in/out; costs out; iterations (nullable) = UpdateCost calls.
 int optimize_core(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* const* d_pts, const int* n_pts,
-                  const rsm_optimize_param* op, double* poses_world, double* costs, int32_t* iterations) {
+                  const rsm_optimize_param* op, double* poses_world, double* costs, int32_t* iterations,
+                  bool map_coords = false) {   // map_coords: poses are given and returned in map cells (adapter path)
   const double kMaxCost = 1.0 * 1000;                         // :231-232
   if (op->iterate_max_times < 1)   // the reference would return the previous call's cost_ (a stale member)
     return fail(ctx, RSM_ERR_INVALID, "rsm_optimize: iterate_max_times must be >= 1");
@@ -2261,13 +2262,15 @@ int optimize_core(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const doubl
     if (iterations) iterations[i] = 0;
     if (!grids[i]->init || n_pts[i] == 0) { costs[i] = kMaxCost; continue; }    // :73-76, pose untouched
     Prob P; P.i = i; P.cost = 0.0; P.last_cost = 0.0;
-    grids[i]->tf.world_to_map(poses_world + 3 * i, P.est);                      // :80-81
+    if (map_coords) { for (int k = 0; k < 3; ++k) P.est[k] = poses_world[3 * i + k]; }
+    else grids[i]->tf.world_to_map(poses_world + 3 * i, P.est);                 // :80-81
     act.push_back(P);
   }
   const size_t out_stride = kOptSums + 1;
   auto finish = [&](const Prob& P) {
     double est[3] = {P.est[0], P.est[1], normalize_angle(P.est[2])};            // :125
-    grids[P.i]->tf.map_to_world(est, poses_world + 3 * P.i);                     // :127
+    if (map_coords) { for (int k = 0; k < 3; ++k) poses_world[3 * P.i + k] = est[k]; }
+    else grids[P.i]->tf.map_to_world(est, poses_world + 3 * P.i);                // :127
     costs[P.i] = P.cost;
   };
   for (int iter = 0; iter < op->iterate_max_times && !act.empty(); ++iter) {
@@ -2497,6 +2500,19 @@ int rsm_optimize(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n
   const int64_t off[2] = {0, n_pts};
   const rsm_grid* gs[1] = {grid};
   return rsm_optimize_batch(ctx, 1, gs, pts_xy, off, param, pose_world, cost, iterations);
+}
+
+int rsm_optimize_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_optimize_param* param,
+                     double pose_map[3], double* cost, int32_t* iterations) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || !param || !pose_map || !cost || n_pts < 0 || (n_pts > 0 && !pts_xy))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_optimize_map: bad arguments");
+  double* d_pts = nullptr;
+  if (n_pts > 0) { int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts); if (rc) return rc; }
+  const rsm_grid* gs[1] = {grid};
+  const double* dp[1] = {d_pts};
+  const int np[1] = {n_pts};
+  return optimize_core(ctx, 1, gs, dp, np, param, pose_map, cost, iterations, true);
 }
 
 int rsm_match_chain_opt(rsm_ctx* ctx, const rsm_grid* coarse_grid, const double* pts_coarse, int n_coarse,

@@ -130,6 +130,97 @@ class BasedCorrelationScanMatch {
   rsm_pass_detail last_detail_{};
 };
 
+#ifdef ROBORTS_SLAM_SCAN_MATCH_OPTIMIZE_SCAN_MATCHER_H
+// Drop-in for the reference's Gauss-Newton matcher (scan_match/optimize_scan_matcher.h:60-237), defined when that
+// header was included first (scan_matchers.h includes both).  Swap scan_matchers.h:401
+//     std::unique_ptr<BasedOptimizeScanMatch> optimize_scan_matcher_;
+// ->  std::unique_ptr<rsm_adapter::BasedOptimizeScanMatch> optimize_scan_matcher_;
+// Same signature and behaviour: invalid input or a NaN step returns kMaxCost = 1000 with best_pose untouched
+// (:73-76, :103-106); otherwise best_pose is the optimised pose (angle normalised, :125-127) and the return value
+// the last cost.  World <-> map uses the live map's own transform.
+class BasedOptimizeScanMatch {
+ public:
+  explicit BasedOptimizeScanMatch(int device = 0) {
+    const int rc = rsm_create(device, &ctx_);
+    if (rc != RSM_OK) throw std::runtime_error("rsm_create failed (status " + std::to_string(rc) + "): no CUDA device, and there is no CPU path");
+  }
+  ~BasedOptimizeScanMatch() {
+    if (grid_) rsm_grid_destroy(ctx_, grid_);
+    if (ctx_) rsm_destroy(ctx_);
+  }
+  BasedOptimizeScanMatch(const BasedOptimizeScanMatch&) = delete;
+  BasedOptimizeScanMatch& operator=(const BasedOptimizeScanMatch&) = delete;
+
+  double ScanMatch(std::shared_ptr<roborts_slam::ScanMatchMap> map,
+                   std::shared_ptr<roborts_slam::RangeDataContainer2d> range_data,
+                   std::shared_ptr<roborts_slam::OptimizeScanMatchParam> optimize_scan_match_param,
+                   Eigen::Vector3d& best_pose) {
+    const double kMaxCost = 1.0 * 1000;
+    if (!map->IsMapInit() || range_data->GetSize() == 0) {
+      LOG(WARNING) << "Invalid scan match input !";
+      return kMaxCost;
+    }
+    SyncGrid(map);
+    const int n = range_data->GetSize();
+    pts_.resize(2 * static_cast<size_t>(n));
+    for (int i = 0; i < n; ++i) {
+      const Eigen::Vector2d& p = range_data->GetDataPoint(i);
+      pts_[2 * i] = p[0];
+      pts_[2 * i + 1] = p[1];
+    }
+    rsm_optimize_param q;
+    q.iterate_max_times = optimize_scan_match_param->iterate_max_times();
+    q.cost_decrease_threshold = optimize_scan_match_param->cost_decrease_threshold();
+    q.cost_min_threshold = optimize_scan_match_param->cost_min_threshold();
+    q.max_update_distance = optimize_scan_match_param->max_update_distance();
+    q.max_update_angle = optimize_scan_match_param->max_update_angle();
+    q.reserved = 0;
+    const Eigen::Vector3d est = map->GetMapCoordsPose(best_pose);                 // :80-81
+    double pose_map[3] = {est[0], est[1], est[2]};
+    double cost = kMaxCost;
+    const int rc = rsm_optimize_map(ctx_, grid_, pts_.data(), n, &q, pose_map, &cost, &last_iterations_);
+    if (rc != RSM_OK) {
+      LOG(WARNING) << "rsm_optimize_map failed: " << rsm_last_error(ctx_);
+      return kMaxCost;
+    }
+    if (cost == kMaxCost && pose_map[0] == est[0] && pose_map[1] == est[1] && pose_map[2] == est[2]) return kMaxCost;   // NaN step
+    best_pose = map->GetWorldCoordsPose(Eigen::Vector3d(pose_map[0], pose_map[1], pose_map[2]));   // :127
+    return cost;
+  }
+
+  int last_iterations() const { return last_iterations_; }
+
+ private:
+  void SyncGrid(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr) {
+    roborts_slam::ScanMatchMap& map = *map_ptr;
+    const int sx = map.GetSizeX(), sy = map.GetSizeY();
+    const bool same = grid_ && seen_map_.lock() == map_ptr && sx == seen_sx_ && sy == seen_sy_ &&
+                      map.map_update_index() == seen_update_ && map.get_scale_factor() == seen_scale_;
+    if (same) return;
+    if (!grid_ || sx != seen_sx_ || sy != seen_sy_ || map.get_scale_factor() != seen_scale_) {
+      if (grid_) { rsm_grid_destroy(ctx_, grid_); grid_ = nullptr; }
+      if (rsm_grid_create_from_scale(ctx_, sx, sy, map.get_scale_factor(), 0.0, 0.0, &grid_) != RSM_OK)
+        throw std::runtime_error(std::string("rsm_grid_create failed: ") + rsm_last_error(ctx_));
+    }
+    cells_.resize(static_cast<size_t>(sx) * sy);
+    for (int i = 0; i < sx * sy; ++i) cells_[i] = map.GetCellValue(i);
+    if (rsm_grid_upload_f32(ctx_, grid_, cells_.data()) != RSM_OK)
+      throw std::runtime_error(std::string("rsm_grid_upload_f32 failed: ") + rsm_last_error(ctx_));
+    seen_map_ = map_ptr; seen_sx_ = sx; seen_sy_ = sy;
+    seen_update_ = map.map_update_index(); seen_scale_ = map.get_scale_factor();
+  }
+
+  rsm_ctx* ctx_ = nullptr;
+  rsm_grid* grid_ = nullptr;
+  std::weak_ptr<roborts_slam::ScanMatchMap> seen_map_;
+  int seen_sx_ = 0, seen_sy_ = 0, seen_update_ = -2;
+  double seen_scale_ = 0.0;
+  std::vector<float> cells_;
+  std::vector<double> pts_;
+  int32_t last_iterations_ = 0;
+};
+#endif  // ROBORTS_SLAM_SCAN_MATCH_OPTIMIZE_SCAN_MATCHER_H
+
 }  // namespace rsm_adapter
 
 #endif

@@ -136,6 +136,8 @@ ABI = {
                                              _PPARAM, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "rsm_optimize": (c_i, [c_p, c_p, c_p, c_i, ctypes.POINTER(OptimizeParamStruct), c_p, ctypes.POINTER(c_d),
                            ctypes.POINTER(ctypes.c_int32)]),
+    "rsm_optimize_map": (c_i, [c_p, c_p, c_p, c_i, ctypes.POINTER(OptimizeParamStruct), c_p, ctypes.POINTER(c_d),
+                               ctypes.POINTER(ctypes.c_int32)]),
     "rsm_optimize_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, ctypes.POINTER(OptimizeParamStruct), c_p, c_p, c_p]),
     "rsm_match_chain_opt": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_i, _PPARAM, ctypes.POINTER(OptimizeParamStruct), c_d, c_i,
                                   c_p, c_p, ctypes.POINTER(c_d), c_p]),

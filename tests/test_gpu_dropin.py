@@ -69,3 +69,29 @@ def test_adapter_follows_map_updates(ref, dropin):
         assert cov_close(g2["cov"], w2["cov"])
     finally:
         ref.destroy_map(m)
+
+
+def test_optimize_adapter_on_live_reference_objects(ref, dropin):
+    """rsm_adapter::BasedOptimizeScanMatch handed a live reference map, scan and OptimizeScanMatchParam returns what
+    the reference's BasedOptimizeScanMatch returns for them (cost and pose, bit for bit), including the invalid-input
+    behaviour (kMaxCost, pose untouched)."""
+    ops = ((10, 0.1, 0.5, 0.5, 0.5), (10, 1.0, 2.0, 0.5, 0.2), (3, 1e-9, 0.0, 0.02, 0.01), (1, 0.1, 0.5, 0.5, 0.5))
+    deltas = ([0.12, -0.07, 0.1], [0.02, 0.01, 0.02], [-0.2, 0.15, -0.12], [0.5, 0.4, -0.3], [0.0, 0.0, 0.0])
+    for sc in [synth.config1()] + synth.config4(2, seed=5):
+        m = ref.create_map(sc.grid)
+        try:
+            seed = sc.truth_pose + np.array(deltas[0])
+            got = dropin.optimize(m, sc.scan_pts, ops[0], seed)          # map not initialised yet
+            assert got["cost"] == 1000.0 and np.array_equal(got["pose"], seed)
+            ref.build_map(m, sc.grid, sc.base_pts, sc.base_poses)
+            for op in ops:
+                for d in deltas:
+                    seed = sc.truth_pose + np.array(d)
+                    want = ref.optimize(m, sc.scan_pts, op, seed)
+                    got = dropin.optimize(m, sc.scan_pts, op, seed)
+                    assert got["cost"] == want["cost"], (sc.name, op, d)
+                    assert np.array_equal(got["pose"], want["pose"])
+            got = dropin.optimize(m, sc.scan_pts[:0], ops[0], seed)      # empty scan
+            assert got["cost"] == 1000.0 and np.array_equal(got["pose"], seed)
+        finally:
+            ref.destroy_map(m)

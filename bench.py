@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=256, help="loop-closure extra (0 = skip)")
+    ap.add_argument("--pairs-per-gpu", type=int, default=512,
+                    help="loop-closure extra: pairs per GPU (BASELINE configs[3] is 4096 pairs over 8 GPUs = 512 each; 0 = skip)")
     ap.add_argument("--cpu-reps", type=int, default=4, help="full config-2 passes timed for cpu_baseline")
     ap.add_argument("--no-widened", action="store_true", help="skip the map-check / Gauss-Newton extras (N = 1 only)")
     ap.add_argument("--lc-contexts", type=int, default=0,

@@ -164,6 +164,28 @@ int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double 
  *                             (pre_grid_offset = -GetFloorMin()), the new map_offset_.  New cells get
  *                             fill_prob, cell 0 first_cell_prob, then the old rows are copied in
  *                             (grid_map_base.h:222-238).  Drops an uploaded occupancy mask. */
+/* The resize policy itself, restated on the host (no device, no context needed): GridMapBase's bound-box
+ * bookkeeping -- UpdateBound / ExtendSize(EXTEND_PARTLY) (map/grid_map_base.h:188-274, util/boundbox.h) -- as
+ * UpdateMapByRange (map/occu_grid_map.h:278-300) and MapSizeCheck (scan_match/scan_matchers.h:365-390) drive
+ * it.  One object per map, fed every scan / check in the reference's order.  *fits = 1: the scan is to be
+ * stamped (rsm_grid_update_by_range / rsm_pubmap_update_by_range); *fits = 0: the map was extended instead
+ * and the scan is dropped, as in the reference -- `geometry` then holds what rsm_grid_extend /
+ * rsm_pubmap_extend need.  half_kernel = rsm_blur_half_size(deviation, resolution) of the map (0 for the
+ * publishing map), use_blur as passed to UpdateMapByRange.  With this a caller needs no reference map object. */
+typedef struct rsm_map_bounds rsm_map_bounds;
+typedef struct rsm_map_geometry {
+  int32_t size_x, size_y;                         /* map size after the call */
+  int32_t pre_grid_offset_x, pre_grid_offset_y;   /* where the old cell (0,0) went in the last extension */
+  double offset_x, offset_y;                      /* GridMapBase::map_offset_ after the call */
+} rsm_map_geometry;
+int rsm_blur_half_size(double sigma, double resolution);   /* GaussianBlur half size, -1 if rejected (occu_grid_map.h:40-59) */
+int rsm_map_bounds_create(int size_x, int size_y, double scale_factor, double offset_x, double offset_y,
+                          double extend_factor, rsm_map_bounds** out);
+void rsm_map_bounds_destroy(rsm_map_bounds* bounds);
+int rsm_map_bounds_update_scan(rsm_map_bounds* bounds, const double* pts_xy, int n_pts, const double pose_world[3],
+                               int half_kernel, int use_blur, int* fits, rsm_map_geometry* geometry /* nullable */);
+int rsm_map_bounds_size_check(rsm_map_bounds* bounds, const double pose_world[3], double range_max, double offset,
+                              int* fits, rsm_map_geometry* geometry /* nullable */);
 int rsm_grid_fill(rsm_ctx* ctx, rsm_grid* grid, float fill_prob, float first_cell_prob);
 int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
                              const double* pts_xy, int n_pts, const double pose_world[3]);

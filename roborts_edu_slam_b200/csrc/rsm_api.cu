@@ -72,6 +72,9 @@ struct rsm_scan_store {
   size_t chunk_used = 0, chunk_cap = 0;
 };
 
+// GridMapBase's bound-box bookkeeping (host only): see MapBounds in rsm_host.h
+struct rsm_map_bounds { MapBounds b; };
+
 // Device-resident publishing map: OccuGridMap<CountCell> (map/slam_map.h:35) as three float planes + the update index.
 struct rsm_pubmap {
   rsm_grid g;                      // geometry + the occupancy mask the map check reads (g.d_occ); no lookup cells
@@ -2010,6 +2013,50 @@ int rsm_pubmap_download(rsm_ctx* ctx, const rsm_pubmap* pm, float* prob_out, flo
   if (hit_out) CU(cudaMemcpyAsync(hit_out, pm->d_hit, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (occupied_out) CU(cudaMemcpyAsync(occupied_out, pm->g.d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
   return sync_stream(ctx);
+}
+
+// ---- map resize policy (host only; no device, no context) -------------------------------------------------------
+int rsm_blur_half_size(double sigma, double resolution) {
+  std::vector<double> k;
+  return blur_kernel(sigma, resolution, k);     // -1: the reference rejects these blur parameters (occu_grid_map.h:40-59)
+}
+
+int rsm_map_bounds_create(int size_x, int size_y, double scale_factor, double offset_x, double offset_y, double extend_factor,
+                          rsm_map_bounds** out) {
+  if (!out || size_x <= 0 || size_y <= 0 || !(scale_factor > 0)) return RSM_ERR_INVALID;
+  rsm_map_bounds* h = new rsm_map_bounds;
+  h->b.init(size_x, size_y, scale_factor, offset_x, offset_y, extend_factor);
+  *out = h;
+  return RSM_OK;
+}
+
+void rsm_map_bounds_destroy(rsm_map_bounds* bounds) { delete bounds; }
+
+}  // extern "C"
+namespace {
+void bounds_geometry(const MapBounds& b, rsm_map_geometry* g) {
+  if (!g) return;
+  g->size_x = b.size_x; g->size_y = b.size_y; g->pre_grid_offset_x = b.pre_x; g->pre_grid_offset_y = b.pre_y;
+  g->offset_x = b.off_x; g->offset_y = b.off_y;
+}
+}  // namespace
+extern "C" {
+
+int rsm_map_bounds_update_scan(rsm_map_bounds* bounds, const double* pts_xy, int n_pts, const double pose_world[3], int half_kernel,
+                               int use_blur, int* fits, rsm_map_geometry* geometry) {
+  // n_pts == 0 would hand an empty (FLT_MAX .. FLT_MIN) box to UpdateBound and send the reference's map size to ~3e38
+  if (!bounds || !pts_xy || n_pts <= 0 || !pose_world || !fits || half_kernel < 0) return RSM_ERR_INVALID;
+  *fits = bounds->b.update(bounds->b.scan_box(pts_xy, n_pts, pose_world, half_kernel, use_blur != 0)) ? 1 : 0;
+  bounds_geometry(bounds->b, geometry);
+  return RSM_OK;
+}
+
+int rsm_map_bounds_size_check(rsm_map_bounds* bounds, const double pose_world[3], double range_max, double offset, int* fits,
+                              rsm_map_geometry* geometry) {
+  if (!bounds || !pose_world || !fits) return RSM_ERR_INVALID;
+  *fits = bounds->b.update(bounds->b.range_box(pose_world, range_max, offset)) ? 1 : 0;
+  bounds_geometry(bounds->b, geometry);
+  return RSM_OK;
 }
 
 // ---- matching ----------------------------------------------------------------------------------

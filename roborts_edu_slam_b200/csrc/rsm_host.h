@@ -278,5 +278,99 @@ inline void ldlt3_solve(const double H[3][3], const double b[3], double x[3]) {
   for (int k = 2; k >= 0; --k) if (perm[k] != k) std::swap(x[k], x[perm[k]]);
 }
 
+// ---- map resize policy (GridMapBase::UpdateBound / ExtendSize, map/grid_map_base.h:188-274; util/boundbox.h) ----------
+// Host-only bookkeeping: which scans fit the map, and when and how the map grows.  The cells live elsewhere (on the
+// device); this object only reproduces the reference's decisions and geometry, bit for bit.
+struct BoundBox2 {
+  // BoundBox<double>: an empty box is min = (FLT_MAX, FLT_MAX), max = (FLT_MIN, FLT_MIN) -- FLT_MIN being the smallest
+  // positive float, not the most negative one (util/boundbox.h:38-42)
+  double min_x = double(FLT_MAX), min_y = double(FLT_MAX), max_x = double(FLT_MIN), max_y = double(FLT_MIN);
+  void add_point(double x, double y) {                       // :103-109
+    if (x < min_x) min_x = x;
+    if (y < min_y) min_y = y;
+    if (x > max_x) max_x = x;
+    if (y > max_y) max_y = y;
+  }
+  void add_box(const BoundBox2& b) { add_point(b.min_x, b.min_y); add_point(b.max_x, b.max_y); }   // :111-115
+  bool in_bounds(double x, double y) const { return x > min_x && x < max_x && y > min_y && y < max_y; }   // :122-126
+  int size_x() const { return int(std::ceil(max_x) - std::floor(min_x)); }   // GetBoxSize, :85-90
+  int size_y() const { return int(std::ceil(max_y) - std::floor(min_y)); }
+};
+
+struct MapBounds {
+  int size_x = 0, size_y = 0;
+  double scale = 1.0, off_x = 0.0, off_y = 0.0, extend_factor = 1.0;
+  BoundBox2 box;                                             // GridMapBase::bound_box_
+  MapTransform tf;
+  // what the last extension did (valid after update() returned false)
+  int pre_x = 0, pre_y = 0;
+
+  void init(int sx, int sy, double scale_factor, double ox, double oy, double extend) {
+    size_x = sx; size_y = sy; scale = scale_factor; off_x = ox; off_y = oy;
+    if (extend > 0) extend_factor = extend;                   // set_extend_factor, :181-185
+    box = BoundBox2();
+    tf.set(scale, off_x, off_y);
+  }
+  bool point_in_map(double x, double y) const { return x > 0 && x < size_x && y > 0 && y < size_y; }   // :330-337
+
+  // ExtendSize(EXTEND_PARTLY), :188-254
+  void extend_partly() {
+    BoundBox2 tmp;
+    tmp.add_box(box);
+    tmp.add_point(0.0, 0.0);
+    tmp.add_point(double(size_x), double(size_y));
+    double mnx = tmp.min_x, mny = tmp.min_y, mxx = tmp.max_x, mxy = tmp.max_y;
+    const double bsx = double(tmp.size_x()) * extend_factor, bsy = double(tmp.size_y()) * extend_factor;
+    if (box.min_x <= 0.0) mnx -= bsx;
+    if (box.min_y <= 0.0) mny -= bsy;
+    if (box.max_x >= double(size_x)) mxx += bsx;
+    if (box.max_y >= double(size_y)) mxy += bsy;
+    tmp.add_point(mnx, mny);
+    tmp.add_point(mxx, mxy);
+    const double fx = std::floor(tmp.min_x), fy = std::floor(tmp.min_y);
+    off_x -= fx / scale;                                      // map_offset_ -= GetFloorMin() / scale_factor_
+    off_y -= fy / scale;
+    pre_x = int(-fx); pre_y = int(-fy);                       // pre_grid_offset = (-GetFloorMin()).cast<int>()
+    size_x = tmp.size_x(); size_y = tmp.size_y();
+    const BoundBox2 old = box;
+    box.min_x = old.min_x - tmp.min_x; box.min_y = old.min_y - tmp.min_y;     // ResetWithBound(min - tmp.min, max - tmp.min)
+    box.max_x = old.max_x - tmp.min_x; box.max_y = old.max_y - tmp.min_y;
+    tf.set(scale, off_x, off_y);                              // SetMapTransform
+  }
+
+  // UpdateBound(bound_box), :257-274: true = the box is inside the map (or was already covered); false = the map was
+  // extended (pre_x / pre_y / size / offset updated)
+  bool update(const BoundBox2& b) {
+    if (box.in_bounds(b.min_x, b.min_y) && box.in_bounds(b.max_x, b.max_y)) return true;
+    box.add_box(b);
+    if (!point_in_map(box.min_x, box.min_y) || !point_in_map(box.max_x, box.max_y)) { extend_partly(); return false; }
+    return true;
+  }
+
+  // the bound box UpdateMapByRange hands to UpdateBound (occu_grid_map.h:278-294): hull of the scan's points in map
+  // cells (pose_transform * p = t + (c x - s y, s x + c y), host libm), grown by the blur kernel's half size
+  BoundBox2 scan_box(const double* pts_xy, int n, const double* pose_world, int half_kernel, bool use_blur) const {
+    double pm[3];
+    tf.world_to_map(pose_world, pm);
+    const double c = std::cos(pm[2]), s = std::sin(pm[2]);
+    BoundBox2 b;
+    for (int i = 0; i < n; ++i) {
+      const double px = pts_xy[2 * i], py = pts_xy[2 * i + 1];
+      b.add_point(pm[0] + (c * px + (-s) * py), pm[1] + (s * px + c * py));
+    }
+    if (use_blur) { b.min_x -= half_kernel; b.min_y -= half_kernel; b.max_x += half_kernel; b.max_y += half_kernel; }   // :288-290
+    return b;
+  }
+  // MapSizeCheck's box (scan_match/scan_matchers.h:365-380)
+  BoundBox2 range_box(const double* pose_world, double range_max, double offset) const {
+    double pm[3];
+    tf.world_to_map(pose_world, pm);
+    const double max_size = (range_max + offset) / (1 / scale);
+    BoundBox2 b;
+    b.min_x = pm[0] - max_size; b.min_y = pm[1] - max_size; b.max_x = pm[0] + max_size; b.max_y = pm[1] + max_size;
+    return b;
+  }
+};
+
 }  // namespace rsm
 #endif

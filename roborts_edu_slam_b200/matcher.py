@@ -65,6 +65,12 @@ class Stats(ctypes.Structure):
         return d
 
 
+class MapGeometryStruct(ctypes.Structure):
+    """rsm_map_geometry"""
+    _fields_ = [("size_x", ctypes.c_int32), ("size_y", ctypes.c_int32), ("pre_grid_offset_x", ctypes.c_int32),
+                ("pre_grid_offset_y", ctypes.c_int32), ("offset_x", c_d), ("offset_y", c_d)]
+
+
 class MapCheckParamStruct(ctypes.Structure):
     """rsm_map_check_param"""
     _fields_ = [("bound_tolerance", c_d), ("penalty_gain", c_d), ("check_point_num", ctypes.c_int32),
@@ -107,6 +113,11 @@ ABI = {
     "rsm_pubmap_download": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "rsm_grid_rebuild": (c_i, [c_p, c_p, c_p, c_i, c_p, ctypes.c_float, c_d, c_d, c_i]),
     "rsm_pubmap_rebuild": (c_i, [c_p, c_p, c_p, c_i, c_p, ctypes.c_float, ctypes.c_float]),
+    "rsm_blur_half_size": (c_i, [c_d, c_d]),
+    "rsm_map_bounds_create": (c_i, [c_i, c_i, c_d, c_d, c_d, c_d, ctypes.POINTER(c_p)]),
+    "rsm_map_bounds_destroy": (None, [c_p]),
+    "rsm_map_bounds_update_scan": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(MapGeometryStruct)]),
+    "rsm_map_bounds_size_check": (c_i, [c_p, c_p, c_d, c_d, ctypes.POINTER(c_i), ctypes.POINTER(MapGeometryStruct)]),
     "rsm_grid_fill": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
     "rsm_grid_update_by_range": (c_i, [c_p, c_p, c_d, c_d, c_i, c_p, c_i, c_p]),
     "rsm_grid_extend": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, ctypes.c_float, ctypes.c_float]),
@@ -414,6 +425,43 @@ class ScanMatchMap:
         m, out = _f64(pose_map), np.zeros(3)
         self.ctx.check(self.ctx.lib.rsm_map_to_world(self.h, m.ctypes.data, out.ctypes.data))
         return out
+
+
+class MapBounds:
+    """GridMapBase's resize policy (UpdateBound / ExtendSize), host only: no GPU needed."""
+
+    def __init__(self, size_x, size_y, resolution, offset_x, offset_y, extend_factor=1.0):
+        self.lib = load_library()
+        h = c_p()
+        rc = self.lib.rsm_map_bounds_create(int(size_x), int(size_y), 1.0 / float(resolution), float(offset_x), float(offset_y),
+                                            float(extend_factor), ctypes.byref(h))
+        if rc != RSM_OK:
+            raise RsmError(rc, "rsm_map_bounds_create")
+        self.h = h
+
+    def _ret(self, rc, fits, g):
+        if rc != RSM_OK:
+            raise RsmError(rc, "rsm_map_bounds")
+        return bool(fits.value), (g.size_x, g.size_y, g.offset_x, g.offset_y), (g.pre_grid_offset_x, g.pre_grid_offset_y)
+
+    def UpdateMapByRange(self, pts_cells, sensor_pose, half_kernel=0, use_blur=False):
+        """-> (stamp this scan?, (size_x, size_y, off_x, off_y), pre_grid_offset of the last extension)"""
+        pts = _f64(np.asarray(pts_cells).reshape(-1, 2))
+        pose = _f64(sensor_pose)
+        fits, g = c_i(0), MapGeometryStruct()
+        return self._ret(self.lib.rsm_map_bounds_update_scan(self.h, pts.ctypes.data, len(pts), pose.ctypes.data, int(half_kernel),
+                                                             int(use_blur), ctypes.byref(fits), ctypes.byref(g)), fits, g)
+
+    def MapSizeCheck(self, pose_world, range_max, offset):
+        pose = _f64(pose_world)
+        fits, g = c_i(0), MapGeometryStruct()
+        return self._ret(self.lib.rsm_map_bounds_size_check(self.h, pose.ctypes.data, float(range_max), float(offset),
+                                                            ctypes.byref(fits), ctypes.byref(g)), fits, g)
+
+    def close(self):
+        if self.h:
+            self.lib.rsm_map_bounds_destroy(self.h)
+            self.h = None
 
 
 class PubMap(ScanMatchMap):

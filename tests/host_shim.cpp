@@ -62,4 +62,27 @@ double hs_finalize(const rsm_pass_param* q, int P, double cell_len, const double
   return std::min(best.score, 1.0);
 }
 
+// map resize policy: one object, updated scan by scan; geom = {size_x, size_y, off_x, off_y, pre_x, pre_y}
+void* hs_bounds_create(int sx, int sy, double scale, double ox, double oy, double extend) {
+  MapBounds* b = new MapBounds;
+  b->init(sx, sy, scale, ox, oy, extend);
+  return b;
+}
+void hs_bounds_destroy(void* h) { delete static_cast<MapBounds*>(h); }
+static void bounds_geom(const MapBounds* b, double* geom) {
+  geom[0] = b->size_x; geom[1] = b->size_y; geom[2] = b->off_x; geom[3] = b->off_y; geom[4] = b->pre_x; geom[5] = b->pre_y;
+}
+int hs_bounds_update_scan(void* h, const double* pts, int n, const double* pose, int half_kernel, int use_blur, double* geom) {
+  MapBounds* b = static_cast<MapBounds*>(h);
+  const bool ok = b->update(b->scan_box(pts, n, pose, half_kernel, use_blur != 0));
+  bounds_geom(b, geom);
+  return ok ? 1 : 0;
+}
+int hs_bounds_size_check(void* h, const double* pose, double range_max, double offset, double* geom) {
+  MapBounds* b = static_cast<MapBounds*>(h);
+  const bool ok = b->update(b->range_box(pose, range_max, offset));
+  bounds_geom(b, geom);
+  return ok ? 1 : 0;
+}
+
 }  // extern "C"

@@ -785,15 +785,17 @@ def test_frontend_map_stays_on_device(ctx):
     dg.fill(0.5, g.default_prob)
     fresh = dg.download()
     assert fresh[0, 0] == np.float32(0.3) and (fresh.ravel()[1:] == np.float32(0.5)).all()
-    scale = 1.0 / g.res
+    # the resize decisions come from the library's own restatement of the policy (no reference map object involved)
+    bounds = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
+    half = ctx.lib.rsm_blur_half_size(g.sigma, g.res)
     n_ext = 0
     for k, (p, s) in enumerate(zip(poses, pts)):
         sx, sy, ox, oy = (int(z["geom"][k][0]), int(z["geom"][k][1]), float(z["geom"][k][2]), float(z["geom"][k][3]))
-        if bool(z["stamped"][k]):
+        fits, geom, pre = bounds.UpdateMapByRange(s, p, half, True)
+        assert fits == bool(z["stamped"][k]) and geom == (sx, sy, ox, oy)
+        if fits:
             dg.UpdateMapByRange(s, p, g.sigma, g.occu_offset, True)
         else:
-            osx, osy, oox, ooy = dg.geometry()
-            pre = (int(round((ox - oox) * scale)), int(round((oy - ooy) * scale)))
             dg.ExtendSize(sx, sy, pre, (ox, oy), 0.5, g.default_prob)
             n_ext += 1
         assert dg.geometry() == (sx, sy, ox, oy)
@@ -835,15 +837,16 @@ def test_publishing_map_on_device(ctx):
     g = mf.spec()
     poses, pts = mf.trajectory(), mf.scans()
     pm = matcher.PubMap(ctx, g.res, g.size_x, g.size_y, g.off_x, g.off_y)
-    scale = 1.0 / g.res
+    bounds = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
     for k, (p, s) in enumerate(zip(poses, pts)):
         sx, sy, ox, oy = (int(z["geom"][k][0]), int(z["geom"][k][1]), float(z["geom"][k][2]), float(z["geom"][k][3]))
         f = mp.factors(k)
-        if bool(z["stamped"][k]):
+        fits, geom, pre = bounds.UpdateMapByRange(s, p, 0, False)
+        assert fits == bool(z["stamped"][k]) and geom == (sx, sy, ox, oy)
+        if fits:
             pm.UpdateMapByRange(s, p, f[0], f[1])
         else:
-            _, _, oox, ooy = pm.geometry()
-            pm.ExtendSize(sx, sy, (int(round((ox - oox) * scale)), int(round((oy - ooy) * scale))), (ox, oy))
+            pm.ExtendSize(sx, sy, pre, (ox, oy))
         assert pm.geometry() == (sx, sy, ox, oy)
         val, cnt, hit, _ = pm.download_all()
         h = hashlib.sha256()

@@ -103,3 +103,126 @@ def test_gauss_newton_host_pieces(shim, oracle, rng):
         want = want - 2.0 * np.pi if want > np.pi else want
         assert shim.hs_normalize_angle(float(a)) == want
     assert shim.hs_max_abs_limit(3.0, 0.5) == 0.5 and shim.hs_max_abs_limit(-3.0, -0.5) == -0.5 and shim.hs_max_abs_limit(0.2, 0.5) == 0.2
+
+
+def _bounds_api(shim):
+    shim.hs_bounds_create.restype = c_p
+    shim.hs_bounds_create.argtypes = [c_i, c_i, c_d, c_d, c_d, c_d]
+    shim.hs_bounds_destroy.argtypes = [c_p]
+    shim.hs_bounds_update_scan.restype = c_i
+    shim.hs_bounds_update_scan.argtypes = [c_p, c_p, c_i, c_p, c_i, c_i, c_p]
+    shim.hs_bounds_size_check.restype = c_i
+    shim.hs_bounds_size_check.argtypes = [c_p, c_p, c_d, c_d, c_p]
+
+
+def test_resize_policy_matches_fixtures(shim):
+    """The host restatement of UpdateBound / ExtendSize (MapBounds) reproduces, step by step, the decisions and the
+    geometry the reference took on the 44-scan trajectory (fixtures of make_frontend.py / make_pubmap.py): stamped
+    or extended, size, map offset -- for the blurred scan-match map and for the publishing map."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_frontend", os.path.join(HERE, "golden", "make_frontend.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    _bounds_api(shim)
+    g = mf.spec()
+    poses, pts = mf.trajectory(), mf.scans()
+    for fixture, half, blur in (("frontend_willow.npz", 2, 1), ("pubmap_willow.npz", 0, 0)):
+        z = np.load(os.path.join(HERE, "golden", fixture), allow_pickle=False)
+        b = shim.hs_bounds_create(g.size_x, g.size_y, 1.0 / g.res, g.off_x, g.off_y, mf.EXTEND)
+        prev = (g.size_x, g.size_y, g.off_x, g.off_y)
+        for k, (p, s) in enumerate(zip(poses, pts)):
+            geom = np.zeros(6)
+            s = np.ascontiguousarray(s)
+            ok = shim.hs_bounds_update_scan(b, s.ctypes.data, len(s), np.ascontiguousarray(p).ctypes.data, half, blur, geom.ctypes.data)
+            want = z["geom"][k]
+            assert bool(ok) == bool(z["stamped"][k]), (fixture, k)
+            assert (int(geom[0]), int(geom[1]), geom[2], geom[3]) == (int(want[0]), int(want[1]), float(want[2]), float(want[3])), (fixture, k)
+            if not ok:       # where the old cell (0, 0) went
+                assert (int(geom[4]), int(geom[5])) == (int(round((geom[2] - prev[2]) / g.res)), int(round((geom[3] - prev[3]) / g.res)))
+            prev = (int(geom[0]), int(geom[1]), geom[2], geom[3])
+        shim.hs_bounds_destroy(b)
+
+
+def test_resize_policy_matches_reference(shim, ref, rng):
+    """Random walks (with MapSizeCheck calls in between, as ScanMatchers::ScanMatch makes them) against the live
+    reference map object: same decisions, same sizes, same offsets, bit for bit."""
+    _bounds_api(shim)
+    occ = synth.load_map("willow")
+    total_ext = 0
+    for trial in range(8):
+        res = float(rng.choice([0.05, 0.1, 0.025]))
+        sigma = res * 3
+        half = int((sigma / res) * np.sqrt(np.log(2)))
+        n = int(rng.choice([200, 480]))
+        start = np.array([14.375, 28.625, 0.3]) + rng.uniform(-1, 1, 3)
+        g = synth.GridSpec(res, sigma, n, n, -(start[0] - 0.5 * n * res), -(start[1] - 0.5 * n * res), 0.3, 0.88, True)
+        extend = float(rng.choice([0.2, 1.0, 0.05]))
+        m = ref.frontend_map_create(g, extend)
+        b = shim.hs_bounds_create(g.size_x, g.size_y, 1.0 / res, g.off_x, g.off_y, extend)
+        p = start.copy()
+        n_ext = 0
+        drift = rng.uniform(-0.5, 0.5, 2)
+        for k in range(40):
+            p = p + np.array([drift[0] + rng.uniform(-0.5, 0.5), drift[1] + rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3)])
+            s = np.ascontiguousarray(synth.raycast(occ, p[0], p[1], p[2], 181, np.deg2rad(270.25), 6.0) / res)
+            if len(s) == 0:
+                continue
+            geom = np.zeros(6)
+            if k % 5 == 4:
+                ok_r, ge_r = ref.frontend_map_size_check(m, p, 6.0, 0.6)
+                ok = shim.hs_bounds_size_check(b, np.ascontiguousarray(p).ctypes.data, 6.0, 0.6, geom.ctypes.data)
+            else:
+                ok_r, ge_r = ref.frontend_map_update(m, s, p, True)
+                ok = shim.hs_bounds_update_scan(b, s.ctypes.data, len(s), np.ascontiguousarray(p).ctypes.data, half, 1, geom.ctypes.data)
+            assert bool(ok) == ok_r, (trial, k)
+            assert (int(geom[0]), int(geom[1]), geom[2], geom[3]) == ge_r, (trial, k, geom, ge_r)
+            n_ext += 0 if ok_r else 1
+        total_ext += n_ext
+        ref.destroy_map(m)
+        shim.hs_bounds_destroy(b)
+    assert total_ext >= 6
+
+
+def test_resize_policy_through_the_c_abi(ref, rng):
+    """The same policy through librsm.so's host-only entry points (rsm_map_bounds_*; callable without a GPU): the
+    fixture trajectories and a random walk against the live reference, plus rsm_blur_half_size."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_frontend", os.path.join(HERE, "golden", "make_frontend.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    lib = matcher.load_library()
+    assert lib.rsm_blur_half_size(0.15, 0.05) == 2 and lib.rsm_blur_half_size(0.4, 0.1) == 3
+    assert lib.rsm_blur_half_size(0.03, 0.025) == 0 and lib.rsm_blur_half_size(0.0, 0.05) == -1
+    g = mf.spec()
+    poses, pts = mf.trajectory(), mf.scans()
+    for fixture, half, blur in (("frontend_willow.npz", 2, True), ("pubmap_willow.npz", 0, False)):
+        z = np.load(os.path.join(HERE, "golden", fixture), allow_pickle=False)
+        mb = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
+        for k, (p, s) in enumerate(zip(poses, pts)):
+            fits, geom, pre = mb.UpdateMapByRange(s, p, half, blur)
+            want = z["geom"][k]
+            assert fits == bool(z["stamped"][k]) and geom == (int(want[0]), int(want[1]), float(want[2]), float(want[3])), (fixture, k)
+        mb.close()
+    occ = synth.load_map("willow")
+    res, n = 0.05, 300
+    start = np.array([14.375, 28.625, 0.3])
+    gs = synth.GridSpec(res, 0.15, n, n, -(start[0] - 0.5 * n * res), -(start[1] - 0.5 * n * res), 0.3, 0.88, True)
+    m = ref.frontend_map_create(gs, 0.3)
+    mb = matcher.MapBounds(n, n, res, gs.off_x, gs.off_y, 0.3)
+    p, n_ext = start.copy(), 0
+    for k in range(60):
+        p = p + np.array([0.35 + rng.uniform(-0.4, 0.4), -0.25 + rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3)])
+        s = synth.raycast(occ, p[0], p[1], p[2], 181, np.deg2rad(270.25), 6.0) / res
+        if len(s) == 0:
+            continue
+        if k % 7 == 6:
+            ok_r, ge_r = ref.frontend_map_size_check(m, p, 6.0, 0.6)
+            fits, geom, pre = mb.MapSizeCheck(p, 6.0, 0.6)
+        else:
+            ok_r, ge_r = ref.frontend_map_update(m, s, p, True)
+            fits, geom, pre = mb.UpdateMapByRange(s, p, 2, True)
+        assert fits == ok_r and geom == ge_r, (k, geom, ge_r)
+        n_ext += 0 if ok_r else 1
+    assert n_ext >= 2
+    ref.destroy_map(m)
+    mb.close()

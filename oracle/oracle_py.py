@@ -64,6 +64,11 @@ class Oracle:
         L.orc_match.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
         L.orc_match_chain.restype = c_d
         L.orc_match_chain.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        L.orc_grid_stamp.restype = c_i
+        L.orc_grid_stamp.argtypes = [c_p, c_i, c_i, ctypes.c_float, c_d, c_d, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_i, c_i]
+        L.orc_grid_extend.argtypes = [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, ctypes.c_float, ctypes.c_float]
+        L.orc_pubmap_update.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, ctypes.c_float,
+                                        ctypes.c_float, ctypes.POINTER(c_i)]
         L.orc_optimize.restype = c_d
         L.orc_optimize.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p]
         L.orc_optimize_cost.argtypes = [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]
@@ -164,6 +169,46 @@ class Oracle:
                                    cov.ctypes.data, resp.ctypes.data, ctypes.byref(sec))
         return dict(score=r, pose=pose, cov=cov, responses=resp, seconds=sec.value)
 
+
+    # ---- front-end maps: incremental UpdateMapByRange, ExtendSize copy, publishing map -------------------
+    def grid_stamp(self, grid, g, pts_cells, pose_world):
+        """UpdateMapByRange(scan, use_blur) on a scan-match map as it is (no reset); grid is modified in place."""
+        n_pts, pts = pack_scans([pts_cells])
+        pose = _f64(pose_world)
+        rc = self.L.orc_grid_stamp(grid.ctypes.data, g.size_x, g.size_y, g.default_prob, g.sigma, g.res, g.occu_offset,
+                                   g.off_x, g.off_y, 1, n_pts.ctypes.data, pts.ctypes.data, pose.ctypes.data, int(g.use_blur), 0)
+        if rc:
+            raise RuntimeError("orc_grid_stamp rc=%d" % rc)
+
+    def grid_extend(self, grid, new_sx, new_sy, pre, fill=0.5, first=0.3):
+        old_sy, old_sx = grid.shape
+        out = np.empty((new_sy, new_sx), dtype=np.float32)
+        grid = np.ascontiguousarray(grid, dtype=np.float32)
+        self.L.orc_grid_extend(grid.ctypes.data, old_sx, old_sy, out.ctypes.data, new_sx, new_sy, int(pre[0]), int(pre[1]),
+                               float(fill), float(first))
+        return out
+
+    def pubmap_new(self, size_x, size_y, default_prob=0.5):
+        shape = (size_y, size_x)
+        return dict(hit=np.zeros(shape, np.float32), passc=np.zeros(shape, np.float32),
+                    value=np.full(shape, np.float32(default_prob), np.float32), index=np.full(shape, -1, np.int32), cur=0)
+
+    def pubmap_update(self, pm, g_res, off_x, off_y, pts_cells, pose_world, free_factor, occu_factor):
+        pts, pose = _f64(pts_cells), _f64(pose_world)
+        cur = c_i(pm["cur"])
+        sy, sx = pm["value"].shape
+        self.L.orc_pubmap_update(pm["hit"].ctypes.data, pm["passc"].ctypes.data, pm["value"].ctypes.data, pm["index"].ctypes.data,
+                                 sx, sy, 1.0 / g_res, off_x, off_y, len(pts), pts.ctypes.data, pose.ctypes.data,
+                                 float(free_factor), float(occu_factor), ctypes.byref(cur))
+        pm["cur"] = cur.value
+
+    def pubmap_extend(self, pm, new_sx, new_sy, pre, default_prob=0.5):
+        out = self.pubmap_new(new_sx, new_sy, default_prob)
+        sy, sx = pm["value"].shape
+        for k in ("hit", "passc", "value", "index"):
+            out[k][pre[1]:pre[1] + sy, pre[0]:pre[0] + sx] = pm[k]
+        out["cur"] = pm["cur"] + 3            # the update that triggered the extension still advances the index (:296-299)
+        return out
 
     # ---- BasedOptimizeScanMatch (optimize_scan_matcher.h) ------------------------------------------
     # op = (iterate_max_times, cost_decrease_threshold, cost_min_threshold, max_update_distance, max_update_angle)

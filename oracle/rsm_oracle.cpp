@@ -349,15 +349,17 @@ int orc_blur_kernel(double sigma, double resolution, double* k, int cap) {
 // Reset to default, then per base scan transform / truncate / bounds-skip / stamp.
 // occu_grid_map.h:222-329, 474-497, 531-576; grid_map_cell.h:361-365; grid_map_base.h:339-346.
 // use_blur == 0 is not restated (SET_CELL_OCCUPIED path, out of the hot-path scope) -> returns 2.
-int orc_grid_build(float* grid, int size_x, int size_y, float default_prob, double sigma,
+// reset != 0: InitMapWithRangeVec (Reset to default_prob first); reset == 0: UpdateMapByRange on the map as it is
+// (the front-end scan-match maps, just_update_occu, slam_processor.cpp:529-571)
+int orc_grid_stamp(float* grid, int size_x, int size_y, float default_prob, double sigma,
                    double resolution, double occu_offset, double off_x, double off_y, int n_scans,
-                   const int* n_pts, const double* pts, const double* poses, int use_blur) {
+                   const int* n_pts, const double* pts, const double* poses, int use_blur, int reset) {
   std::vector<double> kernel(21 * 21);
   int half = orc_blur_kernel(sigma, resolution, kernel.data(), 21 * 21);
   if (!use_blur || half < 0) return 2;
   const int ks = 2 * half + 1;
   const size_t ncell = static_cast<size_t>(size_x) * size_y;
-  for (size_t i = 0; i < ncell; ++i) grid[i] = default_prob;
+  if (reset) for (size_t i = 0; i < ncell; ++i) grid[i] = default_prob;
   const double scale = 1.0 / resolution;
   const MapTf tf = MakeTf(scale, off_x, off_y);
   auto set_prob = [&](int x, int y, float prob) {
@@ -388,6 +390,83 @@ int orc_grid_build(float* grid, int size_x, int size_y, float default_prob, doub
     off += n_pts[s];
   }
   return 0;
+}
+
+int orc_grid_build(float* grid, int size_x, int size_y, float default_prob, double sigma,
+                   double resolution, double occu_offset, double off_x, double off_y, int n_scans,
+                   const int* n_pts, const double* pts, const double* poses, int use_blur) {
+  return orc_grid_stamp(grid, size_x, size_y, default_prob, sigma, resolution, occu_offset, off_x, off_y, n_scans, n_pts, pts,
+                        poses, use_blur, 1);
+}
+
+// GridMapBase::ExtendSize's cell copy (map/grid_map_base.h:222-238): a new array whose cell 0 holds `first` and every
+// other cell `fill` (new CellType[n]{default}), the old rows copied in at (pre_x, pre_y).
+void orc_grid_extend(const float* old_grid, int old_sx, int old_sy, float* new_grid, int new_sx, int new_sy, int pre_x,
+                     int pre_y, float fill, float first) {
+  const size_t n = static_cast<size_t>(new_sx) * new_sy;
+  for (size_t i = 0; i < n; ++i) new_grid[i] = fill;
+  new_grid[0] = first;
+  for (int r = 0; r < old_sy; ++r)
+    std::memcpy(new_grid + static_cast<size_t>(pre_y + r) * new_sx + pre_x, old_grid + static_cast<size_t>(r) * old_sx,
+                sizeof(float) * old_sx);
+}
+
+// OccuGridMap<CountCell>::UpdateMapByRange without blur (the publishing map; map/occu_grid_map.h:258-329, 125-187,
+// 474-530; map/grid_map_cell.h:92-108), in the reference's own order: per beam the Bresenham walk marks cells free
+// (once per update), then the end cell is un-freed and marked occupied (once per update).
+// hit / pass / value / index: the CountCell planes; cur_update_index in/out (advanced by 3).
+void orc_pubmap_update(float* hit, float* pass, float* value, int* index, int size_x, int size_y, double scale, double off_x,
+                       double off_y, int n, const double* pts, const double* pose_world, float free_factor, float occu_factor,
+                       int* cur_update_index) {
+  const MapTf tf = MakeTf(scale, off_x, off_y);
+  double pm[3];
+  WorldToMap(tf, pose_world, pm);
+  const double c = std::cos(pm[2]), sn = std::sin(pm[2]);
+  const int mark_free = *cur_update_index + 1, mark_occu = *cur_update_index + 2;   // :272-273
+  const int sx0 = static_cast<int>((pm[0] + (c * 0.0 + (-sn) * 0.0)) + 0.5);
+  const int sy0 = static_cast<int>((pm[1] + (sn * 0.0 + c * 0.0)) + 0.5);
+  auto in_map = [&](int x, int y) { return x > 1 && x < size_x - 1 && y > 1 && y < size_y - 1; };   // PointInMap(x, y, 0 + 1), :476
+  auto set_free = [&](int x, int y) {                                                // :499-509, grid_map_cell.h:100-103
+    if (!in_map(x, y)) return;
+    const size_t k = static_cast<size_t>(y) * size_x + x;
+    if (index[k] < mark_free) {
+      pass[k] += (1.0f + free_factor);
+      value[k] = hit[k] / pass[k];
+      index[k] = mark_free;
+    }
+  };
+  auto set_occu = [&](int x, int y) {                                                // :511-528, grid_map_cell.h:92-108
+    if (!in_map(x, y)) return;
+    const size_t k = static_cast<size_t>(y) * size_x + x;
+    if (index[k] < mark_occu) {
+      if (index[k] == mark_free) { pass[k] -= (1.0f + free_factor); value[k] = hit[k] / pass[k]; }
+      hit[k] += (1.0f + occu_factor);
+      pass[k] += (1.0f + free_factor);
+      value[k] = hit[k] / pass[k];
+      if (value[k] > 1.0f) value[k] = 1.0f;
+      index[k] = mark_occu;
+    }
+  };
+  for (int i = 0; i < n; ++i) {
+    const double px = pts[2 * i], py = pts[2 * i + 1];
+    const int ex = static_cast<int>((pm[0] + (c * px + (-sn) * py)) + 0.5);
+    const int ey = static_cast<int>((pm[1] + (sn * px + c * py)) + 0.5);
+    if (ex == sx0 && ey == sy0) continue;                                            // :312
+    int x0 = sx0, y0 = sy0, x1 = ex, y1 = ey;                                        // ErgodLineBresenhami, :125-187
+    const bool steep = std::abs(y1 - y0) > std::abs(x1 - x0);
+    if (steep) { std::swap(x0, y0); std::swap(x1, y1); }
+    if (x0 > x1) { std::swap(x0, x1); std::swap(y0, y1); }
+    const int delta_x = x1 - x0, delta_y = std::abs(y1 - y0), y_step = y0 < y1 ? 1 : -1;
+    int error = 0, y = y0;
+    for (int x = x0; x <= x1; ++x) {
+      const int qx = steep ? y : x, qy = steep ? x : y;
+      error += delta_y;
+      if (2 * error >= delta_x) { y += y_step; error -= delta_x; }
+      set_free(qx, qy);
+    }
+    set_occu(ex, ey);
+  }
+  *cur_update_index += 3;                                                            // :326
 }
 
 void orc_world_to_map(double scale, double off_x, double off_y, const double* w, double* out) {

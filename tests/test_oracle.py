@@ -234,3 +234,68 @@ def test_optimize_oracle_matches_reference(oracle, ref, rng):
         compared += 1
         assert a["cost"] == b["cost"] and np.array_equal(a["pose"], b["pose"]), (k, a, b)
     assert compared >= 40
+
+
+# ---- front-end maps: incremental updates, extension, publishing map ---------------------------
+def test_frontend_maps_oracle_matches_golden(oracle):
+    """The restatement of the incremental scan-match map update, ExtendSize's copy and the publishing map's
+    ray-traced CountCell update replays the 44-scan trajectory and reproduces the checksums the reference's own
+    maps had after every step (fixtures), with the resize decisions coming from the product's host policy."""
+    import hashlib
+    import importlib.util
+    import os
+    from roborts_edu_slam_b200 import matcher
+    here = os.path.dirname(os.path.abspath(__file__))
+    mods = {}
+    import sys
+    sys.path.insert(0, os.path.join(here, "golden"))
+    try:
+        for name in ("make_frontend", "make_pubmap"):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(here, "golden", name + ".py"))
+            mods[name] = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mods[name])
+    finally:
+        sys.path.pop(0)
+    mf, mp = mods["make_frontend"], mods["make_pubmap"]
+    g = mf.spec()
+    poses, pts = mf.trajectory(), mf.scans()
+    zf = np.load(os.path.join(here, "golden", "frontend_willow.npz"), allow_pickle=False)
+    zp = np.load(os.path.join(here, "golden", "pubmap_willow.npz"), allow_pickle=False)
+    # scan-match map
+    grid = np.full((g.size_y, g.size_x), np.float32(0.5), dtype=np.float32)
+    grid[0, 0] = np.float32(g.default_prob)
+    cur = synth.GridSpec(g.res, g.sigma, g.size_x, g.size_y, g.off_x, g.off_y, g.default_prob, g.occu_offset, True)
+    bounds = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
+    for k, (p, s) in enumerate(zip(poses, pts)):
+        fits, geom, pre = bounds.UpdateMapByRange(s, p, 2, True)
+        assert fits == bool(zf["stamped"][k])
+        if fits:
+            oracle.grid_stamp(grid, cur, s, p)
+        else:
+            grid = oracle.grid_extend(grid, geom[0], geom[1], pre, 0.5, g.default_prob)
+            cur = synth.GridSpec(g.res, g.sigma, geom[0], geom[1], geom[2], geom[3], g.default_prob, g.occu_offset, True)
+        assert hashlib.sha256(grid.tobytes()).hexdigest() == str(zf["shas"][k]), "scan-match map, step %d" % k
+    bounds.close()
+    # publishing map
+    pm = oracle.pubmap_new(g.size_x, g.size_y)
+    off = (g.off_x, g.off_y)
+    bounds = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
+    for k, (p, s) in enumerate(zip(poses, pts)):
+        f = mp.factors(k)
+        fits, geom, pre = bounds.UpdateMapByRange(s, p, 0, False)
+        assert fits == bool(zp["stamped"][k])
+        if fits:
+            oracle.pubmap_update(pm, g.res, off[0], off[1], s, p, f[0], f[1])
+        else:
+            pm = oracle.pubmap_extend(pm, geom[0], geom[1], pre)
+            off = (geom[2], geom[3])
+        h = hashlib.sha256()
+        for a in (pm["value"], pm["passc"], pm["hit"]):
+            h.update(a.tobytes())
+        assert h.hexdigest() == str(zp["shas"][k]), "publishing map, step %d" % k
+    bounds.close()
+    occ = ((pm["passc"] >= np.float32(zp["knobs"][1])) & ~(pm["value"] < np.float32(zp["knobs"][0]))).astype(np.uint8)
+    assert np.array_equal(occ.ravel(), np.unpackbits(zp["occ_packed"])[: occ.size])
+    gfin = synth.GridSpec(g.res, 0.0, occ.shape[1], occ.shape[0], off[0], off[1], 0.5, 0.88, False)
+    got = np.array([oracle.map_check_penalize(occ, gfin, pts[-1], q, 100, 2.5, 0.015, True) for q in zp["check_poses"]])
+    assert np.array_equal(got, zp["coeff"])

@@ -41,8 +41,12 @@ typedef enum rsm_status {
   RSM_ERR_WINDOW = 4,          /* search window + scan extent leaves the grid (the reference would
                                   read out of bounds here; its callers prevent it with MapSizeCheck,
                                   scan_matchers.h:365-390) */
-  RSM_ERR_UNSUPPORTED = 5,     /* e.g. FAST (branch-and-bound) pass type, non-blur rasterisation */
-  RSM_ERR_NOT_INIT = 6         /* grid has no content yet (reference: !IsMapInit()) */
+  RSM_ERR_UNSUPPORTED = 5,     /* e.g. FAST (branch-and-bound) pass type */
+  RSM_ERR_NOT_INIT = 6,        /* grid has no content yet (reference: !IsMapInit()) */
+  RSM_NEED_EXACT = 7           /* rsm_match_finish only: a consumed candidate set holds exact score ties whose order
+                                  the reference's unstable std::sort decides (correlate_scan_matcher.h:607-608);
+                                  nothing was written -- gather every rank's slice (rsm_match_slice_scores) and call
+                                  rsm_match_finish_exact, which runs that same sort on the whole array */
 } rsm_status;
 
 /* CorrelationScanMatchType, correlate_scan_matcher.h:34-39 */
@@ -100,6 +104,16 @@ int rsm_set_profiling(rsm_ctx* ctx, int on); /* record CUDA events around every 
 int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out);
 int rsm_reset_stats(rsm_ctx* ctx);
 int rsm_synchronize(rsm_ctx* ctx);
+/* Context options.  RSM_OPT_STRICT_TIES (default 0): the fast path already takes the exact std::sort path whenever
+ * the ORDER of exactly tied scores could change which candidates are consumed (ties inside the averaging set, at
+ * the 20/21 covariance cuts).  Ties strictly inside a 20-element covariance prefix keep the same set but may add
+ * the terms in another order than the reference's sort permutation: the covariance then agrees to rounding
+ * (<= 1e-6 relative, the contract) instead of bit for bit.  With the option on those passes take the exact path
+ * too (bit-equal covariance under every tie pattern; a 1.2 M-candidate pass then costs a 50 ms host sort).
+ * RSM_OPT_LANES (default 0 = automatic): sub-batches a batched chain call is cut into, pipelined over as many
+ * streams so that one sub-batch's host finalisation overlaps another's kernels (1 = no pipelining). */
+enum { RSM_OPT_STRICT_TIES = 1, RSM_OPT_LANES = 2 };
+int rsm_set_option(rsm_ctx* ctx, int option, int value);
 /* CUDA-event stopwatch on the context's own stream (what bench.py times with). */
 int rsm_timer_start(rsm_ctx* ctx);
 int rsm_timer_stop(rsm_ctx* ctx, double* elapsed_ms);
@@ -410,7 +424,16 @@ int rsm_pass_scores(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, in
  *                       response, detail.  All ranks obtain identical results.
  *
  * If the consumed sets contain exact ties (whose order the reference's unstable sort decides),
- * rsm_match_finish returns RSM_ERR_UNSUPPORTED: rerun unsliced with rsm_match. */
+ * rsm_match_finish returns RSM_NEED_EXACT on every rank (the decision only reads gathered data) and
+ * writes nothing.  The ranks then exchange their slices' scores and every rank runs the reference's
+ * own sort on the whole array:
+ *
+ *   rsm_match_slice_scores   copies this rank's slice ((angle_end - angle_begin) * n_xy^2 doubles,
+ *                            candidate order) to host memory; capacity 0 only reports the size.
+ *        -- all-gather the slices (rank order = angle order) --
+ *   rsm_match_finish_exact   slices[r] / counts[r] = rank r's scores; together they must cover every
+ *                            candidate of the window exactly once, in angle order.  Same outputs as
+ *                            rsm_match_finish; detail->exact_sort_used = 1. */
 #define RSM_PARTIAL_BYTES 65536
 #define RSM_COLUMNS_BYTES 131072
 int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts,
@@ -420,6 +443,10 @@ int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, v
 int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials,
                      const void* const* columns, double pose_world[3], double cov[9],
                      double* response, rsm_pass_detail* detail /* nullable */);
+int rsm_match_slice_scores(rsm_ctx* ctx, double* scores_out, int64_t capacity, int64_t* n_slice);
+int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int64_t* counts, int n_slices,
+                           double pose_world[3], double cov[9], double* response,
+                           rsm_pass_detail* detail /* nullable */);
 
 /* ---- measurement support ------------------------------------------------------------------
  * Gather-bandwidth micro-benchmark used as the roofline denominator of the scoring kernel:

@@ -60,6 +60,10 @@ class Oracle:
         L.orc_pass_geometry.argtypes = [c_p, c_i, c_d, c_p, c_p, c_p]
         L.orc_scores.restype = c_i
         L.orc_scores.argtypes = [c_p, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p]
+        L.orc_scores_slice.restype = c_i
+        L.orc_scores_slice.argtypes = [c_p, c_i, c_d, c_i, c_p, c_p, c_p, c_i, c_i, c_p]
+        L.orc_finish_scores.restype = c_d
+        L.orc_finish_scores.argtypes = [c_p, c_l, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]
         L.orc_match.restype = c_d
         L.orc_match.argtypes = [c_p, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
         L.orc_match_chain.restype = c_d
@@ -144,6 +148,42 @@ class Oracle:
         self.L.orc_scores(grid.ctypes.data, g.size_x, cell_len, len(pts), pts.ctypes.data, param.ctypes.data,
                           center_map.ctypes.data, score.ctypes.data, _ptr(gx), _ptr(gy))
         return (score, gx, gy) if dump_indices else score
+
+    def scores_threaded(self, grid, g, pts, param, center_map, threads=None):
+        """The same bits as scores(), angle slices on `threads` host threads (ctypes releases the GIL)."""
+        import threading
+        pts, param, center_map = _f64(pts), _f64(param), _f64(center_map)
+        geo = self.geometry(g, param, len(pts), center_map)
+        plane = geo["n_xy"] ** 2
+        score = np.empty(geo["n_ang"] * plane, dtype=np.float64)
+        threads = max(1, min(threads or (os.cpu_count() or 1), geo["n_ang"]))
+        cell_len = 1 / (1.0 / g.res)
+        cuts = [geo["n_ang"] * t // threads for t in range(threads + 1)]
+        rcs = [0] * threads
+
+        def work(t):
+            out = score[cuts[t] * plane: cuts[t + 1] * plane]
+            rcs[t] = self.L.orc_scores_slice(grid.ctypes.data, g.size_x, cell_len, len(pts), pts.ctypes.data, param.ctypes.data,
+                                             center_map.ctypes.data, cuts[t], cuts[t + 1], out.ctypes.data)
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not any(rcs), rcs
+        return score
+
+    def finish_scores(self, score, g, n_pts, param, pose_world, cov=None):
+        """orc_match's tail on a score array computed by scores() / scores_threaded()."""
+        score, param = _f64(score), _f64(param)
+        pose = _f64(pose_world).copy()
+        cov = np.eye(3) if cov is None else _f64(cov).copy()
+        best = np.zeros(4)
+        navg = c_l(0)
+        r = self.L.orc_finish_scores(score.ctypes.data, len(score), int(n_pts), 1.0 / g.res, g.off_x, g.off_y, param.ctypes.data,
+                                     pose.ctypes.data, cov.ctypes.data, best.ctypes.data, ctypes.byref(navg))
+        assert r >= 0.0, "score array does not match the window"
+        return dict(response=r, pose=pose, cov=cov, best_map=best, n_avg=navg.value)
 
     def match(self, grid, g, pts, param, pose_world, cov=None):
         pts, param = _f64(pts), _f64(param)

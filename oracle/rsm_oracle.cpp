@@ -5,7 +5,7 @@
 //
 // Pinning: the reference holds no golden vectors for this path.  The
 // restatement is pinned against the reference's own headers compiled in place
-// (oracle/_ref/libref.so, ref_driver.cpp) by tests/test_oracle_vs_reference.py, and against
+// (oracle/_ref/libref.so, ref_driver.cpp) by tests/test_oracle.py, and against
 // the fixtures that build wrote to tests/golden/ (used where /root/reference is absent).
 //
 // C++ rather than C for one reason: the reference's winner is defined by libstdc++'s unstable
@@ -116,13 +116,17 @@ PassGeometry Geometry(const Param& q, int P, double cell_len, const double* cent
 // One brute-force pass: scores in candidate order k = (ia*n_xy + ix)*n_xy + iy, penalised.
 // correlate_scan_matcher.h:552-603, 637-662, 718-745.  serach_angle_size_/2 (== aoff*2/2) is
 // what the angle table receives (:526,536); aoff*2/2 == aoff exactly in binary floating point.
+// Angles [a_begin, a_end) only (a_end < 0: all); score[] is indexed relative to a_begin.  Every angle is independent of
+// the others, so slices computed on several threads concatenate to the bits of the full pass.
 void ScorePass(const float* grid, int size_x, double cell_len, int P, const double* pts,
-               const Param& q, const double* center, const PassGeometry& g, double* score,
-               int32_t* dump_gx, int32_t* dump_gy) {
+               const Param& q, const double* center, const PassGeometry& g, double* score_out,
+               int32_t* dump_gx, int32_t* dump_gy, int a_begin = 0, int a_end = -1) {
   std::vector<double> lx(P), ly(P);
   const double half_range = (q.aoff * 2) / 2;
   const double start_angle = center[2] - half_range;
-  for (int ia = 0; ia < g.n_ang; ++ia) {
+  if (a_end < 0) a_end = g.n_ang;
+  double* score = score_out - static_cast<size_t>(a_begin) * g.n_xy * g.n_xy;
+  for (int ia = a_begin; ia < a_end; ++ia) {
     const double angle = start_angle + ia * q.ares;
     const double c = std::cos(angle), s = std::sin(angle);
     for (int p = 0; p < P; ++p) {
@@ -152,7 +156,7 @@ void ScorePass(const float* grid, int size_x, double cell_len, int P, const doub
   }
   if (!q.use_center_penalty) return;
   const double gain = (q.type == 0) ? 0.4 : 0.2;  // :588-602, :760-761
-  for (int ia = 0; ia < g.n_ang; ++ia) {
+  for (int ia = a_begin; ia < a_end; ++ia) {
     const double angle = start_angle + ia * q.ares;
     for (int ix = 0; ix < g.n_xy; ++ix) {
       const double x = g.start_x + ix * g.factor;
@@ -348,7 +352,7 @@ int orc_blur_kernel(double sigma, double resolution, double* k, int cap) {
 // Lookup-grid build in the back-end configuration (just_update_occu, no auto-resize):
 // Reset to default, then per base scan transform / truncate / bounds-skip / stamp.
 // occu_grid_map.h:222-329, 474-497, 531-576; grid_map_cell.h:361-365; grid_map_base.h:339-346.
-// use_blur == 0 is not restated (SET_CELL_OCCUPIED path, out of the hot-path scope) -> returns 2.
+// use_blur == 0 (or blur parameters the reference rejects): the SET_CELL_OCCUPIED path, SetCellOccu (:499-516).
 // reset != 0: InitMapWithRangeVec (Reset to default_prob first); reset == 0: UpdateMapByRange on the map as it is
 // (the front-end scan-match maps, just_update_occu, slam_processor.cpp:529-571)
 int orc_grid_stamp(float* grid, int size_x, int size_y, float default_prob, double sigma,
@@ -356,7 +360,9 @@ int orc_grid_stamp(float* grid, int size_x, int size_y, float default_prob, doub
                    const int* n_pts, const double* pts, const double* poses, int use_blur, int reset) {
   std::vector<double> kernel(21 * 21);
   int half = orc_blur_kernel(sigma, resolution, kernel.data(), 21 * 21);
-  if (!use_blur || half < 0) return 2;
+  // GaussianBlur rejected the parameters: half_kernel_size_ = 0, and UpdateMapByRange drops use_blur
+  // (map/occu_grid_map.h:47-59, 265-268)
+  if (half < 0) { half = 0; use_blur = 0; }
   const int ks = 2 * half + 1;
   const size_t ncell = static_cast<size_t>(size_x) * size_y;
   if (reset) for (size_t i = 0; i < ncell; ++i) grid[i] = default_prob;
@@ -366,9 +372,19 @@ int orc_grid_stamp(float* grid, int size_x, int size_y, float default_prob, doub
     float& c = grid[static_cast<size_t>(y) * size_x + x];
     if (c < prob && prob <= 1.0f) c = prob;
   };
+  // SET_CELL_OCCUPIED (use_blur false): SetCellOccu (:499-516) acts once per cell and update --
+  // cell.update_index_ < cur_mark_occu_index -- and adds ProbabilityCellFunctions' update_occu_factor_
+  // (0.5f, map/grid_map_cell.h:333-336, 338-342), clamped to 1.  No ray is traced on these maps
+  // (just_update_occu), so update_index_ never equals cur_mark_free_index; the indices of earlier
+  // updates are always smaller (cur_update_index only grows), hence a per-call plane is equivalent.
+  std::vector<int> update_index;
+  if (!use_blur) update_index.assign(ncell, -1);
+  int cur_update_index = 0;
+  const float update_occu_factor = 0.5f;
   size_t off = 0;
   const double tol = half + 1;
   for (int s = 0; s < n_scans; ++s) {
+    const int cur_mark_occu_index = cur_update_index + 2;   // :272-273
     double pm[3];
     WorldToMap(tf, poses + 3 * s, pm);
     const double c = std::cos(pm[2]), sn = std::sin(pm[2]);
@@ -382,12 +398,23 @@ int orc_grid_stamp(float* grid, int size_x, int size_y, float default_prob, doub
       const int ex = static_cast<int>(mx + 0.5), ey = static_cast<int>(my + 0.5);
       if (ex == sx0 && ey == sy0) continue;
       if (!(ex > tol && ex < size_x - tol && ey > tol && ey < size_y - tol)) continue;
+      if (!use_blur) {
+        const size_t at = static_cast<size_t>(ey) * size_x + ex;
+        if (update_index[at] < cur_mark_occu_index) {
+          float v = grid[at] + update_occu_factor;
+          if (v > 1.0f) v = 1.0f;
+          grid[at] = v;
+          update_index[at] = cur_mark_occu_index;
+        }
+        continue;
+      }
       set_prob(ex, ey, 1.0f);
       for (int j = -half; j <= half; ++j)
         for (int ii = -half; ii <= half; ++ii)
           set_prob(ex + ii, ey + j, static_cast<float>(kernel[(ii + half) + ks * (j + half)] * occu_offset));
     }
     off += n_pts[s];
+    cur_update_index += 3;   // :326
   }
   return 0;
 }
@@ -498,6 +525,40 @@ int orc_scores(const float* grid, int size_x, double cell_len, int P, const doub
 }
 
 // BasedCorrelationScanMatch::ScanMatch restated (correlate_scan_matcher.h:784-875).
+// One angle slice of a pass (the full-size config-5 golden is scored on all host threads, one slice each).
+int orc_scores_slice(const float* grid, int size_x, double cell_len, int P, const double* pts, const double* param,
+                     const double* center_map, int a_begin, int a_end, double* score_out) {
+  const Param q = ReadParam(param);
+  const PassGeometry g = Geometry(q, P, cell_len, center_map);
+  if (a_begin < 0 || a_end > g.n_ang || a_end < a_begin) return 1;
+  ScorePass(grid, size_x, cell_len, P, pts, q, center_map, g, score_out, nullptr, nullptr, a_begin, a_end);
+  return 0;
+}
+
+// Everything after the scores exist (sort, FindBestCandidate, covariance, response, pose write-back) on a score
+// array computed elsewhere (orc_scores / orc_scores_slice): what orc_match does after ScorePass.
+double orc_finish_scores(const double* score, long n_scores, int P, double scale, double off_x, double off_y,
+                         const double* param, double* pose_world, double* cov, double* best_map_out, long* n_avg_out) {
+  const Param q = ReadParam(param);
+  const MapTf tf = MakeTf(scale, off_x, off_y);
+  const double cell_len = 1 / scale;
+  double center[3];
+  WorldToMap(tf, pose_world, center);
+  const PassGeometry g = Geometry(q, P, cell_len, center);
+  const size_t n = static_cast<size_t>(g.n_ang) * g.n_xy * g.n_xy;
+  if (static_cast<size_t>(n_scores) != n) return -1.0;
+  std::vector<Scored> cand(n);
+  for (size_t k = 0; k < n; ++k) { cand[k].score = score[k]; cand[k].index = static_cast<int>(k); }
+  PassOut o = Finish(cand, q, g, cell_len, center, cov);
+  if (best_map_out) { best_map_out[0] = o.best.x; best_map_out[1] = o.best.y; best_map_out[2] = o.best.angle; best_map_out[3] = o.best.score; }
+  if (n_avg_out) *n_avg_out = o.n_avg;
+  if (o.response > q.threshold) {
+    const double b[3] = {o.best.x, o.best.y, o.best.angle};
+    MapToWorld(tf, b, pose_world);
+  }
+  return o.response;
+}
+
 double orc_match(const float* grid, int size_x, int size_y, double scale, double off_x,
                  double off_y, int P, const double* pts, const double* param, double* pose_world,
                  double* cov, double* best_map_out, long* n_avg_out, double* seconds) {

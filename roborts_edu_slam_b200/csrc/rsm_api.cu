@@ -200,19 +200,39 @@ struct SliceState {   // what rsm_match_partial leaves behind for merge / finish
   int cols[kMaxCols];
 };
 
+// One in-flight pass: a stream and the buffers its launches read and write.  Lane 0 is the context's own
+// stream; a batched chain call cuts its items into sub-batches that run on lanes 0..L-1, so that the host
+// finalisation of one sub-batch overlaps the kernels of the others (one context per GPU is enough).
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                 // second staged scoring launch, concurrent with the first
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t done = nullptr;                     // blocking-sync event: a waiting host thread sleeps instead of spinning
+  Buf d_work, h_up, h_down;                       // device arena, pinned staging (up / down)
+  Buf d_aux, h_aux;                               // raster descriptors of a loop-closure sub-batch (live while a pass is prepared)
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { cudaEvent_t a, b; int kc; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+};
+
 struct rsm_ctx {
   int device = 0;
   HostPool pool;
   SliceState slice;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;                 // second staged scoring launch, concurrent with the first
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  Lane L0;
+  std::vector<Lane*> extra_lanes;                 // lanes 1.. (created on first use)
+  cudaStream_t& stream = L0.stream;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::string err;
   rsm_stats stats;
   bool profiling = false;
-  Buf d_work, d_pts, d_flush, d_pool_grids;
-  Buf h_up, h_down;  // pinned staging
+  bool strict_ties = false;                       // RSM_OPT_STRICT_TIES
+  int lanes_wanted = 0;                           // RSM_OPT_LANES (0 = automatic)
+  Buf& d_work = L0.d_work;
+  Buf& h_up = L0.h_up;
+  Buf& h_down = L0.h_down;
+  Buf d_pts, d_flush, d_pool_grids;
   // staged scoring variant: tensor maps of the grids seen so far, keyed by (cells, size, pitch)
   struct alignas(64) TmapPair { CUtensorMap box[2]; };
   std::map<std::tuple<const void*, int, int, int>, TmapPair> tmaps;
@@ -221,10 +241,6 @@ struct rsm_ctx {
   // everything that shapes the launch sequence; the per-call data travels in the pinned buffer
   struct PassGraph { int seen = 0; cudaGraphExec_t exec = nullptr; };
   std::map<std::vector<long long>, PassGraph> graphs;
-  std::vector<cudaEvent_t> ev_pool;
-  struct Span { cudaEvent_t a, b; int kc; };
-  std::vector<Span> spans;
-  size_t ev_used = 0;
 };
 
 namespace {
@@ -307,9 +323,9 @@ int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, const rsm_ctx::TmapPair** out) {
       return fail(ctx, RSM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-int ensure_dev(rsm_ctx* ctx, Buf& b, size_t bytes) {
+int ensure_dev(rsm_ctx* ctx, Buf& b, size_t bytes, cudaStream_t st = nullptr) {
   if (bytes <= b.cap) return RSM_OK;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(st ? st : ctx->stream));
   if (b.p) CU(cudaFree(b.p));
   b.p = nullptr; b.cap = 0;
   size_t cap = bytes + bytes / 4 + 4096;
@@ -318,9 +334,9 @@ int ensure_dev(rsm_ctx* ctx, Buf& b, size_t bytes) {
   return RSM_OK;
 }
 
-int ensure_pinned(rsm_ctx* ctx, Buf& b, size_t bytes) {
+int ensure_pinned(rsm_ctx* ctx, Buf& b, size_t bytes, cudaStream_t st = nullptr) {
   if (bytes <= b.cap) return RSM_OK;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(st ? st : ctx->stream));
   if (b.p) CU(cudaFreeHost(b.p));
   b.p = nullptr; b.cap = 0;
   size_t cap = bytes + bytes / 4 + 4096;
@@ -329,27 +345,61 @@ int ensure_pinned(rsm_ctx* ctx, Buf& b, size_t bytes) {
   return RSM_OK;
 }
 
+// Lanes beyond the context's own stream, created on first use.
+int get_lane(rsm_ctx* ctx, int k, Lane** out) {
+  if (k == 0) { *out = &ctx->L0; return RSM_OK; }
+  while (int(ctx->extra_lanes.size()) < k) {
+    Lane* L = new Lane;
+    if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&L->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L->done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+      delete L;
+      return fail(ctx, RSM_ERR_CUDA, "creating a pipeline lane failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    ctx->extra_lanes.push_back(L);
+  }
+  *out = ctx->extra_lanes[k - 1];
+  return RSM_OK;
+}
+
+void destroy_lane(Lane& L) {
+  if (L.d_work.p) cudaFree(L.d_work.p);
+  if (L.d_aux.p) cudaFree(L.d_aux.p);
+  if (L.h_up.p) cudaFreeHost(L.h_up.p);
+  if (L.h_down.p) cudaFreeHost(L.h_down.p);
+  if (L.h_aux.p) cudaFreeHost(L.h_aux.p);
+  for (cudaEvent_t e : L.ev_pool) cudaEventDestroy(e);
+  if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+  if (L.ev_join) cudaEventDestroy(L.ev_join);
+  if (L.done) cudaEventDestroy(L.done);
+  if (L.stream2) cudaStreamDestroy(L.stream2);
+  if (L.stream) cudaStreamDestroy(L.stream);
+}
+
 // CUDA-event bracket around a kernel class while profiling is on
 struct Prof {
-  rsm_ctx* ctx; int kc; cudaEvent_t a = nullptr, b = nullptr;
-  Prof(rsm_ctx* c, int k) : ctx(c), kc(k) {
+  rsm_ctx* ctx; Lane* L; int kc; cudaEvent_t a = nullptr, b = nullptr;
+  Prof(rsm_ctx* c, int k, Lane* lane = nullptr) : ctx(c), L(lane ? lane : &c->L0), kc(k) {
     if (!ctx->profiling) return;
-    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
-      cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; ctx->ev_pool.push_back(e);
+    while (L->ev_pool.size() < L->ev_used + 2) {
+      cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; L->ev_pool.push_back(e);
     }
-    a = ctx->ev_pool[ctx->ev_used++]; b = ctx->ev_pool[ctx->ev_used++];
-    cudaEventRecord(a, ctx->stream);
+    a = L->ev_pool[L->ev_used++]; b = L->ev_pool[L->ev_used++];
+    cudaEventRecord(a, L->stream);
   }
   ~Prof() {
     if (!a) return;
-    cudaEventRecord(b, ctx->stream);
-    ctx->spans.push_back({a, b, kc});
+    cudaEventRecord(b, L->stream);
+    L->spans.push_back({a, b, kc});
   }
 };
 
-// call after a stream synchronize
-void harvest_profile(rsm_ctx* ctx) {
-  for (auto& s : ctx->spans) {
+// call after the lane's stream has been synchronised
+void harvest_profile(rsm_ctx* ctx, Lane* L = nullptr) {
+  if (!L) L = &ctx->L0;
+  for (auto& s : L->spans) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
       if (s.kc == KC_SCORE) ctx->stats.score_kernel_ms += ms;
@@ -357,14 +407,28 @@ void harvest_profile(rsm_ctx* ctx) {
       else if (s.kc == KC_RASTER) ctx->stats.raster_kernel_ms += ms;
     }
   }
-  ctx->spans.clear();
-  ctx->ev_used = 0;
+  L->spans.clear();
+  L->ev_used = 0;
 }
 
-int sync_stream(rsm_ctx* ctx) {
-  CU(cudaStreamSynchronize(ctx->stream));
-  harvest_profile(ctx);
+int sync_stream(rsm_ctx* ctx, Lane* L = nullptr) {
+  if (!L) L = &ctx->L0;
+  CU(cudaStreamSynchronize(L->stream));
+  harvest_profile(ctx, L);
   return RSM_OK;
+}
+
+// Wait for everything enqueued on the lane so far.  Batches sleep on a blocking-sync event (a rank of a
+// multi-GPU job has few host cores, and a spinning wait takes one from the worker pool); single matches
+// spin in cudaStreamSynchronize, whose wake-up is some 20 us faster.
+int wait_lane(rsm_ctx* ctx, Lane* L, bool blocking) {
+  if (blocking && L->done) {
+    CU(cudaEventRecord(L->done, L->stream));
+    CU(cudaEventSynchronize(L->done));
+    harvest_profile(ctx, L);
+    return RSM_OK;
+  }
+  return sync_stream(ctx, L);
 }
 
 inline double key_to_score(unsigned long long k) {
@@ -450,48 +514,67 @@ static_assert(sizeof(PartialHeader) == 64, "PartialHeader layout");
 struct ColumnsHeader { uint32_t magic; int32_t a0, a1, n_cols; int32_t cols[kMaxCols]; int32_t pad[3]; };
 static_assert(sizeof(ColumnsHeader) == 64, "ColumnsHeader layout");
 
-struct PassScratch {   // device pointers valid until the next pass
-  double* d_score = nullptr;
-};
+// exact path: reproduce the reference's sort on a full score array (candidate k of the array = global index base + k)
+void finish_exact_core(const PassGeo& g, const rsm_pass_param& param, std::vector<Cand>& c, BestPose& best, double* cov) {
+  std::sort(c.begin(), c.end(), by_score_desc);   // correlate_scan_matcher.h:607-608
+  size_t na = 0;
+  while (na < c.size() && DoubleEqual(c[na].score, c[0].score, kResponseFilterTolerance)) ++na;
+  best = find_best(g, c.data(), na);
+  const int type = param.type;
+  if (type == RSM_COARSE || type == RSM_FINE || type == RSM_FAST)
+    positional_cov(g, param, best, c.data(), std::min<size_t>(c.size(), kTopK), cov);
+  if (type == RSM_COARSE || type == RSM_SUPER || type == RSM_FAST) {
+    std::vector<Cand> xy;
+    const double bound = cov_score_bound(best);
+    for (const Cand& e : c) {
+      if (!(e.score >= bound)) break;   // sorted: nothing further can qualify
+      int ia, ix, iy;
+      g.decode(e.index, &ia, &ix, &iy);
+      if (same_xy(g, best, ix, iy)) { xy.push_back(e); if (xy.size() >= size_t(kMaxVarianceUsePointSize)) break; }
+    }
+    angular_cov(g, param, best, xy.data(), xy.size(), cov);
+  }
+}
 
-// exact path: reproduce the reference's sort on the full score array of one item
 void finish_exact(PassItem& it, const double* score) {
   const PassGeo& g = it.geo;
   const int64_t n = it.n_local;
   const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
   std::vector<Cand> c(n);
   for (int64_t k = 0; k < n; ++k) { c[k].score = score[k]; c[k].index = base + k; }
-  std::sort(c.begin(), c.end(), by_score_desc);   // correlate_scan_matcher.h:607-608
-  size_t na = 0;
-  while (na < c.size() && DoubleEqual(c[na].score, c[0].score, kResponseFilterTolerance)) ++na;
-  it.best = find_best(g, c.data(), na);
-  const int type = it.param.type;
-  if (type == RSM_COARSE || type == RSM_FINE || type == RSM_FAST)
-    positional_cov(g, it.param, it.best, c.data(), std::min<size_t>(c.size(), kTopK), it.cov);
-  if (type == RSM_COARSE || type == RSM_SUPER || type == RSM_FAST) {
-    std::vector<Cand> xy;
-    const double bound = cov_score_bound(it.best);
-    for (const Cand& e : c) {
-      if (!(e.score >= bound)) break;   // sorted: nothing further can qualify
-      int ia, ix, iy;
-      g.decode(e.index, &ia, &ix, &iy);
-      if (same_xy(g, it.best, ix, iy)) { xy.push_back(e); if (xy.size() >= size_t(kMaxVarianceUsePointSize)) break; }
-    }
-    angular_cov(g, it.param, it.best, xy.data(), xy.size(), it.cov);
-  }
+  finish_exact_core(g, it.param, c, it.best, it.cov);
 }
 
 bool adjacent_tie(const std::vector<Cand>& v, size_t n) {
-  for (size_t i = 1; i < n; ++i) if (v[i].score == v[i - 1].score) return true;
+  for (size_t i = 1; i < n && i < v.size(); ++i) if (v[i].score == v[i - 1].score) return true;
   return false;
 }
 
-int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* scores_out,
-             int64_t scores_cap, int64_t* scores_written) {
-  const int n_items = int(items.size());
-  PhaseTimer pt(ctx);
-  // ---- host geometry -------------------------------------------------------------------------
+// entries of a sorted list that ComputePositionalCovariance consumes (:904-921)
+size_t positional_prefix(const std::vector<Cand>& top, double bound) {
+  size_t used = 0;
+  while (used < top.size() && used < size_t(kMaxVarianceUsePointSize) && top[used].score > bound) ++used;
+  return used;
+}
+
+// Everything one pass keeps between its launch (pass_begin) and its host finalisation (pass_end).
+struct PassRun {
+  Lane* lane = nullptr;
+  std::vector<PassItem>* items = nullptr;
   std::vector<int> act;
+  PassMode mode = MODE_MATCH;
+  bool pending = false, blocking = false;
+  double* scores_out = nullptr;
+  size_t o_best = 0, o_err = 0, o_poolcnt = 0, o_fcnt = 0, o_ftop = 0, o_speccols = 0, o_spec = 0, o_pool = 0,
+         o_gjobs = 0, o_gout = 0, o_score = 0;
+  size_t head_bytes = 0, gather_doubles = 0;
+  int pool_first = 0, pool_cap = 0;
+};
+
+// ---- geometry of every item; returns the active ones ------------------------------------------------
+int pass_geometry(rsm_ctx* ctx, std::vector<PassItem>& items, std::vector<int>& act) {
+  const int n_items = int(items.size());
+  act.clear();
   for (int i = 0; i < n_items; ++i) {
     PassItem& it = items[i];
     it.active = false; it.exact = false; it.response = 0.0;
@@ -514,9 +597,26 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     it.active = true;
     act.push_back(i);
   }
+  return RSM_OK;
+}
+
+// Items of one launch share the kernel plan (tile shape, variant), which is derived from the window width and
+// the search step: a batch that mixes windows is cut into groups of equal (n_xy, step, cell type).
+bool same_plan(const PassItem& a, const PassItem& b) {
+  return a.geo.n_xy == b.geo.n_xy && a.geo.factor == b.geo.factor && a.grid->fixed == b.grid->fixed;
+}
+
+// ---- launch: host preparation + everything enqueued on the lane's stream ------------------------------
+int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std::vector<int>& act_in, PassMode mode,
+               double* scores_out, int64_t scores_cap, int64_t* scores_written, PassRun& R) {
+  PhaseTimer pt(ctx);
+  R = PassRun();
+  R.lane = lane; R.items = &items; R.act = act_in; R.mode = mode; R.scores_out = scores_out;
+  const std::vector<int>& act = R.act;
   if (scores_written) *scores_written = 0;
   if (act.empty()) return RSM_OK;
   const int na = int(act.size());
+  cudaStream_t st = lane->stream;
 
   // ---- layouts -------------------------------------------------------------------------------
   // the affine variant needs the search step to be the same exact integer number of cells for every job
@@ -600,14 +700,15 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   }
   // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
   bool use_flat = !use_staged && !cfg.affine && std::getenv("RSM_NO_FLAT") == nullptr;
+  int flat_k = 1;                                  // candidates per thread of the flat kernel
   for (int a = 0; a < na && use_flat; ++a) {
     const PassGeo& g = items[act[a]].geo;
     // 16.16 fixed-point coordinates: window coordinates must stay well inside +-2^14 cells
-    // (measured: the tiled kernel wins from about 8 translations per axis on)
-    if (g.n_xy < 3 || g.n_xy > 6 || !(std::fabs(g.start_x) < 8192.0 && std::fabs(g.start_y) < 8192.0 &&
+    if (g.n_xy < 3 || g.n_xy > score_flat_max_nxy() || !(std::fabs(g.start_x) < 8192.0 && std::fabs(g.start_y) < 8192.0 &&
                                        std::fabs(g.x_of(g.n_xy)) < 8192.0 && std::fabs(g.y_of(g.n_xy)) < 8192.0))
       use_flat = false;
   }
+  if (use_flat) flat_k = score_flat_k(items[act[0]].geo.n_xy);
   // patch variant: batches of small unit-step windows on fixed-point grids (the back-end chain's coarse pass).
   // Its CTAs are 8 angles x the whole window x every beam, four resident per SM: below one full wave of them
   // (592) the tiled kernel's many small CTAs balance better (measured: 64-pair sub-batches lose 4 %, 256-pair
@@ -620,7 +721,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     patch_nxy = std::max(patch_nxy, it.geo.n_xy);
     patch_ctas += (it.a1 - it.a0 + score_patch_angles() - 1) / score_patch_angles();
   }
-  if (use_patch && patch_ctas < 592 && std::getenv("RSM_FORCE_PATCH") == nullptr) use_patch = false;
+  if (use_patch && patch_ctas < 256 && std::getenv("RSM_FORCE_PATCH") == nullptr) use_patch = false;
   // immediate-offset variant: unit search step and the same padded pitch for every job
   int const_pitch = 0;
   if (!use_staged && !use_patch && cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
@@ -629,9 +730,10 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     for (int a = 1; a < na && const_pitch; ++a) if (items[act[a]].grid->pitch != const_pitch) const_pitch = 0;
   }
   const int rows = cfg.rows;
-  // small launches of the tiled / flat kernels on fixed-point grids: split the beams of every (angle, tile) over
-  // `beam_split` CTAs that add integer partial sums into per-candidate accumulators; the last one to arrive
-  // finishes.  A single front-end match is 1 .. 81 CTAs that would each walk ~1000 beams alone.
+  // launches of the tiled / flat kernels on fixed-point grids that do not fill the machine: split the beams of every
+  // (angle, tile) over `beam_split` CTAs that add integer partial sums into per-candidate accumulators; the last one
+  // to arrive finishes.  A single front-end match is 1 .. 81 CTAs that would each walk ~1000 beams alone; the
+  // super-fine pass of a 512-pair batch is 512 CTAs, less than one wave.
   int beam_split = 1;
   if (!use_staged && !use_patch && std::getenv("RSM_NO_BEAM_SPLIT") == nullptr) {
     bool all_fixed = true;
@@ -641,19 +743,19 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       const PassItem& it = items[act[a]];
       const PassGeo& g = it.geo;
       if (!it.grid->fixed) all_fixed = false;
-      base_ctas += use_flat ? score_flat_ctas(int(it.n_local))
+      base_ctas += use_flat ? score_flat_ctas(int(it.n_local), flat_k)
                             : (long long)(it.a1 - it.a0) * ((g.n_xy + cfg.lx - 1) / cfg.lx) * ((g.n_xy + rows - 1) / rows);
       cands += it.n_local;
       min_chunks = std::min(min_chunks, (g.visited + 31) / 32);
     }
     long long target = 6 * 148;     // CTAs wanted: these are 128 .. 256-thread CTAs, several resident per SM
     if (const char* e = std::getenv("RSM_SPLIT_TARGET")) target = std::max(1, std::atoi(e));
-    if (all_fixed && base_ctas > 0 && 2 * base_ctas <= target && cands <= (1 << 20)) {
-      beam_split = int(std::max<long long>(1, std::min<long long>({(long long)min_chunks, 32, (target + base_ctas - 1) / base_ctas})));
+    if (all_fixed && base_ctas > 0 && cands <= (1 << 20)) {
+      if (2 * base_ctas <= target)
+        beam_split = int(std::max<long long>(1, std::min<long long>({(long long)min_chunks, 32, (target + base_ctas - 1) / base_ctas})));
+      else if (use_flat && base_ctas < 4 * target)   // a batch's super-fine pass: 3-4 waves of shorter CTAs balance better
+        beam_split = int(std::max<long long>(1, std::min<long long>({(long long)min_chunks / 4, 8, (4 * target + base_ctas - 1) / base_ctas})));
     }
-    // (measured and dropped: splitting mid-size launches of a few waves to cheapen their last, partly empty wave
-    //  shortens a lone 64-pair coarse pass by 14 %, but with several contexts sharing the GPU that wave is filled by
-    //  the other contexts' kernels anyway and the batched throughput does not move)
   }
   std::vector<ScoreJob> sjobs(na);
   std::vector<int> s_cta(na + 1, 0);
@@ -677,7 +779,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       const PassGeo& g = it.geo;
       it.acc_off = acc_total; it.ticket_off = ticket_total;
       acc_total += size_t(it.n_local);
-      ticket_total += use_flat ? size_t(score_flat_ctas(int(it.n_local)))
+      ticket_total += use_flat ? size_t(score_flat_ctas(int(it.n_local), flat_k))
                                : size_t(it.a1 - it.a0) * ((g.n_xy + cfg.lx - 1) / cfg.lx) * ((g.n_xy + rows - 1) / rows);
     }
   const size_t o_acc = dl.take(acc_total * 8, 256);
@@ -720,16 +822,16 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   size_t score_doubles = 0;
   for (int a = 0; a < na; ++a) { items[act[a]].score_off = score_doubles; score_doubles += size_t(items[act[a]].n_local); }
   const size_t o_score = dl.take(score_doubles * 8);
-  int rc = ensure_dev(ctx, ctx->d_work, dl.off);
+  int rc = ensure_dev(ctx, lane->d_work, dl.off, st);
   if (rc) return rc;
-  char* dw = ctx->d_work.p;
-  rc = ensure_pinned(ctx, ctx->h_up, std::max(up_bytes, sizeof(GatherJob) * size_t(na)));
+  char* dw = lane->d_work.p;
+  rc = ensure_pinned(ctx, lane->h_up, std::max(up_bytes, sizeof(GatherJob) * size_t(na)), st);
   if (rc) return rc;
-  rc = ensure_pinned(ctx, ctx->h_down, std::max(down_end - o_best, gather_doubles * 8));
+  rc = ensure_pinned(ctx, lane->h_down, std::max(down_end - o_best, gather_doubles * 8), st);
   if (rc) return rc;
 
   // ---- fill jobs, angle tables ---------------------------------------------------------------
-  char* up = ctx->h_up.p;
+  char* up = lane->h_up.p;
   double* h_trig = reinterpret_cast<double*>(up + o_trig);
   int cta = 0;
   bool any_fixed = false, any_float = false;
@@ -784,7 +886,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     J.half_size = it.param.search_space_size / 2;                     // :734
     J.gain = (it.param.type == RSM_COARSE) ? 0.4 : 0.2;               // :588-602, :759-761
     s_cta[a] = cta;
-    cta += use_flat ? score_flat_ctas(int(it.n_local)) * beam_split
+    cta += use_flat ? score_flat_ctas(int(it.n_local), flat_k) * beam_split
                     : use_patch ? (J.ang_count + score_patch_angles() - 1) / score_patch_angles()
                                 : J.ang_count * J.tiles_x * J.tiles_y * (use_staged ? n_split : beam_split);
     (it.grid->fixed ? any_fixed : any_float) = true;
@@ -856,52 +958,52 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   std::memcpy(up + o_lcta, l_cta.data(), sizeof(int) * (na + 1));
 
   // ---- launch --------------------------------------------------------------------------------
-  char* dn = ctx->h_down.p;
+  char* dn = lane->h_down.p;
   const size_t head_bytes = o_pool - o_best;
   const int pool_first = std::min(pool_cap, std::max(4096, na * 8));
   const bool fork = use_staged && n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
   auto enqueue_score = [&]() -> int {
-    CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(dw + (beam_split > 1 ? zero_begin : o_best), 0, zero_end - (beam_split > 1 ? zero_begin : o_best), ctx->stream));
+    CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dw + (beam_split > 1 ? zero_begin : o_best), 0, zero_end - (beam_split > 1 ? zero_begin : o_best), st));
     {
-      Prof p(ctx, KC_SCORE);
+      Prof p(ctx, KC_SCORE, lane);
       if (use_flat)
-        CU(launch_score_flat(any_fixed, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+        CU(launch_score_flat(any_fixed, flat_k, cta, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                                reinterpret_cast<const int*>(dw + o_scta), na));
       else if (use_patch)
-        CU(launch_score_patch(patch_nxy, cta, ctx->stream, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+        CU(launch_score_patch(patch_nxy, cta, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                               reinterpret_cast<const int*>(dw + o_scta), na));
       else if (use_staged) {
         // the launches cover disjoint angles: the second one goes to a side stream so that its
         // clusters take SMs as soon as CTAs of the first retire (no kernel-boundary drain between them)
-              if (fork) {
-          CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-          CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        if (fork) {
+          CU(cudaEventRecord(lane->ev_fork, st));
+          CU(cudaStreamWaitEvent(lane->stream2, lane->ev_fork, 0));
         }
         for (int l = 0; l < n_launches; ++l) {
           const StagedLaunch& L = launches[l];
-          CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, (fork && l == 1) ? ctx->stream2 : ctx->stream,
+          CU(launch_score_staged(staged_variant, L.split, L.n_cta, L.beams, (fork && l == 1) ? lane->stream2 : st,
                                  reinterpret_cast<const ScoreJob*>(dw + L.jobs_off), reinterpret_cast<const int*>(dw + L.cta_off), L.n_jobs));
         }
         if (fork) {
-          CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
-          CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+          CU(cudaEventRecord(lane->ev_join, lane->stream2));
+          CU(cudaStreamWaitEvent(st, lane->ev_join, 0));
         }
       } else
-        CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, ctx->stream,
+        CU(launch_score(any_fixed, cfg.affine, cfg.lx, cfg.ry, any_fixed ? const_pitch : 0, cta, st,
                         reinterpret_cast<const ScoreJob*>(dw + o_sjobs), reinterpret_cast<const int*>(dw + o_scta), na));
     }
     return RSM_OK;
   };
   auto enqueue_tail = [&]() -> int {
     {
-      Prof p(ctx, KC_SELECT);
-      CU(launch_select(total_sel_cta, ctx->stream, reinterpret_cast<const SelectJob*>(dw + o_ljobs),
+      Prof p(ctx, KC_SELECT, lane);
+      CU(launch_select(total_sel_cta, st, reinterpret_cast<const SelectJob*>(dw + o_ljobs),
                        reinterpret_cast<const int*>(dw + o_lcta), na, reinterpret_cast<PoolEntry*>(dw + o_pool),
                        pool_cap, reinterpret_cast<int*>(dw + o_poolcnt)));
     }
     // read back everything up to the pool, plus a first slice of the pool
-    CU(cudaMemcpyAsync(dn, dw + o_best, head_bytes + size_t(pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(dn, dw + o_best, head_bytes + size_t(pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, st));
     return RSM_OK;
   };
   ctx->stats.h2d_bytes += up_bytes;
@@ -914,13 +1016,13 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (rc) return rc;
     PassItem& it = items[act[0]];
     if (it.n_local > scores_cap) return fail(ctx, RSM_ERR_INVALID, "scores_out too small: need %lld", (long long)it.n_local);
-    CU(cudaMemcpyAsync(scores_out, dw + o_score + it.score_off * 8, size_t(it.n_local) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    rc = sync_stream(ctx);
+    CU(cudaMemcpyAsync(scores_out, dw + o_score + it.score_off * 8, size_t(it.n_local) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(lane->h_down.p, dw + o_err, 4, cudaMemcpyDeviceToHost, st));
+    rc = sync_stream(ctx, lane);
     if (rc) return rc;
     ctx->stats.d2h_bytes += size_t(it.n_local) * 8;
     if (scores_written) *scores_written = it.n_local;
-    int e0; std::memcpy(&e0, ctx->h_down.p, 4);
+    int e0; std::memcpy(&e0, lane->h_down.p, 4);
     if (e0 & kErrWindow) return fail(ctx, RSM_ERR_WINDOW, "search window + scan extent leaves the grid");
     return RSM_OK;
   }
@@ -930,9 +1032,9 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   bool launched = false;
   // (single matches only: that is where the launch sequence is a visible share of the call; a
   //  batch enqueues its few long kernels well ahead of the GPU anyway)
-  if (!ctx->profiling && na <= 8 && std::getenv("RSM_NO_GRAPH") == nullptr) {
+  if (!ctx->profiling && na <= 8 && lane == &ctx->L0 && std::getenv("RSM_NO_GRAPH") == nullptr) {
     std::vector<long long> key = {(long long)(intptr_t)dw, (long long)(intptr_t)up, (long long)(intptr_t)dn, (long long)up_bytes,
-                                  (long long)o_best, (long long)zero_end, use_flat + 2 * (use_patch ? patch_nxy : 0) + 64 * beam_split, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
+                                  (long long)o_best, (long long)zero_end, use_flat * (1 + 8 * flat_k) + 2 * (use_patch ? patch_nxy : 0) + 64 * beam_split, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
                                   total_sel_cta, (long long)o_ljobs, (long long)o_lcta, (long long)o_pool, pool_cap,
                                   (long long)o_poolcnt, (long long)head_bytes, pool_first};
@@ -945,11 +1047,11 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       ctx->graphs.clear();
     }
     rsm_ctx::PassGraph& G = ctx->graphs[key];
-    if (!G.exec && ++G.seen == 2 && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    if (!G.exec && ++G.seen == 2 && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int r = enqueue_score();
       if (r == RSM_OK) r = enqueue_tail();
       cudaGraph_t graph = nullptr;
-      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      const cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (r != RSM_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
         G.exec = nullptr;
         cudaGetLastError();
@@ -957,7 +1059,7 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
       if (graph) cudaGraphDestroy(graph);
     }
     if (G.exec) {
-      CU(cudaGraphLaunch(G.exec, ctx->stream));
+      CU(cudaGraphLaunch(G.exec, st));
       launched = true;
     }
   }
@@ -968,8 +1070,34 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     if (rc) return rc;
   }
   ctx->stats.kernel_launches++;
+  R.pending = true;
+  R.blocking = na > 8;
+  R.o_best = o_best; R.o_err = o_err; R.o_poolcnt = o_poolcnt; R.o_fcnt = o_fcnt; R.o_ftop = o_ftop;
+  R.o_speccols = o_speccols; R.o_spec = o_spec; R.o_pool = o_pool; R.o_gjobs = o_gjobs; R.o_gout = o_gout; R.o_score = o_score;
+  R.head_bytes = head_bytes; R.gather_doubles = gather_doubles; R.pool_first = pool_first; R.pool_cap = pool_cap;
   pt.lap(0);
-  rc = sync_stream(ctx);
+  return RSM_OK;
+}
+
+// ---- wait for the lane, then the host side of the pass -----------------------------------------------
+int pass_end(rsm_ctx* ctx, PassRun& R) {
+  if (!R.pending) return RSM_OK;
+  R.pending = false;
+  PhaseTimer pt(ctx);
+  Lane* lane = R.lane;
+  std::vector<PassItem>& items = *R.items;
+  const std::vector<int>& act = R.act;
+  const int na = int(act.size());
+  const PassMode mode = R.mode;
+  cudaStream_t st = lane->stream;
+  char* dw = lane->d_work.p;
+  char* dn = lane->h_down.p;
+  const size_t o_best = R.o_best, o_err = R.o_err, o_poolcnt = R.o_poolcnt, o_fcnt = R.o_fcnt, o_ftop = R.o_ftop,
+               o_speccols = R.o_speccols, o_spec = R.o_spec, o_pool = R.o_pool, o_gjobs = R.o_gjobs, o_gout = R.o_gout,
+               o_score = R.o_score, head_bytes = R.head_bytes, gather_doubles = R.gather_doubles;
+  const int pool_first = R.pool_first, pool_cap = R.pool_cap;
+  double* scores_out = R.scores_out;
+  int rc = wait_lane(ctx, lane, R.blocking);
   if (rc) return rc;
   ctx->stats.d2h_bytes += head_bytes + size_t(pool_first) * sizeof(PoolEntry);
   const unsigned long long* h_best = reinterpret_cast<const unsigned long long*>(dn);
@@ -985,8 +1113,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   if (pool_count > pool_first) {
     CU(cudaMemcpyAsync(dn + head_bytes + size_t(pool_first) * sizeof(PoolEntry),
                        dw + o_pool + size_t(pool_first) * sizeof(PoolEntry),
-                       size_t(pool_count - pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = sync_stream(ctx);
+                       size_t(pool_count - pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, st));
+    rc = sync_stream(ctx, lane);
     if (rc) return rc;
     ctx->stats.d2h_bytes += size_t(pool_count - pool_first) * sizeof(PoolEntry);
   }
@@ -1023,13 +1151,35 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     it.a_list.clear(); it.top.clear(); it.xy.clear(); it.n_cols = 0;
     if ((h_err[a] & (kErrPoolFull | kErrSelectFull)) || pool_overflow) it.exact = true;
   }
-  const int64_t dummy = 0; (void)dummy;
   for (int e = 0; e < pool_count; ++e) {
     const PoolEntry& pe = h_pool[e];
     PassItem& it = items[act[pe.job]];
     if (it.exact) continue;
     it.a_list.push_back(Cand{pe.score, int64_t(it.a0) * it.geo.n_xy * it.geo.n_xy + pe.index});
   }
+  const bool strict = ctx->strict_ties;
+  // same-(x,y) entries of the gathered columns -> sorted list -> angular covariance; false = exact path needed
+  auto angular_from_columns = [strict](PassItem& it, const double* vals, const int* where) -> bool {
+    const PassGeo& g = it.geo;
+    const double bound = cov_score_bound(it.best);
+    const int nang = it.a1 - it.a0;
+    it.xy.clear();
+    for (int c = 0; c < it.n_cols; ++c)
+      for (int ia = 0; ia < nang; ++ia) {
+        const double s = vals[size_t(where ? where[c] : c) * nang + ia];
+        if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
+      }
+    if (it.xy.size() > size_t(kTopK)) {
+      std::nth_element(it.xy.begin(), it.xy.begin() + kTopK, it.xy.end(), by_score_desc);
+      it.xy.resize(kTopK);
+    }
+    std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
+    if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
+        it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) return false;
+    if (strict && adjacent_tie(it.xy, kMaxVarianceUsePointSize)) return false;
+    angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
+    return true;
+  };
   ctx->pool.run(na, 16, [&](int a_begin, int a_end) {
     for (int a = a_begin; a < a_end; ++a) {
       PassItem& it = items[act[a]];
@@ -1051,6 +1201,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
         // the 20-element prefix is unambiguous unless the 20th and 21st scores tie above the bound
         if (it.top.size() == size_t(kTopK) && it.top[kTopK - 1].score > bound &&
             it.top[kTopK - 1].score == it.top[kTopK - 2].score) { it.exact = true; continue; }
+        // ties inside the prefix keep the set but not the reference's summation order (RSM_OPT_STRICT_TIES)
+        if (strict && adjacent_tie(it.top, positional_prefix(it.top, bound))) { it.exact = true; continue; }
         positional_cov(g, it.param, it.best, it.top.data(), it.top.size(), it.cov);
       }
       if (type == RSM_COARSE || type == RSM_SUPER) {
@@ -1069,7 +1221,6 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
           // covers every same-(x,y) column, else leave n_cols set for the gather round trip
           const int* sc_cols = h_speccols + size_t(a) * (kMaxCols + 1);
           const int nspec = sc_cols[0];
-          const int nang = it.a1 - it.a0;
           int where[kMaxCols];
           bool covered = nspec > 0;
           for (int c = 0; c < it.n_cols && covered; ++c) {
@@ -1078,22 +1229,8 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
             if (where[c] < 0) covered = false;
           }
           if (!covered) continue;
-          const double* vals = h_spec + it.spec_off;
-          it.xy.clear();
-          for (int c = 0; c < it.n_cols; ++c)
-            for (int ia = 0; ia < nang; ++ia) {
-              const double s = vals[size_t(where[c]) * nang + ia];
-              if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
-            }
+          if (!angular_from_columns(it, h_spec + it.spec_off, where)) { it.n_cols = 0; it.exact = true; continue; }
           it.n_cols = 0;   // no round trip needed
-          if (it.xy.size() > size_t(kTopK)) {
-            std::nth_element(it.xy.begin(), it.xy.begin() + kTopK, it.xy.end(), by_score_desc);
-            it.xy.resize(kTopK);
-          }
-          std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
-          if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
-              it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) { it.exact = true; continue; }
-          angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
         }
       }
     }
@@ -1117,38 +1254,21 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   // ---- stage 2: angular covariance from the same-(x,y) columns ---------------------------------
   if (need_gather) {
     const int ng = int(gjobs.size());
-    std::memcpy(ctx->h_up.p, gjobs.data(), sizeof(GatherJob) * ng);
-    CU(cudaMemcpyAsync(dw + o_gjobs, ctx->h_up.p, sizeof(GatherJob) * ng, cudaMemcpyHostToDevice, ctx->stream));
-    CU(launch_gather(ng, ctx->stream, reinterpret_cast<const GatherJob*>(dw + o_gjobs)));
+    std::memcpy(lane->h_up.p, gjobs.data(), sizeof(GatherJob) * ng);
+    CU(cudaMemcpyAsync(dw + o_gjobs, lane->h_up.p, sizeof(GatherJob) * ng, cudaMemcpyHostToDevice, st));
+    CU(launch_gather(ng, st, reinterpret_cast<const GatherJob*>(dw + o_gjobs)));
     ctx->stats.kernel_launches++;
-    CU(cudaMemcpyAsync(ctx->h_down.p, dw + o_gout, gather_doubles * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    rc = sync_stream(ctx);
+    CU(cudaMemcpyAsync(lane->h_down.p, dw + o_gout, gather_doubles * 8, cudaMemcpyDeviceToHost, st));
+    rc = sync_stream(ctx, lane);
     if (rc) return rc;
     ctx->stats.h2d_bytes += sizeof(GatherJob) * ng;
     ctx->stats.d2h_bytes += gather_doubles * 8;
     pt.lap(3);
-    const double* h_g = reinterpret_cast<const double*>(ctx->h_down.p);
+    const double* h_g = reinterpret_cast<const double*>(lane->h_down.p);
     ctx->pool.run(ng, 16, [&](int g_begin, int g_end) {
       for (int gi = g_begin; gi < g_end; ++gi) {
         PassItem& it = items[gitem[gi]];
-        const PassGeo& g = it.geo;
-        const double bound = cov_score_bound(it.best);
-        const int nang = it.a1 - it.a0;
-        const double* col = h_g + it.gather_off;
-        it.xy.clear();
-        for (int c = 0; c < it.n_cols; ++c)
-          for (int ia = 0; ia < nang; ++ia) {
-            const double s = col[size_t(c) * nang + ia];
-            if (s >= bound) it.xy.push_back(Cand{s, (int64_t(it.a0 + ia) * g.n_xy * g.n_xy) + it.cols[c]});
-          }
-        if (it.xy.size() > size_t(kTopK)) {
-          std::nth_element(it.xy.begin(), it.xy.begin() + kTopK, it.xy.end(), by_score_desc);
-          it.xy.resize(kTopK);
-        }
-        std::sort(it.xy.begin(), it.xy.end(), by_score_desc);
-        if (it.xy.size() > size_t(kMaxVarianceUsePointSize) &&
-            it.xy[kMaxVarianceUsePointSize].score == it.xy[kMaxVarianceUsePointSize - 1].score) { it.exact = true; continue; }
-        angular_cov(g, it.param, it.best, it.xy.data(), it.xy.size(), it.cov);
+        if (!angular_from_columns(it, h_g + it.gather_off, nullptr)) it.exact = true;
       }
     });
   }
@@ -1161,15 +1281,15 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
     for (int a = 0; a < na; ++a)
       if (items[act[a]].exact) { ex.push_back(act[a]); ex_off.push_back(ex_doubles); ex_doubles += size_t(items[act[a]].n_local); }
     if (!ex.empty()) {
-      rc = ensure_pinned(ctx, ctx->h_down, ex_doubles * 8);
+      rc = ensure_pinned(ctx, lane->h_down, ex_doubles * 8, st);
       if (rc) return rc;
-      double* h_sc = reinterpret_cast<double*>(ctx->h_down.p);
+      double* h_sc = reinterpret_cast<double*>(lane->h_down.p);
       for (size_t i = 0; i < ex.size(); ++i) {
         const PassItem& it = items[ex[i]];
         CU(cudaMemcpyAsync(h_sc + ex_off[i], dw + o_score + it.score_off * 8, size_t(it.n_local) * 8,
-                           cudaMemcpyDeviceToHost, ctx->stream));
+                           cudaMemcpyDeviceToHost, st));
       }
-      rc = sync_stream(ctx);
+      rc = sync_stream(ctx, lane);
       if (rc) return rc;
       ctx->stats.d2h_bytes += ex_doubles * 8;
       ctx->pool.run(int(ex.size()), 1, [&](int i0, int i1) {
@@ -1202,6 +1322,41 @@ int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* 
   return RSM_OK;
 }
 
+// groups of the active items that share a kernel plan, in first-appearance order
+std::vector<std::vector<int>> plan_groups(const std::vector<PassItem>& items, const std::vector<int>& act) {
+  std::vector<std::vector<int>> groups;
+  for (int i : act) {
+    bool placed = false;
+    for (auto& g : groups) if (same_plan(items[g[0]], items[i])) { g.push_back(i); placed = true; break; }
+    if (!placed) groups.push_back(std::vector<int>{i});
+  }
+  return groups;
+}
+
+// One pass over a batch of items on the context's own lane.
+int run_pass(rsm_ctx* ctx, std::vector<PassItem>& items, PassMode mode, double* scores_out,
+             int64_t scores_cap, int64_t* scores_written) {
+  std::vector<int> act;
+  int rc = pass_geometry(ctx, items, act);
+  if (rc) return rc;
+  if (scores_written) *scores_written = 0;
+  if (act.empty()) return RSM_OK;
+  if (mode != MODE_MATCH) {       // single-item modes
+    PassRun R;
+    rc = pass_begin(ctx, &ctx->L0, items, std::vector<int>{act[0]}, mode, scores_out, scores_cap, scores_written, R);
+    if (rc) return rc;
+    return pass_end(ctx, R);
+  }
+  for (const auto& g : plan_groups(items, act)) {
+    PassRun R;
+    rc = pass_begin(ctx, &ctx->L0, items, g, mode, nullptr, 0, nullptr, R);
+    if (rc) return rc;
+    rc = pass_end(ctx, R);
+    if (rc) return rc;
+  }
+  return RSM_OK;
+}
+
 int upload_points(rsm_ctx* ctx, const double* pts_xy, size_t n_points, double** d_out) {
   const size_t bytes = n_points * 16;
   int rc = ensure_dev(ctx, ctx->d_pts, bytes);
@@ -1212,26 +1367,104 @@ int upload_points(rsm_ctx* ctx, const double* pts_xy, size_t n_points, double** 
   return RSM_OK;
 }
 
-// the coarse -> fine -> super-fine chain over a batch (scan_matchers.h:224-263, 281)
+// How many sub-batches (lanes) a batched chain of n items is cut into.  Each sub-batch must still fill the GPU
+// by itself for most of a kernel (a coarse pass of 128 chains is ~4 waves of the patch kernel's CTAs).
+int chain_lanes(const rsm_ctx* ctx, int n) {
+  int lanes = ctx->lanes_wanted;
+  if (const char* e = std::getenv("RSM_LANES")) lanes = std::atoi(e);
+  if (lanes <= 0) lanes = n >= 384 ? 4 : n >= 192 ? 3 : n >= 64 ? 2 : 1;
+  return std::max(1, std::min({lanes, 8, n}));
+}
+
+// The coarse -> fine -> super-fine chain over a batch (scan_matchers.h:224-263, 281), software-pipelined: the
+// items are cut into contiguous sub-batches, one lane (stream + buffers) each; while the host finalises pass k of
+// one sub-batch and prepares its pass k+1, the kernels of the other sub-batches run.  `pre(lane, first, count)`
+// (optional) enqueues work a sub-batch's first pass depends on -- the grid rasterisation of the batched back-end
+// step -- on that lane's stream.
 int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* d_pts, const int* n_pts,
               const rsm_pass_param* params, bool shared_params, bool use_fine, double* poses, double* covs,
-              double* scores, double* responses) {
+              double* scores, double* responses, const std::function<int(Lane*, int, int)>* pre = nullptr) {
   std::vector<PassItem> items(n);
   std::vector<double> sum(n, 0.0);
   const int n_pass = use_fine ? 3 : 1;
-  for (int pass = 0; pass < n_pass; ++pass) {
-    for (int i = 0; i < n; ++i) {
-      PassItem& it = items[i];
-      it.grid = grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
-      it.param = params[(shared_params ? 0 : 3 * i) + pass];
-      it.pose_world = poses + 3 * i; it.cov = covs + 9 * i;
-      it.ang_begin = 0; it.ang_end = -1;
-    }
-    int rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
-    if (rc) return rc;
+  auto set_pass = [&](int i, int pass) {
+    PassItem& it = items[i];
+    it.grid = grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
+    it.param = params[(shared_params ? 0 : 3 * i) + pass];
+    it.pose_world = poses + 3 * i; it.cov = covs + 9 * i;
+    it.ang_begin = 0; it.ang_end = -1;
+  };
+  auto account = [&](int pass) {
     for (int i = 0; i < n; ++i) {
       sum[i] += items[i].response;
       if (responses) responses[3 * i + pass] = items[i].response;
+    }
+  };
+  int n_lanes = chain_lanes(ctx, n);
+  // the lanes' launches assume one kernel plan per sub-batch: same parameters and the same kind of grid for every item
+  const rsm_grid* g0 = nullptr;
+  for (int i = 0; i < n && n_lanes > 1; ++i) {
+    if (!grids[i]) continue;
+    if (!g0) g0 = grids[i];
+    else if (grids[i]->scale != g0->scale || grids[i]->fixed != g0->fixed) n_lanes = 1;
+  }
+  if (n_lanes <= 1 || !shared_params) {
+    // one lane (small batches), or windows that may differ from item to item: pass after pass, grouped by plan
+    if (pre) { int rc = (*pre)(&ctx->L0, 0, n); if (rc) return rc; }
+    for (int pass = 0; pass < n_pass; ++pass) {
+      for (int i = 0; i < n; ++i) set_pass(i, pass);
+      int rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+      if (rc) return rc;
+      account(pass);
+    }
+  } else {
+    struct Sub { Lane* lane; int first, count; std::vector<PassItem> items; PassRun run; };
+    std::vector<Sub> subs(n_lanes);
+    auto begin_pass = [&](Sub& S, int pass) -> int {
+      for (int k = 0; k < S.count; ++k) { set_pass(S.first + k, pass); S.items[k] = items[S.first + k]; }
+      std::vector<int> act;
+      int rc = pass_geometry(ctx, S.items, act);
+      if (rc) return rc;
+      return pass_begin(ctx, S.lane, S.items, act, MODE_MATCH, nullptr, 0, nullptr, S.run);
+    };
+    int rc_all = RSM_OK;
+    for (int l = 0; l < n_lanes && rc_all == RSM_OK; ++l) {
+      Sub& S = subs[l];
+      S.first = int((long long)n * l / n_lanes);
+      S.count = int((long long)n * (l + 1) / n_lanes) - S.first;
+      S.items.resize(S.count);
+      rc_all = get_lane(ctx, l, &S.lane);
+      // lanes 1.. must see what the caller enqueued on the context's stream (point uploads, grid writes)
+      if (rc_all == RSM_OK && l > 0) {
+        if (cudaEventRecord(ctx->L0.ev_fork, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(S.lane->stream, ctx->L0.ev_fork, 0) != cudaSuccess)
+          rc_all = fail(ctx, RSM_ERR_CUDA, "lane fork failed");
+      }
+      if (rc_all == RSM_OK && pre) rc_all = (*pre)(S.lane, S.first, S.count);
+      if (rc_all == RSM_OK) rc_all = begin_pass(S, 0);
+    }
+    for (int pass = 0; pass < n_pass && rc_all == RSM_OK; ++pass) {
+      for (int l = 0; l < n_lanes && rc_all == RSM_OK; ++l) {
+        Sub& S = subs[l];
+        rc_all = pass_end(ctx, S.run);
+        if (rc_all) break;
+        for (int k = 0; k < S.count; ++k) {
+          items[S.first + k].response = S.items[k].response;
+          sum[S.first + k] += S.items[k].response;
+          if (responses) responses[3 * (S.first + k) + pass] = S.items[k].response;
+        }
+        if (pass + 1 < n_pass) rc_all = begin_pass(S, pass + 1);
+      }
+    }
+    if (rc_all != RSM_OK) {
+      // leave no launch in flight that reads this call's buffers
+      for (int l = 0; l < n_lanes; ++l) if (subs[l].lane) cudaStreamSynchronize(subs[l].lane->stream);
+      return rc_all;
+    }
+    // the context's stream continues after every lane (later calls on it may rewrite the grids / points)
+    for (int l = 1; l < n_lanes; ++l) {
+      if (cudaEventRecord(subs[l].lane->ev_join, subs[l].lane->stream) != cudaSuccess ||
+          cudaStreamWaitEvent(ctx->stream, subs[l].lane->ev_join, 0) != cudaSuccess)
+        return fail(ctx, RSM_ERR_CUDA, "lane join failed");
     }
   }
   for (int i = 0; i < n; ++i) {
@@ -1333,11 +1566,14 @@ int rsm_create(int device, rsm_ctx** out) {
   rsm_ctx* ctx = new rsm_ctx;
   std::memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+  Lane& L = ctx->L0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&L.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L.done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->t0) != cudaSuccess || cudaEventCreate(&ctx->t1) != cudaSuccess) {
+    destroy_lane(L);
     delete ctx;
     return RSM_ERR_CUDA;
   }
@@ -1349,22 +1585,27 @@ void rsm_destroy(rsm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  Buf* dev[] = {&ctx->d_work, &ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids};
+  for (Lane* L : ctx->extra_lanes) { cudaStreamSynchronize(L->stream); destroy_lane(*L); delete L; }
+  Buf* dev[] = {&ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids};
   for (Buf* b : dev) if (b->p) cudaFree(b->p);
-  if (ctx->h_up.p) cudaFreeHost(ctx->h_up.p);
-  if (ctx->h_down.p) cudaFreeHost(ctx->h_down.p);
   for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
-  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
-  cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
-  cudaStreamDestroy(ctx->stream2);
-  cudaStreamDestroy(ctx->stream);
+  destroy_lane(ctx->L0);
   delete ctx;
 }
 
 const char* rsm_last_error(const rsm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int rsm_set_profiling(rsm_ctx* ctx, int on) { if (!ctx) return RSM_ERR_INVALID; ctx->profiling = on != 0; return RSM_OK; }
+int rsm_set_option(rsm_ctx* ctx, int option, int value) {
+  if (!ctx) return RSM_ERR_INVALID;
+  switch (option) {
+    case RSM_OPT_STRICT_TIES: ctx->strict_ties = value != 0; return RSM_OK;
+    case RSM_OPT_LANES: if (value < 0 || value > 8) break; ctx->lanes_wanted = value; return RSM_OK;
+    default: break;
+  }
+  return fail(ctx, RSM_ERR_INVALID, "rsm_set_option: unknown option %d or value %d out of range", option, value);
+}
 int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out) { if (!ctx || !out) return RSM_ERR_INVALID; *out = ctx->stats; return RSM_OK; }
 int rsm_reset_stats(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; std::memset(&ctx->stats, 0, sizeof ctx->stats); return RSM_OK; }
 int rsm_synchronize(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; DeviceGuard device_guard(ctx); return sync_stream(ctx); }
@@ -1554,6 +1795,7 @@ int blur_kernel(double sigma, double resolution, std::vector<double>& k) {
 
 struct RasterPlan {
   bool fixed = true;
+  bool blur = true;      // false: SET_CELL_OCCUPIED (use_blur off, or blur parameters the reference rejects)
   int half = 0, one = 0, fill = 0;
   std::vector<int> stamp;
 };
@@ -1561,17 +1803,27 @@ struct RasterPlan {
 // Decide the cell representation for a rasterised grid and build the stamp patterns.
 int plan_raster(rsm_ctx* ctx, float default_prob, double sigma, double resolution, double occu_offset, int use_blur, RasterPlan& pl) {
   std::vector<double> k;
-  const int half = blur_kernel(sigma, resolution, k);
-  if (!use_blur || half < 0)
-    return fail(ctx, RSM_ERR_UNSUPPORTED, "only the blur (SET_CELL_OCCUPIED_BLUR) construction path is provided");
+  int half = blur_kernel(sigma, resolution, k);
+  if (!(default_prob >= 0.0f)) return fail(ctx, RSM_ERR_INVALID, "default_prob must be >= 0");
+  // GaussianBlur rejected the parameters: half_kernel_size_ = 0 and UpdateMapByRange drops use_blur (occu_grid_map.h:47-59, 265-268)
+  if (half < 0) { half = 0; use_blur = 0; }
   pl.half = half;
+  pl.blur = use_blur != 0;
+  int tmp;
+  const float onef = 1.0f;
+  if (!pl.blur) {
+    // every value SetCellOccu can write is fl(v + 0.5f) clamped to 1: a 2^-25 multiple whenever v is one
+    pl.fixed = fix_ok(default_prob, &tmp);
+    pl.stamp.assign(1, 0);
+    if (pl.fixed) { pl.one = kFixOne; fix_ok(default_prob, &pl.fill); }
+    else { std::memcpy(&pl.one, &onef, 4); std::memcpy(&pl.fill, &default_prob, 4); }
+    return RSM_OK;
+  }
   const int ks = 2 * half + 1;
   std::vector<float> probs(size_t(ks) * ks);
   for (size_t i = 0; i < probs.size(); ++i) probs[i] = static_cast<float>(k[i] * occu_offset);   // :567
-  int tmp;
   bool fixed = fix_ok(default_prob, &tmp);
   for (float p : probs) if (p <= 1.0f && !(p >= 0.0f && fix_ok(p, &tmp))) fixed = false;
-  if (!(default_prob >= 0.0f)) return fail(ctx, RSM_ERR_INVALID, "default_prob must be >= 0");
   pl.fixed = fixed;
   pl.stamp.assign(probs.size(), 0);
   for (size_t i = 0; i < probs.size(); ++i) {
@@ -1579,10 +1831,17 @@ int plan_raster(rsm_ctx* ctx, float default_prob, double sigma, double resolutio
     if (!(p <= 1.0f) || !(p > 0.0f)) continue;   // prob > 1 is ignored by SetGridProbability; <= 0 never raises a cell
     if (fixed) fix_ok(p, &pl.stamp[i]); else std::memcpy(&pl.stamp[i], &p, 4);
   }
-  const float onef = 1.0f;
   if (fixed) { pl.one = kFixOne; fix_ok(default_prob, &pl.fill); }
   else { std::memcpy(&pl.one, &onef, 4); std::memcpy(&pl.fill, &default_prob, 4); }
   return RSM_OK;
+}
+
+// Stamp n_scans scans (device descriptors at d_scans) on stream st: blur = max-compositing, one CTA per scan in any
+// order; non-blur = one CTA per grid (scans [group_begin[g], group_begin[g+1]) in order; d_groups on the device).
+cudaError_t enqueue_raster(const RasterPlan& pl, cudaStream_t st, int n_scans, const RasterScan* d_scans, const int* d_stamp,
+                           int n_groups, const int* d_groups) {
+  if (pl.blur) return launch_raster(n_scans, st, d_scans, d_stamp, pl.half, pl.one);
+  return launch_raster_occu(n_groups, st, d_scans, d_groups, pl.half, pl.fixed ? 1 : 0);
 }
 
 // Fill the RasterScan of one base scan (host libm cos/sin = Eigen::Rotation2Dd, occu_grid_map.h:278-303)
@@ -1616,6 +1875,7 @@ int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double 
   const size_t o_fill = dl.take(sizeof(FillJob));
   const size_t o_scans = dl.take(sizeof(RasterScan) * std::max(1, n_scans));
   const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t o_groups = dl.take(2 * sizeof(int), 4);
   const size_t up_bytes = dl.off;
   rc = ensure_dev(ctx, ctx->d_work, dl.off);
   if (rc) return rc;
@@ -1634,13 +1894,16 @@ int rsm_grid_rasterize(rsm_ctx* ctx, rsm_grid* grid, float default_prob, double 
     off += n_pts[s];
   }
   std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  const int groups[2] = {0, n_scans};
+  std::memcpy(up + o_groups, groups, sizeof groups);
   CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += up_bytes;
   {
     Prof p(ctx, KC_RASTER);
     CU(launch_fill(1, 148, ctx->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
-    CU(launch_raster(n_scans, ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scans),
-                     reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+    if (n_scans > 0)
+      CU(enqueue_raster(pl, ctx->stream, n_scans, reinterpret_cast<const RasterScan*>(dw + o_scans),
+                        reinterpret_cast<const int*>(dw + o_stamp), 1, reinterpret_cast<const int*>(dw + o_groups)));
   }
   ctx->stats.kernel_launches += (n_scans > 0) ? 2 : 1;
   rc = sync_stream(ctx);
@@ -1684,8 +1947,9 @@ int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double 
   // the stamp patterns depend on the map's cell representation, which the fill / upload decided
   int rc = plan_raster(ctx, 0.5f, sigma, grid->resolution, occu_offset, use_blur, pl);
   if (rc) return rc;
+  if (!pl.blur) pl.fixed = grid->fixed;     // SetCellOccu works on either cell representation
   if (grid->fixed && !pl.fixed) return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_grid_update_by_range: the blur levels are not 2^-25 multiples but the map is held in fixed point");
-  if (!grid->fixed && pl.fixed) {     // float map: the same stamps as float patterns
+  if (pl.blur && !grid->fixed && pl.fixed) {     // float map: the same stamps as float patterns
     std::vector<double> k;
     blur_kernel(sigma, grid->resolution, k);
     for (size_t i = 0; i < pl.stamp.size(); ++i) {
@@ -1700,6 +1964,7 @@ int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double 
   Layout dl;
   const size_t o_scan = dl.take(sizeof(RasterScan));
   const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t o_groups = dl.take(2 * sizeof(int), 4);
   const size_t up_bytes = dl.off;
   rc = ensure_dev(ctx, ctx->d_work, dl.off);
   if (rc) return rc;
@@ -1711,11 +1976,14 @@ int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double 
   char* dw = ctx->d_work.p;
   make_raster_scan(grid, pose_world, d_pts, n_pts, *reinterpret_cast<RasterScan*>(up + o_scan));
   std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  const int groups[2] = {0, 1};
+  std::memcpy(up + o_groups, groups, sizeof groups);
   CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += up_bytes;
   {
     Prof p(ctx, KC_RASTER);
-    CU(launch_raster(1, ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scan), reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+    CU(enqueue_raster(pl, ctx->stream, 1, reinterpret_cast<const RasterScan*>(dw + o_scan), reinterpret_cast<const int*>(dw + o_stamp),
+                      1, reinterpret_cast<const int*>(dw + o_groups)));
   }
   ctx->stats.kernel_launches++;
   rc = sync_stream(ctx);
@@ -1928,6 +2196,7 @@ int rsm_grid_rebuild(rsm_ctx* ctx, rsm_grid* grid, const rsm_scan_store* store, 
   const size_t o_fill = dl.take(sizeof(FillJob));
   const size_t o_scans = dl.take(sizeof(RasterScan) * std::max(1, n));
   const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+  const size_t o_groups = dl.take(2 * sizeof(int), 4);
   const size_t up_bytes = dl.off;
   rc = ensure_dev(ctx, ctx->d_work, dl.off);
   if (rc) return rc;
@@ -1943,12 +2212,16 @@ int rsm_grid_rebuild(rsm_ctx* ctx, rsm_grid* grid, const rsm_scan_store* store, 
     make_raster_scan(grid, E.pose, E.d_pts, E.n, hs[i]);
   }
   std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+  const int groups[2] = {0, n};
+  std::memcpy(up + o_groups, groups, sizeof groups);
   CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += up_bytes;
   {
     Prof p(ctx, KC_RASTER);
     CU(launch_fill(1, 148, ctx->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
-    CU(launch_raster(n, ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scans), reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
+    if (n > 0)
+      CU(enqueue_raster(pl, ctx->stream, n, reinterpret_cast<const RasterScan*>(dw + o_scans), reinterpret_cast<const int*>(dw + o_stamp),
+                        1, reinterpret_cast<const int*>(dw + o_groups)));
   }
   ctx->stats.kernel_launches += (n > 0) ? 2 : 1;
   rc = sync_stream(ctx);
@@ -2223,6 +2496,8 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
                       const rsm_grid* pub_map, const double* const* pub_pts, const int32_t* pub_counts,
                       const rsm_map_check_param* check) {
   RasterPlan pl;
+  // use_blur = true as in both shipped configurations; blur parameters the reference's GaussianBlur rejects select the
+  // SET_CELL_OCCUPIED update, as there (map/occu_grid_map.h:265-268)
   int rc = plan_raster(ctx, default_prob, sigma, resolution, occu_offset, 1, pl);
   if (rc) return rc;
   // grids: one pool, one slot per pair
@@ -2248,40 +2523,52 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
     g.init = scan_offset[i + 1] > scan_offset[i];
     gp[i] = &g;
   }
-  const int64_t n_base_scans = scan_offset[n];
-  // raster descriptors
-  Layout dl;
-  const size_t o_fill = dl.take(sizeof(FillJob) * n);
-  const size_t o_scans = dl.take(sizeof(RasterScan) * std::max<int64_t>(1, n_base_scans));
-  const size_t o_stamp = dl.take(pl.stamp.size() * 4);
-  const size_t up_bytes = dl.off;
-  rc = ensure_dev(ctx, ctx->d_work, dl.off);
-  if (rc) return rc;
-  rc = ensure_pinned(ctx, ctx->h_up, up_bytes);
-  if (rc) return rc;
-  char* up = ctx->h_up.p;
-  char* dw = ctx->d_work.p;
-  FillJob* hf = reinterpret_cast<FillJob*>(up + o_fill);
-  RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
-  for (int i = 0; i < n; ++i) {
-    hf[i].grid = gs[i].d_cells; hf[i].n_cells = (long long)cells; hf[i].value = pl.fill;
-    for (int64_t s = scan_offset[i]; s < scan_offset[i + 1]; ++s)
-      make_raster_scan(&gs[i], base[s].pose_world, base[s].d_pts, base[s].n, hs[s]);
-  }
-  std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
-  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->stats.h2d_bytes += up_bytes;
-  {
-    Prof p(ctx, KC_RASTER);
-    CU(launch_fill(n, 4, ctx->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
-    CU(launch_raster(int(n_base_scans), ctx->stream, reinterpret_cast<const RasterScan*>(dw + o_scans),
-                     reinterpret_cast<const int*>(dw + o_stamp), pl.half, pl.one));
-  }
-  ctx->stats.kernel_launches += 2;
-  // run_pass reuses d_work and the pinned staging: the raster launches above must have consumed them first
-  rc = sync_stream(ctx);
-  if (rc) return rc;
-  rc = run_chain(ctx, n, gp.data(), dp, np, params, true, use_fine, poses_world, covs, scores, responses);
+  // Reset + stamp the grids of pairs [first, first + count) on a lane's stream, ahead of that sub-batch's first pass
+  // (the descriptors live in the lane's own aux buffers: the pass preparation reuses the work arena right away)
+  const std::function<int(Lane*, int, int)> pre = [&](Lane* L, int first, int count) -> int {
+    const int64_t s0 = scan_offset[first], s1 = scan_offset[first + count];
+    Layout dl;
+    const size_t o_fill = dl.take(sizeof(FillJob) * size_t(count));
+    const size_t o_scans = dl.take(sizeof(RasterScan) * size_t(std::max<int64_t>(1, s1 - s0)));
+    const size_t o_stamp = dl.take(pl.stamp.size() * 4);
+    const size_t o_groups = dl.take(sizeof(int) * size_t(count + 1), 4);
+    const size_t up_bytes = dl.off;
+    int rc2 = ensure_dev(ctx, L->d_aux, dl.off, L->stream);
+    if (rc2) return rc2;
+    rc2 = ensure_pinned(ctx, L->h_aux, up_bytes, L->stream);
+    if (rc2) return rc2;
+    char* up = L->h_aux.p;
+    char* dw = L->d_aux.p;
+    FillJob* hf = reinterpret_cast<FillJob*>(up + o_fill);
+    RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
+    int* hg = reinterpret_cast<int*>(up + o_groups);
+    for (int k = 0; k < count; ++k) {
+      const int i = first + k;
+      hf[k].grid = gs[i].d_cells; hf[k].n_cells = (long long)cells; hf[k].value = pl.fill;
+      hg[k] = int(scan_offset[i] - s0);
+    }
+    hg[count] = int(s1 - s0);
+    ctx->pool.run(count, 32, [&](int k0, int k1) {
+      for (int k = k0; k < k1; ++k) {
+        const int i = first + k;
+        for (int64_t sidx = scan_offset[i]; sidx < scan_offset[i + 1]; ++sidx)
+          make_raster_scan(&gs[i], base[sidx].pose_world, base[sidx].d_pts, base[sidx].n, hs[sidx - s0]);
+      }
+    });
+    std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
+    CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, L->stream));
+    ctx->stats.h2d_bytes += up_bytes;
+    {
+      Prof p(ctx, KC_RASTER, L);
+      CU(launch_fill(count, 4, L->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
+      if (s1 > s0)
+        CU(enqueue_raster(pl, L->stream, int(s1 - s0), reinterpret_cast<const RasterScan*>(dw + o_scans),
+                          reinterpret_cast<const int*>(dw + o_stamp), count, reinterpret_cast<const int*>(dw + o_groups)));
+    }
+    ctx->stats.kernel_launches += 2;
+    return RSM_OK;
+  };
+  rc = run_chain(ctx, n, gp.data(), dp, np, params, true, use_fine, poses_world, covs, scores, responses, &pre);
   if (rc || !pub_map) return rc;
   // MapCheckPenalize(pub_map_range_data, best_pose, true) on the matched poses (slam_processor.cpp:313-317)
   std::vector<double> coeff(n);
@@ -2757,18 +3044,21 @@ int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, 
     return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: bad arguments");
   SliceState& S = ctx->slice;
   if (!S.valid || !S.merged) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: call rsm_match_partial and rsm_match_merge first");
-  S.valid = false;
   *response = 0.0;
   if (detail) std::memset(detail, 0, sizeof *detail);
-  if (S.exact_needed)
-    return fail(ctx, RSM_ERR_UNSUPPORTED, "exact score ties in the consumed candidate sets: rerun this match unsliced (rsm_match)");
+  // exact ties in a consumed set: the slice stays valid for rsm_match_slice_scores / rsm_match_finish_exact
+  const char* need_exact = "exact score ties in the consumed candidate sets: gather the slices (rsm_match_slice_scores) and call rsm_match_finish_exact";
+  if (S.exact_needed) return fail(ctx, RSM_NEED_EXACT, "%s", need_exact);
   const PassGeo& g = S.geo;
   const int type = S.param.type;
   const double bound = cov_score_bound(S.best);
+  double cov_new[9];
+  std::memcpy(cov_new, cov, sizeof cov_new);
   if (type == RSM_COARSE || type == RSM_FINE) {
     if (S.top.size() == size_t(kTopK) && S.top[kTopK - 1].score > bound && S.top[kTopK - 1].score == S.top[kTopK - 2].score)
-      return fail(ctx, RSM_ERR_UNSUPPORTED, "exact score tie at the covariance cut: rerun this match unsliced (rsm_match)");
-    positional_cov(g, S.param, S.best, S.top.data(), S.top.size(), cov);
+      return fail(ctx, RSM_NEED_EXACT, "%s", need_exact);
+    if (ctx->strict_ties && adjacent_tie(S.top, positional_prefix(S.top, bound))) return fail(ctx, RSM_NEED_EXACT, "%s", need_exact);
+    positional_cov(g, S.param, S.best, S.top.data(), S.top.size(), cov_new);
   }
   if (type == RSM_COARSE || type == RSM_SUPER) {
     std::vector<Cand> xy;
@@ -2788,10 +3078,13 @@ int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, 
       if (xy.size() > size_t(kTopK)) { std::nth_element(xy.begin(), xy.begin() + kTopK, xy.end(), by_score_desc); xy.resize(kTopK); }
       std::sort(xy.begin(), xy.end(), by_score_desc);
       if (xy.size() > size_t(kMaxVarianceUsePointSize) && xy[kMaxVarianceUsePointSize].score == xy[kMaxVarianceUsePointSize - 1].score)
-        return fail(ctx, RSM_ERR_UNSUPPORTED, "exact score tie at the angular covariance cut: rerun this match unsliced (rsm_match)");
+        return fail(ctx, RSM_NEED_EXACT, "%s", need_exact);
+      if (ctx->strict_ties && adjacent_tie(xy, kMaxVarianceUsePointSize)) return fail(ctx, RSM_NEED_EXACT, "%s", need_exact);
     }
-    angular_cov(g, S.param, S.best, xy.data(), xy.size(), cov);
+    angular_cov(g, S.param, S.best, xy.data(), xy.size(), cov_new);
   }
+  S.valid = false;
+  std::memcpy(cov, cov_new, sizeof cov_new);
   const double bs = S.best.score;
   *response = bs > 1.0 ? 1.0 : bs;
   rsm_pass_detail d;
@@ -2807,6 +3100,67 @@ int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, 
   }
   if (detail) *detail = d;
   ctx->stats.passes++;
+  return RSM_OK;
+}
+
+int rsm_match_slice_scores(rsm_ctx* ctx, double* scores_out, int64_t capacity, int64_t* n_slice) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !n_slice || capacity < 0 || (capacity > 0 && !scores_out)) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: bad arguments");
+  SliceState& S = ctx->slice;
+  if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: no rsm_match_partial pending on this context");
+  const int64_t n = int64_t(S.a1 - S.a0) * S.geo.n_xy * S.geo.n_xy;
+  *n_slice = n;
+  if (capacity == 0 || n == 0) return RSM_OK;
+  if (capacity < n) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: need room for %lld scores", (long long)n);
+  CU(cudaMemcpyAsync(scores_out, S.d_score, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.d2h_bytes += size_t(n) * 8;
+  return RSM_OK;
+}
+
+int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int64_t* counts, int n_slices, double pose_world[3],
+                           double cov[9], double* response, rsm_pass_detail* detail) {
+  if (!ctx || !slices || !counts || n_slices < 1 || !pose_world || !cov || !response)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: bad arguments");
+  SliceState& S = ctx->slice;
+  if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: no rsm_match_partial pending on this context");
+  const PassGeo& g = S.geo;
+  int64_t total = 0;
+  for (int r = 0; r < n_slices; ++r) {
+    if (counts[r] < 0 || (counts[r] > 0 && !slices[r]) || counts[r] % (int64_t(g.n_xy) * g.n_xy) != 0)
+      return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: slice %d is not a whole number of angles", r);
+    total += counts[r];
+  }
+  if (total != g.n_cand()) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: the slices hold %lld scores, the window has %lld candidates",
+                                       (long long)total, (long long)g.n_cand());
+  *response = 0.0;
+  if (detail) std::memset(detail, 0, sizeof *detail);
+  // the reference's own sort on the whole candidate array (correlate_scan_matcher.h:607-608), in its candidate order
+  std::vector<Cand> c;
+  c.resize(static_cast<size_t>(total));
+  int64_t k = 0;
+  for (int r = 0; r < n_slices; ++r)
+    for (int64_t i = 0; i < counts[r]; ++i, ++k) { c[k].score = slices[r][i]; c[k].index = k; }
+  BestPose best;
+  finish_exact_core(g, S.param, c, best, cov);
+  S.valid = false;
+  const double bs = best.score;
+  *response = bs > 1.0 ? 1.0 : bs;
+  rsm_pass_detail d;
+  std::memset(&d, 0, sizeof d);
+  d.best_score = bs;
+  d.best_pose_map[0] = best.x; d.best_pose_map[1] = best.y; d.best_pose_map[2] = best.angle;
+  d.n_candidates = g.n_cand(); d.n_avg = best.n_avg; d.exact_sort_used = 1;
+  d.n_ang = g.n_ang; d.n_xy = g.n_xy; d.visited = g.visited; d.divisor = g.divisor;
+  if (*response > S.param.response_threshold) {
+    const double b[3] = {best.x, best.y, best.angle};
+    S.grid->tf.map_to_world(b, pose_world);
+    d.pose_updated = 1;
+  }
+  if (detail) *detail = d;
+  ctx->stats.passes++;
+  ctx->stats.exact_sort_passes++;
   return RSM_OK;
 }
 

@@ -22,6 +22,8 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 #include <cuda_runtime.h>
 #include <limits.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include "rsm_device.h"
@@ -367,14 +369,15 @@ extern "C" int rsm_debug_select(unsigned long long* out) {
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count) {
   const size_t smem = size_t(kSelectSlice) * 8;
-  static bool configured[kMaxDevices] = {false};   // function attributes are per device
+  // function attributes are per device; contexts of different caller threads may get here at the same time
+  static std::atomic<bool> configured[kMaxDevices];
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-  if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (!configured[dev].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // idempotent
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   select_kernel<<<n_cta, kSelectThreads, smem, st>>>(jobs, cta_begin, n_jobs, pool, pool_cap, pool_count);
   return cudaGetLastError();
@@ -470,6 +473,53 @@ raster_kernel(const RasterScan* __restrict__ scans, const int* __restrict__ stam
 cudaError_t launch_raster(int n_scans, cudaStream_t st, const RasterScan* scans, const int* stamp, int half, int one) {
   if (n_scans == 0) return cudaSuccess;
   raster_kernel<<<n_scans, 256, 0, st>>>(scans, stamp, half, one);
+  return cudaGetLastError();
+}
+
+// SET_CELL_OCCUPIED (UpdateMapByRange with use_blur false, or blur parameters the reference rejects): SetCellOccu
+// (map/occu_grid_map.h:499-516) adds ProbabilityCellFunctions' update_occu_factor_ (0.5f, map/grid_map_cell.h:333-342),
+// clamped to 1, ONCE per cell and update -- the reference guards with the cell's update_index_.  That is not a maximum,
+// so the scans of one grid are applied one after the other: one CTA per grid walks its scans in order; within a scan
+// the first thread to reach a cell claims it by setting the (otherwise unused) sign bit together with the new value in
+// one compare-and-swap, later points of the same scan see the bit and pass; a second sweep over the scan's points
+// clears the bits.  Cells are non-negative fixed-point ints or float bit patterns, so bit 31 is free in both.
+__global__ void __launch_bounds__(256)
+raster_occu_kernel(const RasterScan* __restrict__ scans, const int* __restrict__ group_begin, int half, int fixed) {
+  const int s_begin = group_begin[blockIdx.x], s_end = group_begin[blockIdx.x + 1];
+  const int tol = half + 1;
+  const unsigned int kTag = 0x80000000u;
+  for (int s = s_begin; s < s_end; ++s) {
+    const RasterScan S = scans[s];
+    unsigned int* grid = reinterpret_cast<unsigned int*>(S.grid);
+    for (int sweep = 0; sweep < 2; ++sweep) {
+      for (int i = threadIdx.x; i < S.n_pts; i += blockDim.x) {
+        const double px = S.pts[2 * i], py = S.pts[2 * i + 1];
+        const double mx = dadd(S.tx, dadd(dmul(S.c, px), dmul(-S.s, py)));      // occu_grid_map.h:279-283
+        const double my = dadd(S.ty, dadd(dmul(S.s, px), dmul(S.c, py)));
+        const int ex = __double2int_rz(dadd(mx, 0.5)), ey = __double2int_rz(dadd(my, 0.5));
+        if (ex == S.start_x && ey == S.start_y) continue;                                          // :312
+        if (!(ex > tol && ex < S.size_x - tol && ey > tol && ey < S.size_y - tol)) continue;       // :476
+        unsigned int* cell = grid + (long long)ey * S.pitch + ex;
+        if (sweep == 1) { atomicAnd(cell, ~kTag); continue; }
+        unsigned int old = *reinterpret_cast<volatile unsigned int*>(cell);
+        while (!(old & kTag)) {
+          float v = fixed ? __fmul_rn(__int2float_rn((int)old), 2.98023223876953125e-08f) : __uint_as_float(old);   // 2^-25
+          v = __fadd_rn(v, 0.5f);                                                                // UpdateSetOccupied
+          if (v > 1.0f) v = 1.0f;
+          const unsigned int nv = (fixed ? (unsigned int)__float2int_rn(__fmul_rn(v, 33554432.0f)) : __float_as_uint(v)) | kTag;
+          const unsigned int seen = atomicCAS(cell, old, nv);
+          if (seen == old) break;
+          old = seen;
+        }
+      }
+      __syncthreads();     // every claim of this scan is in place before the bits are cleared; every bit is cleared before the next scan
+    }
+  }
+}
+
+cudaError_t launch_raster_occu(int n_groups, cudaStream_t st, const RasterScan* scans, const int* group_begin, int half, int fixed) {
+  if (n_groups == 0) return cudaSuccess;
+  raster_occu_kernel<<<n_groups, 256, 0, st>>>(scans, group_begin, half, fixed);
   return cudaGetLastError();
 }
 

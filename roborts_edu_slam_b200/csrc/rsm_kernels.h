@@ -19,9 +19,11 @@ inline int score_rows(int lx, int ry) { return (score_threads(lx) / lx) * ry; }
 int score_occupancy(bool fixed, bool affine, int lx, int ry, int const_pitch);
 cudaError_t launch_score(bool fixed, bool affine, int lx, int ry, int const_pitch, int n_cta, cudaStream_t st,
                          const ScoreJob* jobs, const int* cta_begin, int n_jobs);
-// Flat variant (small windows, non-integer step): one thread per candidate, 256 candidates per CTA.
-int score_flat_ctas(int n_local);
-cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
+// Flat variant (small windows, non-integer step): k candidates per thread, k * 256 consecutive candidates per CTA.
+int score_flat_max_nxy();
+int score_flat_k(int n_xy);
+int score_flat_ctas(int n_local, int k);
+cudaError_t launch_score_flat(bool fixed, int k, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs);
 // Patch variant (batches of small unit-step windows, fixed point): one CTA = score_patch_angles() consecutive search
 // angles of one job, the whole window (n_xy <= 16) per angle; grid cells reach shared memory as one box per 32 beams.
 int score_patch_angles();
@@ -50,6 +52,8 @@ cudaError_t launch_fill_f32(cudaStream_t st, float* p, long long n, float v);
 cudaError_t launch_optimize(int n_jobs, cudaStream_t st, const OptimizeJob* jobs);
 cudaError_t launch_raster(int n_scans, cudaStream_t st, const RasterScan* scans, const int* stamp,
                           int half, int one);
+// non-blur update (SET_CELL_OCCUPIED): one CTA per grid, its scans [group_begin[g], group_begin[g+1]) applied in order
+cudaError_t launch_raster_occu(int n_groups, cudaStream_t st, const RasterScan* scans, const int* group_begin, int half, int fixed);
 cudaError_t launch_microbench(cudaStream_t st, int mode, const int* g, unsigned int words, int iters,
                               int n_cta, unsigned long long* sink);
 cudaError_t launch_flush(cudaStream_t st, void* buf, long long bytes, int v);

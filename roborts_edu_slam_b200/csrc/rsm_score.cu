@@ -28,6 +28,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "rsm_device.h"
 #include "rsm_kernels.h"
 
@@ -662,15 +665,18 @@ namespace flat {
 
 constexpr int kThreads = 256;
 constexpr int kPC = 32;          // beams per chunk
-constexpr int kMaxAngles = 32;   // angles a CTA may span (n_xy >= 3 -> at most 30)
+constexpr int kMaxAngles = 32;   // angles a CTA may span
 constexpr double kQ = 65536.0;
 
 __device__ __forceinline__ int to_q(double v) {   // rn(v * 2^16), saturated so that sums cannot overflow
   return __double2int_rn(fmin(fmax(dmul(v, kQ), -1073741824.0), 1073741824.0));
 }
 
-template <bool FIXED>
-__global__ void __launch_bounds__(kThreads, 4)
+// K candidates per thread: a CTA takes K * 256 consecutive candidates, thread t the candidates k0 + t + j * 256.
+// Larger windows (the 11 x 11 x 11 fine pass) amortise the chunk tables over more gathers and keep K independent
+// loads in flight per beam.
+template <bool FIXED, int K>
+__global__ void __launch_bounds__(kThreads, K <= 2 ? 4 : 3)
 score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
   const int tid = threadIdx.x;
   __shared__ ScoreJob J;
@@ -692,20 +698,23 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
   const int n_local = J.ang_count * plane;
   const int S = (FIXED && J.n_split > 1) ? J.n_split : 1;      // CTAs sharing the beams of one block of candidates
   const int group = (blockIdx.x - first_cta) / S, split = (blockIdx.x - first_cta) - group * S;
-  const int k0 = group * kThreads;                             // first candidate of this CTA, (angle, y, x) order
-  const int kk = k0 + tid;
-  const bool live = kk < n_local;
-  const int kc = live ? kk : n_local - 1;
-  const int ia_l = kc / plane, rem = kc - ia_l * plane;
-  const int iy = rem / n_xy, ix = rem - iy * n_xy;
+  const int k0 = group * (kThreads * K);                       // first candidate of this CTA, (angle, y, x) order
   const int a_first = k0 / plane;
-  const int a_last = min(k0 + kThreads - 1, n_local - 1) / plane;
+  const int a_last = min(k0 + kThreads * K - 1, n_local - 1) / plane;
   const int n_a = a_last - a_first + 1;
-  const int a_rel = ia_l - a_first;
-  const int ia = J.ang_begin + ia_l;
-  const double x = dadd(J.sx, dmul((double)ix, J.f));          // :569
-  const double y = dadd(J.sy, dmul((double)iy, J.f));          // :572
-  const int xq = to_q(x) + 32768, yq = to_q(y) + 32768;
+  int kk[K], a_rel[K], xq[K], yq[K], cix[K], ciy[K];
+  bool live[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    kk[j] = k0 + tid + j * kThreads;
+    live[j] = kk[j] < n_local;
+    const int kc = live[j] ? kk[j] : n_local - 1;
+    const int ia_l = kc / plane, rem = kc - ia_l * plane;
+    ciy[j] = rem / n_xy; cix[j] = rem - ciy[j] * n_xy;
+    a_rel[j] = ia_l - a_first;
+    xq[j] = to_q(dadd(J.sx, dmul((double)cix[j], J.f))) + 32768;     // :569
+    yq[j] = to_q(dadd(J.sy, dmul((double)ciy[j], J.f))) + 32768;     // :572
+  }
   const int V = J.V, pitch = J.pitch;
   const unsigned int size_x = (unsigned int)J.size_x, size_y = (unsigned int)J.size_y;
   const int nchunks_all = (V + kPC - 1) / kPC;
@@ -729,47 +738,66 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
       }
     }
   };
+  // exact FP64 index of (candidate j, beam v): the fixed-point value is within 2^-15 of a cell boundary, or off the grid
+  auto exact_index = [&](int j, int v, int* err) -> int {
+    const int ia = J.ang_begin + a_first + a_rel[j];
+    const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1);
+    const int p = v * J.step;
+    const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+    int gx = cell_index(dsub(dmul(cs, px), dmul(sn, py)), dadd(J.sx, dmul((double)cix[j], J.f)));      // :647-648
+    int gy = cell_index(dadd(dmul(sn, px), dmul(cs, py)), dadd(J.sy, dmul((double)ciy[j], J.f)));
+    if ((unsigned int)gx >= size_x || (unsigned int)gy >= size_y) {
+      if (live[j]) *err = kErrWindow;
+      gx = max(0, min(gx, (int)size_x - 1));
+      gy = max(0, min(gy, (int)size_y - 1));
+    }
+    return gy * pitch + gx;
+  };
 
-  unsigned int a32 = 0u;
-  unsigned long long a64 = 0ull;
-  double ad = 0.0;
+  unsigned int a32[K];
+  unsigned long long a64[K];
+  double ad[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { a32[j] = 0u; a64[j] = 0ull; ad[j] = 0.0; }
   int err = 0;
   if (c_begin < nchunks) lut_chunk(c_begin);
   __syncthreads();
   for (int c = c_begin; c < nchunks; ++c) {
     if (c + 1 < nchunks) lut_chunk(c + 1);
     const int npc = min(kPC, V - c * kPC);
-    const int2* l = sLutQ[c & 1][a_rel];
-#pragma unroll 4
+    const int2* l[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) l[j] = sLutQ[c & 1][a_rel[j]];
+#pragma unroll 2
     for (int pc = 0; pc < npc; ++pc) {
-      const int2 e = l[pc];
-      const int tx = e.x + xq, ty = e.y + yq;
-      int gx = tx >> 16, gy = ty >> 16;
-      const bool ok = (((unsigned int)(tx - 2) & 0xffffu) <= 65531u) && (((unsigned int)(ty - 2) & 0xffffu) <= 65531u) &&
-                      (unsigned int)gx < size_x && (unsigned int)gy < size_y;
-      if (!ok) {
-        // exact FP64 index: the fixed-point value is within 2^-15 of a cell boundary, or off the grid
-        const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1);
-        const int p = (c * kPC + pc) * J.step;
-        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
-        gx = cell_index(dsub(dmul(cs, px), dmul(sn, py)), x);      // :647-648
-        gy = cell_index(dadd(dmul(sn, px), dmul(cs, py)), y);
-        if ((unsigned int)gx >= size_x || (unsigned int)gy >= size_y) {
-          if (live) err = kErrWindow;
-          gx = max(0, min(gx, (int)size_x - 1));
-          gy = max(0, min(gy, (int)size_y - 1));
-        }
+      int at[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int2 e = l[j][pc];
+        const int tx = e.x + xq[j], ty = e.y + yq[j];
+        const int gx = tx >> 16, gy = ty >> 16;
+        const bool ok = (((unsigned int)(tx - 2) & 0xffffu) <= 65531u) && (((unsigned int)(ty - 2) & 0xffffu) <= 65531u) &&
+                        (unsigned int)gx < size_x && (unsigned int)gy < size_y;
+        at[j] = gy * pitch + gx;
+        if (!ok) at[j] = exact_index(j, c * kPC + pc, &err);
       }
-      if (FIXED) a32 += (unsigned int)__ldg(gridI + (gy * pitch + gx));
-      else ad = dadd(ad, (double)__ldg(gridF + (gy * pitch + gx)));
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (FIXED) a32[j] += (unsigned int)__ldg(gridI + at[j]);
+        else ad[j] = dadd(ad[j], (double)__ldg(gridF + at[j]));
+      }
     }
-    if (FIXED) { a64 += a32; a32 = 0u; }
+    if (FIXED) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) { a64[j] += a32[j]; a32[j] = 0u; }
+    }
     __syncthreads();
   }
 
   if (FIXED && S > 1) {
     __shared__ int s_ticket;
-    if (live && a64) atomicAdd(J.acc + kk, a64);
+#pragma unroll
+    for (int j = 0; j < K; ++j) if (live[j] && a64[j]) atomicAdd(J.acc + kk[j], a64[j]);
     if (err) atomicOr(J.err, err);
     err = 0;
     __threadfence();
@@ -778,11 +806,16 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
     __syncthreads();
     if (s_ticket != S - 1) return;
     __threadfence();
-    if (live) a64 = __ldcg(J.acc + kk);
+#pragma unroll
+    for (int j = 0; j < K; ++j) if (live[j]) a64[j] = __ldcg(J.acc + kk[j]);
   }
   unsigned long long key = 0ull;
-  if (live) {
-    double sc = ddiv(FIXED ? dmul((double)a64, kFixScale) : ad, J.divisor);    // :659
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (!live[j]) continue;
+    const int ia_l = a_first + a_rel[j], ia = J.ang_begin + ia_l;
+    const double x = dadd(J.sx, dmul((double)cix[j], J.f)), y = dadd(J.sy, dmul((double)ciy[j], J.f));
+    double sc = ddiv(FIXED ? dmul((double)a64[j], kFixScale) : ad[j], J.divisor);    // :659
     if (J.use_penalty) {
       const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);             // :728
       if (!zero) {
@@ -796,8 +829,9 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
         sc = dmul(sc, dmul(dp, ap));
       }
     }
-    J.score[((long long)ia_l * n_xy + ix) * n_xy + iy] = sc;
-    key = score_key(sc);
+    J.score[((long long)ia_l * n_xy + cix[j]) * n_xy + ciy[j]] = sc;
+    const unsigned long long kj = score_key(sc);
+    key = kj > key ? kj : key;
   }
   key = warp_max_u64(key);
   if ((tid & 31) == 0) s_wmax[tid >> 5] = key;
@@ -812,11 +846,27 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
 
 }  // namespace flat
 
-int score_flat_ctas(int n_local) { return (n_local + flat::kThreads - 1) / flat::kThreads; }
+// widest window of the flat variant, and candidates per thread for a window width: a CTA of k * 256 consecutive
+// candidates must not span more than kMaxAngles angles, and small jobs should not be mostly padding
+int score_flat_max_nxy() { return 12; }
+int score_flat_k(int n_xy) {
+  const int plane = n_xy * n_xy;
+  if (plane < 36) return 1;      // 3 x 3 .. 5 x 5: up to 30 angles per 256 candidates already
+  return plane < 64 ? 2 : 3;     // 121 x 11 = 1331 candidates -> two CTAs of 768
+}
+int score_flat_ctas(int n_local, int k) { return (n_local + flat::kThreads * k - 1) / (flat::kThreads * k); }
 
-cudaError_t launch_score_flat(bool fixed, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
-  if (fixed) flat::score_flat_kernel<true><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
-  else flat::score_flat_kernel<false><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+cudaError_t launch_score_flat(bool fixed, int k, int n_cta, cudaStream_t st, const ScoreJob* jobs, const int* cta_begin, int n_jobs) {
+  if (n_cta <= 0) return cudaSuccess;
+  if (fixed) {
+    if (k == 1) flat::score_flat_kernel<true, 1><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+    else if (k == 2) flat::score_flat_kernel<true, 2><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+    else flat::score_flat_kernel<true, 3><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  } else {
+    if (k == 1) flat::score_flat_kernel<false, 1><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+    else if (k == 2) flat::score_flat_kernel<false, 2><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+    else flat::score_flat_kernel<false, 3><<<n_cta, flat::kThreads, 0, st>>>(jobs, cta_begin, n_jobs);
+  }
   return cudaGetLastError();
 }
 
@@ -1259,11 +1309,15 @@ static void (*staged_fn(int variant))(const ScoreJob*, const int*, int) {
   return variant == 0 ? staged::score_staged_kernel<3, 6> : staged::score_staged_kernel<2, 4>;
 }
 
+// guards the per-device launch-configuration caches below: contexts of different caller threads share them
+static std::mutex g_config_mutex;
+
 static cudaError_t staged_configure(int variant, size_t smem) {
   static size_t configured[kMaxDevices][2] = {{0, 0}};   // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(g_config_mutex);
   if (smem > configured[dev][variant]) {
     cudaError_t e = cudaFuncSetAttribute(staged_fn(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1275,9 +1329,9 @@ static cudaError_t staged_configure(int variant, size_t smem) {
 // CTAs of the staged variant that can be resident at once when launched as clusters of n_split
 // (a cluster lives inside one GPC, so sizes that do not divide the GPC's SM count leave SMs idle).
 int score_staged_resident_ctas(int variant, int n_split, int max_beams_per_split) {
-  static int cache[2][9] = {{0}};
+  static std::atomic<int> cache[2][9];
   if (n_split < 1 || n_split > 8) return 0;
-  if (cache[variant][n_split]) return cache[variant][n_split];
+  if (const int hit = cache[variant][n_split].load(std::memory_order_acquire)) return hit;
   const size_t smem = score_staged_smem(max_beams_per_split > 2048 ? max_beams_per_split : 2048);
   if (staged_configure(variant, smem) != cudaSuccess) return 0;
   cudaLaunchConfig_t cfg = {};
@@ -1288,8 +1342,8 @@ int score_staged_resident_ctas(int variant, int n_split, int max_beams_per_split
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, staged_fn(variant), &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
-  cache[variant][n_split] = n * n_split;
-  return cache[variant][n_split];
+  cache[variant][n_split].store(n * n_split, std::memory_order_release);
+  return n * n_split;
 }
 
 cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_beams_per_split, cudaStream_t st,

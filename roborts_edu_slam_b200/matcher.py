@@ -26,8 +26,11 @@ SUPER_CORRELATION_SCAN_MATCH = 2
 FAST_CORRELATION_SCAN_MATCH = 3
 
 RSM_OK = 0
+RSM_NEED_EXACT = 7
+RSM_OPT_STRICT_TIES = 1
+RSM_OPT_LANES = 2
 STATUS_NAMES = {0: "RSM_OK", 1: "RSM_ERR_NO_DEVICE", 2: "RSM_ERR_CUDA", 3: "RSM_ERR_INVALID",
-                4: "RSM_ERR_WINDOW", 5: "RSM_ERR_UNSUPPORTED", 6: "RSM_ERR_NOT_INIT"}
+                4: "RSM_ERR_WINDOW", 5: "RSM_ERR_UNSUPPORTED", 6: "RSM_ERR_NOT_INIT", 7: "RSM_NEED_EXACT"}
 
 c_d, c_i, c_p, c_i64 = ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64
 
@@ -91,6 +94,7 @@ ABI = {
     "rsm_destroy": (None, [c_p]),
     "rsm_last_error": (ctypes.c_char_p, [c_p]),
     "rsm_set_profiling": (c_i, [c_p, c_i]),
+    "rsm_set_option": (c_i, [c_p, c_i, c_i]),
     "rsm_get_stats": (c_i, [c_p, ctypes.POINTER(Stats)]),
     "rsm_reset_stats": (c_i, [c_p]),
     "rsm_synchronize": (c_i, [c_p]),
@@ -156,6 +160,8 @@ ABI = {
     "rsm_match_partial": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_i, c_i, c_p]),
     "rsm_match_merge": (c_i, [c_p, c_p, c_i, c_p]),
     "rsm_match_finish": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_match_slice_scores": (c_i, [c_p, c_p, c_i64, ctypes.POINTER(c_i64)]),
+    "rsm_match_finish_exact": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
 }
 
 _lib = None
@@ -246,6 +252,10 @@ class Context:
 
     def set_profiling(self, on):
         self.check(self.lib.rsm_set_profiling(self.h, int(on)))
+
+    def set_option(self, option, value):
+        """RSM_OPT_STRICT_TIES (bit-equal covariance under every tie pattern), RSM_OPT_LANES (pipelined sub-batches)."""
+        self.check(self.lib.rsm_set_option(self.h, int(option), int(value)))
 
     def stats(self):
         s = Stats()
@@ -631,6 +641,11 @@ class SlicedScanMatch:
     def __init__(self, ctx, rank, world_size, all_gather):
         self.ctx, self.rank, self.world, self.all_gather = ctx, rank, world_size, all_gather
         self.last_detail = None
+        self.exact_fallback = False     # the last match needed the gathered exact-tie path
+        self.exchange = "caller-supplied all_gather"
+
+    def close(self):
+        pass
 
     def ScanMatch(self, map_, range_data, scan_match_param, current_pose, cov_matrix):
         from .sharding import contiguous_range
@@ -651,10 +666,50 @@ class SlicedScanMatch:
         cp = (c_p * len(cols))(*[c.ctypes.data for c in cols])
         resp = c_d(0)
         det = PassDetail()
-        ctx.check(ctx.lib.rsm_match_finish(ctx.h, pp, len(partials), cp, current_pose.ctypes.data,
-                                           cov_matrix.ctypes.data, ctypes.byref(resp), ctypes.byref(det)))
+        rc = ctx.lib.rsm_match_finish(ctx.h, pp, len(partials), cp, current_pose.ctypes.data,
+                                      cov_matrix.ctypes.data, ctypes.byref(resp), ctypes.byref(det))
+        self.exact_fallback = rc == RSM_NEED_EXACT
+        if rc == RSM_NEED_EXACT:
+            # Exact score ties in a consumed set (every rank takes this branch: the decision only reads gathered
+            # data).  The reference's answer is then defined by its unstable sort of the WHOLE candidate array
+            # (correlate_scan_matcher.h:607-611): gather the slices and run that sort on every rank.
+            n_xy = det.n_xy if det.n_xy > 0 else int(np.floor(ps.search_space_size / ps.search_space_resolution + 0.5) + 1)
+            plane = n_xy * n_xy
+            counts = [(e - b) * plane for b, e in (contiguous_range(n_ang, r, self.world) for r in range(self.world))]
+            cap = max(max(counts), 1)
+            mine = np.zeros(cap, dtype=np.float64)
+            n_mine = c_i64(0)
+            ctx.check(ctx.lib.rsm_match_slice_scores(ctx.h, mine.ctypes.data, cap, ctypes.byref(n_mine)))
+            assert n_mine.value == counts[self.rank], (n_mine.value, counts[self.rank])
+            slices = [np.ascontiguousarray(sl).view(np.float64) if sl.dtype != np.float64 else np.ascontiguousarray(sl)
+                      for sl in self.all_gather(mine.view(np.uint8))]
+            sp = (c_p * len(slices))(*[sl.ctypes.data for sl in slices])
+            cnt = np.array(counts, dtype=np.int64)
+            rc = ctx.lib.rsm_match_finish_exact(ctx.h, sp, cnt.ctypes.data, len(slices), current_pose.ctypes.data,
+                                                cov_matrix.ctypes.data, ctypes.byref(resp), ctypes.byref(det))
+        ctx.check(rc)
         self.last_detail = det
         return resp.value
+
+
+def make_sliced_matcher(ctx, rank, world_size, dist=None):
+    """SlicedScanMatch for a torch.distributed job (one process per GPU): the small all-gathers go through
+    `dist.all_gather` on CUDA byte tensors.  dist = None (world_size 1): no exchange."""
+    if world_size == 1 or dist is None:
+        sm = SlicedScanMatch(ctx, rank, world_size, lambda buf: [buf])
+        sm.exchange = "none (one rank)"
+        return sm
+    import torch
+
+    def all_gather(buf):
+        t = torch.from_numpy(np.ascontiguousarray(buf).view(np.uint8)).cuda()
+        outs = [torch.empty_like(t) for _ in range(world_size)]
+        dist.all_gather(outs, t)
+        return [o.cpu().numpy() for o in outs]
+
+    sm = SlicedScanMatch(ctx, rank, world_size, all_gather)
+    sm.exchange = "torch.distributed all_gather (NCCL) of host-staged buffers"
+    return sm
 
 
 class ScanMatchers:
@@ -807,18 +862,29 @@ class ScanStore:
             self.h = None
 
 
-def scan_match_interface_batch(ctx, store, grid_spec, centres, chains, match_ids, seed_poses, params, use_fine=True,
-                               pub_map=None, pub_store=None, check=None):
-    """SlamProcessor::ScanMatchInterface (slam_processor.cpp:250-326) for many loop-closure candidates:
-    candidate i matches scan match_ids[i] of `store` against the chain `chains[i]` (list of scan ids) on a
-    back-end grid of grid_spec's size / resolution / blur centred on centres[i].  With pub_map / pub_store /
-    check = (check_point_num, bound_tolerance, penalty_gain, use_logistic) the scores end with the map check.
-    Returns (scores, poses, covs, responses)."""
+def pack_chains(chains):
+    """[[ids of chain 0], [ids of chain 1], ...] -> (chain_offset int64[n + 1], chain_ids int32[...]) for
+    scan_match_interface_batch; a caller that matches the same chains repeatedly packs them once."""
     n = len(chains)
     off = np.zeros(n + 1, dtype=np.int64)
     for i, ch in enumerate(chains):
         off[i + 1] = off[i] + len(ch)
     ids = np.ascontiguousarray(np.concatenate([np.asarray(ch, dtype=np.int32) for ch in chains]) if n else np.zeros(0), dtype=np.int32)
+    return off, ids
+
+
+def scan_match_interface_batch(ctx, store, grid_spec, centres, chains, match_ids, seed_poses, params, use_fine=True,
+                               pub_map=None, pub_store=None, check=None):
+    """SlamProcessor::ScanMatchInterface (slam_processor.cpp:250-326) for many loop-closure candidates:
+    candidate i matches scan match_ids[i] of `store` against the chain `chains[i]` (list of scan ids; or the
+    (offsets, ids) pair of pack_chains) on a back-end grid of grid_spec's size / resolution / blur centred on
+    centres[i].  With pub_map / pub_store / check = (check_point_num, bound_tolerance, penalty_gain, use_logistic)
+    the scores end with the map check.  Returns (scores, poses, covs, responses)."""
+    if isinstance(chains, tuple):
+        off, ids = chains
+    else:
+        off, ids = pack_chains(chains)
+    n = len(off) - 1
     mids = np.ascontiguousarray(match_ids, dtype=np.int32)
     arr = (PassParamStruct * 3)(*[_as_param(p).struct() for p in params])
     poses = _f64(np.asarray(seed_poses).reshape(-1, 3)).copy()

@@ -1,7 +1,7 @@
 """Generate golden input/output vectors from the REFERENCE'S OWN CODE (oracle/_ref/libref.so,
 i.e. /root/reference/src headers compiled in place).  Run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [name-prefix ...]
 
 Each tests/golden/<case>.npz holds the complete inputs of one match (grid geometry, base scans,
 scan, seed pose, pass parameters) and what the reference returned for them: the lookup grid
@@ -41,18 +41,35 @@ def tie_heavy_case():
     return sc
 
 
+def non_blur_cases():
+    """SET_CELL_OCCUPIED construction (map/occu_grid_map.h:317-321, 499-516): use_blur off on the config-1 map, and
+    blur parameters the reference's GaussianBlur rejects (sigma >= 10 * resolution) on a config-4 pair, which makes
+    UpdateMapByRange drop use_blur by itself (:265-268).  Cells end up 0.3, 0.8 (hit by one scan) or 1.0."""
+    a = synth.config1()
+    a.name = "nonblur_icra"
+    a.grid.use_blur = False
+    a.passes = synth.chain_yaml()
+    b = synth.config4(1, seed=99)[0]
+    b.name = "nonblur_badsigma_pair"
+    b.grid.sigma = 5.0
+    return [a, b]
+
+
 def cases():
     c1 = synth.config1()
     c3 = synth.config3(shipped_points=True)
     c3.name = "cfg3_willow_shipped"
     # keep the fixture small: the 2400^2 grid is rebuilt from the stored scans
     c4 = synth.config4(1)[0]
-    return [c1, c3, c4, tie_heavy_case()]
+    return [c1, c3, c4, tie_heavy_case()] + non_blur_cases()
 
 
 def main():
     R = Ref()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]      # optional: name prefixes to (re)generate
     for sc in cases():
+        if only and not sc.name.startswith(tuple(only)):
+            continue
         g = sc.grid
         m = R.create_map(g)
         R.build_map(m, g, sc.base_pts, sc.base_poses)

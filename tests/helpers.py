@@ -16,7 +16,7 @@ def sha(a):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("maps_", "mapcheck_", "optimize_", "frontend_", "pubmap_")))
+                  if not os.path.basename(p).startswith(("maps_", "mapcheck_", "optimize_", "frontend_", "pubmap_", "config5_")))
 
 
 def mapcheck_names():
@@ -51,6 +51,77 @@ def golden_grid(z, g):
     grid = np.full(g.size_x * g.size_y, np.float32(g.default_prob), dtype=np.float32)
     grid[z["grid_nz_index"]] = z["grid_nz_value"]
     return grid.reshape(g.size_y, g.size_x)
+
+
+def load_config5_golden():
+    """-> (config 5 re-synthesised, the fixture of tests/golden/make_config5.py); the fixture holds no inputs, only their
+    checksum, which is verified here."""
+    z = np.load(os.path.join(GOLDEN_DIR, "config5_full.npz"), allow_pickle=False)
+    sc = synth.config5()
+    g = sc.grid
+    h = hashlib.sha256()
+    for a in [sc.scan_pts, sc.base_poses, sc.seed_pose, sc.passes[0]] + list(sc.base_pts):
+        h.update(np.ascontiguousarray(a).tobytes())
+    h.update(np.array([g.res, g.sigma, g.size_x, g.size_y, g.off_x, g.off_y, g.default_prob, g.occu_offset]).tobytes())
+    assert h.hexdigest() == str(z["input_checksum"]), "synthetic config-5 inputs changed since the fixture was made"
+    return sc, z
+
+
+_SHIM = None
+
+
+def host_shim():
+    """The product's host-side arithmetic (csrc/rsm_host.h) compiled with g++ through tests/host_shim.cpp: needs neither
+    nvcc nor librsm.so, so CPU tests can use the host logic on a fresh checkout."""
+    global _SHIM
+    if _SHIM is None:
+        import ctypes
+        import subprocess
+        import tempfile
+        here = os.path.dirname(os.path.abspath(__file__))
+        root = os.path.dirname(here)
+        out = os.path.join(tempfile.mkdtemp(prefix="rsm_host_shim_"), "libhostshim.so")
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                               "-I" + os.path.join(root, "roborts_edu_slam_b200", "csrc"), "-o", out, os.path.join(here, "host_shim.cpp")])
+        L = ctypes.CDLL(out)
+        c_d, c_i, c_p = ctypes.c_double, ctypes.c_int, ctypes.c_void_p
+        L.hs_bounds_create.restype = c_p
+        L.hs_bounds_create.argtypes = [c_i, c_i, c_d, c_d, c_d, c_d]
+        L.hs_bounds_destroy.argtypes = [c_p]
+        L.hs_bounds_update_scan.argtypes = [c_p, c_p, c_i, c_p, c_i, c_i, c_p]
+        L.hs_bounds_size_check.argtypes = [c_p, c_p, c_d, c_d, c_p]
+        _SHIM = L
+    return _SHIM
+
+
+class ShimBounds:
+    """MapBounds of csrc/rsm_host.h through the g++ shim; the interface of matcher.MapBounds (which binds the same code
+    inside librsm.so)."""
+
+    def __init__(self, size_x, size_y, resolution, offset_x, offset_y, extend_factor=1.0):
+        self.L = host_shim()
+        self.h = self.L.hs_bounds_create(int(size_x), int(size_y), 1.0 / float(resolution), float(offset_x), float(offset_y), float(extend_factor))
+
+    def _ret(self, fits, geom):
+        return bool(fits), (int(geom[0]), int(geom[1]), float(geom[2]), float(geom[3])), (int(geom[4]), int(geom[5]))
+
+    def UpdateMapByRange(self, pts_cells, sensor_pose, half_kernel=0, use_blur=False):
+        pts = np.ascontiguousarray(np.asarray(pts_cells, dtype=np.float64).reshape(-1, 2))
+        pose = np.ascontiguousarray(sensor_pose, dtype=np.float64)
+        geom = np.zeros(6)
+        fits = self.L.hs_bounds_update_scan(self.h, pts.ctypes.data, len(pts), pose.ctypes.data, int(half_kernel), int(use_blur), geom.ctypes.data)
+        return self._ret(fits, geom)
+
+    def MapSizeCheck(self, pose_world, range_max, offset):
+        pose = np.ascontiguousarray(pose_world, dtype=np.float64)
+        geom = np.zeros(6)
+        fits = self.L.hs_bounds_size_check(self.h, pose.ctypes.data, float(range_max), float(offset), geom.ctypes.data)
+        return self._ret(fits, geom)
+
+    def close(self):
+        if self.h:
+            self.L.hs_bounds_destroy(self.h)
+            self.h = None
 
 
 def cov_close(a, b, rtol=1e-6):

@@ -252,9 +252,111 @@ def test_config2_full_size(ctx, oracle):
     dg.close()
 
 
+def test_config5_quarter_scale_vs_oracle(ctx, oracle):
+    """BASELINE configs[4] at 1/4 scale (+-2 m / +-45 deg on the full willow map: 81 x 81 x 181 candidates x 938
+    beams = 1.1e9 evaluations, multi-beam-round staged launches): every score, the pose and the covariance
+    against the oracle (0.5 s on 8 host threads, 3.5 s on one), unsliced and angle-sliced."""
+    sc = synth.config5(scale=0.25)
+    g, p = sc.grid, sc.passes[0]
+    grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+    dg = device_grid(ctx, sc)
+    assert np.array_equal(dg.download(), grid)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    want_scores = oracle.scores_threaded(grid, g, sc.scan_pts, p, oracle.world_to_map(g, sc.seed_pose))
+    got = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+    assert np.array_equal(got, want_scores)
+    want = oracle.finish_scores(want_scores, g, len(sc.scan_pts), p, sc.seed_pose)
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    assert_pass_equal(m.ScanMatch(dg, sc.scan_pts, p, pose, cov), pose, cov, want)
+    assert m.last_detail.n_avg == want["n_avg"]
+    # the same window through the sliced calls, 3 emulated ranks on this context's GPU, one after the other
+    gathered = sliced_on_one_gpu(sc, p, sc.seed_pose, 3)
+    for r, pose_s, cov_s, navg in gathered:
+        assert r == want["response"] and np.array_equal(pose_s, want["pose"]) and cov_close(cov_s, want["cov"]) and navg == want["n_avg"]
+    dg.close()
+
+
+def sliced_on_one_gpu(sc, p, pose_in, world):
+    """SlicedScanMatch with `world` emulated ranks (one context each, lock-step threads, list all-gather)."""
+    import threading
+    ctxs = [matcher.Context(0) for _ in range(world)]
+    grids = []
+    for c in ctxs:
+        dg = matcher.ScanMatchMap.from_spec(c, sc.grid)
+        dg.InitMapWithRangeVec(sc.base_pts, sc.base_poses, sc.grid.default_prob, sc.grid.sigma, sc.grid.occu_offset, sc.grid.use_blur)
+        grids.append(dg)
+    slots, barrier, out = [None] * world, threading.Barrier(world), [None] * world
+
+    def make_gather(rank):
+        def gather(buf):
+            slots[rank] = buf.copy()
+            barrier.wait()
+            res = [b.copy() for b in slots]
+            barrier.wait()
+            return res
+        return gather
+
+    def worker(rank):
+        sm = matcher.SlicedScanMatch(ctxs[rank], rank, world, make_gather(rank))
+        pose, cov = pose_in.copy(), np.eye(3)
+        try:
+            r = sm.ScanMatch(grids[rank], sc.scan_pts, p, pose, cov)
+            out[rank] = (r, pose, cov, sm.last_detail.n_avg)
+        except Exception as e:
+            out[rank] = e
+            barrier.abort()
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for dg in grids:
+        dg.close()
+    for c in ctxs:
+        c.close()
+    for o in out:
+        if isinstance(o, Exception):
+            raise o
+    return out
+
+
+def test_config5_full_size_golden(ctx):
+    """BASELINE configs[4] at FULL size (321 x 321 x 721 = 74.3 M candidates, 7.0e10 evaluations, 594 MB of scores,
+    16 partial tiles per angle) against the fixture written by tests/golden/make_config5.py from the reference's own
+    code: every score (sha256 of the array + one checksum per search angle), the head of the sorted list, response,
+    pose, covariance, averaging-set size -- unsliced, and angle-sliced over 4 emulated ranks."""
+    import hashlib
+    from helpers import load_config5_golden
+    sc, z = load_config5_golden()
+    p = sc.passes[0]
+    dg = device_grid(ctx, sc)
+    assert hashlib.sha256(np.ascontiguousarray(dg.download()).tobytes()).hexdigest() == str(z["grid_sha"])
+    assert np.array_equal(dg.GetMapCoordsPose(sc.seed_pose), z["centre_map"])
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    scores = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+    n_ang = int(z["n_ang"])
+    assert scores.size == n_ang * int(z["n_xy"]) ** 2
+    sums = scores.view(np.uint64).reshape(n_ang, -1).sum(axis=1, dtype=np.uint64)
+    bad = np.flatnonzero(sums != z["angle_sums"])
+    assert bad.size == 0, "scores differ from the reference at search angles %s" % bad[:8]
+    assert hashlib.sha256(scores.tobytes()).hexdigest() == str(z["scores_sha"])
+    head = np.partition(scores, scores.size - 64)[-64:]
+    assert np.array_equal(np.sort(head)[::-1], z["sorted_head"])
+    del scores, head
+    pose, cov = sc.seed_pose.copy(), np.eye(3)
+    r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+    assert r == float(z["response"]) and np.array_equal(pose, z["pose"]) and cov_close(cov, z["cov"])
+    assert m.last_detail.n_avg == int(z["n_avg"])
+    assert np.array_equal([m.last_detail.best_pose_map[i] for i in range(3)] + [m.last_detail.best_score], z["best_map"])
+    dg.close()
+    for r, pose_s, cov_s, navg in sliced_on_one_gpu(sc, p, sc.seed_pose, 4):
+        assert r == float(z["response"]) and np.array_equal(pose_s, z["pose"]) and cov_close(cov_s, z["cov"]) and navg == int(z["n_avg"])
+
+
 def test_size_independent_properties_wide_window(ctx):
-    """A window too large for the CPU oracle to finish in seconds (1/4-scale config 5, 1.1e9
-    evaluations): properties that pin the kernel without an oracle."""
+    """1/4-scale config 5 (1.1e9 evaluations): properties that hold at any size, beside the oracle comparison of
+    test_config5_quarter_scale_vs_oracle."""
     sc = synth.config5(scale=0.25)
     dg = device_grid(ctx, sc)
     m = matcher.BasedCorrelationScanMatch(ctx)
@@ -293,7 +395,8 @@ def test_size_independent_properties_wide_window(ctx):
 
 def test_angle_sliced_match_equals_unsliced(oracle):
     """one window cut along the angle index over N ranks, merged through the partial /
-    merge / finish calls, must equal the unsliced match (and hence the reference).  The ranks are
+    merge / finish calls, must equal the unsliced match (and hence the reference) -- also when exact
+    ties send every rank through rsm_match_slice_scores / rsm_match_finish_exact.  The ranks are
     emulated by N contexts on this GPU, run in lock step; the all-gather is a list."""
     import threading
     from roborts_edu_slam_b200.sharding import contiguous_range
@@ -322,10 +425,10 @@ def test_angle_sliced_match_equals_unsliced(oracle):
             pose, cov = pose_in.copy(), np.eye(3)
             try:
                 r = sm.ScanMatch(grids[rank], sc.scan_pts, p, pose, cov)
-                out[rank] = (r, pose, cov, sm.last_detail.n_avg)
-            except matcher.RsmError as e:   # exact ties: the sliced path declines, by contract
-                assert e.status == 5
-                out[rank] = "ties"
+                out[rank] = (r, pose, cov, sm.last_detail.n_avg, sm.exact_fallback, sm.last_detail.exact_sort_used)
+            except Exception as e:      # keep the other ranks' barrier from hanging the test
+                out[rank] = e
+                barrier.abort()
 
         ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
         for t in ts:
@@ -336,9 +439,14 @@ def test_angle_sliced_match_equals_unsliced(oracle):
             dg.close()
         for c in ctxs:
             c.close()
+        for o in out:
+            if isinstance(o, Exception):
+                raise o
         return out
 
-    cases = [(synth.config1(), 3), (synth.config3(True), 2), (synth.config4(1, seed=5)[0], 4)]
+    # ties_icra: thousands of exact ties -> the sliced path gathers the slices and runs the reference's sort itself
+    cases = [(synth.config1(), 3), (synth.config3(True), 2), (synth.config4(1, seed=5)[0], 4), (load_golden("ties_icra")[0], 3)]
+    fallbacks = 0
     for sc, world in cases:
         grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
         pose_in = sc.seed_pose.copy()
@@ -346,28 +454,22 @@ def test_angle_sliced_match_equals_unsliced(oracle):
             want = oracle.match(grid, sc.grid, sc.scan_pts, p, pose_in)
             res = run_sliced(sc, p, pose_in, world)
             assert all(r is not None for r in res)
-            if any(isinstance(r, str) for r in res):
-                # every rank must decline together, and the unsliced match must report the exact path
-                assert all(r == "ties" for r in res)
-                c0 = matcher.Context(0)
-                dg = device_grid(c0, sc)
-                m0 = matcher.BasedCorrelationScanMatch(c0)
-                pose, cov = pose_in.copy(), np.eye(3)
-                assert_pass_equal(m0.ScanMatch(dg, sc.scan_pts, p, pose, cov), pose, cov, want)
-                assert m0.last_detail.exact_sort_used == 1
-                dg.close()
-                c0.close()
-            else:
-                for r, pose, cov, navg in res:     # every rank holds the same, reference-identical result
-                    assert r == want["response"] and np.array_equal(pose, want["pose"]) and cov_close(cov, want["cov"])
-                    assert navg == want["n_avg"]
+            assert len({r[4] for r in res}) == 1, "the ranks must agree on the exact-tie fallback"
+            for r, pose, cov, navg, fell_back, exact_used in res:     # every rank holds the same, reference-identical result
+                assert r == want["response"] and np.array_equal(pose, want["pose"]) and cov_close(cov, want["cov"])
+                assert navg == want["n_avg"]
+                assert bool(exact_used) == bool(fell_back)
+                if fell_back:
+                    assert np.array_equal(cov, want["cov"])       # the same std::sort: bit-equal
+            fallbacks += int(res[0][4])
             pose_in = want["pose"]
+    assert fallbacks >= 1, "ties_icra must exercise the gathered exact path"
     # more ranks than angles: empty slices are fine
     sc = synth.config1()
     p = synth.pass_param(0.2, 0.05, 0.03, 0.0349, 0.3, 100000, True, 0)   # n_ang = 2
     grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
     want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
-    for r, pose, cov, navg in run_sliced(sc, p, sc.seed_pose, 4):
+    for r, pose, cov, navg, _, _ in run_sliced(sc, p, sc.seed_pose, 4):
         assert r == want["response"] and np.array_equal(pose, want["pose"]) and cov_close(cov, want["cov"])
 
 
@@ -953,3 +1055,166 @@ def test_patch_kernel_variant(ctx, oracle, monkeypatch):
     scores2, poses2, covs2, resp2 = matcher.loop_closure_batch(ctx, packed, pairs[0].passes)
     assert np.array_equal(scores, scores2) and np.array_equal(poses, poses2) and np.array_equal(covs, covs2) and np.array_equal(resp, resp2)
     assert ctx.stats()["score_launches"] >= st0
+
+
+# ---- round 2: non-blur update, pipelined lanes, heterogeneous batches, strict ties -----------------------
+def test_non_blur_update_paths(ctx, oracle):
+    """SET_CELL_OCCUPIED (occu_grid_map.h:317-321, 499-516): UpdateMapByRange with use_blur off, and with blur
+    parameters the reference rejects, on a constructed front-end map scan by scan, as a rebuild from the scan store
+    and inside the batched back-end step -- every cell and every chain result against the oracle (whose non-blur path
+    is pinned against the reference: tests/golden/nonblur_*.npz, tests/test_oracle.py)."""
+    import dataclasses
+    sc = synth.config4(1, seed=77)[0]
+    for g in (dataclasses.replace(sc.grid, use_blur=False), dataclasses.replace(sc.grid, sigma=5.0)):
+        want = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+        assert set(np.unique(want)) <= {np.float32(0.3), np.float32(0.8), np.float32(1.0)} and (want == np.float32(0.8)).sum() > 50
+        # (1) one call
+        dg = matcher.ScanMatchMap.from_spec(ctx, g)
+        dg.InitMapWithRangeVec(sc.base_pts, sc.base_poses, g.default_prob, g.sigma, g.occu_offset, g.use_blur)
+        assert np.array_equal(dg.download(), want)
+        # (2) scan by scan on a constructed map (cell 0 = 0.3, the others 0.5): 0.5 -> 1.0 on the first hit
+        dg.fill(0.5, 0.3)
+        host = np.full((g.size_y, g.size_x), np.float32(0.5)); host[0, 0] = np.float32(0.3)
+        for pts, pose in zip(sc.base_pts, sc.base_poses):
+            dg.UpdateMapByRange(pts, pose, g.sigma, g.occu_offset, g.use_blur)
+            oracle.grid_stamp(host, g, pts, pose)
+        assert np.array_equal(dg.download(), host) and (host == np.float32(1.0)).sum() > 100
+        # (3) a float32-held map takes the same path (one non-representable cell forces float cells)
+        bumped = np.full((g.size_y, g.size_x), np.float32(0.3)); bumped[0, 0] = np.float32(0.1)
+        dg.upload(bumped)
+        assert not dg.is_fixed_point()
+        hostf = bumped.copy()
+        for pts, pose in zip(sc.base_pts[:3], sc.base_poses[:3]):
+            dg.UpdateMapByRange(pts, pose, g.sigma, g.occu_offset, g.use_blur)
+            oracle.grid_stamp(hostf, g, pts, pose)
+        assert np.array_equal(dg.download(), hostf)
+        # (4) rebuild from the scan store
+        store = matcher.ScanStore(ctx)
+        ids = [store.AddRangeData(p, q) for p, q in zip(sc.base_pts, sc.base_poses)]
+        mid = store.AddRangeData(sc.scan_pts, sc.seed_pose)
+        dg.InitMapWithStore(store, ids, g.default_prob, g.sigma, g.occu_offset, g.use_blur)
+        assert np.array_equal(dg.download(), want)
+        dg.close()
+        # (5) the batched back-end step only has the sigma to go by (use_blur is on in the call, as shipped)
+        if g.use_blur:
+            w = oracle.match_chain(want, g, sc.scan_pts, sc.passes, sc.seed_pose)
+            s_, p_, c_, r_ = matcher.scan_match_interface_batch(ctx, store, g, [sc.grid_centre] * 3, [ids] * 3, [mid] * 3,
+                                                                [sc.seed_pose] * 3, sc.passes)
+            for i in range(3):
+                assert s_[i] == w["score"] and np.array_equal(p_[i], w["pose"]) and cov_close(c_[i], w["cov"]) and np.array_equal(r_[i], w["responses"])
+        store.close()
+
+
+def test_pipelined_lanes_equal_one_lane(ctx, oracle):
+    """A batched chain call cut into sub-batches over several streams (RSM_OPT_LANES) returns what the single-lane
+    call and the oracle return, item for item -- including items whose exact-tie path or gather round trip makes one
+    lane's host stage longer, an empty chain, and a batch smaller than the lane count."""
+    n = 37
+    pairs = synth.config4(n, seed=2468)
+    want = []
+    for sc in pairs:
+        grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        want.append(oracle.match_chain(grid, sc.grid, sc.scan_pts, sc.passes, sc.seed_pose))
+    packed = matcher.pack_loop_closure(pairs)
+    store = matcher.ScanStore(ctx)
+    chains, mids = [], []
+    for sc in pairs:
+        chains.append([store.AddRangeData(p, q) for p, q in zip(sc.base_pts, sc.base_poses)])
+        mids.append(store.AddRangeData(sc.scan_pts, sc.seed_pose))
+    try:
+        for lanes in (1, 2, 3, 8):
+            ctx.set_option(matcher.RSM_OPT_LANES, lanes)
+            for rep in range(2):      # the second call reuses the lanes' buffers
+                res = [matcher.loop_closure_batch(ctx, packed, pairs[0].passes),
+                       matcher.scan_match_interface_batch(ctx, store, pairs[0].grid, [sc.grid_centre for sc in pairs], chains, mids,
+                                                          [sc.seed_pose for sc in pairs], pairs[0].passes)]
+                for scores, poses, covs, resp in res:
+                    for i, w in enumerate(want):
+                        assert scores[i] == w["score"] and np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"]), (lanes, rep, i)
+                        assert np.array_equal(resp[i], w["responses"])
+        # fewer items than lanes, and an item without base scans in the middle of a sub-batch
+        ctx.set_option(matcher.RSM_OPT_LANES, 4)
+        ch2 = [chains[0], [], chains[2]]
+        s_, p_, c_, r_ = matcher.scan_match_interface_batch(ctx, store, pairs[0].grid, [pairs[i].grid_centre for i in range(3)], ch2, mids[:3],
+                                                            [pairs[i].seed_pose for i in range(3)], pairs[0].passes)
+        assert s_[1] == 0.0 and np.array_equal(p_[1], pairs[1].seed_pose) and np.array_equal(c_[1], np.eye(3))
+        for i in (0, 2):
+            assert s_[i] == want[i]["score"] and np.array_equal(p_[i], want[i]["pose"])
+        # existing grids through rsm_match_batch on several lanes
+        grids = [device_grid(ctx, sc) for sc in pairs[:9]]
+        sm = matcher.ScanMatchers(ctx, pairs[0].passes)
+        ctx.set_option(matcher.RSM_OPT_LANES, 3)
+        scores, poses, covs, resp = sm.ScanMatchBatch(grids, [sc.scan_pts for sc in pairs[:9]], [sc.seed_pose for sc in pairs[:9]])
+        for i in range(9):
+            assert scores[i] == want[i]["score"] and np.array_equal(poses[i], want[i]["pose"]) and cov_close(covs[i], want[i]["cov"])
+        for dg in grids:
+            dg.close()
+    finally:
+        ctx.set_option(matcher.RSM_OPT_LANES, 0)
+        store.close()
+
+
+def test_heterogeneous_batch_is_grouped_by_plan(ctx, oracle, rng):
+    """rsm_match_batch with per-pair parameters (shared_params = 0): a 49-wide unit-step window (staged kernel), a
+    13-wide one (tiled / patch) and a 5-wide half-cell one (flat) in ONE call -- every item must get the kernel plan of
+    its own window, not the first item's."""
+    import ctypes
+    scs = [random_scenario(rng, n_points=150 + 40 * k, size=260) for k in range(5)]
+    wins = [synth.pass_param(2.4, 0.05, 0.07, 0.0349, 0.1, 100000, True, 0),    # 49 x 49, f = 1
+            synth.pass_param(0.6, 0.05, 0.21, 0.0349, 0.1, 100000, True, 0),    # 13 x 13, f = 1
+            synth.pass_param(0.1, 0.025, 0.07, 0.0349, 0.1, 60, True, 0),       # 5 x 5, f = 0.5
+            synth.pass_param(0.8, 0.1, 0.14, 0.0349, 0.1, 100000, False, 0),    # 9 x 9, f = 2
+            synth.pass_param(2.4, 0.05, 0.035, 0.0349, 0.1, 100000, True, 0)]   # 49 x 49 again
+    fine = synth.pass_param(0.2, 0.02, 0.07, 0.0349, 0.1, 100000, True, 1)
+    sup = synth.pass_param(0.02, 0.01, 0.0349, 0.00349, 0.1, 100000, True, 2)
+    grids, want = [], []
+    for sc, w0 in zip(scs, wins):
+        grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        want.append(oracle.match_chain(grid, sc.grid, sc.scan_pts, [w0, fine, sup], sc.seed_pose))
+        grids.append(device_grid(ctx, sc))
+    n = len(scs)
+    params = (matcher.PassParamStruct * (3 * n))(*[matcher._as_param(p).struct() for w0 in wins for p in (w0, fine, sup)])
+    offs = np.zeros(n + 1, dtype=np.int64)
+    for i, sc in enumerate(scs):
+        offs[i + 1] = offs[i] + len(sc.scan_pts)
+    pts = np.ascontiguousarray(np.concatenate([sc.scan_pts for sc in scs], axis=0))
+    poses = np.ascontiguousarray(np.array([sc.seed_pose for sc in scs]))
+    covs = np.tile(np.eye(3), (n, 1, 1))
+    scores, resp = np.zeros(n), np.zeros((n, 3))
+    handles = (ctypes.c_void_p * n)(*[dg.h for dg in grids])
+    ctx.check(ctx.lib.rsm_match_batch(ctx.h, n, handles, pts.ctypes.data, offs.ctypes.data, params, 0, 1, poses.ctypes.data,
+                                      covs.ctypes.data, scores.ctypes.data, resp.ctypes.data))
+    for i, w in enumerate(want):
+        assert scores[i] == w["score"] and np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"]), i
+        assert np.array_equal(resp[i], w["responses"])
+    for dg in grids:
+        dg.close()
+
+
+def test_strict_ties_option(ctx, oracle, rng):
+    """RSM_OPT_STRICT_TIES: on a binary grid the centre penalty leaves mirror-image candidates exactly tied inside the
+    20-element covariance prefix.  Default: same consumed set, covariance within 1e-6 (the contract).  With the option
+    the pass takes the reference's own sort and the covariance is bit-equal."""
+    sc, _ = load_golden("ties_icra")
+    dg = device_grid(ctx, sc)
+    grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    try:
+        for strict in (0, 1):
+            ctx.set_option(matcher.RSM_OPT_STRICT_TIES, strict)
+            exact = 0
+            for k, p in enumerate(sc.passes + [synth.pass_param(0.6, 0.05, 0.349, 0.0349, 0.2, 40, True, 0)]):
+                want = oracle.match(grid, sc.grid, sc.scan_pts, p, sc.seed_pose)
+                pose, cov = sc.seed_pose.copy(), np.eye(3)
+                r = m.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+                assert_pass_equal(r, pose, cov, want)
+                if strict:
+                    assert np.array_equal(cov, want["cov"]), k
+                exact += m.last_detail.exact_sort_used
+            if strict:
+                assert exact >= 1
+    finally:
+        ctx.set_option(matcher.RSM_OPT_STRICT_TIES, 0)
+    with pytest.raises(matcher.RsmError):
+        ctx.set_option(99, 1)
+    dg.close()

@@ -240,11 +240,12 @@ def test_optimize_oracle_matches_reference(oracle, ref, rng):
 def test_frontend_maps_oracle_matches_golden(oracle):
     """The restatement of the incremental scan-match map update, ExtendSize's copy and the publishing map's
     ray-traced CountCell update replays the 44-scan trajectory and reproduces the checksums the reference's own
-    maps had after every step (fixtures), with the resize decisions coming from the product's host policy."""
+    maps had after every step (fixtures), with the resize decisions coming from the product's host policy
+    (csrc/rsm_host.h compiled with g++ through tests/host_shim.cpp: no nvcc, no librsm.so)."""
     import hashlib
     import importlib.util
     import os
-    from roborts_edu_slam_b200 import matcher
+    from helpers import ShimBounds
     here = os.path.dirname(os.path.abspath(__file__))
     mods = {}
     import sys
@@ -265,7 +266,7 @@ def test_frontend_maps_oracle_matches_golden(oracle):
     grid = np.full((g.size_y, g.size_x), np.float32(0.5), dtype=np.float32)
     grid[0, 0] = np.float32(g.default_prob)
     cur = synth.GridSpec(g.res, g.sigma, g.size_x, g.size_y, g.off_x, g.off_y, g.default_prob, g.occu_offset, True)
-    bounds = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
+    bounds = ShimBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
     for k, (p, s) in enumerate(zip(poses, pts)):
         fits, geom, pre = bounds.UpdateMapByRange(s, p, 2, True)
         assert fits == bool(zf["stamped"][k])
@@ -279,7 +280,7 @@ def test_frontend_maps_oracle_matches_golden(oracle):
     # publishing map
     pm = oracle.pubmap_new(g.size_x, g.size_y)
     off = (g.off_x, g.off_y)
-    bounds = matcher.MapBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
+    bounds = ShimBounds(g.size_x, g.size_y, g.res, g.off_x, g.off_y, mf.EXTEND)
     for k, (p, s) in enumerate(zip(poses, pts)):
         f = mp.factors(k)
         fits, geom, pre = bounds.UpdateMapByRange(s, p, 0, False)
@@ -299,3 +300,21 @@ def test_frontend_maps_oracle_matches_golden(oracle):
     gfin = synth.GridSpec(g.res, 0.0, occ.shape[1], occ.shape[0], off[0], off[1], 0.5, 0.88, False)
     got = np.array([oracle.map_check_penalize(occ, gfin, pts[-1], q, 100, 2.5, 0.015, True) for q in zp["check_poses"]])
     assert np.array_equal(got, zp["coeff"])
+
+
+def test_config5_full_size_golden(oracle):
+    """BASELINE configs[4] at full size (74.3 M candidates, 7.0e10 evaluations): the restatement, scored per angle slice on
+    all host threads, against the fixture the reference's own code produced (tests/golden/make_config5.py)."""
+    import hashlib
+    from helpers import load_config5_golden
+    sc, z = load_config5_golden()
+    g, p = sc.grid, sc.passes[0]
+    grid = oracle.build_grid(g, sc.base_pts, sc.base_poses)
+    assert sha(grid) == str(z["grid_sha"])
+    centre = oracle.world_to_map(g, sc.seed_pose)
+    assert np.array_equal(centre, z["centre_map"])
+    scores = oracle.scores_threaded(grid, g, sc.scan_pts, p, centre)
+    assert hashlib.sha256(scores.tobytes()).hexdigest() == str(z["scores_sha"])
+    fin = oracle.finish_scores(scores, g, len(sc.scan_pts), p, sc.seed_pose)
+    assert fin["response"] == float(z["response"]) and np.array_equal(fin["pose"], z["pose"]) and np.array_equal(fin["cov"], z["cov"])
+    assert fin["n_avg"] == int(z["n_avg"]) and np.array_equal(fin["best_map"], z["best_map"])

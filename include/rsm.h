@@ -91,7 +91,8 @@ typedef struct rsm_stats {
   /* host wall-clock per phase of a pass, summed (always on): 0 geometry + angle tables + upload,
    * 1 wait for scoring + selection, 2 host stage 1 (best pose, positional covariance),
    * 3 same-(x,y) gather round trip, 4 host stage 2 (angular covariance), 5 exact-sort path,
-   * 6 grid rasterisation calls, 7 reserved */
+   * 6 set-up of a batched back-end step (grid slots, chain lookup), 7 its pipelined chain as a whole (wall clock; with
+   * several lanes the phases 0-5 of the lanes overlap and add up to more than this) */
   double phase_ms[8];
 } rsm_stats;
 

@@ -111,13 +111,18 @@ namespace {
 // Small persistent worker pool for the per-item host work of large batches (angle tables,
 // FindBestCandidate, covariances): items are independent, so the range is cut into chunks that
 // the workers and the calling thread pull from an atomic counter.
+// set while a thread runs one lane of a pipelined chain: per-item loops then run inline (the lanes are the parallelism)
+thread_local bool t_lane_worker = false;
+
 class HostPool {
  public:
+  explicit HostPool(int fixed_threads = 0) : fixed_(fixed_threads) {}
   ~HostPool() { stop(); }
+  void set_threads(int n) { if (n != fixed_ && workers_.empty()) fixed_ = n; }
   void run(int n, int grain, const std::function<void(int, int)>& fn) {
     if (n <= 0) return;
     const int chunks = (n + grain - 1) / grain;
-    if (chunks <= 1 || threads_wanted() <= 1) { fn(0, n); return; }
+    if (chunks <= 1 || threads_wanted() <= 1 || t_lane_worker) { fn(0, n); return; }
     start();
     {
       std::lock_guard<std::mutex> lk(m_);
@@ -130,8 +135,9 @@ class HostPool {
     fn_ = nullptr;
   }
  private:
+  int threads_wanted() const { return fixed_ > 0 ? fixed_ : env_threads(); }
   // RSM_HOST_THREADS caps the pool (one process per GPU shares the host cores with its peers)
-  static int threads_wanted() {
+  static int env_threads() {
     static const int n = [] {
       unsigned hc = std::thread::hardware_concurrency();
       int t = int(std::min<unsigned>(hc ? hc : 1, 16));
@@ -175,6 +181,7 @@ class HostPool {
     for (auto& w : workers_) w.join();
     workers_.clear();
   }
+  int fixed_ = 0;
   std::vector<std::thread> workers_;
   std::mutex m_;
   std::condition_variable cv_, done_cv_;
@@ -214,11 +221,14 @@ struct Lane {
   struct Span { cudaEvent_t a, b; int kc; };
   std::vector<Span> spans;
   size_t ev_used = 0;
+  rsm_stats stats = {};                           // what this lane's passes counted since the last merge into the context's
 };
 
 struct rsm_ctx {
   int device = 0;
   HostPool pool;
+  HostPool lane_pool{1};                          // one thread per lane of a pipelined chain (resized before first use)
+  std::mutex mu;                                  // err string, tensor-map cache: touched by lane threads
   SliceState slice;
   Lane L0;
   std::vector<Lane*> extra_lanes;                 // lanes 1.. (created on first use)
@@ -246,15 +256,26 @@ struct rsm_ctx {
 namespace {
 
 struct PhaseTimer {   // host wall clock, accumulated into rsm_stats::phase_ms
-  rsm_ctx* ctx;
+  rsm_stats* st;
   std::chrono::steady_clock::time_point t;
-  explicit PhaseTimer(rsm_ctx* c) : ctx(c), t(std::chrono::steady_clock::now()) {}
+  explicit PhaseTimer(rsm_stats* s) : st(s), t(std::chrono::steady_clock::now()) {}
   void lap(int phase) {
     auto n = std::chrono::steady_clock::now();
-    ctx->stats.phase_ms[phase] += std::chrono::duration<double, std::milli>(n - t).count();
+    st->phase_ms[phase] += std::chrono::duration<double, std::milli>(n - t).count();
     t = n;
   }
 };
+
+// lane counters -> context counters (by the calling thread, when no lane thread is running)
+void merge_lane_stats(rsm_ctx* ctx, Lane* L) {
+  rsm_stats& a = ctx->stats;
+  rsm_stats& b = L->stats;
+  a.kernel_launches += b.kernel_launches; a.score_launches += b.score_launches; a.evals += b.evals; a.passes += b.passes;
+  a.exact_sort_passes += b.exact_sort_passes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
+  a.score_kernel_ms += b.score_kernel_ms; a.raster_kernel_ms += b.raster_kernel_ms; a.select_kernel_ms += b.select_kernel_ms;
+  for (int i = 0; i < 8; ++i) a.phase_ms[i] += b.phase_ms[i];
+  std::memset(&b, 0, sizeof b);
+}
 
 int fail(rsm_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -263,6 +284,7 @@ int fail(rsm_ctx* ctx, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->err = buf;
   }
   return code;
@@ -286,34 +308,43 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, const rsm_ctx::TmapPair** out) {
+// The pair is copied out under the context's mutex: lane threads share the cache.
+int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, rsm_ctx::TmapPair* out) {
   const auto key = std::make_tuple((const void*)g->d_cells, g->size_x, g->size_y, g->pitch);
-  auto it = ctx->tmaps.find(key);
-  if (it != ctx->tmaps.end()) { *out = &it->second; return RSM_OK; }
-  if (!ctx->encode_tiled) {
-    cudaDriverEntryPointQueryResult q;
-    void* fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
-        q != cudaDriverEntryPointSuccess)
-      return fail(ctx, RSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    ctx->encode_tiled = fn;
+  const char* what = nullptr;
+  int code = 0;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->tmaps.find(key);
+    if (it != ctx->tmaps.end()) { *out = it->second; return RSM_OK; }
+    if (!ctx->encode_tiled) {
+      cudaDriverEntryPointQueryResult q;
+      void* fn = nullptr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+          q != cudaDriverEntryPointSuccess)
+        what = "cuTensorMapEncodeTiled is not available from this driver";
+      else
+        ctx->encode_tiled = fn;
+    }
+    if (!what) {
+      if (ctx->tmaps.size() > 8192) ctx->tmaps.clear();
+      rsm_ctx::TmapPair pair;
+      int bw[2], bh[2];
+      score_staged_boxes(bw, bh);
+      for (int b = 0; b < 2 && !what; ++b) {
+        const cuuint64_t dims[2] = {cuuint64_t(g->size_x), cuuint64_t(g->size_y)};
+        const cuuint64_t strides[1] = {cuuint64_t(g->pitch) * 4};
+        const cuuint32_t box[2] = {cuuint32_t(bw[b]), cuuint32_t(bh[b])};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+            &pair.box[b], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, g->d_cells, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { what = "cuTensorMapEncodeTiled failed"; code = int(r); }
+      }
+      if (!what) { ctx->tmaps.emplace(key, pair); *out = pair; return RSM_OK; }
+    }
   }
-  if (ctx->tmaps.size() > 8192) ctx->tmaps.clear();
-  rsm_ctx::TmapPair pair;
-  int bw[2], bh[2];
-  score_staged_boxes(bw, bh);
-  for (int b = 0; b < 2; ++b) {
-    const cuuint64_t dims[2] = {cuuint64_t(g->size_x), cuuint64_t(g->size_y)};
-    const cuuint64_t strides[1] = {cuuint64_t(g->pitch) * 4};
-    const cuuint32_t box[2] = {cuuint32_t(bw[b]), cuuint32_t(bh[b])};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        &pair.box[b], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, g->d_cells, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, RSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
-  }
-  *out = &ctx->tmaps.emplace(key, pair).first->second;
-  return RSM_OK;
+  return fail(ctx, RSM_ERR_CUDA, "%s (%d)", what, code);
 }
 
 #define CU(call)                                                                              \
@@ -402,9 +433,9 @@ void harvest_profile(rsm_ctx* ctx, Lane* L = nullptr) {
   for (auto& s : L->spans) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
-      if (s.kc == KC_SCORE) ctx->stats.score_kernel_ms += ms;
-      else if (s.kc == KC_SELECT) ctx->stats.select_kernel_ms += ms;
-      else if (s.kc == KC_RASTER) ctx->stats.raster_kernel_ms += ms;
+      if (s.kc == KC_SCORE) L->stats.score_kernel_ms += ms;
+      else if (s.kc == KC_SELECT) L->stats.select_kernel_ms += ms;
+      else if (s.kc == KC_RASTER) L->stats.raster_kernel_ms += ms;
     }
   }
   L->spans.clear();
@@ -609,7 +640,8 @@ bool same_plan(const PassItem& a, const PassItem& b) {
 // ---- launch: host preparation + everything enqueued on the lane's stream ------------------------------
 int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std::vector<int>& act_in, PassMode mode,
                double* scores_out, int64_t scores_cap, int64_t* scores_written, PassRun& R) {
-  PhaseTimer pt(ctx);
+  rsm_stats& ST = lane->stats;
+  PhaseTimer pt(&ST);
   R = PassRun();
   R.lane = lane; R.items = &items; R.act = act_in; R.mode = mode; R.scores_out = scores_out;
   const std::vector<int>& act = R.act;
@@ -873,10 +905,10 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       J.tickets = reinterpret_cast<int*>(dw + o_tickets) + it.ticket_off;
     }
     if (use_staged) {
-      const rsm_ctx::TmapPair* tp = nullptr;
+      rsm_ctx::TmapPair tp;
       rc = grid_tmaps(ctx, it.grid, &tp);
       if (rc) return rc;
-      std::memcpy(up + o_tmaps + size_t(a) * 256, tp, 256);
+      std::memcpy(up + o_tmaps + size_t(a) * 256, &tp, 256);
       J.tmap = dw + o_tmaps + size_t(a) * 256;
     }
     J.divisor = double(g.divisor);
@@ -905,7 +937,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     L.err = J.err; L.job_id = a; L.n_cta = it.sel_ncta;
     L.slice = (it.n_local + it.sel_ncta - 1) / it.sel_ncta;
     l_cta[a] = it.sel_cta0;
-    ctx->stats.evals += it.n_local * g.visited;
+    ST.evals += it.n_local * g.visited;
   }
   s_cta[na] = cta; l_cta[na] = total_sel_cta;
   if (any_fixed && any_float) return fail(ctx, RSM_ERR_UNSUPPORTED, "a batch must not mix fixed-point and float32 grids");
@@ -1006,9 +1038,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     CU(cudaMemcpyAsync(dn, dw + o_best, head_bytes + size_t(pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, st));
     return RSM_OK;
   };
-  ctx->stats.h2d_bytes += up_bytes;
-  ctx->stats.kernel_launches += use_staged ? n_launches : 1;
-  ctx->stats.score_launches++;
+  ST.h2d_bytes += up_bytes;
+  ST.kernel_launches += use_staged ? n_launches : 1;
+  ST.score_launches++;
 
   if (mode == MODE_SCORES) {
     // parity/debug: hand the raw score array of item 0 back
@@ -1020,7 +1052,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     CU(cudaMemcpyAsync(lane->h_down.p, dw + o_err, 4, cudaMemcpyDeviceToHost, st));
     rc = sync_stream(ctx, lane);
     if (rc) return rc;
-    ctx->stats.d2h_bytes += size_t(it.n_local) * 8;
+    ST.d2h_bytes += size_t(it.n_local) * 8;
     if (scores_written) *scores_written = it.n_local;
     int e0; std::memcpy(&e0, lane->h_down.p, 4);
     if (e0 & kErrWindow) return fail(ctx, RSM_ERR_WINDOW, "search window + scan extent leaves the grid");
@@ -1069,7 +1101,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     rc = enqueue_tail();
     if (rc) return rc;
   }
-  ctx->stats.kernel_launches++;
+  ST.kernel_launches++;
   R.pending = true;
   R.blocking = na > 8;
   R.o_best = o_best; R.o_err = o_err; R.o_poolcnt = o_poolcnt; R.o_fcnt = o_fcnt; R.o_ftop = o_ftop;
@@ -1083,8 +1115,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
 int pass_end(rsm_ctx* ctx, PassRun& R) {
   if (!R.pending) return RSM_OK;
   R.pending = false;
-  PhaseTimer pt(ctx);
   Lane* lane = R.lane;
+  rsm_stats& ST = lane->stats;
+  PhaseTimer pt(&ST);
   std::vector<PassItem>& items = *R.items;
   const std::vector<int>& act = R.act;
   const int na = int(act.size());
@@ -1099,7 +1132,7 @@ int pass_end(rsm_ctx* ctx, PassRun& R) {
   double* scores_out = R.scores_out;
   int rc = wait_lane(ctx, lane, R.blocking);
   if (rc) return rc;
-  ctx->stats.d2h_bytes += head_bytes + size_t(pool_first) * sizeof(PoolEntry);
+  ST.d2h_bytes += head_bytes + size_t(pool_first) * sizeof(PoolEntry);
   const unsigned long long* h_best = reinterpret_cast<const unsigned long long*>(dn);
   const int* h_err = reinterpret_cast<const int*>(dn + (o_err - o_best));
   int pool_count = *reinterpret_cast<const int*>(dn + (o_poolcnt - o_best));
@@ -1116,7 +1149,7 @@ int pass_end(rsm_ctx* ctx, PassRun& R) {
                        size_t(pool_count - pool_first) * sizeof(PoolEntry), cudaMemcpyDeviceToHost, st));
     rc = sync_stream(ctx, lane);
     if (rc) return rc;
-    ctx->stats.d2h_bytes += size_t(pool_count - pool_first) * sizeof(PoolEntry);
+    ST.d2h_bytes += size_t(pool_count - pool_first) * sizeof(PoolEntry);
   }
 
   pt.lap(1);
@@ -1257,12 +1290,12 @@ int pass_end(rsm_ctx* ctx, PassRun& R) {
     std::memcpy(lane->h_up.p, gjobs.data(), sizeof(GatherJob) * ng);
     CU(cudaMemcpyAsync(dw + o_gjobs, lane->h_up.p, sizeof(GatherJob) * ng, cudaMemcpyHostToDevice, st));
     CU(launch_gather(ng, st, reinterpret_cast<const GatherJob*>(dw + o_gjobs)));
-    ctx->stats.kernel_launches++;
+    ST.kernel_launches++;
     CU(cudaMemcpyAsync(lane->h_down.p, dw + o_gout, gather_doubles * 8, cudaMemcpyDeviceToHost, st));
     rc = sync_stream(ctx, lane);
     if (rc) return rc;
-    ctx->stats.h2d_bytes += sizeof(GatherJob) * ng;
-    ctx->stats.d2h_bytes += gather_doubles * 8;
+    ST.h2d_bytes += sizeof(GatherJob) * ng;
+    ST.d2h_bytes += gather_doubles * 8;
     pt.lap(3);
     const double* h_g = reinterpret_cast<const double*>(lane->h_down.p);
     ctx->pool.run(ng, 16, [&](int g_begin, int g_end) {
@@ -1291,11 +1324,11 @@ int pass_end(rsm_ctx* ctx, PassRun& R) {
       }
       rc = sync_stream(ctx, lane);
       if (rc) return rc;
-      ctx->stats.d2h_bytes += ex_doubles * 8;
+      ST.d2h_bytes += ex_doubles * 8;
       ctx->pool.run(int(ex.size()), 1, [&](int i0, int i1) {
         for (int i = i0; i < i1; ++i) finish_exact(items[ex[i]], h_sc + ex_off[i]);
       });
-      ctx->stats.exact_sort_passes += int64_t(ex.size());
+      ST.exact_sort_passes += int64_t(ex.size());
     }
   }
   pt.lap(5);
@@ -1317,7 +1350,7 @@ int pass_end(rsm_ctx* ctx, PassRun& R) {
       if (!it.center_map) it.grid->tf.map_to_world(b, it.pose_world);
       it.detail.pose_updated = 1;
     }
-    ctx->stats.passes++;
+    ST.passes++;
   }
   return RSM_OK;
 }
@@ -1418,15 +1451,11 @@ int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* 
       account(pass);
     }
   } else {
-    struct Sub { Lane* lane; int first, count; std::vector<PassItem> items; PassRun run; };
+    // One host thread per lane runs that sub-batch's whole chain: launch pass k, sleep on the lane's event, finalise,
+    // launch pass k + 1.  The lanes' kernels share the GPU stream by stream, so one lane's host stage overlaps the
+    // others' kernels without any lane waiting for another.
+    struct Sub { Lane* lane = nullptr; int first = 0, count = 0, rc = RSM_OK; std::vector<PassItem> items; PassRun run; };
     std::vector<Sub> subs(n_lanes);
-    auto begin_pass = [&](Sub& S, int pass) -> int {
-      for (int k = 0; k < S.count; ++k) { set_pass(S.first + k, pass); S.items[k] = items[S.first + k]; }
-      std::vector<int> act;
-      int rc = pass_geometry(ctx, S.items, act);
-      if (rc) return rc;
-      return pass_begin(ctx, S.lane, S.items, act, MODE_MATCH, nullptr, 0, nullptr, S.run);
-    };
     int rc_all = RSM_OK;
     for (int l = 0; l < n_lanes && rc_all == RSM_OK; ++l) {
       Sub& S = subs[l];
@@ -1439,25 +1468,43 @@ int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* 
         if (cudaEventRecord(ctx->L0.ev_fork, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(S.lane->stream, ctx->L0.ev_fork, 0) != cudaSuccess)
           rc_all = fail(ctx, RSM_ERR_CUDA, "lane fork failed");
       }
-      if (rc_all == RSM_OK && pre) rc_all = (*pre)(S.lane, S.first, S.count);
-      if (rc_all == RSM_OK) rc_all = begin_pass(S, 0);
     }
-    for (int pass = 0; pass < n_pass && rc_all == RSM_OK; ++pass) {
-      for (int l = 0; l < n_lanes && rc_all == RSM_OK; ++l) {
-        Sub& S = subs[l];
-        rc_all = pass_end(ctx, S.run);
-        if (rc_all) break;
+    if (rc_all != RSM_OK) return rc_all;
+    const int device = ctx->device;
+    auto lane_chain = [&](Sub& S) {
+      cudaSetDevice(device);
+      if (pre) { S.rc = (*pre)(S.lane, S.first, S.count); if (S.rc) return; }
+      for (int pass = 0; pass < n_pass; ++pass) {
         for (int k = 0; k < S.count; ++k) {
-          items[S.first + k].response = S.items[k].response;
+          PassItem& it = S.items[k];
+          const int i = S.first + k;
+          it.grid = grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
+          it.param = params[pass];                      // shared parameters on this path
+          it.pose_world = poses + 3 * i; it.cov = covs + 9 * i;
+          it.ang_begin = 0; it.ang_end = -1;
+        }
+        std::vector<int> act;
+        S.rc = pass_geometry(ctx, S.items, act);
+        if (S.rc == RSM_OK) S.rc = pass_begin(ctx, S.lane, S.items, act, MODE_MATCH, nullptr, 0, nullptr, S.run);
+        if (S.rc == RSM_OK) S.rc = pass_end(ctx, S.run);
+        if (S.rc) return;
+        for (int k = 0; k < S.count; ++k) {
           sum[S.first + k] += S.items[k].response;
           if (responses) responses[3 * (S.first + k) + pass] = S.items[k].response;
         }
-        if (pass + 1 < n_pass) rc_all = begin_pass(S, pass + 1);
       }
-    }
+    };
+    ctx->lane_pool.set_threads(8);
+    ctx->lane_pool.run(n_lanes, 1, [&](int l0, int l1) {
+      const bool was = t_lane_worker;
+      t_lane_worker = true;
+      for (int l = l0; l < l1; ++l) lane_chain(subs[l]);
+      t_lane_worker = was;
+    });
+    for (int l = 0; l < n_lanes; ++l) if (subs[l].rc != RSM_OK && rc_all == RSM_OK) rc_all = subs[l].rc;
     if (rc_all != RSM_OK) {
       // leave no launch in flight that reads this call's buffers
-      for (int l = 0; l < n_lanes; ++l) if (subs[l].lane) cudaStreamSynchronize(subs[l].lane->stream);
+      for (int l = 0; l < n_lanes; ++l) cudaStreamSynchronize(subs[l].lane->stream);
       return rc_all;
     }
     // the context's stream continues after every lane (later calls on it may rewrite the grids / points)
@@ -1606,8 +1653,20 @@ int rsm_set_option(rsm_ctx* ctx, int option, int value) {
   }
   return fail(ctx, RSM_ERR_INVALID, "rsm_set_option: unknown option %d or value %d out of range", option, value);
 }
-int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out) { if (!ctx || !out) return RSM_ERR_INVALID; *out = ctx->stats; return RSM_OK; }
-int rsm_reset_stats(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; std::memset(&ctx->stats, 0, sizeof ctx->stats); return RSM_OK; }
+int rsm_get_stats(rsm_ctx* ctx, rsm_stats* out) {
+  if (!ctx || !out) return RSM_ERR_INVALID;
+  merge_lane_stats(ctx, &ctx->L0);
+  for (Lane* L : ctx->extra_lanes) merge_lane_stats(ctx, L);
+  *out = ctx->stats;
+  return RSM_OK;
+}
+int rsm_reset_stats(rsm_ctx* ctx) {
+  if (!ctx) return RSM_ERR_INVALID;
+  std::memset(&ctx->stats, 0, sizeof ctx->stats);
+  std::memset(&ctx->L0.stats, 0, sizeof ctx->L0.stats);
+  for (Lane* L : ctx->extra_lanes) std::memset(&L->stats, 0, sizeof L->stats);
+  return RSM_OK;
+}
 int rsm_synchronize(rsm_ctx* ctx) { if (!ctx) return RSM_ERR_INVALID; DeviceGuard device_guard(ctx); return sync_stream(ctx); }
 
 int rsm_timer_start(rsm_ctx* ctx) {
@@ -2495,6 +2554,7 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
                       bool use_fine, double* poses_world, double* covs, double* scores, double* responses,
                       const rsm_grid* pub_map, const double* const* pub_pts, const int32_t* pub_counts,
                       const rsm_map_check_param* check) {
+  PhaseTimer pt_setup(&ctx->stats);
   RasterPlan pl;
   // use_blur = true as in both shipped configurations; blur parameters the reference's GaussianBlur rejects select the
   // SET_CELL_OCCUPIED update, as there (map/occu_grid_map.h:265-268)
@@ -2557,7 +2617,7 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
     });
     std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
     CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, L->stream));
-    ctx->stats.h2d_bytes += up_bytes;
+    L->stats.h2d_bytes += up_bytes;
     {
       Prof p(ctx, KC_RASTER, L);
       CU(launch_fill(count, 4, L->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
@@ -2565,10 +2625,12 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
         CU(enqueue_raster(pl, L->stream, int(s1 - s0), reinterpret_cast<const RasterScan*>(dw + o_scans),
                           reinterpret_cast<const int*>(dw + o_stamp), count, reinterpret_cast<const int*>(dw + o_groups)));
     }
-    ctx->stats.kernel_launches += 2;
+    L->stats.kernel_launches += 2;
     return RSM_OK;
   };
+  pt_setup.lap(6);
   rc = run_chain(ctx, n, gp.data(), dp, np, params, true, use_fine, poses_world, covs, scores, responses, &pre);
+  pt_setup.lap(7);
   if (rc || !pub_map) return rc;
   // MapCheckPenalize(pub_map_range_data, best_pose, true) on the matched poses (slam_processor.cpp:313-317)
   std::vector<double> coeff(n);

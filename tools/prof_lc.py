@@ -26,5 +26,5 @@ for r in range(reps + 1):
     s = ctx.stats()
     print("run %d: %.2f ms, %.0f matches/s, %.3g evals/s, launches %d, d2h %d B, h2d %d B, exact %d, phases %s" % (
         r, dt * 1e3, npairs / dt, s["evals"] / dt, s["kernel_launches"], s["d2h_bytes"], s["h2d_bytes"], s["exact_sort_passes"],
-        [round(v, 2) for v in s["phase_ms"][:7]]), flush=True)
+        [round(v, 2) for v in s["phase_ms"][:8]]), flush=True)
 print("accepted", int((res[0] > 0.6).sum()))

@@ -16,8 +16,10 @@ chains, mids = [], []
 for sc in pairs:
     chains.append([st.AddRangeData(p, q) for p, q in zip(sc.base_pts, sc.base_poses)])
     mids.append(st.AddRangeData(sc.scan_pts, sc.seed_pose))
-centres = [sc.grid_centre for sc in pairs]
-seeds = [sc.seed_pose for sc in pairs]
+centres = np.array([sc.grid_centre for sc in pairs])
+seeds = np.array([sc.seed_pose for sc in pairs])
+chains = matcher.pack_chains(chains)
+mids = np.array(mids, dtype=np.int32)
 for r in range(reps + 1):
     ctx.reset_stats()
     t0 = time.perf_counter()

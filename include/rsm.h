@@ -449,6 +449,24 @@ int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int6
                            double pose_world[3], double cov[9], double* response,
                            rsm_pass_detail* detail /* nullable */);
 
+/* The same exchange inside the library, over NCCL on the context's own stream (one process per GPU; libnccl.so.2 is
+ * bound at run time, the copy the process already holds if there is one).  Rank 0 draws an id with rsm_comm_unique_id
+ * and hands it to the others by any means (torch.distributed broadcast, MPI, a file); every rank then calls
+ * rsm_comm_init on its context -- collectively, like ncclCommInitRank.  rsm_match_sliced is BasedCorrelationScanMatch::
+ * ScanMatch (scan_match/correlate_scan_matcher.h:784-875) for ONE window cut along the angle index over the ranks
+ * (contiguous slices, earlier ranks one angle more): every rank passes the same grid content, scan, parameters and
+ * seed and receives the same, reference-identical result.  Per match: the slice is scored and selected, its partial is
+ * packed on the device, ncclAllGather (16 KB per rank), host merge, the same-(x,y) columns go straight from the score
+ * array into the exchange buffer, ncclAllGather (<= 9 columns x slice length), host finalisation -- two stream
+ * synchronisations in all.  Exact ties in a consumed set: the slices' scores are all-gathered device to device and
+ * every rank runs the reference's sort on the whole array (detail->exact_sort_used = 1).  world_size 1 needs no NCCL. */
+#define RSM_COMM_ID_BYTES 128
+int rsm_comm_unique_id(void* id_out /* RSM_COMM_ID_BYTES */);
+int rsm_comm_init(rsm_ctx* ctx, int rank, int world_size, const void* id /* RSM_COMM_ID_BYTES; may be NULL for world_size 1 */);
+int rsm_comm_destroy(rsm_ctx* ctx);
+int rsm_match_sliced(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
+                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail /* nullable */);
+
 /* ---- measurement support ------------------------------------------------------------------
  * Gather-bandwidth micro-benchmark used as the roofline denominator of the scoring kernel:
  * mode 0 = shared-memory row segments (32 consecutive 4-byte words per warp load, the access

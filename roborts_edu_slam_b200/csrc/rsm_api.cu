@@ -16,6 +16,7 @@
 // There is no CPU scoring path anywhere in this file.
 #include <cuda.h>           // CUtensorMap types only; the encoder is fetched through the runtime
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <map>
@@ -245,6 +246,11 @@ struct rsm_ctx {
   Buf& h_up = L0.h_up;
   Buf& h_down = L0.h_down;
   Buf d_pts, d_flush, d_pool_grids;
+  // in-library exchange of the angle-sliced match (rsm_comm_init / rsm_match_sliced): an NCCL communicator of this
+  // context's own, exchange buffers on the device and their pinned host mirror
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  Buf d_xchg, h_xchg;
   // staged scoring variant: tensor maps of the grids seen so far, keyed by (cells, size, pitch)
   struct alignas(64) TmapPair { CUtensorMap box[2]; };
   std::map<std::tuple<const void*, int, int, int>, TmapPair> tmaps;
@@ -547,15 +553,6 @@ struct PassItem {
 
 enum PassMode { MODE_MATCH = 0, MODE_SCORES = 1, MODE_PARTIAL = 2 };
 
-constexpr uint32_t kPartialMagic = 0x52534d50u;   // 'RSMP'
-struct PartialHeader {
-  uint32_t magic; int32_t a0, a1, n_ang, n_xy, n_pool, n_top, flags;
-  unsigned long long best_key;
-  double reserved[3];
-};
-static_assert(sizeof(PartialHeader) == 64, "PartialHeader layout");
-struct ColumnsHeader { uint32_t magic; int32_t a0, a1, n_cols; int32_t cols[kMaxCols]; int32_t pad[3]; };
-static_assert(sizeof(ColumnsHeader) == 64, "ColumnsHeader layout");
 
 // exact path: reproduce the reference's sort on a full score array (candidate k of the array = global index base + k)
 void finish_exact_core(const PassGeo& g, const rsm_pass_param& param, std::vector<Cand>& c, BestPose& best, double* cov) {
@@ -1649,8 +1646,10 @@ void rsm_destroy(rsm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (Lane* L : ctx->extra_lanes) { cudaStreamSynchronize(L->stream); destroy_lane(*L); delete L; }
-  Buf* dev[] = {&ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids};
+  rsm_comm_destroy(ctx);
+  Buf* dev[] = {&ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids, &ctx->d_xchg};
   for (Buf* b : dev) if (b->p) cudaFree(b->p);
+  if (ctx->h_xchg.p) cudaFreeHost(ctx->h_xchg.p);
   for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
   destroy_lane(ctx->L0);
@@ -3037,9 +3036,12 @@ int rsm_match_partial(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, 
   return RSM_OK;
 }
 
-int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, void* columns) {
-  DeviceGuard device_guard(ctx);
-  if (!ctx || !partials || n_partials < 1 || !columns) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: bad arguments");
+}  // extern "C"
+
+namespace {
+// Merge every rank's partial: global maximum, averaging set, best pose, global top list, the same-(x,y) columns the
+// angular covariance needs.  Leaves the result in ctx->slice (exact_needed when the reference's sort order matters).
+int merge_core(rsm_ctx* ctx, const void* const* partials, int n_partials) {
   SliceState& S = ctx->slice;
   if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: no rsm_match_partial pending on this context");
   const PassGeo& g = S.geo;
@@ -3050,6 +3052,7 @@ int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, v
     std::memcpy(&H, partials[r], sizeof H);
     if (H.magic != kPartialMagic) return fail(ctx, RSM_ERR_INVALID, "partial %d is not an rsm partial", r);
     if (H.a1 > H.a0 && (H.n_ang != g.n_ang || H.n_xy != g.n_xy)) return fail(ctx, RSM_ERR_INVALID, "partial %d comes from another window", r);
+    if (H.flags & 2) return fail(ctx, RSM_ERR_WINDOW, "search window + scan extent leaves the grid (slice %d)", r);
     if (H.flags & 1) exact = true;
     best_key = std::max(best_key, H.best_key);
   }
@@ -3083,45 +3086,19 @@ int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, v
       else for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) S.cols[S.n_cols++] = xs[i] * g.n_xy + ys[j];
     }
   }
+  if (exact) S.n_cols = 0;
   S.exact_needed = exact;
   S.merged = true;
-  // this rank's column scores
-  ColumnsHeader CH;
-  std::memset(&CH, 0, sizeof CH);
-  CH.magic = kPartialMagic; CH.a0 = S.a0; CH.a1 = S.a1; CH.n_cols = exact ? 0 : S.n_cols;
-  for (int c = 0; c < CH.n_cols; ++c) CH.cols[c] = S.cols[c];
-  const int nang = S.a1 - S.a0;
-  const size_t need = sizeof(ColumnsHeader) + size_t(CH.n_cols) * nang * 8;
-  if (need > RSM_COLUMNS_BYTES) return fail(ctx, RSM_ERR_UNSUPPORTED, "angle slice too long for RSM_COLUMNS_BYTES (%d angles)", nang);
-  std::memcpy(columns, &CH, sizeof CH);
-  if (CH.n_cols > 0 && nang > 0) {
-    GatherJob G;
-    std::memset(&G, 0, sizeof G);
-    G.score = S.d_score; G.out = S.d_gout; G.n_xy = g.n_xy; G.n_ang = nang; G.n_cols = CH.n_cols;
-    for (int c = 0; c < CH.n_cols; ++c) G.cols[c] = CH.cols[c];
-    int rc = ensure_pinned(ctx, ctx->h_up, sizeof G);
-    if (rc) return rc;
-    rc = ensure_pinned(ctx, ctx->h_down, size_t(CH.n_cols) * nang * 8);
-    if (rc) return rc;
-    std::memcpy(ctx->h_up.p, &G, sizeof G);
-    CU(cudaMemcpyAsync(S.d_gjob, ctx->h_up.p, sizeof G, cudaMemcpyHostToDevice, ctx->stream));
-    CU(launch_gather(1, ctx->stream, reinterpret_cast<const GatherJob*>(S.d_gjob)));
-    ctx->stats.kernel_launches++;
-    CU(cudaMemcpyAsync(ctx->h_down.p, S.d_gout, size_t(CH.n_cols) * nang * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    rc = sync_stream(ctx);
-    if (rc) return rc;
-    std::memcpy(static_cast<char*>(columns) + sizeof(ColumnsHeader), ctx->h_down.p, size_t(CH.n_cols) * nang * 8);
-  }
   return RSM_OK;
 }
 
-int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, const void* const* columns,
-                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
-  DeviceGuard device_guard(ctx);
-  if (!ctx || !partials || !columns || n_partials < 1 || !pose_world || !cov || !response)
-    return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: bad arguments");
+// one rank's same-(x,y) column scores: data[c * stride + (ia - a0)]
+struct ColView { int a0, a1, n_cols; const int* cols; const double* data; int stride; };
+
+// Everything after the columns are known; RSM_NEED_EXACT (nothing written) when ties decide.
+int finish_core(rsm_ctx* ctx, const ColView* views, int n_views, double pose_world[3], double cov[9], double* response,
+                rsm_pass_detail* detail) {
   SliceState& S = ctx->slice;
-  if (!S.valid || !S.merged) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: call rsm_match_partial and rsm_match_merge first");
   *response = 0.0;
   if (detail) std::memset(detail, 0, sizeof *detail);
   // exact ties in a consumed set: the slice stays valid for rsm_match_slice_scores / rsm_match_finish_exact
@@ -3141,16 +3118,13 @@ int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, 
   if (type == RSM_COARSE || type == RSM_SUPER) {
     std::vector<Cand> xy;
     if (!(S.best.score < kDoubleTolerance)) {
-      for (int r = 0; r < n_partials; ++r) {
-        ColumnsHeader CH;
-        std::memcpy(&CH, columns[r], sizeof CH);
-        if (CH.magic != kPartialMagic) return fail(ctx, RSM_ERR_INVALID, "columns %d is not an rsm column block", r);
-        const double* col = reinterpret_cast<const double*>(static_cast<const char*>(columns[r]) + sizeof(ColumnsHeader));
-        const int nang = CH.a1 - CH.a0;
-        for (int c = 0; c < CH.n_cols; ++c)
+      for (int r = 0; r < n_views; ++r) {
+        const ColView& V = views[r];
+        const int nang = V.a1 - V.a0;
+        for (int c = 0; c < V.n_cols; ++c)
           for (int ia = 0; ia < nang; ++ia) {
-            const double s = col[size_t(c) * nang + ia];
-            if (s >= bound) xy.push_back(Cand{s, int64_t(CH.a0 + ia) * g.n_xy * g.n_xy + CH.cols[c]});
+            const double s = V.data[size_t(c) * V.stride + ia];
+            if (s >= bound) xy.push_back(Cand{s, int64_t(V.a0 + ia) * g.n_xy * g.n_xy + V.cols[c]});
           }
       }
       if (xy.size() > size_t(kTopK)) { std::nth_element(xy.begin(), xy.begin() + kTopK, xy.end(), by_score_desc); xy.resize(kTopK); }
@@ -3181,28 +3155,10 @@ int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, 
   return RSM_OK;
 }
 
-int rsm_match_slice_scores(rsm_ctx* ctx, double* scores_out, int64_t capacity, int64_t* n_slice) {
-  DeviceGuard device_guard(ctx);
-  if (!ctx || !n_slice || capacity < 0 || (capacity > 0 && !scores_out)) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: bad arguments");
+// the reference's own sort on the whole candidate array (correlate_scan_matcher.h:607-608), slices in angle order
+int finish_exact_slices(rsm_ctx* ctx, const double* const* slices, const int64_t* counts, int n_slices, double pose_world[3],
+                        double cov[9], double* response, rsm_pass_detail* detail) {
   SliceState& S = ctx->slice;
-  if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: no rsm_match_partial pending on this context");
-  const int64_t n = int64_t(S.a1 - S.a0) * S.geo.n_xy * S.geo.n_xy;
-  *n_slice = n;
-  if (capacity == 0 || n == 0) return RSM_OK;
-  if (capacity < n) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: need room for %lld scores", (long long)n);
-  CU(cudaMemcpyAsync(scores_out, S.d_score, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  int rc = sync_stream(ctx);
-  if (rc) return rc;
-  ctx->stats.d2h_bytes += size_t(n) * 8;
-  return RSM_OK;
-}
-
-int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int64_t* counts, int n_slices, double pose_world[3],
-                           double cov[9], double* response, rsm_pass_detail* detail) {
-  if (!ctx || !slices || !counts || n_slices < 1 || !pose_world || !cov || !response)
-    return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: bad arguments");
-  SliceState& S = ctx->slice;
-  if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: no rsm_match_partial pending on this context");
   const PassGeo& g = S.geo;
   int64_t total = 0;
   for (int r = 0; r < n_slices; ++r) {
@@ -3214,7 +3170,6 @@ int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int6
                                        (long long)total, (long long)g.n_cand());
   *response = 0.0;
   if (detail) std::memset(detail, 0, sizeof *detail);
-  // the reference's own sort on the whole candidate array (correlate_scan_matcher.h:607-608), in its candidate order
   std::vector<Cand> c;
   c.resize(static_cast<size_t>(total));
   int64_t k = 0;
@@ -3240,6 +3195,328 @@ int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int6
   ctx->stats.passes++;
   ctx->stats.exact_sort_passes++;
   return RSM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rsm_match_merge(rsm_ctx* ctx, const void* const* partials, int n_partials, void* columns) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !partials || n_partials < 1 || !columns) return fail(ctx, RSM_ERR_INVALID, "rsm_match_merge: bad arguments");
+  int rc = merge_core(ctx, partials, n_partials);
+  if (rc) return rc;
+  SliceState& S = ctx->slice;
+  const PassGeo& g = S.geo;
+  // this rank's column scores
+  ColumnsHeader CH;
+  std::memset(&CH, 0, sizeof CH);
+  CH.magic = kPartialMagic; CH.a0 = S.a0; CH.a1 = S.a1; CH.n_cols = S.n_cols;
+  for (int c = 0; c < CH.n_cols; ++c) CH.cols[c] = S.cols[c];
+  const int nang = S.a1 - S.a0;
+  const size_t need = sizeof(ColumnsHeader) + size_t(CH.n_cols) * nang * 8;
+  if (need > RSM_COLUMNS_BYTES) return fail(ctx, RSM_ERR_UNSUPPORTED, "angle slice too long for RSM_COLUMNS_BYTES (%d angles)", nang);
+  std::memcpy(columns, &CH, sizeof CH);
+  if (CH.n_cols > 0 && nang > 0) {
+    GatherJob G;
+    std::memset(&G, 0, sizeof G);
+    G.score = S.d_score; G.out = S.d_gout; G.n_xy = g.n_xy; G.n_ang = nang; G.n_cols = CH.n_cols;
+    for (int c = 0; c < CH.n_cols; ++c) G.cols[c] = CH.cols[c];
+    rc = ensure_pinned(ctx, ctx->h_up, sizeof G);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, ctx->h_down, size_t(CH.n_cols) * nang * 8);
+    if (rc) return rc;
+    std::memcpy(ctx->h_up.p, &G, sizeof G);
+    CU(cudaMemcpyAsync(S.d_gjob, ctx->h_up.p, sizeof G, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_gather(1, ctx->stream, reinterpret_cast<const GatherJob*>(S.d_gjob)));
+    ctx->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_down.p, S.d_gout, size_t(CH.n_cols) * nang * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    std::memcpy(static_cast<char*>(columns) + sizeof(ColumnsHeader), ctx->h_down.p, size_t(CH.n_cols) * nang * 8);
+  }
+  return RSM_OK;
+}
+
+int rsm_match_finish(rsm_ctx* ctx, const void* const* partials, int n_partials, const void* const* columns,
+                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !partials || !columns || n_partials < 1 || !pose_world || !cov || !response)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: bad arguments");
+  SliceState& S = ctx->slice;
+  if (!S.valid || !S.merged) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish: call rsm_match_partial and rsm_match_merge first");
+  std::vector<ColView> views(n_partials);
+  std::vector<ColumnsHeader> heads(n_partials);
+  for (int r = 0; r < n_partials; ++r) {
+    std::memcpy(&heads[r], columns[r], sizeof(ColumnsHeader));
+    if (heads[r].magic != kPartialMagic) return fail(ctx, RSM_ERR_INVALID, "columns %d is not an rsm column block", r);
+    views[r] = ColView{heads[r].a0, heads[r].a1, heads[r].n_cols, heads[r].cols,
+                       reinterpret_cast<const double*>(static_cast<const char*>(columns[r]) + sizeof(ColumnsHeader)),
+                       heads[r].a1 - heads[r].a0};
+  }
+  return finish_core(ctx, views.data(), n_partials, pose_world, cov, response, detail);
+}
+
+int rsm_match_slice_scores(rsm_ctx* ctx, double* scores_out, int64_t capacity, int64_t* n_slice) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !n_slice || capacity < 0 || (capacity > 0 && !scores_out)) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: bad arguments");
+  SliceState& S = ctx->slice;
+  if (!S.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: no rsm_match_partial pending on this context");
+  const int64_t n = int64_t(S.a1 - S.a0) * S.geo.n_xy * S.geo.n_xy;
+  *n_slice = n;
+  if (capacity == 0 || n == 0) return RSM_OK;
+  if (capacity < n) return fail(ctx, RSM_ERR_INVALID, "rsm_match_slice_scores: need room for %lld scores", (long long)n);
+  CU(cudaMemcpyAsync(scores_out, S.d_score, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.d2h_bytes += size_t(n) * 8;
+  return RSM_OK;
+}
+
+int rsm_match_finish_exact(rsm_ctx* ctx, const double* const* slices, const int64_t* counts, int n_slices, double pose_world[3],
+                           double cov[9], double* response, rsm_pass_detail* detail) {
+  if (!ctx || !slices || !counts || n_slices < 1 || !pose_world || !cov || !response)
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: bad arguments");
+  if (!ctx->slice.valid) return fail(ctx, RSM_ERR_INVALID, "rsm_match_finish_exact: no rsm_match_partial pending on this context");
+  return finish_exact_slices(ctx, slices, counts, n_slices, pose_world, cov, response, detail);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (no link dependency: a caller that never shards one window never loads it)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };      // ncclUniqueId
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // the copy the process already holds (torch loads its own libnccl.so.2), else the system's
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather) api.lib = h;
+  });
+  return api.lib ? &api : nullptr;
+}
+constexpr int kNcclChar = 0;      // ncclInt8 / ncclChar
+
+// items [begin, end) of `rank`: sizes differ by at most one, earlier ranks get the extra (roborts_edu_slam_b200/sharding.py)
+void contiguous_range(int n_items, int rank, int world, int* begin, int* end) {
+  const int base = n_items / world, extra = n_items % world;
+  *begin = rank * base + std::min(rank, extra);
+  *end = *begin + base + (rank < extra ? 1 : 0);
+}
+}  // namespace
+
+extern "C" {
+
+int rsm_comm_unique_id(void* id_out) {
+  if (!id_out) return RSM_ERR_INVALID;
+  NcclApi* N = nccl_api();
+  if (!N) return RSM_ERR_UNSUPPORTED;
+  NcclId id;
+  if (N->GetUniqueId(&id) != 0) return RSM_ERR_CUDA;
+  std::memcpy(id_out, &id, sizeof id);
+  return RSM_OK;
+}
+
+int rsm_comm_init(rsm_ctx* ctx, int rank, int world_size, const void* id) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || world_size < 1 || rank < 0 || rank >= world_size || (world_size > 1 && !id))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_comm_init: bad arguments");
+  if (ctx->comm) return fail(ctx, RSM_ERR_INVALID, "rsm_comm_init: this context already has a communicator");
+  ctx->comm_rank = rank; ctx->comm_world = world_size;
+  if (world_size == 1) return RSM_OK;
+  NcclApi* N = nccl_api();
+  if (!N) return fail(ctx, RSM_ERR_UNSUPPORTED, "rsm_comm_init: libnccl.so.2 could not be loaded");
+  NcclId nid;
+  std::memcpy(&nid, id, sizeof nid);
+  const int r = N->CommInitRank(&ctx->comm, world_size, nid, rank);
+  if (r != 0) { ctx->comm = nullptr; return fail(ctx, RSM_ERR_CUDA, "ncclCommInitRank failed: %s", N->GetErrorString ? N->GetErrorString(r) : "?"); }
+  return RSM_OK;
+}
+
+int rsm_comm_destroy(rsm_ctx* ctx) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx) return RSM_ERR_INVALID;
+  if (ctx->comm) {
+    cudaStreamSynchronize(ctx->stream);
+    if (NcclApi* N = nccl_api()) N->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->comm_rank = 0; ctx->comm_world = 1;
+  return RSM_OK;
+}
+
+// The whole angle-sliced match on every rank of the communicator: score + select the own slice, pack the partial on
+// the device, ncclAllGather, merge on the host, gather the same-(x,y) columns into the exchange buffer, ncclAllGather,
+// finish.  Two stream synchronisations per match; the collectives run on the context's own stream, device to device.
+int rsm_match_sliced(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param* param,
+                     double pose_world[3], double cov[9], double* response, rsm_pass_detail* detail) {
+  DeviceGuard device_guard(ctx);
+  if (!ctx || !grid || !param || !pose_world || !cov || !response || n_pts < 0 || (n_pts > 0 && !pts_xy))
+    return fail(ctx, RSM_ERR_INVALID, "rsm_match_sliced: bad arguments");
+  *response = 0.0;
+  if (detail) std::memset(detail, 0, sizeof *detail);
+  if (!grid->init || n_pts == 0) return RSM_OK;   // correlate_scan_matcher.h:792-795
+  const int world = ctx->comm_world, rank = ctx->comm_rank;
+  NcclApi* N = world > 1 ? nccl_api() : nullptr;
+  if (world > 1 && (!N || !ctx->comm)) return fail(ctx, RSM_ERR_INVALID, "rsm_match_sliced: call rsm_comm_init first");
+  ctx->slice.valid = false;
+  double* d_pts = nullptr;
+  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
+  if (rc) return rc;
+  double pose[3] = {pose_world[0], pose_world[1], pose_world[2]};
+  double cov_unused[9];
+  std::vector<PassItem> items(1);
+  PassItem& it = items[0];
+  it.grid = grid; it.d_pts = d_pts; it.P = n_pts; it.param = *param; it.pose_world = pose; it.cov = cov_unused;
+  std::vector<int> act;
+  rc = pass_geometry(ctx, items, act);      // full window first: n_ang decides the slices
+  if (rc) return rc;
+  if (act.empty()) return fail(ctx, RSM_ERR_INVALID, "rsm_match_sliced: empty search window");
+  const PassGeo geo = it.geo;
+  int max_nang = 0;
+  std::vector<int> a0s(world), a1s(world);
+  for (int r = 0; r < world; ++r) { contiguous_range(geo.n_ang, r, world, &a0s[r], &a1s[r]); max_nang = std::max(max_nang, a1s[r] - a0s[r]); }
+  it.ang_begin = a0s[rank]; it.ang_end = a1s[rank];
+  const bool have_slice = a1s[rank] > a0s[rank];
+  // exchange buffers: [own partial | all partials] then, reused, [own columns | all columns]
+  const size_t col_bytes = size_t(kMaxCols) * max_nang * 8;
+  const size_t unit = std::max<size_t>(kPartialDevBytes, (col_bytes + 255) / 256 * 256);
+  rc = ensure_dev(ctx, ctx->d_xchg, unit * size_t(world + 1));
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_xchg, unit * size_t(world + 1));
+  if (rc) return rc;
+  char* dx = ctx->d_xchg.p;
+  char* hx = ctx->h_xchg.p;
+  Lane* lane = &ctx->L0;
+  cudaStream_t st = ctx->stream;
+  PassRun R;
+  std::vector<char> own_partial(RSM_PARTIAL_BYTES);
+  if (have_slice) {
+    rc = pass_geometry(ctx, items, act);
+    if (rc) return rc;
+    rc = pass_begin(ctx, lane, items, act, MODE_PARTIAL, reinterpret_cast<double*>(own_partial.data()), 0, nullptr, R);
+    if (rc) return rc;
+    // the partial, packed where the selection left it
+    char* dw = lane->d_work.p;
+    PackJob PJ;
+    std::memset(&PJ, 0, sizeof PJ);
+    PJ.best_key = reinterpret_cast<const unsigned long long*>(dw + R.o_best);
+    PJ.err = reinterpret_cast<const int*>(dw + R.o_err);
+    PJ.pool_count = reinterpret_cast<const int*>(dw + R.o_poolcnt);
+    PJ.pool = reinterpret_cast<const PoolEntry*>(dw + R.o_pool);
+    PJ.ftop = reinterpret_cast<const Entry*>(dw + R.o_ftop);
+    PJ.fcnt = reinterpret_cast<const int*>(dw + R.o_fcnt);
+    PJ.base = int64_t(it.a0) * geo.n_xy * geo.n_xy;
+    PJ.pool_cap = R.pool_cap; PJ.a0 = it.a0; PJ.a1 = it.a1; PJ.n_ang = geo.n_ang; PJ.n_xy = geo.n_xy;
+    PJ.out = dx;
+    CU(launch_pack_partial(st, PJ));
+    lane->stats.kernel_launches++;
+  } else {
+    // more ranks than angles: a well-formed empty partial
+    PartialHeader H;
+    std::memset(&H, 0, sizeof H);
+    H.magic = kPartialMagic; H.a0 = H.a1 = a0s[rank];
+    std::memcpy(hx, &H, sizeof H);
+    CU(cudaMemcpyAsync(dx, hx, sizeof H, cudaMemcpyHostToDevice, st));
+  }
+  if (world > 1) {
+    const int r = N->AllGather(dx, dx + unit, kPartialDevBytes, kNcclChar, ctx->comm, st);
+    if (r != 0) return fail(ctx, RSM_ERR_CUDA, "ncclAllGather(partials) failed: %s", N->GetErrorString ? N->GetErrorString(r) : "?");
+  } else {
+    CU(cudaMemcpyAsync(dx + unit, dx, kPartialDevBytes, cudaMemcpyDeviceToDevice, st));
+  }
+  CU(cudaMemcpyAsync(hx + unit, dx + unit, size_t(kPartialDevBytes) * world, cudaMemcpyDeviceToHost, st));
+  // one wait for: scoring, selection, the own read-back, the exchange and the gathered partials
+  if (have_slice) {
+    R.blocking = false;
+    rc = pass_end(ctx, R);        // sets up ctx->slice (scores stay on the device)
+    if (rc) return rc;
+  } else {
+    rc = sync_stream(ctx);
+    if (rc) return rc;
+    SliceState& S0 = ctx->slice;
+    S0.valid = true; S0.merged = false; S0.exact_needed = false; S0.param = *param; S0.grid = grid; S0.geo = geo;
+    S0.a0 = S0.a1 = a0s[rank]; S0.d_score = nullptr; S0.d_gjob = nullptr; S0.d_gout = nullptr;
+  }
+  ctx->stats.d2h_bytes += size_t(kPartialDevBytes) * world;
+  std::vector<const void*> parts(world);
+  for (int r = 0; r < world; ++r) parts[r] = hx + unit + size_t(r) * kPartialDevBytes;
+  rc = merge_core(ctx, parts.data(), world);
+  if (rc) return rc;
+  SliceState& S = ctx->slice;
+  if (!S.exact_needed) {
+    // same-(x,y) columns of every slice: [c * max_nang + ia] per rank; every rank derives the same column list
+    const int nang = S.a1 - S.a0;
+    if (S.n_cols > 0) {
+      if (nang > 0) {
+        GatherJob G;
+        std::memset(&G, 0, sizeof G);
+        G.score = S.d_score; G.out = reinterpret_cast<double*>(dx); G.n_xy = geo.n_xy; G.n_ang = nang; G.n_cols = S.n_cols;
+        for (int c = 0; c < S.n_cols; ++c) G.cols[c] = S.cols[c];
+        CU(launch_gather_columns(st, G, max_nang));
+        ctx->stats.kernel_launches++;
+      }
+      const size_t msg = size_t(S.n_cols) * max_nang * 8;
+      if (world > 1) {
+        const int r = N->AllGather(dx, dx + unit, msg, kNcclChar, ctx->comm, st);
+        if (r != 0) return fail(ctx, RSM_ERR_CUDA, "ncclAllGather(columns) failed: %s", N->GetErrorString ? N->GetErrorString(r) : "?");
+      } else {
+        CU(cudaMemcpyAsync(dx + unit, dx, msg, cudaMemcpyDeviceToDevice, st));
+      }
+      CU(cudaMemcpyAsync(hx + unit, dx + unit, msg * world, cudaMemcpyDeviceToHost, st));
+      rc = sync_stream(ctx);
+      if (rc) return rc;
+      ctx->stats.d2h_bytes += msg * world;
+    }
+    std::vector<ColView> views(world);
+    const size_t msg = size_t(S.n_cols) * max_nang * 8;
+    for (int r = 0; r < world; ++r)
+      views[r] = ColView{a0s[r], a1s[r], S.n_cols, S.cols, reinterpret_cast<const double*>(hx + unit + size_t(r) * msg), max_nang};
+    rc = finish_core(ctx, views.data(), world, pose_world, cov, response, detail);
+    if (rc != RSM_NEED_EXACT) return rc;
+  }
+  // exact ties: every rank gets every slice's scores (device to device), then runs the reference's sort itself
+  const int64_t plane = int64_t(geo.n_xy) * geo.n_xy;
+  const size_t slot = size_t(max_nang) * size_t(plane) * 8;
+  rc = ensure_dev(ctx, ctx->d_xchg, slot * size_t(world + 1));
+  if (rc) return rc;
+  rc = ensure_pinned(ctx, ctx->h_xchg, slot * size_t(world));
+  if (rc) return rc;
+  dx = ctx->d_xchg.p; hx = ctx->h_xchg.p;
+  const int64_t mine = int64_t(S.a1 - S.a0) * plane;
+  if (mine > 0) CU(cudaMemcpyAsync(dx, S.d_score, size_t(mine) * 8, cudaMemcpyDeviceToDevice, st));
+  if (world > 1) {
+    const int r = N->AllGather(dx, dx + slot, slot, kNcclChar, ctx->comm, st);
+    if (r != 0) return fail(ctx, RSM_ERR_CUDA, "ncclAllGather(scores) failed: %s", N->GetErrorString ? N->GetErrorString(r) : "?");
+  } else {
+    CU(cudaMemcpyAsync(dx + slot, dx, slot, cudaMemcpyDeviceToDevice, st));
+  }
+  CU(cudaMemcpyAsync(hx, dx + slot, slot * world, cudaMemcpyDeviceToHost, st));
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  ctx->stats.d2h_bytes += slot * world;
+  std::vector<const double*> sl(world);
+  std::vector<int64_t> cnt(world);
+  for (int r = 0; r < world; ++r) { sl[r] = reinterpret_cast<const double*>(hx + size_t(r) * slot); cnt[r] = int64_t(a1s[r] - a0s[r]) * plane; }
+  return finish_exact_slices(ctx, sl.data(), cnt.data(), world, pose_world, cov, response, detail);
 }
 
 }  // extern "C"

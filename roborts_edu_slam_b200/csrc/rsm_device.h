@@ -104,6 +104,29 @@ struct GatherJob {
   int cols[kMaxCols];    // ix * n_xy + iy
 };
 
+// Angle-sliced single window (include/rsm.h, rsm_match_partial ...): what one rank tells the others about its slice.
+// A partial is this header followed by n_pool averaging-set candidates and n_top top-list candidates, 16 bytes
+// each: {double score, int64 global candidate index}.
+constexpr uint32_t kPartialMagic = 0x52534d50u;   // 'RSMP'
+struct PartialHeader {
+  uint32_t magic; int32_t a0, a1, n_ang, n_xy, n_pool, n_top, flags;   // flags: 1 = exact path needed, 2 = window left the grid
+  unsigned long long best_key;
+  double reserved[3];
+};
+static_assert(sizeof(PartialHeader) == 64, "PartialHeader layout");
+struct ColumnsHeader { uint32_t magic; int32_t a0, a1, n_cols; int32_t cols[kMaxCols]; int32_t pad[3]; };
+static_assert(sizeof(ColumnsHeader) == 64, "ColumnsHeader layout");
+constexpr int kPartialDevBytes = 16384;           // partial as packed on the device for the in-library exchange
+
+// device-side packing of a slice's partial (one job) for rsm_match_sliced
+struct PackJob {
+  const unsigned long long* best_key; const int* err; const int* pool_count; const PoolEntry* pool;
+  const Entry* ftop; const int* fcnt;
+  long long base;        // global index of the slice's first candidate
+  int pool_cap, a0, a1, n_ang, n_xy, pad0;
+  char* out;             // kPartialDevBytes
+};
+
 // One base scan to stamp into one grid.
 struct RasterScan {
   void* grid;

@@ -396,6 +396,48 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherJob* __restrict
   }
 }
 
+// Partial of one slice, packed where it lies (rsm_match_sliced): header, the pool's candidates, the slice's top list.
+__global__ void __launch_bounds__(256) pack_partial_kernel(PackJob J) {
+  PartialHeader* H = reinterpret_cast<PartialHeader*>(J.out);
+  Entry* out = reinterpret_cast<Entry*>(J.out + sizeof(PartialHeader));
+  const int cap = int((kPartialDevBytes - sizeof(PartialHeader)) / sizeof(Entry)) - kTopK;
+  const int e = *J.err;
+  const int count = *J.pool_count;
+  const bool exact = (e & (kErrPoolFull | kErrSelectFull)) || count > J.pool_cap || count > cap;
+  const int n_pool = exact ? 0 : count;
+  const int n_top = *J.fcnt;
+  for (int i = threadIdx.x; i < n_pool; i += blockDim.x) { Entry c; c.score = J.pool[i].score; c.index = J.base + J.pool[i].index; out[i] = c; }
+  for (int i = threadIdx.x; i < n_top; i += blockDim.x) { Entry c = J.ftop[i]; c.index += J.base; out[n_pool + i] = c; }
+  if (threadIdx.x == 0) {
+    PartialHeader h;
+    h.magic = kPartialMagic; h.a0 = J.a0; h.a1 = J.a1; h.n_ang = J.n_ang; h.n_xy = J.n_xy; h.n_pool = n_pool; h.n_top = n_top;
+    h.flags = (exact ? 1 : 0) | ((e & kErrWindow) ? 2 : 0);
+    h.best_key = *J.best_key;
+    h.reserved[0] = h.reserved[1] = h.reserved[2] = 0.0;
+    *H = h;
+  }
+}
+
+cudaError_t launch_pack_partial(cudaStream_t st, const PackJob& job) {
+  pack_partial_kernel<<<1, 256, 0, st>>>(job);
+  return cudaGetLastError();
+}
+
+// same-(x,y) columns of a slice straight into an exchange buffer: out[c * stride + ia]
+__global__ void __launch_bounds__(128) gather_columns_kernel(GatherJob J, int stride) {
+  const long long plane = (long long)J.n_xy * J.n_xy;
+  const int total = J.n_cols * J.n_ang;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i / J.n_ang, ia = i - c * J.n_ang;
+    J.out[(long long)c * stride + ia] = J.score[(long long)ia * plane + J.cols[c]];
+  }
+}
+
+cudaError_t launch_gather_columns(cudaStream_t st, const GatherJob& job, int stride) {
+  gather_columns_kernel<<<4, 128, 0, st>>>(job, stride);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs) {
   gather_kernel<<<n_jobs, 128, 0, st>>>(jobs);
   return cudaGetLastError();

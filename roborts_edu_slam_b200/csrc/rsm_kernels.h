@@ -42,6 +42,8 @@ cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_bea
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);
 cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);
+cudaError_t launch_pack_partial(cudaStream_t st, const PackJob& job);
+cudaError_t launch_gather_columns(cudaStream_t st, const GatherJob& job, int stride);
 cudaError_t launch_fill(int n_jobs, int ctas_per_job, cudaStream_t st, const FillJob* jobs);
 cudaError_t launch_penalty(int n_jobs, cudaStream_t st, const PenaltyJob* jobs, const unsigned char* occ, int size_x,
                            int size_y, double bound_tolerance);

@@ -162,6 +162,10 @@ ABI = {
     "rsm_match_finish": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
     "rsm_match_slice_scores": (c_i, [c_p, c_p, c_i64, ctypes.POINTER(c_i64)]),
     "rsm_match_finish_exact": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
+    "rsm_comm_unique_id": (c_i, [c_p]),
+    "rsm_comm_init": (c_i, [c_p, c_i, c_i, c_p]),
+    "rsm_comm_destroy": (c_i, [c_p]),
+    "rsm_match_sliced": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
 }
 
 _lib = None
@@ -692,14 +696,61 @@ class SlicedScanMatch:
         return resp.value
 
 
-def make_sliced_matcher(ctx, rank, world_size, dist=None):
-    """SlicedScanMatch for a torch.distributed job (one process per GPU): the small all-gathers go through
-    `dist.all_gather` on CUDA byte tensors.  dist = None (world_size 1): no exchange."""
+RSM_COMM_ID_BYTES = 128
+
+
+class CommSlicedScanMatch:
+    """One large window cut along the angle index over the ranks of a job, exchange inside the library over NCCL
+    (rsm_comm_init / rsm_match_sliced).  `broadcast_id(buf)` must hand rank 0's 128-byte id (a uint8 numpy array,
+    filled on rank 0) to every rank and return it; world_size 1 needs neither NCCL nor a broadcast."""
+
+    def __init__(self, ctx, rank, world_size, broadcast_id=None):
+        self.ctx, self.rank, self.world = ctx, rank, world_size
+        self.last_detail = None
+        self.exact_fallback = False
+        self.exchange = "none (one rank)" if world_size == 1 else "in-library ncclAllGather on the context's stream (device buffers)"
+        ident = np.zeros(RSM_COMM_ID_BYTES, dtype=np.uint8)
+        if world_size > 1:
+            if rank == 0:
+                rc = ctx.lib.rsm_comm_unique_id(ident.ctypes.data)
+                if rc != RSM_OK:
+                    raise RsmError(rc, "rsm_comm_unique_id (libnccl.so.2 not loadable?)")
+            ident = np.ascontiguousarray(broadcast_id(ident), dtype=np.uint8)
+        ctx.check(ctx.lib.rsm_comm_init(ctx.h, int(rank), int(world_size), ident.ctypes.data))
+
+    def ScanMatch(self, map_, range_data, scan_match_param, current_pose, cov_matrix):
+        ctx = self.ctx
+        pts = _f64(range_data).reshape(-1, 2)
+        ps = _as_param(scan_match_param).struct()
+        resp, det = c_d(0), PassDetail()
+        ctx.check(ctx.lib.rsm_match_sliced(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps), current_pose.ctypes.data,
+                                           cov_matrix.ctypes.data, ctypes.byref(resp), ctypes.byref(det)))
+        self.last_detail = det
+        self.exact_fallback = bool(det.exact_sort_used)
+        return resp.value
+
+    def close(self):
+        if getattr(self.ctx, "h", None):
+            self.ctx.lib.rsm_comm_destroy(self.ctx.h)
+
+
+def make_sliced_matcher(ctx, rank, world_size, dist=None, in_library=True):
+    """The angle-sliced matcher of a torch.distributed job (one process per GPU).  in_library: the exchange runs
+    inside librsm.so over its own NCCL communicator (the id travels through dist.broadcast once); else the three-call
+    protocol with `dist.all_gather` on host-staged byte tensors.  dist = None (world_size 1): no exchange."""
     if world_size == 1 or dist is None:
+        if in_library:
+            return CommSlicedScanMatch(ctx, rank, 1)
         sm = SlicedScanMatch(ctx, rank, world_size, lambda buf: [buf])
         sm.exchange = "none (one rank)"
         return sm
     import torch
+    if in_library:
+        def broadcast_id(buf):
+            t = torch.from_numpy(buf.copy()).cuda()
+            dist.broadcast(t, src=0)
+            return t.cpu().numpy()
+        return CommSlicedScanMatch(ctx, rank, world_size, broadcast_id)
 
     def all_gather(buf):
         t = torch.from_numpy(np.ascontiguousarray(buf).view(np.uint8)).cuda()

@@ -1218,3 +1218,46 @@ def test_strict_ties_option(ctx, oracle, rng):
     with pytest.raises(matcher.RsmError):
         ctx.set_option(99, 1)
     dg.close()
+
+
+def test_in_library_sliced_match_one_rank(ctx, oracle):
+    """rsm_match_sliced with a one-rank communicator (no NCCL needed): device-side packing of the partial, merge, the
+    column gather into the exchange buffer, finish -- and the gathered exact path on the tie-heavy fixture."""
+    sm = matcher.CommSlicedScanMatch(ctx, 0, 1)
+    fallbacks = 0
+    for sc in (synth.config1(), load_golden("ties_icra")[0], synth.config3(True)):
+        grid = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+        dg = device_grid(ctx, sc)
+        pose_in = sc.seed_pose.copy()
+        for p in sc.passes:
+            want = oracle.match(grid, sc.grid, sc.scan_pts, p, pose_in)
+            pose, cov = pose_in.copy(), np.eye(3)
+            r = sm.ScanMatch(dg, sc.scan_pts, p, pose, cov)
+            assert_pass_equal(r, pose, cov, want)
+            assert sm.last_detail.n_avg == want["n_avg"]
+            if sm.exact_fallback:
+                assert np.array_equal(cov, want["cov"])
+                fallbacks += 1
+            pose_in = want["pose"]
+        dg.close()
+    assert fallbacks >= 1
+    sm.close()
+
+
+def test_in_library_sliced_match_over_nccl():
+    """The same over real ranks: torchrun with one process per visible GPU (needs two or more), every rank compares
+    its result with the oracle (tools/sliced_check.py)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(n, 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tools", "sliced_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("sliced matches equal the oracle") == n

@@ -395,6 +395,7 @@ score_patch_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ ct
   __shared__ ScoreJob J;
   __shared__ int s_job;
   __shared__ __align__(16) int tile[kBoxW * kBoxH];
+  __shared__ __align__(16) int sBase[kAngles][kPC];   // origins of the chunk's beams that passed the index test, compacted
   __shared__ int s_box[kAngles][4];
   __shared__ unsigned long long s_wmax[kAngles];
 
@@ -416,8 +417,11 @@ score_patch_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ ct
   const int ixl = lane & 15, hp = lane >> 4;
   const double x0 = dadd(J.sx, dmul(0.0, J.f)), y0 = dadd(J.sy, dmul(0.0, J.f));   // candidate (0, 0)   (:569, :572)
   const double xc = dadd(J.sx, dmul((double)ixl, J.f));
-  const int* grid = reinterpret_cast<const int*>(J.grid);
+  const int* __restrict__ grid = reinterpret_cast<const int*>(J.grid);
   const int nchunks = (V + kPC - 1) / kPC;
+  const int* const q_tile = tile + hp * kBoxW + ixl;              // this lane's cell of a patch whose origin is tile[0]
+  const int* const q_grid = grid + hp * pitch + ixl;
+  const int* const bases = sBase[warp];
 
   unsigned int a32[NR];
   unsigned long long a64[NR];
@@ -442,70 +446,78 @@ score_patch_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ ct
       ok = active && fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 &&
            gx0 >= 0 && gx0 + 15 < size_x && gy0 >= 0 && gy0 + 2 * NR - 1 < size_y;
     }
-    const int npc = min(kPC, V - c * kPC);
-    // One segment of the chunk's beams [j0, j1): hull of the origins, copy it if it fits the tile, gather.
-    auto segment = [&](int j0, int j1) {
-      const bool mine = ok && lane >= j0 && lane < j1;
-      {
-        const int xmin = __reduce_min_sync(0xffffffffu, mine ? gx0 : 0x7fffffff), xmax = __reduce_max_sync(0xffffffffu, mine ? gx0 : -1);
-        const int ymin = __reduce_min_sync(0xffffffffu, mine ? gy0 : 0x7fffffff), ymax = __reduce_max_sync(0xffffffffu, mine ? gy0 : -1);
-        if (lane == 0) { s_box[warp][0] = xmin; s_box[warp][1] = xmax; s_box[warp][2] = ymin; s_box[warp][3] = ymax; }
+    // hull of the origins of the CTA's 8 angles x 32 beams; copy it to shared memory if hull + patch fit the tile
+    {
+      const int xmin = __reduce_min_sync(0xffffffffu, ok ? gx0 : 0x7fffffff), xmax = __reduce_max_sync(0xffffffffu, ok ? gx0 : -1);
+      const int ymin = __reduce_min_sync(0xffffffffu, ok ? gy0 : 0x7fffffff), ymax = __reduce_max_sync(0xffffffffu, ok ? gy0 : -1);
+      if (lane == 0) { s_box[warp][0] = xmin; s_box[warp][1] = xmax; s_box[warp][2] = ymin; s_box[warp][3] = ymax; }
+    }
+    __syncthreads();
+    int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
+#pragma unroll
+    for (int w = 0; w < kAngles; ++w) {
+      bx0 = min(bx0, s_box[w][0]); bx1 = max(bx1, s_box[w][1]); by0 = min(by0, s_box[w][2]); by1 = max(by1, s_box[w][3]);
+    }
+    const int xl = bx0 & ~3;                                       // 16-byte aligned rows
+    const bool fits = bx1 >= 0 && (bx1 - xl + 16 <= kBoxW) && (by1 - by0 + 2 * NR <= kBoxH);
+    if (tid == 0) { PDBG_ADD(0, 1); PDBG_ADD(1, fits ? 1 : 0); PDBG_ADD(2, bx1 >= 0 ? bx1 - xl + 16 : 0); PDBG_ADD(3, bx1 >= 0 ? by1 - by0 + 2 * NR : 0); }
+    // the warp's safe beams, compacted: the gather loop below has no per-beam branch
+    const unsigned int safe_mask = __ballot_sync(0xffffffffu, ok);
+    const unsigned int slow_mask = __ballot_sync(0xffffffffu, vb && active && !ok);
+    const int n_safe = __popc(safe_mask);
+    if (ok) sBase[warp][__popc(safe_mask & ((1u << lane) - 1u))] = fits ? (gy0 - by0) * kBoxW + (gx0 - xl) : gy0 * pitch + gx0;
+    if (fits) {
+      const int w4 = (bx1 - xl + 16 + 3) >> 2, hh = by1 - by0 + 2 * NR;       // the hull, in int4 columns x rows
+      for (int q = tid; q < w4 * hh; q += kThreads) {
+        const int r = q / w4, c4 = q - r * w4;
+        const int gy = by0 + r, gx = xl + 4 * c4;
+        int4 val = make_int4(0, 0, 0, 0);
+        if (gy < size_y && gx + 3 < pitch) val = __ldg(reinterpret_cast<const int4*>(grid + (size_t)gy * pitch + gx));
+        *reinterpret_cast<int4*>(tile + r * kBoxW + 4 * c4) = val;
       }
       __syncthreads();
-      int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
+      int j = 0;
+      for (; j + 2 <= n_safe; j += 2) {
+        const int2 b2 = *reinterpret_cast<const int2*>(bases + j);
+        const int* qa = q_tile + b2.x;
+        const int* qb = q_tile + b2.y;
+        int va[NR], vbv[NR];
 #pragma unroll
-      for (int w = 0; w < kAngles; ++w) {
-        bx0 = min(bx0, s_box[w][0]); bx1 = max(bx1, s_box[w][1]); by0 = min(by0, s_box[w][2]); by1 = max(by1, s_box[w][3]);
+        for (int k = 0; k < NR; ++k) { va[k] = qa[k * 2 * kBoxW]; vbv[k] = qb[k * 2 * kBoxW]; }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)va[k] + (unsigned int)vbv[k];
       }
-      const int xl = bx0 & ~3;                                       // 16-byte aligned rows
-      const bool fits = bx1 >= 0 && (bx1 - xl + 16 <= kBoxW) && (by1 - by0 + 2 * NR <= kBoxH);
-      if (tid == 0) { PDBG_ADD(0, 1); PDBG_ADD(1, fits ? 1 : 0); PDBG_ADD(2, bx1 >= 0 ? bx1 - xl + 16 : 0); PDBG_ADD(3, bx1 >= 0 ? by1 - by0 + 2 * NR : 0); }
-      if (fits) {
-        const int w4 = (bx1 - xl + 16 + 3) >> 2, hh = by1 - by0 + 2 * NR;       // the hull, in int4 columns x rows
-        for (int q = tid; q < w4 * hh; q += kThreads) {
-          const int r = q / w4, c4 = q - r * w4;
-          const int gy = by0 + r, gx = xl + 4 * c4;
-          int4 val = make_int4(0, 0, 0, 0);
-          if (gy < size_y && gx + 3 < pitch) val = __ldg(reinterpret_cast<const int4*>(grid + (size_t)gy * pitch + gx));
-          *reinterpret_cast<int4*>(tile + r * kBoxW + 4 * c4) = val;
-        }
-        __syncthreads();
+      if (j < n_safe) {
+        const int* qa = q_tile + bases[j];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)qa[k * 2 * kBoxW];
       }
-      if (active) {
-        const int my_base = ok ? (fits ? (gy0 - by0) * kBoxW + (gx0 - xl) : gy0 * pitch + gx0) : -1;
-        for (int j = j0; j < min(j1, npc); ++j) {
-          const int b = __shfl_sync(0xffffffffu, my_base, j);
-          if (b >= 0) {
-            if (fits) {
-              const int* q = tile + b + hp * kBoxW + ixl;
+    } else {
+      __syncwarp();
+      for (int j = 0; j < n_safe; ++j) {
+        const int* qa = q_grid + bases[j];
 #pragma unroll
-              for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)q[k * 2 * kBoxW];
-            } else {
-              const int* q = grid + b + hp * pitch + ixl;
-#pragma unroll
-              for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)__ldg(q + k * 2 * pitch);
-            }
-          } else {
-            // exact indices for this beam: frac(t0) too close to a cell boundary, or the patch touches the grid border
-            const double lxj = __shfl_sync(0xffffffffu, lx, j), lyj = __shfl_sync(0xffffffffu, ly, j);
-            int gx = cell_index(lxj, xc);
-            if (gx < 0 || gx >= size_x) { if (ixl < n_xy) err |= kErrWindow; gx = max(0, min(gx, size_x - 1)); }
-#pragma unroll
-            for (int k = 0; k < NR; ++k) {
-              const int iy = 2 * k + hp;
-              int gy = cell_index(lyj, dadd(J.sy, dmul((double)iy, J.f)));
-              if (gy < 0 || gy >= size_y) { if (iy < n_xy) err |= kErrWindow; gy = max(0, min(gy, size_y - 1)); }
-              a32[k] += (unsigned int)__ldg(grid + (size_t)gy * pitch + gx);
-            }
-          }
-        }
+        for (int k = 0; k < NR; ++k) a32[k] += (unsigned int)__ldg(qa + k * 2 * pitch);
       }
-      __syncthreads();     // the tile and s_box are reused by the next segment
-    };
-    // (measured: retrying the two halves of a chunk whose hull does not fit made half of them fit but bought no time)
-    segment(0, kPC);
+    }
+    // exact indices for the beams whose frac(t0) is too close to a cell boundary, or whose patch touches the grid border
+    for (unsigned int um = slow_mask; um; um &= um - 1u) {
+      const int j = __ffs(um) - 1;
+      const double lxj = __shfl_sync(0xffffffffu, lx, j), lyj = __shfl_sync(0xffffffffu, ly, j);
+      int gx = cell_index(lxj, xc);
+      if (gx < 0 || gx >= size_x) { if (ixl < n_xy) err |= kErrWindow; gx = max(0, min(gx, size_x - 1)); }
 #pragma unroll
-    for (int k = 0; k < NR; ++k) { a64[k] += a32[k]; a32[k] = 0u; }   // <= 32 cells of <= 2^25 per chunk
+      for (int k = 0; k < NR; ++k) {
+        const int iy = 2 * k + hp;
+        int gy = cell_index(lyj, dadd(J.sy, dmul((double)iy, J.f)));
+        if (gy < 0 || gy >= size_y) { if (iy < n_xy) err |= kErrWindow; gy = max(0, min(gy, size_y - 1)); }
+        a32[k] += (unsigned int)__ldg(grid + (size_t)gy * pitch + gx);
+      }
+    }
+    // two beams are added before the spill: <= 32 cells of <= 2^25 per chunk still fit 32 bits (2^30)
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { a64[k] += a32[k]; a32[k] = 0u; }
+    __syncthreads();     // the tile, s_box and sBase are reused by the next chunk
   }
 
   // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum

@@ -30,6 +30,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 
 #include "rsm_device.h"
 #include "rsm_kernels.h"
@@ -687,14 +688,31 @@ __device__ __forceinline__ int to_q(double v) {   // rn(v * 2^16), saturated so 
 // K candidates per thread: a CTA takes K * 256 consecutive candidates, thread t the candidates k0 + t + j * 256.
 // Larger windows (the 11 x 11 x 11 fine pass) amortise the chunk tables over more gathers and keep K independent
 // loads in flight per beam.
+//
+// Per chunk of 32 beams:
+//   1. table: lutq = rn(rotated endpoint * 2^16) per (angle of the CTA, beam), a SAFE bit per entry -- set when, for
+//      every translation of the window, frac(lutq + xq) stays 2 / 65536 away from a cell boundary (so trunc is exact for
+//      all candidates of that angle and beam: no per-candidate test in the gather loop) -- and the hull of the cells
+//      the safe entries can touch;
+//   2. if the hull fits the shared-memory tile (104 x 96 cells), it is copied there with 16-byte loads; every copied
+//      cell then serves up to K * 256 gathers, and a warp's 32 gathers (2-3 grid rows x 5-6 columns) cost one
+//      shared-memory wavefront instead of 2-3 L1 lines;
+//   3. gather: 2 adds, 2 shifts, 1 multiply-add and 1 load per evaluation; entries without the SAFE bit recompute the
+//      index with the exact FP64 expression (~1e-3 of the beams), chunks whose hull does not fit gather from global memory.
+constexpr int kTileW = 104, kTileH = 96;     // pitch = 8 (mod 32): the 2-3 rows a warp's gathers touch fall into disjoint banks
+
 template <bool FIXED, int K>
 __global__ void __launch_bounds__(kThreads, K <= 2 ? 4 : 3)
 score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta_begin, int n_jobs) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ ScoreJob J;
   __shared__ int s_job;
   __shared__ unsigned long long s_wmax[kThreads / 32];
-  __shared__ int2 sLutQ[2][kMaxAngles][kPC];
+  __shared__ int2 sLutQ[kMaxAngles][kPC];
+  __shared__ unsigned int sSafe[kMaxAngles];          // bit b: beam b of the chunk is safe for every candidate of the angle
+  __shared__ int sXq[16], sYq[16];                    // rn(x_i * 2^16) + 2^15 per translation index
+  __shared__ int sHull[kThreads / 32][4];
+  __shared__ __align__(16) int tile[kTileW * kTileH];
 
   if (tid == 0) s_job = find_job(cta_begin, n_jobs, blockIdx.x);
   __syncthreads();
@@ -714,6 +732,11 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
   const int a_first = k0 / plane;
   const int a_last = min(k0 + kThreads * K - 1, n_local - 1) / plane;
   const int n_a = a_last - a_first + 1;
+  if (tid < n_xy) {
+    sXq[tid] = to_q(dadd(J.sx, dmul((double)tid, J.f))) + 32768;     // :569
+    sYq[tid] = to_q(dadd(J.sy, dmul((double)tid, J.f))) + 32768;     // :572
+  }
+  __syncthreads();
   int kk[K], a_rel[K], xq[K], yq[K], cix[K], ciy[K];
   bool live[K];
 #pragma unroll
@@ -724,11 +747,12 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
     const int ia_l = kc / plane, rem = kc - ia_l * plane;
     ciy[j] = rem / n_xy; cix[j] = rem - ciy[j] * n_xy;
     a_rel[j] = ia_l - a_first;
-    xq[j] = to_q(dadd(J.sx, dmul((double)cix[j], J.f))) + 32768;     // :569
-    yq[j] = to_q(dadd(J.sy, dmul((double)ciy[j], J.f))) + 32768;     // :572
+    xq[j] = sXq[cix[j]];
+    yq[j] = sYq[ciy[j]];
   }
+  const int xq_lo = sXq[0], xq_hi = sXq[n_xy - 1], yq_lo = sYq[0], yq_hi = sYq[n_xy - 1];
   const int V = J.V, pitch = J.pitch;
-  const unsigned int size_x = (unsigned int)J.size_x, size_y = (unsigned int)J.size_y;
+  const int size_x = J.size_x, size_y = J.size_y;
   const int nchunks_all = (V + kPC - 1) / kPC;
   const int per_split = (nchunks_all + S - 1) / S;
   const int c_begin = min(split * per_split, nchunks_all);
@@ -736,21 +760,7 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
   const int* gridI = reinterpret_cast<const int*>(J.grid);
   const float* gridF = reinterpret_cast<const float*>(J.grid);
 
-  // fixed-point rotated endpoints of chunk c for the CTA's angles   (:179-180)
-  auto lut_chunk = [&](int c) {
-    const int npc = min(kPC, V - c * kPC);
-    for (int q = tid; q < n_a * kPC; q += kThreads) {
-      const int a = q / kPC, pc = q % kPC;
-      if (pc < npc) {
-        const int ja = J.ang_begin + a_first + a;
-        const double cs = __ldg(J.trig + 3 * ja), sn = __ldg(J.trig + 3 * ja + 1);
-        const int p = (c * kPC + pc) * J.step;
-        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
-        sLutQ[c & 1][a][pc] = make_int2(to_q(dsub(dmul(cs, px), dmul(sn, py))), to_q(dadd(dmul(sn, px), dmul(cs, py))));
-      }
-    }
-  };
-  // exact FP64 index of (candidate j, beam v): the fixed-point value is within 2^-15 of a cell boundary, or off the grid
+  // exact FP64 index of (candidate j, beam v)
   auto exact_index = [&](int j, int v, int* err) -> int {
     const int ia = J.ang_begin + a_first + a_rel[j];
     const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1);
@@ -758,10 +768,10 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
     const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
     int gx = cell_index(dsub(dmul(cs, px), dmul(sn, py)), dadd(J.sx, dmul((double)cix[j], J.f)));      // :647-648
     int gy = cell_index(dadd(dmul(sn, px), dmul(cs, py)), dadd(J.sy, dmul((double)ciy[j], J.f)));
-    if ((unsigned int)gx >= size_x || (unsigned int)gy >= size_y) {
+    if ((unsigned int)gx >= (unsigned int)size_x || (unsigned int)gy >= (unsigned int)size_y) {
       if (live[j]) *err = kErrWindow;
-      gx = max(0, min(gx, (int)size_x - 1));
-      gy = max(0, min(gy, (int)size_y - 1));
+      gx = max(0, min(gx, size_x - 1));
+      gy = max(0, min(gy, size_y - 1));
     }
     return gy * pitch + gx;
   };
@@ -772,39 +782,103 @@ score_flat_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ cta
 #pragma unroll
   for (int j = 0; j < K; ++j) { a32[j] = 0u; a64[j] = 0ull; ad[j] = 0.0; }
   int err = 0;
-  if (c_begin < nchunks) lut_chunk(c_begin);
-  __syncthreads();
   for (int c = c_begin; c < nchunks; ++c) {
-    if (c + 1 < nchunks) lut_chunk(c + 1);
     const int npc = min(kPC, V - c * kPC);
+    // ---- 1. table, SAFE bits, hull: warp w takes the angles w, w + 8, ...; lane = beam of the chunk ----
+    int hx0 = 0x7fffffff, hx1 = -1, hy0 = 0x7fffffff, hy1 = -1;
+    for (int a = warp; a < n_a; a += kThreads / 32) {
+      bool safe = false;
+      if (lane < npc) {
+        const int ja = J.ang_begin + a_first + a;
+        const double cs = __ldg(J.trig + 3 * ja), sn = __ldg(J.trig + 3 * ja + 1);
+        const int p = (c * kPC + lane) * J.step;
+        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+        const int qx = to_q(dsub(dmul(cs, px), dmul(sn, py))), qy = to_q(dadd(dmul(sn, px), dmul(cs, py)));   // :179-180
+        sLutQ[a][lane] = make_int2(qx, qy);
+        safe = true;
+        for (int i = 0; i < n_xy; ++i) {
+          const unsigned int fx = (unsigned int)(qx + sXq[i] - 2) & 0xffffu, fy = (unsigned int)(qy + sYq[i] - 2) & 0xffffu;
+          if (fx > 65531u || fy > 65531u) safe = false;
+        }
+        // cells the window's candidates touch for this beam (xq ascending with the translation index)
+        const int gx_lo = (qx + xq_lo) >> 16, gx_hi = (qx + xq_hi) >> 16, gy_lo = (qy + yq_lo) >> 16, gy_hi = (qy + yq_hi) >> 16;
+        if (gx_lo < 0 || gx_hi >= size_x || gy_lo < 0 || gy_hi >= size_y) safe = false;     // off the grid: exact path reports it
+        if (safe) { hx0 = min(hx0, gx_lo); hx1 = max(hx1, gx_hi); hy0 = min(hy0, gy_lo); hy1 = max(hy1, gy_hi); }
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, safe);
+      if (lane == 0) sSafe[a] = m;
+    }
+    hx0 = __reduce_min_sync(0xffffffffu, hx0); hx1 = __reduce_max_sync(0xffffffffu, hx1);
+    hy0 = __reduce_min_sync(0xffffffffu, hy0); hy1 = __reduce_max_sync(0xffffffffu, hy1);
+    if (lane == 0) { sHull[warp][0] = hx0; sHull[warp][1] = hx1; sHull[warp][2] = hy0; sHull[warp][3] = hy1; }
+    __syncthreads();
+    int bx0 = 0x7fffffff, bx1 = -1, by0 = 0x7fffffff, by1 = -1;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      bx0 = min(bx0, sHull[w][0]); bx1 = max(bx1, sHull[w][1]); by0 = min(by0, sHull[w][2]); by1 = max(by1, sHull[w][3]);
+    }
+    const int xl = bx0 & ~3;                                        // 16-byte aligned rows
+    const bool fits = bx1 >= 0 && (bx1 - xl + 1 <= kTileW) && (by1 - by0 + 1 <= kTileH);
+    // ---- 2. the hull into shared memory ----
+    if (fits) {
+      const int w4 = (bx1 - xl + 1 + 3) >> 2, hh = by1 - by0 + 1;
+      for (int q = tid; q < w4 * hh; q += kThreads) {
+        const int r = q / w4, c4 = q - r * w4;
+        const int gx = xl + 4 * c4;
+        int4 val = make_int4(0, 0, 0, 0);
+        if (gx + 3 < pitch) val = __ldg(reinterpret_cast<const int4*>(gridI + (size_t)(by0 + r) * pitch + gx));
+        *reinterpret_cast<int4*>(tile + r * kTileW + 4 * c4) = val;
+      }
+      __syncthreads();
+    }
+    // ---- 3. gather ----
+    // Four specialised loops: cells from the tile or from global memory; with or without the per-entry SAFE test.
+    // A warp takes the test-free loop unless one of its lanes' angles has an unsafe beam in this chunk (~10 % of the
+    // warp-chunks), so the common loop is 2 adds, 2 shifts, a multiply-add and a load per evaluation.
+    const unsigned int valid = npc == kPC ? 0xffffffffu : ((1u << npc) - 1u);
     const int2* l[K];
+    unsigned int slow[K];
+    bool any_slow = false;
 #pragma unroll
-    for (int j = 0; j < K; ++j) l[j] = sLutQ[c & 1][a_rel[j]];
-#pragma unroll 2
-    for (int pc = 0; pc < npc; ++pc) {
-      int at[K];
+    for (int j = 0; j < K; ++j) {
+      l[j] = sLutQ[a_rel[j]];
+      slow[j] = ~sSafe[a_rel[j]] & valid;
+      any_slow = any_slow || slow[j] != 0u;
+    }
+    any_slow = __any_sync(0xffffffffu, any_slow);
+    auto gather = [&](auto in_tile, auto checked) {
+      constexpr bool TILE = decltype(in_tile)::value, CHECK = decltype(checked)::value;
+      const int org = TILE ? by0 * kTileW + xl : 0;                 // tile index = gy * kTileW + gx - org
+      const int row = TILE ? kTileW : pitch;
+#pragma unroll 4
+      for (int pc = 0; pc < npc; ++pc) {
+        int vv[K];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const int2 e = l[j][pc];
-        const int tx = e.x + xq[j], ty = e.y + yq[j];
-        const int gx = tx >> 16, gy = ty >> 16;
-        const bool ok = (((unsigned int)(tx - 2) & 0xffffu) <= 65531u) && (((unsigned int)(ty - 2) & 0xffffu) <= 65531u) &&
-                        (unsigned int)gx < size_x && (unsigned int)gy < size_y;
-        at[j] = gy * pitch + gx;
-        if (!ok) at[j] = exact_index(j, c * kPC + pc, &err);
+        for (int j = 0; j < K; ++j) {
+          const int2 e = l[j][pc];
+          const int at = ((e.y + yq[j]) >> 16) * row + ((e.x + xq[j]) >> 16) - org;
+          if (CHECK && ((slow[j] >> pc) & 1u)) vv[j] = __ldg(gridI + exact_index(j, c * kPC + pc, &err));
+          else vv[j] = TILE ? tile[at] : __ldg(gridI + at);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          if (FIXED) a32[j] += (unsigned int)vv[j];
+          else ad[j] = dadd(ad[j], (double)__int_as_float(vv[j]));
+        }
       }
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        if (FIXED) a32[j] += (unsigned int)__ldg(gridI + at[j]);
-        else ad[j] = dadd(ad[j], (double)__ldg(gridF + at[j]));
-      }
+    };
+    if (fits) {
+      if (any_slow) gather(std::true_type{}, std::true_type{}); else gather(std::true_type{}, std::false_type{});
+    } else {
+      if (any_slow) gather(std::false_type{}, std::true_type{}); else gather(std::false_type{}, std::false_type{});
     }
     if (FIXED) {
 #pragma unroll
       for (int j = 0; j < K; ++j) { a64[j] += a32[j]; a32[j] = 0u; }
     }
-    __syncthreads();
+    __syncthreads();      // the table, the SAFE bits and the tile are rewritten by the next chunk
   }
+  (void)gridF;
 
   if (FIXED && S > 1) {
     __shared__ int s_ticket;

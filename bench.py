@@ -564,11 +564,57 @@ def main():
         widened["frontend_update"] = entry
         fine.close()
         pubm.close()
+        # (4) the 4-line drop-in on LIVE reference objects (oracle/_ref/libdropin.so = the product's C++ adapter compiled
+        #     against the unmodified reference headers): per accepted scan, the shipped front-end sequence -- coarse / fine /
+        #     super chain on the fine map (0.01 m, 2400^2), then UpdateMapByRange at the matched pose -- through
+        #     rsm_adapter::BasedCorrelationScanMatch + rsm_adapter::UpdateMapByRange, beside the reference's own classes
+        if args.cpu_reps > 0:
+            from oracle.oracle_py import DropIn, Ref, dropin_available, ref_available
+            if dropin_available() and ref_available():
+                R_, D_ = Ref(), DropIn(local_rank)
+                passes_f = synth.chain_defaults((100, 100, 200))
+                ma, mr = R_.frontend_map_create(gfine, 0.2), R_.frontend_map_create(gfine, 0.2)
+                for m_ in (ma, mr):
+                    R_.frontend_map_update(m_, fine_pts[0], tr[0], True)
+                seeds_f = [tr[k] + np.array([0.03, -0.02, 0.015]) for k in range(24)]
+                same_f = True
+
+                def run_ref(k):
+                    w_ = R_.match_chain(mr, fine_pts[k], passes_f, seeds_f[k])
+                    R_.frontend_map_update(mr, fine_pts[k], w_["pose"], True)
+                    return w_
+
+                def run_adapter(k):
+                    g_ = D_.match_chain(ma, fine_pts[k], passes_f, seeds_f[k])
+                    D_.update_map(ma, fine_pts[k], g_["pose"], True, gfine.sigma, gfine.occu_offset)
+                    return g_
+                for k in range(1, 4):        # warm-up: first sync uploads the whole plane once
+                    w_, g_ = run_ref(k), run_adapter(k)
+                    same_f = same_f and g_["score"] == w_["score"] and np.array_equal(g_["pose"], w_["pose"])
+                full0, inc0 = D_.sync_counts()
+                t0 = time.perf_counter()
+                outs_a = [run_adapter(k) for k in range(4, 24)]
+                dta = (time.perf_counter() - t0) / 20
+                t0 = time.perf_counter()
+                outs_r = [run_ref(k) for k in range(4, 24)]
+                dtr = (time.perf_counter() - t0) / 20
+                full1, inc1 = D_.sync_counts()
+                same_f = same_f and all(a_["score"] == b_["score"] and np.array_equal(a_["pose"], b_["pose"]) and
+                                        np.allclose(a_["cov"], b_["cov"], rtol=1e-6, atol=0.0) for a_, b_ in zip(outs_a, outs_r))
+                widened["dropin_frontend"] = {"ms_per_scan": dta * 1e3, "cpu_ms_per_scan_1core": dtr * 1e3, "speedup": dtr / dta,
+                                              "whole_map_uploads": full1 - full0, "incremental_updates": inc1 - inc0,
+                                              "mirror_equals_host": D_.mirror_equals_host(ma) == 1, "equals_cpu": bool(same_f)}
+                R_.destroy_map(ma)
+                R_.destroy_map(mr)
+                D_.close()
         details["widened"] = {
             "map_check": "MapCheckPenalize, 4096 candidate poses x one 1081-point scan, check_point_num 100, logistic (loop-closure form); host wall clock",
             "optimize": "BasedOptimizeScanMatch, 128 problems (config-4 pairs, 1081-beam scans, 480^2 grids), yaml knobs; host wall clock",
             "frontend_update": "per accepted scan (1081 beams): UpdateMapByRange on the fine scan-match map (0.01 m, 2400^2, blur) and on the "
-                               "publishing map (0.05 m, 480^2, ray-traced free space), both resident on the device; host wall clock, host scan in"}
+                               "publishing map (0.05 m, 480^2, ray-traced free space), both resident on the device; host wall clock, host scan in",
+            "dropin_frontend": "per accepted scan on LIVE reference objects: coarse/fine/super chain (shipped use_point_size 100/100/200) on the "
+                               "fine map (0.01 m, 2400^2) + UpdateMapByRange at the matched pose, through the C++ adapter "
+                               "(csrc/scan_matcher_adapter.hpp compiled against the unmodified reference headers) vs the reference's own classes"}
 
     # ---- the other single-match configurations of BASELINE.json (N = 1 only): latency of one call, host in -> host out --
     small = None

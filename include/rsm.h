@@ -204,6 +204,10 @@ int rsm_map_bounds_size_check(rsm_map_bounds* bounds, const double pose_world[3]
 int rsm_grid_fill(rsm_ctx* ctx, rsm_grid* grid, float fill_prob, float first_cell_prob);
 int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
                              const double* pts_xy, int n_pts, const double pose_world[3]);
+/* The same for a caller that owns the world<->map transform (the C++ adapter mirrors a live reference map, whose
+ * map_offset_ is private: it passes GetMapCoordsPose(sensor_pose), map/grid_map_base.h:83-87). */
+int rsm_grid_update_by_range_map(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
+                                 const double* pts_xy, int n_pts, const double pose_map[3]);
 int rsm_grid_extend(rsm_ctx* ctx, rsm_grid* grid, int new_size_x, int new_size_y, int pre_grid_offset_x,
                     int pre_grid_offset_y, double new_offset_x, double new_offset_y, float fill_prob,
                     float first_cell_prob);

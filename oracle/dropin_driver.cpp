@@ -7,6 +7,7 @@
 // Output: oracle/_ref/libdropin.so, linked against roborts_edu_slam_b200/librsm.so.
 #include <algorithm>
 #include <cassert>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -20,11 +21,12 @@
 using namespace roborts_slam;
 
 namespace {
-std::shared_ptr<RangeDataContainer2d> MakeScan(int n, const double* xy) {
+std::shared_ptr<RangeDataContainer2d> MakeScan(int n, const double* xy, const double* pose_world = nullptr) {
   auto rd = std::make_shared<RangeDataContainer2d>(n > 0 ? n : 1);
   for (int i = 0; i < n; ++i) rd->AddDataPoint(Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]));
   rd->set_sensor_origin(Eigen::Vector2d(0.0, 0.0));
-  rd->set_sensor_pose(Eigen::Vector3d(0.0, 0.0, 0.0));
+  if (pose_world) rd->set_sensor_pose(Eigen::Vector3d(pose_world[0], pose_world[1], pose_world[2]));
+  else rd->set_sensor_pose(Eigen::Vector3d(0.0, 0.0, 0.0));
   return rd;
 }
 std::shared_ptr<CorrelationScanMatchParam> MakeParam(const double* p) {
@@ -76,6 +78,29 @@ double dropin_match_chain(void* h, void* ref_map, int n, const double* xy, const
 
 // the adapter's Gauss-Newton class on a live reference map: op = {iterate_max_times, cost_decrease_threshold,
 // cost_min_threshold, max_update_distance, max_update_angle}; returns the cost, pose_world in/out
+// rsm_adapter::UpdateMapByRange in place of map->UpdateMapByRange (slam_processor.cpp:556,558): the reference's own
+// update on the live host map + the same stamp on the device mirror.  1 = stamped, 0 = the map was extended instead.
+int dropin_update_map(void* ref_map, int n, const double* xy, const double* pose_world, int use_blur, double deviation,
+                      double occu_offset) {
+  auto* rm = static_cast<RefMap*>(ref_map);
+  return rsm_adapter::UpdateMapByRange(rm->map, MakeScan(n, xy, pose_world), use_blur != 0, deviation, occu_offset) ? 1 : 0;
+}
+
+// 1 = the device mirror of the map holds exactly the host map's cells, 0 = it differs, -1 = no mirror
+int dropin_mirror_equals_host(void* ref_map) {
+  auto* rm = static_cast<RefMap*>(ref_map);
+  const std::vector<float> dev = rsm_adapter::DeviceMaps::Get(0).DownloadMirror(rm->map);
+  const int n = rm->map->GetSizeX() * rm->map->GetSizeY();
+  if (dev.empty() || static_cast<int>(dev.size()) != n) return -1;
+  for (int i = 0; i < n; ++i) if (dev[i] != rm->map->GetCellValue(i)) return 0;
+  return 1;
+}
+
+void dropin_sync_counts(long* full_uploads, long* incremental_updates) {
+  *full_uploads = rsm_adapter::DeviceMaps::Get(0).full_uploads();
+  *incremental_updates = rsm_adapter::DeviceMaps::Get(0).incremental_updates();
+}
+
 void* dropin_opt_create(int device) {
   try { return new rsm_adapter::BasedOptimizeScanMatch(device); } catch (...) { return nullptr; }
 }

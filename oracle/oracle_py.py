@@ -412,6 +412,11 @@ class Ref:
         ok = self.L.ref_frontend_map_update(m, len(pts), pts.ctypes.data, pose.ctypes.data, int(use_blur), geom.ctypes.data)
         return bool(ok), (int(geom[0]), int(geom[1]), float(geom[2]), float(geom[3]))
 
+    def map_size(self, m):
+        sx, sy = c_i(0), c_i(0)
+        self.L.ref_map_size(m, ctypes.byref(sx), ctypes.byref(sy))
+        return sx.value, sy.value
+
     def frontend_map_size_check(self, m, pose_world, range_max, offset):
         pose = _f64(pose_world)
         geom = np.zeros(4)
@@ -533,6 +538,11 @@ class DropIn:
         L.dropin_destroy.argtypes = [c_p]
         L.dropin_match_chain.restype = c_d
         L.dropin_match_chain.argtypes = [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        L.dropin_update_map.restype = c_i
+        L.dropin_update_map.argtypes = [c_p, c_i, c_p, c_p, c_i, c_d, c_d]
+        L.dropin_mirror_equals_host.restype = c_i
+        L.dropin_mirror_equals_host.argtypes = [c_p]
+        L.dropin_sync_counts.argtypes = [ctypes.POINTER(c_l), ctypes.POINTER(c_l)]
         L.dropin_opt_create.restype = c_p
         L.dropin_opt_create.argtypes = [c_i]
         L.dropin_opt_destroy.argtypes = [c_p]
@@ -571,3 +581,17 @@ class DropIn:
         s = self.L.dropin_match_chain(self.h, ref_map, len(pts), pts.ctypes.data, params.ctypes.data, n_pass,
                                       pose.ctypes.data, cov.ctypes.data, resp.ctypes.data, ctypes.byref(used))
         return dict(score=s, pose=pose, cov=cov, responses=resp, exact_used=used.value)
+
+    def update_map(self, ref_map, pts_cells, pose_world, use_blur, deviation, occu_offset):
+        """rsm_adapter::UpdateMapByRange: the reference's own update on the host map + the stamp on the device mirror."""
+        pts, pose = _f64(pts_cells), _f64(pose_world)
+        return bool(self.L.dropin_update_map(ref_map, len(pts), pts.ctypes.data, pose.ctypes.data, int(use_blur), float(deviation),
+                                             float(occu_offset)))
+
+    def mirror_equals_host(self, ref_map):
+        return self.L.dropin_mirror_equals_host(ref_map)
+
+    def sync_counts(self):
+        a, b = c_l(0), c_l(0)
+        self.L.dropin_sync_counts(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value

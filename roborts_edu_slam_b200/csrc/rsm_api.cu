@@ -1919,9 +1919,11 @@ cudaError_t enqueue_raster(const RasterPlan& pl, cudaStream_t st, int n_scans, c
 }
 
 // Fill the RasterScan of one base scan (host libm cos/sin = Eigen::Rotation2Dd, occu_grid_map.h:278-303)
-void make_raster_scan(const rsm_grid* g, const double* pose_world, const double* d_pts, int n_pts, RasterScan& S) {
+void make_raster_scan(const rsm_grid* g, const double* pose_world, const double* d_pts, int n_pts, RasterScan& S,
+                      bool pose_in_map = false) {
   double pm[3];
-  g->tf.world_to_map(pose_world, pm);
+  if (pose_in_map) { pm[0] = pose_world[0]; pm[1] = pose_world[1]; pm[2] = pose_world[2]; }
+  else g->tf.world_to_map(pose_world, pm);
   const double c = std::cos(pm[2]), s = std::sin(pm[2]);
   S.grid = g->d_cells; S.pts = d_pts; S.n_pts = n_pts;
   S.pitch = g->pitch; S.size_x = g->size_x; S.size_y = g->size_y;
@@ -2012,8 +2014,24 @@ int rsm_grid_fill(rsm_ctx* ctx, rsm_grid* grid, float fill_prob, float first_cel
   return RSM_OK;
 }
 
+}  // extern "C"
+namespace {
+int grid_update_core(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur, const double* pts_xy, int n_pts,
+                     const double pose_world[3], bool pose_in_map);
+}
+extern "C" {
 int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
                              const double* pts_xy, int n_pts, const double pose_world[3]) {
+  return grid_update_core(ctx, grid, sigma, occu_offset, use_blur, pts_xy, n_pts, pose_world, false);
+}
+int rsm_grid_update_by_range_map(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur,
+                                 const double* pts_xy, int n_pts, const double pose_map[3]) {
+  return grid_update_core(ctx, grid, sigma, occu_offset, use_blur, pts_xy, n_pts, pose_map, true);
+}
+}  // extern "C"
+namespace {
+int grid_update_core(rsm_ctx* ctx, rsm_grid* grid, double sigma, double occu_offset, int use_blur, const double* pts_xy, int n_pts,
+                     const double pose_world[3], bool pose_in_map) {
   DeviceGuard device_guard(ctx);
   if (!ctx || !grid || n_pts < 0 || (n_pts > 0 && !pts_xy) || !pose_world)
     return fail(ctx, RSM_ERR_INVALID, "rsm_grid_update_by_range: bad arguments");
@@ -2048,7 +2066,7 @@ int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double 
   if (n_pts) { rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts); if (rc) return rc; }
   char* up = ctx->h_up.p;
   char* dw = ctx->d_work.p;
-  make_raster_scan(grid, pose_world, d_pts, n_pts, *reinterpret_cast<RasterScan*>(up + o_scan));
+  make_raster_scan(grid, pose_world, d_pts, n_pts, *reinterpret_cast<RasterScan*>(up + o_scan), pose_in_map);
   std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
   const int groups[2] = {0, 1};
   std::memcpy(up + o_groups, groups, sizeof groups);
@@ -2065,6 +2083,8 @@ int rsm_grid_update_by_range(rsm_ctx* ctx, rsm_grid* grid, double sigma, double 
   grid->init = true;      // SetUpdated() (occu_grid_map.h:325)
   return RSM_OK;
 }
+}  // namespace
+extern "C" {
 
 int rsm_grid_extend(rsm_ctx* ctx, rsm_grid* grid, int new_size_x, int new_size_y, int pre_grid_offset_x, int pre_grid_offset_y,
                     double new_offset_x, double new_offset_y, float fill_prob, float first_cell_prob) {

@@ -16,16 +16,19 @@
 //   * the pose is adopted only when response > response_threshold (:866-869);
 //   * world <-> map conversions use the reference map's own GetMapCoordsPose / GetWorldCoordsPose,
 //     so they are whatever Eigen computes in the host build.
-// The lookup grid is handed to the device whenever the live map changed (map_update_index(),
-// size or address); INTEGRATION.md shows how to avoid that copy by building the grid on the
-// device (rsm_grid_rasterize) and how to batch loop-closure candidates.
+// The lookup grid is mirrored on the device (DeviceMaps below, shared by both adapter classes): uploaded
+// whole when the live map changed behind the mirror's back, stamped incrementally when the map update goes
+// through rsm_adapter::UpdateMapByRange (two more edited lines, slam/slam_processor.cpp:556,558).
+// INTEGRATION.md also shows how to keep the maps on the device only and how to batch loop-closure candidates.
 //
 // Link with -lrsm.  Not thread-safe per instance, like the reference (scan_match_mutex_).
 #ifndef RSM_SCAN_MATCHER_ADAPTER_HPP_
 #define RSM_SCAN_MATCHER_ADAPTER_HPP_
 
 #include <cstdint>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -34,16 +37,138 @@
 
 namespace rsm_adapter {
 
-class BasedCorrelationScanMatch {
+// One context per device and one device mirror per live reference map, shared by the correlative and the Gauss-Newton
+// adapter (and by every instance of them): a map is uploaded once, not once per adapter class.  The mirror follows the
+// host map in two ways:
+//   * Sync()             whole-plane upload when the host map changed behind the mirror's back (another map_update_index()
+//                        than the mirror saw, another size or scale) -- always correct, 33 ms for a 2400^2 fine map;
+//   * UpdateMapByRange() the drop-in for the two calls at slam/slam_processor.cpp:556,558: runs the reference's own
+//                        map->UpdateMapByRange(range_data, use_blur) and stamps the same scan on the mirror
+//                        (rsm_grid_update_by_range_map, 0.1 ms), so the next match finds the mirror current.  The map's
+//                        deviation and gaussian_blur_offset are private there, hence the two extra arguments (the call
+//                        site has them in param_).  An update that resized the host map leaves the mirror stale and the
+//                        next Sync() uploads the new plane.
+// All entry points take the registry's mutex: the reference calls the matcher from two threads (scan_match_mutex_) and
+// the map update from a third lock (map_mutex_), while a context is not re-entrant.
+class DeviceMaps {
  public:
-  explicit BasedCorrelationScanMatch(int device = 0) {
+  static DeviceMaps& Get(int device = 0) {
+    // (never destroyed: at process exit the CUDA runtime may already be gone)
+    static std::mutex table_mu;
+    static std::map<int, DeviceMaps*>* table = new std::map<int, DeviceMaps*>();
+    std::lock_guard<std::mutex> lk(table_mu);
+    DeviceMaps*& slot = (*table)[device];
+    if (!slot) slot = new DeviceMaps(device);
+    return *slot;
+  }
+  ~DeviceMaps() {
+    for (auto& kv : mirrors_) if (kv.second.grid) rsm_grid_destroy(ctx_, kv.second.grid);
+    if (ctx_) rsm_destroy(ctx_);
+  }
+  std::recursive_mutex& mutex() { return mu_; }
+  rsm_ctx* context() const { return ctx_; }
+  long full_uploads() const { return full_uploads_; }
+  long incremental_updates() const { return incremental_updates_; }
+
+  // the device grid of a live map, uploaded if the mirror is stale (call with mutex() held)
+  rsm_grid* Sync(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr) {
+    roborts_slam::ScanMatchMap& map = *map_ptr;
+    Mirror& M = mirror_of(map_ptr);
+    const int sx = map.GetSizeX(), sy = map.GetSizeY();
+    if (M.grid && sx == M.sx && sy == M.sy && map.map_update_index() == M.update && map.get_scale_factor() == M.scale) return M.grid;
+    if (!M.grid || sx != M.sx || sy != M.sy || map.get_scale_factor() != M.scale) {
+      if (M.grid) { rsm_grid_destroy(ctx_, M.grid); M.grid = nullptr; }
+      // the adapters do world<->map with the live map's own transform, so the offset handed to the library is irrelevant
+      if (rsm_grid_create_from_scale(ctx_, sx, sy, map.get_scale_factor(), 0.0, 0.0, &M.grid) != RSM_OK)
+        throw std::runtime_error(std::string("rsm_grid_create failed: ") + rsm_last_error(ctx_));
+    }
+    cells_.resize(static_cast<size_t>(sx) * sy);
+    for (int i = 0; i < sx * sy; ++i) cells_[i] = map.GetCellValue(i);   // ProbabilityCell::prob_value_
+    if (rsm_grid_upload_f32(ctx_, M.grid, cells_.data()) != RSM_OK)
+      throw std::runtime_error(std::string("rsm_grid_upload_f32 failed: ") + rsm_last_error(ctx_));
+    M.sx = sx; M.sy = sy; M.update = map.map_update_index(); M.scale = map.get_scale_factor();
+    ++full_uploads_;
+    return M.grid;
+  }
+
+  // OccuGridMap::UpdateMapByRange on the host map and, when the mirror was current, the same stamp on the device
+  bool UpdateMapByRange(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr,
+                        const std::shared_ptr<roborts_slam::RangeDataContainer2d>& range_data, bool use_blur,
+                        double deviation, double gaussian_blur_offset) {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
+    roborts_slam::ScanMatchMap& map = *map_ptr;
+    Mirror& M = mirror_of(map_ptr);
+    const bool current = M.grid && map.GetSizeX() == M.sx && map.GetSizeY() == M.sy && map.map_update_index() == M.update &&
+                         map.get_scale_factor() == M.scale;
+    // the pose in map cells BEFORE the host update: an update that extends the map moves its offset
+    const Eigen::Vector3d pose_map = map.GetMapCoordsPose(range_data->sensor_pose());     // occu_grid_map.h:278
+    const bool stamped = map.UpdateMapByRange(range_data, use_blur);
+    if (!current || !stamped || map.GetSizeX() != M.sx || map.GetSizeY() != M.sy) return stamped;   // next Sync() uploads
+    const int n = range_data->GetSize();
+    pts_.resize(2 * static_cast<size_t>(n));
+    for (int i = 0; i < n; ++i) {
+      const Eigen::Vector2d& p = range_data->GetDataPoint(i);
+      pts_[2 * i] = p[0];
+      pts_[2 * i + 1] = p[1];
+    }
+    const double pm[3] = {pose_map[0], pose_map[1], pose_map[2]};
+    if (rsm_grid_update_by_range_map(ctx_, M.grid, deviation, gaussian_blur_offset, use_blur ? 1 : 0, pts_.data(), n, pm) == RSM_OK) {
+      M.update = map.map_update_index();
+      ++incremental_updates_;
+    }
+    return stamped;
+  }
+
+  // test aid: the mirror's cells (empty if the map has no mirror)
+  std::vector<float> DownloadMirror(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr) {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
+    Mirror& M = mirror_of(map_ptr);
+    std::vector<float> out;
+    if (!M.grid) return out;
+    out.resize(static_cast<size_t>(M.sx) * M.sy);
+    if (rsm_grid_download_f32(ctx_, M.grid, out.data()) != RSM_OK) out.clear();
+    return out;
+  }
+
+ private:
+  struct Mirror {
+    rsm_grid* grid = nullptr;
+    std::weak_ptr<roborts_slam::ScanMatchMap> map;
+    int sx = 0, sy = 0, update = -2;
+    double scale = 0.0;
+  };
+  explicit DeviceMaps(int device) {
     const int rc = rsm_create(device, &ctx_);
     if (rc != RSM_OK) throw std::runtime_error("rsm_create failed (status " + std::to_string(rc) + "): no CUDA device, and there is no CPU path");
   }
-  ~BasedCorrelationScanMatch() {
-    if (grid_) rsm_grid_destroy(ctx_, grid_);
-    if (ctx_) rsm_destroy(ctx_);
+  // a weak_ptr tells a new map object at a recycled address from the one that was mirrored
+  Mirror& mirror_of(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr) {
+    for (auto it = mirrors_.begin(); it != mirrors_.end();) {
+      if (it->second.map.expired()) { if (it->second.grid) rsm_grid_destroy(ctx_, it->second.grid); it = mirrors_.erase(it); }
+      else ++it;
+    }
+    Mirror& M = mirrors_[map_ptr.get()];
+    if (M.map.lock() != map_ptr) { if (M.grid) rsm_grid_destroy(ctx_, M.grid); M = Mirror(); M.map = map_ptr; }
+    return M;
   }
+  rsm_ctx* ctx_ = nullptr;
+  std::recursive_mutex mu_;
+  std::map<const void*, Mirror> mirrors_;
+  std::vector<float> cells_;
+  std::vector<double> pts_;
+  long full_uploads_ = 0, incremental_updates_ = 0;
+};
+
+// drop-in for map->UpdateMapByRange(range_data, use_blur) on a scan-match map (slam/slam_processor.cpp:556,558)
+inline bool UpdateMapByRange(const std::shared_ptr<roborts_slam::ScanMatchMap>& map,
+                             const std::shared_ptr<roborts_slam::RangeDataContainer2d>& range_data, bool use_blur,
+                             double deviation, double gaussian_blur_offset, int device = 0) {
+  return DeviceMaps::Get(device).UpdateMapByRange(map, range_data, use_blur, deviation, gaussian_blur_offset);
+}
+
+class BasedCorrelationScanMatch {
+ public:
+  explicit BasedCorrelationScanMatch(int device = 0) : maps_(DeviceMaps::Get(device)), ctx_(maps_.context()) {}
   BasedCorrelationScanMatch(const BasedCorrelationScanMatch&) = delete;
   BasedCorrelationScanMatch& operator=(const BasedCorrelationScanMatch&) = delete;
 
@@ -55,7 +180,8 @@ class BasedCorrelationScanMatch {
       LOG(WARNING) << "Invalid scan match input !";
       return 0.0;
     }
-    SyncGrid(map);
+    std::lock_guard<std::recursive_mutex> lk(maps_.mutex());
+    rsm_grid* grid_ = maps_.Sync(map);
     const int n = range_data->GetSize();
     pts_.resize(2 * static_cast<size_t>(n));
     for (int i = 0; i < n; ++i) {
@@ -94,38 +220,11 @@ class BasedCorrelationScanMatch {
 
   const rsm_pass_detail& last_detail() const { return last_detail_; }
   rsm_ctx* context() const { return ctx_; }
+  DeviceMaps& maps() { return maps_; }
 
  private:
-  // Hand the live map's prob_value_ plane to the device when it changed since the last call.
-  // "Changed" = another map object (a weak_ptr tells a new object at a recycled address from the
-  // one that was synced), another size / scale, or another update index: every write to the
-  // cells goes through UpdateMapByRange, which ends in SetUpdated() (occu_grid_map.h:325).
-  void SyncGrid(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr) {
-    roborts_slam::ScanMatchMap& map = *map_ptr;
-    const int sx = map.GetSizeX(), sy = map.GetSizeY();
-    const bool same = grid_ && seen_map_.lock() == map_ptr && sx == seen_sx_ && sy == seen_sy_ &&
-                      map.map_update_index() == seen_update_ && map.get_scale_factor() == seen_scale_;
-    if (same) return;
-    if (!grid_ || sx != seen_sx_ || sy != seen_sy_ || map.get_scale_factor() != seen_scale_) {
-      if (grid_) { rsm_grid_destroy(ctx_, grid_); grid_ = nullptr; }
-      // the adapter does world<->map itself, so the offset handed to the library is irrelevant
-      if (rsm_grid_create_from_scale(ctx_, sx, sy, map.get_scale_factor(), 0.0, 0.0, &grid_) != RSM_OK)
-        throw std::runtime_error(std::string("rsm_grid_create failed: ") + rsm_last_error(ctx_));
-    }
-    cells_.resize(static_cast<size_t>(sx) * sy);
-    for (int i = 0; i < sx * sy; ++i) cells_[i] = map.GetCellValue(i);   // ProbabilityCell::prob_value_
-    if (rsm_grid_upload_f32(ctx_, grid_, cells_.data()) != RSM_OK)
-      throw std::runtime_error(std::string("rsm_grid_upload_f32 failed: ") + rsm_last_error(ctx_));
-    seen_map_ = map_ptr; seen_sx_ = sx; seen_sy_ = sy;
-    seen_update_ = map.map_update_index(); seen_scale_ = map.get_scale_factor();
-  }
-
+  DeviceMaps& maps_;
   rsm_ctx* ctx_ = nullptr;
-  rsm_grid* grid_ = nullptr;
-  std::weak_ptr<roborts_slam::ScanMatchMap> seen_map_;
-  int seen_sx_ = 0, seen_sy_ = 0, seen_update_ = -2;
-  double seen_scale_ = 0.0;
-  std::vector<float> cells_;
   std::vector<double> pts_;
   rsm_pass_detail last_detail_{};
 };
@@ -140,14 +239,7 @@ class BasedCorrelationScanMatch {
 // the last cost.  World <-> map uses the live map's own transform.
 class BasedOptimizeScanMatch {
  public:
-  explicit BasedOptimizeScanMatch(int device = 0) {
-    const int rc = rsm_create(device, &ctx_);
-    if (rc != RSM_OK) throw std::runtime_error("rsm_create failed (status " + std::to_string(rc) + "): no CUDA device, and there is no CPU path");
-  }
-  ~BasedOptimizeScanMatch() {
-    if (grid_) rsm_grid_destroy(ctx_, grid_);
-    if (ctx_) rsm_destroy(ctx_);
-  }
+  explicit BasedOptimizeScanMatch(int device = 0) : maps_(DeviceMaps::Get(device)), ctx_(maps_.context()) {}
   BasedOptimizeScanMatch(const BasedOptimizeScanMatch&) = delete;
   BasedOptimizeScanMatch& operator=(const BasedOptimizeScanMatch&) = delete;
 
@@ -160,7 +252,8 @@ class BasedOptimizeScanMatch {
       LOG(WARNING) << "Invalid scan match input !";
       return kMaxCost;
     }
-    SyncGrid(map);
+    std::lock_guard<std::recursive_mutex> lk(maps_.mutex());
+    rsm_grid* grid_ = maps_.Sync(map);
     const int n = range_data->GetSize();
     pts_.resize(2 * static_cast<size_t>(n));
     for (int i = 0; i < n; ++i) {
@@ -191,31 +284,8 @@ class BasedOptimizeScanMatch {
   int last_iterations() const { return last_iterations_; }
 
  private:
-  void SyncGrid(const std::shared_ptr<roborts_slam::ScanMatchMap>& map_ptr) {
-    roborts_slam::ScanMatchMap& map = *map_ptr;
-    const int sx = map.GetSizeX(), sy = map.GetSizeY();
-    const bool same = grid_ && seen_map_.lock() == map_ptr && sx == seen_sx_ && sy == seen_sy_ &&
-                      map.map_update_index() == seen_update_ && map.get_scale_factor() == seen_scale_;
-    if (same) return;
-    if (!grid_ || sx != seen_sx_ || sy != seen_sy_ || map.get_scale_factor() != seen_scale_) {
-      if (grid_) { rsm_grid_destroy(ctx_, grid_); grid_ = nullptr; }
-      if (rsm_grid_create_from_scale(ctx_, sx, sy, map.get_scale_factor(), 0.0, 0.0, &grid_) != RSM_OK)
-        throw std::runtime_error(std::string("rsm_grid_create failed: ") + rsm_last_error(ctx_));
-    }
-    cells_.resize(static_cast<size_t>(sx) * sy);
-    for (int i = 0; i < sx * sy; ++i) cells_[i] = map.GetCellValue(i);
-    if (rsm_grid_upload_f32(ctx_, grid_, cells_.data()) != RSM_OK)
-      throw std::runtime_error(std::string("rsm_grid_upload_f32 failed: ") + rsm_last_error(ctx_));
-    seen_map_ = map_ptr; seen_sx_ = sx; seen_sy_ = sy;
-    seen_update_ = map.map_update_index(); seen_scale_ = map.get_scale_factor();
-  }
-
+  DeviceMaps& maps_;
   rsm_ctx* ctx_ = nullptr;
-  rsm_grid* grid_ = nullptr;
-  std::weak_ptr<roborts_slam::ScanMatchMap> seen_map_;
-  int seen_sx_ = 0, seen_sy_ = 0, seen_update_ = -2;
-  double seen_scale_ = 0.0;
-  std::vector<float> cells_;
   std::vector<double> pts_;
   int32_t last_iterations_ = 0;
 };

@@ -124,6 +124,7 @@ ABI = {
     "rsm_map_bounds_size_check": (c_i, [c_p, c_p, c_d, c_d, ctypes.POINTER(c_i), ctypes.POINTER(MapGeometryStruct)]),
     "rsm_grid_fill": (c_i, [c_p, c_p, ctypes.c_float, ctypes.c_float]),
     "rsm_grid_update_by_range": (c_i, [c_p, c_p, c_d, c_d, c_i, c_p, c_i, c_p]),
+    "rsm_grid_update_by_range_map": (c_i, [c_p, c_p, c_d, c_d, c_i, c_p, c_i, c_p]),
     "rsm_grid_extend": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, ctypes.c_float, ctypes.c_float]),
     "rsm_grid_geometry": (c_i, [c_p, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_d), ctypes.POINTER(c_d)]),
     "rsm_grid_upload_occupancy": (c_i, [c_p, c_p, c_p]),

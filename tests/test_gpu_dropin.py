@@ -95,3 +95,44 @@ def test_optimize_adapter_on_live_reference_objects(ref, dropin):
             assert got["cost"] == 1000.0 and np.array_equal(got["pose"], seed)
         finally:
             ref.destroy_map(m)
+
+
+def frontend_sequence(n_scans=14):
+    """A front-end run on the willow map: (fine GridSpec, [(pose, scan in fine-map cells)])."""
+    occ = synth.load_map("willow")
+    tr = [np.array([14.375 + 0.06 * k, 28.625 + 0.025 * k, 0.3 + 0.012 * k]) for k in range(n_scans)]
+    g = synth.backend_grid(0.01, 0.03, 10.0, tr[0][:2])
+    scans = [synth.raycast(occ, p[0], p[1], p[2], 1081, np.deg2rad(270.25), 10.0) * (1 / 0.01) for p in tr]
+    return g, tr, scans
+
+
+def test_frontend_through_the_adapter(ref, dropin):
+    """The shipped front-end call sequence on live reference objects -- match the new scan against the fine map
+    (coarse / fine / super chain, scan_matchers.h:224-263), then insert it at the matched pose (slam_processor.cpp:558) --
+    with the adapter's matcher and rsm_adapter::UpdateMapByRange against the reference's own classes, step by step.
+    The device mirror is uploaded ONCE and then follows the host map through the incremental stamps."""
+    g, tr, scans = frontend_sequence()
+    passes = synth.chain_defaults((100, 100, 200))
+    ma, mr = ref.frontend_map_create(g, 0.2), ref.frontend_map_create(g, 0.2)
+    full0, inc0 = dropin.sync_counts()
+    try:
+        for m in (ma, mr):
+            ref.frontend_map_update(m, scans[0], tr[0], True)
+        stamped = 0
+        for k in range(1, len(scans)):
+            seed = tr[k] + np.array([0.03, -0.02, 0.015])
+            want = ref.match_chain(mr, scans[k], passes, seed)
+            got = dropin.match_chain(ma, scans[k], passes, seed)
+            assert got["score"] == want["score"] and np.array_equal(got["pose"], want["pose"]) and cov_close(got["cov"], want["cov"]), k
+            ok_r = ref.frontend_map_update(mr, scans[k], want["pose"], True)[0]
+            ok_a = dropin.update_map(ma, scans[k], got["pose"], True, g.sigma, g.occu_offset)
+            assert ok_r == ok_a
+            stamped += int(ok_a)
+        assert dropin.mirror_equals_host(ma) == 1
+        sx, sy = ref.map_size(ma)
+        assert np.array_equal(ref.read_map_sized(ma, sx, sy), ref.read_map_sized(mr, sx, sy))
+        full1, inc1 = dropin.sync_counts()
+        assert full1 - full0 == 1 and inc1 - inc0 == stamped and stamped >= 10, (full1 - full0, inc1 - inc0, stamped)
+    finally:
+        ref.destroy_map(ma)
+        ref.destroy_map(mr)

@@ -392,6 +392,25 @@ int rsm_match_chain_opt(rsm_ctx* ctx, const rsm_grid* coarse_grid, const double*
                         double optimize_failed_cost, int use_fine, double pose_world[3], double cov[9],
                         double* score, double responses[4] /* nullable */);
 
+/* rsm_scan_match_interface_batch with the Gauss-Newton pre-step (use_optimize_scan_match, the reference's in-code default,
+ * scan_match/scan_matchers.h:205-232): ScanMatchInterface resets BOTH back-end maps from the chain
+ * (slam/slam_processor.cpp:282-285) -- the coarse one from coarse_store, whose scan i is scan i of fine_store in
+ * coarse-map cells -- runs the optimiser on the coarse map, keeps its pose when cost <= optimize_failed_cost and
+ * the fine passes follow, else runs the coarse correlative pass on the fine map from the seed; then fine and
+ * super-fine.  scores[i] = the reference's average (optimize_failed_cost / (cost + optimize_failed_cost) stands in
+ * for the dropped coarse response), map check as above.  responses (nullable): 4 per candidate -- optimiser cost,
+ * coarse, fine, super-fine responses (0 for a step not run). */
+int rsm_scan_match_interface_batch_opt(rsm_ctx* ctx, const rsm_scan_store* fine_store, const rsm_scan_store* coarse_store,
+                                       int n, int grid_size, double resolution, double sigma, int coarse_grid_size,
+                                       double coarse_resolution, double coarse_sigma, float default_prob,
+                                       double occu_offset, const double* centres_world, const int64_t* chain_offset,
+                                       const int32_t* chain_ids, const int32_t* match_ids,
+                                       const rsm_pass_param params[3], const rsm_optimize_param* optimize,
+                                       double optimize_failed_cost, int use_fine, double* poses_world, double* covs,
+                                       double* scores, double* responses /* nullable, 4 per candidate */,
+                                       const rsm_grid* pub_map /* nullable */, const rsm_scan_store* pub_store /* nullable */,
+                                       const rsm_map_check_param* check /* nullable */);
+
 /* ---- map rebuilds from the scan store ---------------------------------------------------------
  * SlamProcessor::CorrectPoseAndMap (slam/slam_processor.cpp:329-371) rebuilds all three maps from every
  * stored scan at its corrected pose after a loop closure: InitMapWithRangeVec = Reset + one

@@ -245,7 +245,7 @@ struct rsm_ctx {
   Buf& d_work = L0.d_work;
   Buf& h_up = L0.h_up;
   Buf& h_down = L0.h_down;
-  Buf d_pts, d_flush, d_pool_grids;
+  Buf d_pts, d_flush, d_pool_grids, d_pool_grids2;
   // in-library exchange of the angle-sliced match (rsm_comm_init / rsm_match_sliced): an NCCL communicator of this
   // context's own, exchange buffers on the device and their pinned host mirror
   void* comm = nullptr;
@@ -1429,13 +1429,14 @@ int chain_lanes(const rsm_ctx* ctx, int n) {
 // step -- on that lane's stream.
 int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* d_pts, const int* n_pts,
               const rsm_pass_param* params, bool shared_params, bool use_fine, double* poses, double* covs,
-              double* scores, double* responses, const std::function<int(Lane*, int, int)>* pre = nullptr) {
+              double* scores, double* responses, const std::function<int(Lane*, int, int)>* pre = nullptr,
+              const unsigned char* skip_first = nullptr) {   // skip_first[i]: item i does not run pass 0 (its response is 0)
   std::vector<PassItem> items(n);
   std::vector<double> sum(n, 0.0);
   const int n_pass = use_fine ? 3 : 1;
   auto set_pass = [&](int i, int pass) {
     PassItem& it = items[i];
-    it.grid = grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
+    it.grid = (skip_first && skip_first[i] && pass == 0) ? nullptr : grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
     it.param = params[(shared_params ? 0 : 3 * i) + pass];
     it.pose_world = poses + 3 * i; it.cov = covs + 9 * i;
     it.ang_begin = 0; it.ang_end = -1;
@@ -1491,7 +1492,7 @@ int run_chain(rsm_ctx* ctx, int n, const rsm_grid* const* grids, double* const* 
         for (int k = 0; k < S.count; ++k) {
           PassItem& it = S.items[k];
           const int i = S.first + k;
-          it.grid = grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
+          it.grid = (skip_first && skip_first[i] && pass == 0) ? nullptr : grids[i]; it.d_pts = d_pts[i]; it.P = n_pts[i];
           it.param = params[pass];                      // shared parameters on this path
           it.pose_world = poses + 3 * i; it.cov = covs + 9 * i;
           it.ang_begin = 0; it.ang_end = -1;
@@ -1647,7 +1648,7 @@ void rsm_destroy(rsm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (Lane* L : ctx->extra_lanes) { cudaStreamSynchronize(L->stream); destroy_lane(*L); delete L; }
   rsm_comm_destroy(ctx);
-  Buf* dev[] = {&ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids, &ctx->d_xchg};
+  Buf* dev[] = {&ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids, &ctx->d_pool_grids2, &ctx->d_xchg};
   for (Buf* b : dev) if (b->p) cudaFree(b->p);
   if (ctx->h_xchg.p) cudaFreeHost(ctx->h_xchg.p);
   for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
@@ -2583,90 +2584,174 @@ struct BaseRef { const double* d_pts; int n; const double* pose_world; };   // o
 // grid_size^2 grid centred on centres_world[2i..] from the pair's base scans (:448-462), run the chain, and --
 // when a publishing map is given -- scale the score by the map check and clamp it to 1 (:313-317).
 // base[scan_offset[i] .. scan_offset[i+1]) = base scans of pair i, all points already on the device.
-int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob, double sigma,
-                      double occu_offset, const double* centres_world, const int64_t* scan_offset,
-                      const std::vector<BaseRef>& base, double* const* dp, const int* np, const rsm_pass_param* params,
-                      bool use_fine, double* poses_world, double* covs, double* scores, double* responses,
-                      const rsm_grid* pub_map, const double* const* pub_pts, const int32_t* pub_counts,
-                      const rsm_map_check_param* check) {
-  PhaseTimer pt_setup(&ctx->stats);
+// The Gauss-Newton pre-step of the back-end chain (ScanMatchers::ScanMatch with use_optimize_scan_match_, the in-code
+// default; scan_match/scan_matchers.h:205-232): everything the batched step needs about the coarse map and its scans.
+struct BackendOpt {
+  const std::vector<BaseRef>* base = nullptr;   // the chains' scans in coarse-map cells (same order as the fine ones)
+  double* const* dp = nullptr;                  // the match scans in coarse-map cells
+  const int* np = nullptr;
+  int grid_size = 0;
+  double resolution = 0, sigma = 0;
+  const rsm_optimize_param* op = nullptr;
+  double failed_cost = 0;
+};
+
+int optimize_core(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* const* d_pts, const int* n_pts,
+                  const rsm_optimize_param* op, double* poses_world, double* costs, int32_t* iterations, bool map_coords);
+
+// Reset + stamp one pool of back-end grids: slot i is a grid_size^2 grid centred on centres_world[2i..]
+// (ResetScanMatchMapWithRangeVec, slam/slam_processor.cpp:448-462).
+struct GridPool {
   RasterPlan pl;
+  std::vector<rsm_grid> gs;
+  std::vector<const rsm_grid*> gp;
+  size_t cells = 0;
+  const int64_t* scan_offset = nullptr;
+  const std::vector<BaseRef>* base = nullptr;
+};
+
+int make_grid_pool(rsm_ctx* ctx, Buf& pool_buf, int n, int grid_size, double resolution, float default_prob, double sigma,
+                   double occu_offset, const double* centres_world, const int64_t* scan_offset, const std::vector<BaseRef>& base,
+                   GridPool& P) {
   // use_blur = true as in both shipped configurations; blur parameters the reference's GaussianBlur rejects select the
   // SET_CELL_OCCUPIED update, as there (map/occu_grid_map.h:265-268)
-  int rc = plan_raster(ctx, default_prob, sigma, resolution, occu_offset, 1, pl);
+  int rc = plan_raster(ctx, default_prob, sigma, resolution, occu_offset, 1, P.pl);
   if (rc) return rc;
-  // grids: one pool, one slot per pair
   const int pool_pitch = grid_pitch_for(grid_size);
-  const size_t cells = size_t(pool_pitch) * grid_size;
-  const size_t slot = (cells * 4 + 255) / 256 * 256;
-  rc = ensure_dev(ctx, ctx->d_pool_grids, slot * n);
+  P.cells = size_t(pool_pitch) * grid_size;
+  const size_t slot = (P.cells * 4 + 255) / 256 * 256;
+  rc = ensure_dev(ctx, pool_buf, slot * n);
   if (rc) return rc;
-  std::vector<rsm_grid> gs(n);
-  std::vector<const rsm_grid*> gp(n);
+  P.gs.assign(n, rsm_grid());
+  P.gp.resize(n);
+  P.scan_offset = scan_offset; P.base = &base;
   const double scale = 1.0 / resolution;
   const double cell_len = 1 / scale;
   for (int i = 0; i < n; ++i) {
-    rsm_grid& g = gs[i];
+    rsm_grid& g = P.gs[i];
     g.size_x = g.size_y = grid_size; g.pitch = pool_pitch;
     g.resolution = resolution; g.scale = scale;
     // ResetScanMatchMapWithRangeVec: offset = -(pose - 0.5 * size * cell_len)   (slam_processor.cpp:451-455)
     g.off_x = -(centres_world[2 * i] - 0.5 * grid_size * cell_len);
     g.off_y = -(centres_world[2 * i + 1] - 0.5 * grid_size * cell_len);
     g.tf.set(scale, g.off_x, g.off_y);
-    g.fixed = pl.fixed; g.owned = false;
-    g.d_cells = ctx->d_pool_grids.p + slot * i;
+    g.fixed = P.pl.fixed; g.owned = false;
+    g.d_cells = pool_buf.p + slot * i;
     g.init = scan_offset[i + 1] > scan_offset[i];
-    gp[i] = &g;
+    P.gp[i] = &g;
   }
-  // Reset + stamp the grids of pairs [first, first + count) on a lane's stream, ahead of that sub-batch's first pass
-  // (the descriptors live in the lane's own aux buffers: the pass preparation reuses the work arena right away)
-  const std::function<int(Lane*, int, int)> pre = [&](Lane* L, int first, int count) -> int {
-    const int64_t s0 = scan_offset[first], s1 = scan_offset[first + count];
-    Layout dl;
-    const size_t o_fill = dl.take(sizeof(FillJob) * size_t(count));
-    const size_t o_scans = dl.take(sizeof(RasterScan) * size_t(std::max<int64_t>(1, s1 - s0)));
-    const size_t o_stamp = dl.take(pl.stamp.size() * 4);
-    const size_t o_groups = dl.take(sizeof(int) * size_t(count + 1), 4);
-    const size_t up_bytes = dl.off;
-    int rc2 = ensure_dev(ctx, L->d_aux, dl.off, L->stream);
-    if (rc2) return rc2;
-    rc2 = ensure_pinned(ctx, L->h_aux, up_bytes, L->stream);
-    if (rc2) return rc2;
-    char* up = L->h_aux.p;
-    char* dw = L->d_aux.p;
-    FillJob* hf = reinterpret_cast<FillJob*>(up + o_fill);
-    RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
-    int* hg = reinterpret_cast<int*>(up + o_groups);
-    for (int k = 0; k < count; ++k) {
+  return RSM_OK;
+}
+
+// Reset + stamp the grids of pairs [first, first + count) of a pool on a lane's stream (the descriptors live in the lane's
+// own aux buffers at aux_off: a pass preparation reuses the work arena right away)
+int raster_pool(rsm_ctx* ctx, const GridPool& P, Lane* L, int first, int count) {
+  const int64_t* scan_offset = P.scan_offset;
+  const std::vector<BaseRef>& base = *P.base;
+  const int64_t s0 = scan_offset[first], s1 = scan_offset[first + count];
+  Layout dl;
+  const size_t o_fill = dl.take(sizeof(FillJob) * size_t(count));
+  const size_t o_scans = dl.take(sizeof(RasterScan) * size_t(std::max<int64_t>(1, s1 - s0)));
+  const size_t o_stamp = dl.take(P.pl.stamp.size() * 4);
+  const size_t o_groups = dl.take(sizeof(int) * size_t(count + 1), 4);
+  const size_t up_bytes = dl.off;
+  int rc2 = ensure_dev(ctx, L->d_aux, dl.off, L->stream);
+  if (rc2) return rc2;
+  rc2 = ensure_pinned(ctx, L->h_aux, up_bytes, L->stream);
+  if (rc2) return rc2;
+  char* up = L->h_aux.p;
+  char* dw = L->d_aux.p;
+  FillJob* hf = reinterpret_cast<FillJob*>(up + o_fill);
+  RasterScan* hs = reinterpret_cast<RasterScan*>(up + o_scans);
+  int* hg = reinterpret_cast<int*>(up + o_groups);
+  for (int k = 0; k < count; ++k) {
+    const int i = first + k;
+    hf[k].grid = P.gs[i].d_cells; hf[k].n_cells = (long long)P.cells; hf[k].value = P.pl.fill;
+    hg[k] = int(scan_offset[i] - s0);
+  }
+  hg[count] = int(s1 - s0);
+  ctx->pool.run(count, 32, [&](int k0, int k1) {
+    for (int k = k0; k < k1; ++k) {
       const int i = first + k;
-      hf[k].grid = gs[i].d_cells; hf[k].n_cells = (long long)cells; hf[k].value = pl.fill;
-      hg[k] = int(scan_offset[i] - s0);
+      for (int64_t sidx = scan_offset[i]; sidx < scan_offset[i + 1]; ++sidx)
+        make_raster_scan(&P.gs[i], base[sidx].pose_world, base[sidx].d_pts, base[sidx].n, hs[sidx - s0]);
     }
-    hg[count] = int(s1 - s0);
-    ctx->pool.run(count, 32, [&](int k0, int k1) {
-      for (int k = k0; k < k1; ++k) {
-        const int i = first + k;
-        for (int64_t sidx = scan_offset[i]; sidx < scan_offset[i + 1]; ++sidx)
-          make_raster_scan(&gs[i], base[sidx].pose_world, base[sidx].d_pts, base[sidx].n, hs[sidx - s0]);
-      }
-    });
-    std::memcpy(up + o_stamp, pl.stamp.data(), pl.stamp.size() * 4);
-    CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, L->stream));
-    L->stats.h2d_bytes += up_bytes;
-    {
-      Prof p(ctx, KC_RASTER, L);
-      CU(launch_fill(count, 4, L->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
-      if (s1 > s0)
-        CU(enqueue_raster(pl, L->stream, int(s1 - s0), reinterpret_cast<const RasterScan*>(dw + o_scans),
-                          reinterpret_cast<const int*>(dw + o_stamp), count, reinterpret_cast<const int*>(dw + o_groups)));
-    }
-    L->stats.kernel_launches += 2;
-    return RSM_OK;
+  });
+  std::memcpy(up + o_stamp, P.pl.stamp.data(), P.pl.stamp.size() * 4);
+  CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, L->stream));
+  L->stats.h2d_bytes += up_bytes;
+  {
+    Prof p(ctx, KC_RASTER, L);
+    CU(launch_fill(count, 4, L->stream, reinterpret_cast<const FillJob*>(dw + o_fill)));
+    if (s1 > s0)
+      CU(enqueue_raster(P.pl, L->stream, int(s1 - s0), reinterpret_cast<const RasterScan*>(dw + o_scans),
+                        reinterpret_cast<const int*>(dw + o_stamp), count, reinterpret_cast<const int*>(dw + o_groups)));
+  }
+  L->stats.kernel_launches += 2;
+  return RSM_OK;
+}
+
+int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, float default_prob, double sigma,
+                      double occu_offset, const double* centres_world, const int64_t* scan_offset,
+                      const std::vector<BaseRef>& base, double* const* dp, const int* np, const rsm_pass_param* params,
+                      bool use_fine, double* poses_world, double* covs, double* scores, double* responses,
+                      const rsm_grid* pub_map, const double* const* pub_pts, const int32_t* pub_counts,
+                      const rsm_map_check_param* check, const BackendOpt* opt = nullptr) {
+  PhaseTimer pt_setup(&ctx->stats);
+  GridPool fine;
+  int rc = make_grid_pool(ctx, ctx->d_pool_grids, n, grid_size, resolution, default_prob, sigma, occu_offset, centres_world,
+                          scan_offset, base, fine);
+  if (rc) return rc;
+  const std::function<int(Lane*, int, int)> pre = [&](Lane* L, int first, int count) -> int {
+    return raster_pool(ctx, fine, L, first, count);
   };
+  // ---- Gauss-Newton pre-step on the coarse maps (scan_matchers.h:205-232) -----------------------------------------
+  std::vector<unsigned char> skip_coarse;
+  std::vector<double> opt_cost;
+  if (opt) {
+    GridPool coarse;
+    rc = make_grid_pool(ctx, ctx->d_pool_grids2, n, opt->grid_size, opt->resolution, default_prob, opt->sigma, occu_offset,
+                        centres_world, scan_offset, *opt->base, coarse);
+    if (rc) return rc;
+    rc = raster_pool(ctx, coarse, &ctx->L0, 0, n);
+    if (rc) return rc;
+    rc = sync_stream(ctx);       // optimize_core reuses the staging buffers
+    if (rc) return rc;
+    std::vector<double> process(poses_world, poses_world + 3 * size_t(n));
+    opt_cost.assign(n, 0.0);
+    std::vector<const double*> cdp(n);
+    for (int i = 0; i < n; ++i) cdp[i] = opt->dp[i];
+    rc = optimize_core(ctx, n, coarse.gp.data(), cdp.data(), opt->np, opt->op, process.data(), opt_cost.data(), nullptr, false);   // :207
+    if (rc) return rc;
+    skip_coarse.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+      // the coarse correlative pass runs unless the fine passes follow and the optimiser succeeded (:224-226); it then
+      // starts from the seed again (:232)
+      if (use_fine && !(opt_cost[i] > opt->failed_cost)) {
+        skip_coarse[i] = 1;
+        for (int k = 0; k < 3; ++k) poses_world[3 * i + k] = process[3 * i + k];
+      }
+    }
+  }
   pt_setup.lap(6);
-  rc = run_chain(ctx, n, gp.data(), dp, np, params, true, use_fine, poses_world, covs, scores, responses, &pre);
+  std::vector<double> resp3;
+  double* r3 = responses;
+  if (opt) { resp3.assign(3 * size_t(n), 0.0); r3 = resp3.data(); }
+  rc = run_chain(ctx, n, fine.gp.data(), dp, np, params, true, use_fine, poses_world, covs, scores, r3, &pre,
+                 opt ? skip_coarse.data() : nullptr);
   pt_setup.lap(7);
-  if (rc || !pub_map) return rc;
+  if (rc) return rc;
+  if (opt) {
+    for (int i = 0; i < n; ++i) {
+      // scan_match_score / scan_match_times (:211, :230-240, :247-263, :281)
+      double score = skip_coarse[i] ? opt->failed_cost / (opt_cost[i] + opt->failed_cost) : r3[3 * i];
+      int times = 1;
+      if (use_fine) { score += r3[3 * i + 1]; times++; score += r3[3 * i + 2]; times++; }
+      scores[i] = score / times;
+      if (responses) { responses[4 * i] = opt_cost[i]; for (int k = 0; k < 3; ++k) responses[4 * i + 1 + k] = r3[3 * i + k]; }
+    }
+  }
+  if (!pub_map) return RSM_OK;
   // MapCheckPenalize(pub_map_range_data, best_pose, true) on the matched poses (slam_processor.cpp:313-317)
   std::vector<double> coeff(n);
   rc = map_check_core(ctx, pub_map, n, poses_world, nullptr, 0, 0, nullptr, pub_pts, pub_counts, nullptr,
@@ -2686,7 +2771,7 @@ int loop_closure_core(rsm_ctx* ctx, int n, int grid_size, double resolution, flo
 // cos / sin of the next estimate.  poses_world in/out; costs out; iterations (nullable) = UpdateCost calls.
 int optimize_core(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const double* const* d_pts, const int* n_pts,
                   const rsm_optimize_param* op, double* poses_world, double* costs, int32_t* iterations,
-                  bool map_coords = false) {   // map_coords: poses are given and returned in map cells (adapter path)
+                  bool map_coords) {   // map_coords: poses are given and returned in map cells (adapter path)
   const double kMaxCost = 1.0 * 1000;                         // :231-232
   if (op->iterate_max_times < 1)   // the reference would return the previous call's cost_ (a stale member)
     return fail(ctx, RSM_ERR_INVALID, "rsm_optimize: iterate_max_times must be >= 1");
@@ -2872,6 +2957,66 @@ int rsm_scan_store_get_pose(const rsm_scan_store* store, int32_t id, double pose
   return RSM_OK;
 }
 
+}  // extern "C"
+namespace {
+// the argument checks and id lookups shared by the two batched back-end entry points
+int interface_batch_core(rsm_ctx* ctx, const char* who, const rsm_scan_store* store, int n, int grid_size, double resolution,
+                         float default_prob, double sigma, double occu_offset, const double* centres_world,
+                         const int64_t* chain_offset, const int32_t* chain_ids, const int32_t* match_ids,
+                         const rsm_pass_param params[3], int use_fine, double* poses_world, double* covs, double* scores,
+                         double* responses, const rsm_grid* pub_map, const rsm_scan_store* pub_store,
+                         const rsm_map_check_param* check, const rsm_scan_store* coarse_store, int coarse_grid_size,
+                         double coarse_resolution, double coarse_sigma, const rsm_optimize_param* opt, double optimize_failed_cost) {
+  if (!ctx || !store || n < 0 || grid_size <= 0 || !(resolution > 0) ||
+      (n > 0 && (!centres_world || !chain_offset || !match_ids || !params || !poses_world || !covs || !scores)) ||
+      (pub_map && (!pub_store || !check)) ||
+      (coarse_store && (!opt || coarse_grid_size <= 0 || !(coarse_resolution > 0))))
+    return fail(ctx, RSM_ERR_INVALID, "%s: bad arguments", who);
+  if (n == 0) return RSM_OK;
+  if (pub_map && !pub_map->d_occ) return fail(ctx, RSM_ERR_NOT_INIT, "%s: no occupancy uploaded for the publishing map", who);
+  const int64_t n_entries = chain_offset[n];
+  if (n_entries < 0 || (n_entries > 0 && !chain_ids)) return fail(ctx, RSM_ERR_INVALID, "%s: bad chain list", who);
+  const size_t have = store->scans.size();
+  std::vector<BaseRef> base(n_entries), cbase(coarse_store ? n_entries : 0);
+  for (int64_t s = 0; s < n_entries; ++s) {
+    if (chain_ids[s] < 0 || size_t(chain_ids[s]) >= have) return fail(ctx, RSM_ERR_INVALID, "%s: unknown scan id %d", who, chain_ids[s]);
+    const rsm_scan_store::Entry& E = store->scans[chain_ids[s]];
+    base[s] = BaseRef{E.d_pts, E.n, E.pose};
+    if (coarse_store) {
+      if (size_t(chain_ids[s]) >= coarse_store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "%s: scan id %d is not in the coarse-map store", who, chain_ids[s]);
+      const rsm_scan_store::Entry& C = coarse_store->scans[chain_ids[s]];
+      cbase[s] = BaseRef{C.d_pts, C.n, E.pose};      // one pose per scan: the fine store's (UpdateRangeData updates every resolution alike)
+    }
+  }
+  std::vector<double*> dp(n), cdp(coarse_store ? n : 0);
+  std::vector<int> np(n), cnp(coarse_store ? n : 0);
+  std::vector<const double*> pub_pts(pub_map ? n : 0);
+  std::vector<int32_t> pub_counts(pub_map ? n : 0);
+  for (int i = 0; i < n; ++i) {
+    if (match_ids[i] < 0 || size_t(match_ids[i]) >= have) return fail(ctx, RSM_ERR_INVALID, "%s: unknown scan id %d", who, match_ids[i]);
+    dp[i] = store->scans[match_ids[i]].d_pts; np[i] = store->scans[match_ids[i]].n;
+    if (pub_map) {
+      if (size_t(match_ids[i]) >= pub_store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "%s: scan id %d is not in the publishing-map store", who, match_ids[i]);
+      pub_pts[i] = pub_store->scans[match_ids[i]].d_pts; pub_counts[i] = pub_store->scans[match_ids[i]].n;
+    }
+    if (coarse_store) {
+      if (size_t(match_ids[i]) >= coarse_store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "%s: scan id %d is not in the coarse-map store", who, match_ids[i]);
+      cdp[i] = coarse_store->scans[match_ids[i]].d_pts; cnp[i] = coarse_store->scans[match_ids[i]].n;
+    }
+  }
+  BackendOpt bo;
+  if (coarse_store) {
+    bo.base = &cbase; bo.dp = cdp.data(); bo.np = cnp.data(); bo.grid_size = coarse_grid_size; bo.resolution = coarse_resolution;
+    bo.sigma = coarse_sigma; bo.op = opt; bo.failed_cost = optimize_failed_cost;
+  }
+  return loop_closure_core(ctx, n, grid_size, resolution, default_prob, sigma, occu_offset, centres_world, chain_offset,
+                           base, dp.data(), np.data(), params, use_fine != 0, poses_world, covs, scores, responses,
+                           pub_map, pub_map ? pub_pts.data() : nullptr, pub_map ? pub_counts.data() : nullptr, check,
+                           coarse_store ? &bo : nullptr);
+}
+}  // namespace
+extern "C" {
+
 int rsm_scan_match_interface_batch(rsm_ctx* ctx, const rsm_scan_store* store, int n, int grid_size, double resolution,
                                    float default_prob, double sigma, double occu_offset, const double* centres_world,
                                    const int64_t* chain_offset, const int32_t* chain_ids, const int32_t* match_ids,
@@ -2879,36 +3024,26 @@ int rsm_scan_match_interface_batch(rsm_ctx* ctx, const rsm_scan_store* store, in
                                    double* scores, double* responses, const rsm_grid* pub_map,
                                    const rsm_scan_store* pub_store, const rsm_map_check_param* check) {
   DeviceGuard device_guard(ctx);
-  if (!ctx || !store || n < 0 || grid_size <= 0 || !(resolution > 0) ||
-      (n > 0 && (!centres_world || !chain_offset || !match_ids || !params || !poses_world || !covs || !scores)) ||
-      (pub_map && (!pub_store || !check)))
-    return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: bad arguments");
-  if (n == 0) return RSM_OK;
-  if (pub_map && !pub_map->d_occ) return fail(ctx, RSM_ERR_NOT_INIT, "rsm_scan_match_interface_batch: no occupancy uploaded for the publishing map");
-  const int64_t n_entries = chain_offset[n];
-  if (n_entries < 0 || (n_entries > 0 && !chain_ids)) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: bad chain list");
-  const size_t have = store->scans.size();
-  std::vector<BaseRef> base(n_entries);
-  for (int64_t s = 0; s < n_entries; ++s) {
-    if (chain_ids[s] < 0 || size_t(chain_ids[s]) >= have) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: unknown scan id %d", chain_ids[s]);
-    const rsm_scan_store::Entry& E = store->scans[chain_ids[s]];
-    base[s] = BaseRef{E.d_pts, E.n, E.pose};
-  }
-  std::vector<double*> dp(n);
-  std::vector<int> np(n);
-  std::vector<const double*> pub_pts(pub_map ? n : 0);
-  std::vector<int32_t> pub_counts(pub_map ? n : 0);
-  for (int i = 0; i < n; ++i) {
-    if (match_ids[i] < 0 || size_t(match_ids[i]) >= have) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: unknown scan id %d", match_ids[i]);
-    dp[i] = store->scans[match_ids[i]].d_pts; np[i] = store->scans[match_ids[i]].n;
-    if (pub_map) {
-      if (size_t(match_ids[i]) >= pub_store->scans.size()) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch: scan id %d is not in the publishing-map store", match_ids[i]);
-      pub_pts[i] = pub_store->scans[match_ids[i]].d_pts; pub_counts[i] = pub_store->scans[match_ids[i]].n;
-    }
-  }
-  return loop_closure_core(ctx, n, grid_size, resolution, default_prob, sigma, occu_offset, centres_world, chain_offset,
-                           base, dp.data(), np.data(), params, use_fine != 0, poses_world, covs, scores, responses,
-                           pub_map, pub_map ? pub_pts.data() : nullptr, pub_map ? pub_counts.data() : nullptr, check);
+  return interface_batch_core(ctx, "rsm_scan_match_interface_batch", store, n, grid_size, resolution, default_prob, sigma, occu_offset,
+                              centres_world, chain_offset, chain_ids, match_ids, params, use_fine, poses_world, covs, scores,
+                              responses, pub_map, pub_store, check, nullptr, 0, 0.0, 0.0, nullptr, 0.0);
+}
+
+int rsm_scan_match_interface_batch_opt(rsm_ctx* ctx, const rsm_scan_store* fine_store, const rsm_scan_store* coarse_store, int n,
+                                       int grid_size, double resolution, double sigma, int coarse_grid_size,
+                                       double coarse_resolution, double coarse_sigma, float default_prob, double occu_offset,
+                                       const double* centres_world, const int64_t* chain_offset, const int32_t* chain_ids,
+                                       const int32_t* match_ids, const rsm_pass_param params[3],
+                                       const rsm_optimize_param* optimize, double optimize_failed_cost, int use_fine,
+                                       double* poses_world, double* covs, double* scores, double* responses,
+                                       const rsm_grid* pub_map, const rsm_scan_store* pub_store,
+                                       const rsm_map_check_param* check) {
+  DeviceGuard device_guard(ctx);
+  if (!coarse_store || !optimize) return fail(ctx, RSM_ERR_INVALID, "rsm_scan_match_interface_batch_opt: bad arguments");
+  return interface_batch_core(ctx, "rsm_scan_match_interface_batch_opt", fine_store, n, grid_size, resolution, default_prob, sigma,
+                              occu_offset, centres_world, chain_offset, chain_ids, match_ids, params, use_fine, poses_world, covs,
+                              scores, responses, pub_map, pub_store, check, coarse_store, coarse_grid_size, coarse_resolution,
+                              coarse_sigma, optimize, optimize_failed_cost);
 }
 
 // ---- Gauss-Newton matcher -----------------------------------------------------------------------
@@ -2926,7 +3061,7 @@ int rsm_optimize_batch(rsm_ctx* ctx, int n, const rsm_grid* const* grids, const 
   std::vector<const double*> dp(n);
   std::vector<int> np(n);
   for (int i = 0; i < n; ++i) { dp[i] = d_pts + 2 * pts_offset[i]; np[i] = int(pts_offset[i + 1] - pts_offset[i]); }
-  return optimize_core(ctx, n, grids, dp.data(), np.data(), param, poses_world, costs, iterations);
+  return optimize_core(ctx, n, grids, dp.data(), np.data(), param, poses_world, costs, iterations, false);
 }
 
 int rsm_optimize(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_optimize_param* param,

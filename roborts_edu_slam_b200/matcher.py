@@ -150,6 +150,8 @@ ABI = {
     "rsm_scan_store_size": (c_i, [c_p]),
     "rsm_scan_match_interface_batch": (c_i, [c_p, c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p,
                                              _PPARAM, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "rsm_scan_match_interface_batch_opt": (c_i, [c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_i, c_d, c_d, ctypes.c_float, c_d, c_p, c_p, c_p, c_p,
+                                                 _PPARAM, ctypes.POINTER(OptimizeParamStruct), c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "rsm_optimize": (c_i, [c_p, c_p, c_p, c_i, ctypes.POINTER(OptimizeParamStruct), c_p, ctypes.POINTER(c_d),
                            ctypes.POINTER(ctypes.c_int32)]),
     "rsm_optimize_map": (c_i, [c_p, c_p, c_p, c_i, ctypes.POINTER(OptimizeParamStruct), c_p, ctypes.POINTER(c_d),
@@ -733,6 +735,36 @@ class CommSlicedScanMatch:
     def close(self):
         if getattr(self.ctx, "h", None):
             self.ctx.lib.rsm_comm_destroy(self.ctx.h)
+
+
+def scan_match_interface_batch_opt(ctx, fine_store, coarse_store, fine_spec, coarse_spec, centres, chains, match_ids, seed_poses,
+                                   params, optimize_param, optimize_failed_cost, use_fine=True, pub_map=None, pub_store=None,
+                                   check=None):
+    """rsm_scan_match_interface_batch_opt: the batched back-end step with the Gauss-Newton pre-step on the coarse map
+    (ScanMatchers::ScanMatch with use_optimize_scan_match, scan_matchers.h:205-232).  coarse_store holds the scans of
+    fine_store (same ids) in coarse-map cells.  Returns (scores, poses, covs, responses[n, 4] = optimiser cost + the
+    three pass responses)."""
+    off, ids = chains if isinstance(chains, tuple) else pack_chains(chains)
+    n = len(off) - 1
+    mids = np.ascontiguousarray(match_ids, dtype=np.int32)
+    arr = (PassParamStruct * 3)(*[_as_param(p).struct() for p in params])
+    st = _as_opt(optimize_param).struct()
+    poses = _f64(np.asarray(seed_poses).reshape(-1, 3)).copy()
+    covs = np.tile(np.eye(3), (n, 1, 1))
+    scores = np.zeros(n)
+    resp = np.zeros((n, 4))
+    c = _f64(np.asarray(centres).reshape(-1, 2))
+    gf, gc = fine_spec, coarse_spec
+    chk = None
+    if pub_map is not None:
+        chk = MapCheckParamStruct(float(check[1]), float(check[2]), int(check[0]), int(bool(check[3])))
+    ctx.check(ctx.lib.rsm_scan_match_interface_batch_opt(
+        ctx.h, fine_store.h, coarse_store.h, n, int(gf.size_x), float(gf.res), float(gf.sigma), int(gc.size_x), float(gc.res),
+        float(gc.sigma), float(gf.default_prob), float(gf.occu_offset), c.ctypes.data, off.ctypes.data, ids.ctypes.data,
+        mids.ctypes.data, arr, ctypes.byref(st), float(optimize_failed_cost), int(use_fine), poses.ctypes.data, covs.ctypes.data,
+        scores.ctypes.data, resp.ctypes.data, pub_map.h if pub_map is not None else None,
+        pub_store.h if pub_store is not None else None, ctypes.byref(chk) if chk is not None else None))
+    return scores, poses, covs, resp
 
 
 def make_sliced_matcher(ctx, rank, world_size, dist=None, in_library=True):

@@ -1261,3 +1261,60 @@ def test_in_library_sliced_match_over_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("sliced matches equal the oracle") == n
+
+
+def test_batched_backend_step_with_optimiser(ctx, oracle):
+    """rsm_scan_match_interface_batch_opt: the coarse map + Gauss-Newton pre-step inside the batched back-end step
+    (slam_processor.cpp:282-308, scan_matchers.h:205-232) against the oracle's chain with the optimiser on, candidate by
+    candidate -- seeds close enough for the optimiser to succeed (its pose feeds the fine pass), seeds it fails on (the
+    coarse correlative pass runs from the seed), use_fine off, and the map check on top."""
+    from helpers import load_mapcheck
+    pairs = synth.config4(5)
+    fine, coarse, pub = matcher.ScanStore(ctx), matcher.ScanStore(ctx), matcher.ScanStore(ctx)
+    chains, mids = [], []
+    for sc in pairs:
+        ids = []
+        for p, pose in zip(sc.base_pts, sc.base_poses):
+            ids.append(fine.AddRangeData(p, pose))
+            assert coarse.AddRangeData(p * 0.5, pose) == ids[-1] and pub.AddRangeData(p, pose) == ids[-1]
+        mid = fine.AddRangeData(sc.scan_pts, sc.seed_pose)
+        assert coarse.AddRangeData(sc.scan_pts * 0.5, sc.seed_pose) == mid and pub.AddRangeData(sc.scan_pts, sc.seed_pose) == mid
+        chains.append(ids)
+        mids.append(mid)
+    gf = pairs[0].grid
+    gc = synth.backend_grid(gf.res * 2, gf.sigma * 2, 10.0, pairs[0].grid_centre)
+    op = (10, 0.1, 0.5, 0.5, 0.5)
+    deltas = ([0.02, 0.01, 0.02], [0.12, -0.07, 0.1], [0.5, 0.4, -0.3], [0.0, 0.0, 0.0], [-0.2, 0.15, -0.12])
+    cands = [(i, pairs[i].truth_pose + np.array(deltas[(i + k) % len(deltas)])) for i in range(len(pairs)) for k in range(3)]
+    gpub, occ, _ = load_mapcheck("mapcheck_pair0")
+    pm = matcher.ScanMatchMap.from_spec(ctx, gpub)
+    pm.upload_occupancy(occ)
+    check = (100, 2.5, 0.015, True)
+    branches = set()
+    for failed_cost, use_fine, with_check in ((2.0, True, False), (20.0, True, True), (100.0, True, False), (90.0, False, False)):
+        want = []
+        for who, seed in cands:
+            sc = pairs[who]
+            gci = synth.backend_grid(gc.res, gc.sigma, 10.0, sc.grid_centre)
+            grid_f = oracle.build_grid(sc.grid, sc.base_pts, sc.base_poses)
+            grid_c = oracle.build_grid(gci, [p * 0.5 for p in sc.base_pts], sc.base_poses)
+            w = oracle.match_chain_opt(grid_c, gci, sc.scan_pts * 0.5, grid_f, sc.grid, sc.scan_pts, sc.passes, op, failed_cost, seed,
+                                       use_fine=use_fine)
+            branches.add((bool(w["optimize_cost"] > failed_cost), use_fine))
+            if with_check:
+                c = oracle.map_check_penalize(occ, gpub, sc.scan_pts, w["pose"], *check)
+                s = w["score"] * c
+                w = dict(w, score=1.0 if s > 1.0 else s)
+            want.append(w)
+        scores, poses, covs, resp = matcher.scan_match_interface_batch_opt(
+            ctx, fine, coarse, gf, gc, [pairs[w_].grid_centre for w_, _ in cands], [chains[w_] for w_, _ in cands],
+            [mids[w_] for w_, _ in cands], [s_ for _, s_ in cands], pairs[0].passes, op, failed_cost, use_fine,
+            pm if with_check else None, pub if with_check else None, check if with_check else None)
+        for i, w in enumerate(want):
+            assert scores[i] == w["score"], (failed_cost, use_fine, i, scores[i], w["score"])
+            assert np.array_equal(poses[i], w["pose"]) and cov_close(covs[i], w["cov"])
+            assert resp[i][0] == w["optimize_cost"] and np.array_equal(resp[i][1:], w["responses"])
+    assert {(False, True), (True, True), (False, False)} <= branches      # optimiser kept / dropped with the fine passes on; fine passes off
+    pm.close()
+    for st in (fine, coarse, pub):
+        st.close()

@@ -595,3 +595,63 @@ class DropIn:
         a, b = c_l(0), c_l(0)
         self.L.dropin_sync_counts(ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+
+def batcher_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libbatcher.so"))
+
+
+class Batcher:
+    """The product's back-end batcher (csrc/backend_batcher.hpp) fed from a LIVE reference SensorDataManager
+    (oracle/_ref/libbatcher.so); needs a GPU."""
+
+    def __init__(self, res, dev, sizes, blur_offset, default_prob, passes, opt):
+        L = ctypes.CDLL(os.path.join(_HERE, "_ref", "libbatcher.so"))
+        L.batcher_create.restype = c_p
+        L.batcher_create.argtypes = [c_p, c_p, c_p, c_d, ctypes.c_float, c_p, c_p]
+        L.batcher_destroy.argtypes = [c_p]
+        L.batcher_add_scan.restype = c_i
+        L.batcher_add_scan.argtypes = [c_p, c_i, c_p, c_p]
+        L.batcher_get_fine_scan.restype = c_i
+        L.batcher_get_fine_scan.argtypes = [c_p, c_i, c_p, c_i]
+        L.batcher_set_pose.argtypes = [c_p, c_i, c_p]
+        L.batcher_try_close_loop.restype = c_i
+        L.batcher_try_close_loop.argtypes = [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
+        self.L = L
+        res, dev, passes, opt = _f64(res), _f64(dev), _f64(np.concatenate(passes)), _f64(opt)
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        self.h = L.batcher_create(res.ctypes.data, dev.ctypes.data, sizes.ctypes.data, float(blur_offset), float(default_prob),
+                                  passes.ctypes.data, opt.ctypes.data)
+        if not self.h:
+            raise RuntimeError("batcher could not create a CUDA context")
+
+    def close(self):
+        if self.h:
+            self.L.batcher_destroy(self.h)
+            self.h = None
+
+    def add_scan(self, pts_metres, pose_world):
+        pts, pose = _f64(pts_metres), _f64(pose_world)
+        return self.L.batcher_add_scan(self.h, len(pts), pts.ctypes.data, pose.ctypes.data)
+
+    def fine_scan(self, scan_id, cap=4096):
+        out = np.zeros((cap, 2))
+        n = self.L.batcher_get_fine_scan(self.h, int(scan_id), out.ctypes.data, cap)
+        return out[:n].copy()
+
+    def set_pose(self, scan_id, pose_world):
+        pose = _f64(pose_world)
+        self.L.batcher_set_pose(self.h, int(scan_id), pose.ctypes.data)
+
+    def try_close_loop(self, range_id, chains, scan_pose, centre, thresholds):
+        off = np.zeros(len(chains) + 1, dtype=np.int32)
+        for i, ch in enumerate(chains):
+            off[i + 1] = off[i] + len(ch)
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(ch, dtype=np.int32) for ch in chains]), dtype=np.int32)
+        pose, cen, th = _f64(scan_pose), _f64(centre), _f64(thresholds)
+        best, cov = np.zeros(3), np.zeros(9)
+        s1, s2 = np.zeros(len(chains)), np.zeros(len(chains))
+        hit = self.L.batcher_try_close_loop(self.h, int(range_id), len(chains), off.ctypes.data, ids.ctypes.data, pose.ctypes.data,
+                                            cen.ctypes.data, th.ctypes.data, best.ctypes.data, cov.ctypes.data, s1.ctypes.data,
+                                            s2.ctypes.data)
+        return hit, best, cov.reshape(3, 3), s1, s2

@@ -136,3 +136,58 @@ def test_frontend_through_the_adapter(ref, dropin):
     finally:
         ref.destroy_map(ma)
         ref.destroy_map(mr)
+
+
+def test_batched_loop_closure_on_a_live_sensor_data_manager(ref):
+    """rsm_adapter::BackEndBatcher (csrc/backend_batcher.hpp) compiled against the unmodified reference headers: scans live
+    in a reference SensorDataManager (metres + per-map copies, as SlamProcessor stores them); TryCloseLoop's two-stage test
+    over several candidate chains of one scan runs as two batched calls and must pick the chain, pose and covariance that
+    the reference's sequential loop (range_scan_pose_graph.cpp:299-352, ScanMatchInterface with its own classes) picks."""
+    from oracle.oracle_py import Batcher, batcher_available
+    if not batcher_available():
+        pytest.skip("oracle/_ref/libbatcher.so not built")
+    occ = synth.load_map("willow")
+    base = np.array([14.375, 28.625, 0.3])
+    poses = [base + np.array([0.25 * k, 0.1 * k, 0.04 * k]) for k in range(24)]
+    scans_m = [synth.raycast(occ, p[0], p[1], p[2], 1081, np.deg2rad(270.25), 10.0) for p in poses]
+    passes = synth.chain_yaml((100, 100, 200))
+    g = synth.backend_grid(0.05, 0.15, 10.0, base[:2])
+    B = Batcher((0.05, 0.1, 0.05), (0.15, 0.3), (g.size_x, g.size_x // 2), 0.88, 0.3, passes, (0, 10, 0.1, 0.5, 0.5, 0.5, 20.0))
+    try:
+        ids = [B.add_scan(s, p) for s, p in zip(scans_m, poses)]
+        assert ids == list(range(24))
+        query = 23
+        q_pose = poses[query] + np.array([0.08, -0.05, 0.03])        # the scan's (drifted) pose
+        B.set_pose(query, q_pose)
+        # chain 0 lies far from the query scan (fails stage 1), chain 1 near but sparse, chain 2 the good one
+        chains = [list(range(0, 6)), list(range(10, 14)), list(range(15, 23)), list(range(16, 22))]
+        centre = q_pose[:2]
+        th = (0.6, 0.05, 0.7)         # chain 0 fails the coarse test, chain 1 the fine one, chain 2 closes the loop
+
+        def reference_try_close_loop():
+            stage1, stage2 = [], []
+            hit, best, bcov = -1, None, None
+            for ci, ch in enumerate(chains):
+                gi = synth.backend_grid(0.05, 0.15, 10.0, centre)
+                m = ref.create_map(gi)
+                ref.build_map(m, gi, [B.fine_scan(i) for i in ch], np.array([poses[i] if i != query else q_pose for i in ch]))
+                w1 = ref.match_chain(m, B.fine_scan(query), passes, q_pose)
+                stage1.append(w1["score"])
+                s2 = -1.0
+                if w1["score"] > th[0] and w1["cov"][0, 0] < th[1] and w1["cov"][1, 1] < th[1]:
+                    w2 = ref.match_chain(m, B.fine_scan(query), passes, w1["pose"], w1["cov"])
+                    s2 = w2["score"]
+                    if hit < 0 and s2 >= th[2]:
+                        hit, best, bcov = ci, w2["pose"], w2["cov"]
+                stage2.append(s2)
+                ref.destroy_map(m)
+            return hit, best, bcov, stage1, stage2
+
+        want = reference_try_close_loop()
+        hit, best, cov, s1, s2 = B.try_close_loop(query, chains, q_pose, centre, th)
+        assert hit == want[0] == 2, (hit, want[0], s1, want[3], s2, want[4])
+        assert np.array_equal(s1, want[3]) and np.array_equal(s2, want[4])
+        assert np.array_equal(best, want[1]) and cov_close(cov, want[2])
+        assert sum(1 for v in want[4] if v < 0) >= 1      # at least one chain stopped at stage 1
+    finally:
+        B.close()

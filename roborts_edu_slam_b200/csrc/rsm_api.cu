@@ -883,8 +883,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       double* t = h_trig + it.trig_off;
       for (int ia = 0; ia < g.n_ang; ++ia) {
         const double angle = g.angle_of(ia);
-        t[3 * ia] = std::cos(angle);      // correlate_scan_matcher.h:171-172
-        t[3 * ia + 1] = std::sin(angle);
+        angle_trig(angle, &t[3 * ia], &t[3 * ia + 1]);      // correlate_scan_matcher.h:171-172
         t[3 * ia + 2] = angle;
       }
     }

@@ -16,6 +16,10 @@ void hs_ldlt3(const double* H_rowmajor, const double* b, double* x) {
   ldlt3_solve(H, b, x);
 }
 double hs_normalize_angle(double a) { return normalize_angle(a); }
+// the product's angle-table entry for n angles: out[2i] = cos, out[2i+1] = sin
+void hs_angle_trig(const double* angles, long n, double* out) {
+  for (long i = 0; i < n; ++i) angle_trig(angles[i], &out[2 * i], &out[2 * i + 1]);
+}
 double hs_max_abs_limit(double v, double lim) { return max_abs_limit(v, lim); }
 
 void hs_world_to_map(double scale, double off_x, double off_y, const double* w, double* m) {

@@ -226,3 +226,20 @@ def test_resize_policy_through_the_c_abi(ref, rng):
     assert n_ext >= 2
     ref.destroy_map(m)
     mb.close()
+
+
+def test_angle_tables_are_libm_cos_and_sin(shim, rng):
+    """The product fills its angle tables with glibc's sincos; the reference calls std::cos and std::sin
+    (correlate_scan_matcher.h:171-172).  They must be the same bits: 2 M search angles, small and large."""
+    shim.hs_angle_trig.argtypes = [c_p, c_l, c_p]
+    ang = np.concatenate([rng.uniform(-7.0, 7.0, 1_500_000), rng.uniform(-1e4, 1e4, 500_000), np.array([0.0, -0.0, np.pi, -np.pi / 2])])
+    out = np.zeros((len(ang), 2))
+    shim.hs_angle_trig(ang.ctypes.data, len(ang), out.ctypes.data)
+    # numpy's cos / sin on float64 are its own SIMD kernels, not libm: compare with the C library through ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.cos.restype = libm.sin.restype = c_d
+    libm.cos.argtypes = libm.sin.argtypes = [c_d]
+    idx = rng.integers(0, len(ang), 200_000)
+    for i in idx:
+        a = float(ang[i])
+        assert out[i, 0] == libm.cos(a) and out[i, 1] == libm.sin(a), a

@@ -761,7 +761,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_value["kernel_launches"]),
-            "roofline": {"bound": "smem", "kernel": "staged::score_staged_kernel (all score launches of a step)",
+            "roofline": {"bound": "smem", "kernel": "staged::score_stream_kernel<MapPaired> (the one persistent score launch of a step)",
                          "achieved": achieved, "peak": smem_row, "unit": "GB/s",
                          "frac": achieved / smem_row, "traffic": traffic,
                          "kernel_ms": k_ms, "select_ms": st_value["select_kernel_ms"] / score_launches,

@@ -499,6 +499,17 @@ int rsm_match_sliced(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, i
  * *gbps = bytes gathered / CUDA-event time. */
 int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int iters, double* gbps);
 
+/* The stream plan of the staged scoring kernel, for inspection and tests (host only; no device needed).
+ * runs[3 i .. 3 i + 2] = beams visited, window width n_xy and search angles of job i; variant 0 / 1 / 2 = the
+ * 81 x 96 paired-row, 64 x 64 and 96 x 96 tile mappings (negative: the one the library picks for the widest window).
+ * The jobs' (angle, tile) items form one sequence of beams cut into at most max_ctas contiguous shares.
+ * out receives 12 ints per share: item0, beam0, item1, beam1 (last item inclusive, its end beam exclusive), then for
+ * the first and for the last item {ticket or -1, first partial slot, this share's part, parts} when other shares
+ * visit the same item.  Returns the number of shares (or -needed when cap is too small); *n_items, *n_tickets,
+ * *n_slots describe the launch. */
+int rsm_stream_plan(int n_runs, const int* runs, int variant, int max_ctas, int* out, int cap, int64_t* n_items,
+                    int* n_tickets, int* n_slots);
+
 #ifdef __cplusplus
 }
 #endif

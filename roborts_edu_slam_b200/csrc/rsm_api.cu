@@ -253,8 +253,9 @@ struct rsm_ctx {
   Buf d_xchg, h_xchg;
   // staged scoring variant: tensor maps of the grids seen so far, keyed by (cells, size, pitch)
   struct alignas(64) TmapPair { CUtensorMap box[2]; };
-  std::map<std::tuple<const void*, int, int, int>, TmapPair> tmaps;
+  std::map<std::tuple<const void*, int, int, int, int>, TmapPair> tmaps;   // + box set
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
+  int sm_count = 0;               // multiprocessors of the device (stream plan: persistent CTAs)
   // CUDA graphs of whole passes (upload, zeroing, score launches, select, read-back), keyed by
   // everything that shapes the launch sequence; the per-call data travels in the pinned buffer
   struct PassGraph { int seen = 0; cudaGraphExec_t exec = nullptr; };
@@ -317,8 +318,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // The pair is copied out under the context's mutex: lane threads share the cache.
-int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, rsm_ctx::TmapPair* out) {
-  const auto key = std::make_tuple((const void*)g->d_cells, g->size_x, g->size_y, g->pitch);
+// box_set: -1 = the cluster kernel's boxes, >= 0 = those of that stream-plan variant.
+int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, int box_set, rsm_ctx::TmapPair* out) {
+  const auto key = std::make_tuple((const void*)g->d_cells, g->size_x, g->size_y, g->pitch, box_set);
   const char* what = nullptr;
   int code = 0;
   {
@@ -338,7 +340,7 @@ int grid_tmaps(rsm_ctx* ctx, const rsm_grid* g, rsm_ctx::TmapPair* out) {
       if (ctx->tmaps.size() > 8192) ctx->tmaps.clear();
       rsm_ctx::TmapPair pair;
       int bw[2], bh[2];
-      score_staged_boxes(bw, bh);
+      if (box_set < 0) score_staged_boxes(bw, bh); else score_stream_boxes(box_set, bw, bh);
       for (int b = 0; b < 2 && !what; ++b) {
         const cuuint64_t dims[2] = {cuuint64_t(g->size_x), cuuint64_t(g->size_y)};
         const cuuint64_t strides[1] = {cuuint64_t(g->pitch) * 4};
@@ -646,6 +648,111 @@ bool same_plan(const PassItem& a, const PassItem& b) {
   return a.geo.n_xy == b.geo.n_xy && a.geo.factor == b.geo.factor && a.grid->fixed == b.grid->fixed;
 }
 
+// ---- stream plan of the staged scoring kernel (rsm_score.cu: score_stream_kernel) ----------------------
+// The (job, angle, tile) items of a launch laid end to end; an item costs, in beams of a full tile: its beams x the
+// tile's share of a full tile's shared-memory loads + 19 fixed (job fetch, beam table, pipeline fill) + 55 x that share
+// for the epilogue.  n_cta equal shares; a cut closer than 24 beams to an item's end moves there.
+struct StreamRun { int V, n_xy, ang_count, tiles_x, tiles_y; };
+struct StreamPlan { std::vector<StreamCta> ctas; std::vector<int> item_begin; int n_tickets = 0, n_slots = 0; long long n_items = 0; };
+
+void plan_stream(const std::vector<StreamRun>& runs, int variant, int max_ctas, StreamPlan& out) {
+  constexpr double kFixed = 19.0, kEpilogue = 55.0;
+  int tx, ty;
+  score_stream_tile(variant, &tx, &ty);
+  const double w_full = double(score_stream_weight(variant, tx, ty));
+  // per run: the tiles of one angle (the pattern repeats for every angle)
+  struct Info { double start, per_angle; long long item0; int tiles; size_t t0; };
+  std::vector<Info> info(runs.size());
+  std::vector<double> len, rho;
+  double total = 0.0;
+  long long n_items = 0;
+  out.item_begin.assign(runs.size() + 1, 0);
+  for (size_t r = 0; r < runs.size(); ++r) {
+    const StreamRun& R = runs[r];
+    Info& I = info[r];
+    I.start = total; I.item0 = n_items; I.tiles = R.tiles_x * R.tiles_y; I.t0 = len.size(); I.per_angle = 0.0;
+    for (int t = 0; t < I.tiles; ++t) {
+      const int ex = std::min(tx, R.n_xy - (t % R.tiles_x) * tx), ey = std::min(ty, R.n_xy - (t / R.tiles_x) * ty);
+      const double q = double(score_stream_weight(variant, ex, ey)) / w_full;
+      rho.push_back(q);
+      len.push_back(R.V * q + kFixed + kEpilogue * q);
+      I.per_angle += len.back();
+    }
+    total += I.per_angle * R.ang_count;
+    out.item_begin[r] = int(n_items);
+    n_items += (long long)R.ang_count * I.tiles;
+  }
+  out.item_begin[runs.size()] = int(n_items);
+  out.n_items = n_items;
+  const int G = int(std::max<long long>(1, std::min<long long>(max_ctas, (long long)(total / 96.0))));
+  // cuts: (item, beam, run of the item), strictly increasing; the k-th lies at k / G of the total length
+  struct Cut { long long item; int beam; int run; };
+  std::vector<Cut> cuts;
+  cuts.reserve(size_t(G) + 1);
+  cuts.push_back({0, 0, 0});
+  size_t r = 0;
+  for (int k = 1; k < G; ++k) {
+    const double target = total * k / G;
+    while (r + 1 < runs.size() && target >= info[r + 1].start) ++r;
+    const StreamRun& R = runs[r];
+    const Info& I = info[r];
+    double off = target - I.start;
+    const int ia = int(std::min<double>(R.ang_count - 1, std::floor(off / I.per_angle)));
+    off -= ia * I.per_angle;
+    int t = 0;
+    while (t + 1 < I.tiles && off >= len[I.t0 + t]) { off -= len[I.t0 + t]; ++t; }
+    const long long item = I.item0 + (long long)ia * I.tiles + t;
+    const int guard = std::min(24, R.V / 2);
+    const int beam = int(std::lround((off - kFixed) / rho[I.t0 + t]));
+    Cut c;
+    if (beam < guard || beam <= 0) c = {item, 0, int(r)};
+    else if (beam > R.V - guard || beam >= R.V) {
+      c = {item + 1, 0, int(r)};
+      if (c.item >= I.item0 + (long long)R.ang_count * I.tiles) c.run = int(r) + 1;
+    } else c = {item, beam, int(r)};
+    const Cut& l = cuts.back();
+    if (c.item < n_items && (c.item > l.item || (c.item == l.item && c.beam > l.beam))) cuts.push_back(c);
+  }
+  cuts.push_back({n_items, 0, int(runs.size())});
+  // shared items: those with a cut inside; parts = cuts inside + 1, in beam order
+  const size_t nc = cuts.size();
+  std::vector<int> cut_ticket(nc, -1), cut_ord(nc, 0), t_slot0, t_parts;
+  for (size_t c = 1; c + 1 < nc; ++c) {
+    if (cuts[c].beam == 0) continue;
+    if (cut_ticket[c - 1] >= 0 && cuts[c - 1].item == cuts[c].item && cuts[c - 1].beam > 0) {
+      cut_ticket[c] = cut_ticket[c - 1]; cut_ord[c] = cut_ord[c - 1] + 1;
+    } else {
+      cut_ticket[c] = int(t_parts.size()); cut_ord[c] = 0;
+      t_parts.push_back(1);
+    }
+    t_parts[cut_ticket[c]]++;
+  }
+  t_slot0.resize(t_parts.size());
+  int slots = 0;
+  for (size_t t = 0; t < t_parts.size(); ++t) { t_slot0[t] = slots; slots += t_parts[t]; }
+  out.n_tickets = int(t_parts.size()); out.n_slots = slots;
+  out.ctas.resize(nc - 1);
+  for (size_t c = 0; c + 1 < nc; ++c) {
+    StreamCta& A = out.ctas[c];
+    std::memset(&A, 0, sizeof A);
+    A.ticket0 = A.ticket1 = -1;
+    const Cut& b = cuts[c];
+    const Cut& e = cuts[c + 1];
+    A.item0 = int(b.item); A.beam0 = b.beam;
+    if (e.beam == 0) {
+      A.item1 = int(e.item - 1);
+      const int run = (e.run < int(runs.size()) && e.item > info[e.run].item0) ? e.run : e.run - 1;
+      A.beam1 = runs[run].V;
+    } else { A.item1 = int(e.item); A.beam1 = e.beam; }
+    if (b.beam > 0) { A.ticket0 = cut_ticket[c]; A.part0 = cut_ord[c] + 1; }
+    else if (e.beam > 0 && e.item == b.item) { A.ticket0 = cut_ticket[c + 1]; A.part0 = 0; }
+    if (A.ticket0 >= 0) { A.slot0 = t_slot0[A.ticket0]; A.parts0 = t_parts[A.ticket0]; }
+    if (e.beam > 0 && A.item1 != A.item0) {
+      A.ticket1 = cut_ticket[c + 1]; A.part1 = 0; A.slot1 = t_slot0[A.ticket1]; A.parts1 = t_parts[A.ticket1];
+    }
+  }
+}
+
 // ---- launch: host preparation + everything enqueued on the lane's stream ------------------------------
 int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std::vector<int>& act_in, PassMode mode,
                double* scores_out, int64_t scores_cap, int64_t* scores_written, PassRun& R) {
@@ -688,6 +795,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     max_V = std::max(max_V, it.geo.visited);
   }
   int n_split = 1, staged_variant = 0, split_b = 0;   // split_b: split of the second launch, 0 = one launch
+  bool use_stream = false;
+  int stream_variant = 0;
+  StreamPlan splan;
   long long items_a = 0;                             // (angle, tile) items of the first launch
   if (use_staged) {
     int tx, ty;
@@ -738,6 +848,30 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     if (std::getenv("RSM_DEBUG_SPLIT"))
       std::fprintf(stderr, "[rsm] staged plan: %lld items, split %d for the first %lld, split %d for the rest, cost %.0f\n",
                    work_items, n_split, items_a, split_b, best_cost);
+    // Stream plan (persistent CTAs over one sequence of beams) from half a wave of items on: no wave quantisation
+    // and the paired-row mapping for 65+ columns.  Below that the cluster plan splits the epilogue too.
+    // RSM_STAGED_PLAN=cluster|stream forces one; RSM_STREAM_CTAS / RSM_STREAM_VARIANT override the shape (tests).
+    if (ctx->sm_count <= 0) cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+    const char* plan_env = std::getenv("RSM_STAGED_PLAN");
+    use_stream = plan_env ? std::strcmp(plan_env, "stream") == 0 : 2 * work_items >= ctx->sm_count;
+    if (use_stream) {
+      stream_variant = score_stream_variant(max_nxy);
+      if (const char* e = std::getenv("RSM_STREAM_VARIANT")) stream_variant = std::max(0, std::min(2, std::atoi(e)));
+      score_stream_tile(stream_variant, &tx, &ty);
+      cfg.lx = tx; cfg.rows = ty;
+      std::vector<StreamRun> runs(na);
+      for (int a = 0; a < na; ++a) {
+        const PassItem& it = items[act[a]];
+        runs[a] = {it.geo.visited, it.geo.n_xy, it.a1 - it.a0, (it.geo.n_xy + tx - 1) / tx, (it.geo.n_xy + ty - 1) / ty};
+      }
+      int max_ctas = std::max(1, ctx->sm_count);
+      if (const char* e = std::getenv("RSM_STREAM_CTAS")) max_ctas = std::max(1, std::atoi(e));
+      plan_stream(runs, stream_variant, max_ctas, splan);
+      if (splan.n_items > INT_MAX / 2) use_stream = false;
+      if (std::getenv("RSM_DEBUG_SPLIT"))
+        std::fprintf(stderr, "[rsm] stream plan: variant %d, %lld items over %zu CTAs, %d shared (%d partial slots)\n", stream_variant,
+                     splan.n_items, splan.ctas.size(), splan.n_tickets, splan.n_slots);
+    }
   }
   // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
   bool use_flat = !use_staged && !cfg.affine && std::getenv("RSM_NO_FLAT") == nullptr;
@@ -811,6 +945,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   for (int a = 0; a < na; ++a) { items[act[a]].trig_off = trig_doubles; trig_doubles += size_t(items[act[a]].geo.n_ang) * 3; }
   const size_t o_trig = dl.take(trig_doubles * 8);
   const size_t o_tmaps = dl.take(use_staged ? size_t(na) * 256 : 0, 128);
+  const size_t o_splan = dl.take(use_stream ? splan.ctas.size() * sizeof(StreamCta) : 0, 16);
   const size_t up_bytes = dl.off;          // everything above is uploaded in one copy
   // zero-initialised block: [beam-split accumulators and tickets (not read back),] best keys, err flags, pool counter
   size_t acc_total = 0, ticket_total = 0;
@@ -825,7 +960,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     }
   const size_t o_acc = dl.take(acc_total * 8, 256);
   const size_t o_tickets = dl.take(ticket_total * 4, 4);
-  const size_t zero_begin = beam_split > 1 ? o_acc : dl.off;
+  const size_t o_stickets = dl.take(use_stream ? size_t(splan.n_tickets) * 4 : 0, 4);   // stream plan: tickets of the shared items
+  const size_t zero_begin = beam_split > 1 ? o_acc : use_stream ? o_stickets : dl.off;
+  const bool zero_wide = beam_split > 1 || use_stream;      // the zeroed block starts before the best keys
   const size_t o_best = dl.take(size_t(na) * 8, beam_split > 1 ? 8 : 256);
   const size_t o_err = dl.take(size_t(na) * 4, 4);
   const size_t o_poolcnt = dl.take(4, 4);
@@ -863,6 +1000,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   size_t score_doubles = 0;
   for (int a = 0; a < na; ++a) { items[act[a]].score_off = score_doubles; score_doubles += size_t(items[act[a]].n_local); }
   const size_t o_score = dl.take(score_doubles * 8);
+  const size_t o_spart = dl.take(use_stream ? size_t(splan.n_slots) * score_stream_partial_words(stream_variant) * 8 : 0, 256);
   int rc = ensure_dev(ctx, lane->d_work, dl.off, st);
   if (rc) return rc;
   char* dw = lane->d_work.p;
@@ -907,14 +1045,14 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     J.use_penalty = it.param.use_center_penalty ? 1 : 0;
     J.f_int = cfg.affine ? int(g.factor) : 0;
     J.stepoff = J.f_int * it.grid->pitch;
-    J.n_split = use_staged ? n_split : beam_split;
+    J.n_split = use_stream ? 1 : use_staged ? n_split : beam_split;
     if (beam_split > 1) {
       J.acc = reinterpret_cast<unsigned long long*>(dw + o_acc) + it.acc_off;
       J.tickets = reinterpret_cast<int*>(dw + o_tickets) + it.ticket_off;
     }
     if (use_staged) {
       rsm_ctx::TmapPair tp;
-      rc = grid_tmaps(ctx, it.grid, &tp);
+      rc = grid_tmaps(ctx, it.grid, use_stream ? stream_variant : -1, &tp);
       if (rc) return rc;
       std::memcpy(up + o_tmaps + size_t(a) * 256, &tp, 256);
       J.tmap = dw + o_tmaps + size_t(a) * 256;
@@ -953,7 +1091,12 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   struct StagedLaunch { int split = 1, n_jobs = 0, n_cta = 0, beams = 0; size_t jobs_off = 0, cta_off = 0; };
   StagedLaunch launches[2];
   int n_launches = 0;
-  if (use_staged) {
+  if (use_stream) {
+    std::memcpy(up + o_sjobs, sjobs.data(), sizeof(ScoreJob) * na);
+    std::memcpy(up + o_scta, splan.item_begin.data(), sizeof(int) * (na + 1));
+    std::memcpy(up + o_splan, splan.ctas.data(), sizeof(StreamCta) * splan.ctas.size());
+    n_launches = 1;
+  } else if (use_staged) {
     std::vector<ScoreJob> pj[2];
     std::vector<int> pc[2];
     long long left_a = split_b ? items_a : (long long)1 << 60;
@@ -1001,10 +1144,10 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   char* dn = lane->h_down.p;
   const size_t head_bytes = o_pool - o_best;
   const int pool_first = std::min(pool_cap, std::max(4096, na * 8));
-  const bool fork = use_staged && n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
+  const bool fork = use_staged && !use_stream && n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
   auto enqueue_score = [&]() -> int {
     CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(dw + (beam_split > 1 ? zero_begin : o_best), 0, zero_end - (beam_split > 1 ? zero_begin : o_best), st));
+    CU(cudaMemsetAsync(dw + (zero_wide ? zero_begin : o_best), 0, zero_end - (zero_wide ? zero_begin : o_best), st));
     {
       Prof p(ctx, KC_SCORE, lane);
       if (use_flat)
@@ -1013,6 +1156,10 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       else if (use_patch)
         CU(launch_score_patch(patch_nxy, cta, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                               reinterpret_cast<const int*>(dw + o_scta), na));
+      else if (use_stream)
+        CU(launch_score_stream(stream_variant, int(splan.ctas.size()), max_V, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+                               reinterpret_cast<const int*>(dw + o_scta), na, reinterpret_cast<const StreamCta*>(dw + o_splan),
+                               reinterpret_cast<unsigned long long*>(dw + o_spart), reinterpret_cast<int*>(dw + o_stickets)));
       else if (use_staged) {
         // the launches cover disjoint angles: the second one goes to a side stream so that its
         // clusters take SMs as soon as CTAs of the first retire (no kernel-boundary drain between them)
@@ -1077,7 +1224,8 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
                                   (long long)o_best, (long long)zero_end, use_flat * (1 + 8 * flat_k) + 2 * (use_patch ? patch_nxy : 0) + 64 * beam_split, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
                                   total_sel_cta, (long long)o_ljobs, (long long)o_lcta, (long long)o_pool, pool_cap,
-                                  (long long)o_poolcnt, (long long)head_bytes, pool_first};
+                                  (long long)o_poolcnt, (long long)head_bytes, pool_first, use_stream, stream_variant,
+                                  (long long)splan.ctas.size(), (long long)o_splan, (long long)o_spart, (long long)o_stickets, (long long)zero_begin, max_V};
     for (int l = 0; l < n_launches; ++l) {
       const StagedLaunch& L = launches[l];
       key.insert(key.end(), {L.split, L.n_cta, L.beams, (long long)L.jobs_off, (long long)L.cta_off, L.n_jobs});
@@ -2542,6 +2690,30 @@ int rsm_microbench_gather(rsm_ctx* ctx, int mode, int64_t footprint_bytes, int i
   const double bytes = double(n_cta) * 1024.0 * double(iters) * 4.0;
   *gbps = bytes / (double(ms) * 1e-3) / 1e9;
   return RSM_OK;
+}
+
+int rsm_stream_plan(int n_runs, const int* runs, int variant, int max_ctas, int* out, int cap, int64_t* n_items,
+                    int* n_tickets, int* n_slots) {
+  if (n_runs < 1 || !runs || max_ctas < 1 || variant > 2) return 0;
+  int widest = 0;
+  for (int i = 0; i < n_runs; ++i) widest = std::max(widest, runs[3 * i + 1]);
+  if (variant < 0) variant = score_stream_variant(widest);
+  int tx, ty;
+  score_stream_tile(variant, &tx, &ty);
+  std::vector<StreamRun> rr(n_runs);
+  for (int i = 0; i < n_runs; ++i) {
+    if (runs[3 * i] < 1 || runs[3 * i + 1] < 1 || runs[3 * i + 2] < 1) return 0;
+    rr[i] = {runs[3 * i], runs[3 * i + 1], runs[3 * i + 2], (runs[3 * i + 1] + tx - 1) / tx, (runs[3 * i + 1] + ty - 1) / ty};
+  }
+  StreamPlan P;
+  plan_stream(rr, variant, max_ctas, P);
+  if (n_items) *n_items = P.n_items;
+  if (n_tickets) *n_tickets = P.n_tickets;
+  if (n_slots) *n_slots = P.n_slots;
+  if (int(P.ctas.size()) > cap || !out) return -int(P.ctas.size());
+  static_assert(sizeof(StreamCta) == 12 * sizeof(int), "StreamCta layout");
+  std::memcpy(out, P.ctas.data(), P.ctas.size() * sizeof(StreamCta));
+  return int(P.ctas.size());
 }
 
 int rsm_match_chain(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pts, const rsm_pass_param params[3],

@@ -73,6 +73,17 @@ struct ScoreJob {
   double gain;           // distance penalty gain (:759-761)
 };
 
+// Stream plan of the staged scoring kernel (rsm_score.cu, score_stream_kernel): the (job, angle, tile) items of a
+// launch form one sequence of beams; every persistent CTA takes a contiguous range of it.  An item cut between CTAs
+// is finished by whichever of them arrives last (ticket), from the integer partial sums the others left in a slot.
+struct StreamCta {
+  int item0, beam0;      // first item of the range and the first beam of it this CTA visits
+  int item1, beam1;      // last item (inclusive) and the end of its beams (exclusive)
+  int ticket0, slot0, part0, parts0;   // item0 shared with other CTAs: its ticket, its first partial slot, this CTA's part,
+                                       // the number of parts; ticket0 < 0: item0 is this CTA's alone
+  int ticket1, slot1, part1, parts1;   // the same for item1 when item1 != item0
+};
+
 // Averaging-set candidates of all jobs of a launch land in one pool (appended with an atomic
 // counter, so the order is arbitrary; the host buckets by job and sorts).
 struct PoolEntry {

@@ -39,6 +39,17 @@ size_t score_staged_smem(int beams_per_split);
 int score_staged_resident_ctas(int variant, int n_split, int max_beams_per_split);
 cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_beams_per_split, cudaStream_t st,
                                 const ScoreJob* jobs, const int* cta_begin, int n_jobs);
+// Stream plan of the staged variant: n_cta persistent CTAs, each with a contiguous share (StreamCta) of the launch's
+// (job, angle, tile, beam) sequence; item_begin[j] = first item of job j (items = ang_count * tiles_x * tiles_y).
+// variant: score_stream_variant(n_xy); tiles, TMA boxes and per-beam cost of a (partial) tile come from the variant.
+int score_stream_variant(int n_xy);
+void score_stream_tile(int variant, int* tile_x, int* tile_y);
+void score_stream_boxes(int variant, int box_w[2], int box_h[2]);
+int score_stream_weight(int variant, int ext_x, int ext_y);
+size_t score_stream_partial_words(int variant);   // 64-bit words per partial slot
+size_t score_stream_smem(int max_beams);
+cudaError_t launch_score_stream(int variant, int n_cta, int max_beams, cudaStream_t st, const ScoreJob* jobs, const int* item_begin,
+                                int n_jobs, const StreamCta* plan, unsigned long long* partials, int* tickets);
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,
                           int n_jobs, PoolEntry* pool, int pool_cap, int* pool_count);
 cudaError_t launch_gather(int n_jobs, cudaStream_t st, const GatherJob* jobs);

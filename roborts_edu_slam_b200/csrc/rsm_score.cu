@@ -34,36 +34,9 @@
 
 #include "rsm_device.h"
 #include "rsm_kernels.h"
+#include "rsm_select.cuh"
 
 namespace rsm {
-
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
-
-__device__ __forceinline__ unsigned long long score_key(double v) {
-  unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = w > v ? w : v;
-  }
-  return v;
-}
-
-__device__ __forceinline__ int find_job(const int* __restrict__ cta_begin, int n_jobs, int b) {
-  int lo = 0, hi = n_jobs - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (__ldg(cta_begin + mid) <= b) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
 
 template <int RYP> struct RowVec;
 template <> struct RowVec<1> { __device__ static void load(const int* p, int* r) { r[0] = p[0]; } };
@@ -1373,6 +1346,455 @@ score_staged_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ c
   if (S > 1) cluster_sync();   // peers may still be reading this CTA's partial sums
 }
 
+
+// =================================================================================================
+// stream plan: persistent CTAs over ONE sequence of (angle, tile, beam) units
+// =================================================================================================
+// The cluster plan above quantises: config 2 is 181 (angle, tile) items on 148 SMs -- one full wave and a
+// fifth of a second one.  Here the host lays every item of a launch end to end, weighs it (beams x the
+// tile's shared-memory wavefronts per beam + fixed costs) and gives each of the resident CTAs an equal,
+// contiguous share (StreamCta).  A CTA walks its items with one running TMA pipeline; an item cut between
+// CTAs is finished by whichever arrives last: everyone leaves integer partial sums in a slot of global
+// scratch, takes a ticket, and the last one adds the other slots to its registers and runs the epilogue.
+// Nobody waits for anybody, so the kernel cannot deadlock when fewer CTAs are resident than launched.
+//
+// Two candidate-to-thread mappings:
+//   MapLanes<RX, RY>   as the cluster kernel: a warp owns RY rows, lanes walk RX x 32 columns.
+//   MapPaired          for windows of 32 m + 17 .. 32 m + 32 columns (81 = 2 * 32 + 16 + 1): tiles of 81 columns.
+//                      Columns 0..63 as above (two loads per row); columns 64..79 of rows r and r + 4 share ONE
+//                      load (lanes 0-15 / 16-31) and column 80 of the warp's eight rows one more (lanes 0-7).
+//                      The box pitch is 4 (mod 32) words, so rows r and r + 4 are 16 banks apart and eight rows
+//                      spread over eight banks: both loads are conflict-free.  21 loads for 8 x 81 cells (20.25 at
+//                      best) where three lane groups per row take 24.
+template <int RX, int RY>
+struct MapLanes {
+  static constexpr int kWarps = 16, kRows = RY, kTileX = 32 * RX, kTileY = kWarps * RY, kNC = RX * RY;
+  static constexpr int kW0 = 160, kH0 = 128, kW1 = 128, kH1 = 160;
+  __device__ static __forceinline__ bool slot(int c, int lane, int& dx, int& dy) {
+    dx = lane + 32 * (c % RX); dy = c / RX;
+    return true;
+  }
+  template <int SW, int NX, bool FULL>
+  __device__ static __forceinline__ void beam(unsigned int (&lo)[kNC], const int* q, int rows) {
+    int v[RY][NX];
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < NX; ++rx) v[ry][rx] = (FULL || ry < rows) ? q[ry * SW + rx * 32] : 0;
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < NX; ++rx) lo[ry * RX + rx] += (unsigned int)v[ry][rx];
+  }
+  // the offsets of four beams come with one 16-byte load (a broadcast: one wavefront instead of four)
+  template <int SW, int NX, bool FULL>
+  __device__ static __forceinline__ void run(unsigned int (&lo)[kNC], const int* q0, const int* bases, int n, int rows) {
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {
+      const int4 b = *reinterpret_cast<const int4*>(bases + j);
+      beam<SW, NX, FULL>(lo, q0 + b.x, rows); beam<SW, NX, FULL>(lo, q0 + b.y, rows);
+      beam<SW, NX, FULL>(lo, q0 + b.z, rows); beam<SW, NX, FULL>(lo, q0 + b.w, rows);
+    }
+    for (; j < n; ++j) beam<SW, NX, FULL>(lo, q0 + bases[j], rows);
+  }
+  template <int SW>
+  __device__ static __forceinline__ void round(unsigned int (&lo)[kNC], const int* buf, const int* bases, int n, int warp, int lane,
+                                               int rows, int ext_x) {
+    const int* q0 = buf + warp * RY * SW + lane;
+    const int nx = (ext_x + 31) >> 5;
+    if (rows == RY) {
+      if (nx == RX) run<SW, RX, true>(lo, q0, bases, n, rows);
+      else if (RX > 2 && nx == 2) run<SW, (RX > 2 ? 2 : 1), true>(lo, q0, bases, n, rows);
+      else run<SW, 1, true>(lo, q0, bases, n, rows);
+    } else {
+      if (nx == RX) run<SW, RX, false>(lo, q0, bases, n, rows);
+      else if (RX > 2 && nx == 2) run<SW, (RX > 2 ? 2 : 1), false>(lo, q0, bases, n, rows);
+      else run<SW, 1, false>(lo, q0, bases, n, rows);
+    }
+  }
+};
+
+struct MapPaired {
+  static constexpr int kWarps = 12, kRows = 8, kTileX = 81, kTileY = kWarps * 8, kNC = 21;
+  static constexpr int kW0 = 164, kH0 = 124, kW1 = 132, kH1 = 155;     // pitches = 4 (mod 32)
+  __device__ static __forceinline__ bool slot(int c, int lane, int& dx, int& dy) {
+    if (c < 16) { dx = lane + 32 * (c & 1); dy = c >> 1; return true; }
+    if (c < 20) { dx = 64 + (lane & 15); dy = (c - 16) + 4 * (lane >> 4); return true; }
+    dx = 80; dy = lane & 7;
+    return lane < 8;
+  }
+  template <int SW, int NF, bool PAIR, bool COL, bool FULL>
+  __device__ static __forceinline__ void beam(unsigned int (&lo)[kNC], const int* qa, const int* qp, const int* qc, int rows, int rows_p,
+                                              bool col_ok) {
+    int va[8][NF], vp[4], vc = 0;
+#pragma unroll
+    for (int ry = 0; ry < 8; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < NF; ++rx) va[ry][rx] = (FULL || ry < rows) ? qa[ry * SW + rx * 32] : 0;
+    if (PAIR) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) vp[p] = (FULL || p < rows_p) ? qp[p * SW] : 0;
+    }
+    if (COL) vc = (FULL || col_ok) ? qc[0] : 0;
+#pragma unroll
+    for (int ry = 0; ry < 8; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < NF; ++rx) lo[ry * 2 + rx] += (unsigned int)va[ry][rx];
+    if (PAIR) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) lo[16 + p] += (unsigned int)vp[p];
+    }
+    if (COL) lo[20] += (unsigned int)vc;
+  }
+  // the offsets of four beams come with one 16-byte load (a broadcast: one wavefront instead of four)
+  template <int SW, int NF, bool PAIR, bool COL, bool FULL>
+  __device__ static __forceinline__ void run(unsigned int (&lo)[kNC], const int* qa0, const int* qp0, const int* qc0, const int* bases,
+                                             int n, int rows, int rows_p, bool col_ok) {
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {
+      const int4 b = *reinterpret_cast<const int4*>(bases + j);
+      beam<SW, NF, PAIR, COL, FULL>(lo, qa0 + b.x, qp0 + b.x, qc0 + b.x, rows, rows_p, col_ok);
+      beam<SW, NF, PAIR, COL, FULL>(lo, qa0 + b.y, qp0 + b.y, qc0 + b.y, rows, rows_p, col_ok);
+      beam<SW, NF, PAIR, COL, FULL>(lo, qa0 + b.z, qp0 + b.z, qc0 + b.z, rows, rows_p, col_ok);
+      beam<SW, NF, PAIR, COL, FULL>(lo, qa0 + b.w, qp0 + b.w, qc0 + b.w, rows, rows_p, col_ok);
+    }
+    for (; j < n; ++j) {
+      const int b = bases[j];
+      beam<SW, NF, PAIR, COL, FULL>(lo, qa0 + b, qp0 + b, qc0 + b, rows, rows_p, col_ok);
+    }
+  }
+  template <int SW>
+  __device__ static __forceinline__ void round(unsigned int (&lo)[kNC], const int* buf, const int* bases, int n, int warp, int lane,
+                                               int rows, int ext_x) {
+    const int* qa = buf + warp * 8 * SW + lane;
+    const int* qp = buf + (warp * 8 + 4 * (lane >> 4)) * SW + 64 + (lane & 15);
+    const int* qc = buf + (warp * 8 + (lane & 7)) * SW + 80;
+    const int rows_p = rows - 4 * (lane >> 4);
+    const bool col_ok = (lane & 7) < rows;
+    if (rows == 8) {
+      if (ext_x > 80) run<SW, 2, true, true, true>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+      else if (ext_x > 64) run<SW, 2, true, false, true>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+      else if (ext_x > 32) run<SW, 2, false, false, true>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+      else run<SW, 1, false, false, true>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+    } else {
+      if (ext_x > 80) run<SW, 2, true, true, false>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+      else if (ext_x > 64) run<SW, 2, true, false, false>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+      else if (ext_x > 32) run<SW, 2, false, false, false>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+      else run<SW, 1, false, false, false>(lo, qa, qp, qc, bases, n, rows, rows_p, col_ok);
+    }
+  }
+};
+
+template <class Map>
+__global__ void __launch_bounds__((Map::kWarps + 1) * 32, 1)
+score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ item_begin, int n_jobs,
+                    const StreamCta* __restrict__ plan, unsigned long long* __restrict__ partials, int* __restrict__ tickets) {
+  constexpr int kW = Map::kWarps, kT = (kW + 1) * 32, kCT = kW * 32, NC = Map::kNC, RY = Map::kRows;
+  constexpr int TILE_X = Map::kTileX, TILE_Y = Map::kTileY;
+  static_assert(Map::kW0 * Map::kH0 <= kBufCells && Map::kW1 * Map::kH1 <= kBufCells, "box larger than its buffer");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == kW;
+
+  __shared__ ScoreJob J;
+  __shared__ int s_job, s_ticket;
+  __shared__ unsigned long long s_wmax[kW];
+  __shared__ double sX[TILE_X], sY[TILE_Y], sDX2[TILE_X], sDY2[TILE_Y];
+  __shared__ __align__(16) int sBase[2][kRound];
+  __shared__ int sMeta[2][4];
+  __shared__ __align__(8) uint64_t sFull[2], sEmpty[2];
+  __shared__ int sUnsafeCount;
+  __shared__ int sUnsafe[64];
+  extern __shared__ __align__(128) unsigned char dyn[];
+  int* buf0 = reinterpret_cast<int*>(dyn);
+  int* buf1 = buf0 + kBufCells;
+  int2* sBeam = reinterpret_cast<int2*>(buf1 + kBufCells + 128);   // (+ 512 bytes: lanes beyond the window read past a box)
+
+  const StreamCta P = plan[blockIdx.x];
+  if (tid == 0) {
+    mbar_init(&sFull[0], 1); mbar_init(&sFull[1], 1);
+    mbar_init(&sEmpty[0], kW); mbar_init(&sEmpty[1], kW);
+  }
+  int r = 0;                       // rounds of this CTA so far: the pipeline runs on across items
+
+  for (int item = P.item0; item <= P.item1; ++item) {
+    __syncthreads();               // the previous item is finished: J, the tables and the beam list are free
+    const long long d0 = DBG_T(); (void)d0;
+    if (tid == 0) { s_job = find_job(item_begin, n_jobs, item); sUnsafeCount = 0; }
+    __syncthreads();
+    {
+      const int* src = reinterpret_cast<const int*>(jobs + s_job);
+      int* dst = reinterpret_cast<int*>(&J);
+      for (int i = tid; i < int(sizeof(ScoreJob) / 4); i += kT) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int local = item - __ldg(item_begin + s_job);
+    const int tiles = J.tiles_x * J.tiles_y;
+    const int ia_local = local / tiles;
+    const int tile = local - ia_local * tiles;
+    const int tx0 = (tile % J.tiles_x) * TILE_X;
+    const int ty0 = (tile / J.tiles_x) * TILE_Y;
+    const int ia = J.ang_begin + ia_local;
+    const double cs = __ldg(J.trig + 3 * ia), sn = __ldg(J.trig + 3 * ia + 1), ang = __ldg(J.trig + 3 * ia + 2);
+    const int V = J.V, n_xy = J.n_xy, pitch = J.pitch, size_x = J.size_x, size_y = J.size_y;
+    const int v_begin = item == P.item0 ? P.beam0 : 0;
+    const int v_end = item == P.item1 ? P.beam1 : V;
+    const int nv = v_end - v_begin;
+    const bool first_shared = item == P.item0 && P.ticket0 >= 0;
+    const bool last_shared = item != P.item0 && item == P.item1 && P.ticket1 >= 0;
+    const bool shared = first_shared || last_shared;
+    const int* __restrict__ grid = reinterpret_cast<const int*>(J.grid);
+    const int ext_x = min(TILE_X, n_xy - tx0), ext_y = min(TILE_Y, n_xy - ty0);
+    const int rows = max(0, min(RY, n_xy - (ty0 + warp * RY)));
+
+    for (int i = tid; i < TILE_X + TILE_Y; i += kT) {
+      if (i < TILE_X) {
+        const double x = dadd(J.sx, dmul((double)(tx0 + i), J.f));
+        const double d = dsub(x, J.cx);
+        sX[i] = x; sDX2[i] = dmul(d, d);
+      } else {
+        const double y = dadd(J.sy, dmul((double)(ty0 + i - TILE_X), J.f));
+        const double d = dsub(y, J.cy);
+        sY[i - TILE_X] = y; sDY2[i - TILE_X] = dmul(d, d);
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < nv; j += kT) {
+      const int p = (v_begin + j) * J.step;
+      const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+      const double lx = dsub(dmul(cs, px), dmul(sn, py));
+      const double ly = dadd(dmul(sn, px), dmul(cs, py));
+      const double tx_ = dadd(dadd(lx, sX[0]), 0.5), ty_ = dadd(dadd(ly, sY[0]), 0.5);
+      const int gx0 = __double2int_rz(tx_), gy0 = __double2int_rz(ty_);
+      const double fx = tx_ - (double)gx0, fy = ty_ - (double)gy0;
+      const bool ok = fx > 1e-6 && fx < 1.0 - 1e-6 && fy > 1e-6 && fy < 1.0 - 1e-6 &&
+                      gx0 >= 0 && gx0 + ext_x - 1 < size_x && gy0 >= 0 && gy0 + ext_y - 1 < size_y;
+      sBeam[j] = ok ? make_int2(gx0, gy0) : make_int2(-1, -1);
+      if (!ok) { const int pos = atomicAdd(&sUnsafeCount, 1); if (pos < 64) sUnsafe[pos] = j; }
+    }
+    __syncthreads();
+
+    const long long d1 = DBG_T(); (void)d1;
+    unsigned int lo[NC];
+    unsigned int hi[(NC + 3) / 4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) lo[c] = 0u;
+#pragma unroll
+    for (int c = 0; c < (NC + 3) / 4; ++c) hi[c] = 0u;
+
+    if (nv <= 0) {
+      // (the host never plans an empty share)
+    } else if (producer) {
+      const char* tmaps = reinterpret_cast<const char*>(J.tmap);
+      if (lane == 0) { tmap_acquire(tmaps); tmap_acquire(tmaps + 128); }
+      __syncwarp();
+      int b = 0;
+      for (; b < nv; ++r) {
+        const int which = r & 1;
+        const long long p0 = DBG_T(); (void)p0;
+        const int j = b + lane;
+        int2 e = make_int2(-1, -1);
+        if (j < nv) e = sBeam[j];
+        const bool live = j < nv, safe = live && e.x >= 0;
+        int xmin = safe ? e.x : 0x7fffffff, xmax = safe ? e.x : -1, ymin = safe ? e.y : 0x7fffffff, ymax = safe ? e.y : -1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a0 = __shfl_up_sync(0xffffffffu, xmin, o), a1 = __shfl_up_sync(0xffffffffu, xmax, o);
+          const int a2 = __shfl_up_sync(0xffffffffu, ymin, o), a3 = __shfl_up_sync(0xffffffffu, ymax, o);
+          if (lane >= o) { xmin = min(xmin, a0); xmax = max(xmax, a1); ymin = min(ymin, a2); ymax = max(ymax, a3); }
+        }
+        const bool any = xmax >= 0;
+        const int xl = xmin & ~3;
+        const int dx = xmax - xl + ext_x, dy = ymax - ymin + ext_y;
+        const bool fit0 = live && (!any || (dx <= Map::kW0 && dy <= Map::kH0));
+        const bool fit1 = live && (!any || (dx <= Map::kW1 && dy <= Map::kH1));
+        const unsigned int vote0 = __ballot_sync(0xffffffffu, fit0), vote1 = __ballot_sync(0xffffffffu, fit1);
+        const int n0 = (vote0 == 0xffffffffu) ? 32 : (__ffs(~vote0) - 1);
+        const int n1 = (vote1 == 0xffffffffu) ? 32 : (__ffs(~vote1) - 1);
+        const bool tall = n1 > n0;
+        // (a beam whose own footprint fits neither box cannot occur: the tile is smaller than both)
+        const int n = max(1, tall ? n1 : n0), rw = tall ? Map::kW1 : Map::kW0;
+        const int srcl = n - 1;
+        const bool rany = __shfl_sync(0xffffffffu, (int)any, srcl) != 0;
+        int rxl = __shfl_sync(0xffffffffu, xl, srcl), ryl = __shfl_sync(0xffffffffu, ymin, srcl);
+        if (!rany) { rxl = 0; ryl = 0; }
+        const long long p1 = DBG_T(); (void)p1;
+        if (r >= 2) mbar_wait(&sEmpty[which], (uint32_t)(((r >> 1) - 1) & 1), 100);
+        const long long p2 = DBG_T(); (void)p2;
+        if (lane < n) sBase[which][lane] = safe ? (e.y - ryl) * rw + (e.x - rxl) : -1;
+        const unsigned int unsafe = __ballot_sync(0xffffffffu, lane < n && !safe);
+        if (lane == 0) { sMeta[which][0] = n; sMeta[which][1] = tall ? 1 : 0; sMeta[which][2] = (b + n >= nv) ? 1 : 0; sMeta[which][3] = unsafe == 0u; }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_expect_tx(&sFull[which], (uint32_t)((tall ? Map::kW1 * Map::kH1 : Map::kW0 * Map::kH0) * 4));
+          tma_box(which ? buf1 : buf0, tmaps + (tall ? 128 : 0), rxl, ryl, &sFull[which]);
+        }
+        b += n;
+#ifdef RSM_STAGED_DEBUG
+        if (lane == 0) { DBG_ADD(5, p1 - p0); DBG_ADD(6, p2 - p1); DBG_ADD(7, 1); DBG_ADD(13, DBG_T() - p2); }
+#endif
+      }
+    } else {
+      int pend = 0;                // beams added since the sums were last folded into the overflow counters
+      for (;; ++r) {
+        const int which = r & 1;
+        const long long c0 = DBG_T(); (void)c0;
+        mbar_wait(&sFull[which], (uint32_t)((r >> 1) & 1), 40);
+        const long long c1 = DBG_T(); (void)c1;
+        const int n = sMeta[which][0], tall = sMeta[which][1], last = sMeta[which][2], all_safe = sMeta[which][3];
+        const int* buf = which ? buf1 : buf0;
+        const int* bases = sBase[which];
+        // a beam adds at most 2^25 per sum: after a flush (sums < 2^31) 64 beams fit before the next one is due
+        if (pend + n > 64) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) { hi[c >> 2] += (lo[c] >> 31) << (8 * (c & 3)); lo[c] &= 0x7fffffffu; }
+          pend = 0;
+        }
+        pend += n;
+        if (rows > 0) {
+          if (all_safe) {
+            if (tall) Map::template round<Map::kW1>(lo, buf, bases, n, warp, lane, rows, ext_x);
+            else Map::template round<Map::kW0>(lo, buf, bases, n, warp, lane, rows, ext_x);
+          } else {
+            // a round with a beam that failed the tile-wide index test (rare): its cells come from global memory later
+            const int sw = tall ? Map::kW1 : Map::kW0;
+            for (int j = 0; j < n; ++j) {
+              const int base = bases[j];
+              if (base < 0) continue;
+#pragma unroll
+              for (int c = 0; c < NC; ++c) {
+                int dx, dy;
+                const bool used = Map::slot(c, lane, dx, dy);
+                if (used && dx < ext_x && dy < rows) lo[c] += (unsigned int)buf[base + (warp * RY + dy) * sw + dx];
+              }
+            }
+          }
+        }
+        const long long c2 = DBG_T(); (void)c2;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sEmpty[which]);
+#ifdef RSM_STAGED_DEBUG
+        if (lane == 0 && (warp == 0 || warp == 5)) { const int o = warp == 0 ? 8 : 16; DBG_ADD(o, c1 - c0); DBG_ADD(o + 1, c2 - c1); DBG_ADD(o + 2, DBG_T() - c2); DBG_ADD(o + 3, 1); DBG_ADD(o + 4, n); }
+#endif
+        if (last) { ++r; break; }
+      }
+    }
+    __syncthreads();
+    const long long d2 = DBG_T(); (void)d2;
+
+    unsigned long long a64[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a64[c] = ((unsigned long long)((hi[c >> 2] >> (8 * (c & 3))) & 0xffu) << 31) + lo[c];
+
+    int err = 0;
+    if (!producer && rows > 0) {
+      const int n_unsafe = sUnsafeCount;
+      const int n_slow = n_unsafe <= 64 ? n_unsafe : nv;
+      for (int u = 0; u < n_slow; ++u) {
+        const int j = n_unsafe <= 64 ? sUnsafe[u] : u;
+        if (sBeam[j].x >= 0) continue;
+        const int p = (v_begin + j) * J.step;
+        const double px = __ldg(J.pts + 2 * p), py = __ldg(J.pts + 2 * p + 1);
+        const double lx = dsub(dmul(cs, px), dmul(sn, py));
+        const double ly = dadd(dmul(sn, px), dmul(cs, py));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          int dx, dy;
+          const bool used = Map::slot(c, lane, dx, dy);
+          if (!used || dx >= ext_x || dy >= rows) continue;
+          int gx = cell_index(lx, sX[dx]), gy = cell_index(ly, sY[warp * RY + dy]);
+          if (gx < 0 || gx >= size_x || gy < 0 || gy >= size_y) {
+            err |= kErrWindow;
+            gx = max(0, min(gx, size_x - 1)); gy = max(0, min(gy, size_y - 1));
+          }
+          a64[c] += (unsigned int)__ldg(grid + (gy * pitch + gx));
+        }
+      }
+    }
+
+    if (shared) {
+      const int ticket = first_shared ? P.ticket0 : P.ticket1, slot0 = first_shared ? P.slot0 : P.slot1;
+      const int part = first_shared ? P.part0 : P.part1, parts = first_shared ? P.parts0 : P.parts1;
+      if (!producer) {
+        unsigned long long* mine = partials + (size_t)(slot0 + part) * (NC * kCT) + tid;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) __stcg(mine + c * kCT, a64[c]);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_ticket = atomicAdd(tickets + ticket, 1);
+      __syncthreads();
+      if (s_ticket != parts - 1) {          // somebody else finishes this item
+        if (err) atomicOr(J.err, err);
+#ifdef RSM_STAGED_DEBUG
+        if (tid == 0) { DBG_ADD(0, 1); DBG_ADD(1, d1 - d0); DBG_ADD(2, d2 - d1); DBG_ADD(3, DBG_T() - d2); }
+#endif
+        continue;
+      }
+      __threadfence();
+      if (!producer) {
+        for (int q = 0; q < parts; ++q) {
+          if (q == part) continue;
+          const unsigned long long* theirs = partials + (size_t)(slot0 + q) * (NC * kCT) + tid;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) a64[c] += __ldcg(theirs + c * kCT);
+        }
+      }
+    }
+
+    const long long d3 = DBG_T(); (void)d3;
+    // epilogue: response = sum / divisor (:659), centre penalty (:727-743), store, block maximum.  A rolled loop over the
+    // thread's slots with the sums staged through shared memory (the box buffers are idle): unrolled, the 2 x NC
+    // double-precision divisions alone are ~90 KB of straight-line code that runs once per item -- from a cold
+    // instruction cache every time (measured: 19.6 k -> 15.4 k cycles per item).
+    const long long k_angle = (long long)ia_local * n_xy * n_xy;
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(dyn) + tid;    // [NC][kCT], thread-private slots
+    unsigned long long kmax = 0ull;
+    if (!producer) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) stage[c * kCT] = a64[c];
+      const double da = dsub(ang, J.ca);
+      const double ap = fmax(dsub(1.0, ddiv(dmul(0.25, dmul(da, da)), 0.349)), 0.9);
+      const double divisor = J.divisor, m2 = J.m2, gain = J.gain, half_size = J.half_size;
+      const int use_penalty = J.use_penalty;
+      double* out = J.score + k_angle + (long long)tx0 * n_xy + (ty0 + warp * RY);
+#pragma unroll 1
+      for (int c = 0; c < NC; ++c) {
+        int dx, dy;
+        const bool used = Map::slot(c, lane, dx, dy);
+        if (used && dx < ext_x && dy < rows) {
+          double sc = ddiv(dmul((double)stage[c * kCT], kFixScale), divisor);
+          if (use_penalty) {
+            const bool zero = sc < 0.0 ? (sc >= -1e-06) : (sc <= 1e-06);
+            if (!zero) {
+              double d2 = dadd(sDX2[dx], sDY2[warp * RY + dy]);
+              d2 = dmul(d2, m2);
+              const double dp = fmax(dsub(1.0, ddiv(dmul(gain, d2), half_size)), 0.5);
+              sc = dmul(sc, dmul(dp, ap));
+            }
+          }
+          out[dx * n_xy + dy] = sc;
+          const unsigned long long key = score_key(sc);
+          kmax = key > kmax ? key : kmax;
+        }
+      }
+      const unsigned long long wmax = warp_max_u64(kmax);
+      if (lane == 0) s_wmax[warp] = wmax;
+    }
+    if (err) atomicOr(J.err, err);
+    __syncthreads();
+    unsigned long long item_key = 0ull;
+    for (int w = 0; w < kW; ++w) item_key = s_wmax[w] > item_key ? s_wmax[w] : item_key;
+    if (tid == 0) atomicMax(J.best_key, item_key);
+    const long long d4 = DBG_T(); (void)d4;
+    if (tid == 0) {
+#ifdef RSM_STAGED_DEBUG
+      DBG_ADD(0, 1); DBG_ADD(1, d1 - d0); DBG_ADD(2, d2 - d1); DBG_ADD(3, d3 - d2); DBG_ADD(4, d4 - d3); DBG_ADD(24, 1);
+#endif
+    }
+  }
+}
+
 }  // namespace staged
 
 // Tile shapes of the staged variant: 0 = 96 x 96 candidates per CTA, 1 = 64 x 64.
@@ -1444,6 +1866,76 @@ cudaError_t launch_score_staged(int variant, int n_split, int n_cta, int max_bea
   at[0].val.clusterDim.x = n_split; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, staged_fn(variant), jobs, cta_begin, n_jobs);
+}
+
+// ---- stream plan: host side ------------------------------------------------------------------------
+// variant 0: MapPaired (81 x 96 tiles), 1: MapLanes<2, 4> (64 x 64), 2: MapLanes<3, 6> (96 x 96, the cluster kernel's mapping)
+int score_stream_variant(int n_xy) { return n_xy > 64 ? 0 : 1; }
+
+void score_stream_tile(int variant, int* tile_x, int* tile_y) {
+  if (variant == 0) { *tile_x = staged::MapPaired::kTileX; *tile_y = staged::MapPaired::kTileY; }
+  else if (variant == 1) { *tile_x = 64; *tile_y = 64; }
+  else { *tile_x = 96; *tile_y = 96; }
+}
+
+void score_stream_boxes(int variant, int box_w[2], int box_h[2]) {
+  if (variant == 0) {
+    box_w[0] = staged::MapPaired::kW0; box_h[0] = staged::MapPaired::kH0;
+    box_w[1] = staged::MapPaired::kW1; box_h[1] = staged::MapPaired::kH1;
+  } else {
+    box_w[0] = staged::kBoxW0; box_h[0] = staged::kBoxH0;
+    box_w[1] = staged::kBoxW1; box_h[1] = staged::kBoxH1;
+  }
+}
+
+// shared-memory load instructions one beam costs a CTA on a tile whose window part is ext_x x ext_y
+int score_stream_weight(int variant, int ext_x, int ext_y) {
+  int w = 0;
+  if (variant == 0) {
+    const int per_row = ext_x > 32 ? 2 : 1;
+    for (int y = 0; y < ext_y; y += 8) {
+      const int rows = ext_y - y < 8 ? ext_y - y : 8;
+      w += rows * per_row + (ext_x > 64 ? (rows < 4 ? rows : 4) : 0) + (ext_x > 80 ? 1 : 0) + 1;
+    }
+  } else {
+    const int ry = variant == 1 ? 4 : 6, nx = (ext_x + 31) / 32;
+    for (int y = 0; y < ext_y; y += ry) w += (ext_y - y < ry ? ext_y - y : ry) * nx + 1;
+  }
+  return w;
+}
+
+size_t score_stream_partial_words(int variant) {
+  return variant == 0 ? size_t(staged::MapPaired::kNC) * staged::MapPaired::kWarps * 32
+       : variant == 1 ? size_t(8) * 16 * 32 : size_t(18) * 16 * 32;
+}
+
+size_t score_stream_smem(int max_beams) { return size_t(2 * staged::kBufCells) * 4 + 512 + size_t(max_beams) * 8; }
+
+typedef void (*StreamFn)(const ScoreJob*, const int*, int, const StreamCta*, unsigned long long*, int*);
+static StreamFn stream_fn(int variant) {
+  return variant == 0 ? staged::score_stream_kernel<staged::MapPaired>
+       : variant == 1 ? staged::score_stream_kernel<staged::MapLanes<2, 4>> : staged::score_stream_kernel<staged::MapLanes<3, 6>>;
+}
+
+cudaError_t launch_score_stream(int variant, int n_cta, int max_beams, cudaStream_t st, const ScoreJob* jobs, const int* item_begin,
+                                int n_jobs, const StreamCta* plan, unsigned long long* partials, int* tickets) {
+  static size_t configured[kMaxDevices][3] = {{0, 0, 0}};
+  if (variant < 0 || variant > 2) return cudaErrorInvalidValue;
+  const size_t smem = score_stream_smem(max_beams);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  {
+    std::lock_guard<std::mutex> lock(g_config_mutex);
+    if (smem > configured[dev][variant]) {
+      cudaError_t e = cudaFuncSetAttribute(stream_fn(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured[dev][variant] = smem;
+    }
+  }
+  const int threads = variant == 0 ? (staged::MapPaired::kWarps + 1) * 32 : staged::kThreads;
+  stream_fn(variant)<<<n_cta, threads, smem, st>>>(jobs, item_begin, n_jobs, plan, partials, tickets);
+  return cudaGetLastError();
 }
 
 #ifdef RSM_STAGED_DEBUG

@@ -138,6 +138,7 @@ ABI = {
     "rsm_scan_destroy": (None, [c_p, c_p]),
     "rsm_match_resident": (c_i, [c_p, c_p, c_p, _PPARAM, c_p, c_p, ctypes.POINTER(c_d), ctypes.POINTER(PassDetail)]),
     "rsm_microbench_gather": (c_i, [c_p, c_i, c_i64, c_i, ctypes.POINTER(c_d)]),
+    "rsm_stream_plan": (c_i, [c_i, c_p, c_i, c_i, c_p, c_i, ctypes.POINTER(c_i64), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
     "rsm_match_chain": (c_i, [c_p, c_p, c_p, c_i, _PPARAM, c_i, c_p, c_p, ctypes.POINTER(c_d), c_p]),
     "rsm_match_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, _PPARAM, c_i, c_i, c_p, c_p, c_p, c_p]),
     "rsm_loop_closure_batch": (c_i, [c_p, c_i, c_i, c_d, ctypes.c_float, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
@@ -188,6 +189,20 @@ def load_library():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def stream_plan(runs, variant=-1, max_ctas=148):
+    """The staged scoring kernel's stream plan for jobs (beams, n_xy, angles): host arithmetic only, no device.
+    Returns (shares [n, 12] int32, n_items, n_tickets, n_slots); see rsm_stream_plan in include/rsm.h."""
+    lib = load_library()
+    r = np.ascontiguousarray(np.asarray(runs, dtype=np.int32).reshape(-1, 3))
+    out = np.zeros((max(1, int(max_ctas)), 12), dtype=np.int32)
+    n_items, n_t, n_s = c_i64(0), c_i(0), c_i(0)
+    n = lib.rsm_stream_plan(len(r), r.ctypes.data, int(variant), int(max_ctas), out.ctypes.data, len(out), ctypes.byref(n_items),
+                            ctypes.byref(n_t), ctypes.byref(n_s))
+    if n <= 0:
+        raise ValueError("rsm_stream_plan: bad arguments (%d)" % n)
+    return out[:n].copy(), n_items.value, n_t.value, n_s.value
 
 
 def _f64(a):

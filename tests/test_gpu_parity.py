@@ -524,6 +524,66 @@ def test_staged_tiles_and_clusters(ctx, oracle, rng, n_xy, beams):
     dg.close()
 
 
+@pytest.mark.parametrize("n_xy,beams,variant,ctas", [
+    (81, 1000, 0, 148), (81, 1000, 0, 5), (81, 707, 2, 148), (65, 130, 0, 37), (97, 520, 0, 148), (131, 260, 0, 148),
+    (131, 260, 2, 23), (49, 90, 1, 148), (61, 700, 1, 148), (64, 300, 0, 148), (80, 333, 0, 148), (78, 200, 0, 11),
+    (33, 150, 0, 148), (163, 100, 0, 148), (163, 100, 1, 64)])
+def test_stream_plan_of_the_staged_kernel(ctx, oracle, rng, monkeypatch, n_xy, beams, variant, ctas):
+    """Stream plan (persistent CTAs over one beam sequence, items finished by the last CTA to arrive) with each of its
+    three tile mappings, forced on small windows: every score against the oracle.  Partial tiles on both sides, shares
+    that cut an item into many parts, more CTAs than items and fewer."""
+    monkeypatch.setenv("RSM_STAGED_PLAN", "stream")
+    monkeypatch.setenv("RSM_STREAM_VARIANT", str(variant))
+    monkeypatch.setenv("RSM_STREAM_CTAS", str(ctas))
+    g = synth.GridSpec(0.05, 0.15, 700, 600, 3.0, 2.0)
+    grid = synth.random_grid(rng, g.size_x, g.size_y)
+    dg = matcher.ScanMatchMap.from_spec(ctx, g)
+    dg.upload(grid)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    ang = np.sort(rng.uniform(-np.pi, np.pi, beams))
+    rad = rng.uniform(1.0, 7.0, beams)
+    pts = np.stack([np.cos(ang) * rad, np.sin(ang) * rad], axis=1)
+    pose = np.array([700 * 0.05 / 2 - 3.0 + 0.013, 600 * 0.05 / 2 - 2.0 - 0.021, 0.3])
+    p = synth.pass_param((n_xy - 1) * 0.05, 0.05, 0.06, 0.02, 0.3, 100000, True, 0)      # 6 or 7 angles
+    if n_xy < 48:
+        pytest.skip("staged variants start at 48 translations per axis")
+    so = oracle.scores(grid, g, pts, p, oracle.world_to_map(g, pose))
+    before = ctx.stats()["kernel_launches"]
+    sd = m.scores(dg, pts, p, pose)
+    assert ctx.stats()["kernel_launches"] - before == 1, "one persistent launch"
+    assert np.array_equal(so, sd)
+    want = oracle.match(grid, g, pts, p, pose)
+    for _ in range(3):          # the third call replays the pass as a CUDA graph: tickets must be zeroed again
+        pz, cz = pose.copy(), np.eye(3)
+        assert_pass_equal(m.ScanMatch(dg, pts, p, pz, cz), pz, cz, want)
+    # a window at the grid border: beams whose footprint leaves the grid take exact indices from global memory
+    half = min(n_xy - 1, 80) // 2
+    edge = np.array([-g.off_x + (half + 15) * 0.05 + 0.02, -g.off_y + (half + 15) * 0.05 + 0.03, -0.2])
+    q = synth.pass_param(2 * half * 0.05, 0.05, 0.04, 0.02, 0.3, 100000, True, 0)
+    short = pts[:60] * 0.1        # at most 14 cells long: the lowest cell touched is 0 or 1
+    so = oracle.scores(grid, g, short, q, oracle.world_to_map(g, edge))
+    assert np.array_equal(so, m.scores(dg, short, q, edge))
+    dg.close()
+
+
+def test_stream_plan_is_the_default_for_full_waves(ctx, oracle, monkeypatch):
+    """BASELINE configs[1] (181 items) takes the stream plan by default and equals the cluster plan bit for bit; a
+    batch of different windows shares one persistent launch."""
+    sc = synth.config2()
+    dg = device_grid(ctx, sc)
+    m = matcher.BasedCorrelationScanMatch(ctx)
+    p = sc.passes[0]
+    before = ctx.stats()["kernel_launches"]
+    got = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+    assert ctx.stats()["kernel_launches"] - before == 1
+    monkeypatch.setenv("RSM_STAGED_PLAN", "cluster")
+    before = ctx.stats()["kernel_launches"]
+    ref = m.scores(dg, sc.scan_pts, p, sc.seed_pose)
+    assert ctx.stats()["kernel_launches"] - before == 2
+    assert np.array_equal(got, ref)
+    dg.close()
+
+
 def test_wide_grid_runtime_pitch(ctx, oracle, rng):
     """Grids wider than the largest padded pitch (4128 cells) use the run-time stride variants."""
     g = synth.GridSpec(0.05, 0.15, 4300, 300, 1.0, 1.0)
@@ -778,13 +838,20 @@ def test_optimize_random_and_errors(ctx, oracle, rng):
         dg.close()
 
 
-def test_cell_boundary_fallback_paths(ctx, oracle, rng):
+@pytest.mark.parametrize("plan", ["default", "stream0", "stream1", "stream2"])
+def test_cell_boundary_fallback_paths(ctx, oracle, rng, monkeypatch, plan):
     """Beams whose rotated end point sits exactly on a cell boundary for a whole tile fail the kernels'
     provable index test and take the exact per-thread path.  Regression: the tiled kernel used to read
     those beams' end points from a buffer that the prefetch of a later chunk had already overwritten.
     Axis-aligned search angle (index 0 is exactly 0 rad), an integer-aligned centre and end points on a
-    half-cell lattice put every beam of angle 0 on that path; other angles run the fast path."""
+    half-cell lattice put every beam of angle 0 on that path; other angles run the fast path.
+    plan = stream<v>: the staged kernel's stream plan with tile mapping v forced on the wide windows (few CTAs, so
+    that rounds mix safe and unsafe beams and items are cut between CTAs)."""
     m = matcher.BasedCorrelationScanMatch(ctx)
+    if plan != "default":
+        monkeypatch.setenv("RSM_STAGED_PLAN", "stream")
+        monkeypatch.setenv("RSM_STREAM_VARIANT", plan[-1])
+        monkeypatch.setenv("RSM_STREAM_CTAS", "13")
     for n_pts, half_lattice, window, size in ((200, 1.0, 0.6, 200), (333, 0.2, 0.6, 200), (97, 1.0, 0.25, 200),
                                               (150, 1.0, 2.4, 320), (700, 0.05, 2.4, 320), (260, 1.0, 3.2, 400)):
         g = synth.GridSpec(0.05, 0.15, size, size, 0.0, 0.0)

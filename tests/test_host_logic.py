@@ -243,3 +243,57 @@ def test_angle_tables_are_libm_cos_and_sin(shim, rng):
     for i in idx:
         a = float(ang[i])
         assert out[i, 0] == libm.cos(a) and out[i, 1] == libm.sin(a), a
+
+
+@pytest.mark.parametrize("runs,variant,max_ctas", [
+    ([(707, 81, 181)], 0, 148),                 # BASELINE configs[1]: 181 items on 148 SMs
+    ([(707, 81, 181)], 2, 148),
+    ([(938, 321, 721)], 0, 148),                # configs[4]: 16 tiles per angle, partial tiles on two sides
+    ([(360, 49, 3)], 1, 148),                   # three items over many CTAs: every item has many parts
+    ([(360, 49, 3)], 1, 7),
+    ([(100, 81, 5), (707, 65, 9), (64, 97, 2), (2048, 81, 1)], 0, 33),   # a batch of different windows
+    ([(30, 81, 4)], 0, 148),                    # fewer beams than the cut guard
+])
+def test_stream_plan_covers_every_beam_once(runs, variant, max_ctas):
+    """Host side of the staged kernel's stream plan (csrc/rsm_api.cu plan_stream): the shares tile the (item, beam)
+    sequence exactly, shared items have consistent tickets, parts and disjoint partial slots."""
+    shares, n_items, n_tickets, n_slots = matcher.stream_plan(runs, variant, max_ctas)
+    tile = {0: (81, 96), 1: (64, 64), 2: (96, 96)}[variant]
+    beams = []
+    for v, n_xy, n_ang in runs:
+        beams += [v] * (n_ang * (-(-n_xy // tile[0])) * (-(-n_xy // tile[1])))
+    assert n_items == len(beams) and 1 <= len(shares) <= max_ctas
+    seen = [np.zeros(v, dtype=np.int32) for v in beams]
+    users = {}
+    prev_end = (0, 0)
+    for s in shares:
+        i0, b0, i1, b1, t0, s0, p0, n0, t1, s1, p1, n1 = [int(v) for v in s]
+        assert (i0, b0) == prev_end, "shares are contiguous"
+        assert i0 <= i1 and 0 <= b0 < beams[i0] and 0 < b1 <= beams[i1] and (i0 < i1 or b0 < b1)
+        for it in range(i0, i1 + 1):
+            lo, hi = (b0 if it == i0 else 0), (b1 if it == i1 else beams[it])
+            assert hi > lo, "no empty visit"
+            seen[it][lo:hi] += 1
+            whole = lo == 0 and hi == beams[it]
+            t, sl, pa, n = (t0, s0, p0, n0) if it == i0 else (t1, s1, p1, n1) if it == i1 else (-1, 0, 0, 0)
+            assert (t < 0) == whole, "an item is shared exactly when a share sees a part of it"
+            if t >= 0:
+                users.setdefault(it, []).append((t, sl, pa, n))
+        prev_end = (i1 + 1, 0) if b1 == beams[i1] else (i1, b1)
+    assert prev_end == (n_items, 0)
+    assert all((v == 1).all() for v in seen), "every beam of every item exactly once"
+    assert len(users) == n_tickets
+    slots = []
+    for it, us in users.items():
+        t, sl, _, n = us[0]
+        assert len(us) == n >= 2 and all(u[0] == t and u[1] == sl and u[3] == n for u in us)
+        assert sorted(u[2] for u in us) == list(range(n))
+        slots += list(range(sl, sl + n))
+    assert sorted(u[0][0] for u in users.values()) == list(range(n_tickets))
+    assert sorted(slots) == list(range(n_slots))
+    if len(shares) == max_ctas and len(runs) == 1 and variant != 1:
+        # equal shares: beams x tile weight per share within 15 % of the mean (single job, full-size launch)
+        v, n_xy, _ = runs[0]
+        if n_xy <= tile[0]:
+            w = [sum((b1 if it == i1 else v) - (b0 if it == i0 else 0) for it in range(i0, i1 + 1)) for i0, b0, i1, b1 in shares[:, :4]]
+            assert max(w) <= 1.15 * np.mean(w) and min(w) >= 0.85 * np.mean(w)

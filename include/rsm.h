@@ -18,7 +18,11 @@
  *   - there is NO CPU fallback: without a CUDA device rsm_create fails.
  *
  * Results are identical to the reference's CPU matcher on the same inputs: bit-exact cell
- * indices, candidate scores, response and best pose; covariance within 1e-6 relative.
+ * indices, candidate scores, response and best pose; covariance within 1e-6 relative (bit-equal
+ * unless equal scores tie inside a covariance prefix; RSM_OPT_STRICT_TIES routes those to the exact path).
+ * "The reference" = its own headers compiled against a stand-in for Eigen (oracle/standin): the
+ * Affine2d products of the map transforms and the 3 x 3 LDLT of the Gauss-Newton step follow Eigen 3.3's
+ * evaluation order as restated there, unverified against real Eigen (none in the build image).
  */
 #ifndef RSM_H_
 #define RSM_H_

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <tuple>
 #include <atomic>
 #include <chrono>
@@ -227,6 +228,10 @@ struct Lane {
   rsm_stats stats = {};                           // what this lane's passes counted since the last merge into the context's
 };
 
+// stream plan of the staged scoring kernel (plan_stream below)
+struct StreamRun { int V, n_xy, ang_count, tiles_x, tiles_y; };
+struct StreamPlan { std::vector<StreamCta> ctas; std::vector<int> item_begin; int n_tickets = 0, n_slots = 0; long long n_items = 0; };
+
 struct rsm_ctx {
   int device = 0;
   HostPool pool;
@@ -256,6 +261,7 @@ struct rsm_ctx {
   std::map<std::tuple<const void*, int, int, int, int>, TmapPair> tmaps;   // + box set
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   int sm_count = 0;               // multiprocessors of the device (stream plan: persistent CTAs)
+  std::map<std::vector<int>, std::shared_ptr<const StreamPlan>> stream_plans;   // by (beams, window, angles) per job: a front end repeats its shape
   // CUDA graphs of whole passes (upload, zeroing, score launches, select, read-back), keyed by
   // everything that shapes the launch sequence; the per-call data travels in the pinned buffer
   struct PassGraph { int seen = 0; cudaGraphExec_t exec = nullptr; };
@@ -652,8 +658,6 @@ bool same_plan(const PassItem& a, const PassItem& b) {
 // The (job, angle, tile) items of a launch laid end to end; an item costs, in beams of a full tile: its beams x the
 // tile's share of a full tile's shared-memory loads + 19 fixed (job fetch, beam table, pipeline fill) + 55 x that share
 // for the epilogue.  n_cta equal shares; a cut closer than 24 beams to an item's end moves there.
-struct StreamRun { int V, n_xy, ang_count, tiles_x, tiles_y; };
-struct StreamPlan { std::vector<StreamCta> ctas; std::vector<int> item_begin; int n_tickets = 0, n_slots = 0; long long n_items = 0; };
 
 void plan_stream(const std::vector<StreamRun>& runs, int variant, int max_ctas, StreamPlan& out) {
   constexpr double kFixed = 19.0, kEpilogue = 55.0;
@@ -797,7 +801,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   int n_split = 1, staged_variant = 0, split_b = 0;   // split_b: split of the second launch, 0 = one launch
   bool use_stream = false;
   int stream_variant = 0;
-  StreamPlan splan;
+  static const StreamPlan kNoPlan;
+  std::shared_ptr<const StreamPlan> splan_hold;      // keeps a cached plan alive while this pass uses it
+  const StreamPlan* splan = &kNoPlan;
   long long items_a = 0;                             // (angle, tile) items of the first launch
   if (use_staged) {
     int tx, ty;
@@ -866,11 +872,30 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       }
       int max_ctas = std::max(1, ctx->sm_count);
       if (const char* e = std::getenv("RSM_STREAM_CTAS")) max_ctas = std::max(1, std::atoi(e));
-      plan_stream(runs, stream_variant, max_ctas, splan);
-      if (splan.n_items > INT_MAX / 2) use_stream = false;
+      {
+        std::vector<int> key = {stream_variant, max_ctas};
+        for (const StreamRun& r : runs) key.insert(key.end(), {r.V, r.n_xy, r.ang_count});
+        std::shared_ptr<const StreamPlan> hit;
+        {
+          std::lock_guard<std::mutex> lk(ctx->mu);
+          auto it = ctx->stream_plans.find(key);
+          if (it != ctx->stream_plans.end()) hit = it->second;
+        }
+        if (!hit) {
+          auto made = std::make_shared<StreamPlan>();
+          plan_stream(runs, stream_variant, max_ctas, *made);
+          hit = made;
+          std::lock_guard<std::mutex> lk(ctx->mu);
+          if (ctx->stream_plans.size() >= 32) ctx->stream_plans.clear();
+          ctx->stream_plans[key] = hit;
+        }
+        splan_hold = hit;
+        splan = hit.get();
+      }
+      if (splan->n_items > INT_MAX / 2) use_stream = false;
       if (std::getenv("RSM_DEBUG_SPLIT"))
         std::fprintf(stderr, "[rsm] stream plan: variant %d, %lld items over %zu CTAs, %d shared (%d partial slots)\n", stream_variant,
-                     splan.n_items, splan.ctas.size(), splan.n_tickets, splan.n_slots);
+                     splan->n_items, splan->ctas.size(), splan->n_tickets, splan->n_slots);
     }
   }
   // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
@@ -945,7 +970,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   for (int a = 0; a < na; ++a) { items[act[a]].trig_off = trig_doubles; trig_doubles += size_t(items[act[a]].geo.n_ang) * 3; }
   const size_t o_trig = dl.take(trig_doubles * 8);
   const size_t o_tmaps = dl.take(use_staged ? size_t(na) * 256 : 0, 128);
-  const size_t o_splan = dl.take(use_stream ? splan.ctas.size() * sizeof(StreamCta) : 0, 16);
+  const size_t o_splan = dl.take(use_stream ? splan->ctas.size() * sizeof(StreamCta) : 0, 16);
   const size_t up_bytes = dl.off;          // everything above is uploaded in one copy
   // zero-initialised block: [beam-split accumulators and tickets (not read back),] best keys, err flags, pool counter
   size_t acc_total = 0, ticket_total = 0;
@@ -960,7 +985,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     }
   const size_t o_acc = dl.take(acc_total * 8, 256);
   const size_t o_tickets = dl.take(ticket_total * 4, 4);
-  const size_t o_stickets = dl.take(use_stream ? size_t(splan.n_tickets) * 4 : 0, 4);   // stream plan: tickets of the shared items
+  const size_t o_stickets = dl.take(use_stream ? size_t(splan->n_tickets) * 4 : 0, 4);   // stream plan: tickets of the shared items
   const size_t zero_begin = beam_split > 1 ? o_acc : use_stream ? o_stickets : dl.off;
   const bool zero_wide = beam_split > 1 || use_stream;      // the zeroed block starts before the best keys
   const size_t o_best = dl.take(size_t(na) * 8, beam_split > 1 ? 8 : 256);
@@ -1000,7 +1025,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   size_t score_doubles = 0;
   for (int a = 0; a < na; ++a) { items[act[a]].score_off = score_doubles; score_doubles += size_t(items[act[a]].n_local); }
   const size_t o_score = dl.take(score_doubles * 8);
-  const size_t o_spart = dl.take(use_stream ? size_t(splan.n_slots) * score_stream_partial_words(stream_variant) * 8 : 0, 256);
+  const size_t o_spart = dl.take(use_stream ? size_t(splan->n_slots) * score_stream_partial_words(stream_variant) * 8 : 0, 256);
   int rc = ensure_dev(ctx, lane->d_work, dl.off, st);
   if (rc) return rc;
   char* dw = lane->d_work.p;
@@ -1093,8 +1118,8 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   int n_launches = 0;
   if (use_stream) {
     std::memcpy(up + o_sjobs, sjobs.data(), sizeof(ScoreJob) * na);
-    std::memcpy(up + o_scta, splan.item_begin.data(), sizeof(int) * (na + 1));
-    std::memcpy(up + o_splan, splan.ctas.data(), sizeof(StreamCta) * splan.ctas.size());
+    std::memcpy(up + o_scta, splan->item_begin.data(), sizeof(int) * (na + 1));
+    std::memcpy(up + o_splan, splan->ctas.data(), sizeof(StreamCta) * splan->ctas.size());
     n_launches = 1;
   } else if (use_staged) {
     std::vector<ScoreJob> pj[2];
@@ -1157,7 +1182,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
         CU(launch_score_patch(patch_nxy, cta, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                               reinterpret_cast<const int*>(dw + o_scta), na));
       else if (use_stream)
-        CU(launch_score_stream(stream_variant, int(splan.ctas.size()), max_V, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
+        CU(launch_score_stream(stream_variant, int(splan->ctas.size()), max_V, st, reinterpret_cast<const ScoreJob*>(dw + o_sjobs),
                                reinterpret_cast<const int*>(dw + o_scta), na, reinterpret_cast<const StreamCta*>(dw + o_splan),
                                reinterpret_cast<unsigned long long*>(dw + o_spart), reinterpret_cast<int*>(dw + o_stickets)));
       else if (use_staged) {
@@ -1225,7 +1250,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
                                   total_sel_cta, (long long)o_ljobs, (long long)o_lcta, (long long)o_pool, pool_cap,
                                   (long long)o_poolcnt, (long long)head_bytes, pool_first, use_stream, stream_variant,
-                                  (long long)splan.ctas.size(), (long long)o_splan, (long long)o_spart, (long long)o_stickets, (long long)zero_begin, max_V};
+                                  (long long)splan->ctas.size(), (long long)o_splan, (long long)o_spart, (long long)o_stickets, (long long)zero_begin, max_V};
     for (int l = 0; l < n_launches; ++l) {
       const StagedLaunch& L = launches[l];
       key.insert(key.end(), {L.split, L.n_cta, L.beams, (long long)L.jobs_off, (long long)L.cta_off, L.n_jobs});
@@ -1565,7 +1590,12 @@ int upload_points(rsm_ctx* ctx, const double* pts_xy, size_t n_points, double** 
 int chain_lanes(const rsm_ctx* ctx, int n) {
   int lanes = ctx->lanes_wanted;
   if (const char* e = std::getenv("RSM_LANES")) lanes = std::atoi(e);
-  if (lanes <= 0) lanes = n >= 384 ? 4 : n >= 192 ? 3 : n >= 64 ? 2 : 1;
+  if (lanes <= 0) {
+    lanes = n >= 384 ? 4 : n >= 192 ? 3 : n >= 64 ? 2 : 1;
+    // eight sub-batches of 64 hide more of the host stages between the passes than four of 128 lose in kernel
+    // efficiency (512 pairs on one B200: 2.91 -> 2.63 ms per step) -- where the host has a core per lane thread to spare
+    if (n >= 512 && HostPool::env_threads() >= 12) lanes = 8;
+  }
   return std::max(1, std::min({lanes, 8, n}));
 }
 

@@ -54,6 +54,17 @@ CONFIG2_GRID = "1120x1120 @ 0.025 m"
 N_MAP_COPIES = 32      # x 5.0 MB of cells touched per match = 160 MB > the 126 MB L2
 
 
+def compact(x):
+    """Floats to 6 significant digits: the line stays short enough for a log tail without losing what is measured."""
+    if isinstance(x, float):
+        return float("%.6g" % x)
+    if isinstance(x, dict):
+        return {k: compact(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [compact(v) for v in x]
+    return x
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,16 +462,18 @@ def main():
         lc_roof = None
         if st_k["score_kernel_ms"] > 0:
             ach = ALGO_BYTES_PER_EVAL * st_k["evals"] / (st_k["score_kernel_ms"] * 1e-3) / 1e9
-            lc_roof = {"bound": "smem", "kernels": "score launches of the chain: patch (coarse, shared-memory tiles) + flat (fine, super-fine; L1-resident grid)",
+            lc_roof = {"bound": "smem", "kernels": "patch + flat (see details)",
                        "achieved": ach, "peak": smem_row, "unit": "GB/s", "frac": ach / smem_row,
                        "frac_of_global_row_l1l2": ach / glob_row_lc, "global_row_l1l2_peak": glob_row_lc,
                        "score_kernel_ms": st_k["score_kernel_ms"], "select_kernel_ms": st_k["select_kernel_ms"],
                        "raster_kernel_ms": st_k["raster_kernel_ms"], "evals_per_batch": st_k["evals"],
-                       "note": "one lane, profiled batch; 4 B x evaluations / summed score-kernel time"}
+                       }
         loop = dict(lc_store, pairs=int(args.pairs_per_gpu * world), contexts_per_gpu=1,
                     lanes=args.lanes if args.lanes else "auto", store_equals_host_scans=same, roofline=lc_roof,
                     host_scans={k: lc_host[k] for k in ("matches_per_s", "ms_per_batch", "h2d_bytes_per_batch")})
         details["loop_closure"] = {
+            "roofline": "score launches of the chain: patch (coarse, shared-memory tiles) + flat (fine, super-fine; L1-resident grid); "
+                        "one lane, profiled batch; 4 B x evaluations / summed score-kernel time",
             "workload": "BASELINE configs[3] shape: 1081-beam scan vs 480^2 grid rasterised from 8 base scans, coarse/fine/super chain (YAML values)",
             "scans": "resident in a device scan store, chains named by id (rsm_scan_match_interface_batch); host_scans: every base scan shipped "
                      "from pinned host memory per call (rsm_loop_closure_batch)",
@@ -793,11 +806,11 @@ def main():
                          "achieved": achieved, "peak": smem_row, "unit": "GB/s",
                          "frac": achieved / smem_row, "traffic": traffic,
                          "kernel_ms": k_ms, "select_ms": st_value["select_kernel_ms"] / score_launches,
-                         "peak_source": "rsm_microbench_gather mode 0 (shared-memory row segments), this run",
+                         "peak_source": "rsm_microbench_gather mode 0, this run",
                          "hbm_peak": hbm_peak, "hbm_achieved": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None},
             "exact_sort_passes": int(st_value["exact_sort_passes"]),
             "value_l2_flushed": {"value": evals_all / args.steps / (ms_flushed * 1e-3), "ms_per_step": ms_flushed,
-                                 "protocol": "round 1: 256 MB streamed through L2 before every step (10 steps)"},
+                                 "protocol": "256 MB streamed through L2 before every step, as in round 1"},
         }
         details["roofline_other_peaks_gbs"] = {"smem_random": smem_rand, "global_row_l1l2": glob_row, "global_random_l1l2": glob_rand,
                                                "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
@@ -812,7 +825,7 @@ def main():
             line["wide_window"] = wide
         if loop:
             line["loop_closure"] = loop
-        print(json.dumps(line), flush=True)
+        print(json.dumps(compact(line)), flush=True)
         try:
             dpath = args.details or os.path.join(os.getcwd(), "bench_details_n%d.json" % world)
             json.dump(dict(line, details=details), open(dpath, "w"), indent=1)

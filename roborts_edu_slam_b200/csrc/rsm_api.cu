@@ -481,6 +481,19 @@ int sync_stream(rsm_ctx* ctx, Lane* L = nullptr) {
 int wait_lane(rsm_ctx* ctx, Lane* L, bool blocking) {
   if (blocking && L->done) {
     CU(cudaEventRecord(L->done, L->stream));
+    // Poll and yield first: a blocking wait wakes ~50 us after the event (three times per chain and lane), a polling
+    // thread that yields between queries costs the other lanes and the worker pool next to nothing.  After 2 ms sleep.
+    static const bool yield_wait = [] { const char* e = std::getenv("RSM_WAIT"); return !(e && std::strcmp(e, "block") == 0); }();
+    if (yield_wait) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (;;) {
+        const cudaError_t q = cudaEventQuery(L->done);
+        if (q == cudaSuccess) { harvest_profile(ctx, L); return RSM_OK; }
+        if (q != cudaErrorNotReady) return fail(ctx, RSM_ERR_CUDA, "cudaEventQuery failed: %s", cudaGetErrorString(q));
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+        std::this_thread::yield();
+      }
+    }
     CU(cudaEventSynchronize(L->done));
     harvest_profile(ctx, L);
     return RSM_OK;
@@ -1593,8 +1606,9 @@ int chain_lanes(const rsm_ctx* ctx, int n) {
   if (lanes <= 0) {
     lanes = n >= 384 ? 4 : n >= 192 ? 3 : n >= 64 ? 2 : 1;
     // eight sub-batches of 64 hide more of the host stages between the passes than four of 128 lose in kernel
-    // efficiency (512 pairs on one B200: 2.91 -> 2.63 ms per step) -- where the host has a core per lane thread to spare
-    if (n >= 512 && HostPool::env_threads() >= 12) lanes = 8;
+    // efficiency (512 pairs on one B200: 2.91 -> 2.63 ms per step); with four host cores per rank (8 ranks on a 32-core
+    // box) six do best (3.56 -> 3.44 ms: the step is bound by the host there)
+    if (n >= 512) lanes = HostPool::env_threads() >= 6 ? 8 : 6;
   }
   return std::max(1, std::min({lanes, 8, n}));
 }

@@ -549,6 +549,7 @@ TileCfg pick_tile(int n_xy, bool affine_ok) {
 struct PassItem {
   const rsm_grid* grid = nullptr;
   const double* d_pts = nullptr;   // device points of this scan
+  const double* h_pts = nullptr;   // or host points: they travel in the pass's own upload block (no copy of their own)
   int P = 0;
   rsm_pass_param param;
   double* pose_world = nullptr;    // in/out
@@ -982,6 +983,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   size_t trig_doubles = 0;
   for (int a = 0; a < na; ++a) { items[act[a]].trig_off = trig_doubles; trig_doubles += size_t(items[act[a]].geo.n_ang) * 3; }
   const size_t o_trig = dl.take(trig_doubles * 8);
+  size_t hpts_doubles = 0;
+  for (int a = 0; a < na; ++a) if (items[act[a]].h_pts) hpts_doubles += size_t(items[act[a]].P) * 2;
+  const size_t o_hpts = dl.take(hpts_doubles * 8, 16);
   const size_t o_tmaps = dl.take(use_staged ? size_t(na) * 256 : 0, 128);
   const size_t o_splan = dl.take(use_stream ? splan->ctas.size() * sizeof(StreamCta) : 0, 16);
   const size_t up_bytes = dl.off;          // everything above is uploaded in one copy
@@ -1051,6 +1055,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   char* up = lane->h_up.p;
   double* h_trig = reinterpret_cast<double*>(up + o_trig);
   int cta = 0;
+  size_t hpts_used = 0;
   bool any_fixed = false, any_float = false;
   ctx->pool.run(na, 32, [&](int a0, int a1) {
     for (int a = a0; a < a1; ++a) {
@@ -1071,6 +1076,11 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     std::memset(&J, 0, sizeof J);
     J.grid = it.grid->d_cells;
     J.pts = it.d_pts;
+    if (it.h_pts) {       // host scan: behind the angle tables in the upload block
+      std::memcpy(up + o_hpts + hpts_used * 8, it.h_pts, size_t(it.P) * 16);
+      J.pts = reinterpret_cast<const double*>(dw + o_hpts) + hpts_used;
+      hpts_used += size_t(it.P) * 2;
+    }
     J.trig = reinterpret_cast<const double*>(dw + o_trig) + it.trig_off;
     J.score = reinterpret_cast<double*>(dw + o_score) + it.score_off;
     J.best_key = reinterpret_cast<unsigned long long*>(dw + o_best) + a;
@@ -2627,13 +2637,10 @@ int rsm_match(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int n_pt
   *response = 0.0;
   if (detail) std::memset(detail, 0, sizeof *detail);
   if (!grid->init || n_pts == 0) return RSM_OK;   // correlate_scan_matcher.h:792-795
-  double* d_pts = nullptr;
-  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
-  if (rc) return rc;
   std::vector<PassItem> items(1);
-  items[0].grid = grid; items[0].d_pts = d_pts; items[0].P = n_pts; items[0].param = *param;
+  items[0].grid = grid; items[0].h_pts = pts_xy; items[0].P = n_pts; items[0].param = *param;   // the scan rides in the pass's upload
   items[0].pose_world = pose_world; items[0].cov = cov;
-  rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+  int rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
   if (rc) return rc;
   *response = items[0].response;
   if (detail) *detail = items[0].detail;
@@ -2649,14 +2656,11 @@ int rsm_match_map(rsm_ctx* ctx, const rsm_grid* grid, const double* pts_xy, int 
   *response = 0.0;
   if (detail) std::memset(detail, 0, sizeof *detail);
   if (!grid->init || n_pts == 0) return RSM_OK;   // correlate_scan_matcher.h:792-795
-  double* d_pts = nullptr;
-  int rc = upload_points(ctx, pts_xy, size_t(n_pts), &d_pts);
-  if (rc) return rc;
   double unused_pose[3] = {0.0, 0.0, 0.0};
   std::vector<PassItem> items(1);
-  items[0].grid = grid; items[0].d_pts = d_pts; items[0].P = n_pts; items[0].param = *param;
+  items[0].grid = grid; items[0].h_pts = pts_xy; items[0].P = n_pts; items[0].param = *param;
   items[0].pose_world = unused_pose; items[0].cov = cov; items[0].center_map = center_map;
-  rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
+  int rc = run_pass(ctx, items, MODE_MATCH, nullptr, 0, nullptr);
   if (rc) return rc;
   *response = items[0].response;
   for (int i = 0; i < 3; ++i) best_map_out[i] = items[0].detail.best_pose_map[i];

@@ -985,7 +985,8 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   const size_t o_trig = dl.take(trig_doubles * 8);
   size_t hpts_doubles = 0;
   for (int a = 0; a < na; ++a) if (items[act[a]].h_pts) hpts_doubles += size_t(items[act[a]].P) * 2;
-  const size_t o_hpts = dl.take(hpts_doubles * 8, 16);
+  // (rounded up to 2 KB: the size of the upload is part of a pass graph's key, and scans of one sensor differ by a few points)
+  const size_t o_hpts = dl.take((hpts_doubles * 8 + 2047) / 2048 * 2048, 16);
   const size_t o_tmaps = dl.take(use_staged ? size_t(na) * 256 : 0, 128);
   const size_t o_splan = dl.take(use_stream ? splan->ctas.size() * sizeof(StreamCta) : 0, 16);
   const size_t up_bytes = dl.off;          // everything above is uploaded in one copy

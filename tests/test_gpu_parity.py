@@ -566,6 +566,37 @@ def test_stream_plan_of_the_staged_kernel(ctx, oracle, rng, monkeypatch, n_xy, b
     dg.close()
 
 
+@pytest.mark.parametrize("variant,ctas", [(0, 148), (0, 9), (2, 31), (1, 148)])
+def test_stream_plan_over_a_batch_of_jobs(ctx, oracle, rng, monkeypatch, variant, ctas):
+    """One persistent launch over SEVERAL jobs (rsm_match_batch): different grids, scans of different sizes, shares that
+    run across job boundaries (the CTA reloads the job, its tensor maps and its beam table mid-range)."""
+    monkeypatch.setenv("RSM_STAGED_PLAN", "stream")
+    monkeypatch.setenv("RSM_STREAM_VARIANT", str(variant))
+    monkeypatch.setenv("RSM_STREAM_CTAS", str(ctas))
+    n_xy = 65 if variant != 1 else 57
+    coarse = synth.pass_param((n_xy - 1) * 0.05, 0.05, 0.08, 0.02, 0.3, 100000, True, 0)       # 9 angles
+    sm = matcher.ScanMatchers(ctx, [coarse, coarse, coarse])
+    grids, dgs, scans, poses = [], [], [], []
+    for k, beams in enumerate((70, 333, 64, 1000, 129)):
+        g = synth.GridSpec(0.05, 0.15, 420 + 40 * k, 400, 3.0 + k, 2.0)
+        grid = synth.random_grid(rng, g.size_x, g.size_y)
+        dg = matcher.ScanMatchMap.from_spec(ctx, g)
+        dg.upload(grid)
+        ang = np.sort(rng.uniform(-np.pi, np.pi, beams))
+        rad = rng.uniform(1.0, 5.5, beams)
+        grids.append((g, grid)); dgs.append(dg)
+        scans.append(np.stack([np.cos(ang) * rad, np.sin(ang) * rad], axis=1))
+        poses.append(np.array([g.size_x * 0.05 / 2 - g.off_x + 0.011 * k, 400 * 0.05 / 2 - 2.0 - 0.007 * k, 0.2 + 0.1 * k]))
+    before = ctx.stats()["score_launches"]
+    scores, out_poses, covs, resp = sm.ScanMatchBatch(dgs, scans, np.array(poses), use_fine_scan_match=False)
+    assert ctx.stats()["score_launches"] - before == 1, "one pass, one launch for the whole batch"
+    for k, (g, grid) in enumerate(grids):
+        want = oracle.match(grid, g, scans[k], coarse, poses[k])
+        assert resp[k, 0] == want["response"] and np.array_equal(out_poses[k], want["pose"]) and cov_close(covs[k], want["cov"])
+    for dg in dgs:
+        dg.close()
+
+
 def test_stream_plan_is_the_default_for_full_waves(ctx, oracle, monkeypatch):
     """BASELINE configs[1] (181 items) takes the stream plan by default and equals the cluster plan bit for bit; a
     batch of different windows shares one persistent launch."""

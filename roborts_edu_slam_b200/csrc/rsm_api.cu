@@ -226,6 +226,11 @@ struct Lane {
   std::vector<Span> spans;
   size_t ev_used = 0;
   rsm_stats stats = {};                           // what this lane's passes counted since the last merge into the context's
+  // CUDA graphs of whole passes (upload, zeroing, score launches, select, read-back) enqueued on this lane, keyed by
+  // everything that shapes the launch sequence; the per-call data travels in the pinned buffer.  Per lane: lane threads
+  // capture and replay side by side.
+  struct PassGraph { int seen = 0; cudaGraphExec_t exec = nullptr; };
+  std::map<std::vector<long long>, PassGraph> graphs;
 };
 
 // stream plan of the staged scoring kernel (plan_stream below)
@@ -262,10 +267,6 @@ struct rsm_ctx {
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   int sm_count = 0;               // multiprocessors of the device (stream plan: persistent CTAs)
   std::map<std::vector<int>, std::shared_ptr<const StreamPlan>> stream_plans;   // by (beams, window, angles) per job: a front end repeats its shape
-  // CUDA graphs of whole passes (upload, zeroing, score launches, select, read-back), keyed by
-  // everything that shapes the launch sequence; the per-call data travels in the pinned buffer
-  struct PassGraph { int seen = 0; cudaGraphExec_t exec = nullptr; };
-  std::map<std::vector<long long>, PassGraph> graphs;
 };
 
 namespace {
@@ -422,6 +423,8 @@ int get_lane(rsm_ctx* ctx, int k, Lane** out) {
 }
 
 void destroy_lane(Lane& L) {
+  for (auto& g : L.graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  L.graphs.clear();
   if (L.d_work.p) cudaFree(L.d_work.p);
   if (L.d_aux.p) cudaFree(L.d_aux.p);
   if (L.h_up.p) cudaFreeHost(L.h_up.p);
@@ -1266,9 +1269,9 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   // A whole pass replayed as one CUDA graph once its shape has been seen twice: one launch call
   // instead of a copy, a memset, up to three kernels, two event pairs and a read-back.
   bool launched = false;
-  // (single matches only: that is where the launch sequence is a visible share of the call; a
-  //  batch enqueues its few long kernels well ahead of the GPU anyway)
-  if (!ctx->profiling && na <= 8 && lane == &ctx->L0 && std::getenv("RSM_NO_GRAPH") == nullptr) {
+  // (batches too: a sub-batch's pass is five or six driver calls, ~25 us of host time on the lane's critical path three
+  //  times per chain -- and host time is what bounds a rank with few cores)
+  if (!ctx->profiling && std::getenv("RSM_NO_GRAPH") == nullptr) {
     std::vector<long long> key = {(long long)(intptr_t)dw, (long long)(intptr_t)up, (long long)(intptr_t)dn, (long long)up_bytes,
                                   (long long)o_best, (long long)zero_end, use_flat * (1 + 8 * flat_k) + 2 * (use_patch ? patch_nxy : 0) + 64 * beam_split, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,
@@ -1279,11 +1282,11 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       const StagedLaunch& L = launches[l];
       key.insert(key.end(), {L.split, L.n_cta, L.beams, (long long)L.jobs_off, (long long)L.cta_off, L.n_jobs});
     }
-    if (ctx->graphs.size() > 64) {
-      for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
-      ctx->graphs.clear();
+    if (lane->graphs.size() > 64) {
+      for (auto& g : lane->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+      lane->graphs.clear();
     }
-    rsm_ctx::PassGraph& G = ctx->graphs[key];
+    Lane::PassGraph& G = lane->graphs[key];
     if (!G.exec && ++G.seen == 2 && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int r = enqueue_score();
       if (r == RSM_OK) r = enqueue_tail();
@@ -1853,7 +1856,6 @@ void rsm_destroy(rsm_ctx* ctx) {
   Buf* dev[] = {&ctx->d_pts, &ctx->d_flush, &ctx->d_pool_grids, &ctx->d_pool_grids2, &ctx->d_xchg};
   for (Buf* b : dev) if (b->p) cudaFree(b->p);
   if (ctx->h_xchg.p) cudaFreeHost(ctx->h_xchg.p);
-  for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
   destroy_lane(ctx->L0);
   delete ctx;

@@ -631,7 +631,7 @@ struct PassRun {
   bool pending = false, blocking = false;
   double* scores_out = nullptr;
   size_t o_best = 0, o_err = 0, o_poolcnt = 0, o_fcnt = 0, o_ftop = 0, o_speccols = 0, o_spec = 0, o_pool = 0,
-         o_gjobs = 0, o_gout = 0, o_score = 0;
+         o_gjobs = 0, o_gout = 0, o_score = 0, o_trig = 0;
   size_t head_bytes = 0, gather_doubles = 0;
   int pool_first = 0, pool_cap = 0;
 };
@@ -1316,6 +1316,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   static const int spin_env = [] { const char* e = std::getenv("RSM_SPIN_WAIT"); return e ? std::atoi(e) : -1; }();
   const bool spare_cores = HostPool::env_threads() >= 2 * std::max(1, int(ctx->extra_lanes.size()) + 1);
   R.blocking = na > 8 && (spin_env < 0 ? !spare_cores : spin_env == 0);
+  R.o_trig = o_trig;
   R.o_best = o_best; R.o_err = o_err; R.o_poolcnt = o_poolcnt; R.o_fcnt = o_fcnt; R.o_ftop = o_ftop;
   R.o_speccols = o_speccols; R.o_spec = o_spec; R.o_pool = o_pool; R.o_gjobs = o_gjobs; R.o_gout = o_gout; R.o_score = o_score;
   R.head_bytes = head_bytes; R.gather_doubles = gather_doubles; R.pool_first = pool_first; R.pool_cap = pool_cap;
@@ -1433,7 +1434,8 @@ int pass_end(rsm_ctx* ctx, PassRun& R) {
       const double top_score = key_to_score(h_best[a]);
       std::sort(it.a_list.begin(), it.a_list.end(), by_score_desc);
       if (it.a_list.empty() || it.a_list[0].score != top_score || adjacent_tie(it.a_list, it.a_list.size())) { it.exact = true; continue; }
-      it.best = find_best(g, it.a_list.data(), it.a_list.size());
+      // (the angle table of this pass is still in the lane's upload buffer: cos / sin of every search angle)
+      it.best = find_best(g, it.a_list.data(), it.a_list.size(), reinterpret_cast<const double*>(lane->h_up.p + R.o_trig) + it.trig_off);
       if (size_t(it.best.n_avg) != it.a_list.size()) { it.exact = true; continue; }   // cannot happen; be safe
       const int64_t base = int64_t(it.a0) * g.n_xy * g.n_xy;
       // the job's top-kTopK as merged on the device (descending); their VALUES are unique whatever

@@ -131,7 +131,9 @@ inline bool by_score_desc(const Cand& a, const Cand& b) { return a.score > b.sco
 
 // FindBestCandidate (:670-710).  `a` = the candidates with DoubleEqual(score, top, 1e-2), sorted
 // by descending score in the reference's order; a[0] is the top candidate.
-inline BestPose find_best(const PassGeo& g, const Cand* a, size_t n) {
+// trig (optional): the pass's angle table, cos / sin / angle per search-angle index -- the values std::cos / std::sin give for
+// angle_of(ia) (angle_trig), so that an averaging set of dozens of candidates costs no libm call.
+inline BestPose find_best(const PassGeo& g, const Cand* a, size_t n, const double* trig = nullptr) {
   BestPose b;
   int ia, ix, iy;
   g.decode(a[0].index, &ia, &ix, &iy);
@@ -145,8 +147,8 @@ inline BestPose find_best(const PassGeo& g, const Cand* a, size_t n) {
     const double s = a[i].score, ang = g.angle_of(ia);
     ax += g.x_of(ix) * s;
     ay += g.y_of(iy) * s;
-    tx += std::cos(ang) * s;
-    ty += std::sin(ang) * s;
+    tx += (trig ? trig[3 * ia] : std::cos(ang)) * s;
+    ty += (trig ? trig[3 * ia + 1] : std::sin(ang)) * s;
     ssum += s;
     ++count;
   }

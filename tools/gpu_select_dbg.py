@@ -7,7 +7,7 @@ ctx = matcher.Context(0)
 m = matcher.BasedCorrelationScanMatch(ctx)
 lib = ctypes.CDLL(matcher.LIB_PATH)
 out = (ctypes.c_ulonglong * 16)()
-for name, sc in (("cfg2", synth.config2()), ("cfg5/4", synth.config5(scale=0.25))):
+for name, sc in (("cfg1", synth.config1()), ("cfg2", synth.config2()), ("cfg5/4", synth.config5(scale=0.25))):
     g = sc.grid
     grid = matcher.ScanMatchMap.from_spec(ctx, g)
     grid.InitMapWithRangeVec(sc.base_pts, sc.base_poses, g.default_prob, g.sigma, g.occu_offset, g.use_blur)

@@ -440,7 +440,7 @@ def main():
         def call_host():
             return matcher.loop_closure_batch(ctx, packed, lc_passes)
 
-        def lc_measure(call, reps=5):
+        def lc_measure(call, reps=20):
             for _ in range(2):
                 call()
             barrier()

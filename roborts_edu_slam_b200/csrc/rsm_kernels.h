@@ -47,7 +47,7 @@ void score_stream_tile(int variant, int* tile_x, int* tile_y);
 void score_stream_boxes(int variant, int box_w[2], int box_h[2]);
 int score_stream_weight(int variant, int ext_x, int ext_y);
 size_t score_stream_partial_words(int variant);   // 64-bit words per partial slot
-size_t score_stream_smem(int max_beams);
+size_t score_stream_smem(int variant, int max_beams);
 cudaError_t launch_score_stream(int variant, int n_cta, int max_beams, cudaStream_t st, const ScoreJob* jobs, const int* item_begin,
                                 int n_jobs, const StreamCta* plan, unsigned long long* partials, int* tickets);
 cudaError_t launch_select(int n_cta, cudaStream_t st, const SelectJob* jobs, const int* cta_begin,

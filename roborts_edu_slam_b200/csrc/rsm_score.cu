@@ -1370,6 +1370,7 @@ template <int RX, int RY>
 struct MapLanes {
   static constexpr int kWarps = 16, kRows = RY, kTileX = 32 * RX, kTileY = kWarps * RY, kNC = RX * RY;
   static constexpr int kW0 = 160, kH0 = 128, kW1 = 128, kH1 = 160;
+  static constexpr int kBuffers = 2, kCells = kBufCells;          // two 80 KB boxes in flight
   __device__ static __forceinline__ bool slot(int c, int lane, int& dx, int& dy) {
     dx = lane + 32 * (c % RX); dy = c / RX;
     return true;
@@ -1416,7 +1417,11 @@ struct MapLanes {
 
 struct MapPaired {
   static constexpr int kWarps = 12, kRows = 8, kTileX = 81, kTileY = kWarps * 8, kNC = 21;
-  static constexpr int kW0 = 164, kH0 = 124, kW1 = 132, kH1 = 155;     // pitches = 4 (mod 32)
+  static constexpr int kW0 = 132, kH0 = 124, kW1 = 100, kH1 = 163;     // pitches = 4 (mod 32)
+  // THREE 64 KB boxes in flight: a box lands through the same shared-memory port the gathers saturate, so with two
+  // buffers it arrived ~540 cycles after the warps wanted it (8 % of a round); a third gives it two rounds to trickle in.
+  // Same fill per beam as two 80 KB boxes (simulated on the config-2 / config-5 scans: 27.0 / 28.4 wavefronts per beam).
+  static constexpr int kBuffers = 3, kCells = 16384;
   __device__ static __forceinline__ bool slot(int c, int lane, int& dx, int& dy) {
     if (c < 16) { dx = lane + 32 * (c & 1); dy = c >> 1; return true; }
     if (c < 20) { dx = 64 + (lane & 15); dy = (c - 16) + 4 * (lane >> 4); return true; }
@@ -1491,7 +1496,8 @@ score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ i
                     const StreamCta* __restrict__ plan, unsigned long long* __restrict__ partials, int* __restrict__ tickets) {
   constexpr int kW = Map::kWarps, kT = (kW + 1) * 32, kCT = kW * 32, NC = Map::kNC, RY = Map::kRows;
   constexpr int TILE_X = Map::kTileX, TILE_Y = Map::kTileY;
-  static_assert(Map::kW0 * Map::kH0 <= kBufCells && Map::kW1 * Map::kH1 <= kBufCells, "box larger than its buffer");
+  constexpr int NB = Map::kBuffers, kCells = Map::kCells;
+  static_assert(Map::kW0 * Map::kH0 <= kCells && Map::kW1 * Map::kH1 <= kCells, "box larger than its buffer");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = warp == kW;
 
@@ -1499,20 +1505,18 @@ score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ i
   __shared__ int s_job, s_ticket;
   __shared__ unsigned long long s_wmax[kW];
   __shared__ double sX[TILE_X], sY[TILE_Y], sDX2[TILE_X], sDY2[TILE_Y];
-  __shared__ __align__(16) int sBase[2][kRound];
-  __shared__ int sMeta[2][4];
-  __shared__ __align__(8) uint64_t sFull[2], sEmpty[2];
+  __shared__ __align__(16) int sBase[NB][kRound];
+  __shared__ int sMeta[NB][4];
+  __shared__ __align__(8) uint64_t sFull[NB], sEmpty[NB];
   __shared__ int sUnsafeCount;
   __shared__ int sUnsafe[64];
   extern __shared__ __align__(128) unsigned char dyn[];
-  int* buf0 = reinterpret_cast<int*>(dyn);
-  int* buf1 = buf0 + kBufCells;
-  int2* sBeam = reinterpret_cast<int2*>(buf1 + kBufCells + 128);   // (+ 512 bytes: lanes beyond the window read past a box)
+  int* bufs = reinterpret_cast<int*>(dyn);                         // NB box buffers of kCells cells
+  int2* sBeam = reinterpret_cast<int2*>(bufs + NB * kCells + 128);   // (+ 512 bytes: lanes beyond the window read past a box)
 
   const StreamCta P = plan[blockIdx.x];
   if (tid == 0) {
-    mbar_init(&sFull[0], 1); mbar_init(&sFull[1], 1);
-    mbar_init(&sEmpty[0], kW); mbar_init(&sEmpty[1], kW);
+    for (int b = 0; b < NB; ++b) { mbar_init(&sFull[b], 1); mbar_init(&sEmpty[b], kW); }
   }
   int r = 0;                       // rounds of this CTA so far: the pipeline runs on across items
 
@@ -1589,7 +1593,7 @@ score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ i
       __syncwarp();
       int b = 0;
       for (; b < nv; ++r) {
-        const int which = r & 1;
+        const int which = r % NB, lap = r / NB;
         const long long p0 = DBG_T(); (void)p0;
         const int j = b + lane;
         int2 e = make_int2(-1, -1);
@@ -1618,7 +1622,7 @@ score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ i
         int rxl = __shfl_sync(0xffffffffu, xl, srcl), ryl = __shfl_sync(0xffffffffu, ymin, srcl);
         if (!rany) { rxl = 0; ryl = 0; }
         const long long p1 = DBG_T(); (void)p1;
-        if (r >= 2) mbar_wait(&sEmpty[which], (uint32_t)(((r >> 1) - 1) & 1), 100);
+        if (r >= NB) mbar_wait(&sEmpty[which], (uint32_t)((lap - 1) & 1), 100);
         const long long p2 = DBG_T(); (void)p2;
         if (lane < n) sBase[which][lane] = safe ? (e.y - ryl) * rw + (e.x - rxl) : -1;
         const unsigned int unsafe = __ballot_sync(0xffffffffu, lane < n && !safe);
@@ -1627,7 +1631,7 @@ score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ i
         __syncwarp();
         if (lane == 0) {
           mbar_expect_tx(&sFull[which], (uint32_t)((tall ? Map::kW1 * Map::kH1 : Map::kW0 * Map::kH0) * 4));
-          tma_box(which ? buf1 : buf0, tmaps + (tall ? 128 : 0), rxl, ryl, &sFull[which]);
+          tma_box(bufs + which * kCells, tmaps + (tall ? 128 : 0), rxl, ryl, &sFull[which]);
         }
         b += n;
 #ifdef RSM_STAGED_DEBUG
@@ -1637,12 +1641,12 @@ score_stream_kernel(const ScoreJob* __restrict__ jobs, const int* __restrict__ i
     } else {
       int pend = 0;                // beams added since the sums were last folded into the overflow counters
       for (;; ++r) {
-        const int which = r & 1;
+        const int which = r % NB;
         const long long c0 = DBG_T(); (void)c0;
-        mbar_wait(&sFull[which], (uint32_t)((r >> 1) & 1), 40);
+        mbar_wait(&sFull[which], (uint32_t)((r / NB) & 1), 40);
         const long long c1 = DBG_T(); (void)c1;
         const int n = sMeta[which][0], tall = sMeta[which][1], last = sMeta[which][2], all_safe = sMeta[which][3];
-        const int* buf = which ? buf1 : buf0;
+        const int* buf = bufs + which * kCells;
         const int* bases = sBase[which];
         // a beam adds at most 2^25 per sum: after a flush (sums < 2^31) 64 beams fit before the next one is due
         if (pend + n > 64) {
@@ -1909,7 +1913,10 @@ size_t score_stream_partial_words(int variant) {
        : variant == 1 ? size_t(8) * 16 * 32 : size_t(18) * 16 * 32;
 }
 
-size_t score_stream_smem(int max_beams) { return size_t(2 * staged::kBufCells) * 4 + 512 + size_t(max_beams) * 8; }
+size_t score_stream_smem(int variant, int max_beams) {
+  const size_t boxes = variant == 0 ? size_t(staged::MapPaired::kBuffers) * staged::MapPaired::kCells : size_t(2) * staged::kBufCells;
+  return boxes * 4 + 512 + size_t(max_beams) * 8;
+}
 
 typedef void (*StreamFn)(const ScoreJob*, const int*, int, const StreamCta*, unsigned long long*, int*);
 static StreamFn stream_fn(int variant) {
@@ -1921,7 +1928,7 @@ cudaError_t launch_score_stream(int variant, int n_cta, int max_beams, cudaStrea
                                 int n_jobs, const StreamCta* plan, unsigned long long* partials, int* tickets) {
   static size_t configured[kMaxDevices][3] = {{0, 0, 0}};
   if (variant < 0 || variant > 2) return cudaErrorInvalidValue;
-  const size_t smem = score_stream_smem(max_beams);
+  const size_t smem = score_stream_smem(variant, max_beams);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;

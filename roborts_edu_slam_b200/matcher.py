@@ -224,7 +224,11 @@ class CorrelationScanMatchParam:
         v = self.__dict__.get("_v", {})
         if name.startswith("set_") and name[4:] in v:
             key = name[4:]
-            return lambda value: v.__setitem__(key, value)
+
+            def setter(value, v=v, key=key, d=self.__dict__):
+                v[key] = value
+                d.pop("_struct", None)          # the cached rsm_pass_param is stale
+            return setter
         if name in v:
             return lambda: v[name]
         raise AttributeError(name)
@@ -235,14 +239,35 @@ class CorrelationScanMatchParam:
         return cls(p[0], p[1], p[2], p[3], p[4], int(p[5]), 0, bool(p[6]), int(p[7]))
 
     def struct(self):
+        cached = self.__dict__.get("_struct")
+        if cached is not None:
+            return cached
         v = self._v
-        return PassParamStruct(v["search_space_size"], v["search_space_resolution"], v["search_angle_offset"],
+        self.__dict__["_struct"] = st = PassParamStruct(v["search_space_size"], v["search_space_resolution"], v["search_angle_offset"],
                                v["search_angle_resolution"], v["response_threshold"], int(v["use_point_size"]),
                                1 if v["use_center_penalty"] else 0, int(v["correlation_scan_match_type"]), 0)
+        return st
 
 
 def _as_param(p):
     return p if isinstance(p, CorrelationScanMatchParam) else CorrelationScanMatchParam.from_array(p)
+
+
+_STRUCTS = {}
+
+
+def _param_struct(p):
+    """rsm_pass_param of a parameter object or of the 8-double block of synth.pass_param; the conversion is cached (a
+    front end passes the same three parameter sets for every scan, and building the ctypes struct costs 4 us)."""
+    if isinstance(p, CorrelationScanMatchParam):
+        return p.struct()
+    key = np.asarray(p, dtype=np.float64).tobytes()
+    st = _STRUCTS.get(key)
+    if st is None:
+        if len(_STRUCTS) > 256:
+            _STRUCTS.clear()
+        st = _STRUCTS[key] = CorrelationScanMatchParam.from_array(p).struct()
+    return st
 
 
 class Context:
@@ -545,6 +570,9 @@ class PubMap(ScanMatchMap):
         return prob, cnt, hit, occ
 
 
+_D3, _D9 = ctypes.c_double * 3, ctypes.c_double * 9
+
+
 class BasedCorrelationScanMatch:
     """One pass: ScanMatch(map, range_data, param, current_pose, cov_matrix) -> response.
 
@@ -558,19 +586,18 @@ class BasedCorrelationScanMatch:
     def ScanMatch(self, map_, range_data, scan_match_param, current_pose, cov_matrix):
         ctx = self.ctx
         assert current_pose.dtype == np.float64 and cov_matrix.dtype == np.float64
-        assert current_pose.flags.c_contiguous and cov_matrix.flags.c_contiguous
-        ps = _as_param(scan_match_param).struct()
+        assert current_pose.flags.c_contiguous and cov_matrix.flags.c_contiguous and current_pose.size == 3 and cov_matrix.size == 9
+        ps = _param_struct(scan_match_param)
         resp = c_d(0)
         det = PassDetail()
+        pose_p, cov_p = _D3.from_buffer(current_pose), _D9.from_buffer(cov_matrix)     # (cheaper than ndarray.ctypes.data)
         if isinstance(range_data, RangeDataContainer2d):
-            ctx.check(ctx.lib.rsm_match_resident(ctx.h, map_.h, range_data.h, ctypes.byref(ps),
-                                                 current_pose.ctypes.data, cov_matrix.ctypes.data,
+            ctx.check(ctx.lib.rsm_match_resident(ctx.h, map_.h, range_data.h, ctypes.byref(ps), pose_p, cov_p,
                                                  ctypes.byref(resp), ctypes.byref(det)))
         else:
             pts = _f64(range_data).reshape(-1, 2)
-            ctx.check(ctx.lib.rsm_match(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps),
-                                        current_pose.ctypes.data, cov_matrix.ctypes.data, ctypes.byref(resp),
-                                        ctypes.byref(det)))
+            ctx.check(ctx.lib.rsm_match(ctx.h, map_.h, pts.ctypes.data, len(pts), ctypes.byref(ps), pose_p, cov_p,
+                                        ctypes.byref(resp), ctypes.byref(det)))
         self.last_detail = det
         return resp.value
 

@@ -17,6 +17,7 @@
 #include <cuda.h>           // CUtensorMap types only; the encoder is fetched through the runtime
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>        // environ
 
 #include <algorithm>
 #include <map>
@@ -671,6 +672,24 @@ bool same_plan(const PassItem& a, const PassItem& b) {
   return a.geo.n_xy == b.geo.n_xy && a.geo.factor == b.geo.factor && a.grid->fixed == b.grid->fixed;
 }
 
+// The RSM_* environment switches as they are right now, from ONE pass over environ: a pass consults a dozen of them, and a
+// getenv each is a few microseconds of a 14 us launch path.  (Read per pass, not cached: tests flip them at run time.)
+struct EnvRsm {
+  const char* entry[16];
+  int n = 0;
+  EnvRsm() {
+    for (char** e = ::environ; e && *e; ++e)
+      if ((*e)[0] == 'R' && (*e)[1] == 'S' && (*e)[2] == 'M' && (*e)[3] == '_' && n < 16) entry[n++] = *e + 4;
+  }
+  // value of RSM_<name> or nullptr
+  const char* get(const char* name) const {
+    const size_t len = std::strlen(name);
+    for (int i = 0; i < n; ++i)
+      if (std::strncmp(entry[i], name, len) == 0 && entry[i][len] == '=') return entry[i] + len + 1;
+    return nullptr;
+  }
+};
+
 // ---- stream plan of the staged scoring kernel (rsm_score.cu: score_stream_kernel) ----------------------
 // The (job, angle, tile) items of a launch laid end to end; an item costs, in beams of a full tile: its beams x the
 // tile's share of a full tile's shared-memory loads + 19 fixed (job fetch, beam table, pipeline fill) + 55 x that share
@@ -779,6 +798,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
                double* scores_out, int64_t scores_cap, int64_t* scores_written, PassRun& R) {
   rsm_stats& ST = lane->stats;
   PhaseTimer pt(&ST);
+  const EnvRsm env;      // the debugging switches, read once per pass
   R = PassRun();
   R.lane = lane; R.items = &items; R.act = act_in; R.mode = mode; R.scores_out = scores_out;
   const std::vector<int>& act = R.act;
@@ -808,7 +828,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   // translations per axis at unit step on fixed-point grids.  Measured on B200 against the L1 path:
   // 0.224 vs 0.265 ms on config 2, 11.3 vs 13.6 ms on the wide window.  RSM_NO_STAGED=1 turns it off.
   bool use_staged = affine_ok && items[act[0]].geo.factor == 1.0 && items[act[0]].geo.n_xy >= 48 &&
-                    std::getenv("RSM_NO_STAGED") == nullptr;
+                    env.get("NO_STAGED") == nullptr;
   int max_V = 0;
   for (int a = 0; a < na && use_staged; ++a) {
     const PassItem& it = items[act[a]];
@@ -850,7 +870,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       resident[sp] = score_staged_resident_ctas(staged_variant, sp, max_V);
       unit[sp] = double(max_V) / sp + 19.0 + 55.0 / sp + (sp > 1 ? 10.0 : 0.0);
     }
-    const bool two_phase_ok = std::getenv("RSM_ONE_PHASE") == nullptr;
+    const bool two_phase_ok = env.get("ONE_PHASE") == nullptr;
     double best_cost = 0.0;
     for (int sa = 1; sa <= s_max; ++sa) {
       if (resident[sa] <= 0) continue;
@@ -868,18 +888,18 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
         if (two < best_cost) { best_cost = two; n_split = sa; split_b = sb; items_a = in_a; }
       }
     }
-    if (std::getenv("RSM_DEBUG_SPLIT"))
+    if (env.get("DEBUG_SPLIT"))
       std::fprintf(stderr, "[rsm] staged plan: %lld items, split %d for the first %lld, split %d for the rest, cost %.0f\n",
                    work_items, n_split, items_a, split_b, best_cost);
     // Stream plan (persistent CTAs over one sequence of beams) from half a wave of items on: no wave quantisation
     // and the paired-row mapping for 65+ columns.  Below that the cluster plan splits the epilogue too.
     // RSM_STAGED_PLAN=cluster|stream forces one; RSM_STREAM_CTAS / RSM_STREAM_VARIANT override the shape (tests).
     if (ctx->sm_count <= 0) cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
-    const char* plan_env = std::getenv("RSM_STAGED_PLAN");
+    const char* plan_env = env.get("STAGED_PLAN");
     use_stream = plan_env ? std::strcmp(plan_env, "stream") == 0 : 2 * work_items >= ctx->sm_count;
     if (use_stream) {
       stream_variant = score_stream_variant(max_nxy);
-      if (const char* e = std::getenv("RSM_STREAM_VARIANT")) stream_variant = std::max(0, std::min(2, std::atoi(e)));
+      if (const char* e = env.get("STREAM_VARIANT")) stream_variant = std::max(0, std::min(2, std::atoi(e)));
       score_stream_tile(stream_variant, &tx, &ty);
       cfg.lx = tx; cfg.rows = ty;
       std::vector<StreamRun> runs(na);
@@ -888,7 +908,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
         runs[a] = {it.geo.visited, it.geo.n_xy, it.a1 - it.a0, (it.geo.n_xy + tx - 1) / tx, (it.geo.n_xy + ty - 1) / ty};
       }
       int max_ctas = std::max(1, ctx->sm_count);
-      if (const char* e = std::getenv("RSM_STREAM_CTAS")) max_ctas = std::max(1, std::atoi(e));
+      if (const char* e = env.get("STREAM_CTAS")) max_ctas = std::max(1, std::atoi(e));
       {
         std::vector<int> key = {stream_variant, max_ctas};
         for (const StreamRun& r : runs) key.insert(key.end(), {r.V, r.n_xy, r.ang_count});
@@ -910,13 +930,13 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
         splan = hit.get();
       }
       if (splan->n_items > INT_MAX / 2) use_stream = false;
-      if (std::getenv("RSM_DEBUG_SPLIT"))
+      if (env.get("DEBUG_SPLIT"))
         std::fprintf(stderr, "[rsm] stream plan: variant %d, %lld items over %zu CTAs, %d shared (%d partial slots)\n", stream_variant,
                      splan->n_items, splan->ctas.size(), splan->n_tickets, splan->n_slots);
     }
   }
   // flat variant: small windows whose step is not an integer number of cells (fine / super-fine passes)
-  bool use_flat = !use_staged && !cfg.affine && std::getenv("RSM_NO_FLAT") == nullptr;
+  bool use_flat = !use_staged && !cfg.affine && env.get("NO_FLAT") == nullptr;
   int flat_k = 1;                                  // candidates per thread of the flat kernel
   for (int a = 0; a < na && use_flat; ++a) {
     const PassGeo& g = items[act[a]].geo;
@@ -930,7 +950,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   // Its CTAs are 8 angles x the whole window x every beam, four resident per SM: below one full wave of them
   // (592) the tiled kernel's many small CTAs balance better (measured: 64-pair sub-batches lose 4 %, 256-pair
   // batches gain 18 % of the coarse pass).  RSM_NO_PATCH=1 / RSM_FORCE_PATCH=1 override.
-  bool use_patch = !use_staged && !use_flat && cfg.affine && items[act[0]].geo.factor == 1.0 && std::getenv("RSM_NO_PATCH") == nullptr;
+  bool use_patch = !use_staged && !use_flat && cfg.affine && items[act[0]].geo.factor == 1.0 && env.get("NO_PATCH") == nullptr;
   int patch_nxy = 0, patch_ctas = 0;
   for (int a = 0; a < na && use_patch; ++a) {
     const PassItem& it = items[act[a]];
@@ -938,7 +958,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
     patch_nxy = std::max(patch_nxy, it.geo.n_xy);
     patch_ctas += (it.a1 - it.a0 + score_patch_angles() - 1) / score_patch_angles();
   }
-  if (use_patch && patch_ctas < 256 && std::getenv("RSM_FORCE_PATCH") == nullptr) use_patch = false;
+  if (use_patch && patch_ctas < 256 && env.get("FORCE_PATCH") == nullptr) use_patch = false;
   // immediate-offset variant: unit search step and the same padded pitch for every job
   int const_pitch = 0;
   if (!use_staged && !use_patch && cfg.affine && items[act[0]].geo.factor == 1.0 && cfg.lx >= 16) {
@@ -952,7 +972,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   // to arrive finishes.  A single front-end match is 1 .. 81 CTAs that would each walk ~1000 beams alone; the
   // super-fine pass of a 512-pair batch is 512 CTAs, less than one wave.
   int beam_split = 1;
-  if (!use_staged && !use_patch && std::getenv("RSM_NO_BEAM_SPLIT") == nullptr) {
+  if (!use_staged && !use_patch && env.get("NO_BEAM_SPLIT") == nullptr) {
     bool all_fixed = true;
     long long base_ctas = 0, cands = 0;
     int min_chunks = 1 << 30;
@@ -966,7 +986,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       min_chunks = std::min(min_chunks, (g.visited + 31) / 32);
     }
     long long target = 6 * 148;     // CTAs wanted: these are 128 .. 256-thread CTAs, several resident per SM
-    if (const char* e = std::getenv("RSM_SPLIT_TARGET")) target = std::max(1, std::atoi(e));
+    if (const char* e = env.get("SPLIT_TARGET")) target = std::max(1, std::atoi(e));
     if (all_fixed && base_ctas > 0 && cands <= (1 << 20)) {
       if (2 * base_ctas <= target)
         beam_split = int(std::max<long long>(1, std::min<long long>({(long long)min_chunks, 32, (target + base_ctas - 1) / base_ctas})));
@@ -1196,7 +1216,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   char* dn = lane->h_down.p;
   const size_t head_bytes = o_pool - o_best;
   const int pool_first = std::min(pool_cap, std::max(4096, na * 8));
-  const bool fork = use_staged && !use_stream && n_launches == 2 && std::getenv("RSM_NO_FORK") == nullptr;
+  const bool fork = use_staged && !use_stream && n_launches == 2 && env.get("NO_FORK") == nullptr;
   auto enqueue_score = [&]() -> int {
     CU(cudaMemcpyAsync(dw, up, up_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(dw + (zero_wide ? zero_begin : o_best), 0, zero_end - (zero_wide ? zero_begin : o_best), st));
@@ -1271,7 +1291,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
   bool launched = false;
   // (batches too: a sub-batch's pass is five or six driver calls, ~25 us of host time on the lane's critical path three
   //  times per chain -- and host time is what bounds a rank with few cores)
-  if (!ctx->profiling && std::getenv("RSM_NO_GRAPH") == nullptr) {
+  if (!ctx->profiling && env.get("NO_GRAPH") == nullptr) {
     std::vector<long long> key = {(long long)(intptr_t)dw, (long long)(intptr_t)up, (long long)(intptr_t)dn, (long long)up_bytes,
                                   (long long)o_best, (long long)zero_end, use_flat * (1 + 8 * flat_k) + 2 * (use_patch ? patch_nxy : 0) + 64 * beam_split, use_staged, any_fixed, cfg.affine, cfg.lx, cfg.ry,
                                   const_pitch, staged_variant, cta, na, (long long)o_sjobs, (long long)o_scta, n_launches, fork,

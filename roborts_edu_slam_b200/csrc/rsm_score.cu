@@ -24,6 +24,14 @@
 //                     ~4e-6 of (beam, slot) pairs that fail the test (or touch the grid border)
 //                     recompute their indices exactly per thread.  No per-candidate FP64 at all.
 //
+// Kernels in this file, by the windows they take (rsm_api.cu, pass_begin, picks):
+//   score_stream_kernel<Map>   >= 48 translations per axis, unit step, fixed point, from half a wave of (angle, tile) items on:
+//                              persistent CTAs over one beam sequence, TMA boxes in shared memory (the headline kernel)
+//   score_staged_kernel<RX,RY> the same windows in small launches: thread-block clusters share an item's beams
+//   score_patch_kernel<NR>     batches of unit-step windows of <= 16 translations (the coarse pass of a back-end chain)
+//   score_flat_kernel<F,K>     3 .. 12 translations at a non-integer step (fine / super-fine passes)
+//   score_kernel<...>          everything else (the tiled L1 kernel described above)
+//
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 #include <cuda_runtime.h>
 #include <stdint.h>

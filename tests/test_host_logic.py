@@ -297,3 +297,49 @@ def test_stream_plan_covers_every_beam_once(runs, variant, max_ctas):
         if n_xy <= tile[0]:
             w = [sum((b1 if it == i1 else v) - (b0 if it == i0 else 0) for it in range(i0, i1 + 1)) for i0, b0, i1, b1 in shares[:, :4]]
             assert max(w) <= 1.15 * np.mean(w) and min(w) >= 0.85 * np.mean(w)
+
+
+def _check_plan(runs, variant, max_ctas):
+    shares, n_items, n_tickets, n_slots = matcher.stream_plan(runs, variant, max_ctas)
+    tile = {0: (81, 96), 1: (64, 64), 2: (96, 96)}[variant]
+    beams = []
+    for v, n_xy, n_ang in runs:
+        beams += [v] * (n_ang * (-(-n_xy // tile[0])) * (-(-n_xy // tile[1])))
+    assert n_items == len(beams) and 1 <= len(shares) <= max_ctas
+    covered = np.zeros(len(beams), dtype=np.int64)
+    parts = {}
+    prev_end = (0, 0)
+    for s in shares:
+        i0, b0, i1, b1, t0, s0, p0, n0, t1, s1, p1, n1 = [int(v) for v in s]
+        assert (i0, b0) == prev_end and i0 <= i1 and (i0 < i1 or b0 < b1)
+        for it in (range(i0, i1 + 1) if i1 - i0 < 3 else [i0, i1]):
+            lo, hi = (b0 if it == i0 else 0), (b1 if it == i1 else beams[it])
+            assert 0 <= lo < hi <= beams[it]
+            covered[it] += hi - lo
+            whole = lo == 0 and hi == beams[it]
+            t, sl, pa, n = (t0, s0, p0, n0) if it == i0 else (t1, s1, p1, n1) if it == i1 else (-1, 0, 0, 0)
+            assert (t < 0) == whole
+            if t >= 0:
+                parts.setdefault(t, []).append((sl, pa, n))
+        if i1 - i0 >= 3:
+            covered[i0 + 1:i1] += np.array(beams[i0 + 1:i1])
+        prev_end = (i1 + 1, 0) if b1 == beams[i1] else (i1, b1)
+    assert prev_end == (n_items, 0) and np.array_equal(covered, np.array(beams))
+    assert sorted(parts) == list(range(n_tickets))
+    slots = []
+    for t, us in parts.items():
+        assert len({u[0] for u in us}) == 1 and len(us) == us[0][2] >= 2 and sorted(u[1] for u in us) == list(range(len(us)))
+        slots += list(range(us[0][0], us[0][0] + len(us)))
+    assert sorted(slots) == list(range(n_slots))
+
+
+def test_stream_plan_random_launch_shapes():
+    """Seeded sweep over launch shapes (jobs of different beam counts, windows, angle counts; few and many CTAs): the
+    invariants of test_stream_plan_covers_every_beam_once on 300 random plans."""
+    rng = np.random.default_rng(20261019)
+    for _ in range(300):
+        variant = int(rng.integers(0, 3))
+        n_jobs = int(rng.integers(1, 6))
+        n_xy0 = int(rng.integers(48, 200))
+        runs = [(int(rng.integers(2, 2049)), n_xy0, int(rng.integers(1, 40))) for _ in range(n_jobs)]
+        _check_plan(runs, variant, int(rng.integers(1, 300)))

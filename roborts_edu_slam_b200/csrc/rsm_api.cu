@@ -1307,6 +1307,10 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       lane->graphs.clear();
     }
     Lane::PassGraph& G = lane->graphs[key];
+    // (one capture at a time in the process: lanes see a new shape together, and nothing is gained by capturing side by side)
+    static std::mutex capture_mu;
+    std::unique_lock<std::mutex> capture_lock(capture_mu, std::defer_lock);
+    if (!G.exec && G.seen + 1 == 2) capture_lock.lock();
     if (!G.exec && ++G.seen == 2 && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int r = enqueue_score();
       if (r == RSM_OK) r = enqueue_tail();
@@ -1318,6 +1322,7 @@ int pass_begin(rsm_ctx* ctx, Lane* lane, std::vector<PassItem>& items, const std
       }
       if (graph) cudaGraphDestroy(graph);
     }
+    if (capture_lock.owns_lock()) capture_lock.unlock();
     if (G.exec) {
       CU(cudaGraphLaunch(G.exec, st));
       launched = true;
